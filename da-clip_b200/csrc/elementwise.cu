@@ -1,0 +1,444 @@
+// HBM-bound kernels of the path: SDE / posterior / ODE state update, stem input packing, row LayerNorm,
+// GroupNorm, and the tiny fp32 conditioning MLPs (time / prompt embedding -> FiLM table).
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "../../include/dac_b200.h"
+#include "common.h"
+#include "ptx.cuh"
+
+namespace dac {
+
+// ------------------------------------------------------------------------------------------------ SDE step
+// Arithmetic is spelled with non-contracting intrinsics in the reference's exact operation order
+// (sde_utils.py:44-45,177-187,205-231,245-247) so the result is bit-identical to the fp32 PyTorch expression.
+struct SdeCoef {
+  float c[8];
+};
+
+template <int MODE>
+__device__ __forceinline__ float sde_update(float x, float mu, float n, float e, const SdeCoef& k) {
+  if (MODE == 0 || MODE == 2) {
+    // c: 0 theta, 1 sigma^2 (or 0.5*sigma^2 for the ODE), 2 sigma_bar, 3 dt, 4 sigma, 5 sqrt(dt)
+    const float score = __fdiv_rn(-n, k.c[2]);
+    const float drift = __fmul_rn(__fsub_rn(__fmul_rn(k.c[0], __fsub_rn(mu, x)), __fmul_rn(k.c[1], score)), k.c[3]);
+    float r = __fsub_rn(x, drift);
+    if (MODE == 0) r = __fsub_rn(r, __fmul_rn(k.c[4], __fmul_rn(e, k.c[5])));
+    return r;
+  } else {
+    // c: 0 term1, 1 term2, 2 std, 3 exp(Theta_t dt), 4 sigma_bar
+    const float xm = __fsub_rn(x, mu);
+    const float x0 = __fadd_rn(__fmul_rn(__fsub_rn(xm, __fmul_rn(k.c[4], n)), k.c[3]), mu);
+    const float mean = __fadd_rn(__fadd_rn(__fmul_rn(k.c[0], xm), __fmul_rn(k.c[1], __fsub_rn(x0, mu))), mu);
+    return __fadd_rn(mean, __fmul_rn(k.c[2], e));
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) sde_step_kernel(const float* __restrict__ x, const float* __restrict__ mu,
+                                                       const float* __restrict__ net, const float* __restrict__ eps,
+                                                       float* __restrict__ out, int64_t n, SdeCoef k) {
+  const int64_t n4 = n >> 2;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 a = reinterpret_cast<const float4*>(x)[i];
+    const float4 m = reinterpret_cast<const float4*>(mu)[i];
+    const float4 nn = reinterpret_cast<const float4*>(net)[i];
+    float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (MODE != 2) e = reinterpret_cast<const float4*>(eps)[i];
+    float4 r;
+    r.x = sde_update<MODE>(a.x, m.x, nn.x, e.x, k);
+    r.y = sde_update<MODE>(a.y, m.y, nn.y, e.y, k);
+    r.z = sde_update<MODE>(a.z, m.z, nn.z, e.z, k);
+    r.w = sde_update<MODE>(a.w, m.w, nn.w, e.w, k);
+    reinterpret_cast<float4*>(out)[i] = r;
+  }
+  // tail (n not a multiple of 4)
+  for (int64_t i = (n4 << 2) + static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = sde_update<MODE>(x[i], mu[i], net[i], MODE != 2 ? eps[i] : 0.f, k);
+}
+
+__global__ void __launch_bounds__(256) noise_state_kernel(const float* __restrict__ x, const float* __restrict__ eps,
+                                                          float* __restrict__ out, int64_t n, float s) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = __fadd_rn(x[i], __fmul_rn(eps[i], s));
+}
+
+static int elementwise_grid(int64_t work_items) {
+  int64_t blocks = ceil_div(work_items, 256);
+  const int64_t cap = 148 * 16;
+  return static_cast<int>(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
+}
+
+// ------------------------------------------------------------------------------------------------ stem input
+__global__ void __launch_bounds__(256) stem_input_kernel(const float* __restrict__ xt, const float* __restrict__ cond,
+                                                         __nv_bfloat16* __restrict__ out, int B, int H, int W, int Hp,
+                                                         int Wp) {
+  // one thread per (pixel, kx): 8 channels = one 16 B store
+  const int64_t total = static_cast<int64_t>(B) * Hp * Wp * 8;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int kx = static_cast<int>(i & 7);
+    int64_t pix = i >> 3;
+    const int x = static_cast<int>(pix % Wp);
+    pix /= Wp;
+    const int y = static_cast<int>(pix % Hp);
+    const int b = static_cast<int>(pix / Hp);
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const int xs = x + kx - 3;
+    if (kx < 7 && xs >= 0 && xs < Wp) {
+      const int ys = y < H ? y : 2 * H - 2 - y;      // reflect (arch.py:111-116)
+      const int xr = xs < W ? xs : 2 * W - 2 - xs;
+      const int64_t plane = static_cast<int64_t>(H) * W;
+      const int64_t base = (static_cast<int64_t>(b) * 3) * plane + static_cast<int64_t>(ys) * W + xr;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float cv = __ldg(cond + base + c * plane);
+        v[c] = __fsub_rn(__ldg(xt + base + c * plane), cv);
+        v[3 + c] = cv;
+      }
+    }
+    uint4 u;
+    u.x = pack_bf16(v[0], v[1]);
+    u.y = pack_bf16(v[2], v[3]);
+    u.z = pack_bf16(v[4], v[5]);
+    u.w = pack_bf16(v[6], v[7]);
+    reinterpret_cast<uint4*>(out)[i] = u;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ row LayerNorm
+// One warp per row, 16 B vector loads; the row is re-read from L1/L2 for the variance and the write pass.
+__global__ void __launch_bounds__(256) layernorm_rows_kernel(const __nv_bfloat16* __restrict__ in, int ld_in,
+                                                             __nv_bfloat16* __restrict__ out, int ld_out, int64_t rows,
+                                                             int c, const float* __restrict__ w,
+                                                             const float* __restrict__ b, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  const int nvec = c >> 3;
+  for (int64_t row = warp_global; row < rows; row += nwarps) {
+    const uint4* src = reinterpret_cast<const uint4*>(in + row * ld_in);
+    float sum = 0.f;
+    for (int i = lane; i < nvec; i += 32) {
+      const uint4 u = src[i];
+      const float2 a = unpack_bf16(u.x), bb = unpack_bf16(u.y), cc = unpack_bf16(u.z), d = unpack_bf16(u.w);
+      sum += (a.x + a.y) + (bb.x + bb.y) + (cc.x + cc.y) + (d.x + d.y);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / c;
+    float ss = 0.f;
+    for (int i = lane; i < nvec; i += 32) {
+      const uint4 u = src[i];
+      const float2 a = unpack_bf16(u.x), bb = unpack_bf16(u.y), cc = unpack_bf16(u.z), d = unpack_bf16(u.w);
+      const float e0 = a.x - mean, e1 = a.y - mean, e2 = bb.x - mean, e3 = bb.y - mean;
+      const float e4 = cc.x - mean, e5 = cc.y - mean, e6 = d.x - mean, e7 = d.y - mean;
+      ss += e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3 + e4 * e4 + e5 * e5 + e6 * e6 + e7 * e7;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float rstd = rsqrtf(ss / c + eps);
+    uint4* dst = reinterpret_cast<uint4*>(out + row * ld_out);
+    for (int i = lane; i < nvec; i += 32) {
+      const uint4 u = src[i];
+      float v[8];
+      float2 t;
+      t = unpack_bf16(u.x); v[0] = t.x; v[1] = t.y;
+      t = unpack_bf16(u.y); v[2] = t.x; v[3] = t.y;
+      t = unpack_bf16(u.z); v[4] = t.x; v[5] = t.y;
+      t = unpack_bf16(u.w); v[6] = t.x; v[7] = t.y;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float y = (v[j] - mean) * rstd;
+        if (w) y *= __ldg(w + i * 8 + j);
+        if (b) y += __ldg(b + i * 8 + j);
+        v[j] = y;
+      }
+      uint4 o;
+      o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]);
+      o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+      dst[i] = o;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ GroupNorm
+// stats[b][g] = {sum, sumsq}.  Each thread owns one 8-channel vector column (8 | channels-per-group) and walks
+// pixels of its slab; per-group partials are combined through shared memory then one atomicAdd per group.
+__global__ void __launch_bounds__(256) groupnorm_stats_kernel(const __nv_bfloat16* __restrict__ in, int hw, int c,
+                                                              int groups, int slab, float* __restrict__ stats) {
+  extern __shared__ float sh[];  // [groups*2]
+  const int b = blockIdx.y;
+  const int nvec = c >> 3;
+  const int cpg = c / groups;
+  for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  const int p0 = blockIdx.x * slab, p1 = min(hw, p0 + slab);
+  const int vec = threadIdx.x % nvec;
+  const int prow = threadIdx.x / nvec;
+  const int prows = blockDim.x / nvec;
+  if (prow < prows) {
+    float s = 0.f, ss = 0.f;
+    for (int p = p0 + prow; p < p1; p += prows) {
+      const uint4 u = *reinterpret_cast<const uint4*>(in + (static_cast<int64_t>(b) * hw + p) * c + vec * 8);
+      const float2 a = unpack_bf16(u.x), bb = unpack_bf16(u.y), cc = unpack_bf16(u.z), d = unpack_bf16(u.w);
+      s += (a.x + a.y) + (bb.x + bb.y) + (cc.x + cc.y) + (d.x + d.y);
+      ss += a.x * a.x + a.y * a.y + bb.x * bb.x + bb.y * bb.y + cc.x * cc.x + cc.y * cc.y + d.x * d.x + d.y * d.y;
+    }
+    const int g = (vec * 8) / cpg;
+    atomicAdd(&sh[g * 2], s);
+    atomicAdd(&sh[g * 2 + 1], ss);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) atomicAdd(&stats[(b * groups) * 2 + i], sh[i]);
+}
+
+__global__ void __launch_bounds__(256) groupnorm_apply_kernel(const __nv_bfloat16* __restrict__ in,
+                                                              __nv_bfloat16* __restrict__ out, int B, int hw, int c,
+                                                              int groups, const float* __restrict__ w,
+                                                              const float* __restrict__ bias, float eps,
+                                                              const float* __restrict__ stats) {
+  const int nvec = c >> 3;
+  const int cpg = c / groups;
+  const int64_t total = static_cast<int64_t>(B) * hw * nvec;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  const float inv_n = 1.0f / (static_cast<float>(hw) * cpg);
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int vec = static_cast<int>(i % nvec);
+    const int b = static_cast<int>(i / (static_cast<int64_t>(hw) * nvec));
+    const int g = (vec * 8) / cpg;
+    const float s = __ldg(stats + (b * groups + g) * 2), ss = __ldg(stats + (b * groups + g) * 2 + 1);
+    const float mean = s * inv_n;
+    const float var = fmaxf(ss * inv_n - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + eps);
+    const uint4 u = reinterpret_cast<const uint4*>(in)[i];
+    float v[8];
+    float2 t;
+    t = unpack_bf16(u.x); v[0] = t.x; v[1] = t.y;
+    t = unpack_bf16(u.y); v[2] = t.x; v[3] = t.y;
+    t = unpack_bf16(u.z); v[4] = t.x; v[5] = t.y;
+    t = unpack_bf16(u.w); v[6] = t.x; v[7] = t.y;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (v[j] - mean) * rstd * __ldg(w + vec * 8 + j) + __ldg(bias + vec * 8 + j);
+    uint4 o;
+    o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]);
+    o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+    reinterpret_cast<uint4*>(out)[i] = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ conditioning MLPs
+// y[r] = act(W[r,:] . x + b[r]) for r in [0, rows): one warp per output row, coalesced weight reads.
+__device__ __forceinline__ void block_linear(const float* __restrict__ W, const float* __restrict__ bias,
+                                             const float* x_sh, float* y_sh, int rows, int k) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int r = warp; r < rows; r += nw) {
+    float acc = 0.f;
+    for (int i = lane; i < k; i += 32) acc += __ldg(W + static_cast<int64_t>(r) * k + i) * x_sh[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) y_sh[r] = acc + (bias ? __ldg(bias + r) : 0.f);
+  }
+}
+
+__global__ void __launch_bounds__(256) time_embed_kernel(dac_embed_weights w, const float* __restrict__ time_ptr,
+                                                         const float* __restrict__ text_ctx,
+                                                         float* __restrict__ temb_out) {
+  extern __shared__ float sh[];
+  const int td = w.time_dim;
+  float* a = sh;                 // [max(td, ctx, nf)]
+  float* h = a + max(td, max(w.ctx_dim, w.nf));
+  float* t = h + td;
+  float* q = t + td;
+  const int b = blockIdx.x;
+  const float time = __ldg(time_ptr);
+  // sinusoidal embedding (module_util.py:41-48): [sin | cos], freq_i = exp(-i ln(1e4)/(half-1))
+  const int half = w.nf / 2;
+  for (int i = threadIdx.x; i < half; i += blockDim.x) {
+    const float f = expf(static_cast<float>(i) * -(logf(10000.0f) / static_cast<float>(half - 1)));
+    const float arg = time * f;
+    a[i] = sinf(arg);
+    a[half + i] = cosf(arg);
+  }
+  __syncthreads();
+  block_linear(w.time_w1, w.time_b1, a, h, td, w.nf);
+  __syncthreads();
+  for (int i = threadIdx.x; i < td; i += blockDim.x) h[i] = gelu_f(h[i]);
+  __syncthreads();
+  block_linear(w.time_w2, w.time_b2, h, t, td, td);
+  __syncthreads();
+  if (w.text_w1 != nullptr && text_ctx != nullptr) {
+    for (int i = threadIdx.x; i < w.ctx_dim; i += blockDim.x) a[i] = text_ctx[static_cast<int64_t>(b) * w.ctx_dim + i];
+    __syncthreads();
+    block_linear(w.text_w1, w.text_b1, a, h, td, w.ctx_dim);
+    __syncthreads();
+    for (int i = threadIdx.x; i < td; i += blockDim.x) {
+      const float v = h[i];
+      h[i] = v / (1.0f + expf(-v));
+    }
+    __syncthreads();
+    block_linear(w.text_w2, w.text_b2, h, q, td, td);
+    __syncthreads();
+    // softmax over the td features (arch.py:135), times the learned prompt
+    __shared__ float red[2];
+    if (threadIdx.x < 32) {
+      float m = -INFINITY;
+      for (int i = threadIdx.x; i < td; i += 32) m = fmaxf(m, q[i]);
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      float s = 0.f;
+      for (int i = threadIdx.x; i < td; i += 32) s += expf(q[i] - m);
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (threadIdx.x == 0) { red[0] = m; red[1] = s; }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < td; i += blockDim.x) h[i] = expf(q[i] - red[0]) / red[1] * __ldg(w.prompt + i);
+    __syncthreads();
+    block_linear(w.prompt_w, w.prompt_b, h, q, td, td);
+    __syncthreads();
+    for (int i = threadIdx.x; i < td; i += blockDim.x) t[i] += q[i];
+    __syncthreads();
+  }
+  // every ResBlock mlp starts with SiLU (module_util.py:135-137): store silu(t_emb)
+  for (int i = threadIdx.x; i < td; i += blockDim.x) {
+    const float v = t[i];
+    temb_out[static_cast<int64_t>(b) * td + i] = v / (1.0f + expf(-v));
+  }
+}
+
+__global__ void __launch_bounds__(256) film_kernel(const float* __restrict__ W, const float* __restrict__ bias,
+                                                   const float* __restrict__ s, float* __restrict__ film, int F, int k,
+                                                   int B) {
+  // one warp per output feature f, looping over images; W row held in registers (k <= 256 -> 8 per lane)
+  const int lane = threadIdx.x & 31;
+  const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (f >= F) return;
+  float wr[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) wr[j] = (lane + 32 * j < k) ? __ldg(W + static_cast<int64_t>(f) * k + lane + 32 * j) : 0.f;
+  const float bf = __ldg(bias + f);
+  for (int b = 0; b < B; ++b) {
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (lane + 32 * j < k) acc += wr[j] * __ldg(s + static_cast<int64_t>(b) * k + lane + 32 * j);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) film[static_cast<int64_t>(b) * F + f] = acc + bf;
+  }
+}
+
+__global__ void __launch_bounds__(256) two_linear_kernel(const float* __restrict__ x, int in,
+                                                         const float* __restrict__ w1, int mid,
+                                                         const float* __restrict__ w2, const float* __restrict__ b2,
+                                                         int out, float* __restrict__ y) {
+  extern __shared__ float sh[];
+  float* xs = sh;
+  float* ms = sh + in;
+  float* ys = ms + mid;
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < in; i += blockDim.x) xs[i] = x[static_cast<int64_t>(b) * in + i];
+  __syncthreads();
+  block_linear(w1, nullptr, xs, ms, mid, in);
+  __syncthreads();
+  block_linear(w2, b2, ms, ys, out, mid);
+  __syncthreads();
+  for (int i = threadIdx.x; i < out; i += blockDim.x) y[static_cast<int64_t>(b) * out + i] = ys[i];
+}
+
+}  // namespace dac
+
+using namespace dac;
+
+extern "C" int dac_sde_step(int mode, const float* x, const float* mu, const float* net, const float* eps, float* out,
+                            int64_t n, const float* host_coef, dac_stream_t stream) {
+  if (!x || !mu || !net || !out || !host_coef || (mode != 2 && !eps)) return set_error(-1, "dac_sde_step: null argument");
+  if (n <= 0) return 0;
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(mu) | reinterpret_cast<uintptr_t>(net) |
+       reinterpret_cast<uintptr_t>(eps) | reinterpret_cast<uintptr_t>(out)) & 15)
+    return set_error(-2, "dac_sde_step: pointers must be 16-byte aligned");
+  SdeCoef k;
+  for (int i = 0; i < 8; ++i) k.c[i] = host_coef[i];
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int grid = elementwise_grid(n / 4 + 1);
+  if (mode == 0) sde_step_kernel<0><<<grid, 256, 0, s>>>(x, mu, net, eps, out, n, k);
+  else if (mode == 1) sde_step_kernel<1><<<grid, 256, 0, s>>>(x, mu, net, eps, out, n, k);
+  else if (mode == 2) sde_step_kernel<2><<<grid, 256, 0, s>>>(x, mu, net, eps, out, n, k);
+  else return set_error(-2, "dac_sde_step: unknown mode %d", mode);
+  return check_launch("sde_step_kernel");
+}
+
+extern "C" int dac_noise_state(const float* x, const float* eps, float* out, int64_t n, float max_sigma,
+                               dac_stream_t stream) {
+  if (!x || !eps || !out) return set_error(-1, "dac_noise_state: null argument");
+  if (n <= 0) return 0;
+  noise_state_kernel<<<elementwise_grid(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, eps, out, n, max_sigma);
+  return check_launch("noise_state_kernel");
+}
+
+extern "C" int dac_unet_stem_input(const float* xt, const float* cond, void* out, int B, int H, int W, int Hp, int Wp,
+                                   dac_stream_t stream) {
+  if (!xt || !cond || !out) return set_error(-1, "dac_unet_stem_input: null argument");
+  if (Hp < H || Wp < W || Hp - H >= H || Wp - W >= W) return set_error(-2, "dac_unet_stem_input: bad padding");
+  const int64_t total = static_cast<int64_t>(B) * Hp * Wp * 8;
+  stem_input_kernel<<<elementwise_grid(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      xt, cond, static_cast<__nv_bfloat16*>(out), B, H, W, Hp, Wp);
+  return check_launch("stem_input_kernel");
+}
+
+extern "C" int dac_layernorm_rows(const void* in, int32_t ld_in, void* out, int32_t ld_out, int64_t rows, int32_t c,
+                                  const float* w, const float* b, float eps, dac_stream_t stream) {
+  if (!in || !out) return set_error(-1, "dac_layernorm_rows: null argument");
+  if ((c & 7) || (ld_in & 7) || (ld_out & 7)) return set_error(-2, "dac_layernorm_rows: c and pitches must be multiples of 8");
+  if (rows <= 0) return 0;
+  const int64_t blocks = ceil_div(rows, 8);
+  const int grid = static_cast<int>(blocks > 148 * 8 ? 148 * 8 : blocks);
+  layernorm_rows_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(in), ld_in, static_cast<__nv_bfloat16*>(out), ld_out, rows, c, w, b, eps);
+  return check_launch("layernorm_rows_kernel");
+}
+
+extern "C" int dac_groupnorm_nhwc(const void* in, void* out, int32_t B, int32_t hw, int32_t c, int32_t groups,
+                                  const float* w, const float* b, float eps, float* stats, dac_stream_t stream) {
+  if (!in || !out || !w || !b || !stats) return set_error(-1, "dac_groupnorm_nhwc: null argument");
+  if (c % groups || (c / groups) % 8 || c / 8 > 256) return set_error(-2, "dac_groupnorm_nhwc: need 8 | c/groups, c <= 2048");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  cudaMemsetAsync(stats, 0, sizeof(float) * 2 * B * groups, s);
+  const int slabs = hw >= 1024 ? 16 : (hw >= 64 ? 4 : 1);
+  const int slab = static_cast<int>(ceil_div(hw, slabs));
+  groupnorm_stats_kernel<<<dim3(slabs, B), 256, groups * 2 * sizeof(float), s>>>(
+      static_cast<const __nv_bfloat16*>(in), hw, c, groups, slab, stats);
+  int rc = check_launch("groupnorm_stats_kernel");
+  if (rc) return rc;
+  const int64_t total = static_cast<int64_t>(B) * hw * (c / 8);
+  groupnorm_apply_kernel<<<elementwise_grid(total), 256, 0, s>>>(static_cast<const __nv_bfloat16*>(in),
+                                                                static_cast<__nv_bfloat16*>(out), B, hw, c, groups, w,
+                                                                b, eps, stats);
+  return check_launch("groupnorm_apply_kernel");
+}
+
+extern "C" int dac_time_film(const dac_embed_weights* w, const float* time, const float* text_ctx, int32_t B,
+                             float* temb_scratch, float* film, dac_stream_t stream) {
+  if (!w || !time || !temb_scratch || !film) return set_error(-1, "dac_time_film: null argument");
+  if (w->time_dim > 256 || w->time_dim % 32) return set_error(-2, "dac_time_film: time_dim must be <= 256");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int td = w->time_dim;
+  int amax = td > w->ctx_dim ? td : w->ctx_dim;
+  if (w->nf > amax) amax = w->nf;
+  const size_t sh = sizeof(float) * (amax + 3 * td);
+  time_embed_kernel<<<B, 256, sh, s>>>(*w, time, text_ctx, temb_scratch);
+  int rc = check_launch("time_embed_kernel");
+  if (rc) return rc;
+  film_kernel<<<static_cast<int>(ceil_div(w->F, 8)), 256, 0, s>>>(w->film_w, w->film_b, temb_scratch, film, w->F, td, B);
+  return check_launch("film_kernel");
+}
+
+extern "C" int dac_two_linear(const float* x, int32_t B, int32_t in, const float* w1, int32_t mid, const float* w2,
+                              const float* b2, int32_t out, float* y, dac_stream_t stream) {
+  if (!x || !w1 || !w2 || !y) return set_error(-1, "dac_two_linear: null argument");
+  const size_t sh = sizeof(float) * (in + mid + out);
+  if (sh > 48 * 1024) return set_error(-2, "dac_two_linear: dims too large");
+  two_linear_kernel<<<B, 256, sh, static_cast<cudaStream_t>(stream)>>>(x, in, w1, mid, w2, b2, out, y);
+  return check_launch("two_linear_kernel");
+}

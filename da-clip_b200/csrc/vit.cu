@@ -1,0 +1,176 @@
+// DA-CLIP image-encoder glue kernels (open_clip/transformer.py:507-555 of the reference): patch unfolding for
+// the conv1-as-GEMM, class token + positional embedding + ln_pre, class-token pooling + ln_post + projection,
+// and the degradation-type argmax (da-clip/src/evaluate_daclip.py:46-47,79-81).
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "../../include/dac_b200.h"
+#include "common.h"
+#include "ptx.cuh"
+
+namespace dac {
+
+// out[(b*g*g + gy*g + gx), c*p*p + py*p + px] = image[b, c, gy*p+py, gx*p+px]
+__global__ void __launch_bounds__(256) vit_patchify_kernel(const float* __restrict__ img,
+                                                           __nv_bfloat16* __restrict__ out, int B, int S, int p) {
+  const int g = S / p;
+  const int K = 3 * p * p;
+  const int64_t total = static_cast<int64_t>(B) * g * g * K / 2;  // two px per thread
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t e = i * 2;
+    const int k = static_cast<int>(e % K);
+    const int64_t row = e / K;
+    const int gx = static_cast<int>(row % g), gy = static_cast<int>((row / g) % g), b = static_cast<int>(row / (g * g));
+    const int px = k % p, py = (k / p) % p, c = k / (p * p);
+    const float* src = img + ((static_cast<int64_t>(b) * 3 + c) * S + gy * p + py) * S + gx * p + px;
+    reinterpret_cast<uint32_t*>(out)[i] = pack_bf16(src[0], src[1]);
+  }
+}
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int i = 0; i < (blockDim.x >> 5); ++i) t += red[i];
+  return t;
+}
+
+// one CTA per token: (cls | patch embedding) + positional embedding -> LayerNorm -> bf16
+__global__ void __launch_bounds__(256) vit_embed_kernel(const __nv_bfloat16* __restrict__ patch_emb,
+                                                        const float* __restrict__ cls, const float* __restrict__ pos,
+                                                        const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                                                        __nv_bfloat16* __restrict__ out, int L, int w, float eps) {
+  extern __shared__ float row[];
+  __shared__ float red[8];
+  const int tok = blockIdx.x % L, b = blockIdx.x / L;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < w; i += blockDim.x) {
+    float v = (tok == 0) ? cls[i]
+                         : __bfloat162float(patch_emb[(static_cast<int64_t>(b) * (L - 1) + tok - 1) * w + i]);
+    v += pos[static_cast<int64_t>(tok) * w + i];
+    row[i] = v;
+    s += v;
+  }
+  const float mean = block_sum(s, red) / w;
+  float ss = 0.f;
+  for (int i = threadIdx.x; i < w; i += blockDim.x) {
+    const float d = row[i] - mean;
+    ss += d * d;
+  }
+  const float rstd = rsqrtf(block_sum(ss, red) / w + eps);
+  for (int i = threadIdx.x; i < w; i += blockDim.x)
+    out[(static_cast<int64_t>(b) * L + tok) * w + i] = __float2bfloat16((row[i] - mean) * rstd * ln_w[i] + ln_b[i]);
+}
+
+// one CTA per image: ln_post(x[b,0,:]) @ proj
+__global__ void __launch_bounds__(256) vit_pool_kernel(const __nv_bfloat16* __restrict__ x, int L, int w,
+                                                       const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                                                       float eps, const float* __restrict__ proj, int e,
+                                                       float* __restrict__ out) {
+  extern __shared__ float row[];
+  __shared__ float red[8];
+  const int b = blockIdx.x;
+  const __nv_bfloat16* src = x + static_cast<int64_t>(b) * L * w;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < w; i += blockDim.x) {
+    row[i] = __bfloat162float(src[i]);
+    s += row[i];
+  }
+  const float mean = block_sum(s, red) / w;
+  float ss = 0.f;
+  for (int i = threadIdx.x; i < w; i += blockDim.x) {
+    const float d = row[i] - mean;
+    ss += d * d;
+  }
+  const float rstd = rsqrtf(block_sum(ss, red) / w + eps);
+  __syncthreads();
+  for (int i = threadIdx.x; i < w; i += blockDim.x) row[i] = (row[i] - mean) * rstd * ln_w[i] + ln_b[i];
+  __syncthreads();
+  for (int j = threadIdx.x; j < e; j += blockDim.x) {
+    float a = 0.f;
+    for (int i = 0; i < w; ++i) a += row[i] * __ldg(proj + static_cast<int64_t>(i) * e + j);  // coalesced over j
+    out[static_cast<int64_t>(b) * e + j] = a;
+  }
+}
+
+// one warp per image: logits[j] = 100 * <d/|d|, t_j/|t_j|>; first index of the maximum (torch.argmax tie rule)
+__global__ void __launch_bounds__(32) degradation_argmax_kernel(const float* __restrict__ degra,
+                                                                const float* __restrict__ text, int e, int classes,
+                                                                float* __restrict__ logits,
+                                                                int64_t* __restrict__ argmax) {
+  const int b = blockIdx.x, lane = threadIdx.x;
+  const float* d = degra + static_cast<int64_t>(b) * e;
+  float dn = 0.f;
+  for (int i = lane; i < e; i += 32) dn += d[i] * d[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) dn += __shfl_xor_sync(0xffffffffu, dn, o);
+  dn = sqrtf(dn);
+  float best = -INFINITY;
+  int besti = 0;
+  for (int j = 0; j < classes; ++j) {
+    const float* t = text + static_cast<int64_t>(j) * e;
+    float tn = 0.f, dot = 0.f;
+    for (int i = lane; i < e; i += 32) {
+      tn += t[i] * t[i];
+      dot += (d[i] / dn) * t[i];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      tn += __shfl_xor_sync(0xffffffffu, tn, o);
+      dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    }
+    const float lg = 100.0f * dot / sqrtf(tn);
+    if (logits && lane == 0) logits[static_cast<int64_t>(b) * classes + j] = lg;
+    if (lg > best) {
+      best = lg;
+      besti = j;
+    }
+  }
+  if (lane == 0) argmax[b] = besti;
+}
+
+}  // namespace dac
+
+using namespace dac;
+
+extern "C" int dac_vit_patchify(const float* image, void* out, int32_t B, int32_t S, int32_t p, dac_stream_t stream) {
+  if (!image || !out) return set_error(-1, "dac_vit_patchify: null argument");
+  if (S % p || (p & 1)) return set_error(-2, "dac_vit_patchify: patch must be even and divide the image");
+  const int g = S / p;
+  const int64_t total = static_cast<int64_t>(B) * g * g * 3 * p * p / 2;
+  int64_t blocks = ceil_div(total, 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  vit_patchify_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      image, static_cast<__nv_bfloat16*>(out), B, S, p);
+  return check_launch("vit_patchify_kernel");
+}
+
+extern "C" int dac_vit_embed(const void* patch_emb, const float* cls, const float* pos, const float* ln_w,
+                             const float* ln_b, void* out, int32_t B, int32_t L, int32_t w, float eps,
+                             dac_stream_t stream) {
+  if (!patch_emb || !cls || !pos || !ln_w || !ln_b || !out) return set_error(-1, "dac_vit_embed: null argument");
+  vit_embed_kernel<<<B * L, 256, w * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(patch_emb), cls, pos, ln_w, ln_b, static_cast<__nv_bfloat16*>(out), L, w, eps);
+  return check_launch("vit_embed_kernel");
+}
+
+extern "C" int dac_vit_pool(const void* x, int32_t B, int32_t L, int32_t w, const float* ln_w, const float* ln_b,
+                            float eps, const float* proj, int32_t e, float* out, dac_stream_t stream) {
+  if (!x || !ln_w || !ln_b || !proj || !out) return set_error(-1, "dac_vit_pool: null argument");
+  vit_pool_kernel<<<B, 256, w * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), L, w, ln_w, ln_b, eps, proj, e, out);
+  return check_launch("vit_pool_kernel");
+}
+
+extern "C" int dac_degradation_argmax(const float* degra, const float* text, int32_t B, int32_t e, int32_t classes,
+                                      float* logits, int64_t* argmax, dac_stream_t stream) {
+  if (!degra || !text || !argmax) return set_error(-1, "dac_degradation_argmax: null argument");
+  degradation_argmax_kernel<<<B, 32, 0, static_cast<cudaStream_t>(stream)>>>(degra, text, e, classes, logits, argmax);
+  return check_launch("degradation_argmax_kernel");
+}

@@ -1,0 +1,274 @@
+"""Host-side operator layer: weight repacking into the kernels' native layouts and typed wrappers over the
+C ABI.  Repacking runs once per checkpoint load (torch is used here as memory + layout plumbing only)."""
+import ctypes as C
+
+import torch
+
+from . import lib as L
+
+TILE_SHAPES = [(1, 128), (2, 64), (4, 32), (8, 16), (16, 8)]
+
+
+def choose_tile(oh, ow):
+    """Pixel-tile (h, w) with h*w == 128 that wastes the fewest out-of-image pixels (ties: widest)."""
+    best, best_waste = None, None
+    for th, tw in TILE_SHAPES:
+        waste = (-(-oh // th)) * (-(-ow // tw)) * 128 - oh * ow
+        if best is None or waste < best_waste:
+            best, best_waste = (th, tw), waste
+    return best
+
+
+def choose_block_n(cout):
+    """UMMA N and padded channel count for a plain epilogue."""
+    if cout <= 256:
+        bn = -(-cout // 16) * 16
+        return bn, bn
+    for bn in (256, 128, 64):
+        if cout % bn == 0:
+            return bn, cout
+    bn = 128
+    return bn, -(-cout // bn) * bn
+
+
+def _pad_rows(w, cout_pad):
+    """w: [Z, cout, cin] -> zero-padded [Z, cout_pad, cin] bf16 contiguous."""
+    z, cout, cin = w.shape
+    out = torch.zeros(z, cout_pad, cin, dtype=torch.bfloat16, device=w.device)
+    out[:, :cout] = w.to(torch.bfloat16)
+    return out.contiguous()
+
+
+class PackedWeight:
+    """Weights in kernel layout bf16 [Z][cout_pad][cin] plus the tap geometry that indexes Z."""
+
+    def __init__(self, w, taps, cout, stride=1, ngroups=1, out_scale=1, out_off=((0, 0),)):
+        self.w = w                      # [Z, cout_pad, cin] bf16
+        self.taps = taps                # per group: list of (dy, dx)
+        self.cout = cout
+        self.stride = stride
+        self.ngroups = ngroups
+        self.out_scale = out_scale
+        self.out_off = out_off          # per group (oy, ox)
+
+
+def pack_conv(weight, cout_pad=None, stride=1, pad=None):
+    """nn.Conv2d weight [cout, cin, kh, kw] -> taps-major K-major slabs.  Tap (ky,kx) reads input
+    (y*stride + ky - pad, x*stride + kx - pad)."""
+    cout, cin, kh, kw = weight.shape
+    pad = kh // 2 if pad is None else pad
+    cout_pad = cout_pad or choose_block_n(cout)[1]
+    w = weight.permute(2, 3, 0, 1).reshape(kh * kw, cout, cin)
+    taps = [[(ky - pad, kx - pad) for ky in range(kh) for kx in range(kw)]]
+    return PackedWeight(_pad_rows(w, cout_pad), taps, cout, stride=stride)
+
+
+def pack_linear(weight, cout_pad=None):
+    """nn.Linear weight [out, in] (or a 1x1 conv weight [out, in, 1, 1])."""
+    w = weight.reshape(weight.shape[0], weight.shape[1])
+    cout = w.shape[0]
+    cout_pad = cout_pad or choose_block_n(cout)[1]
+    return PackedWeight(_pad_rows(w[None], cout_pad), [[(0, 0)]], cout)
+
+
+def pack_geglu(weight, bias, block_n=256):
+    """GEGLU proj (attention.py:37-44): rows [0,inner) are values, [inner,2*inner) gates.  Rows are
+    interleaved per N tile as [block_n/2 values | block_n/2 matching gates] so that one accumulator tile holds
+    both halves of the same channels.  Returns (PackedWeight, permuted bias)."""
+    two_inner, cin = weight.shape
+    inner, half = two_inner // 2, block_n // 2
+    assert inner % half == 0
+    idx = []
+    for t in range(inner // half):
+        idx += list(range(t * half, (t + 1) * half)) + list(range(inner + t * half, inner + (t + 1) * half))
+    idx = torch.tensor(idx, device=weight.device)
+    pw = PackedWeight(_pad_rows(weight[idx][None], two_inner), [[(0, 0)]], two_inner)
+    return pw, bias[idx].float().contiguous()
+
+
+def pack_stem(weight):
+    """init_conv 7x7, cin=6 (arch.py:36): K = (kx, c) packed into 64 channels (8 per kx), 7 vertical taps;
+    pairs with dac_unet_stem_input."""
+    cout, cin, kh, kw = weight.shape
+    assert (cin, kh, kw) == (6, 7, 7)
+    w = torch.zeros(kh, cout, 64, dtype=weight.dtype, device=weight.device)
+    for kx in range(kw):
+        w[:, :, kx * 8:kx * 8 + cin] = weight[:, :, :, kx].permute(2, 0, 1)
+    taps = [[(ky - 3, 0) for ky in range(kh)]]
+    return PackedWeight(_pad_rows(w, choose_block_n(cout)[1]), taps, cout)
+
+
+def pack_upsample_conv(weight):
+    """nearest-2x upsample followed by a 3x3 conv (module_util.py:100-104) == four 2x2 convs on the
+    low-resolution input, one per output parity (py, px), whose taps are sums of the original taps that hit the
+    same source pixel.  2.25x fewer MACs and no materialised upsampled tensor."""
+    cout, cin, kh, kw = weight.shape
+    assert (kh, kw) == (3, 3)
+    # parity 0: source offsets -1 <- {k0}, 0 <- {k1,k2};  parity 1: 0 <- {k0,k1}, +1 <- {k2}
+    sets = {0: [(-1, [0]), (0, [1, 2])], 1: [(0, [0, 1]), (1, [2])]}
+    slabs, taps, offs = [], [], []
+    w32 = weight.float()
+    for py in (0, 1):
+        for px in (0, 1):
+            gt = []
+            for dy, kys in sets[py]:
+                for dx, kxs in sets[px]:
+                    acc = torch.zeros(cout, cin, dtype=torch.float32, device=weight.device)
+                    for ky in kys:
+                        for kx in kxs:
+                            acc += w32[:, :, ky, kx]
+                    slabs.append(acc)
+                    gt.append((dy, dx))
+            taps.append(gt)
+            offs.append((py, px))
+    w = torch.stack(slabs)                                   # [16, cout, cin]
+    cout_pad = choose_block_n(cout)[1]
+    return PackedWeight(_pad_rows(w, cout_pad), taps, cout, ngroups=4, out_scale=2, out_off=tuple(offs))
+
+
+class ConvPlan:
+    """One dac_conv plan (TMA descriptors baked for fixed buffers)."""
+
+    def __init__(self, src0, c0, pw: PackedWeight, out=None, *, B, H, W, src1=None, c1=0, ld0=None, ld1=None,
+                 epi=L.EPI_PLAIN, act=L.ACT_NONE, bias=None, bias_img=None, film=None, film_off=0,
+                 ln_g=None, ln_eps=1e-5, res=None, res2=None, out_coff=0, out_nchw=None,
+                 per_image_w=False, block_n=None, weight_override=None, tile=None):
+        L.require_cuda(src0)
+        lib = L.load()
+        d = L.ConvDesc()
+        s = pw.stride
+        OH, OW = (H // s, W // s) if s == 2 else (H, W)
+        th, tw = tile or choose_tile(OH, OW)
+        wt = weight_override if weight_override is not None else pw.w
+        cout_pad = wt.shape[-2]
+        if block_n is None:
+            block_n = choose_block_n(pw.cout)[0] if cout_pad <= 256 else (256 if cout_pad % 256 == 0 else 128)
+        d.src0, d.c0, d.ld0 = src0.data_ptr(), c0, ld0 or src0.shape[-1]
+        if src1 is not None:
+            d.src1, d.c1, d.ld1 = src1.data_ptr(), c1, ld1 or src1.shape[-1]
+        d.B, d.H, d.W, d.OH, d.OW = B, H, W, OH, OW
+        d.stride, d.ngroups, d.ntaps = s, pw.ngroups, len(pw.taps[0])
+        for g, gt in enumerate(pw.taps):
+            for i, (dy, dx) in enumerate(gt):
+                d.tap_dy[g][i], d.tap_dx[g][i] = dy, dx
+        d.out_scale = pw.out_scale
+        for g, (oy, ox) in enumerate(pw.out_off):
+            d.out_oy[g], d.out_ox[g] = oy, ox
+        d.weight, d.cout, d.cout_pad, d.per_image_w = wt.data_ptr(), pw.cout, cout_pad, int(per_image_w)
+        d.block_n, d.tile_h, d.tile_w = block_n, th, tw
+        d.epi, d.act = epi, act
+        d.bias = bias.data_ptr() if bias is not None else None
+        d.bias_img = bias_img.data_ptr() if bias_img is not None else None
+        if film is not None:
+            d.film, d.film_ld, d.film_off = film.data_ptr(), film.shape[-1], film_off
+        if ln_g is not None:
+            d.ln_g, d.ln_eps = ln_g.data_ptr(), ln_eps
+        if res is not None:
+            d.res, d.res_ld = res.data_ptr(), res.shape[-1]
+        if res2 is not None:
+            d.res2, d.res2_ld = res2.data_ptr(), res2.shape[-1]
+        if out is not None:
+            d.out, d.out_ld, d.out_coff = out.data_ptr(), out.shape[-1], out_coff
+        if out_nchw is not None:
+            d.out_nchw = out_nchw.data_ptr()
+            d.out_nchw_c, d.out_nchw_h, d.out_nchw_w = out_nchw.shape[1], out_nchw.shape[2], out_nchw.shape[3]
+        self._keep = (src0, src1, wt, out, bias, bias_img, film, ln_g, res, res2, out_nchw)
+        self.desc = d
+        h = C.c_void_p()
+        L.check(lib.dac_conv_create(C.byref(d), C.byref(h)))
+        self.handle = h
+        self._lib = lib
+        self.flops = 2.0 * B * OH * OW * pw.ngroups * len(pw.taps[0]) * (c0 + c1) * pw.cout
+
+    def run(self):
+        L.check(self._lib.dac_conv_launch(self.handle, L.stream_ptr()))
+
+    def info(self):
+        v = [C.c_int32() for _ in range(4)]
+        L.check(self._lib.dac_conv_info(self.handle, *[C.byref(x) for x in v]))
+        return dict(tiles=v[0].value, ctas=v[1].value, smem=v[2].value, stages=v[3].value)
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self._lib.dac_conv_destroy(self.handle)
+        except Exception:
+            pass
+
+
+# ------------------------------------------------------------------------------------------------ thin wrappers
+def _coef(vals):
+    arr = (C.c_float * 8)()
+    for i, v in enumerate(vals):
+        arr[i] = float(v)
+    return arr
+
+
+def sde_step(mode, x, mu, net, eps, out, coef):
+    L.require_cuda(x, mu, net, out)
+    L.check(L.load().dac_sde_step(mode, L.ptr(x), L.ptr(mu), L.ptr(net), L.ptr(eps), L.ptr(out), x.numel(),
+                                  _coef(coef), L.stream_ptr()))
+
+
+def noise_state(x, eps, out, max_sigma):
+    L.require_cuda(x, eps, out)
+    L.check(L.load().dac_noise_state(L.ptr(x), L.ptr(eps), L.ptr(out), x.numel(), float(max_sigma), L.stream_ptr()))
+
+
+def stem_input(xt, cond, out, H, W):
+    B, Hp, Wp = out.shape[0], out.shape[1], out.shape[2]
+    L.check(L.load().dac_unet_stem_input(L.ptr(xt), L.ptr(cond), L.ptr(out), B, H, W, Hp, Wp, L.stream_ptr()))
+
+
+def layernorm_rows(x, out, rows, c, w=None, b=None, eps=1e-5):
+    L.check(L.load().dac_layernorm_rows(L.ptr(x), x.shape[-1], L.ptr(out), out.shape[-1], rows, c, L.ptr(w), L.ptr(b),
+                                        float(eps), L.stream_ptr()))
+
+
+def groupnorm_nhwc(x, out, B, hw, c, w, b, stats, groups=32, eps=1e-6):
+    L.check(L.load().dac_groupnorm_nhwc(L.ptr(x), L.ptr(out), B, hw, c, groups, L.ptr(w), L.ptr(b), float(eps),
+                                        L.ptr(stats), L.stream_ptr()))
+
+
+def time_film(ew, time, text_ctx, B, temb, film):
+    L.check(L.load().dac_time_film(C.byref(ew), L.ptr(time), L.ptr(text_ctx), B, L.ptr(temb), L.ptr(film),
+                                   L.stream_ptr()))
+
+
+def two_linear(x, w1, w2, b2, y):
+    B, kin = x.shape
+    L.check(L.load().dac_two_linear(L.ptr(x), B, kin, L.ptr(w1), w1.shape[0], L.ptr(w2), L.ptr(b2), w2.shape[0],
+                                    L.ptr(y), L.stream_ptr()))
+
+
+def linattn_context(qkv, B, hw, nchunks, partial):
+    L.check(L.load().dac_linattn_context(L.ptr(qkv), B, hw, nchunks, L.ptr(partial), L.stream_ptr()))
+
+
+def linattn_fold(partial, B, hw, nchunks, w_out, C_, c_pad, weff):
+    L.check(L.load().dac_linattn_fold(L.ptr(partial), B, hw, nchunks, L.ptr(w_out), C_, c_pad, L.ptr(weff),
+                                      L.stream_ptr()))
+
+
+def attention(qkv, out, B, n, heads, d):
+    L.check(L.load().dac_attention(L.ptr(qkv), L.ptr(out), B, n, heads, d, L.stream_ptr()))
+
+
+def vit_patchify(image, out, B, S, p):
+    L.check(L.load().dac_vit_patchify(L.ptr(image), L.ptr(out), B, S, p, L.stream_ptr()))
+
+
+def vit_embed(patch_emb, cls, pos, ln_w, ln_b, out, B, Ltok, w, eps=1e-5):
+    L.check(L.load().dac_vit_embed(L.ptr(patch_emb), L.ptr(cls), L.ptr(pos), L.ptr(ln_w), L.ptr(ln_b), L.ptr(out),
+                                   B, Ltok, w, float(eps), L.stream_ptr()))
+
+
+def vit_pool(x, B, Ltok, w, ln_w, ln_b, proj, out, eps=1e-5):
+    L.check(L.load().dac_vit_pool(L.ptr(x), B, Ltok, w, L.ptr(ln_w), L.ptr(ln_b), float(eps), L.ptr(proj),
+                                  proj.shape[1], L.ptr(out), L.stream_ptr()))
+
+
+def degradation_argmax(degra, text, logits, argmax):
+    B, e = degra.shape
+    L.check(L.load().dac_degradation_argmax(L.ptr(degra), L.ptr(text), B, e, text.shape[0], L.ptr(logits),
+                                            L.ptr(argmax), L.stream_ptr()))

@@ -1,0 +1,165 @@
+/*
+ * dac_b200.h - C ABI of libdac_b200.so: the B200 (sm_100a) kernels behind the DA-CLIP
+ * universal-restoration inference path.
+ *
+ * The reference (yeeecheng/DA-CLIP) is pure Python on PyTorch and has no FFI layer of its own;
+ * each entry point below replaces the PyTorch op sequence of the reference site it cites
+ * (paths relative to /root/reference/universal-image-restoration unless noted):
+ *   SDE  = utils/sde_utils.py
+ *   ARCH = config/daclip-sde/models/modules/DenoisingUNet_arch.py
+ *   MU   = config/daclip-sde/models/modules/module_util.py
+ *   ATT  = config/daclip-sde/models/modules/attention.py
+ *   TR   = open_clip/transformer.py
+ *
+ * Conventions: plain pointers and sizes only (no torch types).  All pointers are DEVICE pointers
+ * owned by the caller unless the name says `host_`.  Activations are NHWC bf16, SDE state is
+ * NCHW fp32 (the reference's layout).  Every call enqueues work on `stream` and returns 0, or a
+ * negative code with a message retrievable through dac_last_error().  Nothing here allocates
+ * device memory; plan objects own only host memory (TMA descriptors).
+ */
+#ifndef DAC_B200_H
+#define DAC_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* dac_stream_t; /* cudaStream_t */
+
+int dac_version(void);
+const char* dac_last_error(void);
+/* Number of kernels this library has launched since load (or since the last reset). */
+int64_t dac_launch_count(void);
+void dac_reset_launch_count(void);
+
+/* ------------------------------------------------------------------ SDE updates (fp32, HBM-bound)
+ * x, mu, net, eps, out: [n] fp32 (any layout, elementwise).  out may alias x.
+ * mode 0: reverse-SDE step     SDE:44-45,177-178,183-187   coef = {theta_t, sigma_t^2, sigma_bar_t, dt, sigma_t, sqrt(dt)}
+ * mode 1: posterior step       SDE:205-231,245-247         coef = {term1, term2, std, exp(Theta_t dt), sigma_bar_t}
+ * mode 2: probability-flow ODE SDE:47-48,180-181           coef = {theta_t, 0.5*sigma_t^2, sigma_bar_t, dt}
+ * host_coef: 8 floats on the HOST (read at call time), computed in fp32 exactly as the reference computes its
+ * 0-dim tensors; the kernel applies them in the reference's operation order without FMA contraction, so the
+ * update is bit-identical to the PyTorch fp32 expression. */
+int dac_sde_step(int mode, const float* x, const float* mu, const float* net, const float* eps, float* out,
+                 int64_t n, const float* host_coef, dac_stream_t stream);
+/* SDE:374-375  out = x + eps * max_sigma */
+int dac_noise_state(const float* x, const float* eps, float* out, int64_t n, float max_sigma, dac_stream_t stream);
+
+/* ------------------------------------------------------------------ UNet stem input  ARCH:123-127
+ * xt, cond: [B,3,H,W] fp32 NCHW.  out: [B,Hp,Wp,64] bf16 NHWC where Hp,Wp = H,W reflect-padded up to a
+ * multiple of 16 and channel (kx*8 + c), kx in 0..6, c in 0..5, holds cat[xt-cond, cond][c] at column x+kx-3
+ * (zero outside the padded image; channels 6,7 of each group and 56..63 are zero).  This turns the 7x7
+ * init_conv (ARCH:36,129) into a 7-tap vertical conv over 64 channels for the tensor-core kernel. */
+int dac_unet_stem_input(const float* xt, const float* cond, void* out, int B, int H, int W, int Hp, int Wp,
+                        dac_stream_t stream);
+
+/* ------------------------------------------------------------------ implicit-GEMM conv / linear (tcgen05)
+ * One descriptor covers: 3x3 / 1x1 / 7x1 stride-1 convs, the 4x4 stride-2 Downsample (MU:107-108), the
+ * nearest-2x-upsample + 3x3 conv (MU:100-104) folded into four 2x2 parity convs, nn.Linear on token tensors,
+ * and a virtual channel concat of two sources (ARCH:158,161,167), with the following fused epilogues. */
+enum {
+  DAC_EPI_PLAIN = 0,  /* out = act(film(acc + bias)) + res                                   MU:115-153 */
+  DAC_EPI_GEGLU = 1,  /* tile cols [0,bn/2) value, [bn/2,bn) gate: out = v * gelu(g)        ATT:37-44 */
+  DAC_EPI_LN = 2,     /* out = LN_c(acc + bias) * g + res   (single N tile)                 MU:77-86,166-168 */
+  DAC_EPI_QKV = 3     /* N-tile 0: per-32-col softmax * 32^-0.5 (q); other tiles raw (k,v)   MU:170-177 */
+};
+enum { DAC_ACT_NONE = 0, DAC_ACT_SILU = 1, DAC_ACT_GELU = 2 };
+
+typedef struct dac_conv_desc {
+  /* input sources (virtual concat along channels): NHWC bf16, c channels used out of pixel pitch ld */
+  const void* src0; int32_t c0; int32_t ld0;
+  const void* src1; int32_t c1; int32_t ld1;
+  int32_t B, H, W;              /* input spatial dims */
+  int32_t OH, OW;               /* conv output grid (per parity group) */
+  int32_t stride;               /* 1 or 2: input coord = out*stride + tap offset */
+  int32_t ngroups;              /* 1, or 4 parity groups for the folded upsample conv */
+  int32_t ntaps;                /* taps per group (<=16) */
+  int8_t tap_dy[4][16];
+  int8_t tap_dx[4][16];
+  int32_t out_scale;            /* output position = out*out_scale + out_off[g] */
+  int8_t out_oy[4], out_ox[4];
+  /* weights: bf16 [Z][cout_pad][c0+c1], Z = ngroups*ntaps (* B if per_image_w); cout_pad multiple of block_n */
+  const void* weight; int32_t cout; int32_t cout_pad; int32_t per_image_w;
+  int32_t block_n;              /* UMMA N: 16..256, multiple of 16 */
+  int32_t tile_h, tile_w;       /* tile_h*tile_w == 128 */
+  /* epilogue */
+  int32_t epi, act;
+  const float* bias;            /* [cout] or NULL */
+  const float* bias_img;        /* [B][cout] or NULL (per-image bias, e.g. constant cross-attention term) */
+  const float* film; int32_t film_ld, film_off;   /* scale at film[b*ld+off+c], shift at +cout; NULL = none */
+  const float* ln_g; float ln_eps;
+  const void* res; int32_t res_ld;                /* residual NHWC bf16 at output coordinates, or NULL */
+  const void* res2; int32_t res2_ld;              /* optional second residual (nested Residual of MU:27-33 + ATT:261) */
+  void* out; int32_t out_ld, out_coff;            /* NHWC bf16 [B, OH*out_scale, OW*out_scale, out_ld] */
+  float* out_nchw; int32_t out_nchw_c, out_nchw_h, out_nchw_w; /* alt. fp32 NCHW output (final_conv), cropped */
+} dac_conv_desc;
+
+typedef struct dac_conv_plan* dac_conv_t;
+int dac_conv_create(const dac_conv_desc* desc, dac_conv_t* plan);
+int dac_conv_launch(dac_conv_t plan, dac_stream_t stream);
+void dac_conv_destroy(dac_conv_t plan);
+/* Tiles, CTAs and dynamic shared memory chosen for a plan (for logs and roofline accounting). */
+int dac_conv_info(dac_conv_t plan, int32_t* tiles, int32_t* ctas, int32_t* smem_bytes, int32_t* stages);
+
+/* ------------------------------------------------------------------ norms
+ * LayerNorm over the last dim of a [rows, c] bf16 matrix (row pitch ld_in / ld_out), fp32 statistics,
+ * biased variance.  w/b may be NULL (gain 1 / no bias).  Serves channel LayerNorm (MU:77-86, gain only, NHWC
+ * rows = pixels) and nn.LayerNorm of the transformer blocks (ATT:203-205) and ViT (TR:22-28). */
+int dac_layernorm_rows(const void* in, int32_t ld_in, void* out, int32_t ld_out, int64_t rows, int32_t c,
+                       const float* w, const float* b, float eps, dac_stream_t stream);
+/* GroupNorm(32 groups, eps) over NHWC bf16 [B, hw, c] (ATT:76-77,251).  stats: workspace [B*32*2] fp32. */
+int dac_groupnorm_nhwc(const void* in, void* out, int32_t B, int32_t hw, int32_t c, int32_t groups,
+                       const float* w, const float* b, float eps, float* stats, dac_stream_t stream);
+
+/* ------------------------------------------------------------------ conditioning vectors
+ * time_mlp + text_mlp/prompt/prompt_mlp (ARCH:51-62,132-137) -> silu(t_emb) [B,256] fp32, then every ResBlock
+ * `mlp` Linear at once (MU:135-137,145-148): film[b, f] = W_all[f,:] . silu(t_emb[b]) + b_all[f].
+ * weights: fp32 row-major in the reference state-dict layout. */
+typedef struct dac_embed_weights {
+  const float *time_w1, *time_b1, *time_w2, *time_b2;       /* [256,64],[256],[256,256],[256] */
+  const float *text_w1, *text_b1, *text_w2, *text_b2;       /* [256,ctx],[256],[256,256],[256] (NULL: no prompt) */
+  const float *prompt, *prompt_w, *prompt_b;                /* [256],[256,256],[256] */
+  const float *film_w, *film_b;                             /* [F,256],[F] */
+  int32_t nf, time_dim, ctx_dim, F;
+} dac_embed_weights;
+int dac_time_film(const dac_embed_weights* w, const float* time /*device scalar: one CUDA graph serves every step*/,
+                  const float* text_ctx /*[B,ctx] or NULL*/, int32_t B,
+                  float* temb_scratch /*[B,time_dim]*/, float* film /*[B,F]*/, dac_stream_t stream);
+/* out[b, :] = W2 (W1 x[b]) + b2  -- the exact value of cross-attention over a 1-token context
+ * (ATT:152-193 with len(context)=1: softmax of one logit == 1).  W1 [mid,in], W2 [out,mid] fp32. */
+int dac_two_linear(const float* x, int32_t B, int32_t in, const float* w1, int32_t mid, const float* w2,
+                   const float* b2, int32_t out, float* y, dac_stream_t stream);
+
+/* ------------------------------------------------------------------ LinearAttention (MU:157-185)
+ * qkv: [B, hw, 384] bf16 (q already soft-maxed by the QKV epilogue).  Pass 1 reduces, per (image, head),
+ * the k-softmax over all pixels and ctx[d,e] = sum_n softmax_n(k)[d,n] v[e,n] / hw into partials; pass 2
+ * merges them and folds ctx into the to_out weight: weff[b][c][h*32+d] = sum_e Wout[c][h*32+e] ctx[b,h,d,e]
+ * (bf16, the per-image weight of the following 1x1 conv plan). */
+int dac_linattn_context(const void* qkv, int32_t B, int32_t hw, int32_t nchunks, float* partial /*[B,4,nchunks,32*34]*/,
+                        dac_stream_t stream);
+int dac_linattn_fold(const float* partial, int32_t B, int32_t hw, int32_t nchunks, const float* w_out /*[C,128] fp32*/,
+                     int32_t C, int32_t c_pad, void* weff /*[B][c_pad][128] bf16*/, dac_stream_t stream);
+
+/* ------------------------------------------------------------------ softmax attention
+ * qkv: [B, n, 3*heads*d] bf16 packed (q | k | v along channels), out [B, n, heads*d] bf16.
+ * d = 32 (UNet self-attention, ATT:178-192) or 64 (ViT, TR:219-230); scale = d^-0.5. */
+int dac_attention(const void* qkv, void* out, int32_t B, int32_t n, int32_t heads, int32_t d, dac_stream_t stream);
+
+/* ------------------------------------------------------------------ DA-CLIP encoder helpers (TR:507-555)
+ * patchify: image [B,3,S,S] fp32 NCHW -> [B*g*g, 3*p*p] bf16 rows (k = c*p*p + py*p + px, conv1 weight order). */
+int dac_vit_patchify(const float* image, void* out, int32_t B, int32_t S, int32_t p, dac_stream_t stream);
+/* tokens[b,0,:] = cls + pos[0]; tokens[b,1+i,:] = patch[b,i,:] + pos[1+i]; then ln_pre -> out bf16 [B,L,w]. */
+int dac_vit_embed(const void* patch_emb, const float* cls, const float* pos, const float* ln_w, const float* ln_b,
+                  void* out, int32_t B, int32_t L, int32_t w, float eps, dac_stream_t stream);
+/* pooled[b] = ln_post(x[b,0,:]) @ proj  -> fp32 [B, e] */
+int dac_vit_pool(const void* x, int32_t B, int32_t L, int32_t w, const float* ln_w, const float* ln_b, float eps,
+                 const float* proj /*[w,e]*/, int32_t e, float* out, dac_stream_t stream);
+/* Degradation-type argmax (da-clip/src/evaluate_daclip.py:46-47,79-81): argmax_j 100*cos(degra[b], text[j]). */
+int dac_degradation_argmax(const float* degra, const float* text, int32_t B, int32_t e, int32_t classes,
+                           float* logits /*[B,classes] or NULL*/, int64_t* argmax, dac_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DAC_B200_H */

@@ -1,0 +1,407 @@
+"""GPU parity tests, kernel by kernel, through the C ABI (daclip_b200.ops -> libdac_b200.so).
+
+Checker: plain fp32 PyTorch ops (TF32 disabled) / the functional oracle in oracle/, on the same seeded
+inputs.  Tolerances: SDE updates are bit-exact (fp32, reference operation order); bf16 tensor-core layers are
+compared on bf16-rounded inputs with fp32 accumulation, so the only differences are accumulation order and the
+final bf16 rounding of the output: |err| <= 2^-8 * max(1, |ref|) + small absolute slack.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def bf(x):
+    return x.to(torch.bfloat16)
+
+
+def nhwc(x):  # NCHW fp32 -> NHWC bf16
+    return bf(x.permute(0, 2, 3, 1)).contiguous()
+
+
+def nchw(x):  # NHWC bf16 -> NCHW fp32
+    return x.float().permute(0, 3, 1, 2).contiguous()
+
+
+def assert_close_bf16(got, ref, name, rel=2 ** -7, abs_=2e-3):
+    got, ref = got.float(), ref.float()
+    assert got.shape == ref.shape, f"{name}: shape {tuple(got.shape)} vs {tuple(ref.shape)}"
+    err = (got - ref).abs()
+    tol = rel * ref.abs() + abs_ * max(1.0, ref.abs().max().item())
+    bad = (err > tol).sum().item()
+    assert bad == 0 and torch.isfinite(got).all(), (
+        f"{name}: {bad}/{err.numel()} elements out of tolerance, max err {err.max().item():.4g} "
+        f"(ref max {ref.abs().max().item():.4g})")
+
+
+@pytest.fixture(scope="module")
+def ops(cuda):
+    from daclip_b200 import lib, ops as o
+    lib.load()
+    return o
+
+
+def rnd(gen, *shape, scale=1.0):
+    return (torch.randn(*shape, generator=gen, device="cuda") * scale)
+
+
+@pytest.fixture()
+def gen(cuda):
+    g = torch.Generator(device="cuda")
+    g.manual_seed(1234)
+    return g
+
+
+# ---------------------------------------------------------------------------------------------- conv / linear
+@pytest.mark.parametrize("tokens,cin,cout", [(1000, 64, 64), (333, 128, 256), (4096, 512, 1536), (50 * 7, 768, 768)])
+def test_linear_plain(ops, gen, tokens, cin, cout):
+    from daclip_b200 import lib as L
+    x = bf(rnd(gen, 1, 1, tokens, cin))
+    w = rnd(gen, cout, cin, scale=cin ** -0.5)
+    b = rnd(gen, cout)
+    pw = ops.pack_linear(w)
+    out = torch.full((1, 1, tokens, cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+    plan = ops.ConvPlan(x, cin, pw, out, B=1, H=1, W=tokens, bias=b)
+    plan.run()
+    torch.cuda.synchronize()
+    ref = F.linear(x.float(), bf(w).float(), b)
+    assert_close_bf16(out, ref, f"linear {tokens}x{cin}->{cout} {plan.info()}")
+
+
+@pytest.mark.parametrize("B,H,W,cin,cout,tile", [
+    (2, 32, 32, 64, 64, None), (1, 16, 48, 128, 128, None), (2, 64, 64, 64, 64, (8, 16)),
+    (1, 256, 256, 64, 64, None), (2, 32, 32, 512, 512, None), (1, 6, 6, 256, 512, None)])
+def test_conv3x3_film_silu(ops, gen, B, H, W, cin, cout, tile):
+    from daclip_b200 import lib as L
+    x = rnd(gen, B, cin, H, W)
+    w = rnd(gen, cout, cin, 3, 3, scale=(9 * cin) ** -0.5)
+    film = rnd(gen, B, 2 * cout + 8, scale=0.5)
+    xh = nhwc(x)
+    out = torch.full((B, H, W, cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+    plan = ops.ConvPlan(xh, cin, ops.pack_conv(w), out, B=B, H=H, W=W, act=L.ACT_SILU, film=film, film_off=8,
+                        tile=tile)
+    plan.run()
+    torch.cuda.synchronize()
+    y = F.conv2d(nchw(xh), bf(w).float(), padding=1)
+    sc = film[:, 8:8 + cout, None, None]
+    sh = film[:, 8 + cout:8 + 2 * cout, None, None]
+    ref = F.silu(y * (sc + 1) + sh)
+    assert_close_bf16(nchw(out), ref, f"conv3x3 {B}x{H}x{W} {cin}->{cout} {plan.info()}")
+
+
+def test_conv3x3_concat_residual(ops, gen):
+    from daclip_b200 import lib as L
+    B, H, W, c0, c1, cout = 3, 16, 16, 64, 128, 128
+    a, s = rnd(gen, B, c0, H, W), rnd(gen, B, c1, H, W)
+    w = rnd(gen, cout, c0 + c1, 3, 3, scale=(9 * (c0 + c1)) ** -0.5)
+    r = rnd(gen, B, cout, H, W)
+    ah, sh_, rh = nhwc(a), nhwc(s), nhwc(r)
+    out = torch.zeros(B, H, W, cout, device="cuda", dtype=torch.bfloat16)
+    plan = ops.ConvPlan(ah, c0, ops.pack_conv(w), out, B=B, H=H, W=W, src1=sh_, c1=c1, act=L.ACT_SILU, res=rh)
+    plan.run()
+    torch.cuda.synchronize()
+    ref = F.silu(F.conv2d(torch.cat([nchw(ah), nchw(sh_)], 1), bf(w).float(), padding=1)) + nchw(rh)
+    assert_close_bf16(nchw(out), ref, "conv3x3 concat+res")
+
+
+def test_conv_channel_slices(ops, gen):
+    """Source read as a channel sub-range of a wider buffer; output written into a channel sub-range."""
+    B, H, W = 2, 8, 16
+    big = bf(rnd(gen, B, H, W, 384))
+    w = rnd(gen, 64, 128, scale=128 ** -0.5)
+    out = torch.zeros(B, H, W, 192, device="cuda", dtype=torch.bfloat16)
+    src = big[..., 128:]                      # view: data_ptr offset, pixel pitch stays 384
+    plan = ops.ConvPlan(src, 128, ops.pack_linear(w), out, B=B, H=H, W=W, ld0=384, out_coff=64)
+    plan.run()
+    torch.cuda.synchronize()
+    ref = F.linear(big[..., 128:256].float(), bf(w).float())
+    assert_close_bf16(out[..., 64:128], ref, "channel-slice linear")
+    assert out[..., :64].abs().max() == 0 and out[..., 128:].abs().max() == 0
+
+
+@pytest.mark.parametrize("B,H,W,cin,cout", [(2, 32, 32, 64, 128), (1, 64, 64, 128, 256), (1, 256, 256, 64, 64)])
+def test_downsample_4x4_s2(ops, gen, B, H, W, cin, cout):
+    x = rnd(gen, B, cin, H, W)
+    w = rnd(gen, cout, cin, 4, 4, scale=(16 * cin) ** -0.5)
+    b = rnd(gen, cout)
+    xh = nhwc(x)
+    out = torch.full((B, H // 2, W // 2, cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+    plan = ops.ConvPlan(xh, cin, ops.pack_conv(w, stride=2, pad=1), out, B=B, H=H, W=W, bias=b)
+    plan.run()
+    torch.cuda.synchronize()
+    ref = F.conv2d(nchw(xh), bf(w).float(), b, stride=2, padding=1)
+    assert_close_bf16(nchw(out), ref, f"downsample {H}x{W} {cin}->{cout}")
+
+
+@pytest.mark.parametrize("B,H,W,cin,cout", [(2, 16, 16, 128, 64), (1, 32, 32, 512, 256), (1, 3, 5, 64, 64)])
+def test_upsample_conv_folded(ops, gen, B, H, W, cin, cout):
+    x = rnd(gen, B, cin, H, W)
+    w = rnd(gen, cout, cin, 3, 3, scale=(9 * cin) ** -0.5)
+    b = rnd(gen, cout)
+    xh = nhwc(x)
+    out = torch.full((B, 2 * H, 2 * W, cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+    plan = ops.ConvPlan(xh, cin, ops.pack_upsample_conv(w), out, B=B, H=H, W=W, bias=b)
+    plan.run()
+    torch.cuda.synchronize()
+    ref = F.conv2d(F.interpolate(nchw(xh), scale_factor=2, mode="nearest"), bf(w).float(), b, padding=1)
+    # folded taps are sums of up to 4 bf16-rounded-once weights: slightly looser than a plain conv
+    assert_close_bf16(nchw(out), ref, f"upsample-conv {H}x{W} {cin}->{cout}", rel=2 ** -6, abs_=6e-3)
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 32, 32), (1, 24, 40), (1, 256, 256)])
+def test_stem_and_init_conv(ops, gen, B, H, W):
+    xt, cond = rnd(gen, B, 3, H, W), rnd(gen, B, 3, H, W)
+    w = rnd(gen, 64, 6, 7, 7, scale=(49 * 6) ** -0.5)
+    Hp, Wp = -(-H // 16) * 16, -(-W // 16) * 16
+    stem = torch.full((B, Hp, Wp, 64), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.stem_input(xt, cond, stem, H, W)
+    out = torch.full((B, Hp, Wp, 64), float("nan"), device="cuda", dtype=torch.bfloat16)
+    plan = ops.ConvPlan(stem, 64, ops.pack_stem(w), out, B=B, H=Hp, W=Wp)
+    plan.run()
+    torch.cuda.synchronize()
+    x = torch.cat([xt - cond, cond], 1)
+    x = F.pad(x, (0, Wp - W, 0, Hp - H), mode="reflect") if (Hp > H or Wp > W) else x
+    ref = F.conv2d(bf(x).float(), bf(w).float(), padding=3)
+    assert_close_bf16(nchw(out), ref, f"init_conv {H}x{W}")
+
+
+def test_final_conv_nchw_crop(ops, gen):
+    B, H, W, Hp, Wp = 2, 24, 40, 32, 48
+    x = rnd(gen, B, 64, Hp, Wp)
+    w, b = rnd(gen, 3, 64, 3, 3, scale=(9 * 64) ** -0.5), rnd(gen, 3)
+    xh = nhwc(x)
+    out = torch.full((B, 3, H, W), float("nan"), device="cuda", dtype=torch.float32)
+    plan = ops.ConvPlan(xh, 64, ops.pack_conv(w), None, B=B, H=Hp, W=Wp, bias=b, out_nchw=out)
+    plan.run()
+    torch.cuda.synchronize()
+    ref = F.conv2d(nchw(xh), bf(w).float(), b, padding=1)[..., :H, :W]
+    assert (out - ref).abs().max().item() < 1e-3, (out - ref).abs().max().item()
+
+
+def test_epilogue_ln_residual(ops, gen):
+    from daclip_b200 import lib as L
+    B, H, W, cin, cout = 2, 16, 32, 128, 128
+    x, r = bf(rnd(gen, B, H, W, cin)), bf(rnd(gen, B, H, W, cout))
+    w, b, g = rnd(gen, cout, cin, scale=cin ** -0.5), rnd(gen, cout), 1 + 0.1 * rnd(gen, cout)
+    out = torch.zeros(B, H, W, cout, device="cuda", dtype=torch.bfloat16)
+    plan = ops.ConvPlan(x, cin, ops.pack_linear(w), out, B=B, H=H, W=W, epi=L.EPI_LN, bias=b, ln_g=g, res=r)
+    plan.run()
+    torch.cuda.synchronize()
+    y = F.linear(x.float(), bf(w).float(), b)
+    ref = (y - y.mean(-1, keepdim=True)) * torch.rsqrt(y.var(-1, unbiased=False, keepdim=True) + 1e-5) * g + r.float()
+    assert_close_bf16(out, ref, "LN epilogue")
+
+
+def test_epilogue_geglu(ops, gen):
+    from daclip_b200 import lib as L
+    B, n, c = 2, 256, 256
+    x = bf(rnd(gen, B, 1, n, c))
+    w, b = rnd(gen, 8 * c, c, scale=c ** -0.5), rnd(gen, 8 * c)
+    pw, bperm = ops.pack_geglu(w, b)
+    out = torch.zeros(B, 1, n, 4 * c, device="cuda", dtype=torch.bfloat16)
+    plan = ops.ConvPlan(x, c, pw, out, B=B, H=1, W=n, epi=L.EPI_GEGLU, bias=bperm, block_n=256)
+    plan.run()
+    torch.cuda.synchronize()
+    y = F.linear(x.float(), bf(w).float(), b)
+    val, gate = y.chunk(2, dim=-1)
+    assert_close_bf16(out, val * F.gelu(gate), "GEGLU epilogue")
+
+
+def test_epilogue_bias_img_two_residuals_gelu(ops, gen):
+    from daclip_b200 import lib as L
+    B, n, c = 3, 200, 256
+    x, r1, r2 = bf(rnd(gen, B, 1, n, c)), bf(rnd(gen, B, 1, n, c)), bf(rnd(gen, B, 1, n, c))
+    w, b, bi = rnd(gen, c, c, scale=c ** -0.5), rnd(gen, c), rnd(gen, B, c)
+    out = torch.zeros(B, 1, n, c, device="cuda", dtype=torch.bfloat16)
+    plan = ops.ConvPlan(x, c, ops.pack_linear(w), out, B=B, H=1, W=n, bias=b, bias_img=bi, act=L.ACT_GELU,
+                        res=r1, res2=r2)
+    plan.run()
+    torch.cuda.synchronize()
+    ref = F.gelu(F.linear(x.float(), bf(w).float(), b) + bi[:, None, None, :]) + r1.float() + r2.float()
+    assert_close_bf16(out, ref, "bias_img + gelu + 2 residuals")
+
+
+# ---------------------------------------------------------------------------------------------- LinearAttention
+@pytest.mark.parametrize("B,H,W,C", [(2, 32, 32, 64), (1, 64, 48, 128), (2, 16, 16, 256)])
+def test_linear_attention_block(ops, gen, B, H, W, C):
+    """to_qkv (+q softmax) -> context reduce -> fold into to_out -> GEMM + LN + residual, vs the oracle."""
+    from daclip_b200 import lib as L
+    from oracle import unet_oracle as O
+    hw = H * W
+    x = rnd(gen, B, C, H, W)
+    sd = {"to_qkv.weight": rnd(gen, 384, C, 1, 1, scale=C ** -0.5),
+          "to_out.0.weight": rnd(gen, C, 128, 1, 1, scale=128 ** -0.5 * 8),
+          "to_out.0.bias": rnd(gen, C, scale=0.1), "to_out.1.g": (1 + 0.1 * rnd(gen, 1, C, 1, 1))}
+    xh = nhwc(x)
+    sdr = dict(sd)
+    sdr["to_qkv.weight"] = bf(sd["to_qkv.weight"]).float()
+    ref = O.linear_attention(sdr, "", nchw(xh)) + nchw(xh)
+
+    qkv = torch.zeros(B, H, W, 384, device="cuda", dtype=torch.bfloat16)
+    p1 = ops.ConvPlan(xh, C, ops.pack_linear(sd["to_qkv.weight"]), qkv, B=B, H=H, W=W, epi=L.EPI_QKV, block_n=128)
+    nchunks = 8
+    partial = torch.zeros(B, 4, nchunks, 32 * 34, device="cuda")
+    c_pad = ops.choose_block_n(C)[1]
+    weff = torch.zeros(B, c_pad, 128, device="cuda", dtype=torch.bfloat16)
+    out = torch.zeros(B, H, W, C, device="cuda", dtype=torch.bfloat16)
+    pw_out = ops.pack_linear(sd["to_out.0.weight"])
+    p2 = ops.ConvPlan(qkv, 128, pw_out, out, B=B, H=H, W=W, epi=L.EPI_LN, bias=sd["to_out.0.bias"],
+                      ln_g=sd["to_out.1.g"].reshape(-1).contiguous(), res=xh, per_image_w=True, weight_override=weff)
+    p1.run()
+    ops.linattn_context(qkv, B, hw, nchunks, partial)
+    ops.linattn_fold(partial, B, hw, nchunks, sd["to_out.0.weight"].reshape(C, 128).contiguous(), C, c_pad, weff)
+    p2.run()
+    torch.cuda.synchronize()
+    # q check (softmax over head channels * scale)
+    q_ref = F.conv2d(nchw(xh), sdr["to_qkv.weight"])[:, :128].reshape(B, 4, 32, hw).softmax(2) * 32 ** -0.5
+    q_got = qkv[..., :128].float().reshape(B, hw, 4, 32).permute(0, 2, 3, 1)
+    assert_close_bf16(q_got, q_ref, "q softmax epilogue")
+    assert_close_bf16(nchw(out), ref, f"linear attention {H}x{W} C={C}", rel=2 ** -5, abs_=2e-2)
+
+
+# ---------------------------------------------------------------------------------------------- attention
+@pytest.mark.parametrize("B,n,heads", [(2, 1024, 8), (1, 4096, 16), (1, 200, 4)])
+def test_flash_attention_d32(ops, gen, B, n, heads):
+    d = 32
+    qkv = bf(rnd(gen, B, n, 3 * heads * d))
+    out = torch.zeros(B, n, heads * d, device="cuda", dtype=torch.bfloat16)
+    ops.attention(qkv, out, B, n, heads, d)
+    torch.cuda.synchronize()
+    q, k, v = [t.reshape(B, n, heads, d).transpose(1, 2) for t in qkv.float().chunk(3, dim=-1)]
+    ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, n, heads * d)
+    assert_close_bf16(out, ref, f"flash d32 n={n}", rel=2 ** -6, abs_=4e-3)
+
+
+def test_small_attention_d64(ops, gen):
+    B, n, heads, d = 3, 50, 12, 64
+    qkv = bf(rnd(gen, B, n, 3 * heads * d))
+    out = torch.zeros(B, n, heads * d, device="cuda", dtype=torch.bfloat16)
+    ops.attention(qkv, out, B, n, heads, d)
+    torch.cuda.synchronize()
+    q, k, v = [t.reshape(B, n, heads, d).transpose(1, 2) for t in qkv.float().chunk(3, dim=-1)]
+    ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, n, heads * d)
+    assert_close_bf16(out, ref, "small attn d64")
+
+
+# ---------------------------------------------------------------------------------------------- norms
+@pytest.mark.parametrize("rows,c,affine", [(1000, 64, "g"), (4096, 512, "wb"), (350, 768, "wb")])
+def test_layernorm_rows(ops, gen, rows, c, affine):
+    x = bf(rnd(gen, rows, c) * 2 + 0.5)
+    w = 1 + 0.1 * rnd(gen, c)
+    b = rnd(gen, c) if affine == "wb" else None
+    out = torch.zeros_like(x)
+    ops.layernorm_rows(x, out, rows, c, w, b, 1e-5)
+    torch.cuda.synchronize()
+    ref = F.layer_norm(x.float(), (c,), w, b, 1e-5)
+    assert_close_bf16(out, ref, "layernorm rows")
+
+
+@pytest.mark.parametrize("B,hw,c", [(2, 1024, 256), (3, 4096, 512), (1, 36, 256)])
+def test_groupnorm(ops, gen, B, hw, c):
+    x = bf(rnd(gen, B, hw, c) + 0.3)
+    w, b = 1 + 0.1 * rnd(gen, c), rnd(gen, c)
+    out, stats = torch.zeros_like(x), torch.zeros(B * 64, device="cuda")
+    ops.groupnorm_nhwc(x, out, B, hw, c, w, b, stats)
+    torch.cuda.synchronize()
+    ref = F.group_norm(x.float().transpose(1, 2), 32, w, b, 1e-6).transpose(1, 2)
+    assert_close_bf16(out, ref, "groupnorm")
+
+
+# ---------------------------------------------------------------------------------------------- SDE updates
+@pytest.mark.parametrize("mode", ["sde", "posterior", "ode"])
+def test_sde_step_bit_exact(cuda, mode):
+    from daclip_b200.sde import IRSDE
+    from oracle import sde_oracle as S
+    sched = S.Schedule(50, 100, "cosine", 0.005)
+    sde = IRSDE(50, T=100, schedule="cosine", eps=0.005, device=cuda)
+    g = torch.Generator().manual_seed(7)
+    shape = (2, 3, 37, 53)  # odd sizes: exercises the scalar tail
+    x, mu, n, e = [torch.randn(shape, generator=g) for _ in range(4)]
+    sde.set_mu(mu.cuda())
+    for t in (100, 57, 2, 1):
+        if mode == "sde":
+            ref = S.sde_step(sched, x, mu, n, e, t)
+            got = sde.reverse_sde_step(x.cuda(), sde.get_score_from_noise(n.cuda(), t), t, eps=e.cuda())
+        elif mode == "posterior":
+            ref = S.posterior_step(sched, x, mu, n, e, t)
+            got = sde.reverse_posterior_step(x.cuda(), n.cuda(), t, eps=e.cuda())
+        else:
+            ref = S.ode_step(sched, x, mu, n, t)
+            got = sde.reverse_ode_step(x.cuda(), sde.get_score_from_noise(n.cuda(), t), t)
+        diff = (got.cpu() - ref).abs().max().item()
+        assert diff <= 2e-7 * max(1.0, ref.abs().max().item()), f"{mode} t={t}: max diff {diff}"
+
+
+# ---------------------------------------------------------------------------------------------- conditioning
+def test_time_film_and_cross_vec(ops, gen):
+    from daclip_b200 import lib as L
+    from oracle import unet_oracle as O
+    B, F_ = 3, 1000
+    sd = {"time_mlp.1.weight": rnd(gen, 256, 64, scale=0.2), "time_mlp.1.bias": rnd(gen, 256, scale=0.1),
+          "time_mlp.3.weight": rnd(gen, 256, 256, scale=0.1), "time_mlp.3.bias": rnd(gen, 256, scale=0.1),
+          "text_mlp.0.weight": rnd(gen, 256, 512, scale=0.05), "text_mlp.0.bias": rnd(gen, 256, scale=0.1),
+          "text_mlp.2.weight": rnd(gen, 256, 256, scale=0.1), "text_mlp.2.bias": rnd(gen, 256, scale=0.1),
+          "prompt": torch.rand(1, 256, generator=gen, device="cuda"),
+          "prompt_mlp.weight": rnd(gen, 256, 256, scale=0.1), "prompt_mlp.bias": rnd(gen, 256, scale=0.1)}
+    fw, fb = rnd(gen, F_, 256, scale=0.1), rnd(gen, F_, scale=0.1)
+    ctx = rnd(gen, B, 512)
+    ew = L.EmbedWeights()
+    for name, key in [("time_w1", "time_mlp.1.weight"), ("time_b1", "time_mlp.1.bias"), ("time_w2", "time_mlp.3.weight"),
+                      ("time_b2", "time_mlp.3.bias"), ("text_w1", "text_mlp.0.weight"), ("text_b1", "text_mlp.0.bias"),
+                      ("text_w2", "text_mlp.2.weight"), ("text_b2", "text_mlp.2.bias"), ("prompt", "prompt"),
+                      ("prompt_w", "prompt_mlp.weight"), ("prompt_b", "prompt_mlp.bias")]:
+        setattr(ew, name, sd[key].data_ptr())
+    ew.film_w, ew.film_b = fw.data_ptr(), fb.data_ptr()
+    ew.nf, ew.time_dim, ew.ctx_dim, ew.F = 64, 256, 512, F_
+    temb, film = torch.zeros(B, 256, device="cuda"), torch.zeros(B, F_, device="cuda")
+    tdev = torch.zeros(1, device="cuda")
+    for t in (100.0, 37.0, 1.0):
+        tdev.fill_(t)
+        ops.time_film(ew, tdev, ctx, B, temb, film)
+        torch.cuda.synchronize()
+        te = O.time_embedding(sd, torch.tensor([t], device="cuda"), 64) + O.prompt_embedding(sd, ctx)
+        ref = F.linear(F.silu(te), fw, fb)
+        assert (film - ref).abs().max().item() < 2e-4 * max(1.0, ref.abs().max().item()), (film - ref).abs().max()
+    w1, w2, b2 = rnd(gen, 256, 512, scale=0.05), rnd(gen, 256, 256, scale=0.1), rnd(gen, 256)
+    y = torch.zeros(B, 256, device="cuda")
+    ops.two_linear(ctx, w1, w2, b2, y)
+    torch.cuda.synchronize()
+    ref = F.linear(F.linear(ctx, w1), w2, b2)
+    assert (y - ref).abs().max().item() < 1e-4 * max(1.0, ref.abs().max().item())
+
+
+# ---------------------------------------------------------------------------------------------- ViT glue
+def test_vit_glue(ops, gen):
+    B, S, p, w, e = 3, 224, 32, 768, 512
+    g = S // p
+    img = rnd(gen, B, 3, S, S)
+    patches = torch.zeros(B * g * g, 3 * p * p, device="cuda", dtype=torch.bfloat16)
+    ops.vit_patchify(img, patches, B, S, p)
+    torch.cuda.synchronize()
+    ref = F.unfold(img, kernel_size=p, stride=p).transpose(1, 2).reshape(B * g * g, 3 * p * p)
+    assert torch.equal(patches, bf(ref))
+    L_ = g * g + 1
+    pe = bf(rnd(gen, B, g * g, w))
+    cls, pos = rnd(gen, w), rnd(gen, L_, w)
+    lw, lb = 1 + 0.1 * rnd(gen, w), rnd(gen, w)
+    tok = torch.zeros(B, L_, w, device="cuda", dtype=torch.bfloat16)
+    ops.vit_embed(pe, cls, pos, lw, lb, tok, B, L_, w)
+    torch.cuda.synchronize()
+    x = torch.cat([cls.expand(B, 1, w), pe.float()], 1) + pos
+    assert_close_bf16(tok, F.layer_norm(x, (w,), lw, lb, 1e-5), "vit embed")
+    proj = rnd(gen, w, e, scale=w ** -0.5)
+    pooled = torch.zeros(B, e, device="cuda")
+    ops.vit_pool(tok, B, L_, w, lw, lb, proj, pooled)
+    torch.cuda.synchronize()
+    ref = F.layer_norm(tok[:, 0].float(), (w,), lw, lb, 1e-5) @ proj
+    assert (pooled - ref).abs().max().item() < 1e-3
+    text = rnd(gen, 10, e)
+    logits, am = torch.zeros(B, 10, device="cuda"), torch.zeros(B, dtype=torch.int64, device="cuda")
+    ops.degradation_argmax(pooled, text, logits, am)
+    torch.cuda.synchronize()
+    from oracle import daclip_oracle as D
+    assert torch.equal(am, D.degradation_argmax(pooled, text))
+    assert (logits - D.degradation_logits(pooled, text)).abs().max().item() < 1e-3
