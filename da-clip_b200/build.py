@@ -25,7 +25,9 @@ def _stale():
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, debug=False):
+    if debug:
+        return _build_debug()
     if not force and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -38,6 +40,18 @@ def build(force=False, verbose=False):
     if verbose:
         sys.stderr.write(r.stderr)
     return LIB
+
+
+def _build_debug():
+    """libdac_b200_debug.so: same sources with -DDAC_DEBUG (device printf in the conv kernel)."""
+    out = LIB.replace(".so", "_debug.so")
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + ["-DDAC_DEBUG"] + [os.path.join(CSRC, f) for f in SOURCES] + ["-o", out]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("nvcc failed building the debug library")
+    return out
 
 
 if __name__ == "__main__":

@@ -29,6 +29,11 @@ int check_launch(const char* what) {
 }  // namespace dac
 
 extern "C" int dac_version(void) { return 100; }
+extern "C" int dac_abi_sizes(int32_t* conv_desc_bytes, int32_t* embed_weights_bytes) {
+  if (conv_desc_bytes) *conv_desc_bytes = (int32_t)sizeof(dac_conv_desc);
+  if (embed_weights_bytes) *embed_weights_bytes = (int32_t)sizeof(dac_embed_weights);
+  return 0;
+}
 extern "C" const char* dac_last_error(void) { return dac::g_err; }
 extern "C" int64_t dac_launch_count(void) { return dac::g_launches.load(); }
 extern "C" void dac_reset_launch_count(void) { dac::g_launches.store(0); }

@@ -309,6 +309,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+#ifdef DAC_DEBUG
+  if (threadIdx.x == 0 && blockIdx.x == 0)
+    printf("[conv] tiles=%d k_steps=%d stages=%d block_n=%d tmem_base=%08x smem=%p OH=%d OW=%d out=%p cout=%d epi=%d\n",
+           total_tiles, k_steps, p.stages, p.block_n, tmem_base, smem, p.OH, p.OW, p.out, p.cout, p.epi);
+#endif
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -383,6 +388,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       const TileCoord t = decode_tile(p, tile);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
+#ifdef DAC_DEBUG
+      if (threadIdx.x == 64 && blockIdx.x == 0) printf("[conv] epilogue tile %d acc %d\n", tile, acc);
+#endif
       const uint32_t tmem_acc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kAccStride;
       if (p.block_n & 31)
         epilogue_tile<16>(p, t, tmem_acc, row);

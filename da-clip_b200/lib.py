@@ -54,6 +54,7 @@ SYMBOLS = {
     "dac_last_error": (C.c_char_p, []),
     "dac_launch_count": (_i64, []),
     "dac_reset_launch_count": (None, []),
+    "dac_abi_sizes": (C.c_int, [C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "dac_sde_step": (C.c_int, [C.c_int, _p, _p, _p, _p, _p, _i64, C.POINTER(C.c_float), _p]),
     "dac_noise_state": (C.c_int, [_p, _p, _p, _i64, _f, _p]),
     "dac_unet_stem_input": (C.c_int, [_p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _p]),
@@ -85,6 +86,8 @@ def load(build_if_missing=True):
     if _lib is not None:
         return _lib
     path = _build.LIB
+    if os.environ.get("DAC_DEBUG") == "1":
+        path = _build.build(debug=True)
     if build_if_missing and not os.path.exists(path):
         _build.build()
     if not os.path.exists(path):
@@ -94,6 +97,11 @@ def load(build_if_missing=True):
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
+    a, b = C.c_int32(), C.c_int32()
+    lib.dac_abi_sizes(C.byref(a), C.byref(b))
+    if (a.value, b.value) != (C.sizeof(ConvDesc), C.sizeof(EmbedWeights)):
+        raise DacError(f"{path} is stale: struct sizes {a.value},{b.value} != binding "
+                       f"{C.sizeof(ConvDesc)},{C.sizeof(EmbedWeights)}; rebuild with `python da-clip_b200/build.py --force`")
     _lib = lib
     return lib
 

@@ -32,6 +32,8 @@ const char* dac_last_error(void);
 /* Number of kernels this library has launched since load (or since the last reset). */
 int64_t dac_launch_count(void);
 void dac_reset_launch_count(void);
+/* sizeof(dac_conv_desc) / sizeof(dac_embed_weights) as compiled: lets a binding detect a stale library. */
+int dac_abi_sizes(int32_t* conv_desc_bytes, int32_t* embed_weights_bytes);
 
 /* ------------------------------------------------------------------ SDE updates (fp32, HBM-bound)
  * x, mu, net, eps, out: [n] fp32 (any layout, elementwise).  out may alias x.
