@@ -1,0 +1,141 @@
+"""Seeded synthetic weights and inputs in the reference's state-dict layouts.
+
+No pretrained checkpoint exists offline (options/test.yml:43-44 point at absent files), so parity and
+throughput use random weights that every party can regenerate from a seed: the golden generator (which loads
+them into the REFERENCE modules), the oracle, the tests and bench.py.  Values come from a CPU torch.Generator
+in state-dict key order, so they are identical on every host with the same torch build.  All-zero-initialised
+reference modules (ControlTransformer.zero_modules, SpatialTransformer.proj_out) get non-zero values on
+purpose - otherwise the control path and every transformer block would be numerically dead and untested.
+"""
+import math
+
+import torch
+
+
+def _is_gain(name):
+    parts = name.split(".")
+    last, parent = parts[-1], (parts[-2] if len(parts) > 1 else "")
+    return last == "g" or (last == "weight" and (parent.startswith("norm") or parent.startswith("ln_")))
+
+
+def _fill(name, t, g):
+    shape = t.shape
+    if _is_gain(name):
+        return 1.0 + 0.1 * torch.randn(shape, generator=g)
+    if name == "prompt":
+        return torch.rand(shape, generator=g)
+    if name.endswith("bias") or name.endswith("in_proj_bias"):
+        return 0.05 * torch.randn(shape, generator=g)
+    if name.endswith(("class_embedding", "positional_embedding")):
+        return shape[-1] ** -0.5 * torch.randn(shape, generator=g)
+    if name.endswith("proj") and len(shape) == 2:          # ViT output projection [width, embed]
+        return shape[0] ** -0.5 * torch.randn(shape, generator=g)
+    if name == "logit_scale" or len(shape) == 0:
+        return torch.tensor(math.log(1 / 0.07))
+    fan_in = 1
+    for s in shape[1:]:
+        fan_in *= s
+    return fan_in ** -0.5 * torch.randn(shape, generator=g)
+
+
+def randomize_state_dict(shapes, seed):
+    """shapes: ordered {key: shape-or-tensor}.  Returns {key: fp32 CPU tensor}."""
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+    for k, v in shapes.items():
+        t = v if torch.is_tensor(v) else torch.empty(v)
+        if not t.is_floating_point():
+            out[k] = t.clone()
+            continue
+        out[k] = _fill(k, t, g).to(torch.float32).reshape(t.shape)
+    return out
+
+
+def unet_state_dict(seed=0, stabilize=True, **ctor):
+    """Synthetic ConditionalUNet weights (test.yml setting by default) in the reference key order."""
+    from .unet import ConditionalUNet
+    kw = dict(in_nc=3, out_nc=3, nf=64, ch_mult=[1, 2, 4, 8], context_dim=512, use_degra_context=True,
+              use_image_context=True)
+    kw.update(ctor)
+    m = ConditionalUNet(**kw)
+    sd = randomize_state_dict({k: v.shape for k, v in m.state_dict().items()}, seed)
+    if stabilize:
+        _add_denoiser_path(sd, kw["nf"])
+    return sd, kw
+
+
+def _add_denoiser_path(sd, nf, gain=5.1, random_scale=0.05):
+    """Make the random network behave like a (crude) denoiser so that T-step trajectories stay O(1).
+
+    With an untrained net the reverse process EXPANDS x - mu by 1/eps = 200x over T steps (it inverts the
+    forward contraction), which turns any end-to-end tolerance into noise.  The ideal prediction for x0 = mu is
+    n = (x - mu) / sigma_bar_t; sigma_bar_t ~ 0.196 for most steps, so a fixed linear path
+    n_lin = gain * (xt - cond), gain = 1/0.196, cancels the expansion.  The architecture has such a path:
+    init_conv -> (concat x_) -> final_res_block.res_conv -> final_conv.  The randomly initialised remainder of
+    the network still contributes ~0.15 std on top, through every layer."""
+    w = sd["init_conv.weight"]
+    w[0:3] = 0
+    for c in range(3):
+        w[c, c, 3, 3] = 1.0                               # x_[c] = (xt - cond)[c]
+    r = sd["final_res_block.res_conv.weight"]
+    r[0:3] = 0
+    for c in range(3):
+        r[c, nf + c, 0, 0] = 1.0                          # skip[c] = x_[c]
+    sd["final_res_block.block2.proj.weight"][0:3] = 0     # SiLU(0) = 0: nothing else lands on channels 0..2
+    sd["final_conv.weight"] *= random_scale
+    sd["final_conv.bias"] *= random_scale
+    f = sd["final_conv.weight"]
+    f[:, 0:3] = 0
+    for c in range(3):
+        f[c, c, 1, 1] = gain
+
+
+def vit_tower_shapes(prefix, width=768, layers=12, patch=32, grid=7, embed=512, control=False):
+    s = {}
+    s[prefix + "class_embedding"] = (width,)
+    s[prefix + "positional_embedding"] = (grid * grid + 1, width)
+    s[prefix + "proj"] = (width, embed)
+    s[prefix + "conv1.weight"] = (width, 3, patch, patch)
+    s[prefix + "ln_pre.weight"] = (width,)
+    s[prefix + "ln_pre.bias"] = (width,)
+    tp = prefix + ("transformer.transformer." if control else "transformer.")
+    for i in range(layers):
+        b = f"{tp}resblocks.{i}."
+        s[b + "ln_1.weight"] = (width,); s[b + "ln_1.bias"] = (width,)
+        s[b + "attn.in_proj_weight"] = (3 * width, width); s[b + "attn.in_proj_bias"] = (3 * width,)
+        s[b + "attn.out_proj.weight"] = (width, width); s[b + "attn.out_proj.bias"] = (width,)
+        s[b + "ln_2.weight"] = (width,); s[b + "ln_2.bias"] = (width,)
+        s[b + "mlp.c_fc.weight"] = (4 * width, width); s[b + "mlp.c_fc.bias"] = (4 * width,)
+        s[b + "mlp.c_proj.weight"] = (width, 4 * width); s[b + "mlp.c_proj.bias"] = (width,)
+    if control:
+        for i in range(layers):
+            s[f"{prefix}transformer.zero_modules.{i}.weight"] = (width, width)
+            s[f"{prefix}transformer.zero_modules.{i}.bias"] = (width,)
+    s[prefix + "ln_post.weight"] = (width,)
+    s[prefix + "ln_post.bias"] = (width,)
+    return s
+
+
+def daclip_visual_state_dict(seed=10):
+    """Synthetic weights of the two ViT-B/32 towers used by encode_image(control=True):
+    `visual.*` (frozen CLIP tower; the reference aliases it as `clip.visual.*`) and `visual_control.*`."""
+    shapes = {}
+    shapes.update(vit_tower_shapes("visual."))
+    shapes.update(vit_tower_shapes("visual_control.", control=True))
+    sd = randomize_state_dict(shapes, seed)
+    # keep the control signal a perturbation, as a trained ControlNet-style branch would be
+    for k in sd:
+        if "zero_modules" in k:
+            sd[k] = sd[k] * 0.25
+    return sd
+
+
+def restoration_inputs(B, H, W, T=100, seed=1, ctx_dim=512):
+    """LQ image batch in [0,1], the noisy start state, per-step Gaussian draws and DA-CLIP-like contexts."""
+    g = torch.Generator().manual_seed(seed)
+    lq = torch.rand(B, 3, H, W, generator=g)
+    eps0 = torch.randn(B, 3, H, W, generator=g)
+    noise = torch.randn(T, B, 3, H, W, generator=g)
+    text_ctx = torch.randn(B, ctx_dim, generator=g)
+    image_ctx = torch.randn(B, ctx_dim, generator=g)
+    return dict(lq=lq, eps0=eps0, noise=noise, text_context=text_ctx, image_context=image_ctx)

@@ -1,0 +1,119 @@
+"""CPU tests: pin the oracle against outputs of the REFERENCE itself (tests/golden/*.pt, produced by
+oracle/gen_golden.py from /root/reference with seeded synthetic weights).  fp32 on both sides; differences are
+summation order only."""
+import os
+
+import pytest
+import torch
+
+from daclip_b200 import synthetic
+from oracle import daclip_oracle as D
+from oracle import sde_oracle as S
+from oracle import unet_oracle as O
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return torch.load(os.path.join(GOLD, "unet_sampler.pt"), weights_only=False)
+
+
+@pytest.fixture(scope="module")
+def net(gold):
+    sd, kw = synthetic.unet_state_dict(gold["weights_seed"])
+    assert kw == gold["ctor"]
+    return sd, O.UNetConfig(**kw)
+
+
+def test_schedule_known_answers(gold):
+    s = S.Schedule(50, 100, "cosine", 0.005)
+    for k in ("thetas", "sigmas", "thetas_cumsum", "sigma_bars"):
+        assert torch.equal(getattr(s, k), gold["schedule"][k]), k
+    assert torch.equal(s.dt, gold["schedule"]["dt"])
+    # SURVEY.md section 8a row A1 known answers (probed from the reference)
+    assert abs(float(s.dt) - 0.104093805) < 1e-8
+    assert abs(float(s.thetas[1]) - 0.00169456005) < 1e-10
+    assert abs(float(s.thetas[100]) - 0.999766588) < 1e-7
+    assert abs(float(s.sigmas[100]) - 0.277264416) < 1e-7
+    assert abs(float(s.sigma_bars[1]) - 0.00368262362) < 1e-9
+    assert abs(float(s.sigma_bars[100]) - 0.196075976) < 1e-7
+    assert abs(float(s.thetas_cumsum[100]) - 50.8994484) < 1e-4
+
+
+def test_linear_and_constant_schedules():
+    for name in ("linear", "constant"):
+        s = S.Schedule(0.1, 20, name, 0.01)
+        assert s.thetas.shape == (21,) and torch.isfinite(s.sigma_bars).all()
+        assert abs(float(torch.exp(-s.thetas_cumsum[-1] * s.dt)) - 0.01) < 1e-6
+
+
+def test_posterior_std_vanishes_at_t1():
+    s = S.Schedule(50, 100, "cosine", 0.005)
+    _, term2, std, _, _ = S.posterior_coeffs(s, 1)
+    assert float(std) < 1e-10 and abs(float(term2) - 1.0) < 1e-6
+
+
+def test_unet_forward_padded(gold, net):
+    sd, cfg = net
+    g = gold["fwd_pad"]
+    B, H, W = g["shape"]
+    inp = synthetic.restoration_inputs(B, H, W, T=1, seed=g["seed"])
+    xt = inp["lq"] + inp["eps0"] * (50 / 255)
+    with torch.no_grad():
+        out = O.unet_forward(sd, cfg, xt, inp["lq"], g["time"], inp["text_context"], inp["image_context"])
+    assert out.shape == g["out"].shape
+    assert (out - g["out"]).abs().max().item() < 2e-4
+
+
+def test_unet_forward_64(gold, net):
+    sd, cfg = net
+    g = gold["fwd_64"]
+    inp = synthetic.restoration_inputs(1, 64, 64, T=1, seed=g["seed"])
+    xt = inp["lq"] + inp["eps0"] * (50 / 255)
+    with torch.no_grad():
+        for t, key in ((100.0, "out_t100"), (1.0, "out_t1")):
+            out = O.unet_forward(sd, cfg, xt, inp["lq"], t, inp["text_context"], inp["image_context"])
+            assert (out - g[key]).abs().max().item() < 2e-4, key
+
+
+@pytest.mark.parametrize("mode", ["sde", "posterior"])
+def test_full_trajectory(gold, net, mode):
+    sd, cfg = net
+    g = gold["trajectory"]
+    inp = synthetic.restoration_inputs(1, 32, 32, T=g["T"], seed=g["seed"])
+    s = S.Schedule(50, g["T"], "cosine", 0.005)
+    x_T = inp["lq"] + inp["eps0"] * s.max_sigma
+    with torch.no_grad():
+        x = S.reverse(s, O.make_denoiser(sd, cfg), x_T, inp["lq"], mode=mode, noise=inp["noise"],
+                      text_context=inp["text_context"], image_context=inp["image_context"])
+    assert (x - g[mode]).abs().max().item() < 1e-3
+
+
+def test_cross_attention_single_token_is_broadcast(net):
+    """attention.py:152-193 with a 1-token context == to_out(to_v(ctx)), independent of the query."""
+    sd, cfg = net
+    p = "mid_attn.fn.fn.transformer_blocks.0.attn2."
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 20, 512, generator=g)
+    ctx = torch.randn(2, 1, 512, generator=g)
+    full = O.attention(sd, p, x, ctx, heads=16)
+    const = torch.nn.functional.linear(torch.nn.functional.linear(ctx, sd[p + "to_v.weight"]),
+                                       sd[p + "to_out.0.weight"], sd[p + "to_out.0.bias"])
+    assert (full - const).abs().max().item() < 1e-5
+
+
+def test_daclip_encode_and_argmax():
+    g = torch.load(os.path.join(GOLD, "daclip.pt"), weights_only=False)
+    sd = synthetic.daclip_visual_state_dict(g["weights_seed"])
+    image = torch.randn(4, 3, 224, 224, generator=torch.Generator().manual_seed(g["image_seed"]))
+    taps = {}
+    with torch.no_grad():
+        img_f, deg_f = D.encode_image_control(sd, image, taps=taps)
+    assert (img_f - g["image_features"]).abs().max().item() < 2e-3 * g["image_features"].abs().max().item()
+    assert (deg_f - g["degra_features"]).abs().max().item() < 2e-3 * g["degra_features"].abs().max().item()
+    assert (D.degradation_logits(deg_f, g["text_features"]) - g["logits"]).abs().max().item() < 5e-3
+    assert torch.equal(D.degradation_argmax(deg_f, g["text_features"]), g["argmax"])
+    assert torch.equal(D.degradation_argmax(g["degra_features"], g["text_features"]), g["argmax"])
+    # the control signal must be alive (zero-init modules were randomised) and consumed in REVERSE order
+    assert all(h.abs().max() > 1e-3 for h in taps["hiddens"])
