@@ -60,6 +60,10 @@ struct ConvKParams {
   int res2_ld;
   __nv_bfloat16* out;
   int out_ld, out_coff;
+  const float* res_f32;
+  int res_f32_ld;
+  float* out_f32;
+  int out_f32_ld;
   int out_scale, OHf, OWf;
   int8_t out_oy[4], out_ox[4];
   float* out_nchw;
@@ -260,9 +264,25 @@ __device__ __forceinline__ void epilogue_tile(const ConvKParams& p, const TileCo
             p.out_nchw[((static_cast<long long>(n) * p.nchw_c + ch + j) * p.nchw_h + Y) * p.nchw_w + X] = v[j];
         }
       } else {
+        if (p.res_f32) {
+          const float* rp = p.res_f32 + opix * p.res_f32_ld + ch;
+#pragma unroll
+          for (int j = 0; j < CW; ++j)
+            if (j < nvalid) v[j] += __ldg(rp + j);
+        }
         if (p.res) add_residual<CW>(p.res + opix * p.res_ld + ch, v, nvalid);
         if (p.res2) add_residual<CW>(p.res2 + opix * p.res2_ld + ch, v, nvalid);
-        store_bf16_chunk<CW>(p.out + opix * p.out_ld + p.out_coff + ch, v, nvalid);
+        if (p.out_f32) {
+          float* op = p.out_f32 + opix * p.out_f32_ld + ch;
+          if (nvalid >= CW) {
+#pragma unroll
+            for (int q = 0; q < CW / 4; ++q)
+              reinterpret_cast<float4*>(op)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          } else {
+            for (int j = 0; j < nvalid; ++j) op[j] = v[j];
+          }
+        }
+        if (p.out) store_bf16_chunk<CW>(p.out + opix * p.out_ld + p.out_coff + ch, v, nvalid);
       }
     }
   }
@@ -477,7 +497,12 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
        reinterpret_cast<uintptr_t>(d->weight) | reinterpret_cast<uintptr_t>(d->out) |
        reinterpret_cast<uintptr_t>(d->res) | reinterpret_cast<uintptr_t>(d->res2)) & 15)
     return set_error(-2, "dac_conv_create: pointers must be 16-byte aligned");
-  if (!d->out && !d->out_nchw) return set_error(-2, "dac_conv_create: no output");
+  if (!d->out && !d->out_nchw && !d->out_f32) return set_error(-2, "dac_conv_create: no output");
+  if ((d->out_f32 && (d->out_f32_ld & 3)) || (d->res_f32 && (d->res_f32_ld & 3)) ||
+      ((reinterpret_cast<uintptr_t>(d->out_f32) | reinterpret_cast<uintptr_t>(d->res_f32)) & 15))
+    return set_error(-2, "dac_conv_create: fp32 stream pointers/pitches must be 16-byte aligned");
+  if ((d->out_f32 || d->res_f32) && d->epi != DAC_EPI_PLAIN)
+    return set_error(-2, "dac_conv_create: fp32 stream only with the PLAIN epilogue");
   if (d->epi == DAC_EPI_LN && (d->cout != d->block_n || d->cout_pad != d->cout || !d->ln_g || (d->cout & 31)))
     return set_error(-2, "dac_conv_create: LN epilogue needs a single N tile with cout %% 32 == 0");
   if (d->epi == DAC_EPI_QKV && (d->block_n != 128 || d->cout != 384))
@@ -512,6 +537,8 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
   k.res = static_cast<const __nv_bfloat16*>(d->res); k.res_ld = d->res_ld;
   k.res2 = static_cast<const __nv_bfloat16*>(d->res2); k.res2_ld = d->res2_ld;
   k.out = static_cast<__nv_bfloat16*>(d->out); k.out_ld = d->out_ld; k.out_coff = d->out_coff;
+  k.res_f32 = d->res_f32; k.res_f32_ld = d->res_f32_ld;
+  k.out_f32 = d->out_f32; k.out_f32_ld = d->out_f32_ld;
   k.out_scale = d->out_scale > 0 ? d->out_scale : 1;
   k.OHf = d->OH * k.out_scale; k.OWf = d->OW * k.out_scale;
   memcpy(k.out_oy, d->out_oy, 4); memcpy(k.out_ox, d->out_ox, 4);

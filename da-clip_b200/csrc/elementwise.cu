@@ -164,6 +164,50 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const __nv_bfloat16
   }
 }
 
+// fp32 rows in (ViT residual stream), bf16 rows out.
+__global__ void __launch_bounds__(256) layernorm_rows_f32_kernel(const float* __restrict__ in, int ld_in,
+                                                                 __nv_bfloat16* __restrict__ out, int ld_out,
+                                                                 int64_t rows, int c, const float* __restrict__ w,
+                                                                 const float* __restrict__ b, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  const int nvec = c >> 2;
+  for (int64_t row = warp_global; row < rows; row += nwarps) {
+    const float4* src = reinterpret_cast<const float4*>(in + row * ld_in);
+    float sum = 0.f;
+    for (int i = lane; i < nvec; i += 32) {
+      const float4 u = src[i];
+      sum += (u.x + u.y) + (u.z + u.w);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / c;
+    float ss = 0.f;
+    for (int i = lane; i < nvec; i += 32) {
+      const float4 u = src[i];
+      const float e0 = u.x - mean, e1 = u.y - mean, e2 = u.z - mean, e3 = u.w - mean;
+      ss += e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float rstd = rsqrtf(ss / c + eps);
+    uint2* dst = reinterpret_cast<uint2*>(out + row * ld_out);
+    for (int i = lane; i < nvec; i += 32) {
+      const float4 u = src[i];
+      float v[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float y = (v[j] - mean) * rstd;
+        if (w) y *= __ldg(w + i * 4 + j);
+        if (b) y += __ldg(b + i * 4 + j);
+        v[j] = y;
+      }
+      dst[i] = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ GroupNorm
 // stats[b][g] = {sum, sumsq}.  Each thread owns one 8-channel vector column (8 | channels-per-group) and walks
 // pixels of its slab; per-group partials are combined through shared memory then one atomicAdd per group.
@@ -397,6 +441,18 @@ extern "C" int dac_layernorm_rows(const void* in, int32_t ld_in, void* out, int3
   layernorm_rows_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(in), ld_in, static_cast<__nv_bfloat16*>(out), ld_out, rows, c, w, b, eps);
   return check_launch("layernorm_rows_kernel");
+}
+
+extern "C" int dac_layernorm_rows_f32(const float* in, int32_t ld_in, void* out, int32_t ld_out, int64_t rows,
+                                      int32_t c, const float* w, const float* b, float eps, dac_stream_t stream) {
+  if (!in || !out) return set_error(-1, "dac_layernorm_rows_f32: null argument");
+  if ((c & 3) || (ld_in & 3) || (ld_out & 3)) return set_error(-2, "dac_layernorm_rows_f32: c and pitches must be multiples of 4");
+  if (rows <= 0) return 0;
+  const int64_t blocks = ceil_div(rows, 8);
+  const int grid = static_cast<int>(blocks > 148 * 8 ? 148 * 8 : blocks);
+  layernorm_rows_f32_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      in, ld_in, static_cast<__nv_bfloat16*>(out), ld_out, rows, c, w, b, eps);
+  return check_launch("layernorm_rows_f32_kernel");
 }
 
 extern "C" int dac_groupnorm_nhwc(const void* in, void* out, int32_t B, int32_t hw, int32_t c, int32_t groups,

@@ -45,7 +45,7 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 __global__ void __launch_bounds__(256) vit_embed_kernel(const __nv_bfloat16* __restrict__ patch_emb,
                                                         const float* __restrict__ cls, const float* __restrict__ pos,
                                                         const float* __restrict__ ln_w, const float* __restrict__ ln_b,
-                                                        __nv_bfloat16* __restrict__ out, int L, int w, float eps) {
+                                                        float* __restrict__ out, int L, int w, float eps) {
   extern __shared__ float row[];
   __shared__ float red[8];
   const int tok = blockIdx.x % L, b = blockIdx.x / L;
@@ -65,21 +65,21 @@ __global__ void __launch_bounds__(256) vit_embed_kernel(const __nv_bfloat16* __r
   }
   const float rstd = rsqrtf(block_sum(ss, red) / w + eps);
   for (int i = threadIdx.x; i < w; i += blockDim.x)
-    out[(static_cast<int64_t>(b) * L + tok) * w + i] = __float2bfloat16((row[i] - mean) * rstd * ln_w[i] + ln_b[i]);
+    out[(static_cast<int64_t>(b) * L + tok) * w + i] = (row[i] - mean) * rstd * ln_w[i] + ln_b[i];
 }
 
 // one CTA per image: ln_post(x[b,0,:]) @ proj
-__global__ void __launch_bounds__(256) vit_pool_kernel(const __nv_bfloat16* __restrict__ x, int L, int w,
+__global__ void __launch_bounds__(256) vit_pool_kernel(const float* __restrict__ x, int L, int w,
                                                        const float* __restrict__ ln_w, const float* __restrict__ ln_b,
                                                        float eps, const float* __restrict__ proj, int e,
                                                        float* __restrict__ out) {
   extern __shared__ float row[];
   __shared__ float red[8];
   const int b = blockIdx.x;
-  const __nv_bfloat16* src = x + static_cast<int64_t>(b) * L * w;
+  const float* src = x + static_cast<int64_t>(b) * L * w;
   float s = 0.f;
   for (int i = threadIdx.x; i < w; i += blockDim.x) {
-    row[i] = __bfloat162float(src[i]);
+    row[i] = src[i];
     s += row[i];
   }
   const float mean = block_sum(s, red) / w;
@@ -156,7 +156,7 @@ extern "C" int dac_vit_embed(const void* patch_emb, const float* cls, const floa
                              dac_stream_t stream) {
   if (!patch_emb || !cls || !pos || !ln_w || !ln_b || !out) return set_error(-1, "dac_vit_embed: null argument");
   vit_embed_kernel<<<B * L, 256, w * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(patch_emb), cls, pos, ln_w, ln_b, static_cast<__nv_bfloat16*>(out), L, w, eps);
+      static_cast<const __nv_bfloat16*>(patch_emb), cls, pos, ln_w, ln_b, static_cast<float*>(out), L, w, eps);
   return check_launch("vit_embed_kernel");
 }
 
@@ -164,7 +164,7 @@ extern "C" int dac_vit_pool(const void* x, int32_t B, int32_t L, int32_t w, cons
                             float eps, const float* proj, int32_t e, float* out, dac_stream_t stream) {
   if (!x || !ln_w || !ln_b || !proj || !out) return set_error(-1, "dac_vit_pool: null argument");
   vit_pool_kernel<<<B, 256, w * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(x), L, w, ln_w, ln_b, eps, proj, e, out);
+      static_cast<const float*>(x), L, w, ln_w, ln_b, eps, proj, e, out);
   return check_launch("vit_pool_kernel");
 }
 

@@ -1,0 +1,287 @@
+"""DaCLIP image side with the reference's API (open_clip/daclip_model.py:17-76, transformer.py:288-555,
+factory.py:365-404 of the reference): `encode_image(image, control=True)` -> (image_features, degra_features),
+two ViT-B/32 towers, the control tower's per-layer hidden states (through their zero-init linears) added to the
+frozen CLIP tower in REVERSED order (`control.pop()`, transformer.py:367-368).
+
+The module holds parameters under the reference's state-dict keys (`visual.*`, its alias `clip.visual.*`,
+`visual_control.*` incl. `visual_control.transformer.zero_modules.N`, `logit_scale`); text-tower keys of a full
+631-key checkpoint are accepted and kept aside (the 10 degradation prompts are encoded once per deployment by
+the reference's own text tower - SURVEY.md section 8f N4 - and enter here as a [classes, 512] tensor).
+
+Execution: every GEMM (patch embedding, in_proj, out_proj, c_fc, c_proj, zero-linear) is the tcgen05 kernel with
+tokens as pixels (M = 50*B); the residual stream stays fp32 (fp32 residual in the GEMM epilogue) so that the
+degradation-type argmax is stable; LayerNorm / 50-token attention / pooling are small fused CUDA kernels.
+"""
+from collections import OrderedDict
+
+import torch
+import torch.nn as nn
+
+from . import lib as L
+from . import ops
+
+DISTORTIONS = ["motion-blurry", "hazy", "jpeg-compressed", "low-light", "noisy", "raindrop", "rainy", "shadowed",
+               "snowy", "uncompleted"]                                         # options/test.yml:4
+
+
+# ------------------------------------------------------------------------------------------------ parameter holders
+class _Holder(nn.Module):
+    def forward(self, *a, **k):  # pragma: no cover
+        raise L.DacError("parameter holder: compute happens in the CUDA engine")
+
+
+class _Mlp(_Holder):
+    def __init__(self, w):
+        super().__init__()
+        self.c_fc = nn.Linear(w, 4 * w)
+        self.gelu = nn.GELU()
+        self.c_proj = nn.Linear(4 * w, w)
+
+
+class _ResidualAttentionBlock(_Holder):  # transformer.py:189-244
+    def __init__(self, w, heads):
+        super().__init__()
+        self.ln_1 = nn.LayerNorm(w)
+        self.attn = nn.MultiheadAttention(w, heads)
+        self.ln_2 = nn.LayerNorm(w)
+        self.mlp = _Mlp(w)
+
+
+class _Transformer(_Holder):  # transformer.py:328-369
+    def __init__(self, w, layers, heads):
+        super().__init__()
+        self.width, self.layers = w, layers
+        self.resblocks = nn.ModuleList([_ResidualAttentionBlock(w, heads) for _ in range(layers)])
+
+
+class _ControlTransformer(_Holder):  # transformer.py:288-325
+    def __init__(self, transformer):
+        super().__init__()
+        self.transformer = transformer
+        self.zero_modules = nn.ModuleList([nn.Linear(transformer.width, transformer.width)
+                                           for _ in range(transformer.layers)])
+        for p in self.zero_modules.parameters():
+            p.detach().zero_()
+
+
+class _VisionTransformer(_Holder):  # transformer.py:372-555
+    def __init__(self, image_size=224, patch=32, width=768, layers=12, heads=12, embed_dim=512, control=False):
+        super().__init__()
+        self.image_size, self.patch, self.width, self.layers, self.heads = image_size, patch, width, layers, heads
+        self.output_dim = embed_dim
+        g = image_size // patch
+        scale = width ** -0.5
+        self.conv1 = nn.Conv2d(3, width, patch, patch, bias=False)
+        self.class_embedding = nn.Parameter(scale * torch.randn(width))
+        self.positional_embedding = nn.Parameter(scale * torch.randn(g * g + 1, width))
+        self.ln_pre = nn.LayerNorm(width)
+        t = _Transformer(width, layers, heads)
+        self.transformer = _ControlTransformer(t) if control else t
+        self.ln_post = nn.LayerNorm(width)
+        self.proj = nn.Parameter(scale * torch.randn(width, embed_dim))
+
+
+class DaCLIP(nn.Module):
+    """Image side of open_clip's `daclip_ViT-B-32` (model_configs/daclip_ViT-B-32.json)."""
+
+    def __init__(self, image_size=224, patch=32, width=768, layers=12, heads=12, embed_dim=512):
+        super().__init__()
+        self.visual = _VisionTransformer(image_size, patch, width, layers, heads, embed_dim)
+        self.visual_control = _VisionTransformer(image_size, patch, width, layers, heads, embed_dim, control=True)
+        self.logit_scale = nn.Parameter(torch.ones([]) * 2.6592600)
+        self.text_state = OrderedDict()      # text-tower tensors of a full checkpoint, untouched
+        self._engines = {}
+        self._packed = None
+        self.register_load_state_dict_post_hook(lambda m, keys: m.invalidate())
+
+    def invalidate(self):
+        self._engines, self._packed = {}, None
+
+    def _apply(self, fn, *a, **k):
+        self.invalidate()
+        return super()._apply(fn, *a, **k)
+
+    def load_reference_state_dict(self, sd):
+        """Accepts the reference's checkpoint layout (factory.py:88-106): optional {'state_dict': ...} wrapper,
+        optional 'module.' prefix, `clip.visual.*` alias of `visual.*`, text-tower keys kept aside."""
+        if "state_dict" in sd and isinstance(sd["state_dict"], dict):
+            sd = sd["state_dict"]
+        own = self.state_dict()
+        mine, self.text_state = OrderedDict(), OrderedDict()
+        for k, v in sd.items():
+            k = k[7:] if k.startswith("module.") else k
+            if k.startswith("clip.visual."):
+                k = k[5:]
+            if k in own:
+                mine[k] = v
+            else:
+                self.text_state[k] = v
+        missing = [k for k in own if k not in mine and k != "logit_scale"]
+        if missing:
+            raise KeyError(f"checkpoint lacks {len(missing)} image-side tensors, e.g. {missing[:3]}")
+        mine.setdefault("logit_scale", own["logit_scale"])
+        self.load_state_dict(mine, strict=True)
+        return self
+
+    # ------------------------------------------------------------------ public API (daclip_model.py:46-55)
+    def encode_image(self, image, control=False, normalize=False):
+        if not control:
+            raise NotImplementedError("the restoration path always calls encode_image(control=True)")
+        L.require_cuda(image)
+        B = image.shape[0]
+        dev = self.visual.proj.device
+        if dev.type != "cuda":
+            raise L.DacError("DaCLIP (daclip_b200) runs on CUDA only")
+        if self._packed is None:
+            self._packed = _PackedDaCLIP(self)
+        if B not in self._engines:
+            self._engines[B] = _EncodeEngine(self._packed, self.visual, B, dev)
+        eng = self._engines[B]
+        eng.image.copy_(image.to(torch.float32))
+        eng.replay()
+        img_f, deg_f = eng.image_features.clone(), eng.degra_features.clone()
+        if normalize:
+            img_f = torch.nn.functional.normalize(img_f, dim=-1)      # plumbing on [B,512] outputs
+            deg_f = torch.nn.functional.normalize(deg_f, dim=-1)
+        return img_f, deg_f
+
+    def degradation_argmax(self, degra_features, text_features, return_logits=False):
+        """argmax_j softmax(100 * cos(degra, text_j)) (da-clip/src/evaluate_daclip.py:46-47,79-81)."""
+        L.require_cuda(degra_features, text_features)
+        d = degra_features.to(torch.float32).contiguous()
+        t = text_features.to(device=d.device, dtype=torch.float32).contiguous()
+        logits = torch.empty(d.shape[0], t.shape[0], device=d.device)
+        am = torch.empty(d.shape[0], dtype=torch.int64, device=d.device)
+        ops.degradation_argmax(d, t, logits, am)
+        return (am, logits) if return_logits else am
+
+
+class _PackedTower:
+    def __init__(self, vit, prefix_blocks, zero_modules=None):
+        dev = vit.proj.device
+
+        def f32(t):
+            return t.detach().to(dev, torch.float32).contiguous()
+
+        self.conv1 = ops.pack_linear(f32(vit.conv1.weight).reshape(vit.width, -1))
+        self.cls, self.pos = f32(vit.class_embedding), f32(vit.positional_embedding)
+        self.ln_pre = (f32(vit.ln_pre.weight), f32(vit.ln_pre.bias))
+        self.ln_post = (f32(vit.ln_post.weight), f32(vit.ln_post.bias))
+        self.proj = f32(vit.proj)
+        self.blocks = []
+        for i, r in enumerate(prefix_blocks):
+            blk = dict(
+                ln1=(f32(r.ln_1.weight), f32(r.ln_1.bias)), ln2=(f32(r.ln_2.weight), f32(r.ln_2.bias)),
+                qkv=ops.pack_linear(f32(r.attn.in_proj_weight)), qkv_b=f32(r.attn.in_proj_bias),
+                out=ops.pack_linear(f32(r.attn.out_proj.weight)), out_b=f32(r.attn.out_proj.bias),
+                fc=ops.pack_linear(f32(r.mlp.c_fc.weight)), fc_b=f32(r.mlp.c_fc.bias),
+                proj=ops.pack_linear(f32(r.mlp.c_proj.weight)), proj_b=f32(r.mlp.c_proj.bias))
+            if zero_modules is not None:
+                blk["zero"] = ops.pack_linear(f32(zero_modules[i].weight))
+                blk["zero_b"] = f32(zero_modules[i].bias)
+            self.blocks.append(blk)
+
+
+class _PackedDaCLIP:
+    def __init__(self, m: DaCLIP):
+        self.clip = _PackedTower(m.visual, m.visual.transformer.resblocks)
+        ct = m.visual_control.transformer
+        self.control = _PackedTower(m.visual_control, ct.transformer.resblocks, ct.zero_modules)
+
+
+class _EncodeEngine:
+    """Launch plan of encode_image(control=True) for a fixed batch, captured in one CUDA graph."""
+
+    def __init__(self, pk: _PackedDaCLIP, vit, B, dev):
+        self.B, self.dev = B, dev
+        S, p, w, heads = vit.image_size, vit.patch, vit.width, vit.heads
+        g = S // p
+        Ltok = g * g + 1
+        M = B * Ltok
+        self.steps, self.flops = [], 0.0
+        bf, f32 = dict(device=dev, dtype=torch.bfloat16), dict(device=dev, dtype=torch.float32)
+        self.image = torch.zeros(B, 3, S, S, **f32)
+        self.image_features = torch.zeros(B, vit.output_dim, **f32)
+        self.degra_features = torch.zeros(B, vit.output_dim, **f32)
+        patches = torch.zeros(1, 1, B * g * g, 3 * p * p, **bf)
+        self.add(lambda: ops.vit_patchify(self.image, patches, B, S, p))
+        hiddens = []
+
+        def tower(tp, out_features, control_in=None):
+            pe = torch.zeros(1, 1, B * g * g, w, **bf)
+            self.conv(patches, 3 * p * p, tp.conv1, pe, B * g * g)
+            x = torch.zeros(1, 1, M, w, **f32)
+            self.add(lambda: ops.vit_embed(pe, tp.cls, tp.pos, tp.ln_pre[0], tp.ln_pre[1], x, B, Ltok, w))
+            n = torch.zeros(1, 1, M, w, **bf)
+            qkv = torch.zeros(1, 1, M, 3 * w, **bf)
+            att = torch.zeros(1, 1, M, w, **bf)
+            hid = torch.zeros(1, 1, M, 4 * w, **bf)
+            for i, blk in enumerate(tp.blocks):
+                self.add(lambda blk=blk: ops.layernorm_rows_f32(x, n, M, w, blk["ln1"][0], blk["ln1"][1], 1e-5))
+                self.conv(n, w, blk["qkv"], qkv, M, bias=blk["qkv_b"])
+                self.add(lambda: ops.attention(qkv, att, B, Ltok, heads, w // heads))
+                self.conv(att, w, blk["out"], None, M, bias=blk["out_b"], res_f32=x, out_f32=x)
+                self.add(lambda blk=blk: ops.layernorm_rows_f32(x, n, M, w, blk["ln2"][0], blk["ln2"][1], 1e-5))
+                self.conv(n, w, blk["fc"], hid, M, bias=blk["fc_b"], act=L.ACT_GELU)
+                if control_in is None:
+                    # control tower: x <- x + mlp; also keep a bf16 copy as the zero-linear's GEMM operand
+                    xb = torch.zeros(1, 1, M, w, **bf)
+                    self.conv(hid, 4 * w, blk["proj"], xb, M, bias=blk["proj_b"], res_f32=x, out_f32=x)
+                    h = torch.zeros(1, 1, M, w, **bf)
+                    self.conv(xb, w, blk["zero"], h, M, bias=blk["zero_b"])
+                    hiddens.append(h)
+                else:
+                    # CLIP tower: x <- x + mlp + control.pop()  (hidden of control layer L-1-i)
+                    self.conv(hid, 4 * w, blk["proj"], None, M, bias=blk["proj_b"], res_f32=x, out_f32=x,
+                              res2=control_in[len(tp.blocks) - 1 - i])
+            self.add(lambda: ops.vit_pool(x, B, Ltok, w, tp.ln_post[0], tp.ln_post[1], tp.proj, out_features))
+
+        tower(pk.control, self.degra_features)
+        tower(pk.clip, self.image_features, control_in=hiddens)
+        self.flops += 2 * 4.0 * B * heads * Ltok * Ltok * (w // heads) * len(pk.clip.blocks)
+        self.graph = None
+
+    def add(self, fn):
+        self.steps.append(fn)
+
+    def conv(self, src, cin, pw, out, M, **kw):
+        plan = ops.ConvPlan(src, cin, pw, out, B=1, H=1, W=M, **kw)
+        self.flops += plan.flops
+        self.steps.append(plan.run)
+
+    def run_eager(self):
+        for fn in self.steps:
+            fn()
+
+    def replay(self):
+        if self.graph is None:
+            self.run_eager()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.run_eager()
+            self.graph = g
+        self.graph.replay()
+
+
+def create_model_from_pretrained(model_name="daclip_ViT-B-32", pretrained=None, device="cuda", **_):
+    """factory.py:365-404 for the one model on this path.  Returns (model, preprocess); `pretrained` is a path
+    to a reference checkpoint (.pt: raw state dict or {'state_dict': ...}), or None for random init."""
+    if model_name not in ("daclip_ViT-B-32",):
+        raise NotImplementedError(f"only daclip_ViT-B-32 is on the restoration path, got {model_name}")
+    model = DaCLIP()
+    if pretrained:
+        model.load_reference_state_dict(torch.load(pretrained, map_location="cpu"))
+    return model.to(device).eval(), clip_preprocess
+
+
+CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
+CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
+
+
+def clip_preprocess(pil_image, resolution=224):
+    """data/util.py:87-93 / open_clip.transform: bicubic resize of the short side, centre crop, normalise.
+    Host-side image IO (PIL/torchvision), outside the measured path."""
+    from torchvision.transforms import CenterCrop, Compose, InterpolationMode, Normalize, Resize, ToTensor
+    return Compose([Resize(resolution, interpolation=InterpolationMode.BICUBIC), CenterCrop(resolution), ToTensor(),
+                    Normalize(CLIP_MEAN, CLIP_STD)])(pil_image)

@@ -33,6 +33,8 @@ class ConvDesc(C.Structure):
         ("res", C.c_void_p), ("res_ld", C.c_int32),
         ("res2", C.c_void_p), ("res2_ld", C.c_int32),
         ("out", C.c_void_p), ("out_ld", C.c_int32), ("out_coff", C.c_int32),
+        ("res_f32", C.c_void_p), ("res_f32_ld", C.c_int32),
+        ("out_f32", C.c_void_p), ("out_f32_ld", C.c_int32),
         ("out_nchw", C.c_void_p), ("out_nchw_c", C.c_int32), ("out_nchw_h", C.c_int32), ("out_nchw_w", C.c_int32),
     ]
 
@@ -63,6 +65,7 @@ SYMBOLS = {
     "dac_conv_destroy": (None, [_p]),
     "dac_conv_info": (C.c_int, [_p] + [C.POINTER(_i32)] * 4),
     "dac_layernorm_rows": (C.c_int, [_p, _i32, _p, _i32, _i64, _i32, _p, _p, _f, _p]),
+    "dac_layernorm_rows_f32": (C.c_int, [_p, _i32, _p, _i32, _i64, _i32, _p, _p, _f, _p]),
     "dac_groupnorm_nhwc": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _p, _p, _f, _p, _p]),
     "dac_time_film": (C.c_int, [C.POINTER(EmbedWeights), _p, _p, _i32, _p, _p, _p]),
     "dac_two_linear": (C.c_int, [_p, _i32, _i32, _p, _i32, _p, _p, _i32, _p, _p]),

@@ -131,7 +131,7 @@ class ConvPlan:
 
     def __init__(self, src0, c0, pw: PackedWeight, out=None, *, B, H, W, src1=None, c1=0, ld0=None, ld1=None,
                  epi=L.EPI_PLAIN, act=L.ACT_NONE, bias=None, bias_img=None, film=None, film_off=0,
-                 ln_g=None, ln_eps=1e-5, res=None, res2=None, out_coff=0, out_nchw=None,
+                 ln_g=None, ln_eps=1e-5, res=None, res2=None, res_f32=None, out_f32=None, out_coff=0, out_nchw=None,
                  per_image_w=False, block_n=None, weight_override=None, tile=None):
         L.require_cuda(src0)
         lib = L.load()
@@ -169,10 +169,14 @@ class ConvPlan:
             d.res2, d.res2_ld = res2.data_ptr(), res2.shape[-1]
         if out is not None:
             d.out, d.out_ld, d.out_coff = out.data_ptr(), out.shape[-1], out_coff
+        if res_f32 is not None:
+            d.res_f32, d.res_f32_ld = res_f32.data_ptr(), res_f32.shape[-1]
+        if out_f32 is not None:
+            d.out_f32, d.out_f32_ld = out_f32.data_ptr(), out_f32.shape[-1]
         if out_nchw is not None:
             d.out_nchw = out_nchw.data_ptr()
             d.out_nchw_c, d.out_nchw_h, d.out_nchw_w = out_nchw.shape[1], out_nchw.shape[2], out_nchw.shape[3]
-        self._keep = (src0, src1, wt, out, bias, bias_img, film, ln_g, res, res2, out_nchw)
+        self._keep = (src0, src1, wt, out, bias, bias_img, film, ln_g, res, res2, out_nchw, res_f32, out_f32)
         self.desc = d
         h = C.c_void_p()
         L.check(lib.dac_conv_create(C.byref(d), C.byref(h)))
@@ -223,6 +227,11 @@ def stem_input(xt, cond, out, H, W):
 def layernorm_rows(x, out, rows, c, w=None, b=None, eps=1e-5):
     L.check(L.load().dac_layernorm_rows(L.ptr(x), x.shape[-1], L.ptr(out), out.shape[-1], rows, c, L.ptr(w), L.ptr(b),
                                         float(eps), L.stream_ptr()))
+
+
+def layernorm_rows_f32(x, out, rows, c, w=None, b=None, eps=1e-5):
+    L.check(L.load().dac_layernorm_rows_f32(L.ptr(x), x.shape[-1], L.ptr(out), out.shape[-1], rows, c, L.ptr(w),
+                                            L.ptr(b), float(eps), L.stream_ptr()))
 
 
 def groupnorm_nhwc(x, out, B, hw, c, w, b, stats, groups=32, eps=1e-6):

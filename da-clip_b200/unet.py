@@ -338,6 +338,8 @@ class UNetEngine:
         self.film = torch.zeros(B, pk.F, **f32)
         self.use_text = False
         self.steps = []          # (name, callable)
+        self.taps = {}           # block name -> output buffer (NHWC bf16), for per-layer parity checks
+        self.conv_names = set()  # steps that are tcgen05 implicit-GEMM launches
         self.flops = 0.0
         self._bytes = 0
         self._build()
@@ -355,8 +357,12 @@ class UNetEngine:
     def conv(self, name, src, c0, pw, out, h, w, **kw):
         plan = ops.ConvPlan(src, c0, pw, out, B=self.B, H=h, W=w, **kw)
         self.flops += plan.flops
+        self.conv_names.add(name)
         self.add(name, plan.run)
         return plan
+
+    def is_conv(self, name):
+        return name in self.conv_names
 
     def resblock(self, prefix, x, xc, h, w, skip=None, sc=0):
         rb = self.pk.rb[prefix]
@@ -434,14 +440,18 @@ class UNetEngine:
                                                     self.temb, self.film))
         x0 = self.buf(B, Hp, Wp, 64)
         self.conv("init_conv", stem, 64, pk.stem, x0, Hp, Wp)
+        self.taps["init_conv"] = x0
         x, h, w = x0, Hp, Wp
         skips = []
         for i, (din, dout) in enumerate(cfg.dims):
             p = f"downs.{i}."
             x = self.resblock(p + "0.", x, din, h, w)
+            self.taps[p + "0"] = x
             skips.append((x, din))
             x = self.resblock(p + "1.", x, din, h, w)
+            self.taps[p + "1"] = x
             x = self.attn_layer(p + "2.", x, din, h, w)
+            self.taps[p + "2"] = x
             skips.append((x, din))
             pw, bias = pk.down[i]
             if i != cfg.depth - 1:
@@ -452,19 +462,26 @@ class UNetEngine:
                 y = self.buf(B, h, w, dout)
                 self.conv(p + "3", x, din, pw, y, h, w)
             x = y
+            self.taps[p + "3"] = x
         md = cfg.mid_dim
         x = self.resblock("mid_block1.", x, md, h, w)
+        self.taps["mid_block1"] = x
         x = self.attn_layer("mid_attn.", x, md, h, w)
+        self.taps["mid_attn"] = x
         x = self.resblock("mid_block2.", x, md, h, w)
+        self.taps["mid_block2"] = x
         for j in range(cfg.depth):
             i = cfg.depth - 1 - j
             din, dout = cfg.dims[i]
             p = f"ups.{j}."
             sk, sc = skips.pop()
             x = self.resblock(p + "0.", x, dout, h, w, skip=sk, sc=sc)
+            self.taps[p + "0"] = x
             sk, sc = skips.pop()
             x = self.resblock(p + "1.", x, dout, h, w, skip=sk, sc=sc)
+            self.taps[p + "1"] = x
             x = self.attn_layer(p + "2.", x, dout, h, w)
+            self.taps[p + "2"] = x
             pw, bias = pk.up[j]
             if i != 0:
                 y = self.buf(B, 2 * h, 2 * w, din)
@@ -474,7 +491,9 @@ class UNetEngine:
                 y = self.buf(B, h, w, din)
                 self.conv(p + "3", x, dout, pw, y, h, w)
             x = y
+            self.taps[p + "3"] = x
         x = self.resblock("final_res_block.", x, cfg.nf, h, w, skip=x0, sc=cfg.nf)
+        self.taps["final_res_block"] = x
         self.conv("final_conv", x, cfg.nf, pk.final_w, None, h, w, bias=pk.final_b, out_nchw=self.out_noise)
 
     # -------------------------------------------------------------- execution

@@ -94,6 +94,8 @@ typedef struct dac_conv_desc {
   const void* res; int32_t res_ld;                /* residual NHWC bf16 at output coordinates, or NULL */
   const void* res2; int32_t res2_ld;              /* optional second residual (nested Residual of MU:27-33 + ATT:261) */
   void* out; int32_t out_ld, out_coff;            /* NHWC bf16 [B, OH*out_scale, OW*out_scale, out_ld] */
+  const float* res_f32; int32_t res_f32_ld;       /* fp32 residual stream (ViT blocks keep x in fp32), PLAIN only */
+  float* out_f32; int32_t out_f32_ld;             /* fp32 copy of the output (may be given together with out) */
   float* out_nchw; int32_t out_nchw_c, out_nchw_h, out_nchw_w; /* alt. fp32 NCHW output (final_conv), cropped */
 } dac_conv_desc;
 
@@ -111,6 +113,9 @@ int dac_conv_info(dac_conv_t plan, int32_t* tiles, int32_t* ctas, int32_t* smem_
 int dac_layernorm_rows(const void* in, int32_t ld_in, void* out, int32_t ld_out, int64_t rows, int32_t c,
                        const float* w, const float* b, float eps, dac_stream_t stream);
 /* GroupNorm(32 groups, eps) over NHWC bf16 [B, hw, c] (ATT:76-77,251).  stats: workspace [B*32*2] fp32. */
+/* Same, fp32 input rows (the ViT residual stream), bf16 output. */
+int dac_layernorm_rows_f32(const float* in, int32_t ld_in, void* out, int32_t ld_out, int64_t rows, int32_t c,
+                           const float* w, const float* b, float eps, dac_stream_t stream);
 int dac_groupnorm_nhwc(const void* in, void* out, int32_t B, int32_t hw, int32_t c, int32_t groups,
                        const float* w, const float* b, float eps, float* stats, dac_stream_t stream);
 
@@ -151,10 +156,10 @@ int dac_attention(const void* qkv, void* out, int32_t B, int32_t n, int32_t head
 /* ------------------------------------------------------------------ DA-CLIP encoder helpers (TR:507-555)
  * patchify: image [B,3,S,S] fp32 NCHW -> [B*g*g, 3*p*p] bf16 rows (k = c*p*p + py*p + px, conv1 weight order). */
 int dac_vit_patchify(const float* image, void* out, int32_t B, int32_t S, int32_t p, dac_stream_t stream);
-/* tokens[b,0,:] = cls + pos[0]; tokens[b,1+i,:] = patch[b,i,:] + pos[1+i]; then ln_pre -> out bf16 [B,L,w]. */
+/* tokens[b,0,:] = cls + pos[0]; tokens[b,1+i,:] = patch[b,i,:] + pos[1+i]; then ln_pre -> out fp32 [B,L,w]. */
 int dac_vit_embed(const void* patch_emb, const float* cls, const float* pos, const float* ln_w, const float* ln_b,
                   void* out, int32_t B, int32_t L, int32_t w, float eps, dac_stream_t stream);
-/* pooled[b] = ln_post(x[b,0,:]) @ proj  -> fp32 [B, e] */
+/* pooled[b] = ln_post(x[b,0,:]) @ proj  -> fp32 [B, e];  x: fp32 [B,L,w] */
 int dac_vit_pool(const void* x, int32_t B, int32_t L, int32_t w, const float* ln_w, const float* ln_b, float eps,
                  const float* proj /*[w,e]*/, int32_t e, float* out, dac_stream_t stream);
 /* Degradation-type argmax (da-clip/src/evaluate_daclip.py:46-47,79-81): argmax_j 100*cos(degra[b], text[j]). */

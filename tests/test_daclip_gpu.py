@@ -1,0 +1,80 @@
+"""GPU parity of DaCLIP.encode_image(control=True) and the degradation-type argmax against outputs of the
+REFERENCE model (tests/golden/daclip.pt) and against the fp32 oracle at a larger batch.
+Tolerance: features within 2 % of their range (bf16 GEMM operands, fp32 residual stream / LayerNorm / softmax);
+the argmax is bit-exact (north_star)."""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def setup(cuda):
+    from daclip_b200 import synthetic
+    from daclip_b200.daclip import DaCLIP
+    g = torch.load(os.path.join(GOLD, "daclip.pt"), weights_only=False)
+    sd = synthetic.daclip_visual_state_dict(g["weights_seed"])
+    m = DaCLIP().load_reference_state_dict(sd).to(cuda).eval()
+    return m, sd, g
+
+
+def rel(a, b):
+    return (a - b).abs().max().item() / b.abs().max().item()
+
+
+def test_encode_image_vs_reference_golden(setup):
+    m, sd, g = setup
+    image = torch.randn(4, 3, 224, 224, generator=torch.Generator().manual_seed(g["image_seed"])).cuda()
+    img_f, deg_f = m.encode_image(image, control=True)
+    assert img_f.shape == (4, 512) and deg_f.dtype == torch.float32
+    assert rel(img_f.cpu(), g["image_features"]) < 2e-2, rel(img_f.cpu(), g["image_features"])
+    assert rel(deg_f.cpu(), g["degra_features"]) < 2e-2, rel(deg_f.cpu(), g["degra_features"])
+    am, logits = m.degradation_argmax(deg_f, g["text_features"].cuda(), return_logits=True)
+    assert torch.equal(am.cpu(), g["argmax"]), (am.cpu(), g["argmax"], (logits.cpu() - g["logits"]).abs().max())
+    assert (logits.cpu() - g["logits"]).abs().max().item() < 0.05
+
+
+def test_reference_checkpoint_layout_roundtrip(setup):
+    """A full-checkpoint-style dict: {'state_dict': {module.clip.visual.*, module.visual_control.*, text keys}}."""
+    from daclip_b200.daclip import DaCLIP
+    m, sd, g = setup
+    full = {}
+    for k, v in sd.items():
+        if k.startswith("visual."):
+            full["module.clip." + k] = v
+            full["module." + k] = v
+        else:
+            full["module." + k] = v
+    full["module.clip.token_embedding.weight"] = torch.zeros(4, 4)
+    m2 = DaCLIP().load_reference_state_dict({"state_dict": full})
+    assert "clip.token_embedding.weight" in m2.text_state
+    for k, v in m.state_dict().items():
+        assert torch.equal(m2.state_dict()[k].cpu(), v.cpu()), k
+
+
+def test_encode_image_batch_vs_oracle(setup):
+    from oracle import daclip_oracle as D
+    m, sd, g = setup
+    B = 16
+    image = torch.randn(B, 3, 224, 224, generator=torch.Generator().manual_seed(11)).cuda()
+    sdc = {k: v.cuda() for k, v in sd.items()}
+    with torch.no_grad():
+        ref_img, ref_deg = D.encode_image_control(sdc, image)
+    img_f, deg_f = m.encode_image(image, control=True)
+    assert rel(img_f, ref_img) < 2e-2 and rel(deg_f, ref_deg) < 2e-2
+    text = g["text_features"].cuda()
+    am, logits = m.degradation_argmax(deg_f, text, return_logits=True)
+    ref_logits = D.degradation_logits(ref_deg, text)
+    top2 = ref_logits.topk(2, dim=-1).values
+    gap = (top2[:, 0] - top2[:, 1])
+    # bit-exact wherever the reference's own top-2 gap exceeds the measured logit error; report the gap otherwise
+    err = (logits - ref_logits).abs().max().item()
+    decided = gap > 4 * err
+    assert torch.equal(am[decided], D.degradation_argmax(ref_deg, text)[decided])
+    assert decided.float().mean().item() > 0.7, (gap, err)
+    # normalize=True path
+    a, b = m.encode_image(image, control=True, normalize=True)
+    assert (a.norm(dim=-1) - 1).abs().max().item() < 1e-4 and (b.norm(dim=-1) - 1).abs().max().item() < 1e-4

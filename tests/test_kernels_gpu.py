@@ -299,6 +299,27 @@ def test_layernorm_rows(ops, gen, rows, c, affine):
     assert_close_bf16(out, ref, "layernorm rows")
 
 
+def test_fp32_residual_stream(ops, gen):
+    """ViT block pattern: x(fp32) -> LN -> bf16 -> GEMM + bias + fp32 residual (+ bf16 control) -> fp32 and bf16."""
+    rows, c = 350, 768
+    x = rnd(gen, 1, 1, rows, c) * 2
+    lw, lb = 1 + 0.1 * rnd(gen, c), rnd(gen, c)
+    n = torch.zeros(1, 1, rows, c, device="cuda", dtype=torch.bfloat16)
+    ops.layernorm_rows_f32(x, n, rows, c, lw, lb, 1e-5)
+    torch.cuda.synchronize()
+    assert_close_bf16(n, F.layer_norm(x, (c,), lw, lb, 1e-5), "layernorm f32-in")
+    w, b = rnd(gen, c, c, scale=c ** -0.5), rnd(gen, c)
+    ctrl = bf(rnd(gen, 1, 1, rows, c))
+    y32 = torch.zeros(1, 1, rows, c, device="cuda")
+    y16 = torch.zeros(1, 1, rows, c, device="cuda", dtype=torch.bfloat16)
+    plan = ops.ConvPlan(n, c, ops.pack_linear(w), y16, B=1, H=1, W=rows, bias=b, res_f32=x, res2=ctrl, out_f32=y32)
+    plan.run()
+    torch.cuda.synchronize()
+    ref = F.linear(n.float(), bf(w).float(), b) + x + ctrl.float()
+    assert (y32 - ref).abs().max().item() < 2e-3 * ref.abs().max().item()
+    assert_close_bf16(y16, ref, "bf16 copy of fp32 stream")
+
+
 @pytest.mark.parametrize("B,hw,c", [(2, 1024, 256), (3, 4096, 512), (1, 36, 256)])
 def test_groupnorm(ops, gen, B, hw, c):
     x = bf(rnd(gen, B, hw, c) + 0.3)
@@ -387,16 +408,16 @@ def test_vit_glue(ops, gen):
     pe = bf(rnd(gen, B, g * g, w))
     cls, pos = rnd(gen, w), rnd(gen, L_, w)
     lw, lb = 1 + 0.1 * rnd(gen, w), rnd(gen, w)
-    tok = torch.zeros(B, L_, w, device="cuda", dtype=torch.bfloat16)
+    tok = torch.zeros(B, L_, w, device="cuda", dtype=torch.float32)
     ops.vit_embed(pe, cls, pos, lw, lb, tok, B, L_, w)
     torch.cuda.synchronize()
     x = torch.cat([cls.expand(B, 1, w), pe.float()], 1) + pos
-    assert_close_bf16(tok, F.layer_norm(x, (w,), lw, lb, 1e-5), "vit embed")
+    assert (tok - F.layer_norm(x, (w,), lw, lb, 1e-5)).abs().max().item() < 1e-4
     proj = rnd(gen, w, e, scale=w ** -0.5)
     pooled = torch.zeros(B, e, device="cuda")
     ops.vit_pool(tok, B, L_, w, lw, lb, proj, pooled)
     torch.cuda.synchronize()
-    ref = F.layer_norm(tok[:, 0].float(), (w,), lw, lb, 1e-5) @ proj
+    ref = F.layer_norm(tok[:, 0], (w,), lw, lb, 1e-5) @ proj
     assert (pooled - ref).abs().max().item() < 1e-3
     text = rnd(gen, 10, e)
     logits, am = torch.zeros(B, 10, device="cuda"), torch.zeros(B, dtype=torch.int64, device="cuda")
