@@ -1,0 +1,443 @@
+// Device side of the implicit-GEMM convolution / linear layer on tcgen05 tensor cores (sm_100a).
+//
+//   D[pixel, cout] = sum_{tap, cin} X[pixel + tap, cin] * W[tap][cout][cin]
+//
+// M = 128 output pixels (a tile_h x tile_w box of one image), N = block_n output channels,
+// K walks (tap, source, 64-channel chunk).  One persistent CTA per SM, three warp roles:
+//   warp 0      TMA producer: per K step one 4-D box load of the (shifted) activation tile - image borders
+//               are zero-filled by TMA, which IS the conv padding - plus one 3-D box load of the weight slab,
+//               both 128B-swizzled, into an smem ring guarded by full/empty mbarriers;
+//   warp 1      allocates TMEM, one lane issues tcgen05.mma (M128 x N x K16, bf16 -> fp32 in TMEM) and
+//               tcgen05.commit's the smem slot back to the producer / the accumulator to the epilogue;
+//   warps 2-9   epilogue (two warps per TMEM lane quadrant, each owning half of the tile's columns):
+//               tcgen05.ld the accumulator (one pixel per thread), apply bias / FiLM / SiLU|GELU / GEGLU /
+//               channel-LayerNorm / q-softmax / residuals in fp32, store NHWC bf16 (and/or fp32, or fp32 NCHW for
+//               final_conv).  Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
+// The epilogue flavour is a template parameter (separate small kernels: the instruction cache matters - a single
+// kernel with every flavour behind runtime flags was 150 KB of SASS and stalled 16 % of the time on fetch).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "../../include/dac_b200.h"
+#include "ptx.cuh"
+
+namespace dac {
+
+constexpr int kTileM = 128;
+constexpr int kChunkK = 64;   // bf16 per K step = one 128 B swizzle row
+constexpr int kThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
+constexpr int kEpiWarps = 8;
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kAccStride = 256;
+constexpr uint32_t kABytes = kTileM * kChunkK * 2;  // 16 KB
+constexpr int kMaxStages = 8;
+
+enum { KE_PLAIN = 0, KE_GEGLU = 1, KE_LN = 2, KE_QKV = 3, KE_NCHW = 4 };
+
+struct ConvKParams {
+  int B, OH, OW, stride;
+  int tile_h, tile_w, tiles_x, tiles_y, m_tiles;
+  int n_tiles, block_n, ngroups, ntaps;
+  int chunks0, chunks1, c0;
+  int per_image_w;
+  int stages;
+  uint32_t b_bytes;
+  int8_t tap_dy[4][16];
+  int8_t tap_dx[4][16];
+  // epilogue
+  int cout;
+  const float* bias;
+  const float* bias_img;
+  const float* film;
+  int film_ld, film_off;
+  const float* ln_g;
+  float ln_eps;
+  const __nv_bfloat16* res;
+  int res_ld;
+  const __nv_bfloat16* res2;
+  int res2_ld;
+  __nv_bfloat16* out;
+  int out_ld, out_coff;
+  const float* res_f32;
+  int res_f32_ld;
+  float* out_f32;
+  int out_f32_ld;
+  int out_scale, OHf, OWf;
+  int8_t out_oy[4], out_ox[4];
+  float* out_nchw;
+  int nchw_c, nchw_h, nchw_w;
+};
+
+struct TileCoord {
+  int g, nt, n, y0, x0;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const ConvKParams& p, int tile) {
+  TileCoord t;
+  t.nt = tile % p.n_tiles;
+  int rest = tile / p.n_tiles;
+  int mt = rest % p.m_tiles;
+  t.g = rest / p.m_tiles;
+  int tx = mt % p.tiles_x;
+  int r2 = mt / p.tiles_x;
+  int ty = r2 % p.tiles_y;
+  t.n = r2 / p.tiles_y;
+  t.y0 = ty * p.tile_h;
+  t.x0 = tx * p.tile_w;
+  return t;
+}
+
+template <int ACT>
+__device__ __forceinline__ float apply_act(float v) {
+  if (ACT == DAC_ACT_SILU) return silu_f(v);
+  if (ACT == DAC_ACT_GELU) return gelu_f(v);
+  return v;
+}
+
+// ---- 32-column chunk helpers: everything statically indexed so the chunk lives in registers ----
+__device__ __forceinline__ void chunk_from_tmem(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  tmem_ld32(taddr, r);
+  tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+}
+__device__ __forceinline__ void chunk_add_f32(const float* __restrict__ src, float (&v)[32]) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src) + q);
+    v[4 * q] += a.x; v[4 * q + 1] += a.y; v[4 * q + 2] += a.z; v[4 * q + 3] += a.w;
+  }
+}
+__device__ __forceinline__ void chunk_film(const float* __restrict__ sc, const float* __restrict__ sh,
+                                           float (&v)[32]) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(sc) + q);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(sh) + q);
+    v[4 * q] = fmaf(v[4 * q], a.x + 1.0f, b.x);
+    v[4 * q + 1] = fmaf(v[4 * q + 1], a.y + 1.0f, b.y);
+    v[4 * q + 2] = fmaf(v[4 * q + 2], a.z + 1.0f, b.z);
+    v[4 * q + 3] = fmaf(v[4 * q + 3], a.w + 1.0f, b.w);
+  }
+}
+__device__ __forceinline__ void chunk_add_bf16(const __nv_bfloat16* __restrict__ src, float (&v)[32]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(src) + q);
+    const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+    v[q * 8 + 0] += a.x; v[q * 8 + 1] += a.y; v[q * 8 + 2] += b.x; v[q * 8 + 3] += b.y;
+    v[q * 8 + 4] += c.x; v[q * 8 + 5] += c.y; v[q * 8 + 6] += d.x; v[q * 8 + 7] += d.y;
+  }
+}
+__device__ __forceinline__ void chunk_store_bf16(__nv_bfloat16* __restrict__ dst, const float (&v)[32]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint4 u;
+    u.x = pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
+    u.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
+    u.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
+    u.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
+    reinterpret_cast<uint4*>(dst)[q] = u;
+  }
+}
+__device__ __forceinline__ void chunk_store_f32(float* __restrict__ dst, const float (&v)[32]) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+    reinterpret_cast<float4*>(dst)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+}
+
+// Epilogue of one 128 x block_n accumulator tile.  Thread = one output pixel (TMEM lane `row`); the warp pair of
+// a lane quadrant splits the columns: this thread owns columns [half*bn/2, (half+1)*bn/2).
+template <int EPI, int ACT, bool FILM>
+__device__ __forceinline__ void epilogue_tile(const ConvKParams& p, const TileCoord& t, uint32_t tmem_acc, int row,
+                                              int half) {
+  const int ty = row / p.tile_w, tx = row - ty * p.tile_w;
+  const int y = t.y0 + ty, x = t.x0 + tx;
+  const bool valid = (y < p.OH) && (x < p.OW);
+  const int Y = y * p.out_scale + p.out_oy[t.g], X = x * p.out_scale + p.out_ox[t.g];
+  const long long opix = (static_cast<long long>(t.n) * p.OHf + Y) * p.OWf + X;
+  const int n = t.n;
+  float v[32];
+
+  if (EPI == KE_NCHW) {
+    // final_conv: 16-column tile, fp32 planar output cropped to the un-padded image; one warp per quadrant works.
+    if (half != 0) return;
+    uint32_t r[16];
+    tmem_ld16(tmem_acc, r);
+    tmem_ld_wait();
+    if (valid && Y < p.nchw_h && X < p.nchw_w) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        if (j < p.nchw_c) {
+          const float o = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + j) : 0.f);
+          p.out_nchw[((static_cast<long long>(n) * p.nchw_c + j) * p.nchw_h + Y) * p.nchw_w + X] = o;
+        }
+      }
+    }
+    return;
+  }
+
+  if (EPI == KE_LN) {
+    // channel LayerNorm over the whole (single) N tile; both warps of a quadrant sweep all columns for the
+    // statistics (TMEM reads are cheap), each normalises and stores its own half.
+    const int C = p.cout;
+    float sum = 0.f;
+    for (int c = 0; c < C; c += 32) {
+      chunk_from_tmem(tmem_acc + c, v);
+      if (p.bias) chunk_add_f32(p.bias + c, v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) sum += v[j];
+    }
+    const float mean = sum / C;
+    float ss = 0.f;
+    for (int c = 0; c < C; c += 32) {
+      chunk_from_tmem(tmem_acc + c, v);
+      if (p.bias) chunk_add_f32(p.bias + c, v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float d = v[j] - mean;
+        ss = fmaf(d, d, ss);
+      }
+    }
+    const float rstd = rsqrtf(ss / C + p.ln_eps);
+    const int c0 = half * (C >> 1);
+    for (int c = c0; c < c0 + (C >> 1); c += 32) {
+      chunk_from_tmem(tmem_acc + c, v);
+      if (p.bias) chunk_add_f32(p.bias + c, v);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(p.ln_g + c) + q);
+        v[4 * q] = (v[4 * q] - mean) * rstd * g.x;
+        v[4 * q + 1] = (v[4 * q + 1] - mean) * rstd * g.y;
+        v[4 * q + 2] = (v[4 * q + 2] - mean) * rstd * g.z;
+        v[4 * q + 3] = (v[4 * q + 3] - mean) * rstd * g.w;
+      }
+      if (valid) {
+        if (p.res) chunk_add_bf16(p.res + opix * p.res_ld + c, v);
+        chunk_store_bf16(p.out + opix * p.out_ld + p.out_coff + c, v);
+      }
+    }
+    return;
+  }
+
+  if (EPI == KE_GEGLU) {
+    const int hn = p.block_n >> 1, qn = p.block_n >> 2;
+    for (int c = half * qn; c < (half + 1) * qn; c += 32) {
+      float g[32];
+      chunk_from_tmem(tmem_acc + c, v);
+      chunk_from_tmem(tmem_acc + hn + c, g);
+      const int col = t.nt * p.block_n + c;  // column in the (permuted) weight / bias row order
+      chunk_add_f32(p.bias + col, v);
+      chunk_add_f32(p.bias + col + hn, g);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] *= gelu_f(g[j]);
+      if (valid) chunk_store_bf16(p.out + opix * p.out_ld + p.out_coff + t.nt * hn + c, v);
+    }
+    return;
+  }
+
+  // KE_PLAIN / KE_QKV
+  const int hn = p.block_n >> 1;
+  for (int c = half * hn; c < (half + 1) * hn; c += 32) {
+    const int ch = t.nt * p.block_n + c;
+    if (ch >= p.cout) break;  // warp-uniform (cout_pad > cout)
+    chunk_from_tmem(tmem_acc + c, v);
+    if (EPI == KE_QKV) {
+      if (t.nt == 0) {  // q: softmax over the 32 channels of one head, times dim_head^-0.5
+        float m = v[0];
+#pragma unroll
+        for (int j = 1; j < 32; ++j) m = fmaxf(m, v[j]);
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          v[j] = exp2f((v[j] - m) * 1.4426950408889634f);
+          s += v[j];
+        }
+        const float inv = __fdividef(0.17677669529663687f, s);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] *= inv;
+      }
+      if (valid) chunk_store_bf16(p.out + opix * p.out_ld + p.out_coff + ch, v);
+      continue;
+    }
+    if (p.bias) chunk_add_f32(p.bias + ch, v);
+    if (p.bias_img) chunk_add_f32(p.bias_img + static_cast<long long>(n) * p.cout + ch, v);
+    if (FILM) {
+      const float* sc = p.film + static_cast<long long>(n) * p.film_ld + p.film_off + ch;
+      chunk_film(sc, sc + p.cout, v);
+    }
+    if (ACT != DAC_ACT_NONE) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = apply_act<ACT>(v[j]);
+    }
+    if (valid) {
+      if (p.res_f32) chunk_add_f32(p.res_f32 + opix * p.res_f32_ld + ch, v);
+      if (p.res) chunk_add_bf16(p.res + opix * p.res_ld + ch, v);
+      if (p.res2) chunk_add_bf16(p.res2 + opix * p.res2_ld + ch, v);
+      if (p.out_f32) chunk_store_f32(p.out_f32 + opix * p.out_f32_ld + ch, v);
+      if (p.out) chunk_store_bf16(p.out + opix * p.out_ld + p.out_coff + ch, v);
+    }
+  }
+}
+
+template <int EPI, int ACT, bool FILM>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+                  const __grid_constant__ CUtensorMap mapW, const __grid_constant__ ConvKParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024 B alignment is required by the 128B swizzle atoms (TMA write and UMMA read agree on address bits).
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t stage_bytes = kABytes + p.b_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(p.stages) * stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kMaxStages;
+  uint64_t* tmem_full = bars + 2 * kMaxStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.ngroups * p.m_tiles * p.n_tiles;
+  const int k_steps = p.ntaps * (p.chunks0 + p.chunks1);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA0);
+    tma_prefetch_desc(&mapA1);
+    tma_prefetch_desc(&mapW);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], kEpiWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+#ifdef DAC_DEBUG
+  if (threadIdx.x == 0 && blockIdx.x == 0)
+    printf("[conv] tiles=%d k_steps=%d stages=%d block_n=%d tmem_base=%08x OH=%d OW=%d out=%p cout=%d epi=%d\n",
+           total_tiles, k_steps, p.stages, p.block_n, tmem_base, p.OH, p.OW, p.out, p.cout, EPI);
+#endif
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile);
+        const int xin = t.x0 * p.stride, yin = t.y0 * p.stride;
+        const int zbase = (p.per_image_w ? t.n * p.ngroups * p.ntaps : 0) + t.g * p.ntaps;
+        for (int tap = 0; tap < p.ntaps; ++tap) {
+          const int dy = p.tap_dy[t.g][tap], dx = p.tap_dx[t.g][tap];
+          for (int ck = 0; ck < p.chunks0 + p.chunks1; ++ck) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
+            mbar_arrive_expect_tx(&full[stage], stage_bytes);
+            if (ck < p.chunks0)
+              tma_load_4d(sa, &mapA0, &full[stage], ck * kChunkK, xin + dx, yin + dy, t.n);
+            else
+              tma_load_4d(sa, &mapA1, &full[stage], (ck - p.chunks0) * kChunkK, xin + dx, yin + dy, t.n);
+            tma_load_3d(sa + kABytes, &mapW, &full[stage], ck * kChunkK, t.nt * p.block_n, zbase + tap);
+            if (++stage == p.stages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = make_idesc_bf16(kTileM, p.block_n);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * kAccStride;
+      for (int ks = 0; ks < k_steps; ++ks) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
+          const uint64_t adesc = make_sw128_desc(a_addr);
+          const uint64_t bdesc = make_sw128_desc(a_addr + kABytes);
+#pragma unroll
+          for (int k = 0; k < kChunkK / 16; ++k)
+            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | k) != 0 ? 1u : 0u);
+          umma_commit(&empty[stage]);
+          if (ks == k_steps - 1) umma_commit(&tmem_full[acc]);
+        }
+        __syncwarp();
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ===================== epilogue warps (2..9) =====================
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;
+    const int row = quad * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile);
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kAccStride;
+      epilogue_tile<EPI, ACT, FILM>(p, t, tmem_acc, row, half);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+typedef void (*ConvKernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const ConvKParams);
+
+// The epilogue flavours that exist as separate kernels; everything else in the epilogue is a warp-uniform
+// runtime branch on a pointer.
+inline ConvKernelFn pick_conv_kernel(int epi, int act, bool film, bool nchw) {
+  if (nchw) return conv_igemm_kernel<KE_NCHW, DAC_ACT_NONE, false>;
+  if (epi == DAC_EPI_GEGLU) return conv_igemm_kernel<KE_GEGLU, DAC_ACT_NONE, false>;
+  if (epi == DAC_EPI_LN) return conv_igemm_kernel<KE_LN, DAC_ACT_NONE, false>;
+  if (epi == DAC_EPI_QKV) return conv_igemm_kernel<KE_QKV, DAC_ACT_NONE, false>;
+  if (act == DAC_ACT_SILU)
+    return film ? conv_igemm_kernel<KE_PLAIN, DAC_ACT_SILU, true> : conv_igemm_kernel<KE_PLAIN, DAC_ACT_SILU, false>;
+  if (act == DAC_ACT_GELU && !film) return conv_igemm_kernel<KE_PLAIN, DAC_ACT_GELU, false>;
+  if (act == DAC_ACT_NONE && !film) return conv_igemm_kernel<KE_PLAIN, DAC_ACT_NONE, false>;
+  return nullptr;
+}
+
+}  // namespace dac

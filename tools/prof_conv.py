@@ -1,0 +1,55 @@
+"""Runs a few representative conv plans repeatedly (for ncu / quick timing).  usage: prof_conv.py [case ...]"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from daclip_b200 import lib as L, ops
+
+CASES = {
+    # name: (B, H, W, cin, cout, kind)
+    "l0_3x3": (16, 256, 256, 64, 64, "3x3"),
+    "l0_3x3_cat": (16, 256, 256, 128, 64, "3x3"),
+    "l0_qkv": (16, 256, 256, 64, 384, "qkv"),
+    "l1_3x3": (16, 128, 128, 128, 128, "3x3"),
+    "l2_3x3": (16, 64, 64, 256, 256, "3x3"),
+    "l3_3x3": (16, 32, 32, 512, 512, "3x3"),
+    "l3_geglu": (16, 32, 32, 512, 4096, "geglu"),
+    "l0_1x1": (16, 256, 256, 128, 64, "1x1"),
+}
+
+def make(name):
+    B, H, W, cin, cout, kind = CASES[name]
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(B, H, W, cin, device="cuda", generator=g).to(torch.bfloat16)
+    out_c = cout // 2 if kind == "geglu" else cout
+    out = torch.zeros(B, H, W, out_c, device="cuda", dtype=torch.bfloat16)
+    if kind == "3x3":
+        w = torch.randn(cout, cin, 3, 3, device="cuda", generator=g) * (9 * cin) ** -0.5
+        film = torch.randn(B, 2 * cout, device="cuda", generator=g) * 0.1
+        plan = ops.ConvPlan(x, cin, ops.pack_conv(w), out, B=B, H=H, W=W, act=L.ACT_SILU, film=film)
+    elif kind == "qkv":
+        w = torch.randn(cout, cin, device="cuda", generator=g) * cin ** -0.5
+        plan = ops.ConvPlan(x, cin, ops.pack_linear(w), out, B=B, H=H, W=W, epi=L.EPI_QKV, block_n=128)
+    elif kind == "geglu":
+        w = torch.randn(cout, cin, device="cuda", generator=g) * cin ** -0.5
+        b = torch.randn(cout, device="cuda", generator=g)
+        pw, bp = ops.pack_geglu(w, b)
+        plan = ops.ConvPlan(x, cin, pw, out, B=B, H=H, W=W, epi=L.EPI_GEGLU, bias=bp, block_n=256)
+    else:
+        w = torch.randn(cout, cin, device="cuda", generator=g) * cin ** -0.5
+        plan = ops.ConvPlan(x, cin, ops.pack_linear(w), out, B=B, H=H, W=W)
+    return plan
+
+names = sys.argv[1:] or list(CASES)
+for name in names:
+    plan = make(name)
+    for _ in range(3):
+        plan.run()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(5):
+        plan.run()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / 5
+    print(f"{name:12s} {ms*1e3:9.1f} us  {plan.flops/ms/1e9:8.1f} TFLOP/s  {plan.info()}", flush=True)
