@@ -121,7 +121,7 @@ def conv_time_per_eval(eng, reps=3):
         total = sum(a.elapsed_time(b) for n, a, b in evs)
         if best is None or total < best[1]:
             best = (conv, total, sum(1 for n, _, _ in evs if eng.is_conv(n)),
-                    sorted(((a.elapsed_time(b), n) for n, a, b in evs), reverse=True)[:8])
+                    sorted(((a.elapsed_time(b), n) for n, a, b in evs), reverse=True)[:30])
     return best
 
 

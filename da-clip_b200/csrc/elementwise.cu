@@ -109,57 +109,71 @@ __global__ void __launch_bounds__(256) stem_input_kernel(const float* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------ row LayerNorm
-// One warp per row, 16 B vector loads; the row is re-read from L1/L2 for the variance and the write pass.
+// LPR lanes cooperate on one row (8 lanes for 64 channels ... 32 lanes for >= 256), so a warp covers 32/LPR rows and
+// every lane moves 16 B vectors; the row is read ONCE and kept in registers (c <= LPR * 8 * VPL).
+template <int LPR, int VPL>
 __global__ void __launch_bounds__(256) layernorm_rows_kernel(const __nv_bfloat16* __restrict__ in, int ld_in,
                                                              __nv_bfloat16* __restrict__ out, int ld_out, int64_t rows,
                                                              int c, const float* __restrict__ w,
                                                              const float* __restrict__ b, float eps) {
   const int lane = threadIdx.x & 31;
+  const int sub = lane % LPR;
+  const int rows_per_warp = 32 / LPR;
   const int64_t warp_global = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
   const int nvec = c >> 3;
-  for (int64_t row = warp_global; row < rows; row += nwarps) {
-    const uint4* src = reinterpret_cast<const uint4*>(in + row * ld_in);
+  const float inv_c = 1.0f / c;
+  for (int64_t row0 = warp_global * rows_per_warp; row0 < rows; row0 += nwarps * rows_per_warp) {
+    const int64_t row = row0 + lane / LPR;
+    const bool live = row < rows;
+    float v[VPL][8];
     float sum = 0.f;
-    for (int i = lane; i < nvec; i += 32) {
-      const uint4 u = src[i];
-      const float2 a = unpack_bf16(u.x), bb = unpack_bf16(u.y), cc = unpack_bf16(u.z), d = unpack_bf16(u.w);
-      sum += (a.x + a.y) + (bb.x + bb.y) + (cc.x + cc.y) + (d.x + d.y);
-    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    const float mean = sum / c;
-    float ss = 0.f;
-    for (int i = lane; i < nvec; i += 32) {
-      const uint4 u = src[i];
-      const float2 a = unpack_bf16(u.x), bb = unpack_bf16(u.y), cc = unpack_bf16(u.z), d = unpack_bf16(u.w);
-      const float e0 = a.x - mean, e1 = a.y - mean, e2 = bb.x - mean, e3 = bb.y - mean;
-      const float e4 = cc.x - mean, e5 = cc.y - mean, e6 = d.x - mean, e7 = d.y - mean;
-      ss += e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3 + e4 * e4 + e5 * e5 + e6 * e6 + e7 * e7;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    const float rstd = rsqrtf(ss / c + eps);
-    uint4* dst = reinterpret_cast<uint4*>(out + row * ld_out);
-    for (int i = lane; i < nvec; i += 32) {
-      const uint4 u = src[i];
-      float v[8];
+    for (int i = 0; i < VPL; ++i) {
+      const int vi = sub + i * LPR;
+      uint4 u = make_uint4(0, 0, 0, 0);
+      if (live && vi < nvec) u = __ldg(reinterpret_cast<const uint4*>(in + row * ld_in) + vi);
       float2 t;
-      t = unpack_bf16(u.x); v[0] = t.x; v[1] = t.y;
-      t = unpack_bf16(u.y); v[2] = t.x; v[3] = t.y;
-      t = unpack_bf16(u.z); v[4] = t.x; v[5] = t.y;
-      t = unpack_bf16(u.w); v[6] = t.x; v[7] = t.y;
+      t = unpack_bf16(u.x); v[i][0] = t.x; v[i][1] = t.y;
+      t = unpack_bf16(u.y); v[i][2] = t.x; v[i][3] = t.y;
+      t = unpack_bf16(u.z); v[i][4] = t.x; v[i][5] = t.y;
+      t = unpack_bf16(u.w); v[i][6] = t.x; v[i][7] = t.y;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float y = (v[j] - mean) * rstd;
-        if (w) y *= __ldg(w + i * 8 + j);
-        if (b) y += __ldg(b + i * 8 + j);
-        v[j] = y;
+      for (int j = 0; j < 8; ++j) sum += v[i][j];
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum * inv_c;
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      if (sub + i * LPR < nvec) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float d = v[i][j] - mean;
+          ss = fmaf(d, d, ss);
+        }
       }
-      uint4 o;
-      o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]);
-      o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
-      dst[i] = o;
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float rstd = rsqrtf(ss * inv_c + eps);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int vi = sub + i * LPR;
+      if (live && vi < nvec) {
+        float y[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          y[j] = (v[i][j] - mean) * rstd;
+          if (w) y[j] *= __ldg(w + vi * 8 + j);
+          if (b) y[j] += __ldg(b + vi * 8 + j);
+        }
+        uint4 o;
+        o.x = pack_bf16(y[0], y[1]); o.y = pack_bf16(y[2], y[3]);
+        o.z = pack_bf16(y[4], y[5]); o.w = pack_bf16(y[6], y[7]);
+        reinterpret_cast<uint4*>(out + row * ld_out)[vi] = o;
+      }
     }
   }
 }
@@ -287,6 +301,9 @@ __device__ __forceinline__ void block_linear(const float* __restrict__ W, const 
   }
 }
 
+// MODE 0: per step   - time MLP, + prompt embedding (precomputed per restoration), SiLU -> temb_out
+// MODE 1: per restoration - text_mlp / softmax*prompt / prompt_mlp of the degradation context -> temb_out
+template <int MODE>
 __global__ void __launch_bounds__(256) time_embed_kernel(dac_embed_weights w, const float* __restrict__ time_ptr,
                                                          const float* __restrict__ text_ctx,
                                                          float* __restrict__ temb_out) {
@@ -297,6 +314,7 @@ __global__ void __launch_bounds__(256) time_embed_kernel(dac_embed_weights w, co
   float* t = h + td;
   float* q = t + td;
   const int b = blockIdx.x;
+  if (MODE == 0) {
   const float time = __ldg(time_ptr);
   // sinusoidal embedding (module_util.py:41-48): [sin | cos], freq_i = exp(-i ln(1e4)/(half-1))
   const int half = w.nf / 2;
@@ -313,7 +331,14 @@ __global__ void __launch_bounds__(256) time_embed_kernel(dac_embed_weights w, co
   __syncthreads();
   block_linear(w.time_w2, w.time_b2, h, t, td, td);
   __syncthreads();
-  if (w.text_w1 != nullptr && text_ctx != nullptr) {
+  // text_ctx holds the precomputed prompt embedding [B, td] here
+  for (int i = threadIdx.x; i < td; i += blockDim.x) {
+    const float v = t[i] + (text_ctx ? text_ctx[static_cast<int64_t>(b) * td + i] : 0.f);
+    temb_out[static_cast<int64_t>(b) * td + i] = v / (1.0f + expf(-v));   // every ResBlock mlp starts with SiLU
+  }
+  return;
+  }
+  {
     for (int i = threadIdx.x; i < w.ctx_dim; i += blockDim.x) a[i] = text_ctx[static_cast<int64_t>(b) * w.ctx_dim + i];
     __syncthreads();
     block_linear(w.text_w1, w.text_b1, a, h, td, w.ctx_dim);
@@ -341,35 +366,35 @@ __global__ void __launch_bounds__(256) time_embed_kernel(dac_embed_weights w, co
     __syncthreads();
     block_linear(w.prompt_w, w.prompt_b, h, q, td, td);
     __syncthreads();
-    for (int i = threadIdx.x; i < td; i += blockDim.x) t[i] += q[i];
-    __syncthreads();
-  }
-  // every ResBlock mlp starts with SiLU (module_util.py:135-137): store silu(t_emb)
-  for (int i = threadIdx.x; i < td; i += blockDim.x) {
-    const float v = t[i];
-    temb_out[static_cast<int64_t>(b) * td + i] = v / (1.0f + expf(-v));
+    for (int i = threadIdx.x; i < td; i += blockDim.x) temb_out[static_cast<int64_t>(b) * td + i] = q[i];
   }
 }
 
 __global__ void __launch_bounds__(256) film_kernel(const float* __restrict__ W, const float* __restrict__ bias,
                                                    const float* __restrict__ s, float* __restrict__ film, int F, int k,
                                                    int B) {
-  // one warp per output feature f, looping over images; W row held in registers (k <= 256 -> 8 per lane)
+  // silu(t_emb) of every image staged in shared memory; one warp per output feature f (grid-stride), its weight
+  // row held in registers (k <= 256 -> 8 per lane), looping over the images.
+  extern __shared__ float s_sh[];
+  for (int i = threadIdx.x; i < B * k; i += blockDim.x) s_sh[i] = s[i];
+  __syncthreads();
   const int lane = threadIdx.x & 31;
-  const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (f >= F) return;
-  float wr[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) wr[j] = (lane + 32 * j < k) ? __ldg(W + static_cast<int64_t>(f) * k + lane + 32 * j) : 0.f;
-  const float bf = __ldg(bias + f);
-  for (int b = 0; b < B; ++b) {
-    float acc = 0.f;
+  const int nw = (gridDim.x * blockDim.x) >> 5;
+  for (int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; f < F; f += nw) {
+    float wr[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j)
-      if (lane + 32 * j < k) acc += wr[j] * __ldg(s + static_cast<int64_t>(b) * k + lane + 32 * j);
+      wr[j] = (lane + 32 * j < k) ? __ldg(W + static_cast<int64_t>(f) * k + lane + 32 * j) : 0.f;
+    const float bf = __ldg(bias + f);
+    for (int b = 0; b < B; ++b) {
+      float acc = 0.f;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) film[static_cast<int64_t>(b) * F + f] = acc + bf;
+      for (int j = 0; j < 8; ++j)
+        if (lane + 32 * j < k) acc = fmaf(wr[j], s_sh[b * k + lane + 32 * j], acc);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) film[static_cast<int64_t>(b) * F + f] = acc + bf;
+    }
   }
 }
 
@@ -436,10 +461,21 @@ extern "C" int dac_layernorm_rows(const void* in, int32_t ld_in, void* out, int3
   if (!in || !out) return set_error(-1, "dac_layernorm_rows: null argument");
   if ((c & 7) || (ld_in & 7) || (ld_out & 7)) return set_error(-2, "dac_layernorm_rows: c and pitches must be multiples of 8");
   if (rows <= 0) return 0;
-  const int64_t blocks = ceil_div(rows, 8);
-  const int grid = static_cast<int>(blocks > 148 * 8 ? 148 * 8 : blocks);
-  layernorm_rows_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(in), ld_in, static_cast<__nv_bfloat16*>(out), ld_out, rows, c, w, b, eps);
+  if (c > 1024) return set_error(-2, "dac_layernorm_rows: c must be <= 1024");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const __nv_bfloat16* ip = static_cast<const __nv_bfloat16*>(in);
+  __nv_bfloat16* op = static_cast<__nv_bfloat16*>(out);
+  const int nvec = c >> 3;
+  const int lpr = nvec <= 8 ? 8 : (nvec <= 16 ? 16 : 32);
+  const int64_t warps = ceil_div(rows, 32 / lpr);
+  int64_t blocks = ceil_div(warps, 8);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  const int grid = static_cast<int>(blocks);
+  if (lpr == 8) layernorm_rows_kernel<8, 1><<<grid, 256, 0, st>>>(ip, ld_in, op, ld_out, rows, c, w, b, eps);
+  else if (lpr == 16) layernorm_rows_kernel<16, 1><<<grid, 256, 0, st>>>(ip, ld_in, op, ld_out, rows, c, w, b, eps);
+  else if (nvec <= 32) layernorm_rows_kernel<32, 1><<<grid, 256, 0, st>>>(ip, ld_in, op, ld_out, rows, c, w, b, eps);
+  else if (nvec <= 64) layernorm_rows_kernel<32, 2><<<grid, 256, 0, st>>>(ip, ld_in, op, ld_out, rows, c, w, b, eps);
+  else layernorm_rows_kernel<32, 4><<<grid, 256, 0, st>>>(ip, ld_in, op, ld_out, rows, c, w, b, eps);
   return check_launch("layernorm_rows_kernel");
 }
 
@@ -474,19 +510,39 @@ extern "C" int dac_groupnorm_nhwc(const void* in, void* out, int32_t B, int32_t 
   return check_launch("groupnorm_apply_kernel");
 }
 
-extern "C" int dac_time_film(const dac_embed_weights* w, const float* time, const float* text_ctx, int32_t B,
+static size_t embed_smem(const dac_embed_weights* w) {
+  int amax = w->time_dim > w->ctx_dim ? w->time_dim : w->ctx_dim;
+  if (w->nf > amax) amax = w->nf;
+  return sizeof(float) * (amax + 3 * w->time_dim);
+}
+
+extern "C" int dac_prompt_embed(const dac_embed_weights* w, const float* text_ctx, int32_t B, float* prompt_emb,
+                                dac_stream_t stream) {
+  if (!w || !text_ctx || !prompt_emb || !w->text_w1) return set_error(-1, "dac_prompt_embed: null argument");
+  if (w->time_dim > 256 || w->time_dim % 32) return set_error(-2, "dac_prompt_embed: time_dim must be <= 256");
+  time_embed_kernel<1><<<B, 256, embed_smem(w), static_cast<cudaStream_t>(stream)>>>(*w, nullptr, text_ctx, prompt_emb);
+  return check_launch("time_embed_kernel<prompt>");
+}
+
+extern "C" int dac_time_film(const dac_embed_weights* w, const float* time, const float* prompt_emb, int32_t B,
                              float* temb_scratch, float* film, dac_stream_t stream) {
   if (!w || !time || !temb_scratch || !film) return set_error(-1, "dac_time_film: null argument");
   if (w->time_dim > 256 || w->time_dim % 32) return set_error(-2, "dac_time_film: time_dim must be <= 256");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int td = w->time_dim;
-  int amax = td > w->ctx_dim ? td : w->ctx_dim;
-  if (w->nf > amax) amax = w->nf;
-  const size_t sh = sizeof(float) * (amax + 3 * td);
-  time_embed_kernel<<<B, 256, sh, s>>>(*w, time, text_ctx, temb_scratch);
+  time_embed_kernel<0><<<B, 256, embed_smem(w), s>>>(*w, time, prompt_emb, temb_scratch);
   int rc = check_launch("time_embed_kernel");
   if (rc) return rc;
-  film_kernel<<<static_cast<int>(ceil_div(w->F, 8)), 256, 0, s>>>(w->film_w, w->film_b, temb_scratch, film, w->F, td, B);
+  const size_t fsh = sizeof(float) * B * td;
+  if (fsh > 160 * 1024) return set_error(-2, "dac_time_film: batch too large for the FiLM kernel's shared memory");
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(film_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    attr_done = true;
+  }
+  int grid = static_cast<int>(ceil_div(w->F, 8 * 4));
+  if (grid > 296) grid = 296;
+  film_kernel<<<grid, 256, fsh, s>>>(w->film_w, w->film_b, temb_scratch, film, w->F, td, B);
   return check_launch("film_kernel");
 }
 

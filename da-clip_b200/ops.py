@@ -239,8 +239,12 @@ def groupnorm_nhwc(x, out, B, hw, c, w, b, stats, groups=32, eps=1e-6):
                                         L.ptr(stats), L.stream_ptr()))
 
 
-def time_film(ew, time, text_ctx, B, temb, film):
-    L.check(L.load().dac_time_film(C.byref(ew), L.ptr(time), L.ptr(text_ctx), B, L.ptr(temb), L.ptr(film),
+def prompt_embed(ew, text_ctx, B, prompt_emb):
+    L.check(L.load().dac_prompt_embed(C.byref(ew), L.ptr(text_ctx), B, L.ptr(prompt_emb), L.stream_ptr()))
+
+
+def time_film(ew, time, prompt_emb, B, temb, film):
+    L.check(L.load().dac_time_film(C.byref(ew), L.ptr(time), L.ptr(prompt_emb), B, L.ptr(temb), L.ptr(film),
                                    L.stream_ptr()))
 
 

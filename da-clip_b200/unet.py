@@ -335,6 +335,8 @@ class UNetEngine:
         self.t_dev = torch.zeros(1, **f32)
         self.out_noise = torch.zeros(B, 3, H, W, **f32)
         self.temb = torch.zeros(B, cfg.time_dim, **f32)
+        self.prompt_emb = torch.zeros(B, cfg.time_dim, **f32)
+        self.pre_steps = []      # step-invariant launches: run once per set_inputs, outside the per-step graph
         self.film = torch.zeros(B, pk.F, **f32)
         self.use_text = False
         self.steps = []          # (name, callable)
@@ -414,8 +416,8 @@ class UNetEngine:
         self.add(prefix + "attn1", lambda: ops.attention(qkv, att, B, hw, heads, 32))
         self.flops += 4.0 * B * heads * hw * hw * 32
         cvec = self.buf(B, C, dtype=torch.float32)
-        self.add(prefix + "attn2.const", lambda: ops.two_linear(self.image_ctx, a["cross_v"], a["cross_o"],
-                                                                a["cross_ob"], cvec))
+        # constant over tokens AND over the T steps: computed once per restoration (set_inputs), not per step
+        self.pre_steps.append(lambda: ops.two_linear(self.image_ctx, a["cross_v"], a["cross_o"], a["cross_ob"], cvec))
         y2 = self.buf(B, h, w, C)
         self.conv(prefix + "attn1.to_out", att, C, a["attn1_out"], y2, h, w, bias=a["attn1_out_b"], bias_img=cvec,
                   res=y0)
@@ -436,7 +438,10 @@ class UNetEngine:
             raise L.DacError("inconsistent config")
         stem = self.buf(B, Hp, Wp, 64)
         self.add("stem_input", lambda: ops.stem_input(self.xt, self.cond, stem, self.H, self.W))
-        self.add("time_film", lambda: ops.time_film(pk.ew, self.t_dev, self.text_ctx if self.use_text else None, B,
+        if pk.has_prompt:
+            self.pre_steps.append(lambda: ops.prompt_embed(pk.ew, self.text_ctx, B, self.prompt_emb)
+                                  if self.use_text else None)
+        self.add("time_film", lambda: ops.time_film(pk.ew, self.t_dev, self.prompt_emb if self.use_text else None, B,
                                                     self.temb, self.film))
         x0 = self.buf(B, Hp, Wp, 64)
         self.conv("init_conv", stem, 64, pk.stem, x0, Hp, Wp)
@@ -515,6 +520,8 @@ class UNetEngine:
                 raise NotImplementedError("SpatialTransformer without image_context (self-attention fallback of "
                                           "attention.py:171) is not on the restoration path")
             self.image_ctx.copy_(image_context.reshape(self.B, -1))
+        for fn in self.pre_steps:
+            fn()
 
     def set_time(self, time):
         if torch.is_tensor(time):

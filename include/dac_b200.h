@@ -130,8 +130,12 @@ typedef struct dac_embed_weights {
   const float *film_w, *film_b;                             /* [F,256],[F] */
   int32_t nf, time_dim, ctx_dim, F;
 } dac_embed_weights;
+/* Per restoration (step-invariant): prompt_emb[b] = prompt_mlp(softmax(text_mlp(text_ctx[b])) * prompt)  ARCH:134-136 */
+int dac_prompt_embed(const dac_embed_weights* w, const float* text_ctx /*[B,ctx]*/, int32_t B,
+                     float* prompt_emb /*[B,time_dim]*/, dac_stream_t stream);
+/* Per step: silu(time_mlp(t) + prompt_emb[b]) -> temb_scratch, then the stacked ResBlock mlp linears -> film. */
 int dac_time_film(const dac_embed_weights* w, const float* time /*device scalar: one CUDA graph serves every step*/,
-                  const float* text_ctx /*[B,ctx] or NULL*/, int32_t B,
+                  const float* prompt_emb /*[B,time_dim] or NULL*/, int32_t B,
                   float* temb_scratch /*[B,time_dim]*/, float* film /*[B,F]*/, dac_stream_t stream);
 /* out[b, :] = W2 (W1 x[b]) + b2  -- the exact value of cross-attention over a 1-token context
  * (ATT:152-193 with len(context)=1: softmax of one logit == 1).  W1 [mid,in], W2 [out,mid] fp32. */

@@ -379,9 +379,13 @@ def test_time_film_and_cross_vec(ops, gen):
     ew.nf, ew.time_dim, ew.ctx_dim, ew.F = 64, 256, 512, F_
     temb, film = torch.zeros(B, 256, device="cuda"), torch.zeros(B, F_, device="cuda")
     tdev = torch.zeros(1, device="cuda")
+    pemb = torch.zeros(B, 256, device="cuda")
+    ops.prompt_embed(ew, ctx, B, pemb)
+    torch.cuda.synchronize()
+    assert (pemb - O.prompt_embedding(sd, ctx)).abs().max().item() < 1e-4
     for t in (100.0, 37.0, 1.0):
         tdev.fill_(t)
-        ops.time_film(ew, tdev, ctx, B, temb, film)
+        ops.time_film(ew, tdev, pemb, B, temb, film)
         torch.cuda.synchronize()
         te = O.time_embedding(sd, torch.tensor([t], device="cuda"), 64) + O.prompt_embedding(sd, ctx)
         ref = F.linear(F.silu(te), fw, fb)
