@@ -48,12 +48,12 @@ struct dac_conv_plan {
 using namespace dac;
 
 static int encode_act_map(CUtensorMap* m, const void* ptr, int c, int ld, int W, int H, int B, int tile_w,
-                          int tile_h, int stride) {
+                          int box_rows, int stride) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return set_error(-10, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
   cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2};
-  cuuint32_t box[4] = {(cuuint32_t)kChunkK, (cuuint32_t)(tile_w * stride), (cuuint32_t)(tile_h * stride), 1};
+  cuuint32_t box[4] = {(cuuint32_t)kChunkK, (cuuint32_t)(tile_w * stride), (cuuint32_t)(box_rows * stride), 1};
   cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -73,7 +73,11 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
     return set_error(-2, "dac_conv_create: bad block_n %d / cout %d / cout_pad %d", d->block_n, d->cout, d->cout_pad);
   if (d->ntaps < 1 || d->ntaps > 16 || (d->ngroups != 1 && d->ngroups != 4) || (d->stride != 1 && d->stride != 2))
     return set_error(-2, "dac_conv_create: bad ntaps/ngroups/stride");
-  if (d->tile_w * d->stride > 256 || d->tile_h * d->stride > 256)
+  if (d->ndy < 1 || d->ncols < 1 || d->ndy * d->ncols != d->ntaps || (d->ndy > 1 && d->stride != 1))
+    return set_error(-2, "dac_conv_create: column groups (%d x %d) must cover the %d taps; ndy > 1 needs stride 1",
+                     d->ncols, d->ndy, d->ntaps);
+  const int a_rows = d->stride == 1 ? d->tile_h + d->ndy - 1 : d->tile_h;   // rows landed in shared memory
+  if (d->tile_w * d->stride > 256 || a_rows * d->stride > 256)
     return set_error(-2, "dac_conv_create: TMA box exceeds 256");
   if ((reinterpret_cast<uintptr_t>(d->src0) | reinterpret_cast<uintptr_t>(d->src1) |
        reinterpret_cast<uintptr_t>(d->weight) | reinterpret_cast<uintptr_t>(d->out) |
@@ -132,8 +136,12 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
   k.chunks0 = d->c0 / kChunkK; k.chunks1 = d->c1 / kChunkK; k.c0 = d->c0;
   k.per_image_w = d->per_image_w;
   k.b_bytes = (uint32_t)d->block_n * kChunkK * 2;
-  memcpy(k.tap_dy, d->tap_dy, sizeof(k.tap_dy));
-  memcpy(k.tap_dx, d->tap_dx, sizeof(k.tap_dx));
+  k.ndy = d->ndy; k.ncols = d->ncols;
+  memcpy(k.col_dx, d->col_dx, sizeof(k.col_dx));
+  memcpy(k.col_dy0, d->col_dy0, sizeof(k.col_dy0));
+  memcpy(k.col_tap, d->col_tap, sizeof(k.col_tap));
+  k.a_bytes = (uint32_t)a_rows * d->tile_w * kChunkK * 2;
+  k.row_shift = (uint32_t)d->tile_w * kChunkK * 2;
   k.cout = d->cout;
   pl->kernel = kernel;
   k.bias = d->bias; k.bias_img = d->bias_img;
@@ -149,19 +157,26 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
   memcpy(k.out_oy, d->out_oy, 4); memcpy(k.out_ox, d->out_ox, 4);
   k.out_nchw = d->out_nchw; k.nchw_c = d->out_nchw_c; k.nchw_h = d->out_nchw_h; k.nchw_w = d->out_nchw_w;
 
-  const uint32_t stage_bytes = kABytes + k.b_bytes;
+  // Weights stay resident in shared memory when the whole tensor fits beside >= 3 activation stages: the
+  // mainloop then streams activations only (L2 -> SM ingest is what bounds the 64/128-channel layers).
   const int smem_budget = 227 * 1024 - 1024 /*align*/ - 256 /*barriers*/;
-  int stages = smem_budget / (int)stage_bytes;
+  const int chunks = k.chunks0 + k.chunks1;
+  const long long res_bytes = (long long)d->ntaps * chunks * k.b_bytes;
+  const bool resident = k.n_tiles == 1 && d->ngroups == 1 && !d->per_image_w && res_bytes <= 160 * 1024 &&
+                        (smem_budget - res_bytes) / (long long)k.a_bytes >= 3;
+  k.b_res_bytes = resident ? (uint32_t)res_bytes : 0u;
+  const uint32_t stage_bytes = k.a_bytes + (resident ? 0u : (uint32_t)d->ndy * k.b_bytes);
+  int stages = (smem_budget - (int)k.b_res_bytes) / (int)stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) { delete pl; return set_error(-2, "dac_conv_create: tile does not fit shared memory"); }
   k.stages = stages;
-  pl->smem = stages * (int)stage_bytes + 1024 + 256;
+  pl->smem = (int)k.b_res_bytes + stages * (int)stage_bytes + 1024 + 256;
   pl->tiles = k.ngroups * k.m_tiles * k.n_tiles;
 
-  int rc = encode_act_map(&pl->mapA0, d->src0, d->c0, d->ld0, d->W, d->H, d->B, d->tile_w, d->tile_h, d->stride);
+  int rc = encode_act_map(&pl->mapA0, d->src0, d->c0, d->ld0, d->W, d->H, d->B, d->tile_w, a_rows, d->stride);
   if (rc == 0) {
     if (d->c1 > 0)
-      rc = encode_act_map(&pl->mapA1, d->src1, d->c1, d->ld1, d->W, d->H, d->B, d->tile_w, d->tile_h, d->stride);
+      rc = encode_act_map(&pl->mapA1, d->src1, d->c1, d->ld1, d->W, d->H, d->B, d->tile_w, a_rows, d->stride);
     else
       pl->mapA1 = pl->mapA0;
   }

@@ -42,9 +42,14 @@ struct ConvKParams {
   int chunks0, chunks1, c0;
   int per_image_w;
   int stages;
-  uint32_t b_bytes;
-  int8_t tap_dy[4][16];
-  int8_t tap_dx[4][16];
+  uint32_t b_bytes;        // one weight tile: block_n rows x 128 B
+  uint32_t a_bytes;        // one activation load: (tile_h + ndy - 1) * tile_w rows x 128 B
+  uint32_t row_shift;      // tile_w * 128 B: descriptor offset between vertically adjacent taps
+  uint32_t b_res_bytes;    // > 0: the whole weight tensor stays resident in shared memory
+  int ndy, ncols;
+  int8_t col_dx[4][16];
+  int8_t col_dy0[4][16];
+  int8_t col_tap[4][16];
   // epilogue
   int cout;
   const float* bias;
@@ -289,18 +294,24 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024 B alignment is required by the 128B swizzle atoms (TMA write and UMMA read agree on address bits).
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const uint32_t stage_bytes = kABytes + p.b_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(p.stages) * stage_bytes);
+  // [resident weights][ring of stages: activation tile (+ ndy weight tiles when streamed)][barriers]
+  const bool b_resident = p.b_res_bytes != 0;
+  uint8_t* b_res = smem;
+  uint8_t* ring = smem + p.b_res_bytes;
+  const uint32_t stage_bytes = p.a_bytes + (b_resident ? 0u : static_cast<uint32_t>(p.ndy) * p.b_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + static_cast<size_t>(p.stages) * stage_bytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + kMaxStages;
   uint64_t* tmem_full = bars + 2 * kMaxStages;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* b_full = tmem_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
+  const int chunks = p.chunks0 + p.chunks1;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.ngroups * p.m_tiles * p.n_tiles;
-  const int k_steps = p.ntaps * (p.chunks0 + p.chunks1);
+  const int k_steps = p.ncols * (p.chunks0 + p.chunks1);   // one activation load (ndy taps) per step
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA0);
@@ -314,6 +325,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], kEpiWarps);
     }
+    mbar_init(b_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -333,23 +345,34 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
+      if (b_resident) {
+        // whole weight tensor (ntaps x chunks tiles) loaded once per CTA; n_tiles == ngroups == 1 here
+        mbar_arrive_expect_tx(b_full, p.b_res_bytes);
+        for (int tap = 0; tap < p.ntaps; ++tap)
+          for (int ck = 0; ck < chunks; ++ck)
+            tma_load_3d(b_res + static_cast<size_t>(tap * chunks + ck) * p.b_bytes, &mapW, b_full, ck * kChunkK, 0, tap);
+      }
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const TileCoord t = decode_tile(p, tile);
         const int xin = t.x0 * p.stride, yin = t.y0 * p.stride;
         const int zbase = (p.per_image_w ? t.n * p.ngroups * p.ntaps : 0) + t.g * p.ntaps;
-        for (int tap = 0; tap < p.ntaps; ++tap) {
-          const int dy = p.tap_dy[t.g][tap], dx = p.tap_dx[t.g][tap];
-          for (int ck = 0; ck < p.chunks0 + p.chunks1; ++ck) {
+        for (int ck = 0; ck < chunks; ++ck) {
+          for (int j = 0; j < p.ncols; ++j) {
+            const int dy = p.col_dy0[t.g][j], dx = p.col_dx[t.g][j];
             mbar_wait(&empty[stage], phase ^ 1);
-            uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
+            uint8_t* sa = ring + static_cast<size_t>(stage) * stage_bytes;
             mbar_arrive_expect_tx(&full[stage], stage_bytes);
             if (ck < p.chunks0)
               tma_load_4d(sa, &mapA0, &full[stage], ck * kChunkK, xin + dx, yin + dy, t.n);
             else
               tma_load_4d(sa, &mapA1, &full[stage], (ck - p.chunks0) * kChunkK, xin + dx, yin + dy, t.n);
-            tma_load_3d(sa + kABytes, &mapW, &full[stage], ck * kChunkK, t.nt * p.block_n, zbase + tap);
+            if (!b_resident) {
+              for (int i = 0; i < p.ndy; ++i)
+                tma_load_3d(sa + p.a_bytes + static_cast<size_t>(i) * p.b_bytes, &mapW, &full[stage], ck * kChunkK,
+                            t.nt * p.block_n, zbase + p.col_tap[t.g][j * p.ndy + i]);
+            }
             if (++stage == p.stages) {
               stage = 0;
               phase ^= 1;
@@ -365,24 +388,37 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
+    if (b_resident) mbar_wait(b_full, 0);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int g = (tile / p.n_tiles) / p.m_tiles;
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * kAccStride;
+      int ck = 0, j = 0;
       for (int ks = 0; ks < k_steps; ++ks) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
         if (lane == 0) {
-          const uint32_t a_addr = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
-          const uint64_t adesc = make_sw128_desc(a_addr);
-          const uint64_t bdesc = make_sw128_desc(a_addr + kABytes);
+          const uint32_t a_addr = smem_u32(ring + static_cast<size_t>(stage) * stage_bytes);
+          for (int i = 0; i < p.ndy; ++i) {
+            // tap i of the column group: the same activation tile, shifted down by i tile rows
+            const uint64_t adesc = make_sw128_desc(a_addr + i * p.row_shift);
+            const uint32_t b_addr =
+                b_resident ? smem_u32(b_res) + static_cast<uint32_t>(p.col_tap[g][j * p.ndy + i] * chunks + ck) * p.b_bytes
+                           : a_addr + p.a_bytes + static_cast<uint32_t>(i) * p.b_bytes;
+            const uint64_t bdesc = make_sw128_desc(b_addr);
 #pragma unroll
-          for (int k = 0; k < kChunkK / 16; ++k)
-            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < kChunkK / 16; ++k)
+              umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | i | k) != 0 ? 1u : 0u);
+          }
           umma_commit(&empty[stage]);
           if (ks == k_steps - 1) umma_commit(&tmem_full[acc]);
         }
         __syncwarp();
+        if (++j == p.ncols) {
+          j = 0;
+          ++ck;
+        }
         if (++stage == p.stages) {
           stage = 0;
           phase ^= 1;

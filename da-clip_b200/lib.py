@@ -22,7 +22,8 @@ class ConvDesc(C.Structure):
         ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
         ("OH", C.c_int32), ("OW", C.c_int32),
         ("stride", C.c_int32), ("ngroups", C.c_int32), ("ntaps", C.c_int32),
-        ("tap_dy", (C.c_int8 * 16) * 4), ("tap_dx", (C.c_int8 * 16) * 4),
+        ("ndy", C.c_int32), ("ncols", C.c_int32),
+        ("col_dx", (C.c_int8 * 16) * 4), ("col_dy0", (C.c_int8 * 16) * 4), ("col_tap", (C.c_int8 * 16) * 4),
         ("out_scale", C.c_int32), ("out_oy", C.c_int8 * 4), ("out_ox", C.c_int8 * 4),
         ("weight", C.c_void_p), ("cout", C.c_int32), ("cout_pad", C.c_int32), ("per_image_w", C.c_int32),
         ("block_n", C.c_int32), ("tile_h", C.c_int32), ("tile_w", C.c_int32),

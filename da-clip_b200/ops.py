@@ -9,13 +9,14 @@ from . import lib as L
 TILE_SHAPES = [(1, 128), (2, 64), (4, 32), (8, 16), (16, 8)]
 
 
-def choose_tile(oh, ow):
-    """Pixel-tile (h, w) with h*w == 128 that wastes the fewest out-of-image pixels (ties: widest)."""
-    best, best_waste = None, None
+def choose_tile(oh, ow, ndy=1):
+    """Pixel-tile (h, w) with h*w == 128 that loads the fewest activation rows: tiles * (h + ndy - 1) * w, where
+    ndy vertically adjacent taps share one load (ties: widest)."""
+    best, best_cost = None, None
     for th, tw in TILE_SHAPES:
-        waste = (-(-oh // th)) * (-(-ow // tw)) * 128 - oh * ow
-        if best is None or waste < best_waste:
-            best, best_waste = (th, tw), waste
+        cost = (-(-oh // th)) * (-(-ow // tw)) * (th + ndy - 1) * tw
+        if best is None or cost < best_cost:
+            best, best_cost = (th, tw), cost
     return best
 
 
@@ -42,9 +43,12 @@ def _pad_rows(w, cout_pad):
 class PackedWeight:
     """Weights in kernel layout bf16 [Z][cout_pad][cin] plus the tap geometry that indexes Z."""
 
-    def __init__(self, w, taps, cout, stride=1, ngroups=1, out_scale=1, out_off=((0, 0),)):
+    def __init__(self, w, taps, cout, stride=1, ngroups=1, out_scale=1, out_off=((0, 0),), cols=None):
         self.w = w                      # [Z, cout_pad, cin] bf16
         self.taps = taps                # per group: list of (dy, dx)
+        # per group: column groups (dx, dy0, [tap indices of dy0, dy0+1, ...]) - vertically adjacent taps that can
+        # share one activation load; None = one load per tap
+        self.cols = cols
         self.cout = cout
         self.stride = stride
         self.ngroups = ngroups
@@ -60,7 +64,8 @@ def pack_conv(weight, cout_pad=None, stride=1, pad=None):
     cout_pad = cout_pad or choose_block_n(cout)[1]
     w = weight.permute(2, 3, 0, 1).reshape(kh * kw, cout, cin)
     taps = [[(ky - pad, kx - pad) for ky in range(kh) for kx in range(kw)]]
-    return PackedWeight(_pad_rows(w, cout_pad), taps, cout, stride=stride)
+    cols = [[(kx - pad, -pad, [ky * kw + kx for ky in range(kh)]) for kx in range(kw)]] if stride == 1 and kh > 1 else None
+    return PackedWeight(_pad_rows(w, cout_pad), taps, cout, stride=stride, cols=cols)
 
 
 def pack_linear(weight, cout_pad=None):
@@ -95,7 +100,7 @@ def pack_stem(weight):
     for kx in range(kw):
         w[:, :, kx * 8:kx * 8 + cin] = weight[:, :, :, kx].permute(2, 0, 1)
     taps = [[(ky - 3, 0) for ky in range(kh)]]
-    return PackedWeight(_pad_rows(w, choose_block_n(cout)[1]), taps, cout)
+    return PackedWeight(_pad_rows(w, choose_block_n(cout)[1]), taps, cout, cols=[[(0, -3, list(range(kh)))]])
 
 
 def pack_upsample_conv(weight):
@@ -106,7 +111,7 @@ def pack_upsample_conv(weight):
     assert (kh, kw) == (3, 3)
     # parity 0: source offsets -1 <- {k0}, 0 <- {k1,k2};  parity 1: 0 <- {k0,k1}, +1 <- {k2}
     sets = {0: [(-1, [0]), (0, [1, 2])], 1: [(0, [0, 1]), (1, [2])]}
-    slabs, taps, offs = [], [], []
+    slabs, taps, offs, cols = [], [], [], []
     w32 = weight.float()
     for py in (0, 1):
         for px in (0, 1):
@@ -121,9 +126,11 @@ def pack_upsample_conv(weight):
                     gt.append((dy, dx))
             taps.append(gt)
             offs.append((py, px))
+            # tap index = a*2 + b (a: row offset index, b: column offset index): the two rows of a column share a load
+            cols.append([(sets[px][b][0], sets[py][0][0], [b, 2 + b]) for b in (0, 1)])
     w = torch.stack(slabs)                                   # [16, cout, cin]
     cout_pad = choose_block_n(cout)[1]
-    return PackedWeight(_pad_rows(w, cout_pad), taps, cout, ngroups=4, out_scale=2, out_off=tuple(offs))
+    return PackedWeight(_pad_rows(w, cout_pad), taps, cout, ngroups=4, out_scale=2, out_off=tuple(offs), cols=cols)
 
 
 class ConvPlan:
@@ -132,25 +139,32 @@ class ConvPlan:
     def __init__(self, src0, c0, pw: PackedWeight, out=None, *, B, H, W, src1=None, c1=0, ld0=None, ld1=None,
                  epi=L.EPI_PLAIN, act=L.ACT_NONE, bias=None, bias_img=None, film=None, film_off=0,
                  ln_g=None, ln_eps=1e-5, res=None, res2=None, res_f32=None, out_f32=None, out_coff=0, out_nchw=None,
-                 per_image_w=False, block_n=None, weight_override=None, tile=None):
+                 per_image_w=False, block_n=None, weight_override=None, tile=None, share_taps=True):
         L.require_cuda(src0)
         lib = L.load()
         d = L.ConvDesc()
         s = pw.stride
         OH, OW = (H // s, W // s) if s == 2 else (H, W)
-        th, tw = tile or choose_tile(OH, OW)
         wt = weight_override if weight_override is not None else pw.w
         cout_pad = wt.shape[-2]
         if block_n is None:
             block_n = choose_block_n(pw.cout)[0] if cout_pad <= 256 else (256 if cout_pad % 256 == 0 else 128)
+        # vertically adjacent taps share one activation load when the weight tiles are small enough to ride along
+        share = pw.cols is not None and s == 1 and block_n <= 128 and share_taps
+        cols = pw.cols if share else [[(dx, dy, [i]) for i, (dy, dx) in enumerate(gt)] for gt in pw.taps]
+        ndy = len(cols[0][0][2])
+        th, tw = tile or choose_tile(OH, OW, ndy)
         d.src0, d.c0, d.ld0 = src0.data_ptr(), c0, ld0 or src0.shape[-1]
         if src1 is not None:
             d.src1, d.c1, d.ld1 = src1.data_ptr(), c1, ld1 or src1.shape[-1]
         d.B, d.H, d.W, d.OH, d.OW = B, H, W, OH, OW
         d.stride, d.ngroups, d.ntaps = s, pw.ngroups, len(pw.taps[0])
-        for g, gt in enumerate(pw.taps):
-            for i, (dy, dx) in enumerate(gt):
-                d.tap_dy[g][i], d.tap_dx[g][i] = dy, dx
+        d.ndy, d.ncols = ndy, len(cols[0])
+        for g, gc in enumerate(cols):
+            for j, (dx, dy0, tap_ids) in enumerate(gc):
+                d.col_dx[g][j], d.col_dy0[g][j] = dx, dy0
+                for i, tid in enumerate(tap_ids):
+                    d.col_tap[g][j * ndy + i] = tid
         d.out_scale = pw.out_scale
         for g, (oy, ox) in enumerate(pw.out_off):
             d.out_oy[g], d.out_ox[g] = oy, ox

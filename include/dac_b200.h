@@ -77,8 +77,14 @@ typedef struct dac_conv_desc {
   int32_t stride;               /* 1 or 2: input coord = out*stride + tap offset */
   int32_t ngroups;              /* 1, or 4 parity groups for the folded upsample conv */
   int32_t ntaps;                /* taps per group (<=16) */
-  int8_t tap_dy[4][16];
-  int8_t tap_dx[4][16];
+  /* Taps are organised in "column groups": ncols groups per parity group, each made of ndy vertically adjacent
+   * taps (dx, dy0 .. dy0+ndy-1).  One TMA load of (tile_h + ndy - 1) rows serves the ndy taps of a column group:
+   * tap i is the same shared-memory tile read through a descriptor shifted by i*tile_w rows.  ndy == 1 gives one
+   * load per tap.  col_tap[g][j*ndy+i] = index (< ntaps) of that tap's weight slab within parity group g. */
+  int32_t ndy, ncols;
+  int8_t col_dx[4][16];
+  int8_t col_dy0[4][16];
+  int8_t col_tap[4][16];
   int32_t out_scale;            /* output position = out*out_scale + out_off[g] */
   int8_t out_oy[4], out_ox[4];
   /* weights: bf16 [Z][cout_pad][c0+c1], Z = ngroups*ntaps (* B if per_image_w); cout_pad multiple of block_n */

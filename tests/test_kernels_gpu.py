@@ -92,6 +92,23 @@ def test_conv3x3_film_silu(ops, gen, B, H, W, cin, cout, tile):
     assert_close_bf16(nchw(out), ref, f"conv3x3 {B}x{H}x{W} {cin}->{cout} {plan.info()}")
 
 
+@pytest.mark.parametrize("share", [True, False])
+@pytest.mark.parametrize("B,H,W,c0,c1,cout", [(2, 40, 24, 64, 0, 64), (1, 64, 64, 128, 64, 128), (1, 16, 16, 256, 0, 256)])
+def test_conv3x3_tap_sharing_modes(ops, gen, share, B, H, W, c0, c1, cout):
+    """One activation load per column of taps (row-shifted descriptors, resident weights when they fit) must give
+    the same result as one load per tap."""
+    a = nhwc(rnd(gen, B, c0, H, W))
+    s_ = nhwc(rnd(gen, B, c1, H, W)) if c1 else None
+    w = rnd(gen, cout, c0 + c1, 3, 3, scale=(9 * (c0 + c1)) ** -0.5)
+    out = torch.full((B, H, W, cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+    plan = ops.ConvPlan(a, c0, ops.pack_conv(w), out, B=B, H=H, W=W, src1=s_, c1=c1, share_taps=share)
+    plan.run()
+    torch.cuda.synchronize()
+    x = nchw(a) if s_ is None else torch.cat([nchw(a), nchw(s_)], 1)
+    ref = F.conv2d(x, bf(w).float(), padding=1)
+    assert_close_bf16(nchw(out), ref, f"conv3x3 share={share} {plan.info()}")
+
+
 def test_conv3x3_concat_residual(ops, gen):
     from daclip_b200 import lib as L
     B, H, W, c0, c1, cout = 3, 16, 16, 64, 128, 128
