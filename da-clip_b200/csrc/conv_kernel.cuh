@@ -311,7 +311,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.ngroups * p.m_tiles * p.n_tiles;
-  const int k_steps = p.ncols * (p.chunks0 + p.chunks1);   // one activation load (ndy taps) per step
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA0);
@@ -343,8 +342,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
 #endif
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (one elected thread) =====================
+    if (elect_one()) {
       if (b_resident) {
         // whole weight tensor (ntaps x chunks tiles) loaded once per CTA; n_tiles == ngroups == 1 here
         mbar_arrive_expect_tx(b_full, p.b_res_bytes);
@@ -358,20 +357,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         const TileCoord t = decode_tile(p, tile);
         const int xin = t.x0 * p.stride, yin = t.y0 * p.stride;
         const int zbase = (p.per_image_w ? t.n * p.ngroups * p.ntaps : 0) + t.g * p.ntaps;
+        const int ncoord = t.nt * p.block_n;
         for (int ck = 0; ck < chunks; ++ck) {
+          const CUtensorMap* mapA = ck < p.chunks0 ? &mapA0 : &mapA1;
+          const int ccoord = (ck < p.chunks0 ? ck : ck - p.chunks0) * kChunkK;
           for (int j = 0; j < p.ncols; ++j) {
-            const int dy = p.col_dy0[t.g][j], dx = p.col_dx[t.g][j];
             mbar_wait(&empty[stage], phase ^ 1);
             uint8_t* sa = ring + static_cast<size_t>(stage) * stage_bytes;
             mbar_arrive_expect_tx(&full[stage], stage_bytes);
-            if (ck < p.chunks0)
-              tma_load_4d(sa, &mapA0, &full[stage], ck * kChunkK, xin + dx, yin + dy, t.n);
-            else
-              tma_load_4d(sa, &mapA1, &full[stage], (ck - p.chunks0) * kChunkK, xin + dx, yin + dy, t.n);
+            tma_load_4d(sa, mapA, &full[stage], ccoord, xin + p.col_dx[t.g][j], yin + p.col_dy0[t.g][j], t.n);
             if (!b_resident) {
               for (int i = 0; i < p.ndy; ++i)
                 tma_load_3d(sa + p.a_bytes + static_cast<size_t>(i) * p.b_bytes, &mapW, &full[stage], ck * kChunkK,
-                            t.nt * p.block_n, zbase + p.col_tap[t.g][j * p.ndy + i]);
+                            ncoord, zbase + p.col_tap[t.g][j * p.ndy + i]);
             }
             if (++stage == p.stages) {
               stage = 0;
@@ -382,51 +380,55 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    const uint32_t idesc = make_idesc_bf16(kTileM, p.block_n);
-    int stage = 0;
-    uint32_t phase = 0;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    if (b_resident) mbar_wait(b_full, 0);
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int g = (tile / p.n_tiles) / p.m_tiles;
-      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * kAccStride;
-      int ck = 0, j = 0;
-      for (int ks = 0; ks < k_steps; ++ks) {
-        mbar_wait(&full[stage], phase);
+    // ===================== MMA issuer (one elected thread; the issue loop is the critical path of the
+    // 64-channel layers - one M128 x N64 x K16 MMA is only 32 tensor-pipe cycles - so it is add-only) ==========
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_bf16(kTileM, p.block_n);
+      const uint64_t desc_fixed = make_sw128_desc(0);                 // every field except the start address
+      const uint32_t ring_lo = (smem_u32(ring) & 0x3FFFF) >> 4;
+      const uint32_t bres_lo = (smem_u32(b_res) & 0x3FFFF) >> 4;
+      const uint32_t stage_lo = stage_bytes >> 4, shift_lo = p.row_shift >> 4, a_lo = p.a_bytes >> 4,
+                     b_lo = p.b_bytes >> 4;
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      if (b_resident) mbar_wait(b_full, 0);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int g = (tile / p.n_tiles) / p.m_tiles;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t a_addr = smem_u32(ring + static_cast<size_t>(stage) * stage_bytes);
-          for (int i = 0; i < p.ndy; ++i) {
-            // tap i of the column group: the same activation tile, shifted down by i tile rows
-            const uint64_t adesc = make_sw128_desc(a_addr + i * p.row_shift);
-            const uint32_t b_addr =
-                b_resident ? smem_u32(b_res) + static_cast<uint32_t>(p.col_tap[g][j * p.ndy + i] * chunks + ck) * p.b_bytes
-                           : a_addr + p.a_bytes + static_cast<uint32_t>(i) * p.b_bytes;
-            const uint64_t bdesc = make_sw128_desc(b_addr);
-#pragma unroll
-            for (int k = 0; k < kChunkK / 16; ++k)
-              umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | i | k) != 0 ? 1u : 0u);
+        const uint32_t d_tmem = tmem_base + acc * kAccStride;
+        uint32_t accumulate = 0;
+        for (int ck = 0; ck < chunks; ++ck) {
+          for (int j = 0; j < p.ncols; ++j) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            const uint32_t a0 = ring_lo + stage * stage_lo;
+            for (int i = 0; i < p.ndy; ++i) {
+              // tap i of the column group: the same activation tile, shifted down by i tile rows
+              const uint64_t adesc = desc_fixed | (a0 + i * shift_lo);
+              const uint64_t bdesc =
+                  desc_fixed | (b_resident ? bres_lo + (p.col_tap[g][j * p.ndy + i] * chunks + ck) * b_lo
+                                           : a0 + a_lo + i * b_lo);
+              umma_bf16(d_tmem, adesc, bdesc, idesc, accumulate);
+              umma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
+              umma_bf16(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
+              umma_bf16(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
+              accumulate = 1u;
+            }
+            umma_commit(&empty[stage]);
+            if (++stage == p.stages) {
+              stage = 0;
+              phase ^= 1;
+            }
           }
-          umma_commit(&empty[stage]);
-          if (ks == k_steps - 1) umma_commit(&tmem_full[acc]);
         }
-        __syncwarp();
-        if (++j == p.ncols) {
-          j = 0;
-          ++ck;
+        umma_commit(&tmem_full[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
         }
-        if (++stage == p.stages) {
-          stage = 0;
-          phase ^= 1;
-        }
-      }
-      if (++acc == 2) {
-        acc = 0;
-        acc_phase ^= 1;
       }
     }
   } else {
