@@ -65,7 +65,7 @@ static int encode_act_map(CUtensorMap* m, const void* ptr, int c, int ld, int W,
 extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
   if (!d || !out) return set_error(-1, "dac_conv_create: null argument");
   *out = nullptr;
-  if (d->tile_h * d->tile_w != kTileM || d->tile_w < 8 || (d->tile_w & 7))
+  if (d->tile_h * d->tile_w != kTileM || d->tile_w < 8 || (d->tile_w & (d->tile_w - 1)))
     return set_error(-2, "dac_conv_create: tile %dx%d must have 128 pixels, width multiple of 8", d->tile_h, d->tile_w);
   if (d->c0 <= 0 || d->c0 % kChunkK || d->c1 % kChunkK || d->ld0 % 8 || (d->c1 && d->ld1 % 8))
     return set_error(-2, "dac_conv_create: channels (%d,%d) must be multiples of 64, pitches of 8", d->c0, d->c1);
@@ -131,8 +131,12 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
   k.tiles_y = (d->OH + d->tile_h - 1) / d->tile_h;
   k.m_tiles = d->B * k.tiles_x * k.tiles_y;
   k.block_n = d->block_n;
+  k.tile_w_shift = 0;
+  while ((1 << k.tile_w_shift) < d->tile_w) ++k.tile_w_shift;
   k.n_tiles = d->cout_pad / d->block_n;
   k.ngroups = d->ngroups; k.ntaps = d->ntaps;
+  k.fd_ntiles = make_fast_div(k.n_tiles); k.fd_mtiles = make_fast_div(k.m_tiles);
+  k.fd_tx = make_fast_div(k.tiles_x); k.fd_ty = make_fast_div(k.tiles_y);
   k.chunks0 = d->c0 / kChunkK; k.chunks1 = d->c1 / kChunkK; k.c0 = d->c0;
   k.per_image_w = d->per_image_w;
   k.b_bytes = (uint32_t)d->block_n * kChunkK * 2;
@@ -159,7 +163,7 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
 
   // Weights stay resident in shared memory when the whole tensor fits beside >= 3 activation stages: the
   // mainloop then streams activations only (L2 -> SM ingest is what bounds the 64/128-channel layers).
-  const int smem_budget = 227 * 1024 - 1024 /*align*/ - 256 /*barriers*/;
+  const int smem_budget = 227 * 1024 - 1024 /*align*/ - 256 /*barriers*/ - 2048 /*FiLM stage*/;
   const int chunks = k.chunks0 + k.chunks1;
   const long long res_bytes = (long long)d->ntaps * chunks * k.b_bytes;
   const bool resident = k.n_tiles == 1 && d->ngroups == 1 && !d->per_image_w && res_bytes <= 160 * 1024 &&
@@ -170,7 +174,7 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) { delete pl; return set_error(-2, "dac_conv_create: tile does not fit shared memory"); }
   k.stages = stages;
-  pl->smem = (int)k.b_res_bytes + stages * (int)stage_bytes + 1024 + 256;
+  pl->smem = (int)k.b_res_bytes + stages * (int)stage_bytes + 1024 + 256 + 2048;
   pl->tiles = k.ngroups * k.m_tiles * k.n_tiles;
 
   int rc = encode_act_map(&pl->mapA0, d->src0, d->c0, d->ld0, d->W, d->H, d->B, d->tile_w, a_rows, d->stride);

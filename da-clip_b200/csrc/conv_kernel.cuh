@@ -35,9 +35,31 @@ constexpr int kMaxStages = 8;
 
 enum { KE_PLAIN = 0, KE_GEGLU = 1, KE_LN = 2, KE_QKV = 3, KE_NCHW = 4 };
 
+// Division by a launch-time constant without the ~60-cycle IDIV sequence (Granlund-Montgomery round-up method):
+// t = umulhi(mul, n); q = (t + ((n - t) >> s1)) >> s2.  Exact for 0 <= n < 2^31.
+struct FastDiv {
+  uint32_t mul, s1, s2, d;
+};
+__device__ __forceinline__ int fast_div(int n, const FastDiv& f) {
+  const uint32_t t = __umulhi(f.mul, static_cast<uint32_t>(n));
+  return static_cast<int>((t + ((static_cast<uint32_t>(n) - t) >> f.s1)) >> f.s2);
+}
+inline FastDiv make_fast_div(uint32_t d) {
+  FastDiv f;
+  uint32_t l = 0;
+  while ((1ull << l) < d) ++l;
+  f.mul = static_cast<uint32_t>(((1ull << 32) * ((1ull << l) - d)) / d + 1);
+  f.s1 = l < 1 ? l : 1;
+  f.s2 = l > 0 ? l - 1 : 0;
+  f.d = d;
+  return f;
+}
+
 struct ConvKParams {
   int B, OH, OW, stride;
   int tile_h, tile_w, tiles_x, tiles_y, m_tiles;
+  int tile_w_shift;
+  FastDiv fd_ntiles, fd_mtiles, fd_tx, fd_ty;
   int n_tiles, block_n, ngroups, ntaps;
   int chunks0, chunks1, c0;
   int per_image_w;
@@ -80,17 +102,24 @@ struct TileCoord {
 
 __device__ __forceinline__ TileCoord decode_tile(const ConvKParams& p, int tile) {
   TileCoord t;
-  t.nt = tile % p.n_tiles;
-  int rest = tile / p.n_tiles;
-  int mt = rest % p.m_tiles;
-  t.g = rest / p.m_tiles;
-  int tx = mt % p.tiles_x;
-  int r2 = mt / p.tiles_x;
-  int ty = r2 % p.tiles_y;
-  t.n = r2 / p.tiles_y;
+  const int rest = fast_div(tile, p.fd_ntiles);
+  t.nt = tile - rest * p.n_tiles;
+  t.g = fast_div(rest, p.fd_mtiles);
+  const int mt = rest - t.g * p.m_tiles;
+  const int r2 = fast_div(mt, p.fd_tx);
+  const int tx = mt - r2 * p.tiles_x;
+  t.n = fast_div(r2, p.fd_ty);
+  const int ty = r2 - t.n * p.tiles_y;
   t.y0 = ty * p.tile_h;
   t.x0 = tx * p.tile_w;
   return t;
+}
+
+// CTA b owns the contiguous tile range [total*b/grid, total*(b+1)/grid): consecutive tiles of a CTA belong to the
+// same image (FiLM parameters stay cached) and neighbouring rows (halo re-reads hit L2).
+__device__ __forceinline__ void tile_range(int total, int& begin, int& end) {
+  begin = static_cast<int>(static_cast<long long>(total) * blockIdx.x / gridDim.x);
+  end = static_cast<int>(static_cast<long long>(total) * (blockIdx.x + 1) / gridDim.x);
 }
 
 template <int ACT>
@@ -157,8 +186,8 @@ __device__ __forceinline__ void chunk_store_f32(float* __restrict__ dst, const f
 // a lane quadrant splits the columns: this thread owns columns [half*bn/2, (half+1)*bn/2).
 template <int EPI, int ACT, bool FILM>
 __device__ __forceinline__ void epilogue_tile(const ConvKParams& p, const TileCoord& t, uint32_t tmem_acc, int row,
-                                              int half) {
-  const int ty = row / p.tile_w, tx = row - ty * p.tile_w;
+                                              int half, const float* film_sh) {
+  const int ty = row >> p.tile_w_shift, tx = row & (p.tile_w - 1);
   const int y = t.y0 + ty, x = t.x0 + tx;
   const bool valid = (y < p.OH) && (x < p.OW);
   const int Y = y * p.out_scale + p.out_oy[t.g], X = x * p.out_scale + p.out_ox[t.g];
@@ -270,8 +299,16 @@ __device__ __forceinline__ void epilogue_tile(const ConvKParams& p, const TileCo
     if (p.bias) chunk_add_f32(p.bias + ch, v);
     if (p.bias_img) chunk_add_f32(p.bias_img + static_cast<long long>(n) * p.cout + ch, v);
     if (FILM) {
-      const float* sc = p.film + static_cast<long long>(n) * p.film_ld + p.film_off + ch;
-      chunk_film(sc, sc + p.cout, v);
+      // (scale + 1, shift) of this image, staged in shared memory by the epilogue warps when the image changes
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 a = *reinterpret_cast<const float4*>(film_sh + c + 4 * q);
+        const float4 b = *reinterpret_cast<const float4*>(film_sh + p.block_n + c + 4 * q);
+        v[4 * q] = fmaf(v[4 * q], a.x, b.x);
+        v[4 * q + 1] = fmaf(v[4 * q + 1], a.y, b.y);
+        v[4 * q + 2] = fmaf(v[4 * q + 2], a.z, b.z);
+        v[4 * q + 3] = fmaf(v[4 * q + 3], a.w, b.w);
+      }
     }
     if (ACT != DAC_ACT_NONE) {
 #pragma unroll
@@ -306,11 +343,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* b_full = tmem_empty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
+  float* film_sh = reinterpret_cast<float*>(bars + 32);   // [2][block_n]: scale + 1 | shift of the current image
   const int chunks = p.chunks0 + p.chunks1;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.ngroups * p.m_tiles * p.n_tiles;
+  int tile_begin, tile_end;
+  tile_range(total_tiles, tile_begin, tile_end);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA0);
@@ -353,7 +393,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       }
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
         const TileCoord t = decode_tile(p, tile);
         const int xin = t.x0 * p.stride, yin = t.y0 * p.stride;
         const int zbase = (p.per_image_w ? t.n * p.ngroups * p.ntaps : 0) + t.g * p.ntaps;
@@ -394,8 +434,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       int acc = 0;
       uint32_t acc_phase = 0;
       if (b_resident) mbar_wait(b_full, 0);
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int g = (tile / p.n_tiles) / p.m_tiles;
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
+        const int g = fast_div(fast_div(tile, p.fd_ntiles), p.fd_mtiles);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kAccStride;
@@ -438,12 +478,28 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     const int row = quad * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    int film_key = -1;
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
       const TileCoord t = decode_tile(p, tile);
+      if (FILM) {
+        // FiLM parameters depend on (image, N tile) only: restage when that pair changes (rare with contiguous
+        // tile ranges).  Named barrier 1 = the 256 epilogue threads.
+        const int key = t.n * p.n_tiles + t.nt;
+        if (key != film_key) {
+          film_key = key;
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          const float* src = p.film + static_cast<long long>(t.n) * p.film_ld + p.film_off + t.nt * p.block_n;
+          for (int i = threadIdx.x - 64; i < 2 * p.block_n; i += 256) {
+            const int c = i < p.block_n ? i : i - p.block_n;
+            film_sh[i] = i < p.block_n ? __ldg(src + c) + 1.0f : __ldg(src + p.cout + c);
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kAccStride;
-      epilogue_tile<EPI, ACT, FILM>(p, t, tmem_acc, row, half);
+      epilogue_tile<EPI, ACT, FILM>(p, t, tmem_acc, row, half, film_sh);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
