@@ -15,140 +15,146 @@
 
 namespace dac {
 
-constexpr int kLaP = 64;       // pixels per sub-tile
-constexpr int kLaKPitch = 34;  // fp32 pitch of the exp(k) tile (even: float2 loads)
+constexpr int kLaP = 64;                 // pixels per sub-tile
+constexpr int kLaPitch = kLaP + 8;       // bf16 pitch of the transposed [channel][pixel] tiles
 constexpr int kPartial = 32 * 32 + 64;
 
-__global__ void __launch_bounds__(256) linattn_context_kernel(const __nv_bfloat16* __restrict__ qkv, int hw,
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// One CTA (4 warps) per (pixel slab, head, image).  Per 64-pixel sub-tile: k and v are scattered transposed
+// ([channel][pixel], bf16) into shared memory; the running column max / rescale / exp / row sums are done by
+// (channel, quarter) threads on 16 contiguous pixels; C[d][e] += sum_p exp(k)[d][p] v[e][p] runs on the warp-level
+// tensor cores (mma.sync m16n8k16 bf16, fp32 accumulate): warp w owns d rows 16*(w/2).. and e cols 16*(w%2)...
+__global__ void __launch_bounds__(128) linattn_context_kernel(const __nv_bfloat16* __restrict__ qkv, int hw,
                                                               int slab, float* __restrict__ partial) {
-  __shared__ __align__(16) float ks[kLaP * kLaKPitch];
-  __shared__ __align__(16) float vs[kLaP * 32];
-  __shared__ float red[8 * 32];
+  __shared__ __align__(16) __nv_bfloat16 Kt[32 * kLaPitch];
+  __shared__ __align__(16) __nv_bfloat16 Vt[32 * kLaPitch];
   __shared__ float m_run[32], s_run[32], scale[32];
-  __shared__ float cred[32 * 32];
 
   const int chunk = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int nchunks = gridDim.x;
-  const int t = threadIdx.x;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const int p_begin = chunk * slab, p_end = min(hw, p_begin + slab);
   const __nv_bfloat16* base = qkv + static_cast<int64_t>(b) * hw * 384;
-
-  // compute-phase mapping: 4 pixel groups x (16 d-pairs x 4 e-octets)
-  const int pg4 = t >> 6, u = t & 63, dp = u >> 2, eo = u & 3;
-  const int d0 = 2 * dp;
-  float acc[2][8];
+  const int d0 = 16 * (warp >> 1), e0 = 16 * (warp & 1);
+  float acc[2][4];
 #pragma unroll
   for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   if (t < 32) {
     m_run[t] = -INFINITY;
     s_run[t] = 0.f;
   }
-  __syncthreads();
+  const __nv_bfloat16 neg_inf = __float2bfloat16(-INFINITY);
 
   for (int p0 = p_begin; p0 < p_end; p0 += kLaP) {
-    {  // load 64 pixels x (32 k + 32 v) channels: thread -> (pixel, 8-channel part)
-      const int pl = t >> 2, part = t & 3;
+    __syncthreads();  // previous sub-tile fully consumed (and m_run / s_run initialised)
+    {  // load 64 pixels x (32 k + 32 v) channels; thread -> (pixel, 16-channel half); scatter transposed
+      const int pl = t >> 1, part = t & 1;
       const int p = p0 + pl;
-      float kv[8], vv[8];
+      uint4 uk[2], uv[2];
       if (p < p_end) {
         const __nv_bfloat16* row = base + static_cast<int64_t>(p) * 384;
-        const uint4 uk = *reinterpret_cast<const uint4*>(row + 128 + h * 32 + part * 8);
-        const uint4 uv = *reinterpret_cast<const uint4*>(row + 256 + h * 32 + part * 8);
+        uk[0] = __ldg(reinterpret_cast<const uint4*>(row + 128 + h * 32 + part * 16));
+        uk[1] = __ldg(reinterpret_cast<const uint4*>(row + 128 + h * 32 + part * 16) + 1);
+        uv[0] = __ldg(reinterpret_cast<const uint4*>(row + 256 + h * 32 + part * 16));
+        uv[1] = __ldg(reinterpret_cast<const uint4*>(row + 256 + h * 32 + part * 16) + 1);
+      }
+      const __nv_bfloat16* kk = reinterpret_cast<const __nv_bfloat16*>(uk);
+      const __nv_bfloat16* vv = reinterpret_cast<const __nv_bfloat16*>(uv);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int c = part * 16 + j;
+        Kt[c * kLaPitch + pl] = (p < p_end) ? kk[j] : neg_inf;           // masked pixel: exp -> 0
+        Vt[c * kLaPitch + pl] = (p < p_end) ? vv[j] : __float2bfloat16(0.f);
+      }
+    }
+    __syncthreads();
+    {  // thread -> (channel d = t/4, 16-pixel quarter): running max, rescale factor, exp in place, row sum
+      const int d = t >> 2, qtr = t & 3;
+      __nv_bfloat16* rowp = &Kt[d * kLaPitch + qtr * 16];
+      float kv[16];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const uint4 u = *reinterpret_cast<const uint4*>(rowp + q * 8);
         float2 f;
-        f = unpack_bf16(uk.x); kv[0] = f.x; kv[1] = f.y;
-        f = unpack_bf16(uk.y); kv[2] = f.x; kv[3] = f.y;
-        f = unpack_bf16(uk.z); kv[4] = f.x; kv[5] = f.y;
-        f = unpack_bf16(uk.w); kv[6] = f.x; kv[7] = f.y;
-        f = unpack_bf16(uv.x); vv[0] = f.x; vv[1] = f.y;
-        f = unpack_bf16(uv.y); vv[2] = f.x; vv[3] = f.y;
-        f = unpack_bf16(uv.z); vv[4] = f.x; vv[5] = f.y;
-        f = unpack_bf16(uv.w); vv[6] = f.x; vv[7] = f.y;
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { kv[j] = -INFINITY; vv[j] = 0.f; }
+        f = unpack_bf16(u.x); kv[q * 8 + 0] = f.x; kv[q * 8 + 1] = f.y;
+        f = unpack_bf16(u.y); kv[q * 8 + 2] = f.x; kv[q * 8 + 3] = f.y;
+        f = unpack_bf16(u.z); kv[q * 8 + 4] = f.x; kv[q * 8 + 5] = f.y;
+        f = unpack_bf16(u.w); kv[q * 8 + 6] = f.x; kv[q * 8 + 7] = f.y;
       }
+      float m = kv[0];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        ks[pl * kLaKPitch + part * 8 + j] = kv[j];
-        vs[pl * 32 + part * 8 + j] = vv[j];
-      }
-    }
-    __syncthreads();
-    {  // tile max per d: thread -> (d = t%32, 8-pixel group t/32)
-      const int d = t & 31, g = t >> 5;
-      float m = -INFINITY;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) m = fmaxf(m, ks[(g * 8 + i) * kLaKPitch + d]);
-      red[g * 32 + d] = m;
-    }
-    __syncthreads();
-    if (t < 32) {
-      float m = red[t];
-#pragma unroll
-      for (int g = 1; g < 8; ++g) m = fmaxf(m, red[g * 32 + t]);
-      const float mo = m_run[t];
+      for (int j = 1; j < 16; ++j) m = fmaxf(m, kv[j]);
+      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+      const float mo = m_run[d];
       const float mn = fmaxf(mo, m);
-      scale[t] = (mo == -INFINITY) ? 0.f : __expf(mo - mn);
-      m_run[t] = mn;
-    }
-    __syncthreads();
-    {  // exponentiate in place + partial row sums
-      const int d = t & 31, g = t >> 5;
-      const float mn = m_run[d];
+      // first sub-tile of a slab always holds at least one live pixel, so mn is finite
       float s = 0.f;
+      uint32_t packed[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int idx = (g * 8 + i) * kLaKPitch + d;
-        const float e = __expf(ks[idx] - mn);  // -inf (masked pixel) -> 0
-        ks[idx] = e;
-        s += e;
+      for (int j = 0; j < 16; j += 2) {
+        const float ea = __expf(kv[j] - mn), eb = __expf(kv[j + 1] - mn);
+        packed[j >> 1] = pack_bf16(ea, eb);
+        const float2 r = unpack_bf16(packed[j >> 1]);      // sum exactly what the tensor cores will multiply
+        s += r.x + r.y;
       }
-      red[g * 32 + d] = s;
-    }
-    __syncthreads();
-    if (t < 32) {
-      float s = 0.f;
-#pragma unroll
-      for (int g = 0; g < 8; ++g) s += red[g * 32 + t];
-      s_run[t] = s_run[t] * scale[t] + s;
-    }
-    {  // C[d][e] += sum_p ek[p][d] v[p][e]
-      const float sc0 = scale[d0], sc1 = scale[d0 + 1];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        acc[0][j] *= sc0;
-        acc[1][j] *= sc1;
-      }
-      for (int p = pg4; p < kLaP; p += 4) {
-        const float2 kk = *reinterpret_cast<const float2*>(&ks[p * kLaKPitch + d0]);
-        const float4 va = *reinterpret_cast<const float4*>(&vs[p * 32 + eo * 8]);
-        const float4 vb = *reinterpret_cast<const float4*>(&vs[p * 32 + eo * 8 + 4]);
-        acc[0][0] += kk.x * va.x; acc[0][1] += kk.x * va.y; acc[0][2] += kk.x * va.z; acc[0][3] += kk.x * va.w;
-        acc[0][4] += kk.x * vb.x; acc[0][5] += kk.x * vb.y; acc[0][6] += kk.x * vb.z; acc[0][7] += kk.x * vb.w;
-        acc[1][0] += kk.y * va.x; acc[1][1] += kk.y * va.y; acc[1][2] += kk.y * va.z; acc[1][3] += kk.y * va.w;
-        acc[1][4] += kk.y * vb.x; acc[1][5] += kk.y * vb.y; acc[1][6] += kk.y * vb.z; acc[1][7] += kk.y * vb.w;
+      *reinterpret_cast<uint4*>(rowp) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+      *reinterpret_cast<uint4*>(rowp + 8) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      __syncwarp();
+      if (qtr == 0) {
+        const float sc = (mo == -INFINITY) ? 0.f : __expf(mo - mn);
+        scale[d] = sc;
+        m_run[d] = mn;
+        s_run[d] = s_run[d] * sc + s;
       }
     }
     __syncthreads();
-  }
-
-  // reduce the 4 pixel groups and write the partial
-  for (int g = 0; g < 4; ++g) {
-    if (pg4 == g) {
+    {  // C[d][e] = C[d][e] * scale[d] + sum_p P[d][p] V[e][p]
+      const int r = lane >> 2, cq = 2 * (lane & 3);
+      const float sc0 = scale[d0 + r], sc1 = scale[d0 + r + 8];
 #pragma unroll
-      for (int i = 0; i < 2; ++i)
+      for (int i = 0; i < 2; ++i) {
+        acc[i][0] *= sc0; acc[i][1] *= sc0; acc[i][2] *= sc1; acc[i][3] *= sc1;
+      }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int idx = (d0 + i) * 32 + eo * 8 + j;
-          cred[idx] = (g == 0 ? 0.f : cred[idx]) + acc[i][j];
+      for (int ks = 0; ks < kLaP / 16; ++ks) {
+        uint32_t a[4];
+        const __nv_bfloat16* ap = &Kt[(d0 + r) * kLaPitch + ks * 16 + cq];
+        a[0] = *reinterpret_cast<const uint32_t*>(ap);
+        a[1] = *reinterpret_cast<const uint32_t*>(ap + 8 * kLaPitch);
+        a[2] = *reinterpret_cast<const uint32_t*>(ap + 8);
+        a[3] = *reinterpret_cast<const uint32_t*>(ap + 8 * kLaPitch + 8);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const __nv_bfloat16* bp = &Vt[(e0 + i * 8 + r) * kLaPitch + ks * 16 + cq];
+          mma_bf16_16816(acc[i], a, *reinterpret_cast<const uint32_t*>(bp), *reinterpret_cast<const uint32_t*>(bp + 8));
         }
+      }
     }
-    __syncthreads();
   }
+  __syncthreads();
   float* out = partial + ((static_cast<int64_t>(b) * 4 + h) * nchunks + chunk) * kPartial;
-  for (int i = t; i < 1024; i += 256) out[i] = cred[i];
+  {
+    const int r = lane >> 2, cq = 2 * (lane & 3);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int e = e0 + i * 8 + cq;
+      out[(d0 + r) * 32 + e] = acc[i][0];
+      out[(d0 + r) * 32 + e + 1] = acc[i][1];
+      out[(d0 + r + 8) * 32 + e] = acc[i][2];
+      out[(d0 + r + 8) * 32 + e + 1] = acc[i][3];
+    }
+  }
   if (t < 32) {
     out[1024 + t] = m_run[t];
     out[1056 + t] = s_run[t];
@@ -202,7 +208,7 @@ extern "C" int dac_linattn_context(const void* qkv, int32_t B, int32_t hw, int32
   if (!qkv || !partial) return set_error(-1, "dac_linattn_context: null argument");
   if (nchunks < 1 || nchunks > 128) return set_error(-2, "dac_linattn_context: nchunks must be in [1,128]");
   const int slab = static_cast<int>(ceil_div(ceil_div(hw, nchunks), kLaP) * kLaP);
-  linattn_context_kernel<<<dim3(nchunks, 4, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  linattn_context_kernel<<<dim3(nchunks, 4, B), 128, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(qkv), hw, slab, partial);
   return check_launch("linattn_context_kernel");
 }

@@ -392,7 +392,7 @@ class UNetEngine:
         if not a["transformer"]:
             qkv = self.buf(B, h, w, 384)
             self.conv(prefix + "to_qkv", xn, C, a["qkv"], qkv, h, w, epi=L.EPI_QKV, block_n=128)
-            nchunks = max(1, min(128, (148 * 2) // (B * 4), hw // 256))
+            nchunks = max(1, min(128, (148 * 8) // (B * 4), hw // 256))
             partial = self.buf(B, 4, nchunks, 32 * 34, dtype=torch.float32)
             c_pad = a["out"].w.shape[-2]
             weff = self.buf(B, c_pad, 128)
