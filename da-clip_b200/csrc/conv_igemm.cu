@@ -7,6 +7,7 @@
 #include <mutex>
 #include <new>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/dac_b200.h"
@@ -37,7 +38,7 @@ static PFN_encodeTiled get_encode_fn() {
 }  // namespace dac
 
 struct dac_conv_plan {
-  CUtensorMap mapA0, mapA1, mapW;
+  CUtensorMap mapA0, mapA1, mapW, mapOut;
   dac::ConvKParams kp;
   dac::ConvKernelFn kernel;
   int grid;
@@ -170,11 +171,24 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
                         (smem_budget - res_bytes) / (long long)k.a_bytes >= 3;
   k.b_res_bytes = resident ? (uint32_t)res_bytes : 0u;
   const uint32_t stage_bytes = k.a_bytes + (resident ? 0u : (uint32_t)d->ndy * k.b_bytes);
-  int stages = (smem_budget - (int)k.b_res_bytes) / (int)stage_bytes;
+  // bf16 NHWC output through a swizzled staging tile + TMA store (coalesced, clipped by the tensor map) whenever the
+  // staging tile leaves room for >= 3 pipeline stages; otherwise each thread stores its own row directly.
+  const int out_cols = d->epi == DAC_EPI_GEGLU ? d->block_n / 2 : d->block_n;
+  uint32_t stg_bytes = 0;
+  if (d->out && !nchw && k.out_scale == 1 && out_cols % 64 == 0 && d->cout % 64 == 0 && (d->out_coff % 64) == 0 &&
+      !getenv("DAC_NO_TMA_STORE")) {
+    const uint32_t want = (uint32_t)(out_cols / 64) * kTileM * 128;
+    int without = (smem_budget - (int)k.b_res_bytes) / (int)stage_bytes;
+    if (without > kMaxStages) without = kMaxStages;
+    const int with = (smem_budget - (int)k.b_res_bytes - (int)want) / (int)stage_bytes;
+    if (with >= 4 || (with >= 3 && with >= without)) stg_bytes = want;
+  }
+  k.stg_bytes = stg_bytes;
+  int stages = (smem_budget - (int)k.b_res_bytes - (int)stg_bytes) / (int)stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) { delete pl; return set_error(-2, "dac_conv_create: tile does not fit shared memory"); }
   k.stages = stages;
-  pl->smem = (int)k.b_res_bytes + stages * (int)stage_bytes + 1024 + 256 + 2048;
+  pl->smem = (int)k.b_res_bytes + stages * (int)stage_bytes + (int)stg_bytes + 1024 + 256 + 2048;
   pl->tiles = k.ngroups * k.m_tiles * k.n_tiles;
 
   int rc = encode_act_map(&pl->mapA0, d->src0, d->c0, d->ld0, d->W, d->H, d->B, d->tile_w, a_rows, d->stride);
@@ -197,6 +211,21 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) rc = set_error(-11, "cuTensorMapEncodeTiled(weight) failed: CUresult %d", (int)r);
   }
+  if (rc == 0 && stg_bytes) {
+    PFN_encodeTiled enc = get_encode_fn();
+    const int valid_c = d->epi == DAC_EPI_GEGLU ? d->cout / 2 : d->cout;
+    cuuint64_t dims[4] = {(cuuint64_t)(d->out_coff + valid_c), (cuuint64_t)k.OWf, (cuuint64_t)k.OHf, (cuuint64_t)d->B};
+    cuuint64_t strides[3] = {(cuuint64_t)d->out_ld * 2, (cuuint64_t)k.OWf * d->out_ld * 2,
+                             (cuuint64_t)k.OHf * k.OWf * d->out_ld * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)d->tile_w, (cuuint32_t)d->tile_h, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&pl->mapOut, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, d->out, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) rc = set_error(-11, "cuTensorMapEncodeTiled(output) failed: CUresult %d", (int)r);
+  } else if (rc == 0) {
+    pl->mapOut = pl->mapA0;
+  }
   if (rc != 0) { delete pl; return rc; }
 
   int dev = 0, sms = 0;
@@ -217,7 +246,7 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
 extern "C" int dac_conv_launch(dac_conv_t pl, dac_stream_t stream) {
   if (!pl) return set_error(-1, "dac_conv_launch: null plan");
   pl->kernel<<<pl->grid, kThreads, pl->smem, static_cast<cudaStream_t>(stream)>>>(pl->mapA0, pl->mapA1, pl->mapW,
-                                                                                  pl->kp);
+                                                                                  pl->mapOut, pl->kp);
   return check_launch("conv_igemm_kernel");
 }
 

@@ -94,6 +94,7 @@ struct ConvKParams {
   int8_t out_oy[4], out_ox[4];
   float* out_nchw;
   int nchw_c, nchw_h, nchw_w;
+  uint32_t stg_bytes;      // > 0: bf16 output goes through a swizzled shared-memory tile and a TMA store
 };
 
 struct TileCoord {
@@ -176,6 +177,21 @@ __device__ __forceinline__ void chunk_store_bf16(__nv_bfloat16* __restrict__ dst
     reinterpret_cast<uint4*>(dst)[q] = u;
   }
 }
+// 32 columns of one row into the staging tile: 64-channel slabs of 128 rows x 128 B, 16 B pieces XOR-swizzled by the
+// row (the SWIZZLE_128B pattern of the output tensor map; also conflict-free for one-row-per-lane writes).
+__device__ __forceinline__ void chunk_stage_bf16(uint8_t* stg, int row, int col, const float (&v)[32]) {
+  uint8_t* slab = stg + (col >> 6) * (kTileM * 128) + row * 128;
+  const int c16 = (col & 63) >> 3;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint4 u;
+    u.x = pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
+    u.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
+    u.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
+    u.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
+    *reinterpret_cast<uint4*>(slab + (((c16 + q) ^ (row & 7)) << 4)) = u;
+  }
+}
 __device__ __forceinline__ void chunk_store_f32(float* __restrict__ dst, const float (&v)[32]) {
 #pragma unroll
   for (int q = 0; q < 8; ++q)
@@ -186,7 +202,7 @@ __device__ __forceinline__ void chunk_store_f32(float* __restrict__ dst, const f
 // a lane quadrant splits the columns: this thread owns columns [half*bn/2, (half+1)*bn/2).
 template <int EPI, int ACT, bool FILM>
 __device__ __forceinline__ void epilogue_tile(const ConvKParams& p, const TileCoord& t, uint32_t tmem_acc, int row,
-                                              int half, const float* film_sh) {
+                                              int half, const float* film_sh, uint8_t* stg) {
   const int ty = row >> p.tile_w_shift, tx = row & (p.tile_w - 1);
   const int y = t.y0 + ty, x = t.x0 + tx;
   const bool valid = (y < p.OH) && (x < p.OW);
@@ -248,10 +264,9 @@ __device__ __forceinline__ void epilogue_tile(const ConvKParams& p, const TileCo
         v[4 * q + 2] = (v[4 * q + 2] - mean) * rstd * g.z;
         v[4 * q + 3] = (v[4 * q + 3] - mean) * rstd * g.w;
       }
-      if (valid) {
-        if (p.res) chunk_add_bf16(p.res + opix * p.res_ld + c, v);
-        chunk_store_bf16(p.out + opix * p.out_ld + p.out_coff + c, v);
-      }
+      if (valid && p.res) chunk_add_bf16(p.res + opix * p.res_ld + c, v);
+      if (stg) chunk_stage_bf16(stg, row, c, v);
+      else if (valid) chunk_store_bf16(p.out + opix * p.out_ld + p.out_coff + c, v);
     }
     return;
   }
@@ -267,7 +282,8 @@ __device__ __forceinline__ void epilogue_tile(const ConvKParams& p, const TileCo
       chunk_add_f32(p.bias + col + hn, g);
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] *= gelu_f(g[j]);
-      if (valid) chunk_store_bf16(p.out + opix * p.out_ld + p.out_coff + t.nt * hn + c, v);
+      if (stg) chunk_stage_bf16(stg, row, c, v);
+      else if (valid) chunk_store_bf16(p.out + opix * p.out_ld + p.out_coff + t.nt * hn + c, v);
     }
     return;
   }
@@ -293,7 +309,8 @@ __device__ __forceinline__ void epilogue_tile(const ConvKParams& p, const TileCo
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] *= inv;
       }
-      if (valid) chunk_store_bf16(p.out + opix * p.out_ld + p.out_coff + ch, v);
+      if (stg) chunk_stage_bf16(stg, row, c, v);
+      else if (valid) chunk_store_bf16(p.out + opix * p.out_ld + p.out_coff + ch, v);
       continue;
     }
     if (p.bias) chunk_add_f32(p.bias + ch, v);
@@ -319,15 +336,17 @@ __device__ __forceinline__ void epilogue_tile(const ConvKParams& p, const TileCo
       if (p.res) chunk_add_bf16(p.res + opix * p.res_ld + ch, v);
       if (p.res2) chunk_add_bf16(p.res2 + opix * p.res2_ld + ch, v);
       if (p.out_f32) chunk_store_f32(p.out_f32 + opix * p.out_f32_ld + ch, v);
-      if (p.out) chunk_store_bf16(p.out + opix * p.out_ld + p.out_coff + ch, v);
+      if (p.out && !stg) chunk_store_bf16(p.out + opix * p.out_ld + p.out_coff + ch, v);
     }
+    if (stg) chunk_stage_bf16(stg, row, c, v);
   }
 }
 
 template <int EPI, int ACT, bool FILM>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
-                  const __grid_constant__ CUtensorMap mapW, const __grid_constant__ ConvKParams p) {
+                  const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapOut,
+                  const __grid_constant__ ConvKParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024 B alignment is required by the 128B swizzle atoms (TMA write and UMMA read agree on address bits).
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -336,7 +355,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   uint8_t* b_res = smem;
   uint8_t* ring = smem + p.b_res_bytes;
   const uint32_t stage_bytes = p.a_bytes + (b_resident ? 0u : static_cast<uint32_t>(p.ndy) * p.b_bytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + static_cast<size_t>(p.stages) * stage_bytes);
+  uint8_t* stg = p.stg_bytes ? ring + static_cast<size_t>(p.stages) * stage_bytes : nullptr;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + static_cast<size_t>(p.stages) * stage_bytes + p.stg_bytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + kMaxStages;
   uint64_t* tmem_full = bars + 2 * kMaxStages;
@@ -356,6 +376,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     tma_prefetch_desc(&mapA0);
     tma_prefetch_desc(&mapA1);
     tma_prefetch_desc(&mapW);
+    tma_prefetch_desc(&mapOut);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
@@ -498,8 +519,23 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
+      if (stg) {
+        // the previous tile's TMA store must have finished reading the staging tile before it is rewritten
+        if (threadIdx.x == 64) tma_store_wait_read();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
       const uint32_t tmem_acc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kAccStride;
-      epilogue_tile<EPI, ACT, FILM>(p, t, tmem_acc, row, half, film_sh);
+      epilogue_tile<EPI, ACT, FILM>(p, t, tmem_acc, row, half, film_sh, stg);
+      if (stg) {
+        fence_proxy_async();                       // generic-proxy smem writes -> visible to the TMA engine
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (threadIdx.x == 64) {
+          const int cols = (EPI == KE_GEGLU) ? (p.block_n >> 1) : p.block_n;   // output columns of this tile
+          for (int s = 0; s * 64 < cols; ++s)
+            tma_store_4d(&mapOut, stg + s * (kTileM * 128), p.out_coff + t.nt * cols + s * 64, t.x0, t.y0, t.n);
+          tma_store_commit();
+        }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -510,6 +546,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     }
   }
 
+  if (stg && threadIdx.x == 64) tma_store_wait_read();   // shared memory must outlive the last bulk store's reads
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -518,7 +555,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   }
 }
 
-typedef void (*ConvKernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const ConvKParams);
+typedef void (*ConvKernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
+                             const ConvKParams);
 
 // The epilogue flavours that exist as separate kernels; everything else in the epilogue is a warp-uniform
 // runtime branch on a pointer.
