@@ -20,6 +20,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
 
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
@@ -143,7 +144,7 @@ def run_product(args):
     lq_host = inp["lq"].pin_memory()
     lq = lq_host.to(dev)
     img_ctx, deg_ctx = clip.encode_image(clip_img_host.to(dev), control=True)
-    gather = [torch.empty(B, 3, S, S, device=dev) for _ in range(world)] if world > 1 else None
+    from daclip_b200.parallel import gather_restored
     net = model.model.module
     eng = net.engine(B, S, S)
     torch.manual_seed(1234 + rank)
@@ -153,9 +154,7 @@ def run_product(args):
         x_T = sde.noise_state(lq)
         model.feed_data(x_T, lq, None, text_context=deg_ctx, image_context=img_ctx)
         model.test(sde, mode=args.mode)
-        if world > 1:
-            dist.all_gather(gather, model.output)
-        return model.output
+        return gather_restored(model.output, world * B)     # one NCCL all_gather of the restored shard (N > 1)
 
     out_host = torch.empty(B, 3, S, S).pin_memory()
 
