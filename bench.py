@@ -122,7 +122,8 @@ def conv_time_per_eval(eng, reps=3):
         total = sum(a.elapsed_time(b) for n, a, b in evs)
         if best is None or total < best[1]:
             best = (conv, total, sum(1 for n, _, _ in evs if eng.is_conv(n)),
-                    sorted(((a.elapsed_time(b), n) for n, a, b in evs), reverse=True)[:30])
+                    sorted(((a.elapsed_time(b), n) for n, a, b in evs), reverse=True)[:12],
+                    [(n, a.elapsed_time(b)) for n, a, b in evs])
     return best
 
 
@@ -209,7 +210,11 @@ def run_product(args):
 
     result = None
     if rank == 0:
-        conv_ms, all_ms, n_conv, top = conv_time_per_eval(eng)
+        conv_ms, all_ms, n_conv, top, layers = conv_time_per_eval(eng)
+        if args.dump_layers:
+            with open(args.dump_layers, "w") as f:
+                for n, ms_ in layers:
+                    f.write(f"{ms_ * 1e3:9.1f} us  {'conv' if eng.is_conv(n) else 'aux '}  {n}\n")
         peak_tf, peak_bw, which = peaks()
         gflop = CONV_GFLOP_PER_EVAL.get(S, CONV_GFLOP_PER_EVAL[256] * (S / 256) ** 2) * B
         achieved = gflop / n_conv / (conv_ms / n_conv) if conv_ms > 0 else 0.0       # GFLOP/ms == TFLOP/s
@@ -327,6 +332,7 @@ def main():
     ap.add_argument("--mode", default="posterior", choices=["posterior", "sde"])
     ap.add_argument("--cpu-evals", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dump-layers", default=None, help="write the per-launch CUDA-event times of one evaluation here")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

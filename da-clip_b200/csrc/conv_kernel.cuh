@@ -159,22 +159,23 @@ __device__ __forceinline__ void chunk_film(const float* __restrict__ sc, const f
 }
 __device__ __forceinline__ void chunk_add_bf16(const __nv_bfloat16* __restrict__ src, float (&v)[32]) {
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(src) + q);
-    const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
-    v[q * 8 + 0] += a.x; v[q * 8 + 1] += a.y; v[q * 8 + 2] += b.x; v[q * 8 + 3] += b.y;
-    v[q * 8 + 4] += c.x; v[q * 8 + 5] += c.y; v[q * 8 + 6] += d.x; v[q * 8 + 7] += d.y;
+  for (int q = 0; q < 2; ++q) {          // 2 x 32 B = this row's 32 channels
+    const U32x8 u = ldg256(src + q * 16);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float2 a = unpack_bf16(u.v[j]);
+      v[q * 16 + 2 * j] += a.x;
+      v[q * 16 + 2 * j + 1] += a.y;
+    }
   }
 }
 __device__ __forceinline__ void chunk_store_bf16(__nv_bfloat16* __restrict__ dst, const float (&v)[32]) {
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    uint4 u;
-    u.x = pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
-    u.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
-    u.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
-    u.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
-    reinterpret_cast<uint4*>(dst)[q] = u;
+  for (int q = 0; q < 2; ++q) {
+    U32x8 u;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) u.v[j] = pack_bf16(v[q * 16 + 2 * j], v[q * 16 + 2 * j + 1]);
+    stg256(dst + q * 16, u);
   }
 }
 // 32 columns of one row into the staging tile: 64-channel slabs of 128 rows x 128 B, 16 B pieces XOR-swizzled by the

@@ -170,6 +170,25 @@ __device__ __forceinline__ uint32_t elect_one() {
   return pred;
 }
 
+// 256-bit global accesses (sm_100: LDG.256 / STG.256): one full 32-byte sector per thread and instruction, so
+// row-per-thread epilogue traffic moves whole sectors instead of two 16-byte halves.
+struct __align__(32) U32x8 {
+  uint32_t v[8];
+};
+__device__ __forceinline__ U32x8 ldg256(const void* p) {
+  U32x8 r;
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]),
+                 "=r"(r.v[7])
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg256(void* p, const U32x8& r) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r.v[0]), "r"(r.v[1]), "r"(r.v[2]),
+               "r"(r.v[3]), "r"(r.v[4]), "r"(r.v[5]), "r"(r.v[6]), "r"(r.v[7])
+               : "memory");
+}
+
 // ---------------------------------------------------------------- math
 __device__ __forceinline__ float tanh_approx(float x) {
   float y;
