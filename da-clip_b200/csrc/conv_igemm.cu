@@ -184,11 +184,16 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
     if (with >= 4 || (with >= 3 && with >= without)) stg_bytes = want;
   }
   k.stg_bytes = stg_bytes;
-  int stages = (smem_budget - (int)k.b_res_bytes - (int)stg_bytes) / (int)stage_bytes;
+  k.stg_count = 1;
+  if (stg_bytes) {   // a second staging tile when it still leaves >= 4 stages (short-K layers are store-latency bound)
+    const int with2 = (smem_budget - (int)k.b_res_bytes - 2 * (int)stg_bytes) / (int)stage_bytes;
+    if (with2 >= 4) k.stg_count = 2;
+  }
+  int stages = (smem_budget - (int)k.b_res_bytes - (int)stg_bytes * k.stg_count) / (int)stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) { delete pl; return set_error(-2, "dac_conv_create: tile does not fit shared memory"); }
   k.stages = stages;
-  pl->smem = (int)k.b_res_bytes + stages * (int)stage_bytes + (int)stg_bytes + 1024 + 256 + 2048;
+  pl->smem = (int)k.b_res_bytes + stages * (int)stage_bytes + (int)stg_bytes * k.stg_count + 1024 + 256 + 2048;
   pl->tiles = k.ngroups * k.m_tiles * k.n_tiles;
 
   int rc = encode_act_map(&pl->mapA0, d->src0, d->c0, d->ld0, d->W, d->H, d->B, d->tile_w, a_rows, d->stride);

@@ -95,6 +95,7 @@ struct ConvKParams {
   float* out_nchw;
   int nchw_c, nchw_h, nchw_w;
   uint32_t stg_bytes;      // > 0: bf16 output goes through a swizzled shared-memory tile and a TMA store
+  int stg_count;           // 1 or 2 staging tiles (2: the store of tile i overlaps the epilogue of tile i+1)
 };
 
 struct TileCoord {
@@ -356,8 +357,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   uint8_t* b_res = smem;
   uint8_t* ring = smem + p.b_res_bytes;
   const uint32_t stage_bytes = p.a_bytes + (b_resident ? 0u : static_cast<uint32_t>(p.ndy) * p.b_bytes);
-  uint8_t* stg = p.stg_bytes ? ring + static_cast<size_t>(p.stages) * stage_bytes : nullptr;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + static_cast<size_t>(p.stages) * stage_bytes + p.stg_bytes);
+  uint8_t* stg_base = p.stg_bytes ? ring + static_cast<size_t>(p.stages) * stage_bytes : nullptr;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + static_cast<size_t>(p.stages) * stage_bytes +
+                                               static_cast<size_t>(p.stg_bytes) * p.stg_count);
   uint64_t* full = bars;
   uint64_t* empty = bars + kMaxStages;
   uint64_t* tmem_full = bars + 2 * kMaxStages;
@@ -520,9 +522,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      if (stg) {
-        // the previous tile's TMA store must have finished reading the staging tile before it is rewritten
-        if (threadIdx.x == 64) tma_store_wait_read();
+      uint8_t* stg = nullptr;
+      if (stg_base) {
+        // the TMA store that last used this staging tile must have finished reading it before it is rewritten
+        stg = stg_base + ((p.stg_count == 2 && ((tile - tile_begin) & 1)) ? p.stg_bytes : 0u);
+        if (threadIdx.x == 64) {
+          if (p.stg_count == 2) tma_store_wait_read1();
+          else tma_store_wait_read();
+        }
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
       const uint32_t tmem_acc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kAccStride;
@@ -547,7 +554,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     }
   }
 
-  if (stg && threadIdx.x == 64) tma_store_wait_read();   // shared memory must outlive the last bulk store's reads
+  if (stg_base && threadIdx.x == 64) tma_store_wait_read();   // shared memory must outlive the last bulk store's reads
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
