@@ -164,7 +164,7 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
 
   // Weights stay resident in shared memory when the whole tensor fits beside >= 3 activation stages: the
   // mainloop then streams activations only (L2 -> SM ingest is what bounds the 64/128-channel layers).
-  const int smem_budget = 227 * 1024 - 1024 /*align*/ - 256 /*barriers*/ - 2048 /*FiLM stage*/;
+  const int smem_budget = 227 * 1024 - 1024 /*align*/ - 256 /*barriers*/ - 4096 /*FiLM stage, 2 groups*/;
   const int chunks = k.chunks0 + k.chunks1;
   const long long res_bytes = (long long)d->ntaps * chunks * k.b_bytes;
   const bool resident = k.n_tiles == 1 && d->ngroups == 1 && !d->per_image_w && res_bytes <= 160 * 1024 &&
@@ -177,23 +177,19 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
   uint32_t stg_bytes = 0;
   if (d->out && !nchw && k.out_scale == 1 && out_cols % 64 == 0 && d->cout % 64 == 0 && (d->out_coff % 64) == 0 &&
       !getenv("DAC_NO_TMA_STORE")) {
-    const uint32_t want = (uint32_t)(out_cols / 64) * kTileM * 128;
+    const uint32_t want = (uint32_t)(out_cols / 64) * kTileM * 128;     // per epilogue group; two groups
     int without = (smem_budget - (int)k.b_res_bytes) / (int)stage_bytes;
     if (without > kMaxStages) without = kMaxStages;
-    const int with = (smem_budget - (int)k.b_res_bytes - (int)want) / (int)stage_bytes;
+    const int with = (smem_budget - (int)k.b_res_bytes - 2 * (int)want) / (int)stage_bytes;
     if (with >= 4 || (with >= 3 && with >= without)) stg_bytes = want;
   }
   k.stg_bytes = stg_bytes;
-  k.stg_count = 1;
-  if (stg_bytes) {   // a second staging tile when it still leaves >= 4 stages (short-K layers are store-latency bound)
-    const int with2 = (smem_budget - (int)k.b_res_bytes - 2 * (int)stg_bytes) / (int)stage_bytes;
-    if (with2 >= 4) k.stg_count = 2;
-  }
+  k.stg_count = stg_bytes ? 2 : 1;   // one staging tile per epilogue group
   int stages = (smem_budget - (int)k.b_res_bytes - (int)stg_bytes * k.stg_count) / (int)stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) { delete pl; return set_error(-2, "dac_conv_create: tile does not fit shared memory"); }
   k.stages = stages;
-  pl->smem = (int)k.b_res_bytes + stages * (int)stage_bytes + (int)stg_bytes * k.stg_count + 1024 + 256 + 2048;
+  pl->smem = (int)k.b_res_bytes + stages * (int)stage_bytes + (int)stg_bytes * k.stg_count + 1024 + 256 + 4096;
   pl->tiles = k.ngroups * k.m_tiles * k.n_tiles;
 
   int rc = encode_act_map(&pl->mapA0, d->src0, d->c0, d->ld0, d->W, d->H, d->B, d->tile_w, a_rows, d->stride);

@@ -9,7 +9,7 @@
 //               both 128B-swizzled, into an smem ring guarded by full/empty mbarriers;
 //   warp 1      allocates TMEM, one lane issues tcgen05.mma (M128 x N x K16, bf16 -> fp32 in TMEM) and
 //               tcgen05.commit's the smem slot back to the producer / the accumulator to the epilogue;
-//   warps 2-9   epilogue (two warps per TMEM lane quadrant, each owning half of the tile's columns):
+//   warps 2-9   epilogue, two groups of four warps, group g draining TMEM accumulator stage g (every 2nd tile):
 //               tcgen05.ld the accumulator (one pixel per thread), apply bias / FiLM / SiLU|GELU / GEGLU /
 //               channel-LayerNorm / q-softmax / residuals in fp32, store NHWC bf16 (and/or fp32, or fp32 NCHW for
 //               final_conv).  Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
@@ -201,10 +201,10 @@ __device__ __forceinline__ void chunk_store_f32(float* __restrict__ dst, const f
 }
 
 // Epilogue of one 128 x block_n accumulator tile.  Thread = one output pixel (TMEM lane `row`); the warp pair of
-// a lane quadrant splits the columns: this thread owns columns [half*bn/2, (half+1)*bn/2).
+// the four warps of an epilogue group cover the four TMEM lane quadrants; a thread handles every column of its row.
 template <int EPI, int ACT, bool FILM>
 __device__ __forceinline__ void epilogue_tile(const ConvKParams& p, const TileCoord& t, uint32_t tmem_acc, int row,
-                                              int half, const float* film_sh, uint8_t* stg) {
+                                              const float* film_sh, uint8_t* stg) {
   const int ty = row >> p.tile_w_shift, tx = row & (p.tile_w - 1);
   const int y = t.y0 + ty, x = t.x0 + tx;
   const bool valid = (y < p.OH) && (x < p.OW);
@@ -215,7 +215,6 @@ __device__ __forceinline__ void epilogue_tile(const ConvKParams& p, const TileCo
 
   if (EPI == KE_NCHW) {
     // final_conv: 16-column tile, fp32 planar output cropped to the un-padded image; one warp per quadrant works.
-    if (half != 0) return;
     uint32_t r[16];
     tmem_ld16(tmem_acc, r);
     tmem_ld_wait();
@@ -232,8 +231,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvKParams& p, const TileCo
   }
 
   if (EPI == KE_LN) {
-    // channel LayerNorm over the whole (single) N tile; both warps of a quadrant sweep all columns for the
-    // statistics (TMEM reads are cheap), each normalises and stores its own half.
+    // channel LayerNorm over the whole (single) N tile: three sweeps over this row's TMEM columns.
     const int C = p.cout;
     float sum = 0.f;
     for (int c = 0; c < C; c += 32) {
@@ -254,8 +252,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvKParams& p, const TileCo
       }
     }
     const float rstd = rsqrtf(ss / C + p.ln_eps);
-    const int c0 = half * (C >> 1);
-    for (int c = c0; c < c0 + (C >> 1); c += 32) {
+    for (int c = 0; c < C; c += 32) {
       chunk_from_tmem(tmem_acc + c, v);
       if (p.bias) chunk_add_f32(p.bias + c, v);
 #pragma unroll
@@ -274,8 +271,8 @@ __device__ __forceinline__ void epilogue_tile(const ConvKParams& p, const TileCo
   }
 
   if (EPI == KE_GEGLU) {
-    const int hn = p.block_n >> 1, qn = p.block_n >> 2;
-    for (int c = half * qn; c < (half + 1) * qn; c += 32) {
+    const int hn = p.block_n >> 1;
+    for (int c = 0; c < hn; c += 32) {
       float g[32];
       chunk_from_tmem(tmem_acc + c, v);
       chunk_from_tmem(tmem_acc + hn + c, g);
@@ -291,8 +288,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvKParams& p, const TileCo
   }
 
   // KE_PLAIN / KE_QKV
-  const int hn = p.block_n >> 1;
-  for (int c = half * hn; c < (half + 1) * hn; c += 32) {
+  for (int c = 0; c < p.block_n; c += 32) {
     const int ch = t.nt * p.block_n + c;
     if (ch >= p.cout) break;  // warp-uniform (cout_pad > cout)
     chunk_from_tmem(tmem_acc + c, v);
@@ -386,7 +382,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], kEpiWarps);
+      mbar_init(&tmem_empty[s], kEpiWarps / 2);
     }
     mbar_init(b_full, 1);
     fence_barrier_init();
@@ -496,65 +492,62 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       }
     }
   } else {
-    // ===================== epilogue warps (2..9) =====================
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
-    const int half = (warp - 2) >> 2;
+    // ===================== epilogue: two groups of four warps (2..5 / 6..9) =====================
+    // Group g owns TMEM accumulator stage g, i.e. every second tile of this CTA: two tiles are in the epilogue at
+    // once, so the latency chain of one (barrier wait, TMEM loads, residual loads, staging, TMA store) hides
+    // behind the other - what bounds the short-K layers (1x1 convs, to_qkv, to_out).
+    const int quad = warp & 3;          // TMEM lane quadrant this warp may access
+    const int group = (warp - 2) >> 2;
     const int row = quad * 32 + lane;
-    int acc = 0;
+    const int gthread = threadIdx.x - 64 - group * 128;   // 0..127 within the group
+    float* film_g = film_sh + group * 512;
+    uint8_t* stg = stg_base ? stg_base + group * p.stg_bytes : nullptr;
     uint32_t acc_phase = 0;
     int film_key = -1;
-    for (int tile = tile_begin; tile < tile_end; ++tile) {
+    for (int tile = tile_begin + group; tile < tile_end; tile += 2) {
       const TileCoord t = decode_tile(p, tile);
       if (FILM) {
         // FiLM parameters depend on (image, N tile) only: restage when that pair changes (rare with contiguous
-        // tile ranges).  Named barrier 1 = the 256 epilogue threads.
+        // tile ranges).  Named barrier 1 + group = the 128 threads of this group.
         const int key = t.n * p.n_tiles + t.nt;
         if (key != film_key) {
           film_key = key;
-          asm volatile("bar.sync 1, 256;" ::: "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");
           const float* src = p.film + static_cast<long long>(t.n) * p.film_ld + p.film_off + t.nt * p.block_n;
-          for (int i = threadIdx.x - 64; i < 2 * p.block_n; i += 256) {
+          for (int i = gthread; i < 2 * p.block_n; i += 128) {
             const int c = i < p.block_n ? i : i - p.block_n;
-            film_sh[i] = i < p.block_n ? __ldg(src + c) + 1.0f : __ldg(src + p.cout + c);
+            film_g[i] = i < p.block_n ? __ldg(src + c) + 1.0f : __ldg(src + p.cout + c);
           }
-          asm volatile("bar.sync 1, 256;" ::: "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");
         }
       }
-      mbar_wait(&tmem_full[acc], acc_phase);
+      mbar_wait(&tmem_full[group], acc_phase);
       tc_fence_after();
-      uint8_t* stg = nullptr;
-      if (stg_base) {
-        // the TMA store that last used this staging tile must have finished reading it before it is rewritten
-        stg = stg_base + ((p.stg_count == 2 && ((tile - tile_begin) & 1)) ? p.stg_bytes : 0u);
-        if (threadIdx.x == 64) {
-          if (p.stg_count == 2) tma_store_wait_read1();
-          else tma_store_wait_read();
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (stg) {
+        // this group's previous TMA store must have finished reading the staging tile before it is rewritten
+        if (gthread == 0) tma_store_wait_read();
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");
       }
-      const uint32_t tmem_acc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kAccStride;
-      epilogue_tile<EPI, ACT, FILM>(p, t, tmem_acc, row, half, film_sh, stg);
+      const uint32_t tmem_acc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + group * kAccStride;
+      epilogue_tile<EPI, ACT, FILM>(p, t, tmem_acc, row, film_g, stg);
       if (stg) {
         fence_proxy_async();                       // generic-proxy smem writes -> visible to the TMA engine
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (threadIdx.x == 64) {
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");
+        if (gthread == 0) {
           const int cols = (EPI == KE_GEGLU) ? (p.block_n >> 1) : p.block_n;   // output columns of this tile
-          for (int s = 0; s * 64 < cols; ++s)
-            tma_store_4d(&mapOut, stg + s * (kTileM * 128), p.out_coff + t.nt * cols + s * 64, t.x0, t.y0, t.n);
+          for (int s_ = 0; s_ * 64 < cols; ++s_)
+            tma_store_4d(&mapOut, stg + s_ * (kTileM * 128), p.out_coff + t.nt * cols + s_ * 64, t.x0, t.y0, t.n);
           tma_store_commit();
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-      if (++acc == 2) {
-        acc = 0;
-        acc_phase ^= 1;
-      }
+      if (lane == 0) mbar_arrive(&tmem_empty[group]);
+      acc_phase ^= 1;
     }
+    if (stg && gthread == 0) tma_store_wait_read();   // shared memory must outlive the last bulk store's reads
   }
 
-  if (stg_base && threadIdx.x == 64) tma_store_wait_read();   // shared memory must outlive the last bulk store's reads
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
