@@ -22,14 +22,36 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-constexpr int kFaBlockQ = 64, kFaBlockK = 64, kFaD = 32;
-constexpr int kKsPitch = kFaD + 8;       // bf16 elements
-constexpr int kVtPitch = kFaBlockK + 8;  // bf16 elements
+constexpr int kFaBlockQ = 128, kFaBlockK = 64, kFaD = 32;
+constexpr int kFaPitch = kFaD + 8;  // bf16 elements per smem row: 80 B rows keep ldmatrix conflict-free
 
-__global__ void __launch_bounds__(128) flash_attn_d32_kernel(const __nv_bfloat16* __restrict__ qkv,
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem)), "l"(gmem), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(smem)));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(smem)));
+}
+
+// 128 query rows per CTA (8 warps x 16 rows); 64-key blocks of K and V, row-major [key][d], double-buffered with
+// cp.async; B fragments via ldmatrix (K) / ldmatrix.trans (V); online softmax with ex2.approx (one MUFU per score -
+// at d = 32 the SFU pipe, not the tensor pipe, bounds this kernel).
+__global__ void __launch_bounds__(256) flash_attn_d32_kernel(const __nv_bfloat16* __restrict__ qkv,
                                                              __nv_bfloat16* __restrict__ out, int n, int heads) {
-  __shared__ __align__(16) __nv_bfloat16 Ks[kFaBlockK * kKsPitch];
-  __shared__ __align__(16) __nv_bfloat16 Vt[kFaD * kVtPitch];
+  __shared__ __align__(16) __nv_bfloat16 Ks[2][kFaBlockK * kFaPitch];
+  __shared__ __align__(16) __nv_bfloat16 Vs[2][kFaBlockK * kFaPitch];
   const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ld = 3 * heads * kFaD;
@@ -37,6 +59,19 @@ __global__ void __launch_bounds__(128) flash_attn_d32_kernel(const __nv_bfloat16
   const int qcol = h * kFaD, kcol = heads * kFaD + h * kFaD, vcol = 2 * heads * kFaD + h * kFaD;
   const int r0 = qb * kFaBlockQ + warp * 16 + (lane >> 2);  // rows r0 and r0 + 8
   const int cq = 2 * (lane & 3);
+
+  auto prefetch = [&](int buf, int k0) {
+    // 64 keys x 4 x 16 B for K and for V: 512 copies, two per thread; rows beyond n are zero-filled
+    for (int i = threadIdx.x; i < kFaBlockK * 8; i += 256) {
+      const int isv = i >> 8, key = (i >> 2) & 63, part = i & 3;
+      const int krow = min(k0 + key, n - 1);
+      const __nv_bfloat16* src = base + static_cast<int64_t>(krow) * ld + (isv ? vcol : kcol) + part * 8;
+      __nv_bfloat16* dst = (isv ? Vs[buf] : Ks[buf]) + key * kFaPitch + part * 8;
+      cp_async16(dst, src, (k0 + key < n) ? 16 : 0);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  prefetch(0, 0);
 
   // Q fragments (A operand), 2 k-steps of 16 channels
   uint32_t qa[2][4];
@@ -58,36 +93,23 @@ __global__ void __launch_bounds__(128) flash_attn_d32_kernel(const __nv_bfloat16
     for (int i = 0; i < 4; ++i) o[j][i] = 0.f;
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
 
-  for (int k0 = 0; k0 < n; k0 += kFaBlockK) {
-    __syncthreads();  // previous block fully consumed
-    // stage K [64][32] and V^T [32][64]
-    for (int i = threadIdx.x; i < kFaBlockK * 4; i += 128) {
-      const int key = i >> 2, part = i & 3;
-      uint4 uk = make_uint4(0, 0, 0, 0), uv = make_uint4(0, 0, 0, 0);
-      if (k0 + key < n) {
-        const __nv_bfloat16* row = base + static_cast<int64_t>(k0 + key) * ld;
-        uk = *reinterpret_cast<const uint4*>(row + kcol + part * 8);
-        uv = *reinterpret_cast<const uint4*>(row + vcol + part * 8);
-      }
-      *reinterpret_cast<uint4*>(&Ks[key * kKsPitch + part * 8]) = uk;
-      const __nv_bfloat16* vv = reinterpret_cast<const __nv_bfloat16*>(&uv);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) Vt[(part * 8 + j) * kVtPitch + key] = vv[j];
-    }
-    __syncthreads();
+  int buf = 0;
+  for (int k0 = 0; k0 < n; k0 += kFaBlockK, buf ^= 1) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                                   // block k0 landed; everyone is done with the other buffer
+    if (k0 + kFaBlockK < n) prefetch(buf ^ 1, k0 + kFaBlockK);
+    const __nv_bfloat16* Kb = Ks[buf];
+    const __nv_bfloat16* Vb = Vs[buf];
 
-    // S = Q K^T : 8 n-tiles of 8 keys
+    // S = Q K^T : 8 n-tiles of 8 keys; one ldmatrix.x4 per n-tile = B fragments of both k-steps
     float s[8][4];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
+      uint32_t kb[4];
+      ldmatrix_x4(kb, Kb + (j * 8 + (lane & 7)) * kFaPitch + (lane >> 3) * 8);
       s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
-#pragma unroll
-      for (int kk = 0; kk < 2; ++kk) {
-        const __nv_bfloat16* kp = &Ks[(j * 8 + (lane >> 2)) * kKsPitch + kk * 16 + cq];
-        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(kp);
-        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(kp + 8);
-        mma_bf16_16816(s[j], qa[kk], b0, b1);
-      }
+      mma_bf16_16816(s[j], qa[0], kb[0], kb[1]);
+      mma_bf16_16816(s[j], qa[1], kb[2], kb[3]);
     }
     if (k0 + kFaBlockK > n) {  // mask keys beyond n
 #pragma unroll
@@ -108,7 +130,7 @@ __global__ void __launch_bounds__(128) flash_attn_d32_kernel(const __nv_bfloat16
     mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-    const float a0 = exp2f((m0 - mx0) * sl2), a1 = exp2f((m1 - mx1) * sl2);  // m = -inf on the first block -> 0
+    const float a0 = ex2_approx((m0 - mx0) * sl2), a1 = ex2_approx((m1 - mx1) * sl2);  // -inf on block 0 -> 0
     m0 = mx0;
     m1 = mx1;
     const float mb0 = mx0 * sl2, mb1 = mx1 * sl2;
@@ -121,22 +143,23 @@ __global__ void __launch_bounds__(128) flash_attn_d32_kernel(const __nv_bfloat16
     uint32_t pa[4][4];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float p0 = exp2f(s[j][0] * sl2 - mb0), p1 = exp2f(s[j][1] * sl2 - mb0);
-      const float p2 = exp2f(s[j][2] * sl2 - mb1), p3 = exp2f(s[j][3] * sl2 - mb1);
+      const float p0 = ex2_approx(fmaf(s[j][0], sl2, -mb0)), p1 = ex2_approx(fmaf(s[j][1], sl2, -mb0));
+      const float p2 = ex2_approx(fmaf(s[j][2], sl2, -mb1)), p3 = ex2_approx(fmaf(s[j][3], sl2, -mb1));
       l0 += p0 + p1;
       l1 += p2 + p3;
       pa[j >> 1][(j & 1) * 2 + 0] = pack_bf16(p0, p1);
       pa[j >> 1][(j & 1) * 2 + 1] = pack_bf16(p2, p3);
     }
-    // O += P V : 4 k-steps of 16 keys, 4 n-tiles of 8 channels
+    // O += P V : 4 k-steps of 16 keys; per k-step two ldmatrix.x4.trans = B fragments of the 4 channel n-tiles
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
 #pragma unroll
-      for (int jd = 0; jd < 4; ++jd) {
-        const __nv_bfloat16* vp = &Vt[(jd * 8 + (lane >> 2)) * kVtPitch + ks * 16 + cq];
-        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(vp);
-        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(vp + 8);
-        mma_bf16_16816(o[jd], pa[ks], b0, b1);
+      for (int jp = 0; jp < 2; ++jp) {
+        uint32_t vb[4];
+        ldmatrix_x4_trans(vb, Vb + (ks * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * kFaPitch +
+                                  (jp * 2 + (lane >> 4)) * 8);
+        mma_bf16_16816(o[jp * 2], pa[ks], vb[0], vb[1]);
+        mma_bf16_16816(o[jp * 2 + 1], pa[ks], vb[2], vb[3]);
       }
     }
   }
@@ -223,7 +246,7 @@ extern "C" int dac_attention(const void* qkv, void* out, int32_t B, int32_t n, i
   if (!qkv || !out) return set_error(-1, "dac_attention: null argument");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (d == 32) {
-    flash_attn_d32_kernel<<<dim3((n + kFaBlockQ - 1) / kFaBlockQ, heads, B), 128, 0, s>>>(
+    flash_attn_d32_kernel<<<dim3((n + kFaBlockQ - 1) / kFaBlockQ, heads, B), 256, 0, s>>>(
         static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), n, heads);
     return check_launch("flash_attn_d32_kernel");
   }

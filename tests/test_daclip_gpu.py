@@ -78,3 +78,25 @@ def test_encode_image_batch_vs_oracle(setup):
     # normalize=True path
     a, b = m.encode_image(image, control=True, normalize=True)
     assert (a.norm(dim=-1) - 1).abs().max().item() < 1e-4 and (b.norm(dim=-1) - 1).abs().max().item() < 1e-4
+
+
+def test_encode_image_batch256_argmax(setup):
+    """BASELINE config C5: encode_image alone at batch 256 (M = 12,800 tokens), degradation-type argmax."""
+    from oracle import daclip_oracle as D
+    m, sd, g = setup
+    B = 256
+    image = torch.randn(B, 3, 224, 224, generator=torch.Generator().manual_seed(21)).cuda()
+    img_f, deg_f = m.encode_image(image, control=True)
+    text = g["text_features"].cuda()
+    am, logits = m.degradation_argmax(deg_f, text, return_logits=True)
+    sdc = {k: v.cuda() for k, v in sd.items()}
+    with torch.no_grad():
+        refs = [D.encode_image_control(sdc, image[i:i + 32]) for i in range(0, B, 32)]
+    ref_img, ref_deg = torch.cat([r[0] for r in refs]), torch.cat([r[1] for r in refs])
+    assert rel(img_f, ref_img) < 2e-2 and rel(deg_f, ref_deg) < 2e-2
+    ref_logits = D.degradation_logits(ref_deg, text)
+    err = (logits - ref_logits).abs().max().item()
+    top2 = ref_logits.topk(2, dim=-1).values
+    decided = (top2[:, 0] - top2[:, 1]) > 4 * err
+    assert torch.equal(am[decided], ref_logits.argmax(-1)[decided])
+    assert decided.float().mean().item() > 0.7

@@ -162,6 +162,38 @@ def test_trajectory_256_batch_vs_oracle(model, cuda):
     assert psnr(x, x_ref) >= 45.0
 
 
+def test_forward_512_vs_oracle(model):
+    """BASELINE config C4 shape (512x512): 4096-token self-attention, larger conv grids."""
+    from daclip_b200 import synthetic
+    from oracle import unet_oracle as O
+    m, sd, kw = model
+    cfg = O.UNetConfig(**kw)
+    inp = {k: v.cuda() for k, v in synthetic.restoration_inputs(1, 512, 512, T=1, seed=9).items()}
+    sdc = {k: v.cuda() for k, v in sd.items()}
+    xt = inp["lq"] + inp["eps0"] * (50 / 255)
+    with torch.no_grad():
+        ref = O.unet_forward(sdc, cfg, xt, inp["lq"], 42.0, inp["text_context"], inp["image_context"])
+    out = m(xt, inp["lq"], 42.0, text_context=inp["text_context"], image_context=inp["image_context"])
+    assert rel_err(out, ref) < 2e-2, rel_err(out, ref)
+
+
+def test_odd_sizes_and_batch(model):
+    """Reflect padding in both directions, batch 3, non-square (reference: arch.py:111-116,172)."""
+    from daclip_b200 import synthetic
+    from oracle import unet_oracle as O
+    m, sd, kw = model
+    cfg = O.UNetConfig(**kw)
+    sdc = {k: v.cuda() for k, v in sd.items()}
+    for (B, H, W) in [(3, 50, 70), (1, 17, 33)]:
+        inp = {k: v.cuda() for k, v in synthetic.restoration_inputs(B, H, W, T=1, seed=12).items()}
+        xt = inp["lq"] + inp["eps0"] * (50 / 255)
+        with torch.no_grad():
+            ref = O.unet_forward(sdc, cfg, xt, inp["lq"], 7.0, inp["text_context"], inp["image_context"])
+        out = m(xt, inp["lq"], 7.0, text_context=inp["text_context"], image_context=inp["image_context"])
+        assert out.shape == (B, 3, H, W)
+        assert rel_err(out, ref) < 2e-2, (B, H, W, rel_err(out, ref))
+
+
 def test_wrapper_test_api(model, cuda):
     """DenoisingModel-style wrapper: feed_data / test(sde, mode) / get_current_visuals (denoising_model.py:121-173)."""
     from daclip_b200 import synthetic
