@@ -38,7 +38,7 @@ static PFN_encodeTiled get_encode_fn() {
 }  // namespace dac
 
 struct dac_conv_plan {
-  CUtensorMap mapA0, mapA1, mapW, mapOut;
+  CUtensorMap mapA0, mapA1, mapW, mapOut, mapOut2;
   dac::ConvKParams kp;
   dac::ConvKernelFn kernel;
   int grid;
@@ -99,8 +99,9 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
     if (d->cout != d->block_n || d->cout_pad != d->cout || !d->ln_g || (d->cout & 63) || !d->out)
       return set_error(-2, "dac_conv_create: LN epilogue needs a single N tile with cout %% 64 == 0");
   } else if (d->epi == DAC_EPI_QKV) {
-    if (d->block_n != 128 || d->cout != 384 || !d->out)
-      return set_error(-2, "dac_conv_create: QKV epilogue needs block_n 128, cout 384");
+    if (d->block_n != 128 || d->cout != 384 || !d->out || !d->out_planar || d->out_scale > 1 ||
+        (reinterpret_cast<uintptr_t>(d->out_planar) & 127))
+      return set_error(-2, "dac_conv_create: QKV epilogue needs block_n 128, cout 384, out (q) and out_planar (k|v)");
   } else if (d->epi == DAC_EPI_GEGLU) {
     if (!d->bias || (d->block_n & 127) || d->cout != d->cout_pad || !d->out)
       return set_error(-2, "dac_conv_create: GEGLU epilogue needs bias and block_n %% 128 == 0");
@@ -160,6 +161,7 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
   k.out_scale = d->out_scale > 0 ? d->out_scale : 1;
   k.OHf = d->OH * k.out_scale; k.OWf = d->OW * k.out_scale;
   memcpy(k.out_oy, d->out_oy, 4); memcpy(k.out_ox, d->out_ox, 4);
+  k.out_planar = static_cast<__nv_bfloat16*>(d->out_planar);
   k.out_nchw = d->out_nchw; k.nchw_c = d->out_nchw_c; k.nchw_h = d->out_nchw_h; k.nchw_w = d->out_nchw_w;
 
   // Weights stay resident in shared memory when the whole tensor fits beside >= 3 activation stages: the
@@ -175,8 +177,9 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
   // staging tile leaves room for >= 3 pipeline stages; otherwise each thread stores its own row directly.
   const int out_cols = d->epi == DAC_EPI_GEGLU ? d->block_n / 2 : d->block_n;
   uint32_t stg_bytes = 0;
+  // (the planar k|v map of the QKV epilogue needs 16-byte row pitches: OW % 8 == 0, else direct stores)
   if (d->out && !nchw && k.out_scale == 1 && out_cols % 64 == 0 && d->cout % 64 == 0 && (d->out_coff % 64) == 0 &&
-      !getenv("DAC_NO_TMA_STORE")) {
+      !(d->epi == DAC_EPI_QKV && (d->OW & 7)) && !getenv("DAC_NO_TMA_STORE")) {
     const uint32_t want = (uint32_t)(out_cols / 64) * kTileM * 128;     // per epilogue group; two groups
     int without = (smem_budget - (int)k.b_res_bytes) / (int)stage_bytes;
     if (without > kMaxStages) without = kMaxStages;
@@ -214,7 +217,7 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
   }
   if (rc == 0 && stg_bytes) {
     PFN_encodeTiled enc = get_encode_fn();
-    const int valid_c = d->epi == DAC_EPI_GEGLU ? d->cout / 2 : d->cout;
+    const int valid_c = d->epi == DAC_EPI_GEGLU ? d->cout / 2 : (d->epi == DAC_EPI_QKV ? 128 : d->cout);
     cuuint64_t dims[4] = {(cuuint64_t)(d->out_coff + valid_c), (cuuint64_t)k.OWf, (cuuint64_t)k.OHf, (cuuint64_t)d->B};
     cuuint64_t strides[3] = {(cuuint64_t)d->out_ld * 2, (cuuint64_t)k.OWf * d->out_ld * 2,
                              (cuuint64_t)k.OHf * k.OWf * d->out_ld * 2};
@@ -224,8 +227,21 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) rc = set_error(-11, "cuTensorMapEncodeTiled(output) failed: CUresult %d", (int)r);
+    pl->mapOut2 = pl->mapOut;
+    if (rc == 0 && d->epi == DAC_EPI_QKV) {
+      // planar k|v tensor [B][256][OH][OW]: box = tile_w x tile_h pixels x 128 channels, un-swizzled, i.e. the
+      // [channel][pixel] staging tile the epilogue wrote
+      cuuint64_t pd[4] = {(cuuint64_t)d->OW, (cuuint64_t)d->OH, 256, (cuuint64_t)d->B};
+      cuuint64_t ps[3] = {(cuuint64_t)d->OW * 2, (cuuint64_t)d->OH * d->OW * 2, (cuuint64_t)256 * d->OH * d->OW * 2};
+      cuuint32_t pb[4] = {(cuuint32_t)d->tile_w, (cuuint32_t)d->tile_h, 128, 1};
+      r = enc(&pl->mapOut2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, d->out_planar, pd, ps, pb, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) rc = set_error(-11, "cuTensorMapEncodeTiled(planar k|v) failed: CUresult %d", (int)r);
+    }
   } else if (rc == 0) {
     pl->mapOut = pl->mapA0;
+    pl->mapOut2 = pl->mapA0;
   }
   if (rc != 0) { delete pl; return rc; }
 
@@ -247,7 +263,7 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
 extern "C" int dac_conv_launch(dac_conv_t pl, dac_stream_t stream) {
   if (!pl) return set_error(-1, "dac_conv_launch: null plan");
   pl->kernel<<<pl->grid, kThreads, pl->smem, static_cast<cudaStream_t>(stream)>>>(pl->mapA0, pl->mapA1, pl->mapW,
-                                                                                  pl->mapOut, pl->kp);
+                                                                                  pl->mapOut, pl->mapOut2, pl->kp);
   return check_launch("conv_igemm_kernel");
 }
 

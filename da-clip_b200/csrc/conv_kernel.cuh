@@ -95,6 +95,7 @@ struct ConvKParams {
   float* out_nchw;
   int nchw_c, nchw_h, nchw_w;
   uint32_t stg_bytes;      // > 0: bf16 output goes through a swizzled shared-memory tile and a TMA store
+  __nv_bfloat16* out_planar;   // QKV: planar k|v output [B][256][OH][OW]
   int stg_count;           // 1 or 2 staging tiles (2: the store of tile i overlaps the epilogue of tile i+1)
 };
 
@@ -307,8 +308,21 @@ __device__ __forceinline__ void epilogue_tile(const ConvKParams& p, const TileCo
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] *= inv;
       }
-      if (stg) chunk_stage_bf16(stg, row, c, v);
-      else if (valid) chunk_store_bf16(p.out + opix * p.out_ld + p.out_coff + ch, v);
+      if (t.nt == 0) {
+        if (stg) chunk_stage_bf16(stg, row, c, v);
+        else if (valid) chunk_store_bf16(p.out + opix * p.out_ld + p.out_coff + ch, v);
+      } else if (stg) {
+        // k / v: transposed staging [channel][pixel] (lanes = consecutive pixels: conflict-free 2-byte stores);
+        // one TMA store writes the 128 pixel-contiguous channel rows into the planar tensor
+        __nv_bfloat16* tp = reinterpret_cast<__nv_bfloat16*>(stg) + c * kTileM + row;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) tp[j * kTileM] = __float2bfloat16(v[j]);
+      } else if (valid) {
+        __nv_bfloat16* dp = p.out_planar + ((static_cast<long long>(n) * 256 + (ch - 128)) * p.OH + y) * p.OW + x;
+        const long long plane = static_cast<long long>(p.OH) * p.OW;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dp[j * plane] = __float2bfloat16(v[j]);
+      }
       continue;
     }
     if (p.bias) chunk_add_f32(p.bias + ch, v);
@@ -344,7 +358,7 @@ template <int EPI, int ACT, bool FILM>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                   const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapOut,
-                  const __grid_constant__ ConvKParams p) {
+                  const __grid_constant__ CUtensorMap mapOut2, const __grid_constant__ ConvKParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024 B alignment is required by the 128B swizzle atoms (TMA write and UMMA read agree on address bits).
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -376,6 +390,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     tma_prefetch_desc(&mapA1);
     tma_prefetch_desc(&mapW);
     tma_prefetch_desc(&mapOut);
+    tma_prefetch_desc(&mapOut2);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
@@ -535,8 +550,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");
         if (gthread == 0) {
           const int cols = (EPI == KE_GEGLU) ? (p.block_n >> 1) : p.block_n;   // output columns of this tile
-          for (int s_ = 0; s_ * 64 < cols; ++s_)
-            tma_store_4d(&mapOut, stg + s_ * (kTileM * 128), p.out_coff + t.nt * cols + s_ * 64, t.x0, t.y0, t.n);
+          if (EPI == KE_QKV && t.nt > 0) {
+            tma_store_4d(&mapOut2, stg, t.x0, t.y0, (t.nt - 1) * 128, t.n);    // planar [x, y, channel, image]
+          } else {
+            for (int s_ = 0; s_ * 64 < cols; ++s_)
+              tma_store_4d(&mapOut, stg + s_ * (kTileM * 128), p.out_coff + t.nt * cols + s_ * 64, t.x0, t.y0, t.n);
+          }
           tma_store_commit();
         }
       }
@@ -557,7 +576,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
 }
 
 typedef void (*ConvKernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
-                             const ConvKParams);
+                             const CUtensorMap, const ConvKParams);
 
 // The epilogue flavours that exist as separate kernels; everything else in the epilogue is a warp-uniform
 // runtime branch on a pointer.

@@ -26,11 +26,12 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// One CTA (4 warps) per (pixel slab, head, image).  Per 64-pixel sub-tile: k and v are scattered transposed
-// ([channel][pixel], bf16) into shared memory; the running column max / rescale / exp / row sums are done by
-// (channel, quarter) threads on 16 contiguous pixels; C[d][e] += sum_p exp(k)[d][p] v[e][p] runs on the warp-level
-// tensor cores (mma.sync m16n8k16 bf16, fp32 accumulate): warp w owns d rows 16*(w/2).. and e cols 16*(w%2)...
-__global__ void __launch_bounds__(128) linattn_context_kernel(const __nv_bfloat16* __restrict__ qkv, int hw,
+// One CTA (4 warps) per (pixel slab, head, image).  k and v arrive PLANAR ([B][256][hw], pixel-contiguous channel
+// rows - written that way by the QKV epilogue), so a (channel, 16-pixel quarter) thread loads its 32 bytes of k and
+// of v straight from global memory: running column max / rescale / exp / row sums on k, then both go to shared
+// memory as [channel][pixel] bf16 tiles - the operand layout of C[d][e] += sum_p exp(k)[d][p] v[e][p] on the
+// warp-level tensor cores (mma.sync m16n8k16 bf16, fp32 accumulate): warp w owns d rows 16*(w/2).., e cols 16*(w%2)..
+__global__ void __launch_bounds__(128) linattn_context_kernel(const __nv_bfloat16* __restrict__ kv, int hw,
                                                               int slab, float* __restrict__ partial) {
   __shared__ __align__(16) __nv_bfloat16 Kt[32 * kLaPitch];
   __shared__ __align__(16) __nv_bfloat16 Vt[32 * kLaPitch];
@@ -40,7 +41,9 @@ __global__ void __launch_bounds__(128) linattn_context_kernel(const __nv_bfloat1
   const int nchunks = gridDim.x;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const int p_begin = chunk * slab, p_end = min(hw, p_begin + slab);
-  const __nv_bfloat16* base = qkv + static_cast<int64_t>(b) * hw * 384;
+  const int d = t >> 2, qtr = t & 3;      // load / softmax mapping: channel row d, 16-pixel quarter
+  const __nv_bfloat16* krow = kv + (static_cast<int64_t>(b) * 256 + h * 32 + d) * hw;
+  const __nv_bfloat16* vrow = kv + (static_cast<int64_t>(b) * 256 + 128 + h * 32 + d) * hw;
   const int d0 = 16 * (warp >> 1), e0 = 16 * (warp & 1);
   float acc[2][4];
 #pragma unroll
@@ -51,72 +54,63 @@ __global__ void __launch_bounds__(128) linattn_context_kernel(const __nv_bfloat1
     m_run[t] = -INFINITY;
     s_run[t] = 0.f;
   }
-  const __nv_bfloat16 neg_inf = __float2bfloat16(-INFINITY);
+  __syncthreads();
 
   for (int p0 = p_begin; p0 < p_end; p0 += kLaP) {
-    __syncthreads();  // previous sub-tile fully consumed (and m_run / s_run initialised)
-    {  // load 64 pixels x (32 k + 32 v) channels; thread -> (pixel, 16-channel half); scatter transposed
-      const int pl = t >> 1, part = t & 1;
-      const int p = p0 + pl;
-      uint4 uk[2], uv[2];
-      if (p < p_end) {
-        const __nv_bfloat16* row = base + static_cast<int64_t>(p) * 384;
-        uk[0] = __ldg(reinterpret_cast<const uint4*>(row + 128 + h * 32 + part * 16));
-        uk[1] = __ldg(reinterpret_cast<const uint4*>(row + 128 + h * 32 + part * 16) + 1);
-        uv[0] = __ldg(reinterpret_cast<const uint4*>(row + 256 + h * 32 + part * 16));
-        uv[1] = __ldg(reinterpret_cast<const uint4*>(row + 256 + h * 32 + part * 16) + 1);
+    const int px = p0 + qtr * 16;
+    float kf[16];
+    uint4 uv[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+    if (px + 16 <= p_end) {
+      const uint4 u0 = __ldg(reinterpret_cast<const uint4*>(krow + px));
+      const uint4 u1 = __ldg(reinterpret_cast<const uint4*>(krow + px) + 1);
+      uv[0] = __ldg(reinterpret_cast<const uint4*>(vrow + px));
+      uv[1] = __ldg(reinterpret_cast<const uint4*>(vrow + px) + 1);
+      const uint32_t w[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float2 f = unpack_bf16(w[j]);
+        kf[2 * j] = f.x;
+        kf[2 * j + 1] = f.y;
       }
-      const __nv_bfloat16* kk = reinterpret_cast<const __nv_bfloat16*>(uk);
-      const __nv_bfloat16* vv = reinterpret_cast<const __nv_bfloat16*>(uv);
+    } else {  // ragged tail: element-wise, masked pixels contribute exp(-inf) = 0 and v = 0
+      __nv_bfloat16* vb = reinterpret_cast<__nv_bfloat16*>(uv);
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        const int c = part * 16 + j;
-        Kt[c * kLaPitch + pl] = (p < p_end) ? kk[j] : neg_inf;           // masked pixel: exp -> 0
-        Vt[c * kLaPitch + pl] = (p < p_end) ? vv[j] : __float2bfloat16(0.f);
+        const bool live = px + j < p_end;
+        kf[j] = live ? __bfloat162float(krow[px + j]) : -INFINITY;
+        vb[j] = live ? vrow[px + j] : __float2bfloat16(0.f);
       }
     }
-    __syncthreads();
-    {  // thread -> (channel d = t/4, 16-pixel quarter): running max, rescale factor, exp in place, row sum
-      const int d = t >> 2, qtr = t & 3;
-      __nv_bfloat16* rowp = &Kt[d * kLaPitch + qtr * 16];
-      float kv[16];
+    float m = kf[0];
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const uint4 u = *reinterpret_cast<const uint4*>(rowp + q * 8);
-        float2 f;
-        f = unpack_bf16(u.x); kv[q * 8 + 0] = f.x; kv[q * 8 + 1] = f.y;
-        f = unpack_bf16(u.y); kv[q * 8 + 2] = f.x; kv[q * 8 + 3] = f.y;
-        f = unpack_bf16(u.z); kv[q * 8 + 4] = f.x; kv[q * 8 + 5] = f.y;
-        f = unpack_bf16(u.w); kv[q * 8 + 6] = f.x; kv[q * 8 + 7] = f.y;
-      }
-      float m = kv[0];
+    for (int j = 1; j < 16; ++j) m = fmaxf(m, kf[j]);
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+    __syncthreads();                       // previous sub-tile's MMAs are done: Kt / Vt / scale may be rewritten
+    const float mo = m_run[d];
+    const float mn = fmaxf(mo, m);         // finite: the first sub-tile of a slab holds at least one live pixel
+    float s = 0.f;
+    uint32_t packed[8];
 #pragma unroll
-      for (int j = 1; j < 16; ++j) m = fmaxf(m, kv[j]);
-      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
-      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
-      const float mo = m_run[d];
-      const float mn = fmaxf(mo, m);
-      // first sub-tile of a slab always holds at least one live pixel, so mn is finite
-      float s = 0.f;
-      uint32_t packed[8];
-#pragma unroll
-      for (int j = 0; j < 16; j += 2) {
-        const float ea = __expf(kv[j] - mn), eb = __expf(kv[j + 1] - mn);
-        packed[j >> 1] = pack_bf16(ea, eb);
-        const float2 r = unpack_bf16(packed[j >> 1]);      // sum exactly what the tensor cores will multiply
-        s += r.x + r.y;
-      }
-      *reinterpret_cast<uint4*>(rowp) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-      *reinterpret_cast<uint4*>(rowp + 8) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      s += __shfl_xor_sync(0xffffffffu, s, 2);
-      __syncwarp();
-      if (qtr == 0) {
-        const float sc = (mo == -INFINITY) ? 0.f : __expf(mo - mn);
-        scale[d] = sc;
-        m_run[d] = mn;
-        s_run[d] = s_run[d] * sc + s;
-      }
+    for (int j = 0; j < 16; j += 2) {
+      packed[j >> 1] = pack_bf16(__expf(kf[j] - mn), __expf(kf[j + 1] - mn));
+      const float2 r = unpack_bf16(packed[j >> 1]);        // sum exactly what the tensor cores will multiply
+      s += r.x + r.y;
+    }
+    __nv_bfloat16* kd = &Kt[d * kLaPitch + qtr * 16];
+    *reinterpret_cast<uint4*>(kd) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    *reinterpret_cast<uint4*>(kd + 8) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+    __nv_bfloat16* vd = &Vt[d * kLaPitch + qtr * 16];
+    *reinterpret_cast<uint4*>(vd) = uv[0];
+    *reinterpret_cast<uint4*>(vd + 8) = uv[1];
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    __syncwarp();
+    if (qtr == 0) {
+      const float sc = (mo == -INFINITY) ? 0.f : __expf(mo - mn);
+      scale[d] = sc;
+      m_run[d] = mn;
+      s_run[d] = s_run[d] * sc + s;
     }
     __syncthreads();
     {  // C[d][e] = C[d][e] * scale[d] + sum_p P[d][p] V[e][p]
@@ -203,13 +197,14 @@ __global__ void __launch_bounds__(256) linattn_fold_kernel(const float* __restri
 
 using namespace dac;
 
-extern "C" int dac_linattn_context(const void* qkv, int32_t B, int32_t hw, int32_t nchunks, float* partial,
+extern "C" int dac_linattn_context(const void* kv, int32_t B, int32_t hw, int32_t nchunks, float* partial,
                                    dac_stream_t stream) {
-  if (!qkv || !partial) return set_error(-1, "dac_linattn_context: null argument");
+  if (!kv || !partial) return set_error(-1, "dac_linattn_context: null argument");
+  if (hw & 7) return set_error(-2, "dac_linattn_context: hw must be a multiple of 8");
   if (nchunks < 1 || nchunks > 128) return set_error(-2, "dac_linattn_context: nchunks must be in [1,128]");
   const int slab = static_cast<int>(ceil_div(ceil_div(hw, nchunks), kLaP) * kLaP);
   linattn_context_kernel<<<dim3(nchunks, 4, B), 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(qkv), hw, slab, partial);
+      static_cast<const __nv_bfloat16*>(kv), hw, slab, partial);
   return check_launch("linattn_context_kernel");
 }
 

@@ -36,6 +36,7 @@ class ConvDesc(C.Structure):
         ("out", C.c_void_p), ("out_ld", C.c_int32), ("out_coff", C.c_int32),
         ("res_f32", C.c_void_p), ("res_f32_ld", C.c_int32),
         ("out_f32", C.c_void_p), ("out_f32_ld", C.c_int32),
+        ("out_planar", C.c_void_p),
         ("out_nchw", C.c_void_p), ("out_nchw_c", C.c_int32), ("out_nchw_h", C.c_int32), ("out_nchw_w", C.c_int32),
     ]
 

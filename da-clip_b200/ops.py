@@ -138,7 +138,8 @@ class ConvPlan:
 
     def __init__(self, src0, c0, pw: PackedWeight, out=None, *, B, H, W, src1=None, c1=0, ld0=None, ld1=None,
                  epi=L.EPI_PLAIN, act=L.ACT_NONE, bias=None, bias_img=None, film=None, film_off=0,
-                 ln_g=None, ln_eps=1e-5, res=None, res2=None, res_f32=None, out_f32=None, out_coff=0, out_nchw=None,
+                 ln_g=None, ln_eps=1e-5, res=None, res2=None, res_f32=None, out_f32=None, out_planar=None, out_coff=0,
+                 out_nchw=None,
                  per_image_w=False, block_n=None, weight_override=None, tile=None, share_taps=True):
         L.require_cuda(src0)
         lib = L.load()
@@ -187,10 +188,12 @@ class ConvPlan:
             d.res_f32, d.res_f32_ld = res_f32.data_ptr(), res_f32.shape[-1]
         if out_f32 is not None:
             d.out_f32, d.out_f32_ld = out_f32.data_ptr(), out_f32.shape[-1]
+        if out_planar is not None:
+            d.out_planar = out_planar.data_ptr()
         if out_nchw is not None:
             d.out_nchw = out_nchw.data_ptr()
             d.out_nchw_c, d.out_nchw_h, d.out_nchw_w = out_nchw.shape[1], out_nchw.shape[2], out_nchw.shape[3]
-        self._keep = (src0, src1, wt, out, bias, bias_img, film, ln_g, res, res2, out_nchw, res_f32, out_f32)
+        self._keep = (src0, src1, wt, out, bias, bias_img, film, ln_g, res, res2, out_nchw, res_f32, out_f32, out_planar)
         self.desc = d
         h = C.c_void_p()
         L.check(lib.dac_conv_create(C.byref(d), C.byref(h)))
@@ -268,8 +271,8 @@ def two_linear(x, w1, w2, b2, y):
                                     L.ptr(y), L.stream_ptr()))
 
 
-def linattn_context(qkv, B, hw, nchunks, partial):
-    L.check(L.load().dac_linattn_context(L.ptr(qkv), B, hw, nchunks, L.ptr(partial), L.stream_ptr()))
+def linattn_context(kv, B, hw, nchunks, partial):
+    L.check(L.load().dac_linattn_context(L.ptr(kv), B, hw, nchunks, L.ptr(partial), L.stream_ptr()))
 
 
 def linattn_fold(partial, B, hw, nchunks, w_out, C_, c_pad, weff):

@@ -390,16 +390,17 @@ class UNetEngine:
         self.add(prefix + "prenorm", lambda: ops.layernorm_rows(x, xn, B * hw, C, a["pre_g"], None, 1e-5))
         out = self.buf(B, h, w, C)
         if not a["transformer"]:
-            qkv = self.buf(B, h, w, 384)
-            self.conv(prefix + "to_qkv", xn, C, a["qkv"], qkv, h, w, epi=L.EPI_QKV, block_n=128)
+            q = self.buf(B, h, w, 128)                  # softmaxed queries, NHWC (A operand of the to_out GEMM)
+            kv = self.buf(B, 256, h, w)                 # k | v, planar: pixel-contiguous rows for the context pass
+            self.conv(prefix + "to_qkv", xn, C, a["qkv"], q, h, w, epi=L.EPI_QKV, block_n=128, out_planar=kv)
             nchunks = max(1, min(128, (148 * 8) // (B * 4), hw // 256))
             partial = self.buf(B, 4, nchunks, 32 * 34, dtype=torch.float32)
             c_pad = a["out"].w.shape[-2]
             weff = self.buf(B, c_pad, 128)
-            self.add(prefix + "context", lambda: ops.linattn_context(qkv, B, hw, nchunks, partial))
+            self.add(prefix + "context", lambda: ops.linattn_context(kv, B, hw, nchunks, partial))
             self.add(prefix + "fold", lambda: ops.linattn_fold(partial, B, hw, nchunks, a["w_out"], C, c_pad, weff))
             self.flops += 2.0 * B * 4 * 32 * 32 * hw      # context einsum (the apply einsum is folded into to_out)
-            self.conv(prefix + "to_out", qkv, 128, a["out"], out, h, w, ld0=384, epi=L.EPI_LN, bias=a["b_out"],
+            self.conv(prefix + "to_out", q, 128, a["out"], out, h, w, epi=L.EPI_LN, bias=a["b_out"],
                       ln_g=a["g_out"], res=x, per_image_w=True, weight_override=weff)
             return out
         heads = a["heads"]

@@ -64,7 +64,9 @@ enum {
   DAC_EPI_PLAIN = 0,  /* out = act(film(acc + bias)) + res                                   MU:115-153 */
   DAC_EPI_GEGLU = 1,  /* tile cols [0,bn/2) value, [bn/2,bn) gate: out = v * gelu(g)        ATT:37-44 */
   DAC_EPI_LN = 2,     /* out = LN_c(acc + bias) * g + res   (single N tile)                 MU:77-86,166-168 */
-  DAC_EPI_QKV = 3     /* N-tile 0: per-32-col softmax * 32^-0.5 (q); other tiles raw (k,v)   MU:170-177 */
+  DAC_EPI_QKV = 3     /* N-tile 0: per-32-col softmax * 32^-0.5 (q) -> out NHWC [.,128]; N-tiles 1,2: raw k, v
+                         written PLANAR to out_planar [B][256][H][W] (pixel-contiguous rows, the layout the
+                         context reduction consumes without a transpose)                     MU:170-177 */
 };
 enum { DAC_ACT_NONE = 0, DAC_ACT_SILU = 1, DAC_ACT_GELU = 2 };
 
@@ -102,6 +104,7 @@ typedef struct dac_conv_desc {
   void* out; int32_t out_ld, out_coff;            /* NHWC bf16 [B, OH*out_scale, OW*out_scale, out_ld] */
   const float* res_f32; int32_t res_f32_ld;       /* fp32 residual stream (ViT blocks keep x in fp32), PLAIN only */
   float* out_f32; int32_t out_f32_ld;             /* fp32 copy of the output (may be given together with out) */
+  void* out_planar;                               /* DAC_EPI_QKV only: bf16 [B][256][OH][OW] for k | v */
   float* out_nchw; int32_t out_nchw_c, out_nchw_h, out_nchw_w; /* alt. fp32 NCHW output (final_conv), cropped */
 } dac_conv_desc;
 
@@ -149,11 +152,11 @@ int dac_two_linear(const float* x, int32_t B, int32_t in, const float* w1, int32
                    const float* b2, int32_t out, float* y, dac_stream_t stream);
 
 /* ------------------------------------------------------------------ LinearAttention (MU:157-185)
- * qkv: [B, hw, 384] bf16 (q already soft-maxed by the QKV epilogue).  Pass 1 reduces, per (image, head),
+ * kv: planar bf16 [B][256][hw] (channels 0..127 k, 128..255 v) from the QKV epilogue.  Pass 1 reduces, per (image, head),
  * the k-softmax over all pixels and ctx[d,e] = sum_n softmax_n(k)[d,n] v[e,n] / hw into partials; pass 2
  * merges them and folds ctx into the to_out weight: weff[b][c][h*32+d] = sum_e Wout[c][h*32+e] ctx[b,h,d,e]
  * (bf16, the per-image weight of the following 1x1 conv plan). */
-int dac_linattn_context(const void* qkv, int32_t B, int32_t hw, int32_t nchunks, float* partial /*[B,4,nchunks,32*34]*/,
+int dac_linattn_context(const void* kv, int32_t B, int32_t hw, int32_t nchunks, float* partial /*[B,4,nchunks,32*34]*/,
                         dac_stream_t stream);
 int dac_linattn_fold(const float* partial, int32_t B, int32_t hw, int32_t nchunks, const float* w_out /*[C,128] fp32*/,
                      int32_t C, int32_t c_pad, void* weff /*[B][c_pad][128] bf16*/, dac_stream_t stream);

@@ -257,25 +257,29 @@ def test_linear_attention_block(ops, gen, B, H, W, C):
     sdr["to_qkv.weight"] = bf(sd["to_qkv.weight"]).float()
     ref = O.linear_attention(sdr, "", nchw(xh)) + nchw(xh)
 
-    qkv = torch.zeros(B, H, W, 384, device="cuda", dtype=torch.bfloat16)
-    p1 = ops.ConvPlan(xh, C, ops.pack_linear(sd["to_qkv.weight"]), qkv, B=B, H=H, W=W, epi=L.EPI_QKV, block_n=128)
+    q = torch.zeros(B, H, W, 128, device="cuda", dtype=torch.bfloat16)
+    kv = torch.full((B, 256, H, W), float("nan"), device="cuda", dtype=torch.bfloat16)
+    p1 = ops.ConvPlan(xh, C, ops.pack_linear(sd["to_qkv.weight"]), q, B=B, H=H, W=W, epi=L.EPI_QKV, block_n=128,
+                      out_planar=kv)
     nchunks = 8
     partial = torch.zeros(B, 4, nchunks, 32 * 34, device="cuda")
     c_pad = ops.choose_block_n(C)[1]
     weff = torch.zeros(B, c_pad, 128, device="cuda", dtype=torch.bfloat16)
     out = torch.zeros(B, H, W, C, device="cuda", dtype=torch.bfloat16)
     pw_out = ops.pack_linear(sd["to_out.0.weight"])
-    p2 = ops.ConvPlan(qkv, 128, pw_out, out, B=B, H=H, W=W, epi=L.EPI_LN, bias=sd["to_out.0.bias"],
+    p2 = ops.ConvPlan(q, 128, pw_out, out, B=B, H=H, W=W, epi=L.EPI_LN, bias=sd["to_out.0.bias"],
                       ln_g=sd["to_out.1.g"].reshape(-1).contiguous(), res=xh, per_image_w=True, weight_override=weff)
     p1.run()
-    ops.linattn_context(qkv, B, hw, nchunks, partial)
+    ops.linattn_context(kv, B, hw, nchunks, partial)
     ops.linattn_fold(partial, B, hw, nchunks, sd["to_out.0.weight"].reshape(C, 128).contiguous(), C, c_pad, weff)
     p2.run()
     torch.cuda.synchronize()
     # q check (softmax over head channels * scale)
     q_ref = F.conv2d(nchw(xh), sdr["to_qkv.weight"])[:, :128].reshape(B, 4, 32, hw).softmax(2) * 32 ** -0.5
-    q_got = qkv[..., :128].float().reshape(B, hw, 4, 32).permute(0, 2, 3, 1)
+    q_got = q.float().reshape(B, hw, 4, 32).permute(0, 2, 3, 1)
     assert_close_bf16(q_got, q_ref, "q softmax epilogue")
+    kv_ref = F.conv2d(nchw(xh), sdr["to_qkv.weight"])[:, 128:]
+    assert_close_bf16(kv, kv_ref, "planar k|v output")
     assert_close_bf16(nchw(out), ref, f"linear attention {H}x{W} C={C}", rel=2 ** -5, abs_=2e-2)
 
 
