@@ -38,7 +38,7 @@ static PFN_encodeTiled get_encode_fn() {
 }  // namespace dac
 
 struct dac_conv_plan {
-  CUtensorMap mapA0, mapA1, mapW, mapOut, mapOut2;
+  CUtensorMap mapA0, mapA1, mapW, mapOut, mapOut2, mapR0, mapR1, mapWR;
   dac::ConvKParams kp;
   dac::ConvKernelFn kernel;
   int grid;
@@ -116,6 +116,15 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
   if ((reinterpret_cast<uintptr_t>(d->bias) | reinterpret_cast<uintptr_t>(d->bias_img) |
        reinterpret_cast<uintptr_t>(d->film) | reinterpret_cast<uintptr_t>(d->ln_g)) & 15)
     return set_error(-2, "dac_conv_create: parameter vectors must be 16-byte aligned");
+  const bool fused_res = d->rsrc0 != nullptr;
+  if (fused_res) {
+    if (d->epi != DAC_EPI_PLAIN || nchw || d->cout_pad != d->block_n || 2 * d->block_n > 256 || !d->rweight ||
+        d->rc0 <= 0 || d->rc0 % kChunkK || d->rc1 % kChunkK || (d->rld0 & 7) || (d->rsrc1 && (d->rld1 & 7)) ||
+        d->stride != 1 || d->ngroups != 1 || d->per_image_w ||
+        ((reinterpret_cast<uintptr_t>(d->rsrc0) | reinterpret_cast<uintptr_t>(d->rsrc1) |
+          reinterpret_cast<uintptr_t>(d->rweight)) & 15))
+      return set_error(-2, "dac_conv_create: fused skip conv needs PLAIN epilogue, one N tile <= 128, stride 1");
+  }
   ConvKernelFn kernel = pick_conv_kernel(d->epi, d->act, d->film != nullptr, nchw);
   if (!kernel) return set_error(-2, "dac_conv_create: unsupported activation / FiLM combination (%d, %d)", d->act,
                                 d->film != nullptr);
@@ -146,6 +155,9 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
   memcpy(k.col_dx, d->col_dx, sizeof(k.col_dx));
   memcpy(k.col_dy0, d->col_dy0, sizeof(k.col_dy0));
   memcpy(k.col_tap, d->col_tap, sizeof(k.col_tap));
+  k.r_chunks0 = fused_res ? d->rc0 / kChunkK : 0;
+  k.r_chunks1 = fused_res ? d->rc1 / kChunkK : 0;
+  k.r_a_bytes = (uint32_t)d->tile_h * d->tile_w * kChunkK * 2;
   k.a_bytes = (uint32_t)a_rows * d->tile_w * kChunkK * 2;
   k.row_shift = (uint32_t)d->tile_w * kChunkK * 2;
   k.cout = d->cout;
@@ -172,7 +184,8 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
   const bool resident = k.n_tiles == 1 && d->ngroups == 1 && !d->per_image_w && res_bytes <= 160 * 1024 &&
                         (smem_budget - res_bytes) / (long long)k.a_bytes >= 3;
   k.b_res_bytes = resident ? (uint32_t)res_bytes : 0u;
-  const uint32_t stage_bytes = k.a_bytes + (resident ? 0u : (uint32_t)d->ndy * k.b_bytes);
+  uint32_t stage_bytes = k.a_bytes + (resident ? 0u : (uint32_t)d->ndy * k.b_bytes);
+  if (fused_res && stage_bytes < k.r_a_bytes + k.b_bytes) stage_bytes = k.r_a_bytes + k.b_bytes;
   // bf16 NHWC output through a swizzled staging tile + TMA store (coalesced, clipped by the tensor map) whenever the
   // staging tile leaves room for >= 3 pipeline stages; otherwise each thread stores its own row directly.
   const int out_cols = d->epi == DAC_EPI_GEGLU ? d->block_n / 2 : d->block_n;
@@ -243,6 +256,24 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
     pl->mapOut = pl->mapA0;
     pl->mapOut2 = pl->mapA0;
   }
+  pl->mapR0 = pl->mapA0; pl->mapR1 = pl->mapA0; pl->mapWR = pl->mapW;
+  if (rc == 0 && fused_res) {
+    rc = encode_act_map(&pl->mapR0, d->rsrc0, d->rc0, d->rld0, d->W, d->H, d->B, d->tile_w, d->tile_h, 1);
+    if (rc == 0 && d->rc1 > 0)
+      rc = encode_act_map(&pl->mapR1, d->rsrc1, d->rc1, d->rld1, d->W, d->H, d->B, d->tile_w, d->tile_h, 1);
+    if (rc == 0) {
+      PFN_encodeTiled enc = get_encode_fn();
+      const int rct = d->rc0 + d->rc1;
+      cuuint64_t dims[3] = {(cuuint64_t)rct, (cuuint64_t)d->cout_pad, 1};
+      cuuint64_t strides[2] = {(cuuint64_t)rct * 2, (cuuint64_t)d->cout_pad * rct * 2};
+      cuuint32_t box[3] = {(cuuint32_t)kChunkK, (cuuint32_t)d->block_n, 1};
+      cuuint32_t estr[3] = {1, 1, 1};
+      CUresult r = enc(&pl->mapWR, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(d->rweight), dims, strides,
+                       box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) rc = set_error(-11, "cuTensorMapEncodeTiled(skip weight) failed: CUresult %d", (int)r);
+    }
+  }
   if (rc != 0) { delete pl; return rc; }
 
   int dev = 0, sms = 0;
@@ -263,7 +294,8 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
 extern "C" int dac_conv_launch(dac_conv_t pl, dac_stream_t stream) {
   if (!pl) return set_error(-1, "dac_conv_launch: null plan");
   pl->kernel<<<pl->grid, kThreads, pl->smem, static_cast<cudaStream_t>(stream)>>>(pl->mapA0, pl->mapA1, pl->mapW,
-                                                                                  pl->mapOut, pl->mapOut2, pl->kp);
+                                                                                  pl->mapOut, pl->mapOut2, pl->mapR0,
+                                                                                  pl->mapR1, pl->mapWR, pl->kp);
   return check_launch("conv_igemm_kernel");
 }
 

@@ -68,6 +68,8 @@ struct ConvKParams {
   uint32_t a_bytes;        // one activation load: (tile_h + ndy - 1) * tile_w rows x 128 B
   uint32_t row_shift;      // tile_w * 128 B: descriptor offset between vertically adjacent taps
   uint32_t b_res_bytes;    // > 0: the whole weight tensor stays resident in shared memory
+  int r_chunks0, r_chunks1;   // fused 1x1 skip conv: K chunks of its two sources (0, 0 = none)
+  uint32_t r_a_bytes;         // its activation tile: tile_h * tile_w rows x 128 B
   int ndy, ncols;
   int8_t col_dx[4][16];
   int8_t col_dy0[4][16];
@@ -343,6 +345,12 @@ __device__ __forceinline__ void epilogue_tile(const ConvKParams& p, const TileCo
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = apply_act<ACT>(v[j]);
     }
+    if (p.r_chunks0) {   // fused res_conv: its product sits in the next block_n TMEM columns
+      float r2[32];
+      chunk_from_tmem(tmem_acc + p.block_n + c, r2);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] += r2[j];
+    }
     if (valid) {
       if (p.res_f32) chunk_add_f32(p.res_f32 + opix * p.res_f32_ld + ch, v);
       if (p.res) chunk_add_bf16(p.res + opix * p.res_ld + ch, v);
@@ -358,7 +366,9 @@ template <int EPI, int ACT, bool FILM>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                   const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapOut,
-                  const __grid_constant__ CUtensorMap mapOut2, const __grid_constant__ ConvKParams p) {
+                  const __grid_constant__ CUtensorMap mapOut2, const __grid_constant__ CUtensorMap mapR0,
+                  const __grid_constant__ CUtensorMap mapR1, const __grid_constant__ CUtensorMap mapWR,
+                  const __grid_constant__ ConvKParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024 B alignment is required by the 128B swizzle atoms (TMA write and UMMA read agree on address bits).
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -366,7 +376,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   const bool b_resident = p.b_res_bytes != 0;
   uint8_t* b_res = smem;
   uint8_t* ring = smem + p.b_res_bytes;
-  const uint32_t stage_bytes = p.a_bytes + (b_resident ? 0u : static_cast<uint32_t>(p.ndy) * p.b_bytes);
+  const int r_chunks = p.r_chunks0 + p.r_chunks1;
+  const uint32_t main_tx = p.a_bytes + (b_resident ? 0u : static_cast<uint32_t>(p.ndy) * p.b_bytes);  // bytes per K step
+  uint32_t stage_bytes = main_tx;
+  if (r_chunks && stage_bytes < p.r_a_bytes + p.b_bytes) stage_bytes = p.r_a_bytes + p.b_bytes;
   uint8_t* stg_base = p.stg_bytes ? ring + static_cast<size_t>(p.stages) * stage_bytes : nullptr;
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + static_cast<size_t>(p.stages) * stage_bytes +
                                                static_cast<size_t>(p.stg_bytes) * p.stg_count);
@@ -391,6 +404,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     tma_prefetch_desc(&mapW);
     tma_prefetch_desc(&mapOut);
     tma_prefetch_desc(&mapOut2);
+    if (p.r_chunks0) {
+      tma_prefetch_desc(&mapR0);
+      tma_prefetch_desc(&mapR1);
+      tma_prefetch_desc(&mapWR);
+    }
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
@@ -439,7 +457,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           for (int j = 0; j < p.ncols; ++j) {
             mbar_wait(&empty[stage], phase ^ 1);
             uint8_t* sa = ring + static_cast<size_t>(stage) * stage_bytes;
-            mbar_arrive_expect_tx(&full[stage], stage_bytes);
+            mbar_arrive_expect_tx(&full[stage], main_tx);
             tma_load_4d(sa, mapA, &full[stage], ccoord, xin + p.col_dx[t.g][j], yin + p.col_dy0[t.g][j], t.n);
             if (!b_resident) {
               for (int i = 0; i < p.ndy; ++i)
@@ -450,6 +468,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
               stage = 0;
               phase ^= 1;
             }
+          }
+        }
+        // fused 1x1 skip conv: one un-shifted tile of each 64-channel chunk of its sources + the weight tile
+        for (int rk = 0; rk < r_chunks; ++rk) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sa = ring + static_cast<size_t>(stage) * stage_bytes;
+          mbar_arrive_expect_tx(&full[stage], p.r_a_bytes + p.b_bytes);
+          if (rk < p.r_chunks0) tma_load_4d(sa, &mapR0, &full[stage], rk * kChunkK, xin, yin, t.n);
+          else tma_load_4d(sa, &mapR1, &full[stage], (rk - p.r_chunks0) * kChunkK, xin, yin, t.n);
+          tma_load_3d(sa + p.r_a_bytes, &mapWR, &full[stage], rk * kChunkK, 0, 0);
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
           }
         }
       }
@@ -497,6 +528,22 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
               stage = 0;
               phase ^= 1;
             }
+          }
+        }
+        for (int rk = 0; rk < r_chunks; ++rk) {   // W_r . rsrc into TMEM columns [block_n, 2 block_n)
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a0 = ring_lo + stage * stage_lo;
+          const uint64_t adesc = desc_fixed | a0;
+          const uint64_t bdesc = desc_fixed | (a0 + (p.r_a_bytes >> 4));
+          umma_bf16(d_tmem + p.block_n, adesc, bdesc, idesc, rk ? 1u : 0u);
+          umma_bf16(d_tmem + p.block_n, adesc + 2, bdesc + 2, idesc, 1u);
+          umma_bf16(d_tmem + p.block_n, adesc + 4, bdesc + 4, idesc, 1u);
+          umma_bf16(d_tmem + p.block_n, adesc + 6, bdesc + 6, idesc, 1u);
+          umma_commit(&empty[stage]);
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
           }
         }
         umma_commit(&tmem_full[acc]);
@@ -576,7 +623,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
 }
 
 typedef void (*ConvKernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
-                             const CUtensorMap, const ConvKParams);
+                             const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
+                             const ConvKParams);
 
 // The epilogue flavours that exist as separate kernels; everything else in the epilogue is a warp-uniform
 // runtime branch on a pointer.

@@ -26,7 +26,11 @@ class ConvDesc(C.Structure):
         ("col_dx", (C.c_int8 * 16) * 4), ("col_dy0", (C.c_int8 * 16) * 4), ("col_tap", (C.c_int8 * 16) * 4),
         ("out_scale", C.c_int32), ("out_oy", C.c_int8 * 4), ("out_ox", C.c_int8 * 4),
         ("weight", C.c_void_p), ("cout", C.c_int32), ("cout_pad", C.c_int32), ("per_image_w", C.c_int32),
-        ("block_n", C.c_int32), ("tile_h", C.c_int32), ("tile_w", C.c_int32),
+        ("block_n", C.c_int32),
+        ("rsrc0", C.c_void_p), ("rc0", C.c_int32), ("rld0", C.c_int32),
+        ("rsrc1", C.c_void_p), ("rc1", C.c_int32), ("rld1", C.c_int32),
+        ("rweight", C.c_void_p),
+        ("tile_h", C.c_int32), ("tile_w", C.c_int32),
         ("epi", C.c_int32), ("act", C.c_int32),
         ("bias", C.c_void_p), ("bias_img", C.c_void_p),
         ("film", C.c_void_p), ("film_ld", C.c_int32), ("film_off", C.c_int32),

@@ -140,7 +140,8 @@ class ConvPlan:
                  epi=L.EPI_PLAIN, act=L.ACT_NONE, bias=None, bias_img=None, film=None, film_off=0,
                  ln_g=None, ln_eps=1e-5, res=None, res2=None, res_f32=None, out_f32=None, out_planar=None, out_coff=0,
                  out_nchw=None,
-                 per_image_w=False, block_n=None, weight_override=None, tile=None, share_taps=True):
+                 per_image_w=False, block_n=None, weight_override=None, tile=None, share_taps=True,
+                 rsrc0=None, rc0=0, rsrc1=None, rc1=0, rweight=None):
         L.require_cuda(src0)
         lib = L.load()
         d = L.ConvDesc()
@@ -171,6 +172,11 @@ class ConvPlan:
             d.out_oy[g], d.out_ox[g] = oy, ox
         d.weight, d.cout, d.cout_pad, d.per_image_w = wt.data_ptr(), pw.cout, cout_pad, int(per_image_w)
         d.block_n, d.tile_h, d.tile_w = block_n, th, tw
+        if rsrc0 is not None:        # fused 1x1 skip conv (rweight: PackedWeight of the [cout, rc0+rc1] matrix)
+            d.rsrc0, d.rc0, d.rld0 = rsrc0.data_ptr(), rc0, rsrc0.shape[-1]
+            if rsrc1 is not None:
+                d.rsrc1, d.rc1, d.rld1 = rsrc1.data_ptr(), rc1, rsrc1.shape[-1]
+            d.rweight = rweight.w.data_ptr()
         d.epi, d.act = epi, act
         d.bias = bias.data_ptr() if bias is not None else None
         d.bias_img = bias_img.data_ptr() if bias_img is not None else None
@@ -199,7 +205,9 @@ class ConvPlan:
         L.check(lib.dac_conv_create(C.byref(d), C.byref(h)))
         self.handle = h
         self._lib = lib
-        self.flops = 2.0 * B * OH * OW * pw.ngroups * len(pw.taps[0]) * (c0 + c1) * pw.cout
+        self._keep += (rsrc0, rsrc1, rweight)
+        self.flops = 2.0 * B * OH * OW * pw.ngroups * len(pw.taps[0]) * (c0 + c1) * pw.cout \
+            + 2.0 * B * OH * OW * (rc0 + rc1) * pw.cout * (rsrc0 is not None)
 
     def run(self):
         L.check(self._lib.dac_conv_launch(self.handle, L.stream_ptr()))

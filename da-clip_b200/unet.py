@@ -373,13 +373,19 @@ class UNetEngine:
         h1 = self.buf(B, h, w, cout)
         self.conv(prefix + "block1", x, xc, rb["w1"], h1, h, w, src1=skip, c1=sc, act=L.ACT_SILU,
                   film=self.film, film_off=self.pk.film_off[prefix])
+        out = self.buf(B, h, w, cout)
+        if rb["wr"] is not None and cout <= 128:
+            # res_conv fused into block2: a second TMEM accumulator fed by extra K steps over (x | skip); neither the
+            # 1x1 conv launch nor its output tensor exists
+            self.conv(prefix + "block2", h1, cout, rb["w2"], out, h, w, act=L.ACT_SILU,
+                      rsrc0=x, rc0=xc, rsrc1=skip, rc1=sc, rweight=rb["wr"])
+            return out
         if rb["wr"] is not None:
             r = self.buf(B, h, w, cout)
             self.conv(prefix + "res_conv", x, xc, rb["wr"], r, h, w, src1=skip, c1=sc)
         else:
             assert skip is None
             r = x
-        out = self.buf(B, h, w, cout)
         self.conv(prefix + "block2", h1, cout, rb["w2"], out, h, w, act=L.ACT_SILU, res=r)
         return out
 

@@ -92,6 +92,12 @@ typedef struct dac_conv_desc {
   /* weights: bf16 [Z][cout_pad][c0+c1], Z = ngroups*ntaps (* B if per_image_w); cout_pad multiple of block_n */
   const void* weight; int32_t cout; int32_t cout_pad; int32_t per_image_w;
   int32_t block_n;              /* UMMA N: 16..256, multiple of 16 */
+  /* Optional fused 1x1 skip convolution (ResBlock.res_conv, MU:141,153): out = act(conv(src)) + W_r . rsrc, the
+   * second product accumulated in its own TMEM columns by extra K steps over rsrc0|rsrc1 (virtual concat).
+   * rweight: bf16 [cout][rc0+rc1].  Needs a single N tile with 2*block_n <= 256 and the PLAIN epilogue. */
+  const void* rsrc0; int32_t rc0; int32_t rld0;
+  const void* rsrc1; int32_t rc1; int32_t rld1;
+  const void* rweight;
   int32_t tile_h, tile_w;       /* tile_h*tile_w == 128 */
   /* epilogue */
   int32_t epi, act;

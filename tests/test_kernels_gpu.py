@@ -124,6 +124,25 @@ def test_conv3x3_concat_residual(ops, gen):
     assert_close_bf16(nchw(out), ref, "conv3x3 concat+res")
 
 
+@pytest.mark.parametrize("B,H,W,c,rc0,rc1", [(2, 32, 32, 64, 64, 64), (1, 40, 24, 128, 128, 64), (1, 16, 16, 64, 64, 0)])
+def test_conv3x3_fused_skip_conv(ops, gen, B, H, W, c, rc0, rc1):
+    """ResBlock tail: out = SiLU(conv3x3(h)) + res_conv(cat[x, skip]) with the 1x1 product in its own TMEM columns."""
+    from daclip_b200 import lib as L
+    hh = nhwc(rnd(gen, B, c, H, W))
+    x = nhwc(rnd(gen, B, rc0, H, W))
+    sk = nhwc(rnd(gen, B, rc1, H, W)) if rc1 else None
+    w = rnd(gen, c, c, 3, 3, scale=(9 * c) ** -0.5)
+    wr = rnd(gen, c, rc0 + rc1, 1, 1, scale=(rc0 + rc1) ** -0.5)
+    out = torch.full((B, H, W, c), float("nan"), device="cuda", dtype=torch.bfloat16)
+    plan = ops.ConvPlan(hh, c, ops.pack_conv(w), out, B=B, H=H, W=W, act=L.ACT_SILU,
+                        rsrc0=x, rc0=rc0, rsrc1=sk, rc1=rc1, rweight=ops.pack_linear(wr))
+    plan.run()
+    torch.cuda.synchronize()
+    xin = nchw(x) if sk is None else torch.cat([nchw(x), nchw(sk)], 1)
+    ref = F.silu(F.conv2d(nchw(hh), bf(w).float(), padding=1)) + F.conv2d(xin, bf(wr).float())
+    assert_close_bf16(nchw(out), ref, f"fused skip conv {plan.info()}")
+
+
 def test_conv_channel_slices(ops, gen):
     """Source read as a channel sub-range of a wider buffer; output written into a channel sub-range."""
     B, H, W = 2, 8, 16
