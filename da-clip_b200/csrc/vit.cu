@@ -68,34 +68,49 @@ __global__ void __launch_bounds__(256) vit_embed_kernel(const __nv_bfloat16* __r
     out[(static_cast<int64_t>(b) * L + tok) * w + i] = (row[i] - mean) * rstd * ln_w[i] + ln_b[i];
 }
 
-// one CTA per image: ln_post(x[b,0,:]) @ proj
-__global__ void __launch_bounds__(256) vit_pool_kernel(const float* __restrict__ x, int L, int w,
+// kPoolImgs images per CTA: ln_post(x[b,0,:]) for each, then @ proj with every projection row read once per CTA
+constexpr int kPoolImgs = 8;
+__global__ void __launch_bounds__(256) vit_pool_kernel(const float* __restrict__ x, int B, int L, int w,
                                                        const float* __restrict__ ln_w, const float* __restrict__ ln_b,
                                                        float eps, const float* __restrict__ proj, int e,
                                                        float* __restrict__ out) {
-  extern __shared__ float row[];
-  __shared__ float red[8];
-  const int b = blockIdx.x;
-  const float* src = x + static_cast<int64_t>(b) * L * w;
-  float s = 0.f;
-  for (int i = threadIdx.x; i < w; i += blockDim.x) {
-    row[i] = src[i];
-    s += row[i];
+  extern __shared__ float rows[];   // [kPoolImgs][w]
+  const int b0 = blockIdx.x * kPoolImgs;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp < kPoolImgs && b0 + warp < B) {   // one warp normalises one class token
+    const float* src = x + static_cast<int64_t>(b0 + warp) * L * w;
+    float* row = rows + warp * w;
+    float s = 0.f;
+    for (int i = lane; i < w; i += 32) {
+      row[i] = src[i];
+      s += row[i];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / w;
+    float ss = 0.f;
+    for (int i = lane; i < w; i += 32) {
+      const float d = row[i] - mean;
+      ss += d * d;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float rstd = rsqrtf(ss / w + eps);
+    for (int i = lane; i < w; i += 32) row[i] = (row[i] - mean) * rstd * ln_w[i] + ln_b[i];
   }
-  const float mean = block_sum(s, red) / w;
-  float ss = 0.f;
-  for (int i = threadIdx.x; i < w; i += blockDim.x) {
-    const float d = row[i] - mean;
-    ss += d * d;
-  }
-  const float rstd = rsqrtf(block_sum(ss, red) / w + eps);
-  __syncthreads();
-  for (int i = threadIdx.x; i < w; i += blockDim.x) row[i] = (row[i] - mean) * rstd * ln_w[i] + ln_b[i];
   __syncthreads();
   for (int j = threadIdx.x; j < e; j += blockDim.x) {
-    float a = 0.f;
-    for (int i = 0; i < w; ++i) a += row[i] * __ldg(proj + static_cast<int64_t>(i) * e + j);  // coalesced over j
-    out[static_cast<int64_t>(b) * e + j] = a;
+    float a[kPoolImgs];
+#pragma unroll
+    for (int m = 0; m < kPoolImgs; ++m) a[m] = 0.f;
+    for (int i = 0; i < w; ++i) {
+      const float pj = __ldg(proj + static_cast<int64_t>(i) * e + j);   // coalesced over j
+#pragma unroll
+      for (int m = 0; m < kPoolImgs; ++m) a[m] = fmaf(rows[m * w + i], pj, a[m]);
+    }
+#pragma unroll
+    for (int m = 0; m < kPoolImgs; ++m)
+      if (b0 + m < B) out[static_cast<int64_t>(b0 + m) * e + j] = a[m];
   }
 }
 
@@ -163,8 +178,9 @@ extern "C" int dac_vit_embed(const void* patch_emb, const float* cls, const floa
 extern "C" int dac_vit_pool(const void* x, int32_t B, int32_t L, int32_t w, const float* ln_w, const float* ln_b,
                             float eps, const float* proj, int32_t e, float* out, dac_stream_t stream) {
   if (!x || !ln_w || !ln_b || !proj || !out) return set_error(-1, "dac_vit_pool: null argument");
-  vit_pool_kernel<<<B, 256, w * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const float*>(x), L, w, ln_w, ln_b, eps, proj, e, out);
+  vit_pool_kernel<<<(B + kPoolImgs - 1) / kPoolImgs, 256, kPoolImgs * w * sizeof(float),
+                    static_cast<cudaStream_t>(stream)>>>(static_cast<const float*>(x), B, L, w, ln_w, ln_b, eps, proj, e,
+                                                         out);
   return check_launch("vit_pool_kernel");
 }
 
