@@ -116,6 +116,12 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
   if ((reinterpret_cast<uintptr_t>(d->bias) | reinterpret_cast<uintptr_t>(d->bias_img) |
        reinterpret_cast<uintptr_t>(d->film) | reinterpret_cast<uintptr_t>(d->ln_g)) & 15)
     return set_error(-2, "dac_conv_create: parameter vectors must be 16-byte aligned");
+  if (d->stats_out && (d->epi != DAC_EPI_PLAIN || nchw || d->cout_pad != d->block_n || d->out_scale > 1 ||
+                       (reinterpret_cast<uintptr_t>(d->stats_out) & 7)))
+    return set_error(-2, "dac_conv_create: stats_out needs the PLAIN epilogue and a single N tile");
+  if ((d->ln_stats != nullptr) != (d->ln_colsum != nullptr) || (d->ln_stats && d->epi != DAC_EPI_QKV) ||
+      ((reinterpret_cast<uintptr_t>(d->ln_stats) & 7) | (reinterpret_cast<uintptr_t>(d->ln_colsum) & 15)))
+    return set_error(-2, "dac_conv_create: ln_stats / ln_colsum go together, QKV epilogue only");
   const bool fused_res = d->rsrc0 != nullptr;
   if (fused_res) {
     if (d->epi != DAC_EPI_PLAIN || nchw || d->cout_pad != d->block_n || 2 * d->block_n > 256 || !d->rweight ||
@@ -174,6 +180,8 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
   k.OHf = d->OH * k.out_scale; k.OWf = d->OW * k.out_scale;
   memcpy(k.out_oy, d->out_oy, 4); memcpy(k.out_ox, d->out_ox, 4);
   k.out_planar = static_cast<__nv_bfloat16*>(d->out_planar);
+  k.stats_out = d->stats_out; k.stats_eps = d->stats_eps;
+  k.ln_stats = d->ln_stats; k.ln_colsum = d->ln_colsum;
   k.out_nchw = d->out_nchw; k.nchw_c = d->out_nchw_c; k.nchw_h = d->out_nchw_h; k.nchw_w = d->out_nchw_w;
 
   // Weights stay resident in shared memory when the whole tensor fits beside >= 3 activation stages: the

@@ -98,6 +98,10 @@ struct ConvKParams {
   int nchw_c, nchw_h, nchw_w;
   uint32_t stg_bytes;      // > 0: bf16 output goes through a swizzled shared-memory tile and a TMA store
   __nv_bfloat16* out_planar;   // QKV: planar k|v output [B][256][OH][OW]
+  float* stats_out;            // PLAIN: per-pixel {mean, rstd} of the stored bf16 row (folded PreNorm)
+  float stats_eps;
+  const float* ln_stats;       // QKV: per-pixel {mean, rstd} of the input row
+  const float* ln_colsum;      // QKV: sum_c W'[n][c]
   int stg_count;           // 1 or 2 staging tiles (2: the store of tile i overlaps the epilogue of tile i+1)
 };
 
@@ -291,11 +295,28 @@ __device__ __forceinline__ void epilogue_tile(const ConvKParams& p, const TileCo
   }
 
   // KE_PLAIN / KE_QKV
+  float st_sum = 0.f, st_sq = 0.f;       // PLAIN + stats_out: moments of the stored (bf16-rounded) row
+  float ln_mean = 0.f, ln_rstd = 1.f;    // QKV + ln_stats: folded PreNorm of the input row
+  if (EPI == KE_QKV && p.ln_stats && valid) {
+    const float2 ms = __ldg(reinterpret_cast<const float2*>(p.ln_stats) + opix);
+    ln_mean = ms.x;
+    ln_rstd = ms.y;
+  }
   for (int c = 0; c < p.block_n; c += 32) {
     const int ch = t.nt * p.block_n + c;
     if (ch >= p.cout) break;  // warp-uniform (cout_pad > cout)
     chunk_from_tmem(tmem_acc + c, v);
     if (EPI == KE_QKV) {
+      if (p.ln_stats) {   // W' x  ->  W' LN(x) = rstd * (W' x - mean * colsum(W'))
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 cs = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + ch) + q);
+          v[4 * q] = (v[4 * q] - ln_mean * cs.x) * ln_rstd;
+          v[4 * q + 1] = (v[4 * q + 1] - ln_mean * cs.y) * ln_rstd;
+          v[4 * q + 2] = (v[4 * q + 2] - ln_mean * cs.z) * ln_rstd;
+          v[4 * q + 3] = (v[4 * q + 3] - ln_mean * cs.w) * ln_rstd;
+        }
+      }
       if (t.nt == 0) {  // q: softmax over the 32 channels of one head, times dim_head^-0.5
         float m = v[0];
 #pragma unroll
@@ -359,6 +380,19 @@ __device__ __forceinline__ void epilogue_tile(const ConvKParams& p, const TileCo
       if (p.out && !stg) chunk_store_bf16(p.out + opix * p.out_ld + p.out_coff + ch, v);
     }
     if (stg) chunk_stage_bf16(stg, row, c, v);
+    if (EPI == KE_PLAIN && p.stats_out) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float r = __bfloat162float(__float2bfloat16(v[j]));   // what the consumer will read
+        st_sum += r;
+        st_sq = fmaf(r, r, st_sq);
+      }
+    }
+  }
+  if (EPI == KE_PLAIN && p.stats_out && valid) {
+    const float mean = st_sum / p.cout;
+    const float var = fmaxf(st_sq / p.cout - mean * mean, 0.f);
+    reinterpret_cast<float2*>(p.stats_out)[opix] = make_float2(mean, rsqrtf(var + p.stats_eps));
   }
 }
 

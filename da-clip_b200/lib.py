@@ -41,6 +41,8 @@ class ConvDesc(C.Structure):
         ("res_f32", C.c_void_p), ("res_f32_ld", C.c_int32),
         ("out_f32", C.c_void_p), ("out_f32_ld", C.c_int32),
         ("out_planar", C.c_void_p),
+        ("stats_out", C.c_void_p), ("stats_eps", C.c_float),
+        ("ln_stats", C.c_void_p), ("ln_colsum", C.c_void_p),
         ("out_nchw", C.c_void_p), ("out_nchw_c", C.c_int32), ("out_nchw_h", C.c_int32), ("out_nchw_w", C.c_int32),
     ]
 

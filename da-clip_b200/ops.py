@@ -141,7 +141,8 @@ class ConvPlan:
                  ln_g=None, ln_eps=1e-5, res=None, res2=None, res_f32=None, out_f32=None, out_planar=None, out_coff=0,
                  out_nchw=None,
                  per_image_w=False, block_n=None, weight_override=None, tile=None, share_taps=True,
-                 rsrc0=None, rc0=0, rsrc1=None, rc1=0, rweight=None):
+                 rsrc0=None, rc0=0, rsrc1=None, rc1=0, rweight=None, stats_out=None, stats_eps=1e-5,
+                 ln_stats=None, ln_colsum=None):
         L.require_cuda(src0)
         lib = L.load()
         d = L.ConvDesc()
@@ -196,6 +197,10 @@ class ConvPlan:
             d.out_f32, d.out_f32_ld = out_f32.data_ptr(), out_f32.shape[-1]
         if out_planar is not None:
             d.out_planar = out_planar.data_ptr()
+        if stats_out is not None:
+            d.stats_out, d.stats_eps = stats_out.data_ptr(), stats_eps
+        if ln_stats is not None:
+            d.ln_stats, d.ln_colsum = ln_stats.data_ptr(), ln_colsum.data_ptr()
         if out_nchw is not None:
             d.out_nchw = out_nchw.data_ptr()
             d.out_nchw_c, d.out_nchw_h, d.out_nchw_w = out_nchw.shape[1], out_nchw.shape[2], out_nchw.shape[3]
@@ -205,7 +210,7 @@ class ConvPlan:
         L.check(lib.dac_conv_create(C.byref(d), C.byref(h)))
         self.handle = h
         self._lib = lib
-        self._keep += (rsrc0, rsrc1, rweight)
+        self._keep += (rsrc0, rsrc1, rweight, stats_out, ln_stats, ln_colsum)
         self.flops = 2.0 * B * OH * OW * pw.ngroups * len(pw.taps[0]) * (c0 + c1) * pw.cout \
             + 2.0 * B * OH * OW * (rc0 + rc1) * pw.cout * (rsrc0 is not None)
 

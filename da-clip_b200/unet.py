@@ -291,7 +291,9 @@ class PackedUNet:
         if not transformer:
             if dim > 256:
                 raise NotImplementedError("LinearAttention with more than 256 channels (fused LN epilogue limit)")
-            a.update(qkv=ops.pack_linear(f32(q + "to_qkv.weight")),
+            wq = f32(q + "to_qkv.weight").reshape(384, dim) * a["pre_g"][None, :]      # W' = W diag(g)
+            a.update(qkv=ops.pack_linear(wq),
+                     qkv_colsum=wq.to(torch.bfloat16).float().sum(dim=1).contiguous(),      # of the bf16 operand
                      out=ops.pack_linear(f32(q + "to_out.0.weight")),
                      w_out=f32(q + "to_out.0.weight").reshape(dim, 128).contiguous(),
                      b_out=f32(q + "to_out.0.bias"), g_out=f32(q + "to_out.1.g").reshape(-1).contiguous())
@@ -366,7 +368,7 @@ class UNetEngine:
     def is_conv(self, name):
         return name in self.conv_names
 
-    def resblock(self, prefix, x, xc, h, w, skip=None, sc=0):
+    def resblock(self, prefix, x, xc, h, w, skip=None, sc=0, stats=None):
         rb = self.pk.rb[prefix]
         cout = rb["cout"]
         B = self.B
@@ -378,7 +380,7 @@ class UNetEngine:
             # res_conv fused into block2: a second TMEM accumulator fed by extra K steps over (x | skip); neither the
             # 1x1 conv launch nor its output tensor exists
             self.conv(prefix + "block2", h1, cout, rb["w2"], out, h, w, act=L.ACT_SILU,
-                      rsrc0=x, rc0=xc, rsrc1=skip, rc1=sc, rweight=rb["wr"])
+                      rsrc0=x, rc0=xc, rsrc1=skip, rc1=sc, rweight=rb["wr"], stats_out=stats)
             return out
         if rb["wr"] is not None:
             r = self.buf(B, h, w, cout)
@@ -386,19 +388,35 @@ class UNetEngine:
         else:
             assert skip is None
             r = x
-        self.conv(prefix + "block2", h1, cout, rb["w2"], out, h, w, act=L.ACT_SILU, res=r)
+        self.conv(prefix + "block2", h1, cout, rb["w2"], out, h, w, act=L.ACT_SILU, res=r, stats_out=stats)
         return out
 
-    def attn_layer(self, prefix, x, C, h, w):
+    # Folding PreNorm around to_qkv (producer writes {mean, rstd}, QKV epilogue finishes the normalisation) removes
+    # the LayerNorm launch and the normalised tensor, but measured SLOWER on B200 at batch 16 (to_qkv 245 -> 306 us,
+    # producer +14 us vs the 54 us LayerNorm kernel saved): the QKV epilogue is already the bottleneck of that
+    # store-bound layer.  Kept as a tested option (tests/test_kernels_gpu.py::test_prenorm_folded_into_qkv).
+    FOLD_PRENORM = False
+
+    def needs_stats(self, prefix):
+        """True if the attention layer `prefix` consumes per-pixel LayerNorm statistics from its producer."""
+        return self.FOLD_PRENORM and not self.pk.attn[prefix]["transformer"]
+
+    def attn_layer(self, prefix, x, C, h, w, stats=None):
         a = self.pk.attn[prefix]
         B, hw = self.B, h * w
-        xn = self.buf(B, h, w, C)
-        self.add(prefix + "prenorm", lambda: ops.layernorm_rows(x, xn, B * hw, C, a["pre_g"], None, 1e-5))
         out = self.buf(B, h, w, C)
         if not a["transformer"]:
+            # PreNorm is folded around to_qkv: raw x in, gain-folded weights, rstd * (acc - mean * colsum) in the
+            # epilogue with the {mean, rstd} the producing ResBlock wrote; no normalised tensor, no LayerNorm launch
             q = self.buf(B, h, w, 128)                  # softmaxed queries, NHWC (A operand of the to_out GEMM)
             kv = self.buf(B, 256, h, w)                 # k | v, planar: pixel-contiguous rows for the context pass
-            self.conv(prefix + "to_qkv", xn, C, a["qkv"], q, h, w, epi=L.EPI_QKV, block_n=128, out_planar=kv)
+            if stats is not None:
+                self.conv(prefix + "to_qkv", x, C, a["qkv"], q, h, w, epi=L.EPI_QKV, block_n=128, out_planar=kv,
+                          ln_stats=stats, ln_colsum=a["qkv_colsum"])
+            else:
+                xn = self.buf(B, h, w, C)
+                self.add(prefix + "prenorm", lambda: ops.layernorm_rows(x, xn, B * hw, C, None, None, 1e-5))
+                self.conv(prefix + "to_qkv", xn, C, a["qkv"], q, h, w, epi=L.EPI_QKV, block_n=128, out_planar=kv)
             nchunks = max(1, min(128, (148 * 8) // (B * 4), hw // 256))
             partial = self.buf(B, 4, nchunks, 32 * 34, dtype=torch.float32)
             c_pad = a["out"].w.shape[-2]
@@ -409,6 +427,8 @@ class UNetEngine:
             self.conv(prefix + "to_out", q, 128, a["out"], out, h, w, epi=L.EPI_LN, bias=a["b_out"],
                       ln_g=a["g_out"], res=x, per_image_w=True, weight_override=weff)
             return out
+        xn = self.buf(B, h, w, C)
+        self.add(prefix + "prenorm", lambda: ops.layernorm_rows(x, xn, B * hw, C, a["pre_g"], None, 1e-5))
         heads = a["heads"]
         gn = self.buf(B, h, w, C)
         stats = self.buf(B * 64, dtype=torch.float32)
@@ -460,9 +480,10 @@ class UNetEngine:
             x = self.resblock(p + "0.", x, din, h, w)
             self.taps[p + "0"] = x
             skips.append((x, din))
-            x = self.resblock(p + "1.", x, din, h, w)
+            st = self.buf(B * h * w, 2, dtype=torch.float32) if self.needs_stats(p + "2.") else None
+            x = self.resblock(p + "1.", x, din, h, w, stats=st)
             self.taps[p + "1"] = x
-            x = self.attn_layer(p + "2.", x, din, h, w)
+            x = self.attn_layer(p + "2.", x, din, h, w, stats=st)
             self.taps[p + "2"] = x
             skips.append((x, din))
             pw, bias = pk.down[i]
@@ -476,9 +497,10 @@ class UNetEngine:
             x = y
             self.taps[p + "3"] = x
         md = cfg.mid_dim
-        x = self.resblock("mid_block1.", x, md, h, w)
+        st = self.buf(B * h * w, 2, dtype=torch.float32) if self.needs_stats("mid_attn.") else None
+        x = self.resblock("mid_block1.", x, md, h, w, stats=st)
         self.taps["mid_block1"] = x
-        x = self.attn_layer("mid_attn.", x, md, h, w)
+        x = self.attn_layer("mid_attn.", x, md, h, w, stats=st)
         self.taps["mid_attn"] = x
         x = self.resblock("mid_block2.", x, md, h, w)
         self.taps["mid_block2"] = x
@@ -490,9 +512,10 @@ class UNetEngine:
             x = self.resblock(p + "0.", x, dout, h, w, skip=sk, sc=sc)
             self.taps[p + "0"] = x
             sk, sc = skips.pop()
-            x = self.resblock(p + "1.", x, dout, h, w, skip=sk, sc=sc)
+            st = self.buf(B * h * w, 2, dtype=torch.float32) if self.needs_stats(p + "2.") else None
+            x = self.resblock(p + "1.", x, dout, h, w, skip=sk, sc=sc, stats=st)
             self.taps[p + "1"] = x
-            x = self.attn_layer(p + "2.", x, dout, h, w)
+            x = self.attn_layer(p + "2.", x, dout, h, w, stats=st)
             self.taps[p + "2"] = x
             pw, bias = pk.up[j]
             if i != 0:

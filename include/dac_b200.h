@@ -111,6 +111,12 @@ typedef struct dac_conv_desc {
   const float* res_f32; int32_t res_f32_ld;       /* fp32 residual stream (ViT blocks keep x in fp32), PLAIN only */
   float* out_f32; int32_t out_f32_ld;             /* fp32 copy of the output (may be given together with out) */
   void* out_planar;                               /* DAC_EPI_QKV only: bf16 [B][256][OH][OW] for k | v */
+  /* Channel LayerNorm (MU:77-86,89-97 PreNorm) folded around a 1x1 conv: the PRODUCER of x (PLAIN epilogue, one N
+   * tile) writes per-pixel {mean, rstd} of its bf16 output row to stats_out; the QKV conv then runs on the raw x
+   * with gain-folded weights W' = W diag(g) and finishes rstd * (acc - mean * colsum(W')) in its epilogue, so the
+   * normalised tensor is never materialised. */
+  float* stats_out; float stats_eps;              /* [B*OH*OW][2] fp32 */
+  const float* ln_stats; const float* ln_colsum;  /* QKV: [B*OH*OW][2], [cout] */
   float* out_nchw; int32_t out_nchw_c, out_nchw_h, out_nchw_w; /* alt. fp32 NCHW output (final_conv), cropped */
 } dac_conv_desc;
 

@@ -302,6 +302,38 @@ def test_linear_attention_block(ops, gen, B, H, W, C):
     assert_close_bf16(nchw(out), ref, f"linear attention {H}x{W} C={C}", rel=2 ** -5, abs_=2e-2)
 
 
+@pytest.mark.parametrize("B,H,W,C", [(2, 32, 32, 64), (1, 16, 48, 128), (1, 16, 16, 256)])
+def test_prenorm_folded_into_qkv(ops, gen, B, H, W, C):
+    """PreNorm (channel LayerNorm, gain only) folded around to_qkv: the producer writes per-pixel {mean, rstd} of its
+    bf16 output, the QKV conv runs on the raw tensor with W diag(g) and finishes the normalisation in its epilogue."""
+    from daclip_b200 import lib as L
+    x = rnd(gen, B, C, H, W) * 2 + 0.7
+    g = 1 + 0.2 * rnd(gen, C)
+    wqkv = rnd(gen, 384, C, scale=C ** -0.5)
+    xh = nhwc(x)
+    # producer: an identity 1x1 conv standing in for the ResBlock tail; writes y = x (bf16) and the row statistics
+    y = torch.zeros(B, H, W, C, device="cuda", dtype=torch.bfloat16)
+    stats = torch.zeros(B * H * W, 2, device="cuda")
+    ops.ConvPlan(xh, C, ops.pack_linear(torch.eye(C, device="cuda")), y, B=B, H=H, W=W, stats_out=stats).run()
+    wf = wqkv * g[None, :]
+    q = torch.zeros(B, H, W, 128, device="cuda", dtype=torch.bfloat16)
+    kv = torch.zeros(B, 256, H, W, device="cuda", dtype=torch.bfloat16)
+    ops.ConvPlan(y, C, ops.pack_linear(wf), q, B=B, H=H, W=W, epi=L.EPI_QKV, block_n=128, out_planar=kv,
+                 ln_stats=stats, ln_colsum=bf(wf).float().sum(1).contiguous()).run()
+    torch.cuda.synchronize()
+    assert torch.equal(y, xh)
+    xf = nchw(xh)
+    mean, var = xf.mean(1), xf.var(1, unbiased=False)
+    assert (stats[:, 0].reshape(B, H, W) - mean).abs().max().item() < 1e-4
+    assert (stats[:, 1].reshape(B, H, W) * torch.sqrt(var + 1e-5) - 1).abs().max().item() < 1e-3
+    xn = (xf - mean[:, None]) * torch.rsqrt(var[:, None] + 1e-5) * g[None, :, None, None]
+    ref = F.conv2d(xn, wqkv[:, :, None, None])
+    assert_close_bf16(kv, ref[:, 128:], "folded PreNorm k|v", rel=2 ** -6, abs_=4e-3)
+    q_ref = ref[:, :128].reshape(B, 4, 32, H * W).softmax(2) * 32 ** -0.5
+    assert_close_bf16(q.float().reshape(B, H * W, 4, 32).permute(0, 2, 3, 1), q_ref, "folded PreNorm q", rel=2 ** -5,
+                      abs_=4e-3)
+
+
 # ---------------------------------------------------------------------------------------------- attention
 @pytest.mark.parametrize("B,n,heads", [(2, 1024, 8), (1, 4096, 16), (1, 200, 4)])
 def test_flash_attention_d32(ops, gen, B, n, heads):
