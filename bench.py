@@ -32,6 +32,9 @@ ALGO_GFLOP_PER_EVAL = {256: 266.2, 512: 1129.1}
 # plus the LinearAttention "apply" einsum that is folded into to_out = 1.41): everything except the k-softmax
 # context einsum (1.41) and the self-attention QK^T/PV (5.37).  At 512^2: 1031.9 + 5.64.
 CONV_GFLOP_PER_EVAL = {256: 257.98 + 1.41, 512: 1031.9 + 5.64}
+# dram__bytes_read.sum + dram__bytes_write.sum of conv_igemm_kernel, averaged over its launches of one evaluation, from
+# the ncu launch list of this same command (profiles/r01_ncu_launches_bench_n1.csv): batch 16, 256^2 only.
+CONV_DRAM_BYTES_PER_LAUNCH = {(16, 256): 135.9e6}
 
 
 def peaks():
@@ -235,7 +238,8 @@ def run_product(args):
             "whole_step_tensor_frac": round(world and (algo * B * T_STEPS / ms_per_step) / peak_tf, 4),
             "roofline": {"bound": "tensor", "kernel": "conv_igemm_kernel (tcgen05 implicit GEMM)",
                          "achieved": round(achieved, 2), "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": round(achieved / peak_tf, 4), "traffic": None,
+                         "frac": round(achieved / peak_tf, 4),
+                         "traffic": CONV_DRAM_BYTES_PER_LAUNCH.get((B, S)),
                          "peak_source": f"{which} bf16_tflops_sustained",
                          "launches_per_eval": n_conv, "conv_ms_per_eval": round(conv_ms, 3),
                          "all_kernels_ms_per_eval": round(all_ms, 3),
