@@ -38,7 +38,7 @@ static PFN_encodeTiled get_encode_fn() {
 }  // namespace dac
 
 struct dac_conv_plan {
-  CUtensorMap mapA0, mapA1, mapW, mapOut, mapOut2, mapR0, mapR1, mapWR;
+  CUtensorMap mapA0, mapA1, mapW, mapOut, mapOut2, mapR0, mapR1, mapWR, mapRes;
   dac::ConvKParams kp;
   dac::ConvKernelFn kernel;
   int grid;
@@ -249,6 +249,18 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) rc = set_error(-11, "cuTensorMapEncodeTiled(output) failed: CUresult %d", (int)r);
     pl->mapOut2 = pl->mapOut;
+    pl->mapRes = pl->mapOut;
+    // bf16 residual through TMA: same box as the output tile, landed in the staging tile before the epilogue runs
+    if (rc == 0 && d->res && d->epi == DAC_EPI_PLAIN && d->cout == d->cout_pad && !getenv("DAC_NO_TMA_RES")) {
+      cuuint64_t rd[4] = {(cuuint64_t)d->cout, (cuuint64_t)k.OWf, (cuuint64_t)k.OHf, (cuuint64_t)d->B};
+      cuuint64_t rs[3] = {(cuuint64_t)d->res_ld * 2, (cuuint64_t)k.OWf * d->res_ld * 2,
+                          (cuuint64_t)k.OHf * k.OWf * d->res_ld * 2};
+      r = enc(&pl->mapRes, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d->res), rd, rs, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) rc = set_error(-11, "cuTensorMapEncodeTiled(residual) failed: CUresult %d", (int)r);
+      else pl->kp.res_tma = 1;
+    }
     if (rc == 0 && d->epi == DAC_EPI_QKV) {
       // planar k|v tensor [B][256][OH][OW]: box = tile_w x tile_h pixels x 128 channels, un-swizzled, i.e. the
       // [channel][pixel] staging tile the epilogue wrote
@@ -263,6 +275,7 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
   } else if (rc == 0) {
     pl->mapOut = pl->mapA0;
     pl->mapOut2 = pl->mapA0;
+    pl->mapRes = pl->mapA0;
   }
   pl->mapR0 = pl->mapA0; pl->mapR1 = pl->mapA0; pl->mapWR = pl->mapW;
   if (rc == 0 && fused_res) {
@@ -303,7 +316,7 @@ extern "C" int dac_conv_launch(dac_conv_t pl, dac_stream_t stream) {
   if (!pl) return set_error(-1, "dac_conv_launch: null plan");
   pl->kernel<<<pl->grid, kThreads, pl->smem, static_cast<cudaStream_t>(stream)>>>(pl->mapA0, pl->mapA1, pl->mapW,
                                                                                   pl->mapOut, pl->mapOut2, pl->mapR0,
-                                                                                  pl->mapR1, pl->mapWR, pl->kp);
+                                                                                  pl->mapR1, pl->mapWR, pl->mapRes, pl->kp);
   return check_launch("conv_igemm_kernel");
 }
 

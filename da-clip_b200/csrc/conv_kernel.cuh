@@ -103,6 +103,7 @@ struct ConvKParams {
   const float* ln_stats;       // QKV: per-pixel {mean, rstd} of the input row
   const float* ln_colsum;      // QKV: sum_c W'[n][c]
   int stg_count;           // 1 or 2 staging tiles (2: the store of tile i overlaps the epilogue of tile i+1)
+  int res_tma;             // the bf16 residual tile is TMA-loaded into the staging tile and updated in place
 };
 
 struct TileCoord {
@@ -199,6 +200,18 @@ __device__ __forceinline__ void chunk_stage_bf16(uint8_t* stg, int row, int col,
     u.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
     u.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
     *reinterpret_cast<uint4*>(slab + (((c16 + q) ^ (row & 7)) << 4)) = u;
+  }
+}
+// ... and the read side: add the 32 staged bf16 values of this row (a TMA-loaded residual tile) to v
+__device__ __forceinline__ void chunk_add_staged(const uint8_t* stg, int row, int col, float (&v)[32]) {
+  const uint8_t* slab = stg + (col >> 6) * (kTileM * 128) + row * 128;
+  const int c16 = (col & 63) >> 3;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint4 u = *reinterpret_cast<const uint4*>(slab + (((c16 + q) ^ (row & 7)) << 4));
+    const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+    v[q * 8 + 0] += a.x; v[q * 8 + 1] += a.y; v[q * 8 + 2] += b.x; v[q * 8 + 3] += b.y;
+    v[q * 8 + 4] += c.x; v[q * 8 + 5] += c.y; v[q * 8 + 6] += d.x; v[q * 8 + 7] += d.y;
   }
 }
 __device__ __forceinline__ void chunk_store_f32(float* __restrict__ dst, const float (&v)[32]) {
@@ -372,9 +385,10 @@ __device__ __forceinline__ void epilogue_tile(const ConvKParams& p, const TileCo
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] += r2[j];
     }
+    if (p.res_tma) chunk_add_staged(stg, row, c, v);   // residual tile already in shared memory (TMA)
     if (valid) {
       if (p.res_f32) chunk_add_f32(p.res_f32 + opix * p.res_f32_ld + ch, v);
-      if (p.res) chunk_add_bf16(p.res + opix * p.res_ld + ch, v);
+      if (p.res && !p.res_tma) chunk_add_bf16(p.res + opix * p.res_ld + ch, v);
       if (p.res2) chunk_add_bf16(p.res2 + opix * p.res2_ld + ch, v);
       if (p.out_f32) chunk_store_f32(p.out_f32 + opix * p.out_f32_ld + ch, v);
       if (p.out && !stg) chunk_store_bf16(p.out + opix * p.out_ld + p.out_coff + ch, v);
@@ -402,7 +416,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
                   const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapOut,
                   const __grid_constant__ CUtensorMap mapOut2, const __grid_constant__ CUtensorMap mapR0,
                   const __grid_constant__ CUtensorMap mapR1, const __grid_constant__ CUtensorMap mapWR,
-                  const __grid_constant__ ConvKParams p) {
+                  const __grid_constant__ CUtensorMap mapRes, const __grid_constant__ ConvKParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024 B alignment is required by the 128B swizzle atoms (TMA write and UMMA read agree on address bits).
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -423,6 +437,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* b_full = tmem_empty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
+  uint64_t* res_bar = b_full + 2;   // one per epilogue group: residual tile landed in the staging tile
   float* film_sh = reinterpret_cast<float*>(bars + 32);   // [2][block_n]: scale + 1 | shift of the current image
   const int chunks = p.chunks0 + p.chunks1;
 
@@ -452,6 +467,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       mbar_init(&tmem_empty[s], kEpiWarps / 2);
     }
     mbar_init(b_full, 1);
+    mbar_init(&res_bar[0], 1);
+    mbar_init(&res_bar[1], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -617,12 +634,21 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");
         }
       }
+      if (stg && gthread == 0) {
+        // this group's previous TMA store must have finished reading the staging tile before it is rewritten
+        tma_store_wait_read();
+        if (p.res_tma) {   // fetch the residual tile now: it lands while the MMAs of this tile are still running
+          const int cols = p.block_n;
+          mbar_arrive_expect_tx(&res_bar[group], static_cast<uint32_t>(cols) * kTileM * 2);
+          for (int s_ = 0; s_ * 64 < cols; ++s_)
+            tma_load_4d(stg + s_ * (kTileM * 128), &mapRes, &res_bar[group], t.nt * cols + s_ * 64, t.x0, t.y0, t.n);
+        }
+      }
       mbar_wait(&tmem_full[group], acc_phase);
       tc_fence_after();
       if (stg) {
-        // this group's previous TMA store must have finished reading the staging tile before it is rewritten
-        if (gthread == 0) tma_store_wait_read();
         asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");
+        if (p.res_tma) mbar_wait(&res_bar[group], acc_phase);
       }
       const uint32_t tmem_acc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + group * kAccStride;
       epilogue_tile<EPI, ACT, FILM>(p, t, tmem_acc, row, film_g, stg);
@@ -658,7 +684,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
 
 typedef void (*ConvKernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
                              const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
-                             const ConvKParams);
+                             const CUtensorMap, const ConvKParams);
 
 // The epilogue flavours that exist as separate kernels; everything else in the epilogue is a warp-uniform
 // runtime branch on a pointer.
