@@ -489,11 +489,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     // ===================== TMA producer (one elected thread) =====================
     if (elect_one()) {
       if (b_resident) {
-        // whole weight tensor (ntaps x chunks tiles) loaded once per CTA; n_tiles == ngroups == 1 here
+        // whole weight tensor (ntaps x chunks tiles) loaded once per CTA, laid out in the ORDER THE MMA LOOP CONSUMES
+        // IT (chunk, column group, tap within the group), so the issuer walks it with one add per tap;
+        // n_tiles == ngroups == 1 here
         mbar_arrive_expect_tx(b_full, p.b_res_bytes);
-        for (int tap = 0; tap < p.ntaps; ++tap)
-          for (int ck = 0; ck < chunks; ++ck)
-            tma_load_3d(b_res + static_cast<size_t>(tap * chunks + ck) * p.b_bytes, &mapW, b_full, ck * kChunkK, 0, tap);
+        for (int ck = 0; ck < chunks; ++ck)
+          for (int jt = 0; jt < p.ntaps; ++jt)
+            tma_load_3d(b_res + static_cast<size_t>(ck * p.ntaps + jt) * p.b_bytes, &mapW, b_full, ck * kChunkK, 0,
+                        p.col_tap[0][jt]);
       }
       int stage = 0;
       uint32_t phase = 0;
@@ -537,9 +540,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one elected thread; the issue loop is the critical path of the
-    // 64-channel layers - one M128 x N64 x K16 MMA is only 32 tensor-pipe cycles - so it is add-only) ==========
-    if (elect_one()) {
+    // ===================== MMA issuer.  The issue loop is the critical path of the 64-channel layers (one
+    // M128 x N64 x K16 MMA is only 32 tensor-pipe cycles).  ALL lanes run the loop and the descriptor arithmetic so
+    // that every operand is provably warp-uniform and lives in uniform registers; only the tcgen05 instructions sit
+    // under elect.sync (a whole-loop `if (elected)` made the compiler compute descriptors in vector registers and
+    // pay two R2UR per operand, ~3x the MMA time). ==========
+    {
       const uint32_t idesc = make_idesc_bf16(kTileM, p.block_n);
       const uint64_t desc_fixed = make_sw128_desc(0);                 // every field except the start address
       const uint32_t ring_lo = (smem_u32(ring) & 0x3FFFF) >> 4;
@@ -552,29 +558,33 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       uint32_t acc_phase = 0;
       if (b_resident) mbar_wait(b_full, 0);
       for (int tile = tile_begin; tile < tile_end; ++tile) {
-        const int g = fast_div(fast_div(tile, p.fd_ntiles), p.fd_mtiles);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kAccStride;
         uint32_t accumulate = 0;
+        uint32_t b_run = bres_lo;   // resident weights: consumed front to back
         for (int ck = 0; ck < chunks; ++ck) {
           for (int j = 0; j < p.ncols; ++j) {
             mbar_wait(&full[stage], phase);
             tc_fence_after();
             const uint32_t a0 = ring_lo + stage * stage_lo;
+            uint32_t a_run = a0, bs_run = a0 + a_lo;
             for (int i = 0; i < p.ndy; ++i) {
               // tap i of the column group: the same activation tile, shifted down by i tile rows
-              const uint64_t adesc = desc_fixed | (a0 + i * shift_lo);
-              const uint64_t bdesc =
-                  desc_fixed | (b_resident ? bres_lo + (p.col_tap[g][j * p.ndy + i] * chunks + ck) * b_lo
-                                           : a0 + a_lo + i * b_lo);
-              umma_bf16(d_tmem, adesc, bdesc, idesc, accumulate);
-              umma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
-              umma_bf16(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
-              umma_bf16(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
+              const uint64_t adesc = desc_fixed | a_run;
+              const uint64_t bdesc = desc_fixed | (b_resident ? b_run : bs_run);
+              a_run += shift_lo;
+              bs_run += b_lo;
+              b_run += b_lo;
+              if (elect_one()) {
+                umma_bf16(d_tmem, adesc, bdesc, idesc, accumulate);
+                umma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
+                umma_bf16(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
+                umma_bf16(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
+              }
               accumulate = 1u;
             }
-            umma_commit(&empty[stage]);
+            if (elect_one()) umma_commit(&empty[stage]);
             if (++stage == p.stages) {
               stage = 0;
               phase ^= 1;
@@ -587,17 +597,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           const uint32_t a0 = ring_lo + stage * stage_lo;
           const uint64_t adesc = desc_fixed | a0;
           const uint64_t bdesc = desc_fixed | (a0 + (p.r_a_bytes >> 4));
-          umma_bf16(d_tmem + p.block_n, adesc, bdesc, idesc, rk ? 1u : 0u);
-          umma_bf16(d_tmem + p.block_n, adesc + 2, bdesc + 2, idesc, 1u);
-          umma_bf16(d_tmem + p.block_n, adesc + 4, bdesc + 4, idesc, 1u);
-          umma_bf16(d_tmem + p.block_n, adesc + 6, bdesc + 6, idesc, 1u);
-          umma_commit(&empty[stage]);
+          if (elect_one()) {
+            umma_bf16(d_tmem + p.block_n, adesc, bdesc, idesc, rk ? 1u : 0u);
+            umma_bf16(d_tmem + p.block_n, adesc + 2, bdesc + 2, idesc, 1u);
+            umma_bf16(d_tmem + p.block_n, adesc + 4, bdesc + 4, idesc, 1u);
+            umma_bf16(d_tmem + p.block_n, adesc + 6, bdesc + 6, idesc, 1u);
+            umma_commit(&empty[stage]);
+          }
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tmem_full[acc]);
+        if (elect_one()) umma_commit(&tmem_full[acc]);
+        __syncwarp();
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;

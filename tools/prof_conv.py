@@ -28,7 +28,9 @@ def make(name):
         plan = ops.ConvPlan(x, cin, ops.pack_conv(w), out, B=B, H=H, W=W, act=L.ACT_SILU, film=film)
     elif kind == "qkv":
         w = torch.randn(cout, cin, device="cuda", generator=g) * cin ** -0.5
-        plan = ops.ConvPlan(x, cin, ops.pack_linear(w), out, B=B, H=H, W=W, epi=L.EPI_QKV, block_n=128)
+        q = torch.zeros(B, H, W, 128, device="cuda", dtype=torch.bfloat16)
+        kv = torch.zeros(B, 256, H, W, device="cuda", dtype=torch.bfloat16)
+        plan = ops.ConvPlan(x, cin, ops.pack_linear(w), q, B=B, H=H, W=W, epi=L.EPI_QKV, block_n=128, out_planar=kv)
     elif kind == "geglu":
         w = torch.randn(cout, cin, device="cuda", generator=g) * cin ** -0.5
         b = torch.randn(cout, device="cuda", generator=g)
