@@ -188,8 +188,8 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
   // mainloop then streams activations only (L2 -> SM ingest is what bounds the 64/128-channel layers).
   const int smem_budget = 227 * 1024 - 1024 /*align*/ - 256 /*barriers*/ - 4096 /*FiLM stage, 2 groups*/;
   const int chunks = k.chunks0 + k.chunks1;
-  const long long res_bytes = (long long)d->ntaps * chunks * k.b_bytes;
-  const bool resident = k.n_tiles == 1 && d->ngroups == 1 && !d->per_image_w && res_bytes <= 160 * 1024 &&
+  const long long res_bytes = (long long)k.n_tiles * d->ntaps * chunks * k.b_bytes;
+  const bool resident = d->ngroups == 1 && !d->per_image_w && res_bytes <= 160 * 1024 &&
                         (smem_budget - res_bytes) / (long long)k.a_bytes >= 3;
   k.b_res_bytes = resident ? (uint32_t)res_bytes : 0u;
   uint32_t stage_bytes = k.a_bytes + (resident ? 0u : (uint32_t)d->ndy * k.b_bytes);

@@ -490,13 +490,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     if (elect_one()) {
       if (b_resident) {
         // whole weight tensor (ntaps x chunks tiles) loaded once per CTA, laid out in the ORDER THE MMA LOOP CONSUMES
-        // IT (chunk, column group, tap within the group), so the issuer walks it with one add per tap;
-        // n_tiles == ngroups == 1 here
+        // IT (N tile, chunk, column group, tap within the group), so the issuer walks it with one add per tap;
+        // ngroups == 1 here
         mbar_arrive_expect_tx(b_full, p.b_res_bytes);
-        for (int ck = 0; ck < chunks; ++ck)
-          for (int jt = 0; jt < p.ntaps; ++jt)
-            tma_load_3d(b_res + static_cast<size_t>(ck * p.ntaps + jt) * p.b_bytes, &mapW, b_full, ck * kChunkK, 0,
-                        p.col_tap[0][jt]);
+        for (int nt = 0; nt < p.n_tiles; ++nt)
+          for (int ck = 0; ck < chunks; ++ck)
+            for (int jt = 0; jt < p.ntaps; ++jt)
+              tma_load_3d(b_res + static_cast<size_t>((nt * chunks + ck) * p.ntaps + jt) * p.b_bytes, &mapW, b_full,
+                          ck * kChunkK, nt * p.block_n, p.col_tap[0][jt]);
       }
       int stage = 0;
       uint32_t phase = 0;
@@ -562,7 +563,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kAccStride;
         uint32_t accumulate = 0;
-        uint32_t b_run = bres_lo;   // resident weights: consumed front to back
+        const int nt = tile - fast_div(tile, p.fd_ntiles) * p.n_tiles;
+        uint32_t b_run = bres_lo + nt * (chunks * p.ntaps) * b_lo;   // resident weights of this N tile, front to back
         for (int ck = 0; ck < chunks; ++ck) {
           for (int j = 0; j < p.ncols; ++j) {
             mbar_wait(&full[stage], phase);
