@@ -84,7 +84,8 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
        reinterpret_cast<uintptr_t>(d->weight) | reinterpret_cast<uintptr_t>(d->out) |
        reinterpret_cast<uintptr_t>(d->res) | reinterpret_cast<uintptr_t>(d->res2)) & 15)
     return set_error(-2, "dac_conv_create: pointers must be 16-byte aligned");
-  if (!d->out && !d->out_nchw && !d->out_f32) return set_error(-2, "dac_conv_create: no output");
+  if (!d->out && !d->out_nchw && !d->out_f32 && d->epi != DAC_EPI_KVCTX)
+    return set_error(-2, "dac_conv_create: no output");
   if ((d->out_f32 && (d->out_f32_ld & 3)) || (d->res_f32 && (d->res_f32_ld & 3)) ||
       ((reinterpret_cast<uintptr_t>(d->out_f32) | reinterpret_cast<uintptr_t>(d->res_f32)) & 15))
     return set_error(-2, "dac_conv_create: fp32 stream pointers/pitches must be 16-byte aligned");
@@ -99,9 +100,16 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
     if (d->cout != d->block_n || d->cout_pad != d->cout || !d->ln_g || (d->cout & 63) || !d->out)
       return set_error(-2, "dac_conv_create: LN epilogue needs a single N tile with cout %% 64 == 0");
   } else if (d->epi == DAC_EPI_QKV) {
-    if (d->block_n != 128 || d->cout != 384 || !d->out || !d->out_planar || d->out_scale > 1 ||
-        (reinterpret_cast<uintptr_t>(d->out_planar) & 127))
-      return set_error(-2, "dac_conv_create: QKV epilogue needs block_n 128, cout 384, out (q) and out_planar (k|v)");
+    const bool q_only = d->cout == 128;   // k | v go through a KVCTX plan instead
+    if (d->block_n != 128 || (d->cout != 384 && !q_only) || !d->out || (!q_only && !d->out_planar) ||
+        d->out_scale > 1 || (reinterpret_cast<uintptr_t>(d->out_planar) & 127))
+      return set_error(-2, "dac_conv_create: QKV epilogue needs block_n 128, cout 384 (128: q only), out (q) and "
+                           "out_planar (k|v)");
+  } else if (d->epi == DAC_EPI_KVCTX) {
+    if (d->block_n != 256 || d->cout != 256 || d->cout_pad != 256 || !d->kv_shift || !d->ctx_acc || d->out ||
+        d->out_f32 || d->ngroups != 1 || d->per_image_w || d->out_scale > 1 ||
+        ((reinterpret_cast<uintptr_t>(d->kv_shift) | reinterpret_cast<uintptr_t>(d->ctx_acc)) & 15))
+      return set_error(-2, "dac_conv_create: KVCTX epilogue needs block_n = cout = 256, kv_shift, ctx_acc, no out");
   } else if (d->epi == DAC_EPI_GEGLU) {
     if (!d->bias || (d->block_n & 127) || d->cout != d->cout_pad || !d->out)
       return set_error(-2, "dac_conv_create: GEGLU epilogue needs bias and block_n %% 128 == 0");
@@ -189,8 +197,9 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
   const int smem_budget = 227 * 1024 - 1024 /*align*/ - 256 /*barriers*/ - 4096 /*FiLM stage, 2 groups*/;
   const int chunks = k.chunks0 + k.chunks1;
   const long long res_bytes = (long long)k.n_tiles * d->ntaps * chunks * k.b_bytes;
+  const long long kv_extra = d->epi == DAC_EPI_KVCTX ? 2ll * kKvStageBytes : 0;   // P / V head tiles, both groups
   const bool resident = d->ngroups == 1 && !d->per_image_w && res_bytes <= 160 * 1024 &&
-                        (smem_budget - res_bytes) / (long long)k.a_bytes >= 3;
+                        (smem_budget - res_bytes - kv_extra) / (long long)k.a_bytes >= 3;
   k.b_res_bytes = resident ? (uint32_t)res_bytes : 0u;
   uint32_t stage_bytes = k.a_bytes + (resident ? 0u : (uint32_t)d->ndy * k.b_bytes);
   if (fused_res && stage_bytes < k.r_a_bytes + k.b_bytes) stage_bytes = k.r_a_bytes + k.b_bytes;
@@ -207,6 +216,8 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
     const int with = (smem_budget - (int)k.b_res_bytes - 2 * (int)want) / (int)stage_bytes;
     if (with >= 4 || (with >= 3 && with >= without)) stg_bytes = want;
   }
+  if (d->epi == DAC_EPI_KVCTX) stg_bytes = kKvStageBytes;   // P / V head tiles of each epilogue group
+  k.kv_shift = d->kv_shift; k.ctx_acc = d->ctx_acc;
   k.stg_bytes = stg_bytes;
   k.stg_count = stg_bytes ? 2 : 1;   // one staging tile per epilogue group
   int stages = (smem_budget - (int)k.b_res_bytes - (int)stg_bytes * k.stg_count) / (int)stage_bytes;
@@ -236,7 +247,7 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) rc = set_error(-11, "cuTensorMapEncodeTiled(weight) failed: CUresult %d", (int)r);
   }
-  if (rc == 0 && stg_bytes) {
+  if (rc == 0 && stg_bytes && d->epi != DAC_EPI_KVCTX) {
     PFN_encodeTiled enc = get_encode_fn();
     const int valid_c = d->epi == DAC_EPI_GEGLU ? d->cout / 2 : (d->epi == DAC_EPI_QKV ? 128 : d->cout);
     cuuint64_t dims[4] = {(cuuint64_t)(d->out_coff + valid_c), (cuuint64_t)k.OWf, (cuuint64_t)k.OHf, (cuuint64_t)d->B};
@@ -261,7 +272,7 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
       if (r != CUDA_SUCCESS) rc = set_error(-11, "cuTensorMapEncodeTiled(residual) failed: CUresult %d", (int)r);
       else pl->kp.res_tma = 1;
     }
-    if (rc == 0 && d->epi == DAC_EPI_QKV) {
+    if (rc == 0 && d->epi == DAC_EPI_QKV && d->out_planar) {
       // planar k|v tensor [B][256][OH][OW]: box = tile_w x tile_h pixels x 128 channels, un-swizzled, i.e. the
       // [channel][pixel] staging tile the epilogue wrote
       cuuint64_t pd[4] = {(cuuint64_t)d->OW, (cuuint64_t)d->OH, 256, (cuuint64_t)d->B};
@@ -314,6 +325,11 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
 
 extern "C" int dac_conv_launch(dac_conv_t pl, dac_stream_t stream) {
   if (!pl) return set_error(-1, "dac_conv_launch: null plan");
+  if (pl->kp.ctx_acc) {   // KVCTX accumulates with atomics: start every launch from zero
+    cudaError_t e = cudaMemsetAsync(pl->kp.ctx_acc, 0, sizeof(float) * pl->kp.B * 4 * kCtxRecord,
+                                    static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return set_error(-20, "dac_conv_launch: memset failed: %s", cudaGetErrorString(e));
+  }
   pl->kernel<<<pl->grid, kThreads, pl->smem, static_cast<cudaStream_t>(stream)>>>(pl->mapA0, pl->mapA1, pl->mapW,
                                                                                   pl->mapOut, pl->mapOut2, pl->mapR0,
                                                                                   pl->mapR1, pl->mapWR, pl->mapRes, pl->kp);

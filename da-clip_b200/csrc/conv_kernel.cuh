@@ -33,7 +33,11 @@ constexpr uint32_t kAccStride = 256;
 constexpr uint32_t kABytes = kTileM * kChunkK * 2;  // 16 KB
 constexpr int kMaxStages = 8;
 
-enum { KE_PLAIN = 0, KE_GEGLU = 1, KE_LN = 2, KE_QKV = 3, KE_NCHW = 4 };
+enum { KE_PLAIN = 0, KE_GEGLU = 1, KE_LN = 2, KE_QKV = 3, KE_NCHW = 4, KE_KVCTX = 5 };
+constexpr int kKvPitch = 40;                                   // bf16 per row of a [128 px][32 ch] head tile
+constexpr uint32_t kKvTileBytes = kTileM * kKvPitch * 2;         // 10 KB
+constexpr uint32_t kKvStageBytes = 4 * kKvTileBytes;             // P and V head tiles, double-buffered: per group
+constexpr int kCtxRecord = 32 * 32 + 64;                        // {C[32][32], m[32], S[32]} per (image, head)
 
 // Division by a launch-time constant without the ~60-cycle IDIV sequence (Granlund-Montgomery round-up method):
 // t = umulhi(mul, n); q = (t + ((n - t) >> s1)) >> s2.  Exact for 0 <= n < 2^31.
@@ -104,6 +108,8 @@ struct ConvKParams {
   const float* ln_colsum;      // QKV: sum_c W'[n][c]
   int stg_count;           // 1 or 2 staging tiles (2: the store of tile i overlaps the epilogue of tile i+1)
   int res_tma;             // the bf16 residual tile is TMA-loaded into the staging tile and updated in place
+  const float* kv_shift;   // KVCTX: [128] upper bound of k per channel, times log2(e)
+  float* ctx_acc;          // KVCTX: [B][4][kCtxRecord] fp32
 };
 
 struct TileCoord {
@@ -410,6 +416,102 @@ __device__ __forceinline__ void epilogue_tile(const ConvKParams& p, const TileCo
   }
 }
 
+// ---- KVCTX: the LinearAttention context reduced straight out of the k|v accumulator (module_util.py:170-177) ----
+// Per epilogue warp: C[h][16 d rows][16 e cols] of every head plus the softmax denominators S[h][16 d rows],
+// carried in registers across the tiles of one image and flushed with atomics when the image changes.
+struct KvCtxAcc {
+  float c[4][2][4];
+  float s[4][4];
+};
+__device__ __forceinline__ void kvctx_zero(KvCtxAcc& a) {
+#pragma unroll
+  for (int h = 0; h < 4; ++h) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      a.c[h][0][j] = 0.f;
+      a.c[h][1][j] = 0.f;
+      a.s[h][j] = 0.f;
+    }
+  }
+}
+__device__ __forceinline__ void kvctx_flush(const ConvKParams& p, int img, int quad, int lane, KvCtxAcc& a) {
+  if (img < 0) return;
+  const int d = 16 * (quad >> 1) + (lane >> 2), e0 = 16 * (quad & 1) + 2 * (lane & 3);
+  float* base = p.ctx_acc + static_cast<long long>(img) * 4 * kCtxRecord;
+#pragma unroll
+  for (int h = 0; h < 4; ++h) {
+    float* hb = base + h * kCtxRecord;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      atomicAdd(hb + d * 32 + e0 + 8 * i, a.c[h][i][0]);
+      atomicAdd(hb + d * 32 + e0 + 8 * i + 1, a.c[h][i][1]);
+      atomicAdd(hb + (d + 8) * 32 + e0 + 8 * i, a.c[h][i][2]);
+      atomicAdd(hb + (d + 8) * 32 + e0 + 8 * i + 1, a.c[h][i][3]);
+    }
+    if ((quad & 1) == 0 && (lane & 3) == 0) {   // every column of the ones-product holds S[d]
+      atomicAdd(hb + 1056 + d, a.s[h][0]);
+      atomicAdd(hb + 1056 + d + 8, a.s[h][2]);
+    }
+  }
+  kvctx_zero(a);
+}
+// One 128-pixel tile: thread = pixel `row`.  Head by head, P = exp(k - shift) and v go to shared memory as
+// [pixel][channel] bf16 tiles (pitch 40: conflict-free for the row-per-lane stores AND the ldmatrix reads); then warp
+// (mt, nh) runs C[16 mt.., 16 nh..] += P^T V over the 128 pixels on mma.sync (A = P^T and B = V both via
+// ldmatrix.trans) and S += P^T 1.  Two buffers per operand: one named barrier per head is enough.
+__device__ __forceinline__ void kvctx_tile(const ConvKParams& p, const TileCoord& t, uint32_t tmem_acc, int row,
+                                           int quad, int lane, int group, uint8_t* stg, KvCtxAcc& a,
+                                           uint64_t* tmem_empty_bar) {
+  const int ty = row >> p.tile_w_shift, tx = row & (p.tile_w - 1);
+  const bool valid = (t.y0 + ty < p.OH) && (t.x0 + tx < p.OW);
+  __nv_bfloat16* tiles = reinterpret_cast<__nv_bfloat16*>(stg);
+  const int mt = quad >> 1, nh = quad & 1;
+  float v[32];
+#pragma unroll
+  for (int h = 0; h < 4; ++h) {
+    __nv_bfloat16* Ph = tiles + (h & 1) * (kTileM * kKvPitch);
+    __nv_bfloat16* Vh = tiles + (2 + (h & 1)) * (kTileM * kKvPitch);
+    chunk_from_tmem(tmem_acc + h * 32, v);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 sh = __ldg(reinterpret_cast<const float4*>(p.kv_shift + h * 32) + q);
+      v[4 * q] = valid ? ex2_approx(fmaf(v[4 * q], 1.4426950408889634f, -sh.x)) : 0.f;
+      v[4 * q + 1] = valid ? ex2_approx(fmaf(v[4 * q + 1], 1.4426950408889634f, -sh.y)) : 0.f;
+      v[4 * q + 2] = valid ? ex2_approx(fmaf(v[4 * q + 2], 1.4426950408889634f, -sh.z)) : 0.f;
+      v[4 * q + 3] = valid ? ex2_approx(fmaf(v[4 * q + 3], 1.4426950408889634f, -sh.w)) : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      *reinterpret_cast<uint4*>(Ph + row * kKvPitch + q * 8) =
+          make_uint4(pack_bf16(v[q * 8], v[q * 8 + 1]), pack_bf16(v[q * 8 + 2], v[q * 8 + 3]),
+                     pack_bf16(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16(v[q * 8 + 6], v[q * 8 + 7]));
+    chunk_from_tmem(tmem_acc + 128 + h * 32, v);
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      *reinterpret_cast<uint4*>(Vh + row * kKvPitch + q * 8) =
+          valid ? make_uint4(pack_bf16(v[q * 8], v[q * 8 + 1]), pack_bf16(v[q * 8 + 2], v[q * 8 + 3]),
+                             pack_bf16(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16(v[q * 8 + 6], v[q * 8 + 7]))
+                : make_uint4(0, 0, 0, 0);
+    if (h == 3) {   // accumulator fully read: hand the TMEM stage back before the last reduction
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty_bar);
+    }
+    asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+      uint32_t af[4], vb[4];
+      ldmatrix_x4_trans(af, Ph + (16 * ks + ((lane >> 4) & 1) * 8 + (lane & 7)) * kKvPitch + 16 * mt +
+                                ((lane >> 3) & 1) * 8);
+      ldmatrix_x4_trans(vb, Vh + (16 * ks + ((lane >> 3) & 1) * 8 + (lane & 7)) * kKvPitch + 16 * nh +
+                                (lane >> 4) * 8);
+      mma_bf16_16816(a.c[h][0], af, vb[0], vb[1]);
+      mma_bf16_16816(a.c[h][1], af, vb[2], vb[3]);
+      mma_bf16_16816(a.s[h], af, 0x3F803F80u, 0x3F803F80u);   // B = ones: row sums of P^T
+    }
+  }
+}
+
 template <int EPI, int ACT, bool FILM>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
@@ -632,6 +734,24 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     uint8_t* stg = stg_base ? stg_base + group * p.stg_bytes : nullptr;
     uint32_t acc_phase = 0;
     int film_key = -1;
+    if (EPI == KE_KVCTX) {
+      KvCtxAcc cacc;
+      kvctx_zero(cacc);
+      int cur_img = -1;
+      for (int tile = tile_begin + group; tile < tile_end; tile += 2) {
+        const TileCoord t = decode_tile(p, tile);
+        if (t.n != cur_img) {
+          kvctx_flush(p, cur_img, quad, lane, cacc);
+          cur_img = t.n;
+        }
+        mbar_wait(&tmem_full[group], acc_phase);
+        tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + group * kAccStride;
+        kvctx_tile(p, t, tmem_acc, row, quad, lane, group, stg, cacc, &tmem_empty[group]);
+        acc_phase ^= 1;
+      }
+      kvctx_flush(p, cur_img, quad, lane, cacc);
+    } else
     for (int tile = tile_begin + group; tile < tile_end; tile += 2) {
       const TileCoord t = decode_tile(p, tile);
       if (FILM) {
@@ -686,7 +806,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       if (lane == 0) mbar_arrive(&tmem_empty[group]);
       acc_phase ^= 1;
     }
-    if (stg && gthread == 0) tma_store_wait_read();   // shared memory must outlive the last bulk store's reads
+    if (EPI != KE_KVCTX && stg && gthread == 0) tma_store_wait_read();   // smem must outlive the last bulk store's reads
   }
 
   tc_fence_before();
@@ -708,6 +828,7 @@ inline ConvKernelFn pick_conv_kernel(int epi, int act, bool film, bool nchw) {
   if (epi == DAC_EPI_GEGLU) return conv_igemm_kernel<KE_GEGLU, DAC_ACT_NONE, false>;
   if (epi == DAC_EPI_LN) return conv_igemm_kernel<KE_LN, DAC_ACT_NONE, false>;
   if (epi == DAC_EPI_QKV) return conv_igemm_kernel<KE_QKV, DAC_ACT_NONE, false>;
+  if (epi == DAC_EPI_KVCTX) return conv_igemm_kernel<KE_KVCTX, DAC_ACT_NONE, false>;
   if (act == DAC_ACT_SILU)
     return film ? conv_igemm_kernel<KE_PLAIN, DAC_ACT_SILU, true> : conv_igemm_kernel<KE_PLAIN, DAC_ACT_SILU, false>;
   if (act == DAC_ACT_GELU && !film) return conv_igemm_kernel<KE_PLAIN, DAC_ACT_GELU, false>;

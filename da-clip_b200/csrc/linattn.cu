@@ -19,13 +19,6 @@ constexpr int kLaP = 64;                 // pixels per sub-tile
 constexpr int kLaPitch = kLaP + 8;       // bf16 pitch of the transposed [channel][pixel] tiles
 constexpr int kPartial = 32 * 32 + 64;
 
-__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-
 // One CTA (4 warps) per (pixel slab, head, image).  k and v arrive PLANAR ([B][256][hw], pixel-contiguous channel
 // rows - written that way by the QKV epilogue), so a (channel, 16-pixel quarter) thread loads its 32 bytes of k and
 // of v straight from global memory: running column max / rescale / exp / row sums on k, then both go to shared

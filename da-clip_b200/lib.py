@@ -44,6 +44,7 @@ class ConvDesc(C.Structure):
         ("stats_out", C.c_void_p), ("stats_eps", C.c_float),
         ("ln_stats", C.c_void_p), ("ln_colsum", C.c_void_p),
         ("out_nchw", C.c_void_p), ("out_nchw_c", C.c_int32), ("out_nchw_h", C.c_int32), ("out_nchw_w", C.c_int32),
+        ("kv_shift", C.c_void_p), ("ctx_acc", C.c_void_p),
     ]
 
 
@@ -54,7 +55,7 @@ class EmbedWeights(C.Structure):
         ("nf", C.c_int32), ("time_dim", C.c_int32), ("ctx_dim", C.c_int32), ("F", C.c_int32)]
 
 
-EPI_PLAIN, EPI_GEGLU, EPI_LN, EPI_QKV = 0, 1, 2, 3
+EPI_PLAIN, EPI_GEGLU, EPI_LN, EPI_QKV, EPI_KVCTX = 0, 1, 2, 3, 4
 ACT_NONE, ACT_SILU, ACT_GELU = 0, 1, 2
 
 # every symbol include/dac_b200.h declares: (restype, argtypes)

@@ -142,7 +142,7 @@ class ConvPlan:
                  out_nchw=None,
                  per_image_w=False, block_n=None, weight_override=None, tile=None, share_taps=True,
                  rsrc0=None, rc0=0, rsrc1=None, rc1=0, rweight=None, stats_out=None, stats_eps=1e-5,
-                 ln_stats=None, ln_colsum=None):
+                 ln_stats=None, ln_colsum=None, kv_shift=None, ctx_acc=None):
         L.require_cuda(src0)
         lib = L.load()
         d = L.ConvDesc()
@@ -201,6 +201,8 @@ class ConvPlan:
             d.stats_out, d.stats_eps = stats_out.data_ptr(), stats_eps
         if ln_stats is not None:
             d.ln_stats, d.ln_colsum = ln_stats.data_ptr(), ln_colsum.data_ptr()
+        if kv_shift is not None:     # EPI_KVCTX: k | v reduced into the LinearAttention context in the epilogue
+            d.kv_shift, d.ctx_acc = kv_shift.data_ptr(), ctx_acc.data_ptr()
         if out_nchw is not None:
             d.out_nchw = out_nchw.data_ptr()
             d.out_nchw_c, d.out_nchw_h, d.out_nchw_w = out_nchw.shape[1], out_nchw.shape[2], out_nchw.shape[3]
@@ -210,7 +212,7 @@ class ConvPlan:
         L.check(lib.dac_conv_create(C.byref(d), C.byref(h)))
         self.handle = h
         self._lib = lib
-        self._keep += (rsrc0, rsrc1, rweight, stats_out, ln_stats, ln_colsum)
+        self._keep += (rsrc0, rsrc1, rweight, stats_out, ln_stats, ln_colsum, kv_shift, ctx_acc)
         self.flops = 2.0 * B * OH * OW * pw.ngroups * len(pw.taps[0]) * (c0 + c1) * pw.cout \
             + 2.0 * B * OH * OW * (rc0 + rc1) * pw.cout * (rsrc0 is not None)
 

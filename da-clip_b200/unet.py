@@ -8,6 +8,8 @@ PyTorch op on activations: it repacks the weights once (bf16, tap-major, K-major
 given (batch, H, W) - every buffer preallocated, every TMA descriptor baked - captures the plan in a CUDA graph
 and replays it.  No CPU fallback.
 """
+import math
+
 import torch
 import torch.nn as nn
 
@@ -292,6 +294,12 @@ class PackedUNet:
             if dim > 256:
                 raise NotImplementedError("LinearAttention with more than 256 channels (fused LN epilogue limit)")
             wq = f32(q + "to_qkv.weight").reshape(384, dim) * a["pre_g"][None, :]      # W' = W diag(g)
+            # fused k|v -> context path: exp(k - c_d) with the data-independent bound c_d = ||W'_k[d]|| sqrt(C) >= |k_d|
+            # (the gain-free LayerNorm output has norm <= sqrt(C)); safe in fp32 while c_d <= 40 (range [-80, 0])
+            wk = wq[128:256].to(torch.bfloat16).float()
+            kbound = 1.02 * wk.norm(dim=1) * math.sqrt(dim)
+            a.update(q=ops.pack_linear(wq[:128].contiguous()), kv=ops.pack_linear(wq[128:].contiguous()),
+                     kv_shift=(kbound * 1.4426950408889634).contiguous(), kv_safe=bool(kbound.max().item() <= 40.0))
             a.update(qkv=ops.pack_linear(wq),
                      qkv_colsum=wq.to(torch.bfloat16).float().sum(dim=1).contiguous(),      # of the bf16 operand
                      out=ops.pack_linear(f32(q + "to_out.0.weight")),
@@ -396,6 +404,7 @@ class UNetEngine:
     # producer +14 us vs the 54 us LayerNorm kernel saved): the QKV epilogue is already the bottleneck of that
     # store-bound layer.  Kept as a tested option (tests/test_kernels_gpu.py::test_prenorm_folded_into_qkv).
     FOLD_PRENORM = False
+    FUSE_KVCTX = True      # LinearAttention: reduce k | v into the context inside the to_kv GEMM epilogue
 
     def needs_stats(self, prefix):
         """True if the attention layer `prefix` consumes per-pixel LayerNorm statistics from its producer."""
@@ -409,6 +418,21 @@ class UNetEngine:
             # PreNorm is folded around to_qkv: raw x in, gain-folded weights, rstd * (acc - mean * colsum) in the
             # epilogue with the {mean, rstd} the producing ResBlock wrote; no normalised tensor, no LayerNorm launch
             q = self.buf(B, h, w, 128)                  # softmaxed queries, NHWC (A operand of the to_out GEMM)
+            c_pad = a["out"].w.shape[-2]
+            if self.FUSE_KVCTX and stats is None and a["kv_safe"]:
+                # k | v never reach memory: the KVCTX epilogue reduces them into {C, S} per (image, head)
+                xn = self.buf(B, h, w, C)
+                self.add(prefix + "prenorm", lambda: ops.layernorm_rows(x, xn, B * hw, C, None, None, 1e-5))
+                ctx = self.buf(B, 4, 1, 32 * 34, dtype=torch.float32)
+                self.conv(prefix + "to_kv", xn, C, a["kv"], None, h, w, epi=L.EPI_KVCTX, block_n=256,
+                          kv_shift=a["kv_shift"], ctx_acc=ctx)
+                self.conv(prefix + "to_q", xn, C, a["q"], q, h, w, epi=L.EPI_QKV, block_n=128)
+                weff = self.buf(B, c_pad, 128)
+                self.add(prefix + "fold", lambda: ops.linattn_fold(ctx, B, hw, 1, a["w_out"], C, c_pad, weff))
+                self.flops += 2.0 * B * 4 * 32 * 32 * hw
+                self.conv(prefix + "to_out", q, 128, a["out"], out, h, w, epi=L.EPI_LN, bias=a["b_out"],
+                          ln_g=a["g_out"], res=x, per_image_w=True, weight_override=weff)
+                return out
             kv = self.buf(B, 256, h, w)                 # k | v, planar: pixel-contiguous rows for the context pass
             if stats is not None:
                 self.conv(prefix + "to_qkv", x, C, a["qkv"], q, h, w, epi=L.EPI_QKV, block_n=128, out_planar=kv,
@@ -419,7 +443,6 @@ class UNetEngine:
                 self.conv(prefix + "to_qkv", xn, C, a["qkv"], q, h, w, epi=L.EPI_QKV, block_n=128, out_planar=kv)
             nchunks = max(1, min(128, (148 * 8) // (B * 4), hw // 256))
             partial = self.buf(B, 4, nchunks, 32 * 34, dtype=torch.float32)
-            c_pad = a["out"].w.shape[-2]
             weff = self.buf(B, c_pad, 128)
             self.add(prefix + "context", lambda: ops.linattn_context(kv, B, hw, nchunks, partial))
             self.add(prefix + "fold", lambda: ops.linattn_fold(partial, B, hw, nchunks, a["w_out"], C, c_pad, weff))

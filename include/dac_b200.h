@@ -64,9 +64,15 @@ enum {
   DAC_EPI_PLAIN = 0,  /* out = act(film(acc + bias)) + res                                   MU:115-153 */
   DAC_EPI_GEGLU = 1,  /* tile cols [0,bn/2) value, [bn/2,bn) gate: out = v * gelu(g)        ATT:37-44 */
   DAC_EPI_LN = 2,     /* out = LN_c(acc + bias) * g + res   (single N tile)                 MU:77-86,166-168 */
-  DAC_EPI_QKV = 3     /* N-tile 0: per-32-col softmax * 32^-0.5 (q) -> out NHWC [.,128]; N-tiles 1,2: raw k, v
+  DAC_EPI_QKV = 3,    /* N-tile 0: per-32-col softmax * 32^-0.5 (q) -> out NHWC [.,128]; N-tiles 1,2: raw k, v
                          written PLANAR to out_planar [B][256][H][W] (pixel-contiguous rows, the layout the
-                         context reduction consumes without a transpose)                     MU:170-177 */
+                         context reduction consumes without a transpose).  cout 128 = q only. MU:170-177 */
+  DAC_EPI_KVCTX = 4   /* cout 256 = k | v of LinearAttention, NEVER written to memory: the epilogue forms
+                         P = exp(k - kv_shift[d]) and accumulates C[h][d][e] += sum_pixels P[d] v[e] and
+                         S[h][d] += sum_pixels P[d] on the warp tensor cores, then adds them into ctx_acc
+                         (one {C[32][32], m[32] = 0, S[32]} record per (image, head) - the partial format of
+                         dac_linattn_fold with nchunks = 1).  kv_shift is a data-independent upper bound of k
+                         (|k_d| <= ||W_k[d]|| sqrt(C) after the gain-free PreNorm), times log2(e)  MU:170-177 */
 };
 enum { DAC_ACT_NONE = 0, DAC_ACT_SILU = 1, DAC_ACT_GELU = 2 };
 
@@ -118,6 +124,7 @@ typedef struct dac_conv_desc {
   float* stats_out; float stats_eps;              /* [B*OH*OW][2] fp32 */
   const float* ln_stats; const float* ln_colsum;  /* QKV: [B*OH*OW][2], [cout] */
   float* out_nchw; int32_t out_nchw_c, out_nchw_h, out_nchw_w; /* alt. fp32 NCHW output (final_conv), cropped */
+  const float* kv_shift; float* ctx_acc;          /* KVCTX: [128] shift * log2(e); [B][4][1088] fp32 (zeroed by launch) */
 } dac_conv_desc;
 
 typedef struct dac_conv_plan* dac_conv_t;

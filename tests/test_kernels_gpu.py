@@ -302,6 +302,41 @@ def test_linear_attention_block(ops, gen, B, H, W, C):
     assert_close_bf16(nchw(out), ref, f"linear attention {H}x{W} C={C}", rel=2 ** -5, abs_=2e-2)
 
 
+@pytest.mark.parametrize("B,H,W,C", [(3, 32, 32, 64), (2, 24, 40, 128), (2, 16, 16, 256), (5, 72, 56, 64)])
+def test_linear_attention_fused_kv_context(ops, gen, B, H, W, C):
+    """KVCTX epilogue: k | v are reduced into the per-(image, head) context inside the GEMM epilogue with the
+    data-independent shift c_d = ||W_k[d]|| sqrt(C); checked through the fold against softmax_pixels(k) v^T / hw in
+    fp32 (module_util.py:170-177), on ragged sizes (masked tile rows) and several images per CTA (flushes)."""
+    from daclip_b200 import lib as L
+    hw = H * W
+    x = rnd(gen, B, C, H, W) * 1.7 + 0.3
+    xn = (x - x.mean(1, keepdim=True)) * torch.rsqrt(x.var(1, unbiased=False, keepdim=True) + 1e-5)
+    xh = nhwc(xn)
+    wkv = rnd(gen, 256, C, scale=C ** -0.5)
+    wkv[:128] *= 1.5                                           # a wider softmax than unit-variance logits
+    w_out = rnd(gen, C, 128, scale=128 ** -0.5)
+    wk = bf(wkv[:128]).float()
+    shift = (1.02 * wk.norm(dim=1) * math.sqrt(C))
+    assert shift.max().item() <= 40
+    ctx = torch.full((B, 4, 1, 32 * 34), float("nan"), device="cuda")
+    plan = ops.ConvPlan(xh, C, ops.pack_linear(wkv), None, B=B, H=H, W=W, epi=L.EPI_KVCTX, block_n=256,
+                        kv_shift=(shift * 1.4426950408889634).contiguous(), ctx_acc=ctx)
+    c_pad = ops.choose_block_n(C)[1]
+    weff = torch.zeros(B, c_pad, 128, device="cuda", dtype=torch.bfloat16)
+    for _ in range(2):                                         # relaunch: the accumulator is re-zeroed every time
+        plan.run()
+    ops.linattn_fold(ctx, B, hw, 1, w_out, C, c_pad, weff)
+    torch.cuda.synchronize()
+    kvr = F.conv2d(nchw(xh), bf(wkv).float()[:, :, None, None]).reshape(B, 2, 4, 32, hw)
+    k, v = kvr[:, 0].softmax(-1), kvr[:, 1] / hw
+    ctx_ref = torch.einsum("bhdn,bhen->bhde", k, v)            # [B, 4, 32, 32]
+    got = ctx[:, :, 0, :1024].reshape(B, 4, 32, 32) / (ctx[:, :, 0, 1056:1088, None] * hw)
+    scale = ctx_ref.abs().max().item()
+    assert (got - ctx_ref).abs().max().item() <= 6e-3 * scale, (got - ctx_ref).abs().max().item() / scale
+    weff_ref = torch.einsum("che,bhde->bchd", w_out.reshape(C, 4, 32), ctx_ref).reshape(B, C, 128)
+    assert_close_bf16(weff[:, :C], weff_ref, "folded context weight", rel=2 ** -6, abs_=1e-2)
+
+
 @pytest.mark.parametrize("B,H,W,C", [(2, 32, 32, 64), (1, 16, 48, 128), (1, 16, 16, 256)])
 def test_prenorm_folded_into_qkv(ops, gen, B, H, W, C):
     """PreNorm (channel LayerNorm, gain only) folded around to_qkv: the producer writes per-pixel {mean, rstd} of its
