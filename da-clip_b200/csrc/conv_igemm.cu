@@ -262,7 +262,8 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
     pl->mapOut2 = pl->mapOut;
     pl->mapRes = pl->mapOut;
     // bf16 residual through TMA: same box as the output tile, landed in the staging tile before the epilogue runs
-    if (rc == 0 && d->res && d->epi == DAC_EPI_PLAIN && d->cout == d->cout_pad && !getenv("DAC_NO_TMA_RES")) {
+    if (rc == 0 && d->res && (d->epi == DAC_EPI_PLAIN || d->epi == DAC_EPI_LN) && d->cout == d->cout_pad &&
+        !getenv("DAC_NO_TMA_RES")) {
       cuuint64_t rd[4] = {(cuuint64_t)d->cout, (cuuint64_t)k.OWf, (cuuint64_t)k.OHf, (cuuint64_t)d->B};
       cuuint64_t rs[3] = {(cuuint64_t)d->res_ld * 2, (cuuint64_t)k.OWf * d->res_ld * 2,
                           (cuuint64_t)k.OHf * k.OWf * d->res_ld * 2};

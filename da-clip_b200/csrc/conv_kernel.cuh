@@ -257,8 +257,64 @@ __device__ __forceinline__ void epilogue_tile(const ConvKParams& p, const TileCo
   }
 
   if (EPI == KE_LN) {
-    // channel LayerNorm over the whole (single) N tile: three sweeps over this row's TMEM columns.
     const int C = p.cout;
+    if (C == 64) {
+      // the whole row (2 chunks) lives in registers: ONE sweep of TMEM loads (issued back to back, one wait),
+      // mean and centred variance from registers, then normalise / residual / store
+      float w[2][32];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        {
+          uint32_t r[32];
+          tmem_ld32(tmem_acc + k * 32, r);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) w[k][j] = __uint_as_float(r[j]);
+        }
+      }
+      tmem_ld_wait();
+      float sum = 0.f;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        {
+          if (p.bias) chunk_add_f32(p.bias + k * 32, w[k]);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sum += w[k][j];
+        }
+      }
+      const float mean = sum / C;
+      float ss = 0.f;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            w[k][j] -= mean;
+            ss = fmaf(w[k][j], w[k][j], ss);
+          }
+        }
+      }
+      const float rstd = rsqrtf(ss / C + p.ln_eps);
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        {
+          const int c = k * 32;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 g = __ldg(reinterpret_cast<const float4*>(p.ln_g + c) + q);
+            w[k][4 * q] *= rstd * g.x;
+            w[k][4 * q + 1] *= rstd * g.y;
+            w[k][4 * q + 2] *= rstd * g.z;
+            w[k][4 * q + 3] *= rstd * g.w;
+          }
+          if (p.res_tma) chunk_add_staged(stg, row, c, w[k]);
+          else if (valid && p.res) chunk_add_bf16(p.res + opix * p.res_ld + c, w[k]);
+          if (stg) chunk_stage_bf16(stg, row, c, w[k]);
+          else if (valid) chunk_store_bf16(p.out + opix * p.out_ld + p.out_coff + c, w[k]);
+        }
+      }
+      return;
+    }
+    // wider rows (C = 128, 256): three sweeps over this row's TMEM columns
     float sum = 0.f;
     for (int c = 0; c < C; c += 32) {
       chunk_from_tmem(tmem_acc + c, v);
@@ -289,7 +345,8 @@ __device__ __forceinline__ void epilogue_tile(const ConvKParams& p, const TileCo
         v[4 * q + 2] = (v[4 * q + 2] - mean) * rstd * g.z;
         v[4 * q + 3] = (v[4 * q + 3] - mean) * rstd * g.w;
       }
-      if (valid && p.res) chunk_add_bf16(p.res + opix * p.res_ld + c, v);
+      if (p.res_tma) chunk_add_staged(stg, row, c, v);
+      else if (valid && p.res) chunk_add_bf16(p.res + opix * p.res_ld + c, v);
       if (stg) chunk_stage_bf16(stg, row, c, v);
       else if (valid) chunk_store_bf16(p.out + opix * p.out_ld + p.out_coff + c, v);
     }
@@ -341,9 +398,10 @@ __device__ __forceinline__ void epilogue_tile(const ConvKParams& p, const TileCo
 #pragma unroll
         for (int j = 1; j < 32; ++j) m = fmaxf(m, v[j]);
         float s = 0.f;
+        const float ml = m * 1.4426950408889634f;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          v[j] = exp2f((v[j] - m) * 1.4426950408889634f);
+          v[j] = ex2_approx(fmaf(v[j], 1.4426950408889634f, -ml));
           s += v[j];
         }
         const float inv = __fdividef(0.17677669529663687f, s);

@@ -14,6 +14,9 @@ CASES = {
     "l3_3x3": (16, 32, 32, 512, 512, "3x3"),
     "l3_geglu": (16, 32, 32, 512, 4096, "geglu"),
     "l0_1x1": (16, 256, 256, 128, 64, "1x1"),
+    "l0_q": (16, 256, 256, 64, 128, "q"),
+    "l0_kv": (16, 256, 256, 64, 256, "kv"),
+    "l0_toout": (16, 256, 256, 128, 64, "toout"),
 }
 
 def make(name):
@@ -31,6 +34,23 @@ def make(name):
         q = torch.zeros(B, H, W, 128, device="cuda", dtype=torch.bfloat16)
         kv = torch.zeros(B, 256, H, W, device="cuda", dtype=torch.bfloat16)
         plan = ops.ConvPlan(x, cin, ops.pack_linear(w), q, B=B, H=H, W=W, epi=L.EPI_QKV, block_n=128, out_planar=kv)
+    elif kind == "q":
+        w = torch.randn(cout, cin, device="cuda", generator=g) * cin ** -0.5
+        q = torch.zeros(B, H, W, 128, device="cuda", dtype=torch.bfloat16)
+        plan = ops.ConvPlan(x, cin, ops.pack_linear(w), q, B=B, H=H, W=W, epi=L.EPI_QKV, block_n=128)
+    elif kind == "kv":
+        w = torch.randn(cout, cin, device="cuda", generator=g) * cin ** -0.5
+        shift = torch.full((128,), 12.0, device="cuda")
+        ctx = torch.zeros(B, 4, 1, 32 * 34, device="cuda")
+        plan = ops.ConvPlan(x, cin, ops.pack_linear(w), None, B=B, H=H, W=W, epi=L.EPI_KVCTX, block_n=256,
+                            kv_shift=shift, ctx_acc=ctx)
+    elif kind == "toout":
+        w = torch.randn(cout, cin, device="cuda", generator=g) * cin ** -0.5
+        weff = (torch.randn(B, cout, cin, device="cuda", generator=g) * cin ** -0.5).to(torch.bfloat16)
+        res = torch.randn(B, H, W, cout, device="cuda", generator=g).to(torch.bfloat16)
+        plan = ops.ConvPlan(x, cin, ops.pack_linear(w), out, B=B, H=H, W=W, epi=L.EPI_LN,
+                            bias=torch.zeros(cout, device="cuda"), ln_g=torch.ones(cout, device="cuda"), res=res,
+                            per_image_w=True, weight_override=weff)
     elif kind == "geglu":
         w = torch.randn(cout, cin, device="cuda", generator=g) * cin ** -0.5
         b = torch.randn(cout, device="cuda", generator=g)
