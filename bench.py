@@ -12,6 +12,7 @@ Prints ONE JSON line (rank 0).
 """
 import argparse
 import json
+import re
 import os
 import subprocess
 import sys
@@ -128,6 +129,68 @@ def conv_time_per_eval(eng, reps=3):
                     sorted(((a.elapsed_time(b), n) for n, a, b in evs), reverse=True)[:12],
                     [(n, a.elapsed_time(b)) for n, a, b in evs])
     return best
+
+
+# the "ConditionalUNet convs" sub-roofline of the north_star = every nn.Conv2d of the module
+# (3x3 205.58 + 1x1 23.89 + 4x4 4.29 + 7x7 2.47 GFLOP per 256^2 image); the spatial subset leaves out the 1x1
+# to_qkv / to_out / proj_in / proj_out layers, whose cost is their softmax / LayerNorm / context epilogues.
+CONV2D_GFLOP = {256: 236.23}
+SPATIAL_GFLOP = {256: 205.58 + 8.05 + 4.29 + 2.47}
+_SPATIAL = re.compile(r"block[12]$|res_conv$|^init_conv$|^final_conv$|^(downs|ups)\.\d\.3$")
+_POINTWISE = re.compile(r"(?<!attn1)\.(to_q|to_kv|to_qkv|to_out|proj_in|proj_out)$")
+
+
+def conv_subroofline(layers, B, S, peak_tf):
+    sp = sum(ms for n, ms in layers if _SPATIAL.search(n))
+    pw = sum(ms for n, ms in layers if _POINTWISE.search(n))
+    scale = (S / 256) ** 2 * B
+    out = {}
+    if sp > 0:
+        tf = SPATIAL_GFLOP[256] * scale / sp
+        out["spatial_convs"] = {"gflop": round(SPATIAL_GFLOP[256] * scale, 1), "ms": round(sp, 3),
+                                "tflops": round(tf, 1), "frac": round(tf / peak_tf, 4)}
+    if sp + pw > 0:
+        tf = CONV2D_GFLOP[256] * scale / (sp + pw)
+        out["all_conv2d"] = {"gflop": round(CONV2D_GFLOP[256] * scale, 1), "ms": round(sp + pw, 3),
+                             "tflops": round(tf, 1), "frac": round(tf / peak_tf, 4)}
+    return out
+
+
+def library_baseline(dev, B, S, mode, evals=5):
+    """The 'library kernel' bar: the same algorithm as plain PyTorch ops (cuDNN / cuBLAS) ON THE GPU -
+    the oracle restatement moved to the device, fp32 and bf16 autocast - timed with CUDA events.  A baseline leg only:
+    nothing here is reachable from the product path."""
+    from daclip_b200 import synthetic
+    from oracle import sde_oracle as So
+    from oracle import unet_oracle as O
+    sd, kw = synthetic.unet_state_dict(0)
+    sd = {k: v.to(dev) for k, v in sd.items()}
+    cfg = O.UNetConfig(**kw)
+    inp = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in
+           synthetic.restoration_inputs(B, S, S, T=2, seed=100).items()}
+    sch = So.Schedule(50, T_STEPS, "cosine", 0.005)
+    den = O.make_denoiser(sd, cfg)
+    step = So.posterior_step if mode == "posterior" else So.sde_step
+    out = {}
+    for label, ctx in (("fp32", torch.autocast("cuda", enabled=False)),
+                       ("bf16_autocast", torch.autocast("cuda", dtype=torch.bfloat16))):
+        x = inp["lq"] + inp["eps0"] * sch.max_sigma
+        times = []
+        with torch.no_grad(), ctx:
+            for i in range(evals + 2):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                n = den(x, inp["lq"], float(T_STEPS - i), text_context=inp["text_context"],
+                        image_context=inp["image_context"])
+                x = step(sch, x, inp["lq"], n.float(), inp["noise"][i % 2], T_STEPS - i)
+                b.record()
+                torch.cuda.synchronize()
+                times.append(a.elapsed_time(b))
+        ms = sorted(times[2:])[len(times[2:]) // 2]
+        out[label] = {"ms_per_denoiser_step": round(ms, 3), "images_per_s": round(B / (ms * T_STEPS / 1e3), 3)}
+    out["what"] = (f"oracle restatement as eager PyTorch {torch.__version__} ops (cuDNN/cuBLAS) on the same GPU, "
+                   f"batch {B} at {S}x{S}, median of {evals} denoiser+update steps after 2 warm-ups, x{T_STEPS}")
+    return out
 
 
 def run_product(args):
@@ -252,6 +315,9 @@ def run_product(args):
             "gpu_launches": int(K * T_STEPS * launches_per_eval),
             "clocks": clocks.summary(),
         }
+        result["roofline"]["unet_convs"] = conv_subroofline(layers, B, S, peak_tf)
+        if world == 1 and args.library_baseline:
+            result["library_baseline"] = library_baseline(dev, B, S, args.mode)
         if world == 1 and not args.no_cpu_baseline:
             result["cpu_baseline"] = cpu_baseline(S, args.mode, batch=1, evals=args.cpu_evals)
         print(json.dumps(result), flush=True)
@@ -336,6 +402,8 @@ def main():
     ap.add_argument("--mode", default="posterior", choices=["posterior", "sde"])
     ap.add_argument("--cpu-evals", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--library-baseline", action="store_true",
+                    help="also time the oracle restatement as eager PyTorch (cuDNN/cuBLAS) on the GPU")
     ap.add_argument("--dump-layers", default=None, help="write the per-launch CUDA-event times of one evaluation here")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -75,16 +75,11 @@ static int elementwise_grid(int64_t work_items) {
 __global__ void __launch_bounds__(256) stem_input_kernel(const float* __restrict__ xt, const float* __restrict__ cond,
                                                          __nv_bfloat16* __restrict__ out, int B, int H, int W, int Hp,
                                                          int Wp) {
-  // one thread per (pixel, kx): 8 channels = one 16 B store
-  const int64_t total = static_cast<int64_t>(B) * Hp * Wp * 8;
-  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int kx = static_cast<int>(i & 7);
-    int64_t pix = i >> 3;
-    const int x = static_cast<int>(pix % Wp);
-    pix /= Wp;
-    const int y = static_cast<int>(pix % Hp);
-    const int b = static_cast<int>(pix / Hp);
+  // one thread per (pixel, kx): 8 channels = one 16 B store; grid = (x blocks, row, image): no index division
+  const int y = blockIdx.y, b = blockIdx.z;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Wp * 8; i += gridDim.x * blockDim.x) {
+    const int kx = i & 7;
+    const int x = i >> 3;
     float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     const int xs = x + kx - 3;
     if (kx < 7 && xs >= 0 && xs < Wp) {
@@ -104,7 +99,7 @@ __global__ void __launch_bounds__(256) stem_input_kernel(const float* __restrict
     u.y = pack_bf16(v[2], v[3]);
     u.z = pack_bf16(v[4], v[5]);
     u.w = pack_bf16(v[6], v[7]);
-    reinterpret_cast<uint4*>(out)[i] = u;
+    reinterpret_cast<uint4*>(out)[(static_cast<int64_t>(b) * Hp + y) * Wp * 8 + i] = u;
   }
 }
 
@@ -457,8 +452,9 @@ extern "C" int dac_unet_stem_input(const float* xt, const float* cond, void* out
                                    dac_stream_t stream) {
   if (!xt || !cond || !out) return set_error(-1, "dac_unet_stem_input: null argument");
   if (Hp < H || Wp < W || Hp - H >= H || Wp - W >= W) return set_error(-2, "dac_unet_stem_input: bad padding");
-  const int64_t total = static_cast<int64_t>(B) * Hp * Wp * 8;
-  stem_input_kernel<<<elementwise_grid(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  if (Hp > 65535 || B > 65535) return set_error(-2, "dac_unet_stem_input: Hp and B must be < 65536");
+  stem_input_kernel<<<dim3(static_cast<unsigned>(ceil_div(static_cast<int64_t>(Wp) * 8, 256)), Hp, B), 256, 0,
+                      static_cast<cudaStream_t>(stream)>>>(
       xt, cond, static_cast<__nv_bfloat16*>(out), B, H, W, Hp, Wp);
   return check_launch("stem_input_kernel");
 }

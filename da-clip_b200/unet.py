@@ -586,6 +586,31 @@ class UNetEngine:
         for _, fn in self.steps:
             fn()
 
+    def _run_forked(self):
+        """Capture order: the FiLM table (time MLP -> every ResBlock's scale/shift; a latency-bound chain of tiny
+        launches) runs on a side branch of the graph, beside stem_input + init_conv which do not need it."""
+        main = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        fork, join = torch.cuda.Event(), torch.cuda.Event()
+        independent = ("stem_input", "init_conv")
+        fork.record(main)
+        side.wait_event(fork)
+        with torch.cuda.stream(side):
+            for name, fn in self.steps:
+                if name == "time_film":
+                    fn()
+        join.record(side)
+        joined = False
+        for name, fn in self.steps:
+            if name == "time_film":
+                continue
+            if not joined and name not in independent:
+                main.wait_event(join)
+                joined = True
+            fn()
+        if not joined:
+            main.wait_event(join)
+
     def run_named(self):
         """Eager run yielding after each launch (debugging / per-layer timing)."""
         for name, fn in self.steps:
@@ -598,7 +623,7 @@ class UNetEngine:
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self.run_eager()
+                self._run_forked()
             self.graph = g
         self.graph.replay()
 
