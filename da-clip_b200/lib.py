@@ -86,6 +86,10 @@ SYMBOLS = {
     "dac_vit_embed": (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _f, _p]),
     "dac_vit_pool": (C.c_int, [_p, _i32, _i32, _i32, _p, _p, _f, _p, _i32, _p, _p]),
     "dac_degradation_argmax": (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p, _p]),
+    "dac_clip_resample_h": (C.c_int, [_p, _i32, _i32, _p, _i32, _p, _p, _i32, _i32, _i32, _p]),
+    "dac_clip_resample_v_norm": (C.c_int, [_p, _i32, _i32, _p, _p, _i32, _i32, _i32, _i32,
+                                           C.POINTER(C.c_float), C.POINTER(C.c_float), _p, _p]),
+    "dac_tensor2img": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _f, _f, _p]),
 }
 
 

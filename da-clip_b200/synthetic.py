@@ -139,3 +139,17 @@ def restoration_inputs(B, H, W, T=100, seed=1, ctx_dim=512):
     text_ctx = torch.randn(B, ctx_dim, generator=g)
     image_ctx = torch.randn(B, ctx_dim, generator=g)
     return dict(lq=lq, eps0=eps0, noise=noise, text_context=text_ctx, image_context=image_ctx)
+
+
+def natural_image(h, w, seed=0):
+    """A seeded float32 HWC RGB test image in [0, 1] with both smooth structure and pixel-level detail (so that a
+    resampler's antialiasing taps and rounding all matter), as a numpy array - the form the reference's dataset hands
+    to clip_transform (data/LQGT_dataset.py:139-143)."""
+    import numpy as np
+    g = torch.Generator().manual_seed(seed)
+    yy = torch.linspace(0, 1, h).view(h, 1, 1)
+    xx = torch.linspace(0, 1, w).view(1, w, 1)
+    ph = torch.rand(3, generator=g).view(1, 1, 3) * 6.28
+    base = 0.5 + 0.35 * torch.sin(9.0 * xx + 5.0 * yy + ph) * torch.cos(7.0 * yy - 3.0 * xx + ph)
+    img = (base + 0.15 * torch.randn(h, w, 3, generator=g)).clamp(0, 1)
+    return np.ascontiguousarray(img.numpy().astype(np.float32))

@@ -198,6 +198,23 @@ int dac_vit_pool(const void* x, int32_t B, int32_t L, int32_t w, const float* ln
 int dac_degradation_argmax(const float* degra, const float* text, int32_t B, int32_t e, int32_t classes,
                            float* logits /*[B,classes] or NULL*/, int64_t* argmax, dac_stream_t stream);
 
+/* ------------------------------------------------------------------ image pre / post-processing
+ * clip_transform (universal-image-restoration/data/util.py:87-93): float RGB HWC image in [0,1] -> (uint8)(v*255) ->
+ * Pillow BICUBIC resize (antialiased, 8-bit fixed point: `bounds` [out][2] = {first tap, tap count}, `kk`
+ * [out][ksize] = coefficients * 2^22, computed on the host as Pillow's precompute_coeffs / normalize_coeffs_8bpc do)
+ * -> CenterCrop -> ToTensor -> Normalize.  Pass 1 resamples rows [y_first, y_first + rows) horizontally into the
+ * uint8 buffer `mid` [rows][Wout][3]; pass 2 resamples vertically, crops res x res at (top, left) and writes
+ * (x / 255 - mean) / std as fp32 [3][res][res].  Bit-exact against Pillow.  mean3 / std3 are HOST pointers. */
+int dac_clip_resample_h(const float* img, int32_t H, int32_t W, void* mid, int32_t Wout, const int32_t* bounds,
+                        const int32_t* kk, int32_t ksize, int32_t y_first, int32_t rows, dac_stream_t stream);
+int dac_clip_resample_v_norm(const void* mid, int32_t Wout, int32_t y_first, const int32_t* bounds, const int32_t* kk,
+                             int32_t ksize, int32_t top, int32_t left, int32_t res, const float* mean3,
+                             const float* std3, float* out, dac_stream_t stream);
+/* tensor2img (universal-image-restoration/utils/img_utils.py:136-163): x fp32 [B][C][H][W], C = 3 (RGB) or 1 ->
+ * uint8 [B][H][W][C], channels reversed (BGR): round_half_even((clamp(x, lo, hi) - lo) / (hi - lo) * 255). */
+int dac_tensor2img(const float* x, void* out, int32_t B, int32_t C, int32_t H, int32_t W, float lo, float hi,
+                   dac_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,78 @@
+"""GPU: the batched test driver gives, per image, what the reference's one-image-at-a-time loop
+(config/daclip-sde/test.py:101-130) gives through the same objects."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def stack(cuda):
+    from daclip_b200 import synthetic
+    from daclip_b200.daclip import DaCLIP
+    from daclip_b200.model import create_model
+    from daclip_b200.sde import IRSDE
+    sd, kw = synthetic.unet_state_dict(0)
+    opt = {"gpu_ids": [0], "is_train": False, "dist": False, "model": "denoising",
+           "network_G": {"which_model_G": "ConditionalUNet", "setting": dict(kw)},
+           "path": {"pretrain_model_G": None, "strict_load": True}}
+    model = create_model(opt)
+    model.load_state_dict_into_model(sd)
+    sde = IRSDE(max_sigma=50, T=100, schedule="cosine", eps=0.005, device=cuda)
+    sde.set_model(model.model)
+    clip = DaCLIP().load_reference_state_dict(synthetic.daclip_visual_state_dict(10)).to(cuda).eval()
+    return model, sde, clip
+
+
+def test_batched_driver_matches_per_image_loop(cuda, stack):
+    from daclip_b200 import imageio, synthetic
+    from daclip_b200.driver import BatchedRestorer
+    model, sde, clip = stack
+    sizes = [(48, 64), (32, 32), (48, 64), (48, 64), (32, 32)]
+    imgs = [synthetic.natural_image(h, w, seed=70 + i) for i, (h, w) in enumerate(sizes)]
+    g = torch.Generator().manual_seed(5)
+    per_image_noise = [torch.randn(101, 1, 3, h, w, generator=g) for h, w in sizes]   # [0] = the noise_state draw
+    text = torch.randn(10, 512, generator=g).cuda()
+
+    # reference-shaped loop, one image at a time (test.py:112-129), with injected noise
+    single = []
+    for im, nz in zip(imgs, per_image_noise):
+        lq = torch.from_numpy(im).permute(2, 0, 1)[None].cuda()
+        ic, dc = clip.encode_image(imageio.clip_transform(im)[None], control=True)
+        x_T = lq + nz[0].cuda() * sde.max_sigma
+        model.feed_data(x_T, lq, None, text_context=dc.float(), image_context=ic.float())
+        sde.set_mu(model.condition)
+        out = sde.reverse_posterior(model.state, noise=nz[1:].cuda(), text_context=dc.float(),
+                                    image_context=ic.float())
+        single.append((out[0], imageio.tensor2img(out), int(clip.degradation_argmax(dc.float(), text)[0])))
+
+    # batched: same noise, grouped by size in input order
+    class FixedNoiseSDE:
+        """Delegates to the IRSDE but replaces the noise_state draw with the injected one."""
+        def __init__(self, inner, draws):
+            self.inner, self.draws = inner, draws
+        def __getattr__(self, k):
+            return getattr(self.inner, k)
+        def noise_state(self, t):
+            return t + self.draws[(t.shape[2], t.shape[3])].to(t.device) * self.inner.max_sigma
+    noise, first = {}, {}
+    for hw in dict.fromkeys(sizes):
+        sel = [nz for s, nz in zip(sizes, per_image_noise) if s == hw]
+        first[hw] = torch.cat([nz[0] for nz in sel])
+        noise[hw] = torch.cat([nz[1:] for nz in sel], dim=1).cuda()
+    r = BatchedRestorer(model, FixedNoiseSDE(sde, first), clip, "posterior", max_batch=8, text_features=text)
+    res = r.restore(imgs, noise=noise)
+    assert len(res) == len(imgs)
+    for i, (o, u8, cls) in enumerate(single):
+        got = res[i]
+        assert got["Output"].shape == (sizes[i][0], sizes[i][1], 3) and got["Output"].dtype == np.uint8
+        err = (got["Output_tensor"] - o).abs().max().item()
+        assert err < 4e-3, f"image {i}: batched vs single max err {err}"       # GroupNorm fp32 atomics order
+        assert np.abs(got["Output"].astype(int) - u8.astype(int)).max() <= 1
+        assert got["degradation"] == cls
+
+    # max_batch splits a size group; no noise injection -> global RNG path runs
+    r2 = BatchedRestorer(model, sde, clip, "sde", max_batch=2)
+    res2 = r2.restore(imgs[:3])
+    assert all(np.isfinite(x["Output_tensor"].cpu().numpy()).all() for x in res2)
