@@ -49,7 +49,7 @@ struct dac_conv_plan {
 using namespace dac;
 
 static int encode_act_map(CUtensorMap* m, const void* ptr, int c, int ld, int W, int H, int B, int tile_w,
-                          int box_rows, int stride) {
+                          int box_rows, int stride) {   // tile_w = box width in pixels
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return set_error(-10, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
   cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
@@ -77,7 +77,11 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
   if (d->ndy < 1 || d->ncols < 1 || d->ndy * d->ncols != d->ntaps || (d->ndy > 1 && d->stride != 1))
     return set_error(-2, "dac_conv_create: column groups (%d x %d) must cover the %d taps; ndy > 1 needs stride 1",
                      d->ncols, d->ndy, d->ntaps);
-  const int a_rows = d->stride == 1 ? d->tile_h + d->ndy - 1 : d->tile_h;   // rows landed in shared memory
+  if (d->halo && (d->stride != 1 || d->ntaps != 9 || d->ndy != 9 || d->ncols != 1 || d->tile_w != 8 ||
+                  d->ngroups != 1 || d->halo > 2))
+    return set_error(-2, "dac_conv_create: halo loads need a 3x3 stride-1 conv, tile_w 8, ncols 1, ndy 9");
+  const int a_rows = d->halo ? d->tile_h + 2 : (d->stride == 1 ? d->tile_h + d->ndy - 1 : d->tile_h);
+  const int box_w = d->halo ? d->tile_w + 2 : d->tile_w;                    // rows x box_w pixels land in smem
   if (d->tile_w * d->stride > 256 || a_rows * d->stride > 256)
     return set_error(-2, "dac_conv_create: TMA box exceeds 256");
   if ((reinterpret_cast<uintptr_t>(d->src0) | reinterpret_cast<uintptr_t>(d->src1) |
@@ -172,8 +176,15 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
   k.r_chunks0 = fused_res ? d->rc0 / kChunkK : 0;
   k.r_chunks1 = fused_res ? d->rc1 / kChunkK : 0;
   k.r_a_bytes = (uint32_t)d->tile_h * d->tile_w * kChunkK * 2;
-  k.a_bytes = (uint32_t)a_rows * d->tile_w * kChunkK * 2;
-  k.row_shift = (uint32_t)d->tile_w * kChunkK * 2;
+  k.a_bytes = (uint32_t)a_rows * box_w * kChunkK * 2;
+  k.a_slot = (k.a_bytes + 1023u) & ~1023u;
+  k.a_sbo = d->halo ? (uint32_t)box_w * 128u : 1024u;          // halo, tile_w 8: one (padded) pixel row per 8-row group
+  k.halo = d->halo;
+  for (int i = 0; i < d->ndy; ++i) {
+    // tap i of a load: halo = (ky, kx) = (i / 3, i % 3) pixels into the haloed box; else i tile rows down
+    const uint32_t off = d->halo ? (uint32_t)((i / 3) * box_w + (i % 3)) * 128u : (uint32_t)i * d->tile_w * 128u;
+    k.tap_off[i] = (uint16_t)(off >> 4);
+  }
   k.cout = d->cout;
   pl->kernel = kernel;
   k.bias = d->bias; k.bias_img = d->bias_img;
@@ -199,9 +210,9 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
   const long long res_bytes = (long long)k.n_tiles * d->ntaps * chunks * k.b_bytes;
   const long long kv_extra = d->epi == DAC_EPI_KVCTX ? 2ll * kKvStageBytes : 0;   // P / V head tiles, both groups
   const bool resident = d->ngroups == 1 && !d->per_image_w && res_bytes <= 160 * 1024 &&
-                        (smem_budget - res_bytes - kv_extra) / (long long)k.a_bytes >= 3;
+                        (smem_budget - res_bytes - kv_extra) / (long long)k.a_slot >= 3;
   k.b_res_bytes = resident ? (uint32_t)res_bytes : 0u;
-  uint32_t stage_bytes = k.a_bytes + (resident ? 0u : (uint32_t)d->ndy * k.b_bytes);
+  uint32_t stage_bytes = k.a_slot + (resident ? 0u : (uint32_t)d->ndy * k.b_bytes);
   if (fused_res && stage_bytes < k.r_a_bytes + k.b_bytes) stage_bytes = k.r_a_bytes + k.b_bytes;
   // bf16 NHWC output through a swizzled staging tile + TMA store (coalesced, clipped by the tensor map) whenever the
   // staging tile leaves room for >= 3 pipeline stages; otherwise each thread stores its own row directly.
@@ -227,10 +238,10 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
   pl->smem = (int)k.b_res_bytes + stages * (int)stage_bytes + (int)stg_bytes * k.stg_count + 1024 + 256 + 4096;
   pl->tiles = k.ngroups * k.m_tiles * k.n_tiles;
 
-  int rc = encode_act_map(&pl->mapA0, d->src0, d->c0, d->ld0, d->W, d->H, d->B, d->tile_w, a_rows, d->stride);
+  int rc = encode_act_map(&pl->mapA0, d->src0, d->c0, d->ld0, d->W, d->H, d->B, box_w, a_rows, d->stride);
   if (rc == 0) {
     if (d->c1 > 0)
-      rc = encode_act_map(&pl->mapA1, d->src1, d->c1, d->ld1, d->W, d->H, d->B, d->tile_w, a_rows, d->stride);
+      rc = encode_act_map(&pl->mapA1, d->src1, d->c1, d->ld1, d->W, d->H, d->B, box_w, a_rows, d->stride);
     else
       pl->mapA1 = pl->mapA0;
   }

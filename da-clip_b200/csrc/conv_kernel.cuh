@@ -69,8 +69,11 @@ struct ConvKParams {
   int per_image_w;
   int stages;
   uint32_t b_bytes;        // one weight tile: block_n rows x 128 B
-  uint32_t a_bytes;        // one activation load: (tile_h + ndy - 1) * tile_w rows x 128 B
-  uint32_t row_shift;      // tile_w * 128 B: descriptor offset between vertically adjacent taps
+  uint32_t a_bytes;        // one activation load: (tile_h + ndy - 1) * tile_w rows x 128 B  (halo: (th+2)(tw+2) rows)
+  uint32_t a_slot;         // a_bytes rounded up to the 1024 B swizzle atom: where the streamed weight tiles start
+  uint32_t a_sbo;          // byte stride between the 8-pixel row groups of the activation operand (1024; halo: 1280)
+  uint16_t tap_off[16];    // descriptor start offset (16 B units) of tap i within the activation load
+  int halo;                // 1 / 2: nine taps from one haloed load (2: descriptor base_offset from the address)
   uint32_t b_res_bytes;    // > 0: the whole weight tensor stays resident in shared memory
   int r_chunks0, r_chunks1;   // fused 1x1 skip conv: K chunks of its two sources (0, 0 = none)
   uint32_t r_a_bytes;         // its activation tile: tile_h * tile_w rows x 128 B
@@ -585,8 +588,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   uint8_t* b_res = smem;
   uint8_t* ring = smem + p.b_res_bytes;
   const int r_chunks = p.r_chunks0 + p.r_chunks1;
-  const uint32_t main_tx = p.a_bytes + (b_resident ? 0u : static_cast<uint32_t>(p.ndy) * p.b_bytes);  // bytes per K step
-  uint32_t stage_bytes = main_tx;
+  const uint32_t b_stream = b_resident ? 0u : static_cast<uint32_t>(p.ndy) * p.b_bytes;
+  const uint32_t main_tx = p.a_bytes + b_stream;   // bytes landing per K step
+  uint32_t stage_bytes = p.a_slot + b_stream;
   if (r_chunks && stage_bytes < p.r_a_bytes + p.b_bytes) stage_bytes = p.r_a_bytes + p.b_bytes;
   uint8_t* stg_base = p.stg_bytes ? ring + static_cast<size_t>(p.stages) * stage_bytes : nullptr;
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + static_cast<size_t>(p.stages) * stage_bytes +
@@ -676,7 +680,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
             tma_load_4d(sa, mapA, &full[stage], ccoord, xin + p.col_dx[t.g][j], yin + p.col_dy0[t.g][j], t.n);
             if (!b_resident) {
               for (int i = 0; i < p.ndy; ++i)
-                tma_load_3d(sa + p.a_bytes + static_cast<size_t>(i) * p.b_bytes, &mapW, &full[stage], ck * kChunkK,
+                tma_load_3d(sa + p.a_slot + static_cast<size_t>(i) * p.b_bytes, &mapW, &full[stage], ck * kChunkK,
                             ncoord, zbase + p.col_tap[t.g][j * p.ndy + i]);
             }
             if (++stage == p.stages) {
@@ -709,9 +713,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     {
       const uint32_t idesc = make_idesc_bf16(kTileM, p.block_n);
       const uint64_t desc_fixed = make_sw128_desc(0);                 // every field except the start address
+      const uint64_t desc_fixed_a = make_sw128_desc(0, p.a_sbo);
       const uint32_t ring_lo = (smem_u32(ring) & 0x3FFFF) >> 4;
       const uint32_t bres_lo = (smem_u32(b_res) & 0x3FFFF) >> 4;
-      const uint32_t stage_lo = stage_bytes >> 4, shift_lo = p.row_shift >> 4, a_lo = p.a_bytes >> 4,
+      const uint32_t stage_lo = stage_bytes >> 4, a_lo = p.a_slot >> 4,
                      b_lo = p.b_bytes >> 4;
       int stage = 0;
       uint32_t phase = 0;
@@ -730,12 +735,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
             mbar_wait(&full[stage], phase);
             tc_fence_after();
             const uint32_t a0 = ring_lo + stage * stage_lo;
-            uint32_t a_run = a0, bs_run = a0 + a_lo;
+            uint32_t bs_run = a0 + a_lo;
             for (int i = 0; i < p.ndy; ++i) {
-              // tap i of the column group: the same activation tile, shifted down by i tile rows
-              const uint64_t adesc = desc_fixed | a_run;
+              // tap i of the load: the same activation tile, shifted down by whole tile rows (halo: and sideways
+              // by one pixel = 128 B, with the row groups (tile_w + 2) * 128 B apart)
+              const uint32_t a_tap = a0 + p.tap_off[i];
+              uint64_t adesc = desc_fixed_a | a_tap;
+              if (p.halo == 2) adesc |= static_cast<uint64_t>((a_tap >> 3) & 7) << 49;   // matrix base offset
               const uint64_t bdesc = desc_fixed | (b_resident ? b_run : bs_run);
-              a_run += shift_lo;
               bs_run += b_lo;
               b_run += b_lo;
               if (elect_one()) {

@@ -45,6 +45,7 @@ class ConvDesc(C.Structure):
         ("ln_stats", C.c_void_p), ("ln_colsum", C.c_void_p),
         ("out_nchw", C.c_void_p), ("out_nchw_c", C.c_int32), ("out_nchw_h", C.c_int32), ("out_nchw_w", C.c_int32),
         ("kv_shift", C.c_void_p), ("ctx_acc", C.c_void_p),
+        ("halo", C.c_int32),
     ]
 
 

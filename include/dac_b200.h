@@ -125,6 +125,9 @@ typedef struct dac_conv_desc {
   const float* ln_stats; const float* ln_colsum;  /* QKV: [B*OH*OW][2], [cout] */
   float* out_nchw; int32_t out_nchw_c, out_nchw_h, out_nchw_w; /* alt. fp32 NCHW output (final_conv), cropped */
   const float* kv_shift; float* ctx_acc;          /* KVCTX: [128] shift * log2(e); [B][4][1088] fp32 (zeroed by launch) */
+  int32_t halo;                                   /* 3x3 stride-1, tile_w 8: ONE (tile_h+2) x (tile_w+2) load per K chunk
+                                                     serves all nine taps (descriptors with a (tile_w+2)*128 B group
+                                                     stride); ncols = 1, ndy = 9, col_dx = col_dy0 = -1 */
 } dac_conv_desc;
 
 typedef struct dac_conv_plan* dac_conv_t;

@@ -92,6 +92,27 @@ def test_conv3x3_film_silu(ops, gen, B, H, W, cin, cout, tile):
     assert_close_bf16(nchw(out), ref, f"conv3x3 {B}x{H}x{W} {cin}->{cout} {plan.info()}")
 
 
+@pytest.mark.parametrize("B,H,W,c0,c1,cout", [(2, 40, 24, 64, 0, 64), (3, 37, 51, 64, 64, 64), (1, 16, 8, 128, 0, 64),
+                                               (2, 9, 200, 64, 0, 128)])
+def test_conv3x3_halo_load(ops, gen, B, H, W, c0, c1, cout):
+    """ONE haloed (16+2) x (8+2) activation load per K chunk, nine shifted operand views (1280 B row-group stride):
+    same result as the three-column-load path up to the fp32 accumulation order of the taps, on ragged sizes."""
+    a = nhwc(rnd(gen, B, c0, H, W))
+    s_ = nhwc(rnd(gen, B, c1, H, W)) if c1 else None
+    w = rnd(gen, cout, c0 + c1, 3, 3, scale=(9 * (c0 + c1)) ** -0.5)
+    outs = []
+    for halo in (1, 0):
+        out = torch.full((B, H, W, cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+        plan = ops.ConvPlan(a, c0, ops.pack_conv(w), out, B=B, H=H, W=W, src1=s_, c1=c1, halo=halo,
+                            tile=None if halo else (16, 8))
+        plan.run()
+        torch.cuda.synchronize()
+        outs.append(out)
+    x = nchw(a) if s_ is None else torch.cat([nchw(a), nchw(s_)], 1)
+    assert_close_bf16(nchw(outs[0]), F.conv2d(x, bf(w).float(), padding=1), f"conv3x3 halo {plan.info()}")
+    assert_close_bf16(outs[0], outs[1], "halo vs column loads", rel=2 ** -7, abs_=1e-3)
+
+
 @pytest.mark.parametrize("share", [True, False])
 @pytest.mark.parametrize("B,H,W,c0,c1,cout", [(2, 40, 24, 64, 0, 64), (1, 64, 64, 128, 64, 128), (1, 16, 16, 256, 0, 256)])
 def test_conv3x3_tap_sharing_modes(ops, gen, share, B, H, W, c0, c1, cout):
