@@ -13,28 +13,11 @@
 #include "../../include/dac_b200.h"
 #include "common.h"
 #include "conv_kernel.cuh"
+#include "tensormap.h"
 
 namespace dac {
 
 // ------------------------------------------------------------------------------------------- host side
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static PFN_encodeTiled get_encode_fn() {
-  static PFN_encodeTiled fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    void* f = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    // No link-time dependency on libcuda: the library must load on hosts without a driver.
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<PFN_encodeTiled>(f);
-  });
-  return fn;
-}
-
 }  // namespace dac
 
 struct dac_conv_plan {

@@ -21,17 +21,9 @@
 
 #include "../../include/dac_b200.h"
 #include "ptx.cuh"
+#include "tile_common.cuh"
 
 namespace dac {
-
-constexpr int kTileM = 128;
-constexpr int kChunkK = 64;   // bf16 per K step = one 128 B swizzle row
-constexpr int kThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
-constexpr int kEpiWarps = 8;
-constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kAccStride = 256;
-constexpr uint32_t kABytes = kTileM * kChunkK * 2;  // 16 KB
-constexpr int kMaxStages = 8;
 
 enum { KE_PLAIN = 0, KE_GEGLU = 1, KE_LN = 2, KE_QKV = 3, KE_NCHW = 4, KE_KVCTX = 5 };
 constexpr int kKvPitch = 40;                                   // bf16 per row of a [128 px][32 ch] head tile
@@ -134,99 +126,11 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvKParams& p, int tile)
   return t;
 }
 
-// CTA b owns the contiguous tile range [total*b/grid, total*(b+1)/grid): consecutive tiles of a CTA belong to the
-// same image (FiLM parameters stay cached) and neighbouring rows (halo re-reads hit L2).
-__device__ __forceinline__ void tile_range(int total, int& begin, int& end) {
-  begin = static_cast<int>(static_cast<long long>(total) * blockIdx.x / gridDim.x);
-  end = static_cast<int>(static_cast<long long>(total) * (blockIdx.x + 1) / gridDim.x);
-}
-
 template <int ACT>
 __device__ __forceinline__ float apply_act(float v) {
   if (ACT == DAC_ACT_SILU) return silu_f(v);
   if (ACT == DAC_ACT_GELU) return gelu_f(v);
   return v;
-}
-
-// ---- 32-column chunk helpers: everything statically indexed so the chunk lives in registers ----
-__device__ __forceinline__ void chunk_from_tmem(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  tmem_ld32(taddr, r);
-  tmem_ld_wait();
-#pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-}
-__device__ __forceinline__ void chunk_add_f32(const float* __restrict__ src, float (&v)[32]) {
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(src) + q);
-    v[4 * q] += a.x; v[4 * q + 1] += a.y; v[4 * q + 2] += a.z; v[4 * q + 3] += a.w;
-  }
-}
-__device__ __forceinline__ void chunk_film(const float* __restrict__ sc, const float* __restrict__ sh,
-                                           float (&v)[32]) {
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(sc) + q);
-    const float4 b = __ldg(reinterpret_cast<const float4*>(sh) + q);
-    v[4 * q] = fmaf(v[4 * q], a.x + 1.0f, b.x);
-    v[4 * q + 1] = fmaf(v[4 * q + 1], a.y + 1.0f, b.y);
-    v[4 * q + 2] = fmaf(v[4 * q + 2], a.z + 1.0f, b.z);
-    v[4 * q + 3] = fmaf(v[4 * q + 3], a.w + 1.0f, b.w);
-  }
-}
-__device__ __forceinline__ void chunk_add_bf16(const __nv_bfloat16* __restrict__ src, float (&v)[32]) {
-#pragma unroll
-  for (int q = 0; q < 2; ++q) {          // 2 x 32 B = this row's 32 channels
-    const U32x8 u = ldg256(src + q * 16);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float2 a = unpack_bf16(u.v[j]);
-      v[q * 16 + 2 * j] += a.x;
-      v[q * 16 + 2 * j + 1] += a.y;
-    }
-  }
-}
-__device__ __forceinline__ void chunk_store_bf16(__nv_bfloat16* __restrict__ dst, const float (&v)[32]) {
-#pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    U32x8 u;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) u.v[j] = pack_bf16(v[q * 16 + 2 * j], v[q * 16 + 2 * j + 1]);
-    stg256(dst + q * 16, u);
-  }
-}
-// 32 columns of one row into the staging tile: 64-channel slabs of 128 rows x 128 B, 16 B pieces XOR-swizzled by the
-// row (the SWIZZLE_128B pattern of the output tensor map; also conflict-free for one-row-per-lane writes).
-__device__ __forceinline__ void chunk_stage_bf16(uint8_t* stg, int row, int col, const float (&v)[32]) {
-  uint8_t* slab = stg + (col >> 6) * (kTileM * 128) + row * 128;
-  const int c16 = (col & 63) >> 3;
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    uint4 u;
-    u.x = pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
-    u.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
-    u.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
-    u.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
-    *reinterpret_cast<uint4*>(slab + (((c16 + q) ^ (row & 7)) << 4)) = u;
-  }
-}
-// ... and the read side: add the 32 staged bf16 values of this row (a TMA-loaded residual tile) to v
-__device__ __forceinline__ void chunk_add_staged(const uint8_t* stg, int row, int col, float (&v)[32]) {
-  const uint8_t* slab = stg + (col >> 6) * (kTileM * 128) + row * 128;
-  const int c16 = (col & 63) >> 3;
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const uint4 u = *reinterpret_cast<const uint4*>(slab + (((c16 + q) ^ (row & 7)) << 4));
-    const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
-    v[q * 8 + 0] += a.x; v[q * 8 + 1] += a.y; v[q * 8 + 2] += b.x; v[q * 8 + 3] += b.y;
-    v[q * 8 + 4] += c.x; v[q * 8 + 5] += c.y; v[q * 8 + 6] += d.x; v[q * 8 + 7] += d.y;
-  }
-}
-__device__ __forceinline__ void chunk_store_f32(float* __restrict__ dst, const float (&v)[32]) {
-#pragma unroll
-  for (int q = 0; q < 8; ++q)
-    reinterpret_cast<float4*>(dst)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
 }
 
 // Epilogue of one 128 x block_n accumulator tile.  Thread = one output pixel (TMEM lane `row`); the warp pair of

@@ -243,6 +243,31 @@ class ConvPlan:
             pass
 
 
+class QoutPlan:
+    """LinearAttention query side (to_q softmax -> W_eff q -> LayerNorm -> + x) as one chained-GEMM launch."""
+
+    def __init__(self, xn, wq, weff, res, out, bias, ln_g, ln_eps, B, hw, Cn):
+        L.require_cuda(xn, wq, weff, res, out, ln_g)
+        lib = L.load()
+        h = C.c_void_p()
+        L.check(lib.dac_linattn_qout_create(xn.data_ptr(), wq.data_ptr(), weff.data_ptr(), weff.shape[-2],
+                                            res.data_ptr(), out.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                            ln_g.data_ptr(), ln_eps, B, hw, Cn, C.byref(h)))
+        self.handle, self._lib = h, lib
+        self._keep = (xn, wq, weff, res, out, bias, ln_g)
+        self.flops = 2.0 * B * hw * 128 * Cn * 2
+
+    def run(self):
+        L.check(self._lib.dac_linattn_qout_launch(self.handle, L.stream_ptr()))
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self._lib.dac_linattn_qout_destroy(self.handle)
+        except Exception:
+            pass
+
+
 # ------------------------------------------------------------------------------------------------ thin wrappers
 def _coef(vals):
     arr = (C.c_float * 8)()

@@ -404,6 +404,7 @@ class UNetEngine:
     # producer +14 us vs the 54 us LayerNorm kernel saved): the QKV epilogue is already the bottleneck of that
     # store-bound layer.  Kept as a tested option (tests/test_kernels_gpu.py::test_prenorm_folded_into_qkv).
     FOLD_PRENORM = False
+    FUSE_QOUT = True       # LinearAttention: to_q + softmax + to_out + LayerNorm + residual as one chained-GEMM kernel
     FUSE_KVCTX = True      # LinearAttention: reduce k | v into the context inside the to_kv GEMM epilogue
 
     def needs_stats(self, prefix):
@@ -426,10 +427,18 @@ class UNetEngine:
                 ctx = self.buf(B, 4, 1, 32 * 34, dtype=torch.float32)
                 self.conv(prefix + "to_kv", xn, C, a["kv"], None, h, w, epi=L.EPI_KVCTX, block_n=256,
                           kv_shift=a["kv_shift"], ctx_acc=ctx)
-                self.conv(prefix + "to_q", xn, C, a["q"], q, h, w, epi=L.EPI_QKV, block_n=128)
                 weff = self.buf(B, c_pad, 128)
-                self.add(prefix + "fold", lambda: ops.linattn_fold(ctx, B, hw, 1, a["w_out"], C, c_pad, weff))
                 self.flops += 2.0 * B * 4 * 32 * 32 * hw
+                if self.FUSE_QOUT and C in (64, 128) and hw % 128 == 0:
+                    # q never reaches memory either: to_q -> softmax -> W_eff q -> LayerNorm -> + x in one kernel
+                    self.add(prefix + "fold", lambda: ops.linattn_fold(ctx, B, hw, 1, a["w_out"], C, c_pad, weff))
+                    plan = ops.QoutPlan(xn, a["q"].w, weff, x, out, a["b_out"], a["g_out"], 1e-5, B, hw, C)
+                    self.flops += plan.flops
+                    self.conv_names.add(prefix + "to_q_out")
+                    self.add(prefix + "to_q_out", plan.run)
+                    return out
+                self.conv(prefix + "to_q", xn, C, a["q"], q, h, w, epi=L.EPI_QKV, block_n=128)
+                self.add(prefix + "fold", lambda: ops.linattn_fold(ctx, B, hw, 1, a["w_out"], C, c_pad, weff))
                 self.conv(prefix + "to_out", q, 128, a["out"], out, h, w, epi=L.EPI_LN, bias=a["b_out"],
                           ln_g=a["g_out"], res=x, per_image_w=True, weight_override=weff)
                 return out

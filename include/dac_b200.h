@@ -183,6 +183,18 @@ int dac_linattn_context(const void* kv, int32_t B, int32_t hw, int32_t nchunks, 
 int dac_linattn_fold(const float* partial, int32_t B, int32_t hw, int32_t nchunks, const float* w_out /*[C,128] fp32*/,
                      int32_t C, int32_t c_pad, void* weff /*[B][c_pad][128] bf16*/, dac_stream_t stream);
 
+/* Query side of LinearAttention as ONE chained-GEMM kernel (MU:170-185): per 128-pixel tile
+ *   q = softmax_head-channels(wq . xn) * 32^-0.5   (kept in shared memory, bf16)
+ *   out = LayerNorm_c(weff[b] . q + bias) * ln_g + res
+ * xn, res, out: bf16 [B*hw, C] (C = 64 or 128, hw % 128 == 0); wq: bf16 [128][C] (gain-folded rows of to_qkv);
+ * weff: bf16 [B][c_pad][128] from dac_linattn_fold.  Replaces the to_q (DAC_EPI_QKV) + to_out (DAC_EPI_LN) pair. */
+typedef struct dac_qout_plan* dac_qout_t;
+int dac_linattn_qout_create(const void* xn, const void* wq, const void* weff, int32_t c_pad, const void* res,
+                            void* out, const float* bias, const float* ln_g, float ln_eps, int32_t B, int32_t hw,
+                            int32_t C, dac_qout_t* plan);
+int dac_linattn_qout_launch(dac_qout_t plan, dac_stream_t stream);
+void dac_linattn_qout_destroy(dac_qout_t plan);
+
 /* ------------------------------------------------------------------ softmax attention
  * qkv: [B, n, 3*heads*d] bf16 packed (q | k | v along channels), out [B, n, heads*d] bf16.
  * d = 32 (UNet self-attention, ATT:178-192) or 64 (ViT, TR:219-230); scale = d^-0.5. */

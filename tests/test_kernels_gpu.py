@@ -358,6 +358,41 @@ def test_linear_attention_fused_kv_context(ops, gen, B, H, W, C):
     assert_close_bf16(weff[:, :C], weff_ref, "folded context weight", rel=2 ** -6, abs_=1e-2)
 
 
+@pytest.mark.parametrize("B,H,W,C", [(3, 32, 32, 64), (2, 16, 40, 128), (5, 64, 48, 64), (1, 8, 16, 128)])
+def test_linear_attention_chained_q_out(ops, gen, B, H, W, C):
+    """Whole LinearAttention block on the fused path: KVCTX context -> fold -> chained kernel (to_q, head softmax,
+    W_eff q, LayerNorm, + residual), vs the oracle block (module_util.py:157-185) in fp32."""
+    from daclip_b200 import lib as L
+    from oracle import unet_oracle as O
+    hw = H * W
+    x = rnd(gen, B, C, H, W) * 1.3 + 0.2
+    xn = (x - x.mean(1, keepdim=True)) * torch.rsqrt(x.var(1, unbiased=False, keepdim=True) + 1e-5)
+    xh, rh = nhwc(xn), nhwc(rnd(gen, B, C, H, W))
+    sd = {"to_qkv.weight": rnd(gen, 384, C, 1, 1, scale=C ** -0.5),
+          "to_out.0.weight": rnd(gen, C, 128, 1, 1, scale=128 ** -0.5 * 8),
+          "to_out.0.bias": rnd(gen, C, scale=0.1), "to_out.1.g": (1 + 0.1 * rnd(gen, 1, C, 1, 1))}
+    sdr = dict(sd)
+    sdr["to_qkv.weight"] = bf(sd["to_qkv.weight"]).float()
+    ref = O.linear_attention(sdr, "", nchw(xh)) + nchw(rh)
+    wqkv = sd["to_qkv.weight"].reshape(384, C)
+    shift = 1.02 * bf(wqkv[128:256]).float().norm(dim=1) * math.sqrt(C)
+    ctx = torch.zeros(B, 4, 1, 32 * 34, device="cuda")
+    c_pad = ops.choose_block_n(C)[1]
+    weff = torch.zeros(B, c_pad, 128, device="cuda", dtype=torch.bfloat16)
+    out = torch.full((B, H, W, C), float("nan"), device="cuda", dtype=torch.bfloat16)
+    pkv = ops.ConvPlan(xh, C, ops.pack_linear(wqkv[128:].contiguous()), None, B=B, H=H, W=W, epi=L.EPI_KVCTX,
+                       block_n=256, kv_shift=(shift * 1.4426950408889634).contiguous(), ctx_acc=ctx)
+    wq = ops.pack_linear(wqkv[:128].contiguous())
+    pq = ops.QoutPlan(xh, wq.w, weff, rh, out, sd["to_out.0.bias"], sd["to_out.1.g"].reshape(-1).contiguous(), 1e-5,
+                      B, hw, C)
+    for _ in range(2):
+        pkv.run()
+        ops.linattn_fold(ctx, B, hw, 1, sd["to_out.0.weight"].reshape(C, 128).contiguous(), C, c_pad, weff)
+        pq.run()
+    torch.cuda.synchronize()
+    assert_close_bf16(nchw(out), ref, f"chained linear attention {H}x{W} C={C}", rel=2 ** -5, abs_=2e-2)
+
+
 @pytest.mark.parametrize("B,H,W,C", [(2, 32, 32, 64), (1, 16, 48, 128), (1, 16, 16, 256)])
 def test_prenorm_folded_into_qkv(ops, gen, B, H, W, C):
     """PreNorm (channel LayerNorm, gain only) folded around to_qkv: the producer writes per-pixel {mean, rstd} of its
