@@ -426,7 +426,7 @@ def test_prenorm_folded_into_qkv(ops, gen, B, H, W, C):
 
 
 # ---------------------------------------------------------------------------------------------- attention
-@pytest.mark.parametrize("B,n,heads", [(2, 1024, 8), (1, 4096, 16), (1, 200, 4)])
+@pytest.mark.parametrize("B,n,heads", [(2, 1024, 8), (1, 4096, 16), (1, 200, 4), (1, 128, 2), (3, 384, 6), (5, 1024, 16)])
 def test_flash_attention_d32(ops, gen, B, n, heads):
     d = 32
     qkv = bf(rnd(gen, B, n, 3 * heads * d))
