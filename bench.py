@@ -21,7 +21,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+# rank 0 prints ONE JSON line on stdout: NCCL's banner / debug output (printed at every level >= VERSION) goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
@@ -137,7 +138,7 @@ def conv_time_per_eval(eng, reps=3):
 CONV2D_GFLOP = {256: 236.23}
 SPATIAL_GFLOP = {256: 205.58 + 8.05 + 4.29 + 2.47}
 _SPATIAL = re.compile(r"block[12]$|res_conv$|^init_conv$|^final_conv$|^(downs|ups)\.\d\.3$")
-_POINTWISE = re.compile(r"(?<!attn1)\.(to_q|to_kv|to_qkv|to_out|proj_in|proj_out)$")
+_POINTWISE = re.compile(r"(?<!attn1)\.(to_q|to_kv|to_qkv|to_q_out|to_out|proj_in|proj_out)$")
 
 
 def conv_subroofline(layers, B, S, peak_tf):
