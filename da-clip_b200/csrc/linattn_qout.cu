@@ -205,14 +205,18 @@ linattn_qout_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
     for (int i = group; i < n; i += 2) {
       const int tile = begin + i;
       const uint32_t ph = (i >> 1) & 1;
-      if (gthread == 0) {
-        tma_store_wait_read();                            // the previous output store has finished reading qt
-        if (C == 64) {                                    // residual tile: lands while the GEMMs run
+      if (C == 64) {
+        // the output of a tile is staged IN the residual tile (rt) and stored from there, so nobody has to wait for the
+        // previous store before writing the q tile; only the prefetch of the next residual does (one thread)
+        if (gthread == 0) {
+          tma_store_wait_read();
           mbar_arrive_expect_tx(&res_bar[group], kSlab);
           tma_load_2d(rt, &mapRes, &res_bar[group], 0, tile * kTileM);
         }
+      } else {
+        if (gthread == 0) tma_store_wait_read();          // the previous output store has finished reading qt
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");
       }
-      asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");
       // ---- epilogue 1: q = softmax over the 32 channels of each head, * 32^-0.5 -> bf16 A operand of GEMM 2
       mbar_wait(&acc1_full[group], ph);
       tc_fence_after();
@@ -287,7 +291,7 @@ linattn_qout_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
             w[k][4 * q + 3] *= rstd * g.w;
           }
           chunk_add_staged(rt, row, k * 32, w[k]);
-          chunk_stage_bf16(qt, row, k * 32, w[k]);
+          chunk_stage_bf16(rt, row, k * 32, w[k]);        // in place: same thread, same 16-byte pieces
         }
       } else {
         for (int c = 0; c < C; c += 32) {
@@ -328,7 +332,7 @@ linattn_qout_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
       fence_proxy_async();
       asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");
       if (gthread == 0) {
-        for (int s_ = 0; s_ < kCh; ++s_) tma_store_2d(&mapOut, qt + s_ * kSlab, s_ * 64, tile * kTileM);
+        for (int s_ = 0; s_ < kCh; ++s_) tma_store_2d(&mapOut, (C == 64 ? rt : qt) + s_ * kSlab, s_ * 64, tile * kTileM);
         tma_store_commit();
       }
     }

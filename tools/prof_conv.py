@@ -17,6 +17,8 @@ CASES = {
     "l0_q": (16, 256, 256, 64, 128, "q"),
     "l0_kv": (16, 256, 256, 64, 256, "kv"),
     "l0_toout": (16, 256, 256, 128, 64, "toout"),
+    "l0_qout": (16, 256, 256, 64, 64, "qout"),
+    "l1_qout": (16, 128, 128, 128, 128, "qout"),
 }
 
 def make(name):
@@ -51,6 +53,13 @@ def make(name):
         plan = ops.ConvPlan(x, cin, ops.pack_linear(w), out, B=B, H=H, W=W, epi=L.EPI_LN,
                             bias=torch.zeros(cout, device="cuda"), ln_g=torch.ones(cout, device="cuda"), res=res,
                             per_image_w=True, weight_override=weff)
+    elif kind == "qout":
+        wq = (torch.randn(1, 128, cin, device="cuda", generator=g) * cin ** -0.5).to(torch.bfloat16)
+        weff = (torch.randn(B, cout, 128, device="cuda", generator=g) * 128 ** -0.5).to(torch.bfloat16)
+        res = torch.randn(B, H, W, cout, device="cuda", generator=g).to(torch.bfloat16)
+        plan = ops.QoutPlan(x, wq, weff, res, out, torch.zeros(cout, device="cuda"), torch.ones(cout, device="cuda"),
+                            1e-5, B, H * W, cout)
+        plan.info = lambda: {}
     elif kind == "geglu":
         w = torch.randn(cout, cin, device="cuda", generator=g) * cin ** -0.5
         b = torch.randn(cout, device="cuda", generator=g)
