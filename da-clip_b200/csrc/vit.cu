@@ -99,18 +99,30 @@ __global__ void __launch_bounds__(256) vit_pool_kernel(const float* __restrict__
     for (int i = lane; i < w; i += 32) row[i] = (row[i] - mean) * rstd * ln_w[i] + ln_b[i];
   }
   __syncthreads();
-  for (int j = threadIdx.x; j < e; j += blockDim.x) {
-    float a[kPoolImgs];
+  // blockIdx.y owns 64 projection columns; the 256 threads = 64 columns x 4 slices of the w contraction, reduced
+  // through shared memory (fixed order: slice 0 + 1 + 2 + 3)
+  __shared__ float part[4][kPoolImgs][64];
+  const int jl = threadIdx.x & 63, ks = threadIdx.x >> 6;
+  const int j = blockIdx.y * 64 + jl;
+  const int i0 = ks * (w / 4), i1 = ks == 3 ? w : i0 + w / 4;
+  float a[kPoolImgs];
 #pragma unroll
-    for (int m = 0; m < kPoolImgs; ++m) a[m] = 0.f;
-    for (int i = 0; i < w; ++i) {
+  for (int m = 0; m < kPoolImgs; ++m) a[m] = 0.f;
+  if (j < e) {
+    for (int i = i0; i < i1; ++i) {
       const float pj = __ldg(proj + static_cast<int64_t>(i) * e + j);   // coalesced over j
 #pragma unroll
       for (int m = 0; m < kPoolImgs; ++m) a[m] = fmaf(rows[m * w + i], pj, a[m]);
     }
+  }
+#pragma unroll
+  for (int m = 0; m < kPoolImgs; ++m) part[ks][m][jl] = a[m];
+  __syncthreads();
+  if (ks == 0 && j < e) {
 #pragma unroll
     for (int m = 0; m < kPoolImgs; ++m)
-      if (b0 + m < B) out[static_cast<int64_t>(b0 + m) * e + j] = a[m];
+      if (b0 + m < B)
+        out[static_cast<int64_t>(b0 + m) * e + j] = ((part[0][m][jl] + part[1][m][jl]) + part[2][m][jl]) + part[3][m][jl];
   }
 }
 
@@ -178,7 +190,7 @@ extern "C" int dac_vit_embed(const void* patch_emb, const float* cls, const floa
 extern "C" int dac_vit_pool(const void* x, int32_t B, int32_t L, int32_t w, const float* ln_w, const float* ln_b,
                             float eps, const float* proj, int32_t e, float* out, dac_stream_t stream) {
   if (!x || !ln_w || !ln_b || !proj || !out) return set_error(-1, "dac_vit_pool: null argument");
-  vit_pool_kernel<<<(B + kPoolImgs - 1) / kPoolImgs, 256, kPoolImgs * w * sizeof(float),
+  vit_pool_kernel<<<dim3((B + kPoolImgs - 1) / kPoolImgs, (e + 63) / 64), 256, kPoolImgs * w * sizeof(float),
                     static_cast<cudaStream_t>(stream)>>>(static_cast<const float*>(x), B, L, w, ln_w, ln_b, eps, proj, e,
                                                          out);
   return check_launch("vit_pool_kernel");

@@ -152,7 +152,14 @@ class ConvPlan:
         wt = weight_override if weight_override is not None else pw.w
         cout_pad = wt.shape[-2]
         if block_n is None:
-            block_n = choose_block_n(pw.cout)[0] if cout_pad <= 256 else (256 if cout_pad % 256 == 0 else 128)
+            if cout_pad <= 256:
+                block_n = choose_block_n(pw.cout)[0]
+            else:
+                # several N tiles: pick the tile width whose tile count quantises best onto the 148 persistent CTAs
+                # (e.g. 12800 tokens x 768 outputs: 300 tiles of 256 need 3 rounds of 148, 400 tiles of 192 also 3)
+                m_tiles = -(-(B * OH * OW) // 128) * pw.ngroups
+                cands = [bn for bn in (256, 192, 128) if cout_pad % bn == 0 and (epi == L.EPI_PLAIN or bn != 192)]
+                block_n = min(cands or [128], key=lambda bn: (-(-(m_tiles * (cout_pad // bn)) // 148) * (bn + 24), -bn))
         # vertically adjacent taps share one activation load when the weight tiles are small enough to ride along
         share = pw.cols is not None and s == 1 and block_n <= 128 and share_taps
         cols = pw.cols if share else [[(dx, dy, [i]) for i, (dy, dx) in enumerate(gt)] for gt in pw.taps]
