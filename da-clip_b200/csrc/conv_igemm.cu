@@ -212,6 +212,10 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
   }
   if (d->epi == DAC_EPI_KVCTX) stg_bytes = kKvStageBytes;   // P / V head tiles of each epilogue group
   k.kv_shift = d->kv_shift; k.ctx_acc = d->ctx_acc;
+  // FiLM parameters in TMEM when three block_n-wide regions fit one accumulator stage (the 64-channel layers, which
+  // are the shared-memory-bound ones); alignment of the float4 parameter loads needs cout % 4 == 0 (validated above)
+  k.film_tmem = (d->film && !fused_res && d->block_n % 32 == 0 && 3 * d->block_n <= (int)kAccStride &&
+                 !getenv("DAC_NO_FILM_TMEM")) ? 1 : 0;
   k.stg_bytes = stg_bytes;
   k.stg_count = stg_bytes ? 2 : 1;   // one staging tile per epilogue group
   int stages = (smem_budget - (int)k.b_res_bytes - (int)stg_bytes * k.stg_count) / (int)stage_bytes;

@@ -103,6 +103,7 @@ struct ConvKParams {
   const float* ln_colsum;      // QKV: sum_c W'[n][c]
   int stg_count;           // 1 or 2 staging tiles (2: the store of tile i overlaps the epilogue of tile i+1)
   int res_tma;             // the bf16 residual tile is TMA-loaded into the staging tile and updated in place
+  int film_tmem;           // FiLM (scale + 1 | shift) of the current image lives in TMEM columns [bn, 3 bn) of the stage
   const float* kv_shift;   // KVCTX: [128] upper bound of k per channel, times log2(e)
   float* ctx_acc;          // KVCTX: [B][4][kCtxRecord] fp32
 };
@@ -334,7 +335,17 @@ __device__ __forceinline__ void epilogue_tile(const ConvKParams& p, const TileCo
     }
     if (p.bias) chunk_add_f32(p.bias + ch, v);
     if (p.bias_img) chunk_add_f32(p.bias_img + static_cast<long long>(n) * p.cout + ch, v);
-    if (FILM) {
+    if (FILM && p.film_tmem) {
+      // (scale + 1, shift) of this image replicated in every TMEM lane: two 32-column loads, no shared-memory traffic
+      // (a broadcast LDS.128 is four wavefronts on the pipe that bounds these layers)
+      float f[32];
+      chunk_from_tmem(tmem_acc + p.block_n + c, f);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] *= f[j];
+      chunk_from_tmem(tmem_acc + 2 * p.block_n + c, f);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] += f[j];
+    } else if (FILM) {
       // (scale + 1, shift) of this image, staged in shared memory by the epilogue warps when the image changes
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
@@ -727,7 +738,27 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         // FiLM parameters depend on (image, N tile) only: restage when that pair changes (rare with contiguous
         // tile ranges).  Named barrier 1 + group = the 128 threads of this group.
         const int key = t.n * p.n_tiles + t.nt;
-        if (key != film_key) {
+        if (key != film_key && p.film_tmem) {
+          // every thread writes the image's 2 x block_n parameters into its own TMEM lane, beside the accumulator
+          film_key = key;
+          const float* src = p.film + static_cast<long long>(t.n) * p.film_ld + p.film_off + t.nt * p.block_n;
+          const uint32_t faddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + group * kAccStride + p.block_n;
+          for (int c = 0; c < 2 * p.block_n; c += 32) {
+            const bool is_scale = c < p.block_n;
+            const float* s_ = is_scale ? src + c : src + p.cout + (c - p.block_n);
+            uint32_t r[32];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 a = __ldg(reinterpret_cast<const float4*>(s_) + q);
+              r[4 * q] = __float_as_uint(is_scale ? a.x + 1.0f : a.x);
+              r[4 * q + 1] = __float_as_uint(is_scale ? a.y + 1.0f : a.y);
+              r[4 * q + 2] = __float_as_uint(is_scale ? a.z + 1.0f : a.z);
+              r[4 * q + 3] = __float_as_uint(is_scale ? a.w + 1.0f : a.w);
+            }
+            tmem_st32(faddr + c, r);
+          }
+          tmem_st_wait();
+        } else if (key != film_key) {
           film_key = key;
           asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");
           const float* src = p.film + static_cast<long long>(t.n) * p.film_ld + p.film_off + t.nt * p.block_n;
