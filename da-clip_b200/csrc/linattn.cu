@@ -151,11 +151,19 @@ __global__ void __launch_bounds__(128) linattn_context_kernel(const __nv_bfloat1
 __global__ void __launch_bounds__(256) linattn_fold_kernel(const float* __restrict__ partial, int hw, int nchunks,
                                                            const float* __restrict__ w_out, int C, int c_pad,
                                                            __nv_bfloat16* __restrict__ weff) {
-  __shared__ float ctx[32 * 33];
-  __shared__ float wgt[128 * 32];
-  __shared__ float inv_s[32];
+  // one CTA per (head, image): everything staged in shared memory with coalesced loads first (the kernel is a latency
+  // chain, not a throughput problem), then C x 32 dot products of length 32
+  extern __shared__ float fold_sm[];
+  float* ctx = fold_sm;                 // [32][33]
+  float* wgt = ctx + 32 * 33;           // [nchunks][32] merge weights
+  float* inv_s = wgt + nchunks * 32;    // [32]
+  float* wsm = inv_s + 32;              // [C][33]: W_out[c][h*32 + e]
   const int h = blockIdx.x, b = blockIdx.y, t = threadIdx.x;
   const float* pbase = partial + (static_cast<int64_t>(b) * 4 + h) * nchunks * kPartial;
+  for (int i = t; i < C * 32; i += 256) {
+    const int c = i >> 5, e = i & 31;
+    wsm[c * 33 + e] = __ldg(w_out + static_cast<int64_t>(c) * 128 + h * 32 + e);
+  }
   if (t < 32) {
     float M = -INFINITY;
     for (int c = 0; c < nchunks; ++c) M = fmaxf(M, pbase[c * kPartial + 1024 + t]);
@@ -178,10 +186,9 @@ __global__ void __launch_bounds__(256) linattn_fold_kernel(const float* __restri
   __syncthreads();
   const int d = t & 31;
   for (int c = t >> 5; c < C; c += 8) {
-    const float* wr = w_out + static_cast<int64_t>(c) * 128 + h * 32;
     float a = 0.f;
 #pragma unroll
-    for (int e = 0; e < 32; ++e) a += __ldg(wr + e) * ctx[d * 33 + e];
+    for (int e = 0; e < 32; ++e) a = fmaf(wsm[c * 33 + e], ctx[d * 33 + e], a);
     weff[(static_cast<int64_t>(b) * c_pad + c) * 128 + h * 32 + d] = __float2bfloat16(a);
   }
 }
@@ -205,7 +212,13 @@ extern "C" int dac_linattn_fold(const float* partial, int32_t B, int32_t hw, int
                                 int32_t C, int32_t c_pad, void* weff, dac_stream_t stream) {
   if (!partial || !w_out || !weff) return set_error(-1, "dac_linattn_fold: null argument");
   if (nchunks < 1 || nchunks > 128) return set_error(-2, "dac_linattn_fold: nchunks must be in [1,128]");
-  linattn_fold_kernel<<<dim3(4, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  if (C <= 0 || C > 256) return set_error(-2, "dac_linattn_fold: C must be in [1,256]");
+  const size_t smem = sizeof(float) * (32 * 33 + nchunks * 32 + 32 + static_cast<size_t>(C) * 33);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(linattn_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_error(-12, "dac_linattn_fold: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  }
+  linattn_fold_kernel<<<dim3(4, B), 256, smem, static_cast<cudaStream_t>(stream)>>>(
       partial, hw, nchunks, w_out, C, c_pad, static_cast<__nv_bfloat16*>(weff));
   return check_launch("linattn_fold_kernel");
 }
