@@ -110,7 +110,8 @@ class _Residual(_Holder):  # module_util.py:27-33
 
 
 class UNetConfig:
-    def __init__(self, in_nc, out_nc, nf, ch_mult, context_dim, use_degra_context, use_image_context):
+    def __init__(self, in_nc, out_nc, nf, ch_mult, context_dim, use_degra_context, use_image_context, scale=1):
+        self.scale = scale
         self.in_nc, self.out_nc, self.nf = in_nc, out_nc, nf
         self.ch_mult = list(ch_mult)
         self.depth = len(self.ch_mult)
@@ -139,19 +140,26 @@ class UNetConfig:
 
 
 class ConditionalUNet(nn.Module):
-    """Same signature as the reference class (arch.py:22-23)."""
+    """Same signature as the reference class (arch.py:22-23); `scale` is the last argument of the wild-ir variant of
+    the class (config/wild-ir/models/modules/DenoisingUNet_arch.py:22-40: scale 0.5 = the whole UNet runs at half
+    resolution between an extra Downsample(nf, nf) and Upsample(nf, nf))."""
 
     def __init__(self, in_nc, out_nc, nf, ch_mult=[1, 2, 4, 4], context_dim=512, use_degra_context=True,
-                 use_image_context=False, upscale=1):
+                 use_image_context=False, upscale=1, scale=1):
         super().__init__()
-        cfg = UNetConfig(in_nc, out_nc, nf, ch_mult, context_dim, use_degra_context, use_image_context)
+        if scale not in (1, 0.5):
+            raise NotImplementedError("scale must be 1 or 0.5 (the reference only builds the resamplers for 0.5)")
+        cfg = UNetConfig(in_nc, out_nc, nf, ch_mult, context_dim, use_degra_context, use_image_context, scale)
         if in_nc != 3 or out_nc != 3 or nf != 64:
             raise NotImplementedError("the sm_100a engine is built for in_nc=out_nc=3, nf=64 (options/test.yml)")
         self.cfg = cfg
-        self.depth, self.upscale = cfg.depth, upscale
+        self.depth, self.upscale, self.scale = cfg.depth, upscale, scale
         self.context_dim, self.use_image_context, self.use_degra_context = cfg.context_dim, use_image_context, use_degra_context
         td = cfg.time_dim
         self.init_conv = nn.Conv2d(in_nc * 2, nf, 7, padding=3, bias=False)
+        if scale == 0.5:
+            self.downsample = nn.Conv2d(nf, nf, 4, 2, 1)
+            self.upsample = nn.Sequential(nn.Upsample(scale_factor=2, mode="nearest"), nn.Conv2d(nf, nf, 3, 1, 1))
         self.time_mlp = nn.Sequential(nn.Identity(), nn.Linear(nf, td), nn.GELU(), nn.Linear(td, td))
         if cfg.context_dim > 0 and use_degra_context:
             self.prompt = nn.Parameter(torch.rand(1, td))
@@ -283,6 +291,9 @@ class PackedUNet:
                 self.up.append((ops.pack_upsample_conv(f32(f"ups.{j}.3.1.weight")), f32(f"ups.{j}.3.1.bias")))
             else:
                 self.up.append((ops.pack_conv(f32(f"ups.{j}.3.weight")), None))
+        if cfg.scale == 0.5:
+            self.pre_down = (ops.pack_conv(f32("downsample.weight"), stride=2, pad=1), f32("downsample.bias"))
+            self.post_up = (ops.pack_upsample_conv(f32("upsample.1.weight")), f32("upsample.1.bias"))
         self.final_w = ops.pack_conv(f32("final_conv.weight"))
         self.final_b = f32("final_conv.bias")
 
@@ -506,6 +517,11 @@ class UNetEngine:
         self.conv("init_conv", stem, 64, pk.stem, x0, Hp, Wp)
         self.taps["init_conv"] = x0
         x, h, w = x0, Hp, Wp
+        if cfg.scale == 0.5:         # wild-ir: everything between here and final_res_block runs at half resolution
+            h, w = Hp // 2, Wp // 2
+            x = self.buf(B, h, w, cfg.nf)
+            self.conv("downsample", x0, cfg.nf, pk.pre_down[0], x, Hp, Wp, bias=pk.pre_down[1])
+            self.taps["downsample"] = x
         skips = []
         for i, (din, dout) in enumerate(cfg.dims):
             p = f"downs.{i}."
@@ -559,6 +575,11 @@ class UNetEngine:
                 self.conv(p + "3", x, dout, pw, y, h, w)
             x = y
             self.taps[p + "3"] = x
+        if cfg.scale == 0.5:
+            y = self.buf(B, 2 * h, 2 * w, cfg.nf)
+            self.conv("upsample", x, cfg.nf, pk.post_up[0], y, h, w, bias=pk.post_up[1])
+            x, h, w = y, 2 * h, 2 * w
+            self.taps["upsample"] = x
         x = self.resblock("final_res_block.", x, cfg.nf, h, w, skip=x0, sc=cfg.nf)
         self.taps["final_res_block"] = x
         self.conv("final_conv", x, cfg.nf, pk.final_w, None, h, w, bias=pk.final_b, out_nchw=self.out_noise)

@@ -20,7 +20,10 @@ class UNetConfig:
     """Constructor arguments of ConditionalUNet (arch.py:22-23) + derived dims."""
 
     def __init__(self, in_nc=3, out_nc=3, nf=64, ch_mult=(1, 2, 4, 8), context_dim=512,
-                 use_degra_context=True, use_image_context=True, upscale=1):
+                 use_degra_context=True, use_image_context=True, upscale=1, scale=1):
+        # `scale` is the wild-ir variant's argument (config/wild-ir/models/modules/DenoisingUNet_arch.py:22-40): 0.5 adds
+        # a Downsample(nf, nf) after init_conv and an Upsample(nf, nf) before the final concat
+        self.scale = scale
         self.in_nc, self.out_nc, self.nf = in_nc, out_nc, nf
         self.ch_mult = list(ch_mult)
         self.depth = len(self.ch_mult)
@@ -175,6 +178,8 @@ def unet_forward(sd, cfg: UNetConfig, xt, cond, time, text_context=None, image_c
         x = F.pad(x, (0, pw, 0, ph), mode="reflect")
     x = tap("init_conv", F.conv2d(x, sd["init_conv.weight"], padding=3))
     x_first = x
+    if cfg.scale == 0.5:                                   # wild-ir arch.py:136-140
+        x = tap("downsample", F.conv2d(x, sd["downsample.weight"], sd["downsample.bias"], stride=2, padding=1))
 
     t = time_embedding(sd, time, cfg.nf)
     context = None
@@ -216,6 +221,9 @@ def unet_forward(sd, cfg: UNetConfig, xt, cond, time, text_context=None, image_c
             x = F.conv2d(x, sd[p + "3.weight"], padding=1)
         tap(p + "3", x)
 
+    if cfg.scale == 0.5:                                   # wild-ir arch.py:176-180
+        x = F.interpolate(x, scale_factor=2, mode="nearest")
+        x = tap("upsample", F.conv2d(x, sd["upsample.1.weight"], sd["upsample.1.bias"], padding=1))
     x = res_block(sd, "final_res_block.", torch.cat([x, x_first], dim=1), t)
     tap("final_res_block", x)
     x = F.conv2d(x, sd["final_conv.weight"], sd["final_conv.bias"], padding=1)

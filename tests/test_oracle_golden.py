@@ -117,3 +117,20 @@ def test_daclip_encode_and_argmax():
     assert torch.equal(D.degradation_argmax(g["degra_features"], g["text_features"]), g["argmax"])
     # the control signal must be alive (zero-init modules were randomised) and consumed in REVERSE order
     assert all(h.abs().max() > 1e-3 for h in taps["hiddens"])
+
+
+def test_unet_wild_ir_variant_vs_reference_golden():
+    """wild-ir ConditionalUNet (context_dim 768, no degradation prompt, scale 0.5 resampler pair): the oracle against
+    outputs of the reference's wild-ir class (tests/golden/unet_wild.pt, oracle/gen_golden_wild.py)."""
+    g = torch.load(os.path.join(GOLD, "unet_wild.pt"), weights_only=False)
+    sd, kw = synthetic.unet_state_dict(g["weights_seed"], **g["ctor"])
+    assert "downsample.weight" in sd and "upsample.1.bias" in sd and "prompt" not in sd
+    cfg = O.UNetConfig(**kw)
+    for case in g["cases"][:2]:
+        B, H, W = case["shape"]
+        inp = synthetic.restoration_inputs(B, H, W, T=1, seed=case["seed"], ctx_dim=768)
+        xt = inp["lq"] + inp["eps0"] * (50 / 255)
+        with torch.no_grad():
+            out = O.unet_forward(sd, cfg, xt, inp["lq"], case["time"], inp["text_context"], inp["image_context"])
+        assert out.shape == case["out"].shape
+        assert (out - case["out"]).abs().max().item() < 2e-4

@@ -218,3 +218,23 @@ def test_wrapper_test_api(model, cuda):
         vis = wrapper.get_current_visuals()
         assert set(vis) == {"Input", "Output", "GT"} and vis["Output"].shape == (3, 32, 32)
         assert torch.isfinite(vis["Output"]).all() and vis["Output"].device.type == "cpu"
+
+
+def test_wild_ir_variant_vs_reference_golden(cuda):
+    """the wild-ir denoiser (context_dim 768, use_degra_context false, scale 0.5 = extra Downsample /
+    Upsample pair around the UNet) against outputs of the reference's wild-ir class, incl. a reflect-padded size."""
+    from daclip_b200 import synthetic
+    from daclip_b200.unet import ConditionalUNet
+    g = torch.load(os.path.join(GOLD, "unet_wild.pt"), weights_only=False)
+    sd, kw = synthetic.unet_state_dict(g["weights_seed"], **g["ctor"])
+    m = ConditionalUNet(**kw)
+    m.load_state_dict(sd, strict=True)
+    m = m.to(cuda).eval()
+    for case in g["cases"]:
+        B, H, W = case["shape"]
+        inp = {k: v.cuda() for k, v in synthetic.restoration_inputs(B, H, W, T=1, seed=case["seed"], ctx_dim=768).items()}
+        xt = inp["lq"] + inp["eps0"] * (50 / 255)
+        out = m(xt, inp["lq"], case["time"], text_context=inp["text_context"], image_context=inp["image_context"])
+        ref = case["out"].cuda()
+        assert out.shape == ref.shape
+        assert rel_err(out, ref) < 2e-2, (case["shape"], rel_err(out, ref))
