@@ -13,7 +13,8 @@ namespace dac {
 
 // out[(b*g*g + gy*g + gx), c*p*p + py*p + px] = image[b, c, gy*p+py, gx*p+px]
 __global__ void __launch_bounds__(256) vit_patchify_kernel(const float* __restrict__ img,
-                                                           __nv_bfloat16* __restrict__ out, int B, int S, int p) {
+                                                           __nv_bfloat16* __restrict__ out, int B, int S, int p,
+                                                           int ld_out) {
   const int g = S / p;
   const int K = 3 * p * p;
   const int64_t total = static_cast<int64_t>(B) * g * g * K / 2;  // two px per thread
@@ -25,7 +26,7 @@ __global__ void __launch_bounds__(256) vit_patchify_kernel(const float* __restri
     const int gx = static_cast<int>(row % g), gy = static_cast<int>((row / g) % g), b = static_cast<int>(row / (g * g));
     const int px = k % p, py = (k / p) % p, c = k / (p * p);
     const float* src = img + ((static_cast<int64_t>(b) * 3 + c) * S + gy * p + py) * S + gx * p + px;
-    reinterpret_cast<uint32_t*>(out)[i] = pack_bf16(src[0], src[1]);
+    *reinterpret_cast<uint32_t*>(out + row * ld_out + k) = pack_bf16(src[0], src[1]);
   }
 }
 
@@ -166,15 +167,17 @@ __global__ void __launch_bounds__(32) degradation_argmax_kernel(const float* __r
 
 using namespace dac;
 
-extern "C" int dac_vit_patchify(const float* image, void* out, int32_t B, int32_t S, int32_t p, dac_stream_t stream) {
+extern "C" int dac_vit_patchify(const float* image, void* out, int32_t B, int32_t S, int32_t p, int32_t ld_out,
+                                dac_stream_t stream) {
   if (!image || !out) return set_error(-1, "dac_vit_patchify: null argument");
   if (S % p || (p & 1)) return set_error(-2, "dac_vit_patchify: patch must be even and divide the image");
+  if (ld_out < 3 * p * p || (ld_out & 1)) return set_error(-2, "dac_vit_patchify: ld_out must be even and >= 3*p*p");
   const int g = S / p;
   const int64_t total = static_cast<int64_t>(B) * g * g * 3 * p * p / 2;
   int64_t blocks = ceil_div(total, 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   vit_patchify_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      image, static_cast<__nv_bfloat16*>(out), B, S, p);
+      image, static_cast<__nv_bfloat16*>(out), B, S, p, ld_out);
   return check_launch("vit_patchify_kernel");
 }
 

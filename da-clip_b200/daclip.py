@@ -82,7 +82,11 @@ class _VisionTransformer(_Holder):  # transformer.py:372-555
 
 
 class DaCLIP(nn.Module):
-    """Image side of open_clip's `daclip_ViT-B-32` (model_configs/daclip_ViT-B-32.json)."""
+    """Image side of open_clip's `daclip_ViT-B-32` (model_configs/daclip_ViT-B-32.json; the defaults) and of
+    `daclip_ViT-L-14` (model_configs/daclip_ViT-L-14.json, the wild-ir encoder: see ARCHS)."""
+
+    ARCHS = {"daclip_ViT-B-32": dict(image_size=224, patch=32, width=768, layers=12, heads=12, embed_dim=512),
+             "daclip_ViT-L-14": dict(image_size=224, patch=14, width=1024, layers=24, heads=16, embed_dim=768)}
 
     def __init__(self, image_size=224, patch=32, width=768, layers=12, heads=12, embed_dim=512):
         super().__init__()
@@ -163,7 +167,9 @@ class _PackedTower:
         def f32(t):
             return t.detach().to(dev, torch.float32).contiguous()
 
-        self.conv1 = ops.pack_linear(f32(vit.conv1.weight).reshape(vit.width, -1))
+        w1 = f32(vit.conv1.weight).reshape(vit.width, -1)
+        kpad = -(-w1.shape[1] // 64) * 64
+        self.conv1 = ops.pack_linear(torch.nn.functional.pad(w1, (0, kpad - w1.shape[1])))
         self.cls, self.pos = f32(vit.class_embedding), f32(vit.positional_embedding)
         self.ln_pre = (f32(vit.ln_pre.weight), f32(vit.ln_pre.bias))
         self.ln_post = (f32(vit.ln_post.weight), f32(vit.ln_post.bias))
@@ -203,13 +209,14 @@ class _EncodeEngine:
         self.image = torch.zeros(B, 3, S, S, **f32)
         self.image_features = torch.zeros(B, vit.output_dim, **f32)
         self.degra_features = torch.zeros(B, vit.output_dim, **f32)
-        patches = torch.zeros(1, 1, B * g * g, 3 * p * p, **bf)
+        kpad = -(-(3 * p * p) // 64) * 64           # GEMM K in 64-channel chunks (ViT-L/14: 588 -> 640, zero columns)
+        patches = torch.zeros(1, 1, B * g * g, kpad, **bf)
         self.add(lambda: ops.vit_patchify(self.image, patches, B, S, p))
         hiddens = []
 
         def tower(tp, out_features, control_in=None):
             pe = torch.zeros(1, 1, B * g * g, w, **bf)
-            self.conv(patches, 3 * p * p, tp.conv1, pe, B * g * g)
+            self.conv(patches, kpad, tp.conv1, pe, B * g * g)
             x = torch.zeros(1, 1, M, w, **f32)
             self.add(lambda: ops.vit_embed(pe, tp.cls, tp.pos, tp.ln_pre[0], tp.ln_pre[1], x, B, Ltok, w))
             n = torch.zeros(1, 1, M, w, **bf)
@@ -267,9 +274,9 @@ class _EncodeEngine:
 def create_model_from_pretrained(model_name="daclip_ViT-B-32", pretrained=None, device="cuda", **_):
     """factory.py:365-404 for the one model on this path.  Returns (model, preprocess); `pretrained` is a path
     to a reference checkpoint (.pt: raw state dict or {'state_dict': ...}), or None for random init."""
-    if model_name not in ("daclip_ViT-B-32",):
-        raise NotImplementedError(f"only daclip_ViT-B-32 is on the restoration path, got {model_name}")
-    model = DaCLIP()
+    if model_name not in DaCLIP.ARCHS:
+        raise NotImplementedError(f"{model_name}: only {sorted(DaCLIP.ARCHS)} are on the restoration path")
+    model = DaCLIP(**DaCLIP.ARCHS[model_name])
     if pretrained:
         model.load_reference_state_dict(torch.load(pretrained, map_location="cpu"))
     return model.to(device).eval(), clip_preprocess

@@ -83,7 +83,7 @@ SYMBOLS = {
     "dac_linattn_context": (C.c_int, [_p, _i32, _i32, _i32, _p, _p]),
     "dac_linattn_fold": (C.c_int, [_p, _i32, _i32, _i32, _p, _i32, _i32, _p, _p]),
     "dac_attention": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _p]),
-    "dac_vit_patchify": (C.c_int, [_p, _p, _i32, _i32, _i32, _p]),
+    "dac_vit_patchify": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _p]),
     "dac_vit_embed": (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _f, _p]),
     "dac_vit_pool": (C.c_int, [_p, _i32, _i32, _i32, _p, _p, _f, _p, _i32, _p, _p]),
     "dac_degradation_argmax": (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p, _p]),

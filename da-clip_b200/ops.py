@@ -343,7 +343,7 @@ def attention(qkv, out, B, n, heads, d):
 
 
 def vit_patchify(image, out, B, S, p):
-    L.check(L.load().dac_vit_patchify(L.ptr(image), L.ptr(out), B, S, p, L.stream_ptr()))
+    L.check(L.load().dac_vit_patchify(L.ptr(image), L.ptr(out), B, S, p, out.shape[-1], L.stream_ptr()))
 
 
 def vit_embed(patch_emb, cls, pos, ln_w, ln_b, out, B, Ltok, w, eps=1e-5):

@@ -116,12 +116,16 @@ def vit_tower_shapes(prefix, width=768, layers=12, patch=32, grid=7, embed=512, 
     return s
 
 
-def daclip_visual_state_dict(seed=10):
-    """Synthetic weights of the two ViT-B/32 towers used by encode_image(control=True):
+VIT_ARCHS = {"ViT-B-32": dict(width=768, layers=12, patch=32, grid=7, embed=512),
+             "ViT-L-14": dict(width=1024, layers=24, patch=14, grid=16, embed=768)}
+
+
+def daclip_visual_state_dict(seed=10, arch="ViT-B-32"):
+    """Synthetic weights of the two ViT towers used by encode_image(control=True):
     `visual.*` (frozen CLIP tower; the reference aliases it as `clip.visual.*`) and `visual_control.*`."""
     shapes = {}
-    shapes.update(vit_tower_shapes("visual."))
-    shapes.update(vit_tower_shapes("visual_control.", control=True))
+    shapes.update(vit_tower_shapes("visual.", **VIT_ARCHS[arch]))
+    shapes.update(vit_tower_shapes("visual_control.", control=True, **VIT_ARCHS[arch]))
     sd = randomize_state_dict(shapes, seed)
     # keep the control signal a perturbation, as a trained ControlNet-style branch would be
     for k in sd:

@@ -201,8 +201,11 @@ void dac_linattn_qout_destroy(dac_qout_t plan);
 int dac_attention(const void* qkv, void* out, int32_t B, int32_t n, int32_t heads, int32_t d, dac_stream_t stream);
 
 /* ------------------------------------------------------------------ DA-CLIP encoder helpers (TR:507-555)
- * patchify: image [B,3,S,S] fp32 NCHW -> [B*g*g, 3*p*p] bf16 rows (k = c*p*p + py*p + px, conv1 weight order). */
-int dac_vit_patchify(const float* image, void* out, int32_t B, int32_t S, int32_t p, dac_stream_t stream);
+ * patchify: image [B,3,S,S] fp32 NCHW -> [B*g*g, 3*p*p] bf16 rows (k = c*p*p + py*p + px, conv1 weight order) at a
+ * row pitch of ld_out >= 3*p*p elements (the GEMM wants K % 64 == 0: ViT-L/14 pads 588 -> 640; pad columns are left
+ * untouched, the caller zeroes them once). */
+int dac_vit_patchify(const float* image, void* out, int32_t B, int32_t S, int32_t p, int32_t ld_out,
+                     dac_stream_t stream);
 /* tokens[b,0,:] = cls + pos[0]; tokens[b,1+i,:] = patch[b,i,:] + pos[1+i]; then ln_pre -> out fp32 [B,L,w]. */
 int dac_vit_embed(const void* patch_emb, const float* cls, const float* pos, const float* ln_w, const float* ln_b,
                   void* out, int32_t B, int32_t L, int32_t w, float eps, dac_stream_t stream);

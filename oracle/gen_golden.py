@@ -110,6 +110,30 @@ def gen_daclip():
           (probs.topk(2).values[:, 0] - probs.topk(2).values[:, 1]).tolist())
 
 
+def gen_daclip_l14():
+    """wild-ir encoder: daclip_ViT-L-14 (model_configs/daclip_ViT-L-14.json), both towers, B = 2."""
+    sys.modules.setdefault("ftfy", types.SimpleNamespace(fix_text=lambda s: s))
+    import open_clip
+    torch.manual_seed(21)
+    with um.patch.object(torch.nn.Module, "cuda", lambda self, *a, **k: self):
+        model = open_clip.create_model("daclip_ViT-L-14", pretrained=None, device="cpu")
+    model.eval()
+    vis = synthetic.daclip_visual_state_dict(30, arch="ViT-L-14")
+    full = model.state_dict()
+    missing = [k for k in vis if k not in full]
+    assert not missing, missing[:5]
+    for k, v in vis.items():
+        assert full[k].shape == v.shape, (k, full[k].shape, v.shape)
+    model.load_state_dict(vis, strict=False)
+    g = torch.Generator().manual_seed(6)
+    image = torch.randn(2, 3, 224, 224, generator=g)
+    with torch.no_grad():
+        image_features, degra_features = model.encode_image(image, control=True)
+    torch.save(dict(weights_seed=30, image_seed=6, image_features=image_features, degra_features=degra_features),
+               os.path.join(GOLD, "daclip_l14.pt"))
+    print("daclip_l14.pt written", image_features.shape, image_features.abs().mean().item())
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     which = sys.argv[1:] or ["unet", "daclip"]
@@ -117,3 +141,5 @@ if __name__ == "__main__":
         gen_unet_and_sampler()
     if "daclip" in which:
         gen_daclip()
+    if "daclip_l14" in which:
+        gen_daclip_l14()

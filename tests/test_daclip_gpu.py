@@ -100,3 +100,19 @@ def test_encode_image_batch256_argmax(setup):
     decided = (top2[:, 0] - top2[:, 1]) > 4 * err
     assert torch.equal(am[decided], ref_logits.argmax(-1)[decided])
     assert decided.float().mean().item() > 0.7
+
+
+def test_vit_l14_encode_vs_reference_golden(cuda):
+    """the wild-ir encoder daclip_ViT-L-14 (patch 14 -> K = 588 padded to 640, 257 tokens, d = 64 heads,
+    24 + 24 layers) against features of the reference model itself."""
+    from daclip_b200 import synthetic
+    from daclip_b200.daclip import create_model_from_pretrained
+    g = torch.load(os.path.join(GOLD, "daclip_l14.pt"), weights_only=False)
+    m, _ = create_model_from_pretrained("daclip_ViT-L-14", device=cuda)
+    m.load_reference_state_dict(synthetic.daclip_visual_state_dict(g["weights_seed"], arch="ViT-L-14"))
+    m = m.to(cuda).eval()
+    image = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(g["image_seed"])).cuda()
+    img_f, deg_f = m.encode_image(image, control=True)
+    assert img_f.shape == (2, 768) and deg_f.shape == (2, 768)
+    assert rel(img_f.cpu(), g["image_features"]) < 2e-2, rel(img_f.cpu(), g["image_features"])
+    assert rel(deg_f.cpu(), g["degra_features"]) < 2e-2, rel(deg_f.cpu(), g["degra_features"])

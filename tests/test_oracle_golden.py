@@ -134,3 +134,17 @@ def test_unet_wild_ir_variant_vs_reference_golden():
             out = O.unet_forward(sd, cfg, xt, inp["lq"], case["time"], inp["text_context"], inp["image_context"])
         assert out.shape == case["out"].shape
         assert (out - case["out"]).abs().max().item() < 2e-4
+
+
+def test_daclip_vit_l14_encode_vs_reference_golden():
+    """wild-ir encoder (daclip_ViT-L-14: patch 14, 257 tokens, width 1024, 24 layers, 16 heads, embed 768): oracle vs
+    the reference model's own features (tests/golden/daclip_l14.pt)."""
+    g = torch.load(os.path.join(GOLD, "daclip_l14.pt"), weights_only=False)
+    sd = synthetic.daclip_visual_state_dict(g["weights_seed"], arch="ViT-L-14")
+    image = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(g["image_seed"]))
+    cfg = D.ViTConfig(image_size=224, patch=14, width=1024, layers=24, heads=16, embed_dim=768)
+    with torch.no_grad():
+        img_f, deg_f = D.encode_image_control(sd, image, cfg)
+    assert img_f.shape == (2, 768)
+    assert (img_f - g["image_features"]).abs().max().item() < 2e-3 * g["image_features"].abs().max().item()
+    assert (deg_f - g["degra_features"]).abs().max().item() < 2e-3 * g["degra_features"].abs().max().item()
