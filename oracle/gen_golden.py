@@ -77,6 +77,31 @@ def gen_unet_and_sampler():
           "posterior final absmax", traj["posterior"].abs().max().item())
 
 
+def gen_reduced_step():
+    """Reduced-step sampling: IRSDE(T=100, sample_T=20) - tables for 20 steps, network queried at 5 t."""
+    from models.modules.DenoisingUNet_arch import ConditionalUNet
+    from utils.sde_utils import IRSDE
+    sd, kw = synthetic.unet_state_dict(0)
+    net = ConditionalUNet(**kw)
+    net.load_state_dict(sd, strict=True)
+    net.eval()
+    ST = 20
+    inp = synthetic.restoration_inputs(1, 32, 32, T=ST, seed=8)
+    sde = IRSDE(max_sigma=50, T=100, sample_T=ST, schedule="cosine", eps=0.005, device="cpu")
+    sde.set_model(net)
+    sde.set_mu(inp["lq"])
+    x_T = inp["lq"] + inp["eps0"] * sde.max_sigma
+    out = dict(seed=8, shape=(1, 32, 32), T=100, sample_T=ST, dt=sde.dt.clone(), sigma_bars=sde.sigma_bars.clone())
+    with torch.no_grad():
+        for mode in ("sde", "posterior"):
+            it = iter(inp["noise"])
+            with um.patch("torch.randn_like", lambda t: next(it)):
+                fn = sde.reverse_sde if mode == "sde" else sde.reverse_posterior
+                out[mode] = fn(x_T, text_context=inp["text_context"], image_context=inp["image_context"])
+    torch.save(out, os.path.join(GOLD, "sampler_reduced.pt"))
+    print("sampler_reduced.pt written", out["sde"].abs().max().item(), out["posterior"].abs().max().item())
+
+
 def gen_daclip():
     sys.modules.setdefault("ftfy", types.SimpleNamespace(fix_text=lambda s: s))
     import open_clip
@@ -141,5 +166,7 @@ if __name__ == "__main__":
         gen_unet_and_sampler()
     if "daclip" in which:
         gen_daclip()
+    if "reduced" in which:
+        gen_reduced_step()
     if "daclip_l14" in which:
         gen_daclip_l14()

@@ -94,17 +94,19 @@ def posterior_step(s: Schedule, x, mu, net_out, eps, t):
     return mean + std * eps
 
 
-def reverse(s: Schedule, denoiser, xt, mu, mode="posterior", noise=None, T=None, **ctx):
+def reverse(s: Schedule, denoiser, xt, mu, mode="posterior", noise=None, T=None, time_scale=1.0, **ctx):
     """Full reverse loop (sde_utils.py:261-313).
 
     ``denoiser(x, mu, t, **ctx)`` predicts the noise; ``noise`` is a ``[T, ...]``
     tensor indexed as noise[T - t] (step order) so that both sides of a parity
     check consume identical Gaussian draws.  mode: 'sde' | 'posterior' | 'ode'.
+    ``time_scale`` = T / sample_T of reduced-step sampling (sde_utils.py:87-89,195-202: the tables are built for
+    sample_T steps and the network is queried at t * T / sample_T).
     """
     T = s.T if T is None else T
     x = xt.clone()
     for i, t in enumerate(range(T, 0, -1)):
-        n = denoiser(x, mu, float(t), **ctx)
+        n = denoiser(x, mu, float(t) * time_scale, **ctx)
         if mode == "ode":
             x = ode_step(s, x, mu, n, t)
             continue

@@ -148,3 +148,19 @@ def test_daclip_vit_l14_encode_vs_reference_golden():
     assert img_f.shape == (2, 768)
     assert (img_f - g["image_features"]).abs().max().item() < 2e-3 * g["image_features"].abs().max().item()
     assert (deg_f - g["degra_features"]).abs().max().item() < 2e-3 * g["degra_features"].abs().max().item()
+
+
+@pytest.mark.parametrize("mode", ["sde", "posterior"])
+def test_reduced_step_sampling_vs_reference_golden(net, mode):
+    """IRSDE(T=100, sample_T=20) (sde_utils.py:87-89,195-202): tables for 20 steps, the network queried at 5 t."""
+    sd, cfg = net
+    g = torch.load(os.path.join(GOLD, "sampler_reduced.pt"), weights_only=False)
+    ST = g["sample_T"]
+    inp = synthetic.restoration_inputs(1, 32, 32, T=ST, seed=g["seed"])
+    s = S.Schedule(50, ST, "cosine", 0.005)
+    assert torch.equal(s.dt, g["dt"]) and torch.equal(s.sigma_bars, g["sigma_bars"])
+    x_T = inp["lq"] + inp["eps0"] * s.max_sigma
+    with torch.no_grad():
+        x = S.reverse(s, O.make_denoiser(sd, cfg), x_T, inp["lq"], mode=mode, noise=inp["noise"],
+                      time_scale=g["T"] / ST, text_context=inp["text_context"], image_context=inp["image_context"])
+    assert (x - g[mode]).abs().max().item() < 1e-3

@@ -238,3 +238,24 @@ def test_wild_ir_variant_vs_reference_golden(cuda):
         ref = case["out"].cuda()
         assert out.shape == ref.shape
         assert rel_err(out, ref) < 2e-2, (case["shape"], rel_err(out, ref))
+
+
+@pytest.mark.parametrize("mode", ["sde", "posterior"])
+def test_reduced_step_sampling_vs_reference_golden(model, cuda, mode):
+    """IRSDE(T=100, sample_T=20) through the drop-in sampler (fused loop) against the reference's loop."""
+    from daclip_b200 import synthetic
+    from daclip_b200.sde import IRSDE
+    m, _, _ = model
+    g = torch.load(os.path.join(GOLD, "sampler_reduced.pt"), weights_only=False)
+    ST = g["sample_T"]
+    inp = {k: v.cuda() for k, v in synthetic.restoration_inputs(1, 32, 32, T=ST, seed=g["seed"]).items()}
+    sde = IRSDE(max_sigma=50, T=g["T"], sample_T=ST, schedule="cosine", eps=0.005, device=cuda)
+    assert sde.sample_scale == g["T"] / ST and torch.equal(sde.sigma_bars.cpu(), g["sigma_bars"])
+    sde.set_model(m)
+    sde.set_mu(inp["lq"])
+    x_T = inp["lq"] + inp["eps0"] * sde.max_sigma
+    fn = sde.reverse_sde if mode == "sde" else sde.reverse_posterior
+    out = fn(x_T, noise=inp["noise"], text_context=inp["text_context"], image_context=inp["image_context"]).cpu()
+    ref = g[mode]
+    assert (out - ref).abs().max().item() < 2e-2, (out - ref).abs().max().item()
+    assert psnr(out, ref) > 45.0
