@@ -1,0 +1,353 @@
+// LinearAttention, key/value side, entirely on the tcgen05 tensor cores (module_util.py:170-177 of the reference):
+//
+//   k | v = W_kv xn                      GEMM 1 per 128-pixel tile: two M128 x N128 MMAs (one per pair of heads)
+//   P = exp(k - c_d)                     epilogue, data-independent shift c_d >= |k_d| (see DAC_EPI_KVCTX)
+//   C[(h,d)][(h',e)] += P^T V            GEMM 2: M128 x N128 x K128(pixels), P and V as MN-major operands straight from
+//   S[(h,d)]         += P^T 1            the [pixel][channel] tiles the epilogue wrote; N16 against a tile of ones
+//
+// k, v and P never leave the SM, and the context accumulates in TENSOR MEMORY across all the tiles of an image (the
+// diagonal 32 x 32 blocks h = h' of C are the four per-head contexts; the off-diagonal blocks are the price of using
+// the 128-wide MMA and cost nothing that matters: the kernel is bound by its epilogue).  At an image boundary and at the
+// end the accumulator is read once and added into ctx_acc (the record format of dac_linattn_fold, nchunks = 1).
+//
+// Roles (320 threads, one persistent CTA per SM): warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 / 6-9 epilogue
+// groups.  Both groups work on EVERY tile: group g owns heads 2g, 2g+1 (weight rows are packed k_2g k_2g+1 v_2g v_2g+1
+// per group, so its N128 accumulator holds exactly its columns) and the 64-channel P / V slabs of those heads.
+// TMEM: [0,128) / [128,256) GEMM-1 accumulators of group 0 / 1, [256,384) C, [384,400) S.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <new>
+
+#include "../../include/dac_b200.h"
+#include "common.h"
+#include "tensormap.h"
+#include "tile_common.cuh"
+
+namespace dac {
+
+constexpr uint32_t kKvSlab = kTileM * 128;     // 128 rows x 64 bf16 (16 KB)
+constexpr uint32_t kColC = 256, kColS = 384;
+constexpr int kCtxRec = 32 * 32 + 64;          // {C[32][32], m[32], S[32]} per (image, head)
+
+struct KvParams {
+  int tiles, tiles_per_image, stages, nbuf;
+  const float* shift;      // [128]: c_d * log2(e), original k channel order (head-major)
+  float* ctx_acc;          // [B][4][kCtxRec]
+};
+
+template <int C>
+__global__ void __launch_bounds__(kThreads, 1)
+linattn_kv_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW,
+                  const __grid_constant__ KvParams p) {
+  constexpr int kCh = C / 64;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* wres = smem;                                         // [kCh][2 groups] x [128 rows x 128 B]
+  uint8_t* ones = wres + kCh * 2 * kKvSlab;                     // 128 x 64 bf16 of 1.0
+  uint8_t* pv = ones + kKvSlab;                                 // [nbuf][P0 P1 V0 V1]
+  uint8_t* ring = pv + static_cast<size_t>(p.nbuf) * 4 * kKvSlab;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + static_cast<size_t>(p.stages) * kKvSlab);
+  uint64_t* full = bars;                 // [8]
+  uint64_t* empty = bars + 8;            // [8]
+  uint64_t* acc_full = bars + 16;        // [2]
+  uint64_t* acc_empty = bars + 18;       // [2] count 128
+  uint64_t* pv_full = bars + 20;         // [2] count 256
+  uint64_t* pv_free = bars + 22;         // [2]
+  uint64_t* ctx_done = bars + 24;
+  uint64_t* ctx_flushed = bars + 25;     // count 128
+  uint64_t* w_full = bars + 26;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 27);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int begin, end;
+  tile_range(p.tiles, begin, end);
+  const int n = end - begin;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapX);
+    tma_prefetch_desc(&mapW);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&acc_full[g], 1);
+      mbar_init(&acc_empty[g], 128);
+      mbar_init(&pv_full[g], 256);
+      mbar_init(&pv_free[g], 1);
+    }
+    mbar_init(ctx_done, 1);
+    mbar_init(ctx_flushed, 128);
+    mbar_init(w_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  // the tile of ones (B operand of S += P^T 1): plain stores, every element equal, so the swizzle does not matter
+  for (uint32_t i = threadIdx.x; i < kKvSlab / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(ones)[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      mbar_arrive_expect_tx(w_full, kCh * 2 * kKvSlab);
+      for (int ck = 0; ck < kCh; ++ck)
+        for (int g = 0; g < 2; ++g)
+          tma_load_2d(wres + (ck * 2 + g) * kKvSlab, &mapW, w_full, ck * 64, g * 128);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int i = 0; i < n; ++i) {
+        for (int ck = 0; ck < kCh; ++ck) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full[stage], kKvSlab);
+          tma_load_2d(ring + static_cast<size_t>(stage) * kKvSlab, &mapX, &full[stage], ck * 64, (begin + i) * kTileM);
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: kv(0); then per tile i: kv(i+1), ctx(i) =====================
+    const uint32_t idesc_kv = make_idesc_bf16(kTileM, 128);
+    const uint32_t idesc_c = make_idesc_bf16(kTileM, 128) | (1u << 15) | (1u << 16);   // A and B MN-major
+    const uint32_t idesc_s = make_idesc_bf16(kTileM, 16) | (1u << 15) | (1u << 16);
+    const uint64_t desc_k = make_sw128_desc(0);
+    // MN-major operands spanning two 64-channel swizzle atoms: leading byte offset = distance between the atoms (slabs)
+    const uint64_t desc_mn = (desc_k & ~(static_cast<uint64_t>(0x3FFF) << 16)) | (static_cast<uint64_t>(kKvSlab >> 4) << 16);
+    const uint32_t ring_lo = (smem_u32(ring) & 0x3FFFF) >> 4, w_lo = (smem_u32(wres) & 0x3FFFF) >> 4,
+                   pv_lo = (smem_u32(pv) & 0x3FFFF) >> 4, ones_lo = (smem_u32(ones) & 0x3FFFF) >> 4,
+                   slab_lo = kKvSlab >> 4;
+    int stage = 0;
+    uint32_t phase = 0;
+    int cur_img = -1;
+    uint32_t flushes = 0, ctx_acc_flag = 0;
+    auto kv = [&](int i) {
+      for (int ck = 0; ck < kCh; ++ck) {
+        mbar_wait(&full[stage], phase);
+        if (ck == 0) {
+          mbar_wait(&acc_empty[0], (i & 1) ^ 1);
+          mbar_wait(&acc_empty[1], (i & 1) ^ 1);
+        }
+        tc_fence_after();
+        const uint64_t adesc = desc_k | (ring_lo + stage * slab_lo);
+        if (elect_one()) {
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            const uint64_t bdesc = desc_k | (w_lo + (ck * 2 + g) * slab_lo);
+            const uint32_t d = tmem_base + g * 128;
+            umma_bf16(d, adesc, bdesc, idesc_kv, ck ? 1u : 0u);
+            umma_bf16(d, adesc + 2, bdesc + 2, idesc_kv, 1u);
+            umma_bf16(d, adesc + 4, bdesc + 4, idesc_kv, 1u);
+            umma_bf16(d, adesc + 6, bdesc + 6, idesc_kv, 1u);
+          }
+          umma_commit(&empty[stage]);
+          if (ck == kCh - 1) {
+            umma_commit(&acc_full[0]);
+            umma_commit(&acc_full[1]);
+          }
+        }
+        __syncwarp();
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    };
+    auto ctx = [&](int i) {
+      const int img = (begin + i) / p.tiles_per_image;
+      if (img != cur_img) {
+        if (cur_img >= 0) {               // hand the finished image's accumulator to epilogue group 0, wait for the read
+          if (elect_one()) umma_commit(ctx_done);
+          __syncwarp();
+          mbar_wait(ctx_flushed, flushes & 1);
+          tc_fence_after();
+          ++flushes;
+        }
+        cur_img = img;
+        ctx_acc_flag = 0;
+      }
+      const int b = p.nbuf == 2 ? (i & 1) : 0;
+      const uint32_t use = p.nbuf == 2 ? (i >> 1) : i;     // how many times this buffer has been filled before
+      mbar_wait(&pv_full[b], use & 1);
+      tc_fence_after();
+      const uint32_t p_lo = pv_lo + b * 4 * slab_lo, v_lo = p_lo + 2 * slab_lo;
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {   // 16 pixels (rows of the [pixel][channel] tiles) per K step: +2048 B
+          const uint64_t adesc = desc_mn | (p_lo + ks * 128);
+          umma_bf16(tmem_base + kColC, adesc, desc_mn | (v_lo + ks * 128), idesc_c, ctx_acc_flag | (ks ? 1u : 0u));
+          umma_bf16(tmem_base + kColS, adesc, desc_mn | (ones_lo + ks * 128), idesc_s, ctx_acc_flag | (ks ? 1u : 0u));
+        }
+        umma_commit(&pv_free[b]);
+      }
+      __syncwarp();
+      ctx_acc_flag = 1;
+    };
+    mbar_wait(w_full, 0);
+    if (n > 0) kv(0);
+    for (int i = 0; i < n; ++i) {
+      if (i + 1 < n) kv(i + 1);
+      ctx(i);
+    }
+    if (n > 0) {
+      if (elect_one()) umma_commit(ctx_done);
+      __syncwarp();
+    }
+  } else {
+    // ===================== epilogue groups =====================
+    const int quad = warp & 3;
+    const int g = (warp - 2) >> 2;
+    const int row = quad * 32 + lane;
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const uint32_t acc = lane_base + g * 128;
+    float v[32];
+    uint32_t flushes = 0;
+    // group 0 adds the accumulated {C, S} of image `img` into ctx_acc: TMEM lane = (head, d)
+    auto flush = [&](int img) {
+      mbar_wait(ctx_done, flushes & 1);
+      tc_fence_after();
+      ++flushes;
+      const int h = quad, d = lane;                       // lane row = 32 h + d
+      float* rec = p.ctx_acc + (static_cast<long long>(img) * 4 + h) * kCtxRec;
+      chunk_from_tmem(lane_base + kColC + 32 * h, v);     // the diagonal block: columns (h, e)
+#pragma unroll
+      for (int e = 0; e < 32; ++e) atomicAdd(rec + d * 32 + e, v[e]);
+      uint32_t r[16];
+      tmem_ld16(lane_base + kColS, r);
+      tmem_ld_wait();
+      atomicAdd(rec + 1056 + d, __uint_as_float(r[0]));
+      tc_fence_before();
+      mbar_arrive(ctx_flushed);
+    };
+    int prev_img = -1;
+    for (int i = 0; i < n; ++i) {
+      const int img = (begin + i) / p.tiles_per_image;
+      const int b = p.nbuf == 2 ? (i & 1) : 0;
+      const uint32_t use = p.nbuf == 2 ? (i >> 1) : i;
+      uint8_t* pt = pv + (static_cast<size_t>(b) * 4 + g) * kKvSlab;        // P slab of this group's heads
+      uint8_t* vt = pt + 2 * kKvSlab;                                       // V slab
+      mbar_wait(&acc_full[g], i & 1);
+      mbar_wait(&pv_free[b], (use & 1) ^ 1);                                // GEMM 2 of the previous user is done
+      tc_fence_after();
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        chunk_from_tmem(acc + 32 * j, v);                                   // k of head 2g + j
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + (2 * g + j) * 32) + q);
+          v[4 * q] = ex2_approx(fmaf(v[4 * q], 1.4426950408889634f, -sh.x));
+          v[4 * q + 1] = ex2_approx(fmaf(v[4 * q + 1], 1.4426950408889634f, -sh.y));
+          v[4 * q + 2] = ex2_approx(fmaf(v[4 * q + 2], 1.4426950408889634f, -sh.z));
+          v[4 * q + 3] = ex2_approx(fmaf(v[4 * q + 3], 1.4426950408889634f, -sh.w));
+        }
+        chunk_stage_bf16(pt, row, 32 * j, v);
+        chunk_from_tmem(acc + 64 + 32 * j, v);                              // v of head 2g + j
+        chunk_stage_bf16(vt, row, 32 * j, v);
+      }
+      tc_fence_before();
+      mbar_arrive(&acc_empty[g]);
+      fence_proxy_async();
+      mbar_arrive(&pv_full[b]);
+      if (g == 0 && prev_img >= 0 && img != prev_img) flush(prev_img);      // the issuer is waiting before ctx(i)
+      prev_img = img;
+    }
+    if (g == 0 && n > 0) flush(prev_img);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace dac
+
+using namespace dac;
+
+struct dac_kv_plan {
+  CUtensorMap mapX, mapW;
+  KvParams kp;
+  int C, B, grid, smem;
+};
+
+static int kv_encode_2d(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t rows, uint32_t box_rows,
+                        const char* what) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return set_error(-10, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+  cuuint64_t dims[2] = {inner, rows};
+  cuuint64_t strides[1] = {inner * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(-11, "cuTensorMapEncodeTiled(%s) failed: CUresult %d", what, (int)r);
+  return 0;
+}
+
+extern "C" int dac_linattn_kv_create(const void* xn, const void* wkv, const float* kv_shift, float* ctx_acc,
+                                     int32_t B, int32_t hw, int32_t C, dac_kv_t* plan) {
+  if (!xn || !wkv || !kv_shift || !ctx_acc || !plan) return set_error(-1, "dac_linattn_kv_create: null argument");
+  *plan = nullptr;
+  if (C != 64 && C != 128) return set_error(-2, "dac_linattn_kv_create: C must be 64 or 128 (got %d)", C);
+  if (B <= 0 || hw <= 0 || hw % kTileM) return set_error(-2, "dac_linattn_kv_create: hw must be a multiple of 128");
+  if ((reinterpret_cast<uintptr_t>(xn) | reinterpret_cast<uintptr_t>(wkv) | reinterpret_cast<uintptr_t>(kv_shift) |
+       reinterpret_cast<uintptr_t>(ctx_acc)) & 15)
+    return set_error(-2, "dac_linattn_kv_create: pointers must be 16-byte aligned");
+  dac_kv_plan* pl = new (std::nothrow) dac_kv_plan();
+  if (!pl) return set_error(-3, "out of host memory");
+  const uint64_t rows = static_cast<uint64_t>(B) * hw;
+  int rc = kv_encode_2d(&pl->mapX, xn, C, rows, kTileM, "xn");
+  if (!rc) rc = kv_encode_2d(&pl->mapW, wkv, C, 256, 128, "wkv");
+  if (rc) { delete pl; return rc; }
+  KvParams& k = pl->kp;
+  k.tiles = static_cast<int>(rows / kTileM);
+  k.tiles_per_image = hw / kTileM;
+  k.shift = kv_shift;
+  k.ctx_acc = ctx_acc;
+  k.nbuf = C == 64 ? 2 : 1;
+  const int fixed = (C / 64) * 2 * (int)kKvSlab + (int)kKvSlab + k.nbuf * 4 * (int)kKvSlab + 1024 + 512;
+  int stages = (227 * 1024 - fixed) / (int)kKvSlab;
+  if (stages > 8) stages = 8;
+  if (stages < 2) { delete pl; return set_error(-2, "dac_linattn_kv_create: does not fit shared memory"); }
+  k.stages = stages;
+  pl->smem = fixed + stages * (int)kKvSlab;
+  pl->C = C;
+  pl->B = B;
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  pl->grid = k.tiles < sms ? k.tiles : sms;
+  cudaError_t e = C == 64 ? cudaFuncSetAttribute(linattn_kv_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->smem)
+                          : cudaFuncSetAttribute(linattn_kv_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->smem);
+  if (e != cudaSuccess) {
+    const int smem = pl->smem;
+    delete pl;
+    return set_error(-12, "dac_linattn_kv_create: cudaFuncSetAttribute(%d B smem): %s", smem, cudaGetErrorString(e));
+  }
+  *plan = pl;
+  return 0;
+}
+
+extern "C" int dac_linattn_kv_launch(dac_kv_t pl, dac_stream_t stream) {
+  if (!pl) return set_error(-1, "dac_linattn_kv_launch: null plan");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemsetAsync(pl->kp.ctx_acc, 0, sizeof(float) * pl->B * 4 * kCtxRec, st);
+  if (e != cudaSuccess) return set_error(-20, "dac_linattn_kv_launch: memset failed: %s", cudaGetErrorString(e));
+  if (pl->C == 64) linattn_kv_kernel<64><<<pl->grid, kThreads, pl->smem, st>>>(pl->mapX, pl->mapW, pl->kp);
+  else linattn_kv_kernel<128><<<pl->grid, kThreads, pl->smem, st>>>(pl->mapX, pl->mapW, pl->kp);
+  return check_launch("linattn_kv_kernel");
+}
+
+extern "C" void dac_linattn_kv_destroy(dac_kv_t pl) { delete pl; }

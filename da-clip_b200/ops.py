@@ -250,6 +250,37 @@ class ConvPlan:
             pass
 
 
+def pack_kv_grouped(wkv):
+    """[256, C] rows (k heads 0-3 | v heads 0-3, 32 each) -> rows packed per head pair g: k_2g k_2g+1 v_2g v_2g+1
+    (the N = 128 accumulator of epilogue group g then holds exactly its heads); bf16 contiguous."""
+    k, v = wkv[:128].reshape(2, 64, -1), wkv[128:].reshape(2, 64, -1)
+    return torch.cat([k[0], v[0], k[1], v[1]], 0).to(torch.bfloat16).contiguous()
+
+
+class KvPlan:
+    """LinearAttention key/value side on tcgen05: k|v GEMM, exp, context GEMM accumulated in tensor memory."""
+
+    def __init__(self, xn, wkv_grouped, kv_shift, ctx_acc, B, hw, Cn):
+        L.require_cuda(xn, wkv_grouped, kv_shift, ctx_acc)
+        lib = L.load()
+        h = C.c_void_p()
+        L.check(lib.dac_linattn_kv_create(xn.data_ptr(), wkv_grouped.data_ptr(), kv_shift.data_ptr(),
+                                          ctx_acc.data_ptr(), B, hw, Cn, C.byref(h)))
+        self.handle, self._lib = h, lib
+        self._keep = (xn, wkv_grouped, kv_shift, ctx_acc)
+        self.flops = 2.0 * B * hw * Cn * 256
+
+    def run(self):
+        L.check(self._lib.dac_linattn_kv_launch(self.handle, L.stream_ptr()))
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self._lib.dac_linattn_kv_destroy(self.handle)
+        except Exception:
+            pass
+
+
 class QoutPlan:
     """LinearAttention query side (to_q softmax -> W_eff q -> LayerNorm -> + x) as one chained-GEMM launch."""
 

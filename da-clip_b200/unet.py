@@ -310,6 +310,7 @@ class PackedUNet:
             wk = wq[128:256].to(torch.bfloat16).float()
             kbound = 1.02 * wk.norm(dim=1) * math.sqrt(dim)
             a.update(q=ops.pack_linear(wq[:128].contiguous()), kv=ops.pack_linear(wq[128:].contiguous()),
+                     kv_grouped=ops.pack_kv_grouped(wq[128:]),
                      kv_shift=(kbound * 1.4426950408889634).contiguous(), kv_safe=bool(kbound.max().item() <= 40.0))
             a.update(qkv=ops.pack_linear(wq),
                      qkv_colsum=wq.to(torch.bfloat16).float().sum(dim=1).contiguous(),      # of the bf16 operand
@@ -415,6 +416,7 @@ class UNetEngine:
     # producer +14 us vs the 54 us LayerNorm kernel saved): the QKV epilogue is already the bottleneck of that
     # store-bound layer.  Kept as a tested option (tests/test_kernels_gpu.py::test_prenorm_folded_into_qkv).
     FOLD_PRENORM = False
+    FUSE_KV_TC = True      # LinearAttention: the k|v context reduction as a second tcgen05 GEMM (TMEM-resident context)
     FUSE_QOUT = True       # LinearAttention: to_q + softmax + to_out + LayerNorm + residual as one chained-GEMM kernel
     FUSE_KVCTX = True      # LinearAttention: reduce k | v into the context inside the to_kv GEMM epilogue
 
@@ -436,8 +438,17 @@ class UNetEngine:
                 xn = self.buf(B, h, w, C)
                 self.add(prefix + "prenorm", lambda: ops.layernorm_rows(x, xn, B * hw, C, None, None, 1e-5))
                 ctx = self.buf(B, 4, 1, 32 * 34, dtype=torch.float32)
-                self.conv(prefix + "to_kv", xn, C, a["kv"], None, h, w, epi=L.EPI_KVCTX, block_n=256,
-                          kv_shift=a["kv_shift"], ctx_acc=ctx)
+                if self.FUSE_KV_TC and C == 64 and hw % 128 == 0:
+                    # ... and reduced on tcgen05 too: P^T V with MN-major operands, context accumulated in TMEM
+                    # (measured: 128 -> 111 us at level 0; the C = 128 instances have room for one P|V buffer only
+                    # and run 25 % slower than the KVCTX epilogue, so they keep it)
+                    plan = ops.KvPlan(xn, a["kv_grouped"], a["kv_shift"], ctx, B, hw, C)
+                    self.flops += plan.flops
+                    self.conv_names.add(prefix + "to_kv")
+                    self.add(prefix + "to_kv", plan.run)
+                else:
+                    self.conv(prefix + "to_kv", xn, C, a["kv"], None, h, w, epi=L.EPI_KVCTX, block_n=256,
+                              kv_shift=a["kv_shift"], ctx_acc=ctx)
                 weff = self.buf(B, c_pad, 128)
                 self.flops += 2.0 * B * 4 * 32 * 32 * hw
                 if self.FUSE_QOUT and C in (64, 128) and hw % 128 == 0:

@@ -183,6 +183,17 @@ int dac_linattn_context(const void* kv, int32_t B, int32_t hw, int32_t nchunks, 
 int dac_linattn_fold(const float* partial, int32_t B, int32_t hw, int32_t nchunks, const float* w_out /*[C,128] fp32*/,
                      int32_t C, int32_t c_pad, void* weff /*[B][c_pad][128] bf16*/, dac_stream_t stream);
 
+/* Key/value side of LinearAttention entirely on tcgen05 (MU:170-177): per 128-pixel tile k | v = wkv . xn, P = exp(k - c_d)
+ * (kv_shift as for DAC_EPI_KVCTX), then C += P^T V and S += P^T 1 as a second tensor-core GEMM with MN-major operands,
+ * accumulated in tensor memory over the tiles of an image and added into ctx_acc ([B][4][1088] fp32, zeroed by the
+ * launch; record format of dac_linattn_fold with nchunks = 1).  xn: bf16 [B*hw, C] (C = 64 or 128, hw % 128 == 0);
+ * wkv: bf16 [256][C], rows packed per head pair g as k_2g k_2g+1 v_2g v_2g+1.  Replaces DAC_EPI_KVCTX where it fits. */
+typedef struct dac_kv_plan* dac_kv_t;
+int dac_linattn_kv_create(const void* xn, const void* wkv, const float* kv_shift, float* ctx_acc, int32_t B,
+                          int32_t hw, int32_t C, dac_kv_t* plan);
+int dac_linattn_kv_launch(dac_kv_t plan, dac_stream_t stream);
+void dac_linattn_kv_destroy(dac_kv_t plan);
+
 /* Query side of LinearAttention as ONE chained-GEMM kernel (MU:170-185): per 128-pixel tile
  *   q = softmax_head-channels(wq . xn) * 32^-0.5   (kept in shared memory, bf16)
  *   out = LayerNorm_c(weff[b] . q + bias) * ln_g + res

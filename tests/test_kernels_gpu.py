@@ -358,6 +358,31 @@ def test_linear_attention_fused_kv_context(ops, gen, B, H, W, C):
     assert_close_bf16(weff[:, :C], weff_ref, "folded context weight", rel=2 ** -6, abs_=1e-2)
 
 
+@pytest.mark.parametrize("B,H,W,C", [(3, 32, 32, 64), (2, 16, 40, 128), (5, 64, 48, 64), (1, 8, 16, 128), (40, 16, 8, 64)])
+def test_linear_attention_kv_tensor_core_context(ops, gen, B, H, W, C):
+    """dac_linattn_kv: k|v GEMM -> exp -> P^T V / P^T 1 as a second tcgen05 GEMM with MN-major operands, context held
+    in tensor memory across tiles and flushed per image; checked against softmax_pixels(k) v^T / hw in fp32."""
+    hw = H * W
+    x = rnd(gen, B, C, H, W) * 1.7 + 0.3
+    xn = (x - x.mean(1, keepdim=True)) * torch.rsqrt(x.var(1, unbiased=False, keepdim=True) + 1e-5)
+    xh = nhwc(xn)
+    wkv = rnd(gen, 256, C, scale=C ** -0.5)
+    wkv[:128] *= 1.5
+    shift = 1.02 * bf(wkv[:128]).float().norm(dim=1) * math.sqrt(C)
+    ctx = torch.full((B, 4, 1, 32 * 34), float("nan"), device="cuda")
+    plan = ops.KvPlan(xh, ops.pack_kv_grouped(wkv), (shift * 1.4426950408889634).contiguous(), ctx, B, hw, C)
+    for _ in range(2):
+        plan.run()
+    torch.cuda.synchronize()
+    kvr = F.conv2d(nchw(xh), bf(wkv).float()[:, :, None, None]).reshape(B, 2, 4, 32, hw)
+    k, v = kvr[:, 0].softmax(-1), kvr[:, 1] / hw
+    ctx_ref = torch.einsum("bhdn,bhen->bhde", k, v)
+    got = ctx[:, :, 0, :1024].reshape(B, 4, 32, 32) / (ctx[:, :, 0, 1056:1088, None] * hw)
+    scale = ctx_ref.abs().max().item()
+    assert torch.isfinite(got).all()
+    assert (got - ctx_ref).abs().max().item() <= 6e-3 * scale, (got - ctx_ref).abs().max().item() / scale
+
+
 @pytest.mark.parametrize("B,H,W,C", [(3, 32, 32, 64), (2, 16, 40, 128), (5, 64, 48, 64), (1, 8, 16, 128)])
 def test_linear_attention_chained_q_out(ops, gen, B, H, W, C):
     """Whole LinearAttention block on the fused path: KVCTX context -> fold -> chained kernel (to_q, head softmax,
