@@ -4,7 +4,8 @@
 // m16n8k16 bf16, fp32 accumulate; B fragments via ldmatrix / ldmatrix.trans), online softmax in registers.
 //  * d = 32: SpatialTransformer self-attention (attention.py:178-192), n = 1024 / 4096 tokens, 8 warps per CTA;
 //    2 % of the step's FLOPs at 256^2 (the convolution GEMMs are the tcgen05 kernels).
-//  * d = 64: the ViT-B/32 blocks of DA-CLIP (transformer.py:219-230), n = 50 tokens, 4 warps per (image, head).
+//  * d = 64: the ViT-B/32 blocks of DA-CLIP (transformer.py:219-230), n = 50 tokens, 4 warps per (image, head);
+//    with kCausal the CLIP text tower (model.py:237-249: 77 tokens under build_attention_mask's upper-triangular -inf).
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdlib.h>
@@ -25,7 +26,7 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src
 // 128 query rows per CTA (8 warps x 16 rows); 64-key blocks of K and V, row-major [key][d], double-buffered with
 // cp.async; B fragments via ldmatrix (K) / ldmatrix.trans (V); online softmax with ex2.approx (one MUFU per score -
 // at d = 32 the SFU pipe, not the tensor pipe, bounds this kernel).
-template <int kFaD, int kWarps>
+template <int kFaD, int kWarps, bool kCausal = false>
 __global__ void __launch_bounds__(kWarps * 32) flash_attn_kernel(const __nv_bfloat16* __restrict__ qkv,
                                                                  __nv_bfloat16* __restrict__ out, int n, int heads,
                                                                  float scale_log2) {
@@ -78,10 +79,12 @@ __global__ void __launch_bounds__(kWarps * 32) flash_attn_kernel(const __nv_bflo
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
 
   int buf = 0;
-  for (int k0 = 0; k0 < n; k0 += kFaBlockK, buf ^= 1) {
+  // causal: key blocks past the CTA's last query row contribute nothing
+  const int k_end = kCausal ? min(n, (qb + 1) * kFaBlockQ) : n;
+  for (int k0 = 0; k0 < k_end; k0 += kFaBlockK, buf ^= 1) {
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();                                   // block k0 landed; everyone is done with the other buffer
-    if (k0 + kFaBlockK < n) prefetch(buf ^ 1, k0 + kFaBlockK);
+    if (k0 + kFaBlockK < k_end) prefetch(buf ^ 1, k0 + kFaBlockK);
     const __nv_bfloat16* Kb = Ks[buf];
     const __nv_bfloat16* Vb = Vs[buf];
 
@@ -104,6 +107,16 @@ __global__ void __launch_bounds__(kWarps * 32) flash_attn_kernel(const __nv_bflo
         const int key = k0 + j * 8 + cq;
         if (key >= n) s[j][0] = s[j][2] = -INFINITY;
         if (key + 1 >= n) s[j][1] = s[j][3] = -INFINITY;
+      }
+    }
+    if (kCausal && k0 + kFaBlockK > qb * kFaBlockQ) {  // query i sees keys <= i (key 0 is always visible)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int key = k0 + j * 8 + cq;
+        if (key > r0) s[j][0] = -INFINITY;
+        if (key + 1 > r0) s[j][1] = -INFINITY;
+        if (key > r0 + 8) s[j][2] = -INFINITY;
+        if (key + 1 > r0 + 8) s[j][3] = -INFINITY;
       }
     }
     // online softmax (rows r0: regs 0,1; r0+8: regs 2,3)
@@ -193,4 +206,14 @@ extern "C" int dac_attention(const void* qkv, void* out, int32_t B, int32_t n, i
     return check_launch("flash_attn_kernel<64>");
   }
   return set_error(-2, "dac_attention: unsupported head dim %d / length %d", d, n);
+}
+
+extern "C" int dac_attention_causal(const void* qkv, void* out, int32_t B, int32_t n, int32_t heads, int32_t d,
+                                    dac_stream_t stream) {
+  if (!qkv || !out) return set_error(-1, "dac_attention_causal: null argument");
+  if (d != 64 || B <= 0 || n <= 0 || heads <= 0)
+    return set_error(-2, "dac_attention_causal: head dim 64 only (got %d), positive sizes", d);
+  flash_attn_kernel<64, 4, true><<<dim3((n + 63) / 64, heads, B), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), n, heads, 0.125f * 1.4426950408889634f);
+  return check_launch("flash_attn_kernel<64, causal>");
 }

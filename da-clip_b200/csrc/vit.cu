@@ -71,7 +71,9 @@ __global__ void __launch_bounds__(256) vit_embed_kernel(const __nv_bfloat16* __r
 
 // kPoolImgs images per CTA: ln_post(x[b,0,:]) for each, then @ proj with every projection row read once per CTA
 constexpr int kPoolImgs = 8;
-__global__ void __launch_bounds__(256) vit_pool_kernel(const float* __restrict__ x, int B, int L, int w,
+// (row_index: the token pooled per image - NULL = the class token 0; the text tower pools its end-of-text token)
+__global__ void __launch_bounds__(256) vit_pool_kernel(const float* __restrict__ x, const int* __restrict__ row_index,
+                                                       int B, int L, int w,
                                                        const float* __restrict__ ln_w, const float* __restrict__ ln_b,
                                                        float eps, const float* __restrict__ proj, int e,
                                                        float* __restrict__ out) {
@@ -79,7 +81,7 @@ __global__ void __launch_bounds__(256) vit_pool_kernel(const float* __restrict__
   const int b0 = blockIdx.x * kPoolImgs;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp < kPoolImgs && b0 + warp < B) {   // one warp normalises one class token
-    const float* src = x + static_cast<int64_t>(b0 + warp) * L * w;
+    const float* src = x + (static_cast<int64_t>(b0 + warp) * L + (row_index ? row_index[b0 + warp] : 0)) * w;
     float* row = rows + warp * w;
     float s = 0.f;
     for (int i = lane; i < w; i += 32) {
@@ -124,6 +126,38 @@ __global__ void __launch_bounds__(256) vit_pool_kernel(const float* __restrict__
     for (int m = 0; m < kPoolImgs; ++m)
       if (b0 + m < B)
         out[static_cast<int64_t>(b0 + m) * e + j] = ((part[0][m][jl] + part[1][m][jl]) + part[2][m][jl]) + part[3][m][jl];
+  }
+}
+
+// CLIP text-tower entry (open_clip/model.py:240-242,248): one CTA per token, x[b,t,:] = token_embedding[text[b,t]] +
+// positional_embedding[t] in fp32; the CTA of token 0 also records eot[b] = argmax_t text[b,t] (first maximum, the
+// torch.argmax rule; the end-of-text id is the largest of the vocabulary).  Ids outside [0, vocab) are clamped here;
+// the host binding rejects them before the launch (the reference raises an IndexError).
+__global__ void __launch_bounds__(128) text_embed_kernel(const int64_t* __restrict__ text,
+                                                         const float* __restrict__ emb, const float* __restrict__ pos,
+                                                         float* __restrict__ out, int* __restrict__ eot, int L, int w,
+                                                         int vocab) {
+  const int t = blockIdx.x % L, b = blockIdx.x / L;
+  int64_t id = text[static_cast<int64_t>(b) * L + t];
+  id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+  const float4* e = reinterpret_cast<const float4*>(emb + id * w);
+  const float4* p = reinterpret_cast<const float4*>(pos + static_cast<int64_t>(t) * w);
+  float4* o = reinterpret_cast<float4*>(out + (static_cast<int64_t>(b) * L + t) * w);
+  for (int i = threadIdx.x; i < w / 4; i += blockDim.x) {
+    const float4 a = __ldg(e + i), c = __ldg(p + i);
+    o[i] = make_float4(a.x + c.x, a.y + c.y, a.z + c.z, a.w + c.w);
+  }
+  if (t == 0 && threadIdx.x == 0) {
+    int best = 0;
+    int64_t bv = text[static_cast<int64_t>(b) * L];
+    for (int i = 1; i < L; ++i) {
+      const int64_t v = text[static_cast<int64_t>(b) * L + i];
+      if (v > bv) {
+        bv = v;
+        best = i;
+      }
+    }
+    eot[b] = best;
   }
 }
 
@@ -194,9 +228,29 @@ extern "C" int dac_vit_pool(const void* x, int32_t B, int32_t L, int32_t w, cons
                             float eps, const float* proj, int32_t e, float* out, dac_stream_t stream) {
   if (!x || !ln_w || !ln_b || !proj || !out) return set_error(-1, "dac_vit_pool: null argument");
   vit_pool_kernel<<<dim3((B + kPoolImgs - 1) / kPoolImgs, (e + 63) / 64), 256, kPoolImgs * w * sizeof(float),
-                    static_cast<cudaStream_t>(stream)>>>(static_cast<const float*>(x), B, L, w, ln_w, ln_b, eps, proj, e,
-                                                         out);
+                    static_cast<cudaStream_t>(stream)>>>(static_cast<const float*>(x), nullptr, B, L, w, ln_w, ln_b, eps,
+                                                         proj, e, out);
   return check_launch("vit_pool_kernel");
+}
+
+extern "C" int dac_text_embed(const int64_t* text, const float* token_embedding, const float* pos, float* out,
+                              int32_t* eot, int32_t B, int32_t L, int32_t w, int32_t vocab, dac_stream_t stream) {
+  if (!text || !token_embedding || !pos || !out || !eot) return set_error(-1, "dac_text_embed: null argument");
+  if (B <= 0 || L <= 0 || w <= 0 || (w & 3) || vocab <= 0)
+    return set_error(-2, "dac_text_embed: sizes must be positive, width a multiple of 4");
+  text_embed_kernel<<<B * L, 128, 0, static_cast<cudaStream_t>(stream)>>>(text, token_embedding, pos, out, eot, L, w,
+                                                                         vocab);
+  return check_launch("text_embed_kernel");
+}
+
+extern "C" int dac_text_pool(const void* x, const int32_t* eot, int32_t B, int32_t L, int32_t w, const float* ln_w,
+                             const float* ln_b, float eps, const float* proj, int32_t e, float* out,
+                             dac_stream_t stream) {
+  if (!x || !eot || !ln_w || !ln_b || !proj || !out) return set_error(-1, "dac_text_pool: null argument");
+  vit_pool_kernel<<<dim3((B + kPoolImgs - 1) / kPoolImgs, (e + 63) / 64), 256, kPoolImgs * w * sizeof(float),
+                    static_cast<cudaStream_t>(stream)>>>(static_cast<const float*>(x), eot, B, L, w, ln_w, ln_b, eps,
+                                                         proj, e, out);
+  return check_launch("vit_pool_kernel(text)");
 }
 
 extern "C" int dac_degradation_argmax(const float* degra, const float* text, int32_t B, int32_t e, int32_t classes,

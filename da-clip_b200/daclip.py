@@ -1,12 +1,14 @@
-"""DaCLIP image side with the reference's API (open_clip/daclip_model.py:17-76, transformer.py:288-555,
+"""DaCLIP with the reference's API (open_clip/daclip_model.py:17-76, transformer.py:288-555, model.py:187-249,
 factory.py:365-404 of the reference): `encode_image(image, control=True)` -> (image_features, degra_features),
 two ViT-B/32 towers, the control tower's per-layer hidden states (through their zero-init linears) added to the
-frozen CLIP tower in REVERSED order (`control.pop()`, transformer.py:367-368).
+frozen CLIP tower in REVERSED order (`control.pop()`, transformer.py:367-368); `encode_text(tokens)` -> the CLIP text
+tower (12 causal pre-LN blocks over 77 tokens, end-of-text token pooled through ln_final and text_projection), used once
+per deployment for the degradation prompts.
 
 The module holds parameters under the reference's state-dict keys (`visual.*`, its alias `clip.visual.*`,
-`visual_control.*` incl. `visual_control.transformer.zero_modules.N`, `logit_scale`); text-tower keys of a full
-631-key checkpoint are accepted and kept aside (the 10 degradation prompts are encoded once per deployment by
-the reference's own text tower - SURVEY.md section 8f N4 - and enter here as a [classes, 512] tensor).
+`visual_control.*` incl. `visual_control.transformer.zero_modules.N`, `logit_scale`, and the text side `clip.transformer.*`,
+`clip.token_embedding.weight`, `clip.positional_embedding`, `clip.ln_final.*`, `clip.text_projection`, `clip.logit_scale`:
+the 631 keys of a full checkpoint).
 
 Execution: every GEMM (patch embedding, in_proj, out_proj, c_fc, c_proj, zero-linear) is the tcgen05 kernel with
 tokens as pixels (M = 50*B); the residual stream stays fp32 (fp32 residual in the GEMM epilogue) so that the
@@ -81,25 +83,63 @@ class _VisionTransformer(_Holder):  # transformer.py:372-555
         self.proj = nn.Parameter(scale * torch.randn(width, embed_dim))
 
 
+class _TextSide(_Holder):
+    """Text half of open_clip's CLIP (model.py:203-213) under the reference's `clip.*` keys; initialised like
+    TextTransformer.init_parameters (transformer.py:609-627)."""
+
+    def __init__(self, width=512, heads=8, layers=12, context_length=77, vocab_size=49408, embed_dim=512):
+        super().__init__()
+        self.width, self.heads, self.layers = width, heads, layers
+        self.context_length, self.vocab_size = context_length, vocab_size
+        self.transformer = _Transformer(width, layers, heads)
+        self.token_embedding = nn.Embedding(vocab_size, width)
+        self.positional_embedding = nn.Parameter(torch.empty(context_length, width))
+        self.ln_final = nn.LayerNorm(width)
+        self.text_projection = nn.Parameter(torch.empty(width, embed_dim))
+        self.logit_scale = nn.Parameter(torch.ones([]) * 2.6592600)
+        nn.init.normal_(self.token_embedding.weight, std=0.02)
+        nn.init.normal_(self.positional_embedding, std=0.01)
+        proj_std, attn_std, fc_std = (width ** -0.5) * ((2 * layers) ** -0.5), width ** -0.5, (2 * width) ** -0.5
+        for r in self.transformer.resblocks:
+            nn.init.normal_(r.attn.in_proj_weight, std=attn_std)
+            nn.init.normal_(r.attn.out_proj.weight, std=proj_std)
+            nn.init.normal_(r.mlp.c_fc.weight, std=fc_std)
+            nn.init.normal_(r.mlp.c_proj.weight, std=proj_std)
+        nn.init.normal_(self.text_projection, std=width ** -0.5)
+
+
 class DaCLIP(nn.Module):
-    """Image side of open_clip's `daclip_ViT-B-32` (model_configs/daclip_ViT-B-32.json; the defaults) and of
-    `daclip_ViT-L-14` (model_configs/daclip_ViT-L-14.json, the wild-ir encoder: see ARCHS)."""
+    """open_clip's `daclip_ViT-B-32` (model_configs/daclip_ViT-B-32.json; the defaults) and `daclip_ViT-L-14`
+    (model_configs/daclip_ViT-L-14.json, the wild-ir encoder: see ARCHS)."""
 
-    ARCHS = {"daclip_ViT-B-32": dict(image_size=224, patch=32, width=768, layers=12, heads=12, embed_dim=512),
-             "daclip_ViT-L-14": dict(image_size=224, patch=14, width=1024, layers=24, heads=16, embed_dim=768)}
+    ARCHS = {"daclip_ViT-B-32": dict(image_size=224, patch=32, width=768, layers=12, heads=12, embed_dim=512,
+                                     text_width=512, text_heads=8, text_layers=12),
+             "daclip_ViT-L-14": dict(image_size=224, patch=14, width=1024, layers=24, heads=16, embed_dim=768,
+                                     text_width=768, text_heads=12, text_layers=12)}
 
-    def __init__(self, image_size=224, patch=32, width=768, layers=12, heads=12, embed_dim=512):
+    def __init__(self, image_size=224, patch=32, width=768, layers=12, heads=12, embed_dim=512,
+                 text_width=512, text_heads=8, text_layers=12, context_length=77, vocab_size=49408):
         super().__init__()
         self.visual = _VisionTransformer(image_size, patch, width, layers, heads, embed_dim)
         self.visual_control = _VisionTransformer(image_size, patch, width, layers, heads, embed_dim, control=True)
         self.logit_scale = nn.Parameter(torch.ones([]) * 2.6592600)
-        self.text_state = OrderedDict()      # text-tower tensors of a full checkpoint, untouched
+        self.clip = _TextSide(text_width, text_heads, text_layers, context_length, vocab_size, embed_dim)
+        self.context_length, self.vocab_size = context_length, vocab_size
+        self.has_text_weights = False         # set by load_reference_state_dict when the checkpoint carries the text side
         self._engines = {}
+        self._text_engines = {}
         self._packed = None
+        self._packed_text = None
         self.register_load_state_dict_post_hook(lambda m, keys: m.invalidate())
 
     def invalidate(self):
         self._engines, self._packed = {}, None
+        self._text_engines, self._packed_text = {}, None
+
+    @property
+    def text_state(self):
+        """The text-side tensors under their reference keys (`clip.*`)."""
+        return OrderedDict((k, v) for k, v in self.state_dict().items() if k.startswith("clip."))
 
     def _apply(self, fn, *a, **k):
         self.invalidate()
@@ -111,7 +151,7 @@ class DaCLIP(nn.Module):
         if "state_dict" in sd and isinstance(sd["state_dict"], dict):
             sd = sd["state_dict"]
         own = self.state_dict()
-        mine, self.text_state = OrderedDict(), OrderedDict()
+        mine, unexpected = OrderedDict(), []
         for k, v in sd.items():
             k = k[7:] if k.startswith("module.") else k
             if k.startswith("clip.visual."):
@@ -119,11 +159,18 @@ class DaCLIP(nn.Module):
             if k in own:
                 mine[k] = v
             else:
-                self.text_state[k] = v
-        missing = [k for k in own if k not in mine and k != "logit_scale"]
+                unexpected.append(k)
+        if unexpected:
+            raise KeyError(f"checkpoint has {len(unexpected)} tensors this model does not know, e.g. {unexpected[:3]}")
+        missing = [k for k in own if k not in mine and not k.startswith("clip.") and k != "logit_scale"]
         if missing:
             raise KeyError(f"checkpoint lacks {len(missing)} image-side tensors, e.g. {missing[:3]}")
-        mine.setdefault("logit_scale", own["logit_scale"])
+        text_missing = [k for k in own if k.startswith("clip.") and k not in mine and k != "clip.logit_scale"]
+        if text_missing and len(text_missing) != sum(k.startswith("clip.") and k != "clip.logit_scale" for k in own):
+            raise KeyError(f"checkpoint has part of the text tower only; missing e.g. {text_missing[:3]}")
+        self.has_text_weights = not text_missing        # image-side-only checkpoints keep the text side's init
+        for k in own:
+            mine.setdefault(k, own[k])
         self.load_state_dict(mine, strict=True)
         return self
 
@@ -148,6 +195,29 @@ class DaCLIP(nn.Module):
             img_f = torch.nn.functional.normalize(img_f, dim=-1)      # plumbing on [B,512] outputs
             deg_f = torch.nn.functional.normalize(deg_f, dim=-1)
         return img_f, deg_f
+
+    def encode_text(self, text, normalize=False):
+        """CLIP.encode_text (model.py:237-249) through DaCLIP.encode_text (daclip_model.py:55-56): text = int64 token ids
+        [N, context_length] (see daclip_b200.tokenizer) -> fp32 [N, embed_dim] features of each row's end-of-text token."""
+        dev = self.visual.proj.device
+        if dev.type != "cuda":
+            raise L.DacError("DaCLIP (daclip_b200) runs on CUDA only")
+        if text.dim() != 2 or text.shape[1] != self.context_length:
+            raise ValueError(f"encode_text takes [N, {self.context_length}] token ids, got {tuple(text.shape)}")
+        if text.dtype not in (torch.int64, torch.int32):
+            raise TypeError("encode_text takes integer token ids")
+        if text.numel() and (int(text.min()) < 0 or int(text.max()) >= self.vocab_size):
+            raise IndexError("index out of range in self")        # what nn.Embedding raises in the reference
+        N = text.shape[0]
+        if self._packed_text is None:
+            self._packed_text = _PackedText(self.clip)
+        if N not in self._text_engines:
+            self._text_engines[N] = _TextEngine(self._packed_text, self.clip, N, dev)
+        eng = self._text_engines[N]
+        eng.tokens.copy_(text.to(device=dev, dtype=torch.int64))
+        eng.replay()
+        f = eng.features.clone()
+        return torch.nn.functional.normalize(f, dim=-1) if normalize else f
 
     def degradation_argmax(self, degra_features, text_features, return_logits=False):
         """argmax_j softmax(100 * cos(degra, text_j)) (da-clip/src/evaluate_daclip.py:46-47,79-81)."""
@@ -174,18 +244,36 @@ class _PackedTower:
         self.ln_pre = (f32(vit.ln_pre.weight), f32(vit.ln_pre.bias))
         self.ln_post = (f32(vit.ln_post.weight), f32(vit.ln_post.bias))
         self.proj = f32(vit.proj)
-        self.blocks = []
-        for i, r in enumerate(prefix_blocks):
-            blk = dict(
-                ln1=(f32(r.ln_1.weight), f32(r.ln_1.bias)), ln2=(f32(r.ln_2.weight), f32(r.ln_2.bias)),
-                qkv=ops.pack_linear(f32(r.attn.in_proj_weight)), qkv_b=f32(r.attn.in_proj_bias),
-                out=ops.pack_linear(f32(r.attn.out_proj.weight)), out_b=f32(r.attn.out_proj.bias),
-                fc=ops.pack_linear(f32(r.mlp.c_fc.weight)), fc_b=f32(r.mlp.c_fc.bias),
-                proj=ops.pack_linear(f32(r.mlp.c_proj.weight)), proj_b=f32(r.mlp.c_proj.bias))
-            if zero_modules is not None:
-                blk["zero"] = ops.pack_linear(f32(zero_modules[i].weight))
-                blk["zero_b"] = f32(zero_modules[i].bias)
-            self.blocks.append(blk)
+        self.blocks = _pack_blocks(prefix_blocks, f32, zero_modules)
+
+
+def _pack_blocks(resblocks, f32, zero_modules=None):
+    blocks = []
+    for i, r in enumerate(resblocks):
+        blk = dict(
+            ln1=(f32(r.ln_1.weight), f32(r.ln_1.bias)), ln2=(f32(r.ln_2.weight), f32(r.ln_2.bias)),
+            qkv=ops.pack_linear(f32(r.attn.in_proj_weight)), qkv_b=f32(r.attn.in_proj_bias),
+            out=ops.pack_linear(f32(r.attn.out_proj.weight)), out_b=f32(r.attn.out_proj.bias),
+            fc=ops.pack_linear(f32(r.mlp.c_fc.weight)), fc_b=f32(r.mlp.c_fc.bias),
+            proj=ops.pack_linear(f32(r.mlp.c_proj.weight)), proj_b=f32(r.mlp.c_proj.bias))
+        if zero_modules is not None:
+            blk["zero"] = ops.pack_linear(f32(zero_modules[i].weight))
+            blk["zero_b"] = f32(zero_modules[i].bias)
+        blocks.append(blk)
+    return blocks
+
+
+class _PackedText:
+    def __init__(self, t: _TextSide):
+        dev = t.text_projection.device
+
+        def f32(x):
+            return x.detach().to(dev, torch.float32).contiguous()
+
+        self.emb, self.pos = f32(t.token_embedding.weight), f32(t.positional_embedding)
+        self.ln_final = (f32(t.ln_final.weight), f32(t.ln_final.bias))
+        self.proj = f32(t.text_projection)
+        self.blocks = _pack_blocks(t.transformer.resblocks, f32)
 
 
 class _PackedDaCLIP:
@@ -269,6 +357,37 @@ class _EncodeEngine:
                 self.run_eager()
             self.graph = g
         self.graph.replay()
+
+
+class _TextEngine(_EncodeEngine):
+    """Launch plan of encode_text for a fixed number of prompts: the ViT block chain with causal attention, the
+    residual stream in fp32, entry = embedding gather, exit = end-of-text pooling; one CUDA graph."""
+
+    def __init__(self, pk: _PackedText, t: _TextSide, N, dev):
+        self.B, self.dev = N, dev
+        Ltok, w, heads = t.context_length, t.width, t.heads
+        M = N * Ltok
+        self.steps, self.flops = [], 0.0
+        bf, f32 = dict(device=dev, dtype=torch.bfloat16), dict(device=dev, dtype=torch.float32)
+        self.tokens = torch.zeros(N, Ltok, device=dev, dtype=torch.int64)
+        self.eot = torch.zeros(N, device=dev, dtype=torch.int32)
+        self.features = torch.zeros(N, pk.proj.shape[1], **f32)
+        x = torch.zeros(1, 1, M, w, **f32)
+        n = torch.zeros(1, 1, M, w, **bf)
+        qkv = torch.zeros(1, 1, M, 3 * w, **bf)
+        att = torch.zeros(1, 1, M, w, **bf)
+        hid = torch.zeros(1, 1, M, 4 * w, **bf)
+        self.add(lambda: ops.text_embed(self.tokens, pk.emb, pk.pos, x, self.eot, N, Ltok, w))
+        for blk in pk.blocks:
+            self.add(lambda blk=blk: ops.layernorm_rows_f32(x, n, M, w, blk["ln1"][0], blk["ln1"][1], 1e-5))
+            self.conv(n, w, blk["qkv"], qkv, M, bias=blk["qkv_b"])
+            self.add(lambda: ops.attention_causal(qkv, att, N, Ltok, heads, w // heads))
+            self.conv(att, w, blk["out"], None, M, bias=blk["out_b"], res_f32=x, out_f32=x)
+            self.add(lambda blk=blk: ops.layernorm_rows_f32(x, n, M, w, blk["ln2"][0], blk["ln2"][1], 1e-5))
+            self.conv(n, w, blk["fc"], hid, M, bias=blk["fc_b"], act=L.ACT_GELU)
+            self.conv(hid, 4 * w, blk["proj"], None, M, bias=blk["proj_b"], res_f32=x, out_f32=x)
+        self.add(lambda: ops.text_pool(x, self.eot, N, Ltok, w, pk.ln_final[0], pk.ln_final[1], pk.proj, self.features))
+        self.graph = None
 
 
 def create_model_from_pretrained(model_name="daclip_ViT-B-32", pretrained=None, device="cuda", **_):

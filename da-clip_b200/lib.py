@@ -86,6 +86,9 @@ SYMBOLS = {
     "dac_vit_patchify": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _p]),
     "dac_vit_embed": (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _f, _p]),
     "dac_vit_pool": (C.c_int, [_p, _i32, _i32, _i32, _p, _p, _f, _p, _i32, _p, _p]),
+    "dac_attention_causal": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _p]),
+    "dac_text_embed": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _p]),
+    "dac_text_pool": (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p, _f, _p, _i32, _p, _p]),
     "dac_degradation_argmax": (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p, _p]),
     "dac_linattn_kv_create": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _i32, C.POINTER(_p)]),
     "dac_linattn_kv_launch": (C.c_int, [_p, _p]),

@@ -387,6 +387,20 @@ def vit_pool(x, B, Ltok, w, ln_w, ln_b, proj, out, eps=1e-5):
                                   proj.shape[1], L.ptr(out), L.stream_ptr()))
 
 
+def attention_causal(qkv, out, B, n, heads, d):
+    L.check(L.load().dac_attention_causal(L.ptr(qkv), L.ptr(out), B, n, heads, d, L.stream_ptr()))
+
+
+def text_embed(text, token_embedding, pos, out, eot, B, Ltok, w):
+    L.check(L.load().dac_text_embed(L.ptr(text), L.ptr(token_embedding), L.ptr(pos), L.ptr(out), L.ptr(eot), B, Ltok, w,
+                                    token_embedding.shape[0], L.stream_ptr()))
+
+
+def text_pool(x, eot, B, Ltok, w, ln_w, ln_b, proj, out, eps=1e-5):
+    L.check(L.load().dac_text_pool(L.ptr(x), L.ptr(eot), B, Ltok, w, L.ptr(ln_w), L.ptr(ln_b), float(eps), L.ptr(proj),
+                                   proj.shape[1], L.ptr(out), L.stream_ptr()))
+
+
 def degradation_argmax(degra, text, logits, argmax):
     B, e = degra.shape
     L.check(L.load().dac_degradation_argmax(L.ptr(degra), L.ptr(text), B, e, text.shape[0], L.ptr(logits),

@@ -134,6 +134,30 @@ def daclip_visual_state_dict(seed=10, arch="ViT-B-32"):
     return sd
 
 
+TEXT_ARCHS = {"ViT-B-32": dict(width=512, layers=12, embed=512), "ViT-L-14": dict(width=768, layers=12, embed=768)}
+
+
+def daclip_text_state_dict(seed=12, arch="ViT-B-32", context_length=77, vocab_size=49408):
+    """Synthetic weights of the CLIP text tower under the reference's `clip.*` keys (open_clip/model.py:203-213)."""
+    a = TEXT_ARCHS[arch]
+    w = a["width"]
+    s = {"clip.positional_embedding": (context_length, w), "clip.text_projection": (w, a["embed"])}
+    for i in range(a["layers"]):
+        b = f"clip.transformer.resblocks.{i}."
+        s[b + "ln_1.weight"] = (w,); s[b + "ln_1.bias"] = (w,)
+        s[b + "attn.in_proj_weight"] = (3 * w, w); s[b + "attn.in_proj_bias"] = (3 * w,)
+        s[b + "attn.out_proj.weight"] = (w, w); s[b + "attn.out_proj.bias"] = (w,)
+        s[b + "ln_2.weight"] = (w,); s[b + "ln_2.bias"] = (w,)
+        s[b + "mlp.c_fc.weight"] = (4 * w, w); s[b + "mlp.c_fc.bias"] = (4 * w,)
+        s[b + "mlp.c_proj.weight"] = (w, 4 * w); s[b + "mlp.c_proj.bias"] = (w,)
+    s["clip.token_embedding.weight"] = (vocab_size, w)
+    s["clip.ln_final.weight"] = (w,)
+    s["clip.ln_final.bias"] = (w,)
+    sd = randomize_state_dict(s, seed)
+    sd["clip.token_embedding.weight"] *= 8.0       # O(1) token rows, so the positional term does not dominate
+    return sd
+
+
 def restoration_inputs(B, H, W, T=100, seed=1, ctx_dim=512):
     """LQ image batch in [0,1], the noisy start state, per-step Gaussian draws and DA-CLIP-like contexts."""
     g = torch.Generator().manual_seed(seed)

@@ -211,6 +211,11 @@ void dac_linattn_qout_destroy(dac_qout_t plan);
  * d = 32 (UNet self-attention, ATT:178-192) or 64 (ViT, TR:219-230); scale = d^-0.5. */
 int dac_attention(const void* qkv, void* out, int32_t B, int32_t n, int32_t heads, int32_t d, dac_stream_t stream);
 
+/* Causal variant for the CLIP text tower (OC/model.py:237-249; mask = build_attention_mask, OC/transformer.py:
+ * upper triangle -inf): query i attends keys 0..i.  d = 64 only (text widths 512 / 768 with 8 / 12 heads). */
+int dac_attention_causal(const void* qkv, void* out, int32_t B, int32_t n, int32_t heads, int32_t d,
+                         dac_stream_t stream);
+
 /* ------------------------------------------------------------------ DA-CLIP encoder helpers (TR:507-555)
  * patchify: image [B,3,S,S] fp32 NCHW -> [B*g*g, 3*p*p] bf16 rows (k = c*p*p + py*p + px, conv1 weight order) at a
  * row pitch of ld_out >= 3*p*p elements (the GEMM wants K % 64 == 0: ViT-L/14 pads 588 -> 640; pad columns are left
@@ -223,6 +228,16 @@ int dac_vit_embed(const void* patch_emb, const float* cls, const float* pos, con
 /* pooled[b] = ln_post(x[b,0,:]) @ proj  -> fp32 [B, e];  x: fp32 [B,L,w] */
 int dac_vit_pool(const void* x, int32_t B, int32_t L, int32_t w, const float* ln_w, const float* ln_b, float eps,
                  const float* proj /*[w,e]*/, int32_t e, float* out, dac_stream_t stream);
+/* Text tower entry and exit (CLIP.encode_text, OC/model.py:237-249):
+ * embed: out[b,t,:] = token_embedding[text[b,t]] + pos[t] (fp32 [B,L,w]); eot[b] = argmax_t text[b,t] (first maximum).
+ *        text: int64 [B,L] token ids in [0, vocab) (the binding validates them; the reference raises on others).
+ * pool:  out[b] = ln_final(x[b, eot[b], :]) @ text_projection -> fp32 [B, e]. */
+int dac_text_embed(const int64_t* text, const float* token_embedding /*[vocab,w]*/, const float* pos /*[L,w]*/,
+                   float* out, int32_t* eot /*[B]*/, int32_t B, int32_t L, int32_t w, int32_t vocab,
+                   dac_stream_t stream);
+int dac_text_pool(const void* x, const int32_t* eot, int32_t B, int32_t L, int32_t w, const float* ln_w,
+                  const float* ln_b, float eps, const float* proj /*[w,e]*/, int32_t e, float* out,
+                  dac_stream_t stream);
 /* Degradation-type argmax (da-clip/src/evaluate_daclip.py:46-47,79-81): argmax_j 100*cos(degra[b], text[j]). */
 int dac_degradation_argmax(const float* degra, const float* text, int32_t B, int32_t e, int32_t classes,
                            float* logits /*[B,classes] or NULL*/, int64_t* argmax, dac_stream_t stream);

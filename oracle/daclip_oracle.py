@@ -77,6 +77,31 @@ def encode_image_control(sd, image, cfg: ViTConfig = None, taps=None):
     return _pool(sd, pv, cfg, x), degra
 
 
+def encode_text(sd, text, heads=8, prefix="clip."):
+    """CLIP.encode_text (open_clip/model.py:237-249): token + positional embedding, the ResidualAttentionBlock chain
+    under the causal mask of build_attention_mask (tr.py:629-635), ln_final, the row of each prompt's end-of-text token
+    (= argmax of the ids) times text_projection.  text: int64 [N, 77]; un-normalised [N, embed_dim]."""
+    x = sd[prefix + "token_embedding.weight"][text] + sd[prefix + "positional_embedding"]
+    n, L, w = x.shape
+    hd = w // heads
+    mask = torch.full((L, L), float("-inf"), device=x.device).triu_(1)
+    i = 0
+    while f"{prefix}transformer.resblocks.{i}.ln_1.weight" in sd:
+        p = f"{prefix}transformer.resblocks.{i}."
+        y = F.layer_norm(x, (w,), sd[p + "ln_1.weight"], sd[p + "ln_1.bias"], 1e-5)
+        qkv = F.linear(y, sd[p + "attn.in_proj_weight"], sd[p + "attn.in_proj_bias"])
+        q, k, v = [t.reshape(n, L, heads, hd).transpose(1, 2) for t in qkv.chunk(3, dim=-1)]
+        att = torch.softmax(torch.matmul(q, k.transpose(2, 3)) * hd ** -0.5 + mask, dim=-1)
+        y = torch.matmul(att, v).transpose(1, 2).reshape(n, L, w)
+        x = x + F.linear(y, sd[p + "attn.out_proj.weight"], sd[p + "attn.out_proj.bias"])
+        y = F.layer_norm(x, (w,), sd[p + "ln_2.weight"], sd[p + "ln_2.bias"], 1e-5)
+        y = F.gelu(F.linear(y, sd[p + "mlp.c_fc.weight"], sd[p + "mlp.c_fc.bias"]))
+        x = x + F.linear(y, sd[p + "mlp.c_proj.weight"], sd[p + "mlp.c_proj.bias"])
+        i += 1
+    x = F.layer_norm(x, (w,), sd[prefix + "ln_final.weight"], sd[prefix + "ln_final.bias"], 1e-5)
+    return x[torch.arange(n, device=x.device), text.argmax(dim=-1)] @ sd[prefix + "text_projection"]
+
+
 def degradation_logits(degra_features, text_features):
     """100 * cos-sim logits against the class prompts (evaluate_daclip.py:46-47,79-80)."""
     d = degra_features / degra_features.norm(dim=-1, keepdim=True)

@@ -159,6 +159,41 @@ def gen_daclip_l14():
     print("daclip_l14.pt written", image_features.shape, image_features.abs().mean().item())
 
 
+TEXT_PROMPTS = DISTORTIONS + [
+    "a photo of a rainy street at night, reflections on the wet asphalt",
+    "Low-Light  indoor scene;   heavy JPEG artefacts &amp; motion blur!",
+    "x",
+    " ".join(f"token{i}" for i in range(60)),            # longer than the context: truncated, forced end-of-text
+]
+
+
+def gen_daclip_text():
+    """CLIP.encode_text of the reference (open_clip/model.py:237-249) for both model configs, tokens from
+    the reference tokenizer (open_clip/tokenizer.py:159-188), seeded synthetic text weights."""
+    sys.modules.setdefault("ftfy", types.SimpleNamespace(fix_text=lambda s: s))
+    import open_clip
+    out = dict(prompts=TEXT_PROMPTS)
+    for name, arch, seed in (("daclip_ViT-B-32", "ViT-B-32", 12), ("daclip_ViT-L-14", "ViT-L-14", 32)):
+        torch.manual_seed(22)
+        with um.patch.object(torch.nn.Module, "cuda", lambda self, *a, **k: self):
+            model = open_clip.create_model(name, pretrained=None, device="cpu")
+        model.eval()
+        txt = synthetic.daclip_text_state_dict(seed, arch=arch)
+        full = model.state_dict()
+        for k, v in txt.items():
+            assert full[k].shape == v.shape, (k, full[k].shape, v.shape)
+        text_keys = [k for k in full if k.startswith("clip.") and not k.startswith("clip.visual.") and k != "clip.logit_scale"]
+        assert sorted(text_keys) == sorted(txt), set(text_keys) ^ set(txt)
+        model.load_state_dict(txt, strict=False)
+        tokens = open_clip.get_tokenizer(name.replace("daclip_", ""))(TEXT_PROMPTS)
+        with torch.no_grad():
+            feats = model.encode_text(tokens)
+        out["tokens"] = tokens.to(torch.int32)
+        out[arch] = dict(weights_seed=seed, features=feats)
+        print(name, feats.shape, feats.abs().mean().item(), tokens.argmax(-1).tolist())
+    torch.save(out, os.path.join(GOLD, "daclip_text.pt"))
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     which = sys.argv[1:] or ["unet", "daclip"]
@@ -170,3 +205,5 @@ if __name__ == "__main__":
         gen_reduced_step()
     if "daclip_l14" in which:
         gen_daclip_l14()
+    if "daclip_text" in which:
+        gen_daclip_text()

@@ -164,3 +164,48 @@ def test_reduced_step_sampling_vs_reference_golden(net, mode):
         x = S.reverse(s, O.make_denoiser(sd, cfg), x_T, inp["lq"], mode=mode, noise=inp["noise"],
                       time_scale=g["T"] / ST, text_context=inp["text_context"], image_context=inp["image_context"])
     assert (x - g[mode]).abs().max().item() < 1e-3
+
+
+@pytest.mark.parametrize("arch,heads", [("ViT-B-32", 8), ("ViT-L-14", 12)])
+def test_daclip_encode_text_vs_reference_golden(arch, heads):
+    """the oracle's encode_text against CLIP.encode_text of the reference (tests/golden/daclip_text.pt:
+    degradation prompts, two captions, a one-letter prompt and a truncated 60-word prompt)."""
+    g = torch.load(os.path.join(GOLD, "daclip_text.pt"), weights_only=False)
+    sd = synthetic.daclip_text_state_dict(g[arch]["weights_seed"], arch=arch)
+    with torch.no_grad():
+        f = D.encode_text(sd, g["tokens"].long(), heads=heads)
+    ref = g[arch]["features"]
+    assert f.shape == ref.shape
+    assert (f - ref).abs().max().item() <= 2e-4 * ref.abs().max().item()
+
+
+def test_tokenizer_vs_reference_golden_and_live_reference():
+    """daclip_b200.tokenizer against the token ids the reference tokenizer produced (golden), and - where the reference
+    checkout and its vocabulary are present (this container, not the GPU box) - against the reference tokenizer live on
+    strings with unicode, html entities, contractions, special tokens and over-long input."""
+    ref_root = "/root/reference/universal-image-restoration"
+    vocab = os.path.join(ref_root, "open_clip", "bpe_simple_vocab_16e6.txt.gz")
+    if not os.path.isfile(vocab):
+        pytest.skip("the BPE merge table is a reference asset that does not travel")
+    from daclip_b200.tokenizer import SimpleTokenizer
+    tk = SimpleTokenizer(vocab)
+    g = torch.load(os.path.join(GOLD, "daclip_text.pt"), weights_only=False)
+    assert torch.equal(tk(g["prompts"]).to(torch.int32), g["tokens"])
+    assert tk.vocab_size == 49408 and tk.eot_token == 49407
+    import sys
+    import types
+    sys.path.insert(0, ref_root)
+    had = "ftfy" in sys.modules
+    sys.modules.setdefault("ftfy", types.SimpleNamespace(fix_text=lambda s: s))
+    try:
+        from open_clip import tokenizer as RT
+    finally:
+        sys.path.remove(ref_root)
+        if not had:
+            sys.modules.pop("ftfy", None)
+    texts = ["A photo of a cat's   whiskers, isn't it?  ", "Ünïcödé çafé — naïve 12345 résumé",
+             "&amp;lt;b&amp;gt; html &quot;entities&quot;", "emoji 😀 and 中文 текст",
+             "<start_of_text> weird <end_of_text> specials", "x" * 300, "", "I'LL we'RE THEY'd 's"]
+    assert torch.equal(tk(texts), RT.tokenize(texts))
+    ids = tk.encode(texts[0])
+    assert tk.decode(ids) == RT._tokenizer.decode(ids)
