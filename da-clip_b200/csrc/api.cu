@@ -10,6 +10,8 @@ namespace dac {
 
 static thread_local char g_err[512] = "";
 static std::atomic<int64_t> g_launches{0};
+static thread_local int g_pdl = 0;
+bool pdl_enabled() { return g_pdl != 0; }
 
 int set_error(int code, const char* fmt, ...) {
   va_list ap;
@@ -29,6 +31,7 @@ int check_launch(const char* what) {
 }  // namespace dac
 
 extern "C" int dac_version(void) { return 100; }
+extern "C" void dac_set_pdl(int32_t on) { dac::g_pdl = on; }
 extern "C" int dac_abi_sizes(int32_t* conv_desc_bytes, int32_t* embed_weights_bytes) {
   if (conv_desc_bytes) *conv_desc_bytes = (int32_t)sizeof(dac_conv_desc);
   if (embed_weights_bytes) *embed_weights_bytes = (int32_t)sizeof(dac_embed_weights);

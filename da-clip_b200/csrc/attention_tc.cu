@@ -85,6 +85,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_launch();   // programmatic dependent launch: see conv_kernel.cuh
 
   // item -> (image b, head pair, query tile); rows of the packed [B*n, 3*heads*32] matrix
   auto decode = [&](int item, int& row0, int& pair, int& brow) {
@@ -101,6 +102,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constant
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+      griddep_wait();
       for (int it = begin; it < end; ++it) {
         int row0, pair, brow;
         decode(it, row0, pair, brow);
@@ -199,6 +201,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constant
     const int quad = warp & 3;
     const int g = (warp - 2) >> 2;
     const int row = quad * 32 + lane;
+    griddep_wait();
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     const uint32_t s_addr = lane_base + kAtColS + g * 128;
     const uint32_t o_addr = lane_base + kAtColO + g * 64 + g * 32;   // this head's 32 channels of the N = 64 product
@@ -328,6 +331,6 @@ int dac_attention_tc(const void* qkv, void* out, int B, int n, int heads, cudaSt
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = k.items < sms ? k.items : sms;
-  attn_tc_kernel<<<grid, kAtThreads, smem, stream>>>(map, k);
+  launch_k(attn_tc_kernel, dim3(grid), dim3(kAtThreads), smem, stream, map, k);
   return check_launch("attn_tc_kernel");
 }

@@ -9,4 +9,26 @@ int set_error(int code, const char* fmt, ...);
 // Counts the launch and turns a launch-time CUDA error into a negative return code.
 int check_launch(const char* what);
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// Programmatic dependent launch (dac_set_pdl): while the flag is up, launch sites that go through launch_k() add
+// cudaLaunchAttributeProgrammaticStreamSerialization, so the grid may be scheduled - barrier / TMEM set-up, resident
+// weight loads - while the previous kernel of the stream drains.  Only kernels that execute griddepcontrol.wait before
+// touching anything an earlier kernel wrote (or still reads) may be launched this way.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  if (pdl_enabled()) {
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+  }
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 }  // namespace dac

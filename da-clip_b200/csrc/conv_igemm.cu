@@ -329,9 +329,13 @@ extern "C" int dac_conv_launch(dac_conv_t pl, dac_stream_t stream) {
                                     static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return set_error(-20, "dac_conv_launch: memset failed: %s", cudaGetErrorString(e));
   }
-  pl->kernel<<<pl->grid, kThreads, pl->smem, static_cast<cudaStream_t>(stream)>>>(pl->mapA0, pl->mapA1, pl->mapW,
-                                                                                  pl->mapOut, pl->mapOut2, pl->mapR0,
-                                                                                  pl->mapR1, pl->mapWR, pl->mapRes, pl->kp);
+  if (pl->kp.ctx_acc)   // behind a memset node: a plain launch
+    pl->kernel<<<pl->grid, kThreads, pl->smem, static_cast<cudaStream_t>(stream)>>>(pl->mapA0, pl->mapA1, pl->mapW,
+                                                                                    pl->mapOut, pl->mapOut2, pl->mapR0,
+                                                                                    pl->mapR1, pl->mapWR, pl->mapRes, pl->kp);
+  else
+    launch_k(pl->kernel, dim3(pl->grid), dim3(kThreads), pl->smem, static_cast<cudaStream_t>(stream), pl->mapA0, pl->mapA1,
+             pl->mapW, pl->mapOut, pl->mapOut2, pl->mapR0, pl->mapR1, pl->mapWR, pl->mapRes, pl->kp);
   return check_launch("conv_igemm_kernel");
 }
 

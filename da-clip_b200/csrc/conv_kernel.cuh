@@ -558,6 +558,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: the next kernel of the stream may be scheduled from now on (its CTAs land on an SM
+  // when ours exits and run their set-up); everything above this line and the resident weight load below touch nothing
+  // an earlier kernel produces, so they overlap the tail of the previous kernel - the waits sit in the producer (before
+  // the first activation load) and in the epilogue warps (before any parameter / residual read or output write).
+  griddep_launch();
 #ifdef DAC_DEBUG
   if (threadIdx.x == 0 && blockIdx.x == 0)
     printf("[conv] tiles=%d k_steps=%d stages=%d block_n=%d tmem_base=%08x OH=%d OW=%d out=%p cout=%d epi=%d\n",
@@ -580,6 +585,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       }
       int stage = 0;
       uint32_t phase = 0;
+      griddep_wait();
       for (int tile = tile_begin; tile < tile_end; ++tile) {
         const TileCoord t = decode_tile(p, tile);
         const int xin = t.x0 * p.stride, yin = t.y0 * p.stride;
@@ -714,6 +720,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     uint8_t* stg = stg_base ? stg_base + group * p.stg_bytes : nullptr;
     uint32_t acc_phase = 0;
     int film_key = -1;
+    griddep_wait();
     if (EPI == KE_KVCTX) {
       KvCtxAcc cacc;
       kvctx_zero(cacc);

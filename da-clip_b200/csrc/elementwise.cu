@@ -77,6 +77,7 @@ __global__ void __launch_bounds__(256) stem_input_kernel(const float* __restrict
                                                          int Wp) {
   // one thread per (pixel, kx): 8 channels = one 16 B store; grid = (x blocks, row, image): no index division
   const int y = blockIdx.y, b = blockIdx.z;
+  griddep_launch();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Wp * 8; i += gridDim.x * blockDim.x) {
     const int kx = i & 7;
     const int x = i >> 3;
@@ -111,6 +112,8 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const __nv_bfloat16
                                                              __nv_bfloat16* __restrict__ out, int ld_out, int64_t rows,
                                                              int c, const float* __restrict__ w,
                                                              const float* __restrict__ b, float eps) {
+  griddep_wait();       // programmatic dependent launch (common.h): nothing to do before the producer is done
+  griddep_launch();
   const int lane = threadIdx.x & 31;
   const int sub = lane % LPR;
   const int rows_per_warp = 32 / LPR;
@@ -253,6 +256,7 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const __nv_bfloat1
                                                               int groups, const float* __restrict__ w,
                                                               const float* __restrict__ bias, float eps,
                                                               const float* __restrict__ stats) {
+  griddep_launch();
   const int nvec = c >> 3;
   const int cpg = c / groups;
   const int64_t total = static_cast<int64_t>(B) * hw * nvec;
@@ -474,11 +478,13 @@ extern "C" int dac_layernorm_rows(const void* in, int32_t ld_in, void* out, int3
   int64_t blocks = ceil_div(warps, 8);
   if (blocks > 148 * 8) blocks = 148 * 8;
   const int grid = static_cast<int>(blocks);
-  if (lpr == 8) layernorm_rows_kernel<8, 1><<<grid, 256, 0, st>>>(ip, ld_in, op, ld_out, rows, c, w, b, eps);
-  else if (lpr == 16) layernorm_rows_kernel<16, 1><<<grid, 256, 0, st>>>(ip, ld_in, op, ld_out, rows, c, w, b, eps);
-  else if (nvec <= 32) layernorm_rows_kernel<32, 1><<<grid, 256, 0, st>>>(ip, ld_in, op, ld_out, rows, c, w, b, eps);
-  else if (nvec <= 64) layernorm_rows_kernel<32, 2><<<grid, 256, 0, st>>>(ip, ld_in, op, ld_out, rows, c, w, b, eps);
-  else layernorm_rows_kernel<32, 4><<<grid, 256, 0, st>>>(ip, ld_in, op, ld_out, rows, c, w, b, eps);
+  const dim3 g(grid), t(256);
+  const long long rows_ll = rows;
+  if (lpr == 8) launch_k(layernorm_rows_kernel<8, 1>, g, t, 0, st, ip, ld_in, op, ld_out, rows_ll, c, w, b, eps);
+  else if (lpr == 16) launch_k(layernorm_rows_kernel<16, 1>, g, t, 0, st, ip, ld_in, op, ld_out, rows_ll, c, w, b, eps);
+  else if (nvec <= 32) launch_k(layernorm_rows_kernel<32, 1>, g, t, 0, st, ip, ld_in, op, ld_out, rows_ll, c, w, b, eps);
+  else if (nvec <= 64) launch_k(layernorm_rows_kernel<32, 2>, g, t, 0, st, ip, ld_in, op, ld_out, rows_ll, c, w, b, eps);
+  else launch_k(layernorm_rows_kernel<32, 4>, g, t, 0, st, ip, ld_in, op, ld_out, rows_ll, c, w, b, eps);
   return check_launch("layernorm_rows_kernel");
 }
 

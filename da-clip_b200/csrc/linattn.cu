@@ -160,10 +160,12 @@ __global__ void __launch_bounds__(256) linattn_fold_kernel(const float* __restri
   float* wsm = inv_s + 32;              // [C][33]: W_out[c][h*32 + e]
   const int h = blockIdx.x, b = blockIdx.y, t = threadIdx.x;
   const float* pbase = partial + (static_cast<int64_t>(b) * 4 + h) * nchunks * kPartial;
-  for (int i = t; i < C * 32; i += 256) {
+  griddep_launch();
+  for (int i = t; i < C * 32; i += 256) {       // a constant: staged while the context kernel drains
     const int c = i >> 5, e = i & 31;
     wsm[c * 33 + e] = __ldg(w_out + static_cast<int64_t>(c) * 128 + h * 32 + e);
   }
+  griddep_wait();
   if (t < 32) {
     float M = -INFINITY;
     for (int c = 0; c < nchunks; ++c) M = fmaxf(M, pbase[c * kPartial + 1024 + t]);
@@ -218,7 +220,7 @@ extern "C" int dac_linattn_fold(const float* partial, int32_t B, int32_t hw, int
     cudaError_t e = cudaFuncSetAttribute(linattn_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error(-12, "dac_linattn_fold: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   }
-  linattn_fold_kernel<<<dim3(4, B), 256, smem, static_cast<cudaStream_t>(stream)>>>(
-      partial, hw, nchunks, w_out, C, c_pad, static_cast<__nv_bfloat16*>(weff));
+  launch_k(linattn_fold_kernel, dim3(4, B), dim3(256), smem, static_cast<cudaStream_t>(stream), partial, hw, nchunks, w_out,
+           C, c_pad, static_cast<__nv_bfloat16*>(weff));
   return check_launch("linattn_fold_kernel");
 }

@@ -93,6 +93,7 @@ linattn_kv_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_launch();   // the next kernel may be scheduled (this one sits behind a memset node and is launched plainly)
 
   if (warp == 0) {
     // ===================== TMA producer =====================

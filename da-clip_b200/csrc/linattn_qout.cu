@@ -90,12 +90,14 @@ linattn_qout_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_launch();   // see conv_kernel.cuh: set-up and the W_q load overlap the previous kernel's tail
 
   if (warp == 0) {
     // ===================== TMA producer: A1(t0); then per tile i: A1(t_{i+1}), B2(t_i) =====================
     if (elect_one()) {
       mbar_arrive_expect_tx(wq_full, kCh * kSlab);
       for (int ck = 0; ck < kCh; ++ck) tma_load_2d(wq + ck * kSlab, &mapWq, wq_full, ck * 64, 0);
+      griddep_wait();
       int stage = 0;
       uint32_t phase = 0;
       auto advance = [&]() {
@@ -197,6 +199,7 @@ linattn_qout_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
     const int group = (warp - 2) >> 2;
     const int row = quad * 32 + lane;
     const int gthread = threadIdx.x - 64 - group * 128;
+    griddep_wait();
     uint8_t* qt = a2 + group * 2 * kSlab;                 // this group's q tile / output staging
     uint8_t* rt = (C == 64) ? rbuf + group * kSlab : qt;  // where the residual tile lands
     const uint32_t acc1 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + group * kAccStride;
@@ -423,11 +426,11 @@ extern "C" int dac_linattn_qout_launch(dac_qout_t pl, dac_stream_t stream) {
   if (!pl) return set_error(-1, "dac_linattn_qout_launch: null plan");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (pl->C == 64)
-    linattn_qout_kernel<64><<<pl->grid, kThreads, pl->smem, st>>>(pl->mapX, pl->mapWq, pl->mapWeff, pl->mapOut,
-                                                                  pl->mapRes, pl->kp);
+    launch_k(linattn_qout_kernel<64>, dim3(pl->grid), dim3(kThreads), pl->smem, st, pl->mapX, pl->mapWq, pl->mapWeff,
+             pl->mapOut, pl->mapRes, pl->kp);
   else
-    linattn_qout_kernel<128><<<pl->grid, kThreads, pl->smem, st>>>(pl->mapX, pl->mapWq, pl->mapWeff, pl->mapOut,
-                                                                   pl->mapRes, pl->kp);
+    launch_k(linattn_qout_kernel<128>, dim3(pl->grid), dim3(kThreads), pl->smem, st, pl->mapX, pl->mapWq, pl->mapWeff,
+             pl->mapOut, pl->mapRes, pl->kp);
   return check_launch("linattn_qout_kernel");
 }
 

@@ -188,6 +188,12 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t m, uint32_t n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
+// Programmatic dependent launch: wait = every earlier grid of the stream has completed and its writes are visible
+// (no-op for a grid launched without the attribute); launch_dependents = the next grid may be scheduled as soon as
+// every CTA of this one has said so (it still waits for our completion at its own griddepcontrol.wait).
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t elect_one() {
   uint32_t pred;
   asm volatile(

@@ -86,6 +86,7 @@ SYMBOLS = {
     "dac_vit_patchify": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _p]),
     "dac_vit_embed": (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _f, _p]),
     "dac_vit_pool": (C.c_int, [_p, _i32, _i32, _i32, _p, _p, _f, _p, _i32, _p, _p]),
+    "dac_set_pdl": (None, [_i32]),
     "dac_attention_causal": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _p]),
     "dac_text_embed": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _p]),
     "dac_text_pool": (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p, _f, _p, _i32, _p, _p]),
@@ -152,6 +153,10 @@ def stream_ptr():
 
 def ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def set_pdl(on):
+    load().dac_set_pdl(1 if on else 0)
 
 
 def launch_count():

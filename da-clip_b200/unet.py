@@ -416,6 +416,7 @@ class UNetEngine:
     # producer +14 us vs the 54 us LayerNorm kernel saved): the QKV epilogue is already the bottleneck of that
     # store-bound layer.  Kept as a tested option (tests/test_kernels_gpu.py::test_prenorm_folded_into_qkv).
     FOLD_PRENORM = False
+    PDL = True             # programmatic dependent launch between consecutive kernel nodes of the step graph
     FUSE_KV_TC = True      # LinearAttention: the k|v context reduction as a second tcgen05 GEMM (TMEM-resident context)
     FUSE_QOUT = True       # LinearAttention: to_q + softmax + to_out + LayerNorm + residual as one chained-GEMM kernel
     FUSE_KVCTX = True      # LinearAttention: reduce k | v into the context inside the to_kv GEMM epilogue
@@ -642,13 +643,20 @@ class UNetEngine:
                     fn()
         join.record(side)
         joined = False
-        for name, fn in self.steps:
-            if name == "time_film":
-                continue
-            if not joined and name not in independent:
-                main.wait_event(join)
-                joined = True
-            fn()
+        prev_kernel = False      # programmatic dependent launch only straight behind a kernel node of the same stream
+        try:
+            for name, fn in self.steps:
+                if name == "time_film":
+                    continue
+                just_joined = False
+                if not joined and name not in independent:
+                    main.wait_event(join)
+                    joined = just_joined = True
+                L.set_pdl(self.PDL and prev_kernel and not just_joined)
+                fn()
+                prev_kernel = True   # every step ends with a kernel launch (memsets come first where there are any)
+        finally:
+            L.set_pdl(False)
         if not joined:
             main.wait_event(join)
 

@@ -28,6 +28,12 @@ extern "C" {
 typedef void* dac_stream_t; /* cudaStream_t */
 
 int dac_version(void);
+/* Programmatic dependent launch for the calling thread's following launches (0 = off, the default): kernels of this
+ * library that wait with griddepcontrol before their first dependent access are then launched with
+ * cudaLaunchAttributeProgrammaticStreamSerialization, so their set-up overlaps the tail of the previous kernel in the
+ * stream.  The caller raises it only when the previous operation in the stream is a kernel of this library (the UNet
+ * engine does, step by step, while capturing its CUDA graph). */
+void dac_set_pdl(int32_t on);
 const char* dac_last_error(void);
 /* Number of kernels this library has launched since load (or since the last reset). */
 int64_t dac_launch_count(void);
