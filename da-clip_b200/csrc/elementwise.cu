@@ -75,32 +75,44 @@ static int elementwise_grid(int64_t work_items) {
 __global__ void __launch_bounds__(256) stem_input_kernel(const float* __restrict__ xt, const float* __restrict__ cond,
                                                          __nv_bfloat16* __restrict__ out, int B, int H, int W, int Hp,
                                                          int Wp) {
-  // one thread per (pixel, kx): 8 channels = one 16 B store; grid = (x blocks, row, image): no index division
-  const int y = blockIdx.y, b = blockIdx.z;
+  // One CTA per (row, image).  Phase 1: the row's six channels (xt - cond | cond), reflect-padded to Wp and with the
+  // three zero columns of the 7-tap window on either side, go to shared memory with coalesced loads.  Phase 2: one
+  // thread per (pixel, kx) packs its 8 channels (6 + 2 zeros; kx = 7 is all zero) into one 16 B store - the row's
+  // Wp * 128 B are written fully coalesced and every input value is read from global memory once, not seven times.
+  extern __shared__ float srow[];                      // [6][Wp + 6]; column j holds source x = j - 3
+  const int y = blockIdx.x, b = blockIdx.y;
+  const int pitch = Wp + 6;
+  const int ys = y < H ? y : 2 * H - 2 - y;            // reflect (arch.py:111-116)
+  const int64_t plane = static_cast<int64_t>(H) * W;
+  const int64_t base = (static_cast<int64_t>(b) * 3) * plane + static_cast<int64_t>(ys) * W;
   griddep_launch();
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Wp * 8; i += gridDim.x * blockDim.x) {
-    const int kx = i & 7;
-    const int x = i >> 3;
-    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    const int xs = x + kx - 3;
-    if (kx < 7 && xs >= 0 && xs < Wp) {
-      const int ys = y < H ? y : 2 * H - 2 - y;      // reflect (arch.py:111-116)
+  for (int j = threadIdx.x; j < pitch; j += blockDim.x) {
+    const int xs = j - 3;
+    float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (xs >= 0 && xs < Wp) {
       const int xr = xs < W ? xs : 2 * W - 2 - xs;
-      const int64_t plane = static_cast<int64_t>(H) * W;
-      const int64_t base = (static_cast<int64_t>(b) * 3) * plane + static_cast<int64_t>(ys) * W + xr;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        const float cv = __ldg(cond + base + c * plane);
-        v[c] = __fsub_rn(__ldg(xt + base + c * plane), cv);
+        const float cv = __ldg(cond + base + c * plane + xr);
+        v[c] = __fsub_rn(__ldg(xt + base + c * plane + xr), cv);
         v[3 + c] = cv;
       }
     }
-    uint4 u;
-    u.x = pack_bf16(v[0], v[1]);
-    u.y = pack_bf16(v[2], v[3]);
-    u.z = pack_bf16(v[4], v[5]);
-    u.w = pack_bf16(v[6], v[7]);
-    reinterpret_cast<uint4*>(out)[(static_cast<int64_t>(b) * Hp + y) * Wp * 8 + i] = u;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) srow[c * pitch + j] = v[c];
+  }
+  __syncthreads();
+  uint4* orow = reinterpret_cast<uint4*>(out) + (static_cast<int64_t>(b) * Hp + y) * Wp * 8;
+  for (int i = threadIdx.x; i < Wp * 8; i += blockDim.x) {
+    const int kx = i & 7;
+    const float* s = srow + (i >> 3) + kx;             // source x = pixel + kx - 3  ->  column pixel + kx
+    uint4 u = make_uint4(0u, 0u, 0u, 0u);
+    if (kx < 7) {
+      u.x = pack_bf16(s[0], s[pitch]);
+      u.y = pack_bf16(s[2 * pitch], s[3 * pitch]);
+      u.z = pack_bf16(s[4 * pitch], s[5 * pitch]);
+    }
+    orow[i] = u;
   }
 }
 
@@ -162,10 +174,16 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const __nv_bfloat16
       if (live && vi < nvec) {
         float y[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          y[j] = (v[i][j] - mean) * rstd;
-          if (w) y[j] *= __ldg(w + vi * 8 + j);
-          if (b) y[j] += __ldg(b + vi * 8 + j);
+        for (int j = 0; j < 8; ++j) y[j] = (v[i][j] - mean) * rstd;
+        if (w) {      // 16-byte parameter loads (one scalar load per element made this kernel issue-bound)
+          const float4 w0 = __ldg(reinterpret_cast<const float4*>(w) + vi * 2), w1 = __ldg(reinterpret_cast<const float4*>(w) + vi * 2 + 1);
+          y[0] *= w0.x; y[1] *= w0.y; y[2] *= w0.z; y[3] *= w0.w;
+          y[4] *= w1.x; y[5] *= w1.y; y[6] *= w1.z; y[7] *= w1.w;
+        }
+        if (b) {
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(b) + vi * 2), b1 = __ldg(reinterpret_cast<const float4*>(b) + vi * 2 + 1);
+          y[0] += b0.x; y[1] += b0.y; y[2] += b0.z; y[3] += b0.w;
+          y[4] += b1.x; y[5] += b1.y; y[6] += b1.z; y[7] += b1.w;
         }
         uint4 o;
         o.x = pack_bf16(y[0], y[1]); o.y = pack_bf16(y[2], y[3]);
@@ -277,8 +295,14 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const __nv_bfloat1
     t = unpack_bf16(u.y); v[2] = t.x; v[3] = t.y;
     t = unpack_bf16(u.z); v[4] = t.x; v[5] = t.y;
     t = unpack_bf16(u.w); v[6] = t.x; v[7] = t.y;
+    {
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(w) + vec * 2), w1 = __ldg(reinterpret_cast<const float4*>(w) + vec * 2 + 1);
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias) + vec * 2), b1 = __ldg(reinterpret_cast<const float4*>(bias) + vec * 2 + 1);
+      const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = (v[j] - mean) * rstd * __ldg(w + vec * 8 + j) + __ldg(bias + vec * 8 + j);
+      for (int j = 0; j < 8; ++j) v[j] = (v[j] - mean) * rstd * wv[j] + bv[j];
+    }
     uint4 o;
     o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]);
     o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
@@ -457,8 +481,8 @@ extern "C" int dac_unet_stem_input(const float* xt, const float* cond, void* out
   if (!xt || !cond || !out) return set_error(-1, "dac_unet_stem_input: null argument");
   if (Hp < H || Wp < W || Hp - H >= H || Wp - W >= W) return set_error(-2, "dac_unet_stem_input: bad padding");
   if (Hp > 65535 || B > 65535) return set_error(-2, "dac_unet_stem_input: Hp and B must be < 65536");
-  stem_input_kernel<<<dim3(static_cast<unsigned>(ceil_div(static_cast<int64_t>(Wp) * 8, 256)), Hp, B), 256, 0,
-                      static_cast<cudaStream_t>(stream)>>>(
+  if (Wp > 2000) return set_error(-2, "dac_unet_stem_input: padded width must be <= 2000 (one row in 48 KB of shared memory)");
+  stem_input_kernel<<<dim3(Hp, B), 256, sizeof(float) * 6 * (Wp + 6), static_cast<cudaStream_t>(stream)>>>(
       xt, cond, static_cast<__nv_bfloat16*>(out), B, H, W, Hp, Wp);
   return check_launch("stem_input_kernel");
 }
@@ -469,6 +493,8 @@ extern "C" int dac_layernorm_rows(const void* in, int32_t ld_in, void* out, int3
   if ((c & 7) || (ld_in & 7) || (ld_out & 7)) return set_error(-2, "dac_layernorm_rows: c and pitches must be multiples of 8");
   if (rows <= 0) return 0;
   if (c > 1024) return set_error(-2, "dac_layernorm_rows: c must be <= 1024");
+  if ((reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(b)) & 15)
+    return set_error(-2, "dac_layernorm_rows: w and b must be 16-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const __nv_bfloat16* ip = static_cast<const __nv_bfloat16*>(in);
   __nv_bfloat16* op = static_cast<__nv_bfloat16*>(out);
@@ -504,6 +530,8 @@ extern "C" int dac_groupnorm_nhwc(const void* in, void* out, int32_t B, int32_t 
                                   const float* w, const float* b, float eps, float* stats, dac_stream_t stream) {
   if (!in || !out || !w || !b || !stats) return set_error(-1, "dac_groupnorm_nhwc: null argument");
   if (c % groups || (c / groups) % 8 || c / 8 > 256) return set_error(-2, "dac_groupnorm_nhwc: need 8 | c/groups, c <= 2048");
+  if ((reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(b)) & 15)
+    return set_error(-2, "dac_groupnorm_nhwc: w and b must be 16-byte aligned");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   cudaMemsetAsync(stats, 0, sizeof(float) * 2 * B * groups, s);
   const int slabs = hw >= 1024 ? 16 : (hw >= 64 ? 4 : 1);
