@@ -212,6 +212,7 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
   }
   if (d->epi == DAC_EPI_KVCTX) stg_bytes = kKvStageBytes;   // P / V head tiles of each epilogue group
   k.kv_shift = d->kv_shift; k.ctx_acc = d->ctx_acc;
+  k.ctx_slots = d->ctx_slots; k.ctx_tpi = k.tiles_x * k.tiles_y;
   // FiLM parameters in TMEM when three block_n-wide regions fit one accumulator stage (the 64-channel layers, which
   // are the shared-memory-bound ones); alignment of the float4 parameter loads needs cout % 4 == 0 (validated above)
   k.film_tmem = (d->film && !fused_res && d->block_n % 32 == 0 && 3 * d->block_n <= (int)kAccStride &&
@@ -312,6 +313,14 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (sms <= 0) sms = 148;
   pl->grid = pl->tiles < sms ? pl->tiles : sms;
+  if (k.ctx_acc) {
+    const int need = 2 * max_image_span(d->B, k.ctx_tpi, pl->grid);
+    if (k.n_tiles != 1 || k.ngroups != 1 || d->ctx_slots < need) {
+      const int have = d->ctx_slots;
+      delete pl;
+      return set_error(-2, "dac_conv_create: KVCTX needs ctx_slots >= %d (dac_linattn_ctx_slots), got %d", need, have);
+    }
+  }
   if (cudaFuncSetAttribute(reinterpret_cast<const void*>(kernel), cudaFuncAttributeMaxDynamicSharedMemorySize,
                            227 * 1024) != cudaSuccess) {
     cudaGetLastError();
@@ -322,10 +331,23 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
   return 0;
 }
 
+extern "C" int32_t dac_linattn_ctx_slots(int32_t B, int32_t tiles_per_image, int32_t groups) {
+  if (B <= 0 || tiles_per_image <= 0 || groups <= 0) return 0;
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+      sms <= 0) {
+    cudaGetLastError();
+    sms = 148;
+  }
+  const long long tiles = static_cast<long long>(B) * tiles_per_image;
+  const int grid = tiles < sms ? static_cast<int>(tiles) : sms;
+  return groups * max_image_span(B, tiles_per_image, grid);
+}
+
 extern "C" int dac_conv_launch(dac_conv_t pl, dac_stream_t stream) {
   if (!pl) return set_error(-1, "dac_conv_launch: null plan");
-  if (pl->kp.ctx_acc) {   // KVCTX accumulates with atomics: start every launch from zero
-    cudaError_t e = cudaMemsetAsync(pl->kp.ctx_acc, 0, sizeof(float) * pl->kp.B * 4 * kCtxRecord,
+  if (pl->kp.ctx_acc) {   // KVCTX: slots no CTA writes (an image spanning fewer CTAs than the widest one) must read as zero
+    cudaError_t e = cudaMemsetAsync(pl->kp.ctx_acc, 0, sizeof(float) * pl->kp.B * 4 * pl->kp.ctx_slots * kCtxRecord,
                                     static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return set_error(-20, "dac_conv_launch: memset failed: %s", cudaGetErrorString(e));
   }

@@ -105,7 +105,8 @@ struct ConvKParams {
   int res_tma;             // the bf16 residual tile is TMA-loaded into the staging tile and updated in place
   int film_tmem;           // FiLM (scale + 1 | shift) of the current image lives in TMEM columns [bn, 3 bn) of the stage
   const float* kv_shift;   // KVCTX: [128] upper bound of k per channel, times log2(e)
-  float* ctx_acc;          // KVCTX: [B][4][kCtxRecord] fp32
+  float* ctx_acc;          // KVCTX: [B][4][ctx_slots][kCtxRecord] fp32 partial records
+  int ctx_slots, ctx_tpi;  // slots per (image, head); tiles per image
 };
 
 struct TileCoord {
@@ -394,7 +395,9 @@ __device__ __forceinline__ void epilogue_tile(const ConvKParams& p, const TileCo
 
 // ---- KVCTX: the LinearAttention context reduced straight out of the k|v accumulator (module_util.py:170-177) ----
 // Per epilogue warp: C[h][16 d rows][16 e cols] of every head plus the softmax denominators S[h][16 d rows],
-// carried in registers across the tiles of one image and flushed with atomics when the image changes.
+// carried in registers across the tiles of one image and STORED as this (CTA, group)'s partial record when the image
+// changes (slot = 2 * (CTA - first CTA of the image) + group: the fold kernel adds the slots in order, so the result does
+// not depend on which CTA finishes first).
 struct KvCtxAcc {
   float c[4][2][4];
   float s[4][4];
@@ -410,23 +413,24 @@ __device__ __forceinline__ void kvctx_zero(KvCtxAcc& a) {
     }
   }
 }
-__device__ __forceinline__ void kvctx_flush(const ConvKParams& p, int img, int quad, int lane, KvCtxAcc& a) {
+__device__ __forceinline__ void kvctx_flush(const ConvKParams& p, int img, int quad, int lane, int group,
+                                            KvCtxAcc& a) {
   if (img < 0) return;
   const int d = 16 * (quad >> 1) + (lane >> 2), e0 = 16 * (quad & 1) + 2 * (lane & 3);
-  float* base = p.ctx_acc + static_cast<long long>(img) * 4 * kCtxRecord;
+  const int total = p.B * p.ctx_tpi;
+  const int slot = 2 * (static_cast<int>(blockIdx.x) - tile_owner(img * p.ctx_tpi, total, gridDim.x)) + group;
+  float* base = p.ctx_acc + (static_cast<long long>(img) * 4 * p.ctx_slots + slot) * kCtxRecord;
 #pragma unroll
   for (int h = 0; h < 4; ++h) {
-    float* hb = base + h * kCtxRecord;
+    float* hb = base + static_cast<long long>(h) * p.ctx_slots * kCtxRecord;
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-      atomicAdd(hb + d * 32 + e0 + 8 * i, a.c[h][i][0]);
-      atomicAdd(hb + d * 32 + e0 + 8 * i + 1, a.c[h][i][1]);
-      atomicAdd(hb + (d + 8) * 32 + e0 + 8 * i, a.c[h][i][2]);
-      atomicAdd(hb + (d + 8) * 32 + e0 + 8 * i + 1, a.c[h][i][3]);
+      *reinterpret_cast<float2*>(hb + d * 32 + e0 + 8 * i) = make_float2(a.c[h][i][0], a.c[h][i][1]);
+      *reinterpret_cast<float2*>(hb + (d + 8) * 32 + e0 + 8 * i) = make_float2(a.c[h][i][2], a.c[h][i][3]);
     }
     if ((quad & 1) == 0 && (lane & 3) == 0) {   // every column of the ones-product holds S[d]
-      atomicAdd(hb + 1056 + d, a.s[h][0]);
-      atomicAdd(hb + 1056 + d + 8, a.s[h][2]);
+      hb[1056 + d] = a.s[h][0];
+      hb[1056 + d + 8] = a.s[h][2];
     }
   }
   kvctx_zero(a);
@@ -728,7 +732,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       for (int tile = tile_begin + group; tile < tile_end; tile += 2) {
         const TileCoord t = decode_tile(p, tile);
         if (t.n != cur_img) {
-          kvctx_flush(p, cur_img, quad, lane, cacc);
+          kvctx_flush(p, cur_img, quad, lane, group, cacc);
           cur_img = t.n;
         }
         mbar_wait(&tmem_full[group], acc_phase);
@@ -737,7 +741,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         kvctx_tile(p, t, tmem_acc, row, quad, lane, group, stg, cacc, &tmem_empty[group]);
         acc_phase ^= 1;
       }
-      kvctx_flush(p, cur_img, quad, lane, cacc);
+      kvctx_flush(p, cur_img, quad, lane, group, cacc);
     } else
     for (int tile = tile_begin + group; tile < tile_end; tile += 2) {
       const TileCoord t = decode_tile(p, tile);

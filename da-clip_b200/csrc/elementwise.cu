@@ -239,56 +239,80 @@ __global__ void __launch_bounds__(256) layernorm_rows_f32_kernel(const float* __
 }
 
 // ------------------------------------------------------------------------------------------------ GroupNorm
-// stats[b][g] = {sum, sumsq}.  Each thread owns one 8-channel vector column (8 | channels-per-group) and walks
-// pixels of its slab; per-group partials are combined through shared memory then one atomicAdd per group.
+// Pass 1: CTA (slab, image) -> stats[b][slab][g] = {sum, sumsq} of its pixel slab.  Each thread owns one 8-channel vector
+// column (8 | channels-per-group) and walks its pixels; the per-thread partials meet in shared memory and ONE thread per
+// group adds them in a fixed order - no atomics anywhere, so the statistics are bit-reproducible.
+constexpr int kGnSlabs = 16;
 __global__ void __launch_bounds__(256) groupnorm_stats_kernel(const __nv_bfloat16* __restrict__ in, int hw, int c,
                                                               int groups, int slab, float* __restrict__ stats) {
-  extern __shared__ float sh[];  // [groups*2]
+  __shared__ float2 part[256];
+  griddep_wait();
+  griddep_launch();
   const int b = blockIdx.y;
   const int nvec = c >> 3;
   const int cpg = c / groups;
-  for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) sh[i] = 0.f;
-  __syncthreads();
   const int p0 = blockIdx.x * slab, p1 = min(hw, p0 + slab);
   const int vec = threadIdx.x % nvec;
   const int prow = threadIdx.x / nvec;
   const int prows = blockDim.x / nvec;
+  float s = 0.f, ss = 0.f;
   if (prow < prows) {
-    float s = 0.f, ss = 0.f;
     for (int p = p0 + prow; p < p1; p += prows) {
       const uint4 u = *reinterpret_cast<const uint4*>(in + (static_cast<int64_t>(b) * hw + p) * c + vec * 8);
       const float2 a = unpack_bf16(u.x), bb = unpack_bf16(u.y), cc = unpack_bf16(u.z), d = unpack_bf16(u.w);
       s += (a.x + a.y) + (bb.x + bb.y) + (cc.x + cc.y) + (d.x + d.y);
       ss += a.x * a.x + a.y * a.y + bb.x * bb.x + bb.y * bb.y + cc.x * cc.x + cc.y * cc.y + d.x * d.x + d.y * d.y;
     }
-    const int g = (vec * 8) / cpg;
-    atomicAdd(&sh[g * 2], s);
-    atomicAdd(&sh[g * 2 + 1], ss);
   }
+  part[threadIdx.x] = make_float2(s, ss);
   __syncthreads();
-  for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) atomicAdd(&stats[(b * groups) * 2 + i], sh[i]);
+  if (threadIdx.x < groups) {
+    const int g = threadIdx.x, vpg = cpg >> 3;
+    float gs = 0.f, gss = 0.f;
+    for (int r = 0; r < prows; ++r)
+      for (int v = 0; v < vpg; ++v) {
+        const float2 t = part[r * nvec + g * vpg + v];
+        gs += t.x;
+        gss += t.y;
+      }
+    reinterpret_cast<float2*>(stats)[(static_cast<int64_t>(b) * gridDim.x + blockIdx.x) * groups + g] = make_float2(gs, gss);
+  }
 }
 
+// Pass 2: CTA (chunk, image): the image's group statistics are summed over the slabs in order, once per CTA.
 __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const __nv_bfloat16* __restrict__ in,
-                                                              __nv_bfloat16* __restrict__ out, int B, int hw, int c,
-                                                              int groups, const float* __restrict__ w,
+                                                              __nv_bfloat16* __restrict__ out, int hw, int c,
+                                                              int groups, int slabs, const float* __restrict__ w,
                                                               const float* __restrict__ bias, float eps,
                                                               const float* __restrict__ stats) {
+  __shared__ float2 mr[256];                     // {mean, rstd} per group
+  griddep_wait();
   griddep_launch();
+  const int b = blockIdx.y;
   const int nvec = c >> 3;
   const int cpg = c / groups;
-  const int64_t total = static_cast<int64_t>(B) * hw * nvec;
-  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  const float inv_n = 1.0f / (static_cast<float>(hw) * cpg);
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int vec = static_cast<int>(i % nvec);
-    const int b = static_cast<int>(i / (static_cast<int64_t>(hw) * nvec));
-    const int g = (vec * 8) / cpg;
-    const float s = __ldg(stats + (b * groups + g) * 2), ss = __ldg(stats + (b * groups + g) * 2 + 1);
+  if (threadIdx.x < groups) {
+    float s = 0.f, ss = 0.f;
+    for (int k = 0; k < slabs; ++k) {
+      const float2 t = __ldg(reinterpret_cast<const float2*>(stats) + (static_cast<int64_t>(b) * slabs + k) * groups + threadIdx.x);
+      s += t.x;
+      ss += t.y;
+    }
+    const float inv_n = 1.0f / (static_cast<float>(hw) * cpg);
     const float mean = s * inv_n;
     const float var = fmaxf(ss * inv_n - mean * mean, 0.f);
-    const float rstd = rsqrtf(var + eps);
-    const uint4 u = reinterpret_cast<const uint4*>(in)[i];
+    mr[threadIdx.x] = make_float2(mean, rsqrtf(var + eps));
+  }
+  __syncthreads();
+  const int64_t per_image = static_cast<int64_t>(hw) * nvec;
+  const uint4* ib = reinterpret_cast<const uint4*>(in) + b * per_image;
+  uint4* ob = reinterpret_cast<uint4*>(out) + b * per_image;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < per_image;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int vec = static_cast<int>(i % nvec);
+    const float2 m = mr[(vec * 8) / cpg];
+    const float mean = m.x, rstd = m.y;
+    const uint4 u = ib[i];
     float v[8];
     float2 t;
     t = unpack_bf16(u.x); v[0] = t.x; v[1] = t.y;
@@ -306,7 +330,7 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const __nv_bfloat1
     uint4 o;
     o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]);
     o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
-    reinterpret_cast<uint4*>(out)[i] = o;
+    ob[i] = o;
   }
 }
 
@@ -532,18 +556,20 @@ extern "C" int dac_groupnorm_nhwc(const void* in, void* out, int32_t B, int32_t 
   if (c % groups || (c / groups) % 8 || c / 8 > 256) return set_error(-2, "dac_groupnorm_nhwc: need 8 | c/groups, c <= 2048");
   if ((reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(b)) & 15)
     return set_error(-2, "dac_groupnorm_nhwc: w and b must be 16-byte aligned");
+  if (groups > 256 || B > 65535) return set_error(-2, "dac_groupnorm_nhwc: groups <= 256, B <= 65535");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  cudaMemsetAsync(stats, 0, sizeof(float) * 2 * B * groups, s);
-  const int slabs = hw >= 1024 ? 16 : (hw >= 64 ? 4 : 1);
-  const int slab = static_cast<int>(ceil_div(hw, slabs));
-  groupnorm_stats_kernel<<<dim3(slabs, B), 256, groups * 2 * sizeof(float), s>>>(
-      static_cast<const __nv_bfloat16*>(in), hw, c, groups, slab, stats);
+  const int slab = static_cast<int>(ceil_div(hw, kGnSlabs));
+  launch_k(groupnorm_stats_kernel, dim3(kGnSlabs, B), dim3(256), 0, s, static_cast<const __nv_bfloat16*>(in), hw, c, groups,
+           slab, stats);
   int rc = check_launch("groupnorm_stats_kernel");
   if (rc) return rc;
-  const int64_t total = static_cast<int64_t>(B) * hw * (c / 8);
-  groupnorm_apply_kernel<<<elementwise_grid(total), 256, 0, s>>>(static_cast<const __nv_bfloat16*>(in),
-                                                                static_cast<__nv_bfloat16*>(out), B, hw, c, groups, w,
-                                                                b, eps, stats);
+  const int64_t per_image = static_cast<int64_t>(hw) * (c / 8);
+  int64_t chunks = ceil_div(per_image, 256 * 4);
+  const int64_t cap = ceil_div(148 * 16, B);
+  if (chunks > cap) chunks = cap;
+  launch_k(groupnorm_apply_kernel, dim3(static_cast<unsigned>(chunks < 1 ? 1 : chunks), B), dim3(256), 0, s,
+           static_cast<const __nv_bfloat16*>(in), static_cast<__nv_bfloat16*>(out), hw, c, groups, kGnSlabs, w, b, eps,
+           static_cast<const float*>(stats));
   return check_launch("groupnorm_apply_kernel");
 }
 

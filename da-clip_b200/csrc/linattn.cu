@@ -148,17 +148,22 @@ __global__ void __launch_bounds__(128) linattn_context_kernel(const __nv_bfloat1
   }
 }
 
+// One CTA per (head, image, group of kFoldRows d rows): the merge is a sum over `nchunks` partial records in a FIXED
+// order (two interleaved chains + one add; warp-shuffle trees for the denominators), so the result is bit-reproducible
+// whichever CTA of the producing kernel finished first.  Splitting the d rows over CTAs keeps the kernel short when one
+// image spans every CTA of the producer (batch 1: 148 or 296 records per head).
+constexpr int kFoldRows = 4;
 __global__ void __launch_bounds__(256) linattn_fold_kernel(const float* __restrict__ partial, int hw, int nchunks,
                                                            const float* __restrict__ w_out, int C, int c_pad,
                                                            __nv_bfloat16* __restrict__ weff) {
-  // one CTA per (head, image): everything staged in shared memory with coalesced loads first (the kernel is a latency
-  // chain, not a throughput problem), then C x 32 dot products of length 32
   extern __shared__ float fold_sm[];
-  float* ctx = fold_sm;                 // [32][33]
-  float* wgt = ctx + 32 * 33;           // [nchunks][32] merge weights
-  float* inv_s = wgt + nchunks * 32;    // [32]
-  float* wsm = inv_s + 32;              // [C][33]: W_out[c][h*32 + e]
-  const int h = blockIdx.x, b = blockIdx.y, t = threadIdx.x;
+  float* wsm = fold_sm;                          // [C][33]: W_out[c][h*32 + e]
+  float* wgt = wsm + C * 33;                     // [nchunks][kFoldRows] merge weights exp(m_c - M)
+  float* red = wgt + nchunks * kFoldRows;        // [2][kFoldRows * 32] the two chains
+  float* ctx = red + 2 * kFoldRows * 32;         // [kFoldRows][33]
+  __shared__ float inv_s[kFoldRows];
+  const int h = blockIdx.x, b = blockIdx.y, d0 = blockIdx.z * kFoldRows, t = threadIdx.x;
+  const int warp = t >> 5, lane = t & 31;
   const float* pbase = partial + (static_cast<int64_t>(b) * 4 + h) * nchunks * kPartial;
   griddep_launch();
   for (int i = t; i < C * 32; i += 256) {       // a constant: staged while the context kernel drains
@@ -166,32 +171,42 @@ __global__ void __launch_bounds__(256) linattn_fold_kernel(const float* __restri
     wsm[c * 33 + e] = __ldg(w_out + static_cast<int64_t>(c) * 128 + h * 32 + e);
   }
   griddep_wait();
-  if (t < 32) {
+  if (warp < kFoldRows) {                        // warp w: running-max merge weights and the denominator of row d0 + w
+    const int d = d0 + warp;
     float M = -INFINITY;
-    for (int c = 0; c < nchunks; ++c) M = fmaxf(M, pbase[c * kPartial + 1024 + t]);
+    for (int c = lane; c < nchunks; c += 32) M = fmaxf(M, pbase[c * kPartial + 1024 + d]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o));
     float S = 0.f;
-    for (int c = 0; c < nchunks; ++c) {
-      const float mc = pbase[c * kPartial + 1024 + t];
+    for (int c = lane; c < nchunks; c += 32) {
+      const float mc = pbase[c * kPartial + 1024 + d];
       const float w = (mc == -INFINITY) ? 0.f : __expf(mc - M);
-      wgt[c * 32 + t] = w;
-      S += pbase[c * kPartial + 1056 + t] * w;
+      wgt[c * kFoldRows + warp] = w;
+      S += pbase[c * kPartial + 1056 + d] * w;
     }
-    inv_s[t] = 1.0f / (S * static_cast<float>(hw));   // softmax denominator and v / (h*w) (module_util.py:177)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) S += __shfl_xor_sync(0xffffffffu, S, o);
+    if (lane == 0) inv_s[warp] = 1.0f / (S * static_cast<float>(hw));   // softmax denominator and v / (h*w) (module_util.py:177)
   }
   __syncthreads();
-  for (int i = t; i < 1024; i += 256) {
-    const int d = i >> 5, e = i & 31;
+  {
+    const int elem = t & (kFoldRows * 32 - 1), part = t >> 7;            // 128 context elements x 2 chains
+    const int dl = elem >> 5;
+    const float* src = pbase + d0 * 32 + elem;
     float a = 0.f;
-    for (int c = 0; c < nchunks; ++c) a += pbase[c * kPartial + i] * wgt[c * 32 + d];
-    ctx[d * 33 + e] = a * inv_s[d];
+#pragma unroll 4
+    for (int c = part; c < nchunks; c += 2) a += src[static_cast<int64_t>(c) * kPartial] * wgt[c * kFoldRows + dl];
+    red[part * (kFoldRows * 32) + elem] = a;
   }
   __syncthreads();
-  const int d = t & 31;
-  for (int c = t >> 5; c < C; c += 8) {
+  if (t < kFoldRows * 32) ctx[(t >> 5) * 33 + (t & 31)] = (red[t] + red[kFoldRows * 32 + t]) * inv_s[t >> 5];
+  __syncthreads();
+  const int dl = t & (kFoldRows - 1);
+  for (int c = t >> 2; c < C; c += 64) {
     float a = 0.f;
 #pragma unroll
-    for (int e = 0; e < 32; ++e) a = fmaf(wsm[c * 33 + e], ctx[d * 33 + e], a);
-    weff[(static_cast<int64_t>(b) * c_pad + c) * 128 + h * 32 + d] = __float2bfloat16(a);
+    for (int e = 0; e < 32; ++e) a = fmaf(wsm[c * 33 + e], ctx[dl * 33 + e], a);
+    weff[(static_cast<int64_t>(b) * c_pad + c) * 128 + h * 32 + d0 + dl] = __float2bfloat16(a);
   }
 }
 
@@ -213,14 +228,15 @@ extern "C" int dac_linattn_context(const void* kv, int32_t B, int32_t hw, int32_
 extern "C" int dac_linattn_fold(const float* partial, int32_t B, int32_t hw, int32_t nchunks, const float* w_out,
                                 int32_t C, int32_t c_pad, void* weff, dac_stream_t stream) {
   if (!partial || !w_out || !weff) return set_error(-1, "dac_linattn_fold: null argument");
-  if (nchunks < 1 || nchunks > 128) return set_error(-2, "dac_linattn_fold: nchunks must be in [1,128]");
+  if (nchunks < 1 || nchunks > 2048) return set_error(-2, "dac_linattn_fold: nchunks must be in [1,2048]");
   if (C <= 0 || C > 256) return set_error(-2, "dac_linattn_fold: C must be in [1,256]");
-  const size_t smem = sizeof(float) * (32 * 33 + nchunks * 32 + 32 + static_cast<size_t>(C) * 33);
+  const size_t smem = sizeof(float) * (static_cast<size_t>(C) * 33 + static_cast<size_t>(nchunks) * kFoldRows +
+                                       2 * kFoldRows * 32 + kFoldRows * 33);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(linattn_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error(-12, "dac_linattn_fold: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   }
-  launch_k(linattn_fold_kernel, dim3(4, B), dim3(256), smem, static_cast<cudaStream_t>(stream), partial, hw, nchunks, w_out,
+  launch_k(linattn_fold_kernel, dim3(4, B, 32 / kFoldRows), dim3(256), smem, static_cast<cudaStream_t>(stream), partial, hw, nchunks, w_out,
            C, c_pad, static_cast<__nv_bfloat16*>(weff));
   return check_launch("linattn_fold_kernel");
 }

@@ -32,7 +32,8 @@ constexpr int kCtxRec = 32 * 32 + 64;          // {C[32][32], m[32], S[32]} per 
 struct KvParams {
   int tiles, tiles_per_image, stages, nbuf;
   const float* shift;      // [128]: c_d * log2(e), original k channel order (head-major)
-  float* ctx_acc;          // [B][4][kCtxRec]
+  float* ctx_acc;          // [B][4][slots][kCtxRec]: one partial record per (CTA, image), slot = CTA - first CTA of the image
+  int slots;
 };
 
 template <int C>
@@ -218,14 +219,16 @@ linattn_kv_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       tc_fence_after();
       ++flushes;
       const int h = quad, d = lane;                       // lane row = 32 h + d
-      float* rec = p.ctx_acc + (static_cast<long long>(img) * 4 + h) * kCtxRec;
+      const int slot = static_cast<int>(blockIdx.x) - tile_owner(img * p.tiles_per_image, p.tiles, gridDim.x);
+      float* rec = p.ctx_acc + ((static_cast<long long>(img) * 4 + h) * p.slots + slot) * kCtxRec;
       chunk_from_tmem(lane_base + kColC + 32 * h, v);     // the diagonal block: columns (h, e)
 #pragma unroll
-      for (int e = 0; e < 32; ++e) atomicAdd(rec + d * 32 + e, v[e]);
+      for (int q = 0; q < 8; ++q)
+        *reinterpret_cast<float4*>(rec + d * 32 + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
       uint32_t r[16];
       tmem_ld16(lane_base + kColS, r);
       tmem_ld_wait();
-      atomicAdd(rec + 1056 + d, __uint_as_float(r[0]));
+      rec[1056 + d] = __uint_as_float(r[0]);
       tc_fence_before();
       mbar_arrive(ctx_flushed);
     };
@@ -298,7 +301,7 @@ static int kv_encode_2d(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_
 }
 
 extern "C" int dac_linattn_kv_create(const void* xn, const void* wkv, const float* kv_shift, float* ctx_acc,
-                                     int32_t B, int32_t hw, int32_t C, dac_kv_t* plan) {
+                                     int32_t ctx_slots, int32_t B, int32_t hw, int32_t C, dac_kv_t* plan) {
   if (!xn || !wkv || !kv_shift || !ctx_acc || !plan) return set_error(-1, "dac_linattn_kv_create: null argument");
   *plan = nullptr;
   if (C != 64 && C != 128) return set_error(-2, "dac_linattn_kv_create: C must be 64 or 128 (got %d)", C);
@@ -330,6 +333,12 @@ extern "C" int dac_linattn_kv_create(const void* xn, const void* wkv, const floa
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   pl->grid = k.tiles < sms ? k.tiles : sms;
+  k.slots = ctx_slots;
+  if (ctx_slots < max_image_span(B, k.tiles_per_image, pl->grid)) {
+    const int need = max_image_span(B, k.tiles_per_image, pl->grid);
+    delete pl;
+    return set_error(-2, "dac_linattn_kv_create: ctx_slots must be >= %d (dac_linattn_ctx_slots), got %d", need, ctx_slots);
+  }
   cudaError_t e = C == 64 ? cudaFuncSetAttribute(linattn_kv_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->smem)
                           : cudaFuncSetAttribute(linattn_kv_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->smem);
   if (e != cudaSuccess) {
@@ -344,7 +353,7 @@ extern "C" int dac_linattn_kv_create(const void* xn, const void* wkv, const floa
 extern "C" int dac_linattn_kv_launch(dac_kv_t pl, dac_stream_t stream) {
   if (!pl) return set_error(-1, "dac_linattn_kv_launch: null plan");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  cudaError_t e = cudaMemsetAsync(pl->kp.ctx_acc, 0, sizeof(float) * pl->B * 4 * kCtxRec, st);
+  cudaError_t e = cudaMemsetAsync(pl->kp.ctx_acc, 0, sizeof(float) * pl->B * 4 * pl->kp.slots * kCtxRec, st);
   if (e != cudaSuccess) return set_error(-20, "dac_linattn_kv_launch: memset failed: %s", cudaGetErrorString(e));
   if (pl->C == 64) linattn_kv_kernel<64><<<pl->grid, kThreads, pl->smem, st>>>(pl->mapX, pl->mapW, pl->kp);
   else linattn_kv_kernel<128><<<pl->grid, kThreads, pl->smem, st>>>(pl->mapX, pl->mapW, pl->kp);

@@ -24,6 +24,20 @@ __device__ __forceinline__ void tile_range(int total, int& begin, int& end) {
   end = static_cast<int>(static_cast<long long>(total) * (blockIdx.x + 1) / gridDim.x);
 }
 
+// Inverse of tile_range: the CTA whose range holds tile t (ceil((t + 1) * grid / total) - 1).
+__host__ __device__ __forceinline__ int tile_owner(int t, int total, int grid) {
+  return static_cast<int>((static_cast<long long>(t + 1) * grid + total - 1) / total) - 1;
+}
+// Most CTAs any image spans when every image is tpi consecutive tiles of B * tpi (see dac_linattn_ctx_slots).
+inline int max_image_span(int B, int tpi, int grid) {
+  int span = 1;
+  for (int b = 0; b < B; ++b) {
+    const int s = tile_owner((b + 1) * tpi - 1, B * tpi, grid) - tile_owner(b * tpi, B * tpi, grid) + 1;
+    span = s > span ? s : span;
+  }
+  return span;
+}
+
 // ---- 32-column chunk helpers: everything statically indexed so the chunk lives in registers ----
 __device__ __forceinline__ void chunk_from_tmem(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];

@@ -46,6 +46,7 @@ class ConvDesc(C.Structure):
         ("out_nchw", C.c_void_p), ("out_nchw_c", C.c_int32), ("out_nchw_h", C.c_int32), ("out_nchw_w", C.c_int32),
         ("kv_shift", C.c_void_p), ("ctx_acc", C.c_void_p),
         ("halo", C.c_int32),
+        ("ctx_slots", C.c_int32),
     ]
 
 
@@ -91,7 +92,8 @@ SYMBOLS = {
     "dac_text_embed": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _p]),
     "dac_text_pool": (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p, _f, _p, _i32, _p, _p]),
     "dac_degradation_argmax": (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p, _p]),
-    "dac_linattn_kv_create": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _i32, C.POINTER(_p)]),
+    "dac_linattn_ctx_slots": (C.c_int32, [_i32, _i32, _i32]),
+    "dac_linattn_kv_create": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _i32, _i32, C.POINTER(_p)]),
     "dac_linattn_kv_launch": (C.c_int, [_p, _p]),
     "dac_linattn_kv_destroy": (None, [_p]),
     "dac_linattn_qout_create": (C.c_int, [_p, _p, _p, _i32, _p, _p, _p, _p, _f, _i32, _i32, _i32, C.POINTER(_p)]),

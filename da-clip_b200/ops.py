@@ -221,6 +221,7 @@ class ConvPlan:
             d.ln_stats, d.ln_colsum = ln_stats.data_ptr(), ln_colsum.data_ptr()
         if kv_shift is not None:     # EPI_KVCTX: k | v reduced into the LinearAttention context in the epilogue
             d.kv_shift, d.ctx_acc = kv_shift.data_ptr(), ctx_acc.data_ptr()
+            d.ctx_slots = ctx_acc.shape[-2]              # [B, 4, slots, 1088]: see ctx_slots()
         if out_nchw is not None:
             d.out_nchw = out_nchw.data_ptr()
             d.out_nchw_c, d.out_nchw_h, d.out_nchw_w = out_nchw.shape[1], out_nchw.shape[2], out_nchw.shape[3]
@@ -250,6 +251,17 @@ class ConvPlan:
             pass
 
 
+def ctx_slots(B, h, w, tensor_core_kv):
+    """Partial context records per (image, head) the k|v kernels store (dac_linattn_ctx_slots): one per CTA that touches
+    the image for dac_linattn_kv, two (one per epilogue group) for the KVCTX convolution epilogue."""
+    if tensor_core_kv:
+        tpi, groups = (h * w) // 128, 1
+    else:
+        th, tw = choose_tile(h, w, 1)
+        tpi, groups = (-(-h // th)) * (-(-w // tw)), 2
+    return int(L.load().dac_linattn_ctx_slots(B, tpi, groups))
+
+
 def pack_kv_grouped(wkv):
     """[256, C] rows (k heads 0-3 | v heads 0-3, 32 each) -> rows packed per head pair g: k_2g k_2g+1 v_2g v_2g+1
     (the N = 128 accumulator of epilogue group g then holds exactly its heads); bf16 contiguous."""
@@ -265,7 +277,7 @@ class KvPlan:
         lib = L.load()
         h = C.c_void_p()
         L.check(lib.dac_linattn_kv_create(xn.data_ptr(), wkv_grouped.data_ptr(), kv_shift.data_ptr(),
-                                          ctx_acc.data_ptr(), B, hw, Cn, C.byref(h)))
+                                          ctx_acc.data_ptr(), ctx_acc.shape[-2], B, hw, Cn, C.byref(h)))
         self.handle, self._lib = h, lib
         self._keep = (xn, wkv_grouped, kv_shift, ctx_acc)
         self.flops = 2.0 * B * hw * Cn * 256

@@ -438,8 +438,12 @@ class UNetEngine:
                 # k | v never reach memory: the KVCTX epilogue reduces them into {C, S} per (image, head)
                 xn = self.buf(B, h, w, C)
                 self.add(prefix + "prenorm", lambda: ops.layernorm_rows(x, xn, B * hw, C, None, None, 1e-5))
-                ctx = self.buf(B, 4, 1, 32 * 34, dtype=torch.float32)
-                if self.FUSE_KV_TC and C == 64 and hw % 128 == 0:
+                kv_tc = self.FUSE_KV_TC and C == 64 and hw % 128 == 0
+                # partial {C, S} records, one per CTA (and epilogue group) that touches the image, merged in slot order by
+                # the fold kernel: no atomics, so an evaluation is bit-reproducible
+                nslots = ops.ctx_slots(B, h, w, kv_tc)
+                ctx = self.buf(B, 4, nslots, 32 * 34, dtype=torch.float32)
+                if kv_tc:
                     # ... and reduced on tcgen05 too: P^T V with MN-major operands, context accumulated in TMEM
                     # (measured: 128 -> 111 us at level 0; the C = 128 instances have room for one P|V buffer only
                     # and run 25 % slower than the KVCTX epilogue, so they keep it)
@@ -454,14 +458,14 @@ class UNetEngine:
                 self.flops += 2.0 * B * 4 * 32 * 32 * hw
                 if self.FUSE_QOUT and C in (64, 128) and hw % 128 == 0:
                     # q never reaches memory either: to_q -> softmax -> W_eff q -> LayerNorm -> + x in one kernel
-                    self.add(prefix + "fold", lambda: ops.linattn_fold(ctx, B, hw, 1, a["w_out"], C, c_pad, weff))
+                    self.add(prefix + "fold", lambda: ops.linattn_fold(ctx, B, hw, nslots, a["w_out"], C, c_pad, weff))
                     plan = ops.QoutPlan(xn, a["q"].w, weff, x, out, a["b_out"], a["g_out"], 1e-5, B, hw, C)
                     self.flops += plan.flops
                     self.conv_names.add(prefix + "to_q_out")
                     self.add(prefix + "to_q_out", plan.run)
                     return out
                 self.conv(prefix + "to_q", xn, C, a["q"], q, h, w, epi=L.EPI_QKV, block_n=128)
-                self.add(prefix + "fold", lambda: ops.linattn_fold(ctx, B, hw, 1, a["w_out"], C, c_pad, weff))
+                self.add(prefix + "fold", lambda: ops.linattn_fold(ctx, B, hw, nslots, a["w_out"], C, c_pad, weff))
                 self.conv(prefix + "to_out", q, 128, a["out"], out, h, w, epi=L.EPI_LN, bias=a["b_out"],
                           ln_g=a["g_out"], res=x, per_image_w=True, weight_override=weff)
                 return out
@@ -486,7 +490,7 @@ class UNetEngine:
         self.add(prefix + "prenorm", lambda: ops.layernorm_rows(x, xn, B * hw, C, a["pre_g"], None, 1e-5))
         heads = a["heads"]
         gn = self.buf(B, h, w, C)
-        stats = self.buf(B * 64, dtype=torch.float32)
+        stats = self.buf(B * 16 * 64, dtype=torch.float32)       # [B][16 slabs][32 groups][2]
         self.add(prefix + "groupnorm", lambda: ops.groupnorm_nhwc(xn, gn, B, hw, C, a["gn_w"], a["gn_b"], stats))
         y0 = self.buf(B, h, w, C)
         self.conv(prefix + "proj_in", gn, C, a["proj_in"], y0, h, w, bias=a["proj_in_b"])

@@ -75,9 +75,11 @@ enum {
                          context reduction consumes without a transpose).  cout 128 = q only. MU:170-177 */
   DAC_EPI_KVCTX = 4   /* cout 256 = k | v of LinearAttention, NEVER written to memory: the epilogue forms
                          P = exp(k - kv_shift[d]) and accumulates C[h][d][e] += sum_pixels P[d] v[e] and
-                         S[h][d] += sum_pixels P[d] on the warp tensor cores, then adds them into ctx_acc
-                         (one {C[32][32], m[32] = 0, S[32]} record per (image, head) - the partial format of
-                         dac_linattn_fold with nchunks = 1).  kv_shift is a data-independent upper bound of k
+                         S[h][d] += sum_pixels P[d] on the warp tensor cores, then STORES them as partial records
+                         {C[32][32], m[32] = 0, S[32]} in ctx_acc [B][4][ctx_slots][1088] - the partial format of
+                         dac_linattn_fold with nchunks = ctx_slots; slot = 2 * (CTA - first CTA of the image) +
+                         epilogue group, so the fold adds them in a fixed order: bit-reproducible, no atomics (see
+                         dac_linattn_ctx_slots).  kv_shift is a data-independent upper bound of k
                          (|k_d| <= ||W_k[d]|| sqrt(C) after the gain-free PreNorm), times log2(e)  MU:170-177 */
 };
 enum { DAC_ACT_NONE = 0, DAC_ACT_SILU = 1, DAC_ACT_GELU = 2 };
@@ -130,10 +132,12 @@ typedef struct dac_conv_desc {
   float* stats_out; float stats_eps;              /* [B*OH*OW][2] fp32 */
   const float* ln_stats; const float* ln_colsum;  /* QKV: [B*OH*OW][2], [cout] */
   float* out_nchw; int32_t out_nchw_c, out_nchw_h, out_nchw_w; /* alt. fp32 NCHW output (final_conv), cropped */
-  const float* kv_shift; float* ctx_acc;          /* KVCTX: [128] shift * log2(e); [B][4][1088] fp32 (zeroed by launch) */
+  const float* kv_shift; float* ctx_acc;          /* KVCTX: [128] shift * log2(e); [B][4][ctx_slots][1088] fp32 (zeroed by launch) */
   int32_t halo;                                   /* 3x3 stride-1, tile_w 8: ONE (tile_h+2) x (tile_w+2) load per K chunk
                                                      serves all nine taps (descriptors with a (tile_w+2)*128 B group
                                                      stride); ncols = 1, ndy = 9, col_dx = col_dy0 = -1 */
+  int32_t ctx_slots;                              /* KVCTX: partial records per (image, head) in ctx_acc,
+                                                     >= dac_linattn_ctx_slots(B, tiles per image, 2) */
 } dac_conv_desc;
 
 typedef struct dac_conv_plan* dac_conv_t;
@@ -149,7 +153,8 @@ int dac_conv_info(dac_conv_t plan, int32_t* tiles, int32_t* ctas, int32_t* smem_
  * rows = pixels) and nn.LayerNorm of the transformer blocks (ATT:203-205) and ViT (TR:22-28). */
 int dac_layernorm_rows(const void* in, int32_t ld_in, void* out, int32_t ld_out, int64_t rows, int32_t c,
                        const float* w, const float* b, float eps, dac_stream_t stream);
-/* GroupNorm(32 groups, eps) over NHWC bf16 [B, hw, c] (ATT:76-77,251).  stats: workspace [B*32*2] fp32. */
+/* GroupNorm(32 groups, eps) over NHWC bf16 [B, hw, c] (ATT:76-77,251).  stats: workspace [B][16][groups][2] fp32 (per-slab
+ * partial sums, added in a fixed order: no atomics, bit-reproducible). */
 /* Same, fp32 input rows (the ViT residual stream), bf16 output. */
 int dac_layernorm_rows_f32(const float* in, int32_t ld_in, void* out, int32_t ld_out, int64_t rows, int32_t c,
                            const float* w, const float* b, float eps, dac_stream_t stream);
@@ -189,14 +194,21 @@ int dac_linattn_context(const void* kv, int32_t B, int32_t hw, int32_t nchunks, 
 int dac_linattn_fold(const float* partial, int32_t B, int32_t hw, int32_t nchunks, const float* w_out /*[C,128] fp32*/,
                      int32_t C, int32_t c_pad, void* weff /*[B][c_pad][128] bf16*/, dac_stream_t stream);
 
+/* Partial records per (image, head) that the context-reducing kernels need: an image's tiles are contiguous in the tile
+ * order and CTA b owns tiles [tiles*b/grid, tiles*(b+1)/grid), grid = min(tiles, SM count); every CTA that touches an
+ * image stores `groups` partials for it (2 for DAC_EPI_KVCTX - one per epilogue group - 1 for dac_linattn_kv).  Returns
+ * groups * (largest number of CTAs any image spans). */
+int32_t dac_linattn_ctx_slots(int32_t B, int32_t tiles_per_image, int32_t groups);
+
 /* Key/value side of LinearAttention entirely on tcgen05 (MU:170-177): per 128-pixel tile k | v = wkv . xn, P = exp(k - c_d)
  * (kv_shift as for DAC_EPI_KVCTX), then C += P^T V and S += P^T 1 as a second tensor-core GEMM with MN-major operands,
- * accumulated in tensor memory over the tiles of an image and added into ctx_acc ([B][4][1088] fp32, zeroed by the
- * launch; record format of dac_linattn_fold with nchunks = 1).  xn: bf16 [B*hw, C] (C = 64 or 128, hw % 128 == 0);
+ * accumulated in tensor memory over the CTA's tiles of an image and stored as one partial record per (CTA, image) into
+ * ctx_acc [B][4][ctx_slots][1088] fp32 (zeroed by the launch; ctx_slots >= dac_linattn_ctx_slots(B, hw / 128, 1);
+ * merged in slot order by dac_linattn_fold with nchunks = ctx_slots).  xn: bf16 [B*hw, C] (C = 64 or 128, hw % 128 == 0);
  * wkv: bf16 [256][C], rows packed per head pair g as k_2g k_2g+1 v_2g v_2g+1.  Replaces DAC_EPI_KVCTX where it fits. */
 typedef struct dac_kv_plan* dac_kv_t;
-int dac_linattn_kv_create(const void* xn, const void* wkv, const float* kv_shift, float* ctx_acc, int32_t B,
-                          int32_t hw, int32_t C, dac_kv_t* plan);
+int dac_linattn_kv_create(const void* xn, const void* wkv, const float* kv_shift, float* ctx_acc, int32_t ctx_slots,
+                          int32_t B, int32_t hw, int32_t C, dac_kv_t* plan);
 int dac_linattn_kv_launch(dac_kv_t plan, dac_stream_t stream);
 void dac_linattn_kv_destroy(dac_kv_t plan);
 

@@ -339,15 +339,25 @@ def test_linear_attention_fused_kv_context(ops, gen, B, H, W, C):
     wk = bf(wkv[:128]).float()
     shift = (1.02 * wk.norm(dim=1) * math.sqrt(C))
     assert shift.max().item() <= 40
-    ctx = torch.full((B, 4, 1, 32 * 34), float("nan"), device="cuda")
+    ns = ops.ctx_slots(B, H, W, False)
+    ctx = torch.full((B, 4, ns, 32 * 34), float("nan"), device="cuda")
     plan = ops.ConvPlan(xh, C, ops.pack_linear(wkv), None, B=B, H=H, W=W, epi=L.EPI_KVCTX, block_n=256,
                         kv_shift=(shift * 1.4426950408889634).contiguous(), ctx_acc=ctx)
     c_pad = ops.choose_block_n(C)[1]
     weff = torch.zeros(B, c_pad, 128, device="cuda", dtype=torch.bfloat16)
-    for _ in range(2):                                         # relaunch: the accumulator is re-zeroed every time
+    for _ in range(2):                                         # relaunch: the partial records are re-zeroed every time
         plan.run()
-    ops.linattn_fold(ctx, B, hw, 1, w_out, C, c_pad, weff)
+    ops.linattn_fold(ctx, B, hw, ns, w_out, C, c_pad, weff)
     torch.cuda.synchronize()
+    first = (ctx.clone(), weff.clone())
+    plan.run()                                                 # stores in fixed slots, fixed-order merge: bit-reproducible
+    ops.linattn_fold(ctx, B, hw, ns, w_out, C, c_pad, weff)
+    torch.cuda.synchronize()
+    assert torch.equal(ctx, first[0]) and torch.equal(weff, first[1])
+    with pytest.raises(L.DacError):                            # too few slots is an error, not a silent overflow
+        ops.ConvPlan(xh, C, ops.pack_linear(wkv), None, B=B, H=H, W=W, epi=L.EPI_KVCTX, block_n=256,
+                     kv_shift=(shift * 1.4426950408889634).contiguous(), ctx_acc=ctx[:, :, :1].contiguous())
+    ctx = ctx.sum(2, keepdim=True)
     kvr = F.conv2d(nchw(xh), bf(wkv).float()[:, :, None, None]).reshape(B, 2, 4, 32, hw)
     k, v = kvr[:, 0].softmax(-1), kvr[:, 1] / hw
     ctx_ref = torch.einsum("bhdn,bhen->bhde", k, v)            # [B, 4, 32, 32]
@@ -369,11 +379,16 @@ def test_linear_attention_kv_tensor_core_context(ops, gen, B, H, W, C):
     wkv = rnd(gen, 256, C, scale=C ** -0.5)
     wkv[:128] *= 1.5
     shift = 1.02 * bf(wkv[:128]).float().norm(dim=1) * math.sqrt(C)
-    ctx = torch.full((B, 4, 1, 32 * 34), float("nan"), device="cuda")
+    ctx = torch.full((B, 4, ops.ctx_slots(B, H, W, True), 32 * 34), float("nan"), device="cuda")
     plan = ops.KvPlan(xh, ops.pack_kv_grouped(wkv), (shift * 1.4426950408889634).contiguous(), ctx, B, hw, C)
     for _ in range(2):
         plan.run()
     torch.cuda.synchronize()
+    first = ctx.clone()
+    plan.run()
+    torch.cuda.synchronize()
+    assert torch.equal(ctx, first)                             # one record per (CTA, image), plain stores
+    ctx = ctx.sum(2, keepdim=True)
     kvr = F.conv2d(nchw(xh), bf(wkv).float()[:, :, None, None]).reshape(B, 2, 4, 32, hw)
     k, v = kvr[:, 0].softmax(-1), kvr[:, 1] / hw
     ctx_ref = torch.einsum("bhdn,bhen->bhde", k, v)
@@ -401,7 +416,8 @@ def test_linear_attention_chained_q_out(ops, gen, B, H, W, C):
     ref = O.linear_attention(sdr, "", nchw(xh)) + nchw(rh)
     wqkv = sd["to_qkv.weight"].reshape(384, C)
     shift = 1.02 * bf(wqkv[128:256]).float().norm(dim=1) * math.sqrt(C)
-    ctx = torch.zeros(B, 4, 1, 32 * 34, device="cuda")
+    ns = ops.ctx_slots(B, H, W, False)
+    ctx = torch.zeros(B, 4, ns, 32 * 34, device="cuda")
     c_pad = ops.choose_block_n(C)[1]
     weff = torch.zeros(B, c_pad, 128, device="cuda", dtype=torch.bfloat16)
     out = torch.full((B, H, W, C), float("nan"), device="cuda", dtype=torch.bfloat16)
@@ -412,7 +428,7 @@ def test_linear_attention_chained_q_out(ops, gen, B, H, W, C):
                       B, hw, C)
     for _ in range(2):
         pkv.run()
-        ops.linattn_fold(ctx, B, hw, 1, sd["to_out.0.weight"].reshape(C, 128).contiguous(), C, c_pad, weff)
+        ops.linattn_fold(ctx, B, hw, ns, sd["to_out.0.weight"].reshape(C, 128).contiguous(), C, c_pad, weff)
         pq.run()
     torch.cuda.synchronize()
     assert_close_bf16(nchw(out), ref, f"chained linear attention {H}x{W} C={C}", rel=2 ** -5, abs_=2e-2)
@@ -512,7 +528,7 @@ def test_fp32_residual_stream(ops, gen):
 def test_groupnorm(ops, gen, B, hw, c):
     x = bf(rnd(gen, B, hw, c) + 0.3)
     w, b = 1 + 0.1 * rnd(gen, c), rnd(gen, c)
-    out, stats = torch.zeros_like(x), torch.zeros(B * 64, device="cuda")
+    out, stats = torch.zeros_like(x), torch.full((B * 16 * 64,), float("nan"), device="cuda")
     ops.groupnorm_nhwc(x, out, B, hw, c, w, b, stats)
     torch.cuda.synchronize()
     ref = F.group_norm(x.float().transpose(1, 2), 32, w, b, 1e-6).transpose(1, 2)

@@ -43,7 +43,7 @@ def make(name):
     elif kind == "kv":
         w = torch.randn(cout, cin, device="cuda", generator=g) * cin ** -0.5
         shift = torch.full((128,), 12.0, device="cuda")
-        ctx = torch.zeros(B, 4, 1, 32 * 34, device="cuda")
+        ctx = torch.zeros(B, 4, ops.ctx_slots(B, H, W, False), 32 * 34, device="cuda")
         plan = ops.ConvPlan(x, cin, ops.pack_linear(w), None, B=B, H=H, W=W, epi=L.EPI_KVCTX, block_n=256,
                             kv_shift=shift, ctx_acc=ctx)
     elif kind == "toout":
