@@ -114,9 +114,9 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
   if (d->stats_out && (d->epi != DAC_EPI_PLAIN || nchw || d->cout_pad != d->block_n || d->out_scale > 1 ||
                        (reinterpret_cast<uintptr_t>(d->stats_out) & 7)))
     return set_error(-2, "dac_conv_create: stats_out needs the PLAIN epilogue and a single N tile");
-  if ((d->ln_stats != nullptr) != (d->ln_colsum != nullptr) || (d->ln_stats && d->epi != DAC_EPI_QKV) ||
+  if ((d->ln_stats != nullptr) != (d->ln_colsum != nullptr) || (d->ln_stats && d->epi != DAC_EPI_QKV && d->epi != DAC_EPI_KVCTX) ||
       ((reinterpret_cast<uintptr_t>(d->ln_stats) & 7) | (reinterpret_cast<uintptr_t>(d->ln_colsum) & 15)))
-    return set_error(-2, "dac_conv_create: ln_stats / ln_colsum go together, QKV epilogue only");
+    return set_error(-2, "dac_conv_create: ln_stats / ln_colsum go together, QKV and KVCTX epilogues only");
   const bool fused_res = d->rsrc0 != nullptr;
   if (fused_res) {
     if (d->epi != DAC_EPI_PLAIN || nchw || d->cout_pad != d->block_n || 2 * d->block_n > 256 || !d->rweight ||

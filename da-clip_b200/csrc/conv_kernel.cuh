@@ -447,6 +447,16 @@ __device__ __forceinline__ void kvctx_tile(const ConvKParams& p, const TileCoord
   __nv_bfloat16* tiles = reinterpret_cast<__nv_bfloat16*>(stg);
   const int mt = quad >> 1, nh = quad & 1;
   float v[32];
+  // folded PreNorm (raw input rows, gain-folded weights): W' LN(x) = rstd * (W' x - mean * colsum(W'))
+  float ka = 1.4426950408889634f, kb = 0.f, va = 1.f, vb = 0.f;
+  if (p.ln_stats && valid) {
+    const float2 ms = __ldg(reinterpret_cast<const float2*>(p.ln_stats) +
+                            (static_cast<long long>(t.n) * p.OH + t.y0 + ty) * p.OW + t.x0 + tx);
+    va = ms.y;
+    vb = -ms.x * ms.y;
+    ka = va * 1.4426950408889634f;
+    kb = vb * 1.4426950408889634f;
+  }
 #pragma unroll
   for (int h = 0; h < 4; ++h) {
     __nv_bfloat16* Ph = tiles + (h & 1) * (kTileM * kKvPitch);
@@ -454,11 +464,15 @@ __device__ __forceinline__ void kvctx_tile(const ConvKParams& p, const TileCoord
     chunk_from_tmem(tmem_acc + h * 32, v);
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      const float4 sh = __ldg(reinterpret_cast<const float4*>(p.kv_shift + h * 32) + q);
-      v[4 * q] = valid ? ex2_approx(fmaf(v[4 * q], 1.4426950408889634f, -sh.x)) : 0.f;
-      v[4 * q + 1] = valid ? ex2_approx(fmaf(v[4 * q + 1], 1.4426950408889634f, -sh.y)) : 0.f;
-      v[4 * q + 2] = valid ? ex2_approx(fmaf(v[4 * q + 2], 1.4426950408889634f, -sh.z)) : 0.f;
-      v[4 * q + 3] = valid ? ex2_approx(fmaf(v[4 * q + 3], 1.4426950408889634f, -sh.w)) : 0.f;
+      float4 sh = __ldg(reinterpret_cast<const float4*>(p.kv_shift + h * 32) + q);
+      if (p.ln_stats) {
+        const float4 cs = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + h * 32) + q);
+        sh.x = fmaf(cs.x, -kb, sh.x); sh.y = fmaf(cs.y, -kb, sh.y); sh.z = fmaf(cs.z, -kb, sh.z); sh.w = fmaf(cs.w, -kb, sh.w);
+      }
+      v[4 * q] = valid ? ex2_approx(fmaf(v[4 * q], ka, -sh.x)) : 0.f;
+      v[4 * q + 1] = valid ? ex2_approx(fmaf(v[4 * q + 1], ka, -sh.y)) : 0.f;
+      v[4 * q + 2] = valid ? ex2_approx(fmaf(v[4 * q + 2], ka, -sh.z)) : 0.f;
+      v[4 * q + 3] = valid ? ex2_approx(fmaf(v[4 * q + 3], ka, -sh.w)) : 0.f;
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q)
@@ -466,6 +480,16 @@ __device__ __forceinline__ void kvctx_tile(const ConvKParams& p, const TileCoord
           make_uint4(pack_bf16(v[q * 8], v[q * 8 + 1]), pack_bf16(v[q * 8 + 2], v[q * 8 + 3]),
                      pack_bf16(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16(v[q * 8 + 6], v[q * 8 + 7]));
     chunk_from_tmem(tmem_acc + 128 + h * 32, v);
+    if (p.ln_stats) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 cs = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + 128 + h * 32) + q);
+        v[4 * q] = fmaf(v[4 * q], va, cs.x * vb);
+        v[4 * q + 1] = fmaf(v[4 * q + 1], va, cs.y * vb);
+        v[4 * q + 2] = fmaf(v[4 * q + 2], va, cs.z * vb);
+        v[4 * q + 3] = fmaf(v[4 * q + 3], va, cs.w * vb);
+      }
+    }
 #pragma unroll
     for (int q = 0; q < 4; ++q)
       *reinterpret_cast<uint4*>(Vh + row * kKvPitch + q * 8) =

@@ -34,6 +34,8 @@ struct KvParams {
   const float* shift;      // [128]: c_d * log2(e), original k channel order (head-major)
   float* ctx_acc;          // [B][4][slots][kCtxRec]: one partial record per (CTA, image), slot = CTA - first CTA of the image
   int slots;
+  const float* ln_stats;   // folded PreNorm: per-pixel {mean, rstd} of the RAW input row (NULL: the input is normalised)
+  const float* ln_colsum;  // [256] sum_c W'[n][c] of the bf16 weight rows, in the packed (grouped) row order
 };
 
 template <int C>
@@ -239,6 +241,15 @@ linattn_kv_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       const uint32_t use = p.nbuf == 2 ? (i >> 1) : i;
       uint8_t* pt = pv + (static_cast<size_t>(b) * 4 + g) * kKvSlab;        // P slab of this group's heads
       uint8_t* vt = pt + 2 * kKvSlab;                                       // V slab
+      // folded PreNorm: W' LN(x) = rstd * (W' x - mean * colsum(W')); ka / kb put that and log2(e) into the exponent's FMA
+      float ka = 1.4426950408889634f, kb = 0.f, va = 1.f, vb = 0.f;
+      if (p.ln_stats) {
+        const float2 ms = __ldg(reinterpret_cast<const float2*>(p.ln_stats) + static_cast<long long>(begin + i) * kTileM + row);
+        va = ms.y;
+        vb = -ms.x * ms.y;
+        ka = va * 1.4426950408889634f;
+        kb = vb * 1.4426950408889634f;
+      }
       mbar_wait(&acc_full[g], i & 1);
       mbar_wait(&pv_free[b], (use & 1) ^ 1);                                // GEMM 2 of the previous user is done
       tc_fence_after();
@@ -247,14 +258,28 @@ linattn_kv_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         chunk_from_tmem(acc + 32 * j, v);                                   // k of head 2g + j
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + (2 * g + j) * 32) + q);
-          v[4 * q] = ex2_approx(fmaf(v[4 * q], 1.4426950408889634f, -sh.x));
-          v[4 * q + 1] = ex2_approx(fmaf(v[4 * q + 1], 1.4426950408889634f, -sh.y));
-          v[4 * q + 2] = ex2_approx(fmaf(v[4 * q + 2], 1.4426950408889634f, -sh.z));
-          v[4 * q + 3] = ex2_approx(fmaf(v[4 * q + 3], 1.4426950408889634f, -sh.w));
+          float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + (2 * g + j) * 32) + q);
+          if (p.ln_stats) {
+            const float4 cs = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + g * 128 + 32 * j) + q);
+            sh.x = fmaf(cs.x, -kb, sh.x); sh.y = fmaf(cs.y, -kb, sh.y); sh.z = fmaf(cs.z, -kb, sh.z); sh.w = fmaf(cs.w, -kb, sh.w);
+          }
+          v[4 * q] = ex2_approx(fmaf(v[4 * q], ka, -sh.x));
+          v[4 * q + 1] = ex2_approx(fmaf(v[4 * q + 1], ka, -sh.y));
+          v[4 * q + 2] = ex2_approx(fmaf(v[4 * q + 2], ka, -sh.z));
+          v[4 * q + 3] = ex2_approx(fmaf(v[4 * q + 3], ka, -sh.w));
         }
         chunk_stage_bf16(pt, row, 32 * j, v);
         chunk_from_tmem(acc + 64 + 32 * j, v);                              // v of head 2g + j
+        if (p.ln_stats) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 cs = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + g * 128 + 64 + 32 * j) + q);
+            v[4 * q] = fmaf(v[4 * q], va, cs.x * vb);
+            v[4 * q + 1] = fmaf(v[4 * q + 1], va, cs.y * vb);
+            v[4 * q + 2] = fmaf(v[4 * q + 2], va, cs.z * vb);
+            v[4 * q + 3] = fmaf(v[4 * q + 3], va, cs.w * vb);
+          }
+        }
         chunk_stage_bf16(vt, row, 32 * j, v);
       }
       tc_fence_before();
@@ -301,7 +326,8 @@ static int kv_encode_2d(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_
 }
 
 extern "C" int dac_linattn_kv_create(const void* xn, const void* wkv, const float* kv_shift, float* ctx_acc,
-                                     int32_t ctx_slots, int32_t B, int32_t hw, int32_t C, dac_kv_t* plan) {
+                                     int32_t ctx_slots, const float* ln_stats, const float* ln_colsum, int32_t B,
+                                     int32_t hw, int32_t C, dac_kv_t* plan) {
   if (!xn || !wkv || !kv_shift || !ctx_acc || !plan) return set_error(-1, "dac_linattn_kv_create: null argument");
   *plan = nullptr;
   if (C != 64 && C != 128) return set_error(-2, "dac_linattn_kv_create: C must be 64 or 128 (got %d)", C);
@@ -320,6 +346,13 @@ extern "C" int dac_linattn_kv_create(const void* xn, const void* wkv, const floa
   k.tiles_per_image = hw / kTileM;
   k.shift = kv_shift;
   k.ctx_acc = ctx_acc;
+  k.ln_stats = ln_stats;
+  k.ln_colsum = ln_colsum;
+  if ((ln_stats != nullptr) != (ln_colsum != nullptr) ||
+      ((reinterpret_cast<uintptr_t>(ln_stats) | reinterpret_cast<uintptr_t>(ln_colsum)) & 15)) {
+    delete pl;
+    return set_error(-2, "dac_linattn_kv_create: ln_stats and ln_colsum come together, 16-byte aligned");
+  }
   k.nbuf = C == 64 ? 2 : 1;
   const int fixed = (C / 64) * 2 * (int)kKvSlab + (int)kKvSlab + k.nbuf * 4 * (int)kKvSlab + 1024 + 512;
   int stages = (227 * 1024 - fixed) / (int)kKvSlab;

@@ -31,6 +31,8 @@ struct QoutParams {
   const float* bias;
   const float* ln_g;
   float ln_eps;
+  const float* ln_stats;   // folded PreNorm: per-pixel {mean, rstd} of the RAW input row (NULL: the input is normalised)
+  const float* ln_colsum;  // [128] sum_c W'_q[n][c] of the bf16 weight rows
 };
 
 template <int C>
@@ -221,19 +223,36 @@ linattn_qout_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
         asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");
       }
       // ---- epilogue 1: q = softmax over the 32 channels of each head, * 32^-0.5 -> bf16 A operand of GEMM 2
+      // folded PreNorm: q_raw = rstd * (W'_q x - mean * colsum); rstd > 0, so it only scales the softmax exponent
+      float qa = 1.4426950408889634f, qmean = 0.f;
+      if (p.ln_stats) {
+        const float2 ms = __ldg(reinterpret_cast<const float2*>(p.ln_stats) + static_cast<long long>(tile) * kTileM + row);
+        qmean = ms.x;
+        qa = ms.y * 1.4426950408889634f;
+      }
       mbar_wait(&acc1_full[group], ph);
       tc_fence_after();
 #pragma unroll
       for (int c = 0; c < 128; c += 32) {
         chunk_from_tmem(acc1 + c, v);
+        if (p.ln_stats) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 cs = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + c) + q);
+            v[4 * q] = fmaf(-qmean, cs.x, v[4 * q]);
+            v[4 * q + 1] = fmaf(-qmean, cs.y, v[4 * q + 1]);
+            v[4 * q + 2] = fmaf(-qmean, cs.z, v[4 * q + 2]);
+            v[4 * q + 3] = fmaf(-qmean, cs.w, v[4 * q + 3]);
+          }
+        }
         float m = v[0];
 #pragma unroll
         for (int j = 1; j < 32; ++j) m = fmaxf(m, v[j]);
-        const float ml = m * 1.4426950408889634f;
+        const float ml = m * qa;
         float s = 0.f;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          v[j] = ex2_approx(fmaf(v[j], 1.4426950408889634f, -ml));
+          v[j] = ex2_approx(fmaf(v[j], qa, -ml));
           s += v[j];
         }
         const float inv = __fdividef(0.17677669529663687f, s);
@@ -377,7 +396,8 @@ static int encode_2d(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t r
 
 extern "C" int dac_linattn_qout_create(const void* xn, const void* wq, const void* weff, int32_t c_pad,
                                        const void* res, void* out, const float* bias, const float* ln_g,
-                                       float ln_eps, int32_t B, int32_t hw, int32_t C, dac_qout_t* plan) {
+                                       float ln_eps, const float* ln_stats, const float* ln_colsum, int32_t B,
+                                       int32_t hw, int32_t C, dac_qout_t* plan) {
   if (!xn || !wq || !weff || !res || !out || !ln_g || !plan) return set_error(-1, "dac_linattn_qout_create: null argument");
   *plan = nullptr;
   if (C != 64 && C != 128) return set_error(-2, "dac_linattn_qout_create: C must be 64 or 128 (got %d)", C);
@@ -401,6 +421,12 @@ extern "C" int dac_linattn_qout_create(const void* xn, const void* wq, const voi
   k.tiles_per_image = hw / kTileM;
   k.c_pad = c_pad;
   k.bias = bias; k.ln_g = ln_g; k.ln_eps = ln_eps;
+  k.ln_stats = ln_stats; k.ln_colsum = ln_colsum;
+  if ((ln_stats != nullptr) != (ln_colsum != nullptr) ||
+      ((reinterpret_cast<uintptr_t>(ln_stats) | reinterpret_cast<uintptr_t>(ln_colsum)) & 15)) {
+    delete pl;
+    return set_error(-2, "dac_linattn_qout_create: ln_stats and ln_colsum come together, 16-byte aligned");
+  }
   const int fixed = (C / 64) * (int)kSlab + 4 * (int)kSlab + (C == 64 ? 2 * (int)kSlab : 0) + 1024 + 512;
   int stages = (227 * 1024 - fixed) / (int)kSlab;
   if (stages > kMaxStages) stages = kMaxStages;

@@ -272,14 +272,15 @@ def pack_kv_grouped(wkv):
 class KvPlan:
     """LinearAttention key/value side on tcgen05: k|v GEMM, exp, context GEMM accumulated in tensor memory."""
 
-    def __init__(self, xn, wkv_grouped, kv_shift, ctx_acc, B, hw, Cn):
-        L.require_cuda(xn, wkv_grouped, kv_shift, ctx_acc)
+    def __init__(self, xn, wkv_grouped, kv_shift, ctx_acc, B, hw, Cn, ln_stats=None, ln_colsum=None):
+        L.require_cuda(xn, wkv_grouped, kv_shift, ctx_acc, ln_stats, ln_colsum)
         lib = L.load()
         h = C.c_void_p()
         L.check(lib.dac_linattn_kv_create(xn.data_ptr(), wkv_grouped.data_ptr(), kv_shift.data_ptr(),
-                                          ctx_acc.data_ptr(), ctx_acc.shape[-2], B, hw, Cn, C.byref(h)))
+                                          ctx_acc.data_ptr(), ctx_acc.shape[-2], L.ptr(ln_stats), L.ptr(ln_colsum),
+                                          B, hw, Cn, C.byref(h)))
         self.handle, self._lib = h, lib
-        self._keep = (xn, wkv_grouped, kv_shift, ctx_acc)
+        self._keep = (xn, wkv_grouped, kv_shift, ctx_acc, ln_stats, ln_colsum)
         self.flops = 2.0 * B * hw * Cn * 256
 
     def run(self):
@@ -296,15 +297,16 @@ class KvPlan:
 class QoutPlan:
     """LinearAttention query side (to_q softmax -> W_eff q -> LayerNorm -> + x) as one chained-GEMM launch."""
 
-    def __init__(self, xn, wq, weff, res, out, bias, ln_g, ln_eps, B, hw, Cn):
-        L.require_cuda(xn, wq, weff, res, out, ln_g)
+    def __init__(self, xn, wq, weff, res, out, bias, ln_g, ln_eps, B, hw, Cn, ln_stats=None, ln_colsum=None):
+        L.require_cuda(xn, wq, weff, res, out, ln_g, ln_stats, ln_colsum)
         lib = L.load()
         h = C.c_void_p()
         L.check(lib.dac_linattn_qout_create(xn.data_ptr(), wq.data_ptr(), weff.data_ptr(), weff.shape[-2],
                                             res.data_ptr(), out.data_ptr(), bias.data_ptr() if bias is not None else None,
-                                            ln_g.data_ptr(), ln_eps, B, hw, Cn, C.byref(h)))
+                                            ln_g.data_ptr(), ln_eps, L.ptr(ln_stats), L.ptr(ln_colsum), B, hw, Cn,
+                                            C.byref(h)))
         self.handle, self._lib = h, lib
-        self._keep = (xn, wq, weff, res, out, bias, ln_g)
+        self._keep = (xn, wq, weff, res, out, bias, ln_g, ln_stats, ln_colsum)
         self.flops = 2.0 * B * hw * 128 * Cn * 2
 
     def run(self):

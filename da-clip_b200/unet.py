@@ -9,6 +9,7 @@ given (batch, H, W) - every buffer preallocated, every TMA descriptor baked - ca
 and replays it.  No CPU fallback.
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -312,8 +313,11 @@ class PackedUNet:
             a.update(q=ops.pack_linear(wq[:128].contiguous()), kv=ops.pack_linear(wq[128:].contiguous()),
                      kv_grouped=ops.pack_kv_grouped(wq[128:]),
                      kv_shift=(kbound * 1.4426950408889634).contiguous(), kv_safe=bool(kbound.max().item() <= 40.0))
+            colsum = wq.to(torch.bfloat16).float().sum(dim=1)                               # of the bf16 operand
+            a.update(q_colsum=colsum[:128].contiguous(), kv_colsum=colsum[128:].contiguous(),
+                     kv_grouped_colsum=ops.pack_kv_grouped(wq[128:]).float().sum(dim=1).contiguous())
             a.update(qkv=ops.pack_linear(wq),
-                     qkv_colsum=wq.to(torch.bfloat16).float().sum(dim=1).contiguous(),      # of the bf16 operand
+                     qkv_colsum=colsum.contiguous(),
                      out=ops.pack_linear(f32(q + "to_out.0.weight")),
                      w_out=f32(q + "to_out.0.weight").reshape(dim, 128).contiguous(),
                      b_out=f32(q + "to_out.0.bias"), g_out=f32(q + "to_out.1.g").reshape(-1).contiguous())
@@ -411,19 +415,28 @@ class UNetEngine:
         self.conv(prefix + "block2", h1, cout, rb["w2"], out, h, w, act=L.ACT_SILU, res=r, stats_out=stats)
         return out
 
-    # Folding PreNorm around to_qkv (producer writes {mean, rstd}, QKV epilogue finishes the normalisation) removes
-    # the LayerNorm launch and the normalised tensor, but measured SLOWER on B200 at batch 16 (to_qkv 245 -> 306 us,
-    # producer +14 us vs the 54 us LayerNorm kernel saved): the QKV epilogue is already the bottleneck of that
-    # store-bound layer.  Kept as a tested option (tests/test_kernels_gpu.py::test_prenorm_folded_into_qkv).
+    # Folded PreNorm: the ResBlock before a LinearAttention writes per-pixel {mean, rstd} of its output and the k|v and q
+    # GEMMs run on the raw tensor, finishing the normalisation in their epilogues (rstd * (acc - mean * colsum)): no
+    # LayerNorm launch, no normalised tensor.  Measured per instance at batch 16 (layer dumps, same box): the k|v and
+    # q-out kernels are bound by their epilogues, so the two extra FMAs and the column-sum loads per element cost them
+    # 20-25 %.  At 256^2 with 64 channels that is more than the 51 us LayerNorm pass it removes (+16 producer, +25 k|v,
+    # +25 q-out); at the smaller levels it wins (128^2: -13 us, 64^2: -8 / -17 us per instance).  So: folded wherever an
+    # image has at most FOLD_PRENORM_MAX_HW pixels at that level; FOLD_PRENORM=True forces it everywhere (tested both ways).
     FOLD_PRENORM = False
+    FOLD_PRENORM_MAX_HW = 128 * 128
     PDL = True             # programmatic dependent launch between consecutive kernel nodes of the step graph
     FUSE_KV_TC = True      # LinearAttention: the k|v context reduction as a second tcgen05 GEMM (TMEM-resident context)
     FUSE_QOUT = True       # LinearAttention: to_q + softmax + to_out + LayerNorm + residual as one chained-GEMM kernel
     FUSE_KVCTX = True      # LinearAttention: reduce k | v into the context inside the to_kv GEMM epilogue
 
-    def needs_stats(self, prefix):
+    # A/B switches from the environment, e.g. DAC_SWITCHES="FOLD_PRENORM=1,PDL=0" (tools/ab_engine.py, bench.py runs)
+    for _kv in filter(None, os.environ.get("DAC_SWITCHES", "").split(",")):
+        _k, _v = _kv.split("=")
+        locals()[_k] = bool(int(_v))
+
+    def needs_stats(self, prefix, hw):
         """True if the attention layer `prefix` consumes per-pixel LayerNorm statistics from its producer."""
-        return self.FOLD_PRENORM and not self.pk.attn[prefix]["transformer"]
+        return (self.FOLD_PRENORM or hw <= self.FOLD_PRENORM_MAX_HW) and not self.pk.attn[prefix]["transformer"]
 
     def attn_layer(self, prefix, x, C, h, w, stats=None):
         a = self.pk.attn[prefix]
@@ -434,10 +447,16 @@ class UNetEngine:
             # epilogue with the {mean, rstd} the producing ResBlock wrote; no normalised tensor, no LayerNorm launch
             q = self.buf(B, h, w, 128)                  # softmaxed queries, NHWC (A operand of the to_out GEMM)
             c_pad = a["out"].w.shape[-2]
-            if self.FUSE_KVCTX and stats is None and a["kv_safe"]:
+            if self.FUSE_KVCTX and a["kv_safe"]:
                 # k | v never reach memory: the KVCTX epilogue reduces them into {C, S} per (image, head)
-                xn = self.buf(B, h, w, C)
-                self.add(prefix + "prenorm", lambda: ops.layernorm_rows(x, xn, B * hw, C, None, None, 1e-5))
+                if stats is None:
+                    xn = self.buf(B, h, w, C)
+                    self.add(prefix + "prenorm", lambda: ops.layernorm_rows(x, xn, B * hw, C, None, None, 1e-5))
+                else:
+                    # folded PreNorm: the k|v and q GEMMs run on the raw tensor and finish the normalisation in their
+                    # epilogues from the {mean, rstd} the producing ResBlock wrote - no LayerNorm pass, no normalised tensor
+                    xn = x
+                fold = stats is not None
                 kv_tc = self.FUSE_KV_TC and C == 64 and hw % 128 == 0
                 # partial {C, S} records, one per CTA (and epilogue group) that touches the image, merged in slot order by
                 # the fold kernel: no atomics, so an evaluation is bit-reproducible
@@ -447,24 +466,28 @@ class UNetEngine:
                     # ... and reduced on tcgen05 too: P^T V with MN-major operands, context accumulated in TMEM
                     # (measured: 128 -> 111 us at level 0; the C = 128 instances have room for one P|V buffer only
                     # and run 25 % slower than the KVCTX epilogue, so they keep it)
-                    plan = ops.KvPlan(xn, a["kv_grouped"], a["kv_shift"], ctx, B, hw, C)
+                    plan = ops.KvPlan(xn, a["kv_grouped"], a["kv_shift"], ctx, B, hw, C, ln_stats=stats,
+                                      ln_colsum=a["kv_grouped_colsum"] if fold else None)
                     self.flops += plan.flops
                     self.conv_names.add(prefix + "to_kv")
                     self.add(prefix + "to_kv", plan.run)
                 else:
                     self.conv(prefix + "to_kv", xn, C, a["kv"], None, h, w, epi=L.EPI_KVCTX, block_n=256,
-                              kv_shift=a["kv_shift"], ctx_acc=ctx)
+                              kv_shift=a["kv_shift"], ctx_acc=ctx, ln_stats=stats,
+                              ln_colsum=a["kv_colsum"] if fold else None)
                 weff = self.buf(B, c_pad, 128)
                 self.flops += 2.0 * B * 4 * 32 * 32 * hw
                 if self.FUSE_QOUT and C in (64, 128) and hw % 128 == 0:
                     # q never reaches memory either: to_q -> softmax -> W_eff q -> LayerNorm -> + x in one kernel
                     self.add(prefix + "fold", lambda: ops.linattn_fold(ctx, B, hw, nslots, a["w_out"], C, c_pad, weff))
-                    plan = ops.QoutPlan(xn, a["q"].w, weff, x, out, a["b_out"], a["g_out"], 1e-5, B, hw, C)
+                    plan = ops.QoutPlan(xn, a["q"].w, weff, x, out, a["b_out"], a["g_out"], 1e-5, B, hw, C, ln_stats=stats,
+                                        ln_colsum=a["q_colsum"] if fold else None)
                     self.flops += plan.flops
                     self.conv_names.add(prefix + "to_q_out")
                     self.add(prefix + "to_q_out", plan.run)
                     return out
-                self.conv(prefix + "to_q", xn, C, a["q"], q, h, w, epi=L.EPI_QKV, block_n=128)
+                self.conv(prefix + "to_q", xn, C, a["q"], q, h, w, epi=L.EPI_QKV, block_n=128, ln_stats=stats,
+                          ln_colsum=a["q_colsum"] if fold else None)
                 self.add(prefix + "fold", lambda: ops.linattn_fold(ctx, B, hw, nslots, a["w_out"], C, c_pad, weff))
                 self.conv(prefix + "to_out", q, 128, a["out"], out, h, w, epi=L.EPI_LN, bias=a["b_out"],
                           ln_g=a["g_out"], res=x, per_image_w=True, weight_override=weff)
@@ -544,7 +567,7 @@ class UNetEngine:
             x = self.resblock(p + "0.", x, din, h, w)
             self.taps[p + "0"] = x
             skips.append((x, din))
-            st = self.buf(B * h * w, 2, dtype=torch.float32) if self.needs_stats(p + "2.") else None
+            st = self.buf(B * h * w, 2, dtype=torch.float32) if self.needs_stats(p + "2.", h * w) else None
             x = self.resblock(p + "1.", x, din, h, w, stats=st)
             self.taps[p + "1"] = x
             x = self.attn_layer(p + "2.", x, din, h, w, stats=st)
@@ -561,7 +584,7 @@ class UNetEngine:
             x = y
             self.taps[p + "3"] = x
         md = cfg.mid_dim
-        st = self.buf(B * h * w, 2, dtype=torch.float32) if self.needs_stats("mid_attn.") else None
+        st = self.buf(B * h * w, 2, dtype=torch.float32) if self.needs_stats("mid_attn.", h * w) else None
         x = self.resblock("mid_block1.", x, md, h, w, stats=st)
         self.taps["mid_block1"] = x
         x = self.attn_layer("mid_attn.", x, md, h, w, stats=st)
@@ -576,7 +599,7 @@ class UNetEngine:
             x = self.resblock(p + "0.", x, dout, h, w, skip=sk, sc=sc)
             self.taps[p + "0"] = x
             sk, sc = skips.pop()
-            st = self.buf(B * h * w, 2, dtype=torch.float32) if self.needs_stats(p + "2.") else None
+            st = self.buf(B * h * w, 2, dtype=torch.float32) if self.needs_stats(p + "2.", h * w) else None
             x = self.resblock(p + "1.", x, dout, h, w, skip=sk, sc=sc, stats=st)
             self.taps[p + "1"] = x
             x = self.attn_layer(p + "2.", x, dout, h, w, stats=st)

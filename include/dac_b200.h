@@ -130,7 +130,7 @@ typedef struct dac_conv_desc {
    * with gain-folded weights W' = W diag(g) and finishes rstd * (acc - mean * colsum(W')) in its epilogue, so the
    * normalised tensor is never materialised. */
   float* stats_out; float stats_eps;              /* [B*OH*OW][2] fp32 */
-  const float* ln_stats; const float* ln_colsum;  /* QKV: [B*OH*OW][2], [cout] */
+  const float* ln_stats; const float* ln_colsum;  /* QKV, KVCTX: [B*OH*OW][2], [cout]: folded PreNorm of the input rows */
   float* out_nchw; int32_t out_nchw_c, out_nchw_h, out_nchw_w; /* alt. fp32 NCHW output (final_conv), cropped */
   const float* kv_shift; float* ctx_acc;          /* KVCTX: [128] shift * log2(e); [B][4][ctx_slots][1088] fp32 (zeroed by launch) */
   int32_t halo;                                   /* 3x3 stride-1, tile_w 8: ONE (tile_h+2) x (tile_w+2) load per K chunk
@@ -205,10 +205,14 @@ int32_t dac_linattn_ctx_slots(int32_t B, int32_t tiles_per_image, int32_t groups
  * accumulated in tensor memory over the CTA's tiles of an image and stored as one partial record per (CTA, image) into
  * ctx_acc [B][4][ctx_slots][1088] fp32 (zeroed by the launch; ctx_slots >= dac_linattn_ctx_slots(B, hw / 128, 1);
  * merged in slot order by dac_linattn_fold with nchunks = ctx_slots).  xn: bf16 [B*hw, C] (C = 64 or 128, hw % 128 == 0);
- * wkv: bf16 [256][C], rows packed per head pair g as k_2g k_2g+1 v_2g v_2g+1.  Replaces DAC_EPI_KVCTX where it fits. */
+ * wkv: bf16 [256][C], rows packed per head pair g as k_2g k_2g+1 v_2g v_2g+1.  Replaces DAC_EPI_KVCTX where it fits.
+ * Folded PreNorm (MU:89-97): with ln_stats ([B*hw][2] fp32 {mean, rstd} per pixel, written by the producing layer's
+ * stats_out) and ln_colsum ([256] fp32 row sums of the bf16 wkv rows, same packed order) `xn` is the RAW input and the
+ * epilogue finishes the normalisation: W' LN(x) = rstd (W' x - mean colsum(W')); both NULL: xn is already normalised. */
 typedef struct dac_kv_plan* dac_kv_t;
 int dac_linattn_kv_create(const void* xn, const void* wkv, const float* kv_shift, float* ctx_acc, int32_t ctx_slots,
-                          int32_t B, int32_t hw, int32_t C, dac_kv_t* plan);
+                          const float* ln_stats, const float* ln_colsum, int32_t B, int32_t hw, int32_t C,
+                          dac_kv_t* plan);
 int dac_linattn_kv_launch(dac_kv_t plan, dac_stream_t stream);
 void dac_linattn_kv_destroy(dac_kv_t plan);
 
@@ -216,11 +220,13 @@ void dac_linattn_kv_destroy(dac_kv_t plan);
  *   q = softmax_head-channels(wq . xn) * 32^-0.5   (kept in shared memory, bf16)
  *   out = LayerNorm_c(weff[b] . q + bias) * ln_g + res
  * xn, res, out: bf16 [B*hw, C] (C = 64 or 128, hw % 128 == 0); wq: bf16 [128][C] (gain-folded rows of to_qkv);
- * weff: bf16 [B][c_pad][128] from dac_linattn_fold.  Replaces the to_q (DAC_EPI_QKV) + to_out (DAC_EPI_LN) pair. */
+ * weff: bf16 [B][c_pad][128] from dac_linattn_fold.  Replaces the to_q (DAC_EPI_QKV) + to_out (DAC_EPI_LN) pair.
+ * ln_stats / ln_colsum ([B*hw][2], [128]; or both NULL): folded PreNorm as for dac_linattn_kv_create - xn is then the
+ * raw input (normally the same tensor as res). */
 typedef struct dac_qout_plan* dac_qout_t;
 int dac_linattn_qout_create(const void* xn, const void* wq, const void* weff, int32_t c_pad, const void* res,
-                            void* out, const float* bias, const float* ln_g, float ln_eps, int32_t B, int32_t hw,
-                            int32_t C, dac_qout_t* plan);
+                            void* out, const float* bias, const float* ln_g, float ln_eps, const float* ln_stats,
+                            const float* ln_colsum, int32_t B, int32_t hw, int32_t C, dac_qout_t* plan);
 int dac_linattn_qout_launch(dac_qout_t plan, dac_stream_t stream);
 void dac_linattn_qout_destroy(dac_qout_t plan);
 

@@ -434,6 +434,56 @@ def test_linear_attention_chained_q_out(ops, gen, B, H, W, C):
     assert_close_bf16(nchw(out), ref, f"chained linear attention {H}x{W} C={C}", rel=2 ** -5, abs_=2e-2)
 
 
+@pytest.mark.parametrize("B,H,W,C,kv_tc", [(3, 32, 32, 64, True), (2, 16, 40, 128, False), (5, 64, 48, 64, True),
+                                            (1, 8, 16, 128, False), (2, 16, 24, 64, False)])
+def test_linear_attention_folded_prenorm(ops, gen, B, H, W, C, kv_tc):
+    """PreNorm folded into the fused LinearAttention kernels: the k|v kernel (tcgen05 context or KVCTX epilogue) and the
+    chained q / to_out kernel take the RAW tensor plus the per-pixel {mean, rstd} its producer wrote and gain-folded
+    weights with their column sums; checked against PreNorm(LinearAttention) of the oracle on the same tensor."""
+    from daclip_b200 import lib as L
+    from oracle import unet_oracle as O
+    hw = H * W
+    x = rnd(gen, B, C, H, W) * 1.7 + 0.4
+    xh = nhwc(x)                                                 # bf16 NHWC: what the producing ResBlock stored
+    xf = nchw(xh)
+    g = 1 + 0.2 * rnd(gen, C)
+    sd = {"to_qkv.weight": rnd(gen, 384, C, 1, 1, scale=C ** -0.5),
+          "to_out.0.weight": rnd(gen, C, 128, 1, 1, scale=128 ** -0.5 * 8),
+          "to_out.0.bias": rnd(gen, C, scale=0.1), "to_out.1.g": (1 + 0.1 * rnd(gen, 1, C, 1, 1))}
+    wf = sd["to_qkv.weight"].reshape(384, C) * g[None, :]        # W' = W diag(g)
+    sdr = dict(sd)
+    sdr["to_qkv.weight"] = bf(wf).float().reshape(384, C, 1, 1)
+    xn = (xf - xf.mean(1, keepdim=True)) * torch.rsqrt(xf.var(1, unbiased=False, keepdim=True) + 1e-5)
+    ref = O.linear_attention(sdr, "", xn) + xf
+    # the producer's statistics (moments of the stored bf16 row, E[x^2] - mean^2)
+    rows = xh.float().reshape(B * hw, C)
+    mean = rows.mean(1)
+    stats = torch.stack([mean, torch.rsqrt((rows * rows).mean(1) - mean * mean + 1e-5)], 1).contiguous()
+    colsum = bf(wf).float().sum(1)
+    shift = 1.02 * bf(wf[128:256]).float().norm(dim=1) * math.sqrt(C)
+    ns = ops.ctx_slots(B, H, W, kv_tc)
+    ctx = torch.zeros(B, 4, ns, 32 * 34, device="cuda")
+    c_pad = ops.choose_block_n(C)[1]
+    weff = torch.zeros(B, c_pad, 128, device="cuda", dtype=torch.bfloat16)
+    out = torch.full((B, H, W, C), float("nan"), device="cuda", dtype=torch.bfloat16)
+    sh = (shift * 1.4426950408889634).contiguous()
+    if kv_tc:
+        grouped = ops.pack_kv_grouped(wf[128:])
+        pkv = ops.KvPlan(xh, grouped, sh, ctx, B, hw, C, ln_stats=stats, ln_colsum=grouped.float().sum(1).contiguous())
+    else:
+        pkv = ops.ConvPlan(xh, C, ops.pack_linear(wf[128:].contiguous()), None, B=B, H=H, W=W, epi=L.EPI_KVCTX,
+                           block_n=256, kv_shift=sh, ctx_acc=ctx, ln_stats=stats, ln_colsum=colsum[128:].contiguous())
+    pq = ops.QoutPlan(xh, ops.pack_linear(wf[:128].contiguous()).w, weff, xh, out, sd["to_out.0.bias"],
+                      sd["to_out.1.g"].reshape(-1).contiguous(), 1e-5, B, hw, C, ln_stats=stats,
+                      ln_colsum=colsum[:128].contiguous())
+    for _ in range(2):
+        pkv.run()
+        ops.linattn_fold(ctx, B, hw, ns, sd["to_out.0.weight"].reshape(C, 128).contiguous(), C, c_pad, weff)
+        pq.run()
+    torch.cuda.synchronize()
+    assert_close_bf16(nchw(out), ref, f"folded PreNorm linear attention {H}x{W} C={C}", rel=2 ** -5, abs_=2e-2)
+
+
 @pytest.mark.parametrize("B,H,W,C", [(2, 32, 32, 64), (1, 16, 48, 128), (1, 16, 16, 256)])
 def test_prenorm_folded_into_qkv(ops, gen, B, H, W, C):
     """PreNorm (channel LayerNorm, gain only) folded around to_qkv: the producer writes per-pixel {mean, rstd} of its

@@ -1,5 +1,6 @@
 """A/B timing of the UNet step graph under engine switches on ONE box (clocks differ between boxes):
-usage: ab_engine.py [B H W] -- times the captured evaluation with each setting of UNetEngine.PDL, interleaved."""
+usage: ab_engine.py [B H W] [SWITCH] -- times the captured evaluation with UNetEngine.SWITCH (default PDL) off and on,
+interleaved, and reports how far the outputs of the two settings are apart."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -7,6 +8,7 @@ from daclip_b200 import synthetic
 from daclip_b200.unet import ConditionalUNet, UNetEngine
 
 B, H, W = (int(a) for a in sys.argv[1:4]) if len(sys.argv) >= 4 else (16, 256, 256)
+SWITCH = sys.argv[4] if len(sys.argv) >= 5 else "PDL"
 sd, kw = synthetic.unet_state_dict(0)
 inp = {k: v.cuda() for k, v in synthetic.restoration_inputs(B, H, W, T=1, seed=3).items()}
 
@@ -37,7 +39,7 @@ def timeit(eng, n=40):
     return e0.elapsed_time(e1) / n
 
 
-variants = {"pdl_off": dict(PDL=False), "pdl_off2": dict(PDL=False), "pdl_on": dict(PDL=True)}
+variants = {"pdl_off": {SWITCH: False}, "pdl_off2": {SWITCH: False}, "pdl_on": {SWITCH: True}}
 engines = {k: build(**v) for k, v in variants.items()}
 ref = engines["pdl_off"][1].out_noise.clone()
 for k, (_, e) in engines.items():
