@@ -212,6 +212,21 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
   }
   if (d->epi == DAC_EPI_KVCTX) stg_bytes = kKvStageBytes;   // P / V head tiles of each epilogue group
   k.kv_shift = d->kv_shift; k.ctx_acc = d->ctx_acc;
+  if (d->epi == DAC_EPI_KVCTX) {
+    // softmax over the pixels of a channel is invariant to any per-channel constant: one scalar shift per head (the
+    // largest bound) keeps exp() in range just as well and costs the epilogue no loads
+    float sh[128];
+    cudaError_t ce = cudaMemcpy(sh, d->kv_shift, sizeof(sh), cudaMemcpyDeviceToHost);
+    if (ce != cudaSuccess) {
+      delete pl;
+      return set_error(-20, "dac_conv_create: reading kv_shift: %s", cudaGetErrorString(ce));
+    }
+    for (int h = 0; h < 4; ++h) {
+      float m = sh[h * 32];
+      for (int j = 1; j < 32; ++j) m = sh[h * 32 + j] > m ? sh[h * 32 + j] : m;
+      k.kv_shift_max[h] = m;
+    }
+  }
   k.ctx_slots = d->ctx_slots; k.ctx_tpi = k.tiles_x * k.tiles_y;
   // FiLM parameters in TMEM when three block_n-wide regions fit one accumulator stage (the 64-channel layers, which
   // are the shared-memory-bound ones); alignment of the float4 parameter loads needs cout % 4 == 0 (validated above)

@@ -104,7 +104,8 @@ struct ConvKParams {
   int stg_count;           // 1 or 2 staging tiles (2: the store of tile i overlaps the epilogue of tile i+1)
   int res_tma;             // the bf16 residual tile is TMA-loaded into the staging tile and updated in place
   int film_tmem;           // FiLM (scale + 1 | shift) of the current image lives in TMEM columns [bn, 3 bn) of the stage
-  const float* kv_shift;   // KVCTX: [128] upper bound of k per channel, times log2(e)
+  const float* kv_shift;   // KVCTX: [128] upper bound of k per channel, times log2(e) (host side: reduced to kv_shift_max)
+  float kv_shift_max[4];   // KVCTX: the largest bound of each head - one scalar shift per head is all the softmax needs
   float* ctx_acc;          // KVCTX: [B][4][ctx_slots][kCtxRecord] fp32 partial records
   int ctx_slots, ctx_tpi;  // slots per (image, head); tiles per image
 };
@@ -464,7 +465,7 @@ __device__ __forceinline__ void kvctx_tile(const ConvKParams& p, const TileCoord
     chunk_from_tmem(tmem_acc + h * 32, v);
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      float4 sh = __ldg(reinterpret_cast<const float4*>(p.kv_shift + h * 32) + q);
+      float4 sh = make_float4(p.kv_shift_max[h], p.kv_shift_max[h], p.kv_shift_max[h], p.kv_shift_max[h]);
       if (p.ln_stats) {
         const float4 cs = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + h * 32) + q);
         sh.x = fmaf(cs.x, -kb, sh.x); sh.y = fmaf(cs.y, -kb, sh.y); sh.z = fmaf(cs.z, -kb, sh.z); sh.w = fmaf(cs.w, -kb, sh.w);

@@ -232,33 +232,45 @@ linattn_qout_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
       }
       mbar_wait(&acc1_full[group], ph);
       tc_fence_after();
+      // two heads at a time: both TMEM loads issued before one wait so that the two softmax chains (max tree, exponentials,
+      // sum tree, scale, pack) interleave in the instruction stream - this epilogue is a latency chain, not a throughput
+      // problem (two warps per scheduler)
 #pragma unroll
-      for (int c = 0; c < 128; c += 32) {
-        chunk_from_tmem(acc1 + c, v);
-        if (p.ln_stats) {
+      for (int c = 0; c < 128; c += 64) {
+        uint32_t r[2][32];
+        tmem_ld32(acc1 + c, r[0]);
+        tmem_ld32(acc1 + c + 32, r[1]);
+        tmem_ld_wait();
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 cs = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + c) + q);
-            v[4 * q] = fmaf(-qmean, cs.x, v[4 * q]);
-            v[4 * q + 1] = fmaf(-qmean, cs.y, v[4 * q + 1]);
-            v[4 * q + 2] = fmaf(-qmean, cs.z, v[4 * q + 2]);
-            v[4 * q + 3] = fmaf(-qmean, cs.w, v[4 * q + 3]);
+        for (int hh = 0; hh < 2; ++hh) {
+          float w[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) w[j] = __uint_as_float(r[hh][j]);
+          if (p.ln_stats) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 cs = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + c + 32 * hh) + q);
+              w[4 * q] = fmaf(-qmean, cs.x, w[4 * q]);
+              w[4 * q + 1] = fmaf(-qmean, cs.y, w[4 * q + 1]);
+              w[4 * q + 2] = fmaf(-qmean, cs.z, w[4 * q + 2]);
+              w[4 * q + 3] = fmaf(-qmean, cs.w, w[4 * q + 3]);
+            }
           }
+          float m4[4] = {w[0], w[1], w[2], w[3]};
+#pragma unroll
+          for (int j = 4; j < 32; ++j) m4[j & 3] = fmaxf(m4[j & 3], w[j]);
+          const float ml = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * qa;
+          float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            w[j] = ex2_approx(fmaf(w[j], qa, -ml));
+            s4[j & 3] += w[j];
+          }
+          const float inv = __fdividef(0.17677669529663687f, (s4[0] + s4[1]) + (s4[2] + s4[3]));
+#pragma unroll
+          for (int j = 0; j < 32; ++j) w[j] *= inv;
+          chunk_stage_bf16(qt, row, c + 32 * hh, w);
         }
-        float m = v[0];
-#pragma unroll
-        for (int j = 1; j < 32; ++j) m = fmaxf(m, v[j]);
-        const float ml = m * qa;
-        float s = 0.f;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          v[j] = ex2_approx(fmaf(v[j], qa, -ml));
-          s += v[j];
-        }
-        const float inv = __fdividef(0.17677669529663687f, s);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] *= inv;
-        chunk_stage_bf16(qt, row, c, v);
       }
       tc_fence_before();
       fence_proxy_async();                                // generic-proxy smem writes -> visible to the tensor core

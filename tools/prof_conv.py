@@ -18,6 +18,7 @@ CASES = {
     "l0_kv": (16, 256, 256, 64, 256, "kv"),
     "l0_toout": (16, 256, 256, 128, 64, "toout"),
     "l0_qout": (16, 256, 256, 64, 64, "qout"),
+    "l0_kvtc": (16, 256, 256, 64, 256, "kvtc"),
     "l1_qout": (16, 128, 128, 128, 128, "qout"),
 }
 
@@ -46,6 +47,12 @@ def make(name):
         ctx = torch.zeros(B, 4, ops.ctx_slots(B, H, W, False), 32 * 34, device="cuda")
         plan = ops.ConvPlan(x, cin, ops.pack_linear(w), None, B=B, H=H, W=W, epi=L.EPI_KVCTX, block_n=256,
                             kv_shift=shift, ctx_acc=ctx)
+    elif kind == "kvtc":
+        w = torch.randn(cout, cin, device="cuda", generator=g) * cin ** -0.5
+        shift = torch.full((128,), 12.0, device="cuda")
+        ctx = torch.zeros(B, 4, ops.ctx_slots(B, H, W, True), 32 * 34, device="cuda")
+        plan = ops.KvPlan(x.reshape(B * H * W, cin), ops.pack_kv_grouped(w), shift, ctx, B, H * W, cin)
+        plan.info = lambda: {}
     elif kind == "toout":
         w = torch.randn(cout, cin, device="cuda", generator=g) * cin ** -0.5
         weff = (torch.randn(B, cout, cin, device="cuda", generator=g) * cin ** -0.5).to(torch.bfloat16)
