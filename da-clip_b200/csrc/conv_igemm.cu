@@ -126,6 +126,13 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
           reinterpret_cast<uintptr_t>(d->rweight)) & 15))
       return set_error(-2, "dac_conv_create: fused skip conv needs PLAIN epilogue, one N tile <= 128, stride 1");
   }
+  if (d->pair) {
+    if (!d->halo || d->block_n != 128 || d->cout != 128 || d->cout_pad != 128 || d->epi != DAC_EPI_PLAIN || nchw ||
+        fused_res || d->stats_out || d->per_image_w || d->c0 % 128 || d->c1 % 128 || d->out_scale > 1 || d->out_f32 ||
+        d->res_f32 || d->bias_img)
+      return set_error(-2, "dac_conv_create: pixel-pair mode needs a haloed 3x3 conv, PLAIN epilogue, wide views with "
+                           "block_n = cout = 128 and channel counts that are multiples of 128");
+  }
   ConvKernelFn kernel = pick_conv_kernel(d->epi, d->act, d->film != nullptr, nchw);
   if (!kernel) return set_error(-2, "dac_conv_create: unsupported activation / FiLM combination (%d, %d)", d->act,
                                 d->film != nullptr);
@@ -192,9 +199,19 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
   const int chunks = k.chunks0 + k.chunks1;
   const long long res_bytes = (long long)k.n_tiles * d->ntaps * chunks * k.b_bytes;
   const long long kv_extra = d->epi == DAC_EPI_KVCTX ? 2ll * kKvStageBytes : 0;   // P / V head tiles, both groups
-  const bool resident = d->ngroups == 1 && !d->per_image_w && res_bytes <= 160 * 1024 &&
-                        (smem_budget - res_bytes - kv_extra) / (long long)k.a_slot >= 3;
+  bool resident = d->ngroups == 1 && !d->per_image_w && res_bytes <= 160 * 1024 &&
+                  (smem_budget - res_bytes - kv_extra) / (long long)k.a_slot >= 3;
   k.b_res_bytes = resident ? (uint32_t)res_bytes : 0u;
+  k.pair = d->pair ? 1 : 0;
+  if (d->pair) {   // one 192-row block per (64-channel source slice, ky), always resident
+    k.b_res_bytes = (uint32_t)(chunks / 2) * 3u * kPairBlock;
+    k.film_cols = 64;
+    resident = true;
+    if ((smem_budget - (long long)k.b_res_bytes) / (long long)k.a_slot < 2) {
+      delete pl;
+      return set_error(-2, "dac_conv_create: pixel-pair weights (%u B) leave no room for two pipeline stages", k.b_res_bytes);
+    }
+  }
   uint32_t stage_bytes = k.a_slot + (resident ? 0u : (uint32_t)d->ndy * k.b_bytes);
   if (fused_res && stage_bytes < k.r_a_bytes + k.b_bytes) stage_bytes = k.r_a_bytes + k.b_bytes;
   // bf16 NHWC output through a swizzled staging tile + TMA store (coalesced, clipped by the tensor map) whenever the
@@ -230,8 +247,9 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
   k.ctx_slots = d->ctx_slots; k.ctx_tpi = k.tiles_x * k.tiles_y;
   // FiLM parameters in TMEM when three block_n-wide regions fit one accumulator stage (the 64-channel layers, which
   // are the shared-memory-bound ones); alignment of the float4 parameter loads needs cout % 4 == 0 (validated above)
-  k.film_tmem = (d->film && !fused_res && d->block_n % 32 == 0 && 3 * d->block_n <= (int)kAccStride &&
-                 !getenv("DAC_NO_FILM_TMEM")) ? 1 : 0;
+  k.film_tmem = (d->film && !fused_res && d->block_n % 32 == 0 &&
+                 d->block_n + 2 * (k.film_cols ? k.film_cols : d->block_n) <= (int)kAccStride &&
+                 (k.pair || !getenv("DAC_NO_FILM_TMEM"))) ? 1 : 0;
   k.stg_bytes = stg_bytes;
   k.stg_count = stg_bytes ? 2 : 1;   // one staging tile per epilogue group
   int stages = (smem_budget - (int)k.b_res_bytes - (int)stg_bytes * k.stg_count) / (int)stage_bytes;
@@ -250,11 +268,12 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
   }
   if (rc == 0) {
     PFN_encodeTiled enc = get_encode_fn();
-    const int ctot = d->c0 + d->c1;
-    const long long Z = (long long)d->ngroups * d->ntaps * (d->per_image_w ? d->B : 1);
-    cuuint64_t dims[3] = {(cuuint64_t)ctot, (cuuint64_t)d->cout_pad, (cuuint64_t)Z};
-    cuuint64_t strides[2] = {(cuuint64_t)ctot * 2, (cuuint64_t)d->cout_pad * ctot * 2};
-    cuuint32_t box[3] = {(cuuint32_t)kChunkK, (cuuint32_t)d->block_n, 1};
+    const int ctot = d->pair ? (d->c0 + d->c1) / 2 : d->c0 + d->c1;
+    const long long Z = d->pair ? 3 : (long long)d->ngroups * d->ntaps * (d->per_image_w ? d->B : 1);
+    const int wrows = d->pair ? 192 : d->cout_pad;
+    cuuint64_t dims[3] = {(cuuint64_t)ctot, (cuuint64_t)wrows, (cuuint64_t)Z};
+    cuuint64_t strides[2] = {(cuuint64_t)ctot * 2, (cuuint64_t)wrows * ctot * 2};
+    cuuint32_t box[3] = {(cuuint32_t)kChunkK, (cuuint32_t)(d->pair ? 192 : d->block_n), 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(&pl->mapW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(d->weight), dims, strides,
                      box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,

@@ -30,6 +30,7 @@ constexpr int kKvPitch = 40;                                   // bf16 per row o
 constexpr uint32_t kKvTileBytes = kTileM * kKvPitch * 2;         // 10 KB
 constexpr uint32_t kKvStageBytes = 4 * kKvTileBytes;             // P and V head tiles, double-buffered: per group
 constexpr int kCtxRecord = 32 * 32 + 64;                        // {C[32][32], m[32], S[32]} per (image, head)
+constexpr uint32_t kPairBlock = 192 * 128;                       // pixel-pair mode: three 64-row weight tiles of one (slice, ky)
 
 // Division by a launch-time constant without the ~60-cycle IDIV sequence (Granlund-Montgomery round-up method):
 // t = umulhi(mul, n); q = (t + ((n - t) >> s1)) >> s2.  Exact for 0 <= n < 2^31.
@@ -104,6 +105,8 @@ struct ConvKParams {
   int stg_count;           // 1 or 2 staging tiles (2: the store of tile i overlaps the epilogue of tile i+1)
   int res_tma;             // the bf16 residual tile is TMA-loaded into the staging tile and updated in place
   int film_tmem;           // FiLM (scale + 1 | shift) of the current image lives in TMEM columns [bn, 3 bn) of the stage
+  int pair;                // pixel-pair mode (see the issuer): the tensors are [B, H, W/2, 2C] views, block_n = 2 cout
+  int film_cols;           // pair: the FiLM vectors have block_n / 2 entries and serve both pixels of a pair
   const float* kv_shift;   // KVCTX: [128] upper bound of k per channel, times log2(e) (host side: reduced to kv_shift_max)
   float kv_shift_max[4];   // KVCTX: the largest bound of each head - one scalar shift per head is all the softmax needs
   float* ctx_acc;          // KVCTX: [B][4][ctx_slots][kCtxRecord] fp32 partial records
@@ -341,10 +344,12 @@ __device__ __forceinline__ void epilogue_tile(const ConvKParams& p, const TileCo
       // (scale + 1, shift) of this image replicated in every TMEM lane: two 32-column loads, no shared-memory traffic
       // (a broadcast LDS.128 is four wavefronts on the pipe that bounds these layers)
       float f[32];
-      chunk_from_tmem(tmem_acc + p.block_n + c, f);
+      const int fcols = p.film_cols ? p.film_cols : p.block_n;   // pair mode: both pixels of the pair share the vectors
+      const int fc = p.film_cols ? (c & (p.film_cols - 1)) : c;
+      chunk_from_tmem(tmem_acc + p.block_n + fc, f);
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] *= f[j];
-      chunk_from_tmem(tmem_acc + 2 * p.block_n + c, f);
+      chunk_from_tmem(tmem_acc + p.block_n + fcols + fc, f);
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] += f[j];
     } else if (FILM) {
@@ -606,6 +611,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         // IT (N tile, chunk, column group, tap within the group), so the issuer walks it with one add per tap;
         // ngroups == 1 here
         mbar_arrive_expect_tx(b_full, p.b_res_bytes);
+        if (p.pair) {
+          // per (64-channel source slice, ky): ONE 192-row block [W(kx=2); W(kx=1); W(kx=0)] - the even and the odd
+          // chunk of the slice read overlapping 128-row windows of it (see the issuer)
+          for (int s_ = 0; s_ < (chunks >> 1); ++s_)
+            for (int ky = 0; ky < 3; ++ky)
+              tma_load_3d(b_res + static_cast<size_t>(s_ * 3 + ky) * kPairBlock, &mapW, b_full, s_ * kChunkK, 0, ky);
+        } else
         for (int nt = 0; nt < p.n_tiles; ++nt)
           for (int ck = 0; ck < chunks; ++ck)
             for (int jt = 0; jt < p.ntaps; ++jt)
@@ -680,6 +692,59 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         uint32_t accumulate = 0;
         const int nt = tile - fast_div(tile, p.fd_ntiles) * p.n_tiles;
         uint32_t b_run = bres_lo + nt * (chunks * p.ntaps) * b_lo;   // resident weights of this N tile, front to back
+        if (p.pair) {
+          // ---- pixel-pair mode.  A row of the tile is a PAIR of horizontally adjacent pixels: the activation tensors
+          // are viewed as [B, H, W/2, 2C] (64-channel chunk 2s = the even pixels of source slice s, chunk 2s + 1 = the
+          // odd ones) and the accumulator row holds both outputs, columns [0, cout) = pixel 2i, [cout, 2 cout) = 2i + 1.
+          // An M128 x N64 MMA is bound by its 6 KB shared-memory operand fetch (48 cycles for 32 of math); here the
+          // centre views feed N = 128 MMAs (8 KB in 64 cycles: balanced) against two overlapping windows of ONE
+          // 192-row weight block [W(kx=2); W(kx=1); W(kx=0)]:
+          //   even chunk, pair i     : rows [64, 192) = W(1) | W(0)  ->  x[2i] is the centre of pixel 2i, the left of 2i+1
+          //   odd  chunk, pair i     : rows [0, 128)  = W(2) | W(1)  ->  x[2i+1] is the right of 2i, the centre of 2i+1
+          //   odd  chunk, pair i - 1 : rows [128, 192) = W(0), N = 64 into columns [0, cout)      (left of pixel 2i)
+          //   even chunk, pair i + 1 : rows [0, 64)    = W(2), N = 64 into columns [cout, 2 cout)  (right of pixel 2i+1)
+          // = 224 instead of 288 fetch-bound cycles per 256 output pixels and K step.
+          const uint32_t idesc_half = make_idesc_bf16(kTileM, p.block_n >> 1);
+          const uint32_t half_cols = p.block_n >> 1;
+          const uint32_t blk_lo = kPairBlock >> 4, rows64_lo = (64u * 128u) >> 4;
+          for (int ck = 0; ck < chunks; ++ck) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            const uint32_t a0 = ring_lo + stage * stage_lo;
+            const uint32_t odd = ck & 1;
+            const uint32_t wsrc = bres_lo + (ck >> 1) * 3 * blk_lo;
+            for (int ky = 0; ky < 3; ++ky) {
+              const uint32_t wb = wsrc + ky * blk_lo;
+              // centre view (pair i): tap (ky, 1); side view: tap (ky, 0) for the odd chunk, (ky, 2) for the even one
+              const uint32_t a_c = a0 + p.tap_off[ky * 3 + 1];
+              const uint32_t a_s = a0 + p.tap_off[ky * 3 + (odd ? 0 : 2)];
+              uint64_t adesc_c = desc_fixed_a | a_c, adesc_s = desc_fixed_a | a_s;
+              if (p.halo == 2) {
+                adesc_c |= static_cast<uint64_t>((a_c >> 3) & 7) << 49;
+                adesc_s |= static_cast<uint64_t>((a_s >> 3) & 7) << 49;
+              }
+              const uint64_t bdesc_c = desc_fixed | (odd ? wb : wb + rows64_lo);
+              const uint64_t bdesc_s = desc_fixed | (odd ? wb + 2 * rows64_lo : wb);
+              const uint32_t d_s = d_tmem + (odd ? 0u : half_cols);
+              if (elect_one()) {
+                umma_bf16(d_tmem, adesc_c, bdesc_c, idesc, accumulate);
+                umma_bf16(d_tmem, adesc_c + 2, bdesc_c + 2, idesc, 1u);
+                umma_bf16(d_tmem, adesc_c + 4, bdesc_c + 4, idesc, 1u);
+                umma_bf16(d_tmem, adesc_c + 6, bdesc_c + 6, idesc, 1u);
+                umma_bf16(d_s, adesc_s, bdesc_s, idesc_half, 1u);
+                umma_bf16(d_s, adesc_s + 2, bdesc_s + 2, idesc_half, 1u);
+                umma_bf16(d_s, adesc_s + 4, bdesc_s + 4, idesc_half, 1u);
+                umma_bf16(d_s, adesc_s + 6, bdesc_s + 6, idesc_half, 1u);
+              }
+              accumulate = 1u;
+            }
+            if (elect_one()) umma_commit(&empty[stage]);
+            if (++stage == p.stages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        } else
         for (int ck = 0; ck < chunks; ++ck) {
           for (int j = 0; j < p.ncols; ++j) {
             mbar_wait(&full[stage], phase);
@@ -779,9 +844,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           film_key = key;
           const float* src = p.film + static_cast<long long>(t.n) * p.film_ld + p.film_off + t.nt * p.block_n;
           const uint32_t faddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + group * kAccStride + p.block_n;
-          for (int c = 0; c < 2 * p.block_n; c += 32) {
-            const bool is_scale = c < p.block_n;
-            const float* s_ = is_scale ? src + c : src + p.cout + (c - p.block_n);
+          const int fcols = p.film_cols ? p.film_cols : p.block_n, fcout = p.film_cols ? p.film_cols : p.cout;
+          for (int c = 0; c < 2 * fcols; c += 32) {
+            const bool is_scale = c < fcols;
+            const float* s_ = is_scale ? src + c : src + fcout + (c - fcols);
             uint32_t r[32];
 #pragma unroll
             for (int q = 0; q < 8; ++q) {

@@ -47,6 +47,7 @@ class ConvDesc(C.Structure):
         ("kv_shift", C.c_void_p), ("ctx_acc", C.c_void_p),
         ("halo", C.c_int32),
         ("ctx_slots", C.c_int32),
+        ("pair", C.c_int32),
     ]
 
 

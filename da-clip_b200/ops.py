@@ -251,6 +251,61 @@ class ConvPlan:
             pass
 
 
+def pack_conv_pair(weight):
+    """3x3 stride-1 conv weight [64, cin, 3, 3] for the pixel-pair mode of the conv kernel (dac_conv_desc.pair): per ky
+    one 192-row block [W(kx=2); W(kx=1); W(kx=0)], K-major [3][192][cin] bf16.  The even-pixel chunk reads rows [64,192)
+    (centre of the even output | left neighbour of the odd one) and rows [0,64) (right neighbour of the odd output, from
+    the next pair); the odd-pixel chunk rows [0,128) and rows [128,192)."""
+    cout, cin, kh, kw = weight.shape
+    assert (cout, kh, kw) == (64, 3, 3) and cin % 64 == 0
+    w = torch.stack([torch.cat([weight[:, :, ky, 2], weight[:, :, ky, 1], weight[:, :, ky, 0]], 0) for ky in range(3)])
+    return w.to(torch.bfloat16).contiguous()
+
+
+def pair_eligible(pw, cout, c0, c1, W):
+    """3x3 stride-1 convs with 64 output channels, 64-channel sources and an even width (see PairConvPlan)."""
+    return (cout == 64 and c0 == 64 and c1 in (0, 64) and W % 2 == 0 and W >= 16 and not os.environ.get("DAC_NO_PAIR"))
+
+
+class PairConvPlan(ConvPlan):
+    """A 64-output-channel 3x3 conv in pixel-pair mode: every NHWC tensor [B, H, W, C] is handed to the kernel as its
+    [B, H, W/2, 2C] view, so a GEMM row is a pair of adjacent pixels and the centre taps run as N = 128 MMAs (an N = 64
+    MMA is capped at 66.6 % of the tensor peak by its shared-memory operand fetch, profiles/r01_mma_rate.txt)."""
+
+    def __init__(self, src0, wpair, out, *, B, H, W, src1=None, act=L.ACT_NONE, film=None, film_off=0, res=None):
+        L.require_cuda(src0, wpair, out)
+        assert W % 2 == 0 and src0.shape[-1] == 64 and out.shape[-1] == 64
+        lib = L.load()
+        d = L.ConvDesc()
+        Wp = W // 2
+        d.src0, d.c0, d.ld0 = src0.data_ptr(), 128, 128
+        if src1 is not None:
+            assert src1.shape[-1] == 64
+            d.src1, d.c1, d.ld1 = src1.data_ptr(), 128, 128
+        d.B, d.H, d.W, d.OH, d.OW = B, H, Wp, H, Wp
+        d.stride, d.ngroups, d.ntaps, d.ndy, d.ncols = 1, 1, 9, 9, 1
+        d.col_dx[0][0], d.col_dy0[0][0] = -1, -1
+        for i in range(9):
+            d.col_tap[0][i] = i
+        d.out_scale = 1
+        d.weight, d.cout, d.cout_pad, d.per_image_w = wpair.data_ptr(), 128, 128, 0
+        d.block_n, d.tile_h, d.tile_w = 128, 16, 8
+        d.epi, d.act, d.halo, d.pair = L.EPI_PLAIN, act, 1, 1
+        if film is not None:
+            d.film, d.film_ld, d.film_off = film.data_ptr(), film.shape[-1], film_off
+        if res is not None:
+            assert res.shape[-1] == 64
+            d.res, d.res_ld = res.data_ptr(), 128
+        d.out, d.out_ld, d.out_coff = out.data_ptr(), 128, 0
+        self._keep = (src0, src1, wpair, out, film, res)
+        self.desc = d
+        h = C.c_void_p()
+        L.check(lib.dac_conv_create(C.byref(d), C.byref(h)))
+        self.handle = h
+        self._lib = lib
+        self.flops = 2.0 * B * H * W * 9 * (64 + (64 if src1 is not None else 0)) * 64
+
+
 def ctx_slots(B, h, w, tensor_core_kv):
     """Partial context records per (image, head) the k|v kernels store (dac_linattn_ctx_slots): one per CTA that touches
     the image for dac_linattn_kv, two (one per epilogue group) for the KVCTX convolution epilogue."""

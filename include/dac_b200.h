@@ -138,6 +138,12 @@ typedef struct dac_conv_desc {
                                                      stride); ncols = 1, ndy = 9, col_dx = col_dy0 = -1 */
   int32_t ctx_slots;                              /* KVCTX: partial records per (image, head) in ctx_acc,
                                                      >= dac_linattn_ctx_slots(B, tiles per image, 2) */
+  int32_t pair;                                   /* pixel-pair mode of a 3x3 stride-1 conv with 64 output channels (the
+                                                     layers an N = 64 MMA caps at 66.6 % of the tensor peak): every tensor
+                                                     is passed as its [B, H, W/2, 2C] view (W even; c0 / c1 / cout / block_n
+                                                     = twice the real counts, 128), halo loads, weight = bf16
+                                                     [3 ky][192 = kx 2,1,0 x 64 cout][cin], FiLM vectors of 64 entries;
+                                                     the centre taps run as N = 128 MMAs.  PLAIN epilogue only */
 } dac_conv_desc;
 
 typedef struct dac_conv_plan* dac_conv_t;

@@ -92,6 +92,37 @@ def test_conv3x3_film_silu(ops, gen, B, H, W, cin, cout, tile):
     assert_close_bf16(nchw(out), ref, f"conv3x3 {B}x{H}x{W} {cin}->{cout} {plan.info()}")
 
 
+@pytest.mark.parametrize("B,H,W,concat,mode", [
+    (2, 32, 32, False, "film"), (1, 16, 48, True, "film"), (3, 40, 24, False, "res"), (2, 37, 50, True, "plain"),
+    (1, 256, 256, False, "film"), (5, 16, 16, False, "res"), (1, 8, 16, True, "res")])
+def test_conv3x3_pixel_pair(ops, gen, B, H, W, concat, mode):
+    """Pixel-pair mode (dac_conv_desc.pair): the tensors viewed as [B, H, W/2, 2C], centre taps as N = 128 MMAs against
+    overlapping windows of one 192-row weight block per ky, side taps as N = 64 MMAs into one half of the accumulator;
+    FiLM vectors shared by the two pixels of a pair; ragged sizes (partial tiles, odd pair counts)."""
+    from daclip_b200 import lib as L
+    cin = 128 if concat else 64
+    x = rnd(gen, B, cin, H, W)
+    w = rnd(gen, 64, cin, 3, 3, scale=(9 * cin) ** -0.5)
+    xh = nhwc(x)
+    a = xh[..., :64].contiguous()
+    s_ = xh[..., 64:].contiguous() if concat else None
+    film = rnd(gen, B, 2 * 64 + 8, scale=0.5) if mode == "film" else None
+    res = nhwc(rnd(gen, B, 64, H, W)) if mode == "res" else None
+    out = torch.full((B, H, W, 64), float("nan"), device="cuda", dtype=torch.bfloat16)
+    act = L.ACT_NONE if mode == "plain" else L.ACT_SILU
+    plan = ops.PairConvPlan(a, ops.pack_conv_pair(w), out, B=B, H=H, W=W, src1=s_, act=act, film=film, film_off=8,
+                            res=res)
+    for _ in range(2):
+        plan.run()
+    torch.cuda.synchronize()
+    y = F.conv2d(nchw(xh), bf(w).float(), padding=1)
+    if mode == "film":
+        y = F.silu(y * (film[:, 8:72, None, None] + 1) + film[:, 72:136, None, None])
+    elif mode == "res":
+        y = F.silu(y) + nchw(res)
+    assert_close_bf16(nchw(out), y, f"pixel-pair conv3x3 {B}x{H}x{W} {cin}->64 {mode} {plan.info()}")
+
+
 @pytest.mark.parametrize("B,H,W,c0,c1,cout", [(2, 40, 24, 64, 0, 64), (3, 37, 51, 64, 64, 64), (1, 16, 8, 128, 0, 64),
                                                (2, 9, 200, 64, 0, 128)])
 def test_conv3x3_halo_load(ops, gen, B, H, W, c0, c1, cout):

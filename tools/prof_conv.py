@@ -19,6 +19,10 @@ CASES = {
     "l0_toout": (16, 256, 256, 128, 64, "toout"),
     "l0_qout": (16, 256, 256, 64, 64, "qout"),
     "l0_kvtc": (16, 256, 256, 64, 256, "kvtc"),
+    "l0_pair": (16, 256, 256, 64, 64, "pair"),
+    "l0_pair_cat": (16, 256, 256, 128, 64, "pair"),
+    "l1_pair": (16, 128, 128, 64, 64, "pair"),
+    "l1_3x3_64": (16, 128, 128, 64, 64, "3x3"),
     "l1_qout": (16, 128, 128, 128, 128, "qout"),
 }
 
@@ -47,6 +51,12 @@ def make(name):
         ctx = torch.zeros(B, 4, ops.ctx_slots(B, H, W, False), 32 * 34, device="cuda")
         plan = ops.ConvPlan(x, cin, ops.pack_linear(w), None, B=B, H=H, W=W, epi=L.EPI_KVCTX, block_n=256,
                             kv_shift=shift, ctx_acc=ctx)
+    elif kind == "pair":
+        w = torch.randn(cout, cin, 3, 3, device="cuda", generator=g) * (9 * cin) ** -0.5
+        film = torch.randn(B, 2 * cout, device="cuda", generator=g) * 0.1
+        a = x[..., :64].contiguous()
+        s1 = x[..., 64:].contiguous() if cin == 128 else None
+        plan = ops.PairConvPlan(a, ops.pack_conv_pair(w), out, B=B, H=H, W=W, src1=s1, act=L.ACT_SILU, film=film)
     elif kind == "kvtc":
         w = torch.randn(cout, cin, device="cuda", generator=g) * cin ** -0.5
         shift = torch.full((128,), 12.0, device="cuda")
