@@ -250,6 +250,9 @@ class PackedUNet:
                 w2=ops.pack_conv(f32(prefix + "block2.proj.weight")),
                 wr=ops.pack_linear(f32(prefix + "res_conv.weight")) if prefix + "res_conv.weight" in sd else None,
                 cin=cin, cout=cout)
+            if cout == 64 and cin in (64, 128):       # pixel-pair packing for the 64-output-channel layers (ops.PairConvPlan)
+                self.rb[prefix].update(w1p=ops.pack_conv_pair(f32(prefix + "block1.proj.weight")),
+                                       w2p=ops.pack_conv_pair(f32(prefix + "block2.proj.weight")))
         self.film_w, self.film_b, self.F = torch.cat(ws).contiguous(), torch.cat(bs).contiguous(), off
         self.has_prompt = cfg.context_dim > 0 and cfg.use_degra_context
         ew = L.EmbedWeights()
@@ -292,6 +295,8 @@ class PackedUNet:
                 self.up.append((ops.pack_upsample_conv(f32(f"ups.{j}.3.1.weight")), f32(f"ups.{j}.3.1.bias")))
             else:
                 self.up.append((ops.pack_conv(f32(f"ups.{j}.3.weight")), None))
+                if cfg.dims[0][0] == 64 and cfg.dims[0][1] == 64:
+                    self.up_last_pair = ops.pack_conv_pair(f32(f"ups.{j}.3.weight"))
         if cfg.scale == 0.5:
             self.pre_down = (ops.pack_conv(f32("downsample.weight"), stride=2, pad=1), f32("downsample.bias"))
             self.post_up = (ops.pack_upsample_conv(f32("upsample.1.weight")), f32("upsample.1.bias"))
@@ -392,14 +397,32 @@ class UNetEngine:
     def is_conv(self, name):
         return name in self.conv_names
 
+    def pair_conv(self, name, src0, wpair, out, h, w, **kw):
+        plan = ops.PairConvPlan(src0, wpair, out, B=self.B, H=h, W=w, **kw)
+        self.flops += plan.flops
+        self.conv_names.add(name)
+        self.add(name, plan.run)
+        return plan
+
     def resblock(self, prefix, x, xc, h, w, skip=None, sc=0, stats=None):
         rb = self.pk.rb[prefix]
         cout = rb["cout"]
         B = self.B
         h1 = self.buf(B, h, w, cout)
-        self.conv(prefix + "block1", x, xc, rb["w1"], h1, h, w, src1=skip, c1=sc, act=L.ACT_SILU,
-                  film=self.film, film_off=self.pk.film_off[prefix])
+        # 64-output-channel 3x3 layers in pixel-pair mode (N = 128 MMAs; an N = 64 MMA is capped at 66.6 % of the tensor
+        # peak by its operand fetch): block1, and block2 when its skip is the identity
+        pair = self.PAIR and "w1p" in rb and ops.pair_eligible(None, cout, xc, sc, w)
+        if pair:
+            self.pair_conv(prefix + "block1", x, rb["w1p"], h1, h, w, src1=skip, act=L.ACT_SILU, film=self.film,
+                           film_off=self.pk.film_off[prefix])
+        else:
+            self.conv(prefix + "block1", x, xc, rb["w1"], h1, h, w, src1=skip, c1=sc, act=L.ACT_SILU,
+                      film=self.film, film_off=self.pk.film_off[prefix])
         out = self.buf(B, h, w, cout)
+        if pair and rb["wr"] is None and stats is None:
+            assert skip is None
+            self.pair_conv(prefix + "block2", h1, rb["w2p"], out, h, w, act=L.ACT_SILU, res=x)
+            return out
         if rb["wr"] is not None and cout <= 128:
             # res_conv fused into block2: a second TMEM accumulator fed by extra K steps over (x | skip); neither the
             # 1x1 conv launch nor its output tensor exists
@@ -425,6 +448,7 @@ class UNetEngine:
     FOLD_PRENORM = False
     FOLD_PRENORM_MAX_HW = 128 * 128
     PDL = True             # programmatic dependent launch between consecutive kernel nodes of the step graph
+    PAIR = True            # pixel-pair mode for the 64-output-channel 3x3 convolutions (ops.PairConvPlan)
     FUSE_KV_TC = True      # LinearAttention: the k|v context reduction as a second tcgen05 GEMM (TMEM-resident context)
     FUSE_QOUT = True       # LinearAttention: to_q + softmax + to_out + LayerNorm + residual as one chained-GEMM kernel
     FUSE_KVCTX = True      # LinearAttention: reduce k | v into the context inside the to_kv GEMM epilogue
@@ -611,7 +635,10 @@ class UNetEngine:
                 h, w = 2 * h, 2 * w
             else:
                 y = self.buf(B, h, w, din)
-                self.conv(p + "3", x, dout, pw, y, h, w)
+                if self.PAIR and getattr(pk, "up_last_pair", None) is not None and ops.pair_eligible(None, din, dout, 0, w):
+                    self.pair_conv(p + "3", x, pk.up_last_pair, y, h, w)
+                else:
+                    self.conv(p + "3", x, dout, pw, y, h, w)
             x = y
             self.taps[p + "3"] = x
         if cfg.scale == 0.5:
