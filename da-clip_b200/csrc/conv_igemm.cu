@@ -128,7 +128,7 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
   }
   if (d->pair) {
     if (!d->halo || d->block_n != 128 || d->cout != 128 || d->cout_pad != 128 || d->epi != DAC_EPI_PLAIN || nchw ||
-        fused_res || d->stats_out || d->per_image_w || d->c0 % 128 || d->c1 % 128 || d->out_scale > 1 || d->out_f32 ||
+        d->stats_out || d->per_image_w || d->rc0 % 128 || d->rc1 % 128 || d->c0 % 128 || d->c1 % 128 || d->out_scale > 1 || d->out_f32 ||
         d->res_f32 || d->bias_img)
       return set_error(-2, "dac_conv_create: pixel-pair mode needs a haloed 3x3 conv, PLAIN epilogue, wide views with "
                            "block_n = cout = 128 and channel counts that are multiples of 128");
@@ -166,6 +166,7 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
   k.r_chunks0 = fused_res ? d->rc0 / kChunkK : 0;
   k.r_chunks1 = fused_res ? d->rc1 / kChunkK : 0;
   k.r_a_bytes = (uint32_t)d->tile_h * d->tile_w * kChunkK * 2;
+  k.r_b_bytes = d->pair ? 64u * kChunkK * 2 : k.b_bytes;
   k.a_bytes = (uint32_t)a_rows * box_w * kChunkK * 2;
   k.a_slot = (k.a_bytes + 1023u) & ~1023u;
   k.a_sbo = d->halo ? (uint32_t)box_w * 128u : 1024u;          // halo, tile_w 8: one (padded) pixel row per 8-row group
@@ -213,7 +214,7 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
     }
   }
   uint32_t stage_bytes = k.a_slot + (resident ? 0u : (uint32_t)d->ndy * k.b_bytes);
-  if (fused_res && stage_bytes < k.r_a_bytes + k.b_bytes) stage_bytes = k.r_a_bytes + k.b_bytes;
+  if (fused_res && stage_bytes < k.r_a_bytes + k.r_b_bytes) stage_bytes = k.r_a_bytes + k.r_b_bytes;
   // bf16 NHWC output through a swizzled staging tile + TMA store (coalesced, clipped by the tensor map) whenever the
   // staging tile leaves room for >= 3 pipeline stages; otherwise each thread stores its own row directly.
   const int out_cols = d->epi == DAC_EPI_GEGLU ? d->block_n / 2 : d->block_n;
@@ -329,10 +330,12 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
       rc = encode_act_map(&pl->mapR1, d->rsrc1, d->rc1, d->rld1, d->W, d->H, d->B, d->tile_w, d->tile_h, 1);
     if (rc == 0) {
       PFN_encodeTiled enc = get_encode_fn();
-      const int rct = d->rc0 + d->rc1;
-      cuuint64_t dims[3] = {(cuuint64_t)rct, (cuuint64_t)d->cout_pad, 1};
-      cuuint64_t strides[2] = {(cuuint64_t)rct * 2, (cuuint64_t)d->cout_pad * rct * 2};
-      cuuint32_t box[3] = {(cuuint32_t)kChunkK, (cuuint32_t)d->block_n, 1};
+      // pair mode: the skip weight is the real [64][rc / 2] matrix; every wide chunk multiplies one 64-row tile of it
+      const int rct = d->pair ? (d->rc0 + d->rc1) / 2 : d->rc0 + d->rc1;
+      const int rrows = d->pair ? 64 : d->cout_pad;
+      cuuint64_t dims[3] = {(cuuint64_t)rct, (cuuint64_t)rrows, 1};
+      cuuint64_t strides[2] = {(cuuint64_t)rct * 2, (cuuint64_t)rrows * rct * 2};
+      cuuint32_t box[3] = {(cuuint32_t)kChunkK, (cuuint32_t)(d->pair ? 64 : d->block_n), 1};
       cuuint32_t estr[3] = {1, 1, 1};
       CUresult r = enc(&pl->mapWR, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(d->rweight), dims, strides,
                        box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,

@@ -70,6 +70,7 @@ struct ConvKParams {
   uint32_t b_res_bytes;    // > 0: the whole weight tensor stays resident in shared memory
   int r_chunks0, r_chunks1;   // fused 1x1 skip conv: K chunks of its two sources (0, 0 = none)
   uint32_t r_a_bytes;         // its activation tile: tile_h * tile_w rows x 128 B
+  uint32_t r_b_bytes;         // its weight tile: block_n rows x 128 B (pair mode: the 64 real output channels)
   int ndy, ncols;
   int8_t col_dx[4][16];
   int8_t col_dy0[4][16];
@@ -540,7 +541,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   const uint32_t b_stream = b_resident ? 0u : static_cast<uint32_t>(p.ndy) * p.b_bytes;
   const uint32_t main_tx = p.a_bytes + b_stream;   // bytes landing per K step
   uint32_t stage_bytes = p.a_slot + b_stream;
-  if (r_chunks && stage_bytes < p.r_a_bytes + p.b_bytes) stage_bytes = p.r_a_bytes + p.b_bytes;
+  if (r_chunks && stage_bytes < p.r_a_bytes + p.r_b_bytes) stage_bytes = p.r_a_bytes + p.r_b_bytes;
   uint8_t* stg_base = p.stg_bytes ? ring + static_cast<size_t>(p.stages) * stage_bytes : nullptr;
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + static_cast<size_t>(p.stages) * stage_bytes +
                                                static_cast<size_t>(p.stg_bytes) * p.stg_count);
@@ -655,10 +656,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         for (int rk = 0; rk < r_chunks; ++rk) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = ring + static_cast<size_t>(stage) * stage_bytes;
-          mbar_arrive_expect_tx(&full[stage], p.r_a_bytes + p.b_bytes);
+          mbar_arrive_expect_tx(&full[stage], p.r_a_bytes + p.r_b_bytes);
           if (rk < p.r_chunks0) tma_load_4d(sa, &mapR0, &full[stage], rk * kChunkK, xin, yin, t.n);
           else tma_load_4d(sa, &mapR1, &full[stage], (rk - p.r_chunks0) * kChunkK, xin, yin, t.n);
-          tma_load_3d(sa + p.r_a_bytes, &mapWR, &full[stage], rk * kChunkK, 0, 0);
+          // pair mode: the even and the odd chunk of a 64-channel slice use the same weight columns
+          tma_load_3d(sa + p.r_a_bytes, &mapWR, &full[stage], (p.pair ? (rk >> 1) : rk) * kChunkK, 0, 0);
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1;
@@ -781,11 +783,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           const uint32_t a0 = ring_lo + stage * stage_lo;
           const uint64_t adesc = desc_fixed | a0;
           const uint64_t bdesc = desc_fixed | (a0 + (p.r_a_bytes >> 4));
+          // pair mode: the 1x1 conv of the even pixels lands in the first half of the second accumulator, odd: second half
+          const uint32_t d_r = d_tmem + p.block_n + ((p.pair && (rk & 1)) ? (p.block_n >> 1) : 0);
+          const uint32_t idesc_r = p.pair ? make_idesc_bf16(kTileM, p.block_n >> 1) : idesc;
+          const uint32_t acc_r = p.pair ? (rk >= 2 ? 1u : 0u) : (rk ? 1u : 0u);
           if (elect_one()) {
-            umma_bf16(d_tmem + p.block_n, adesc, bdesc, idesc, rk ? 1u : 0u);
-            umma_bf16(d_tmem + p.block_n, adesc + 2, bdesc + 2, idesc, 1u);
-            umma_bf16(d_tmem + p.block_n, adesc + 4, bdesc + 4, idesc, 1u);
-            umma_bf16(d_tmem + p.block_n, adesc + 6, bdesc + 6, idesc, 1u);
+            umma_bf16(d_r, adesc, bdesc, idesc_r, acc_r);
+            umma_bf16(d_r, adesc + 2, bdesc + 2, idesc_r, 1u);
+            umma_bf16(d_r, adesc + 4, bdesc + 4, idesc_r, 1u);
+            umma_bf16(d_r, adesc + 6, bdesc + 6, idesc_r, 1u);
             umma_commit(&empty[stage]);
           }
           if (++stage == p.stages) {

@@ -272,7 +272,8 @@ class PairConvPlan(ConvPlan):
     [B, H, W/2, 2C] view, so a GEMM row is a pair of adjacent pixels and the centre taps run as N = 128 MMAs (an N = 64
     MMA is capped at 66.6 % of the tensor peak by its shared-memory operand fetch, profiles/r01_mma_rate.txt)."""
 
-    def __init__(self, src0, wpair, out, *, B, H, W, src1=None, act=L.ACT_NONE, film=None, film_off=0, res=None):
+    def __init__(self, src0, wpair, out, *, B, H, W, src1=None, act=L.ACT_NONE, film=None, film_off=0, res=None,
+                 rsrc0=None, rsrc1=None, rweight=None):
         L.require_cuda(src0, wpair, out)
         assert W % 2 == 0 and src0.shape[-1] == 64 and out.shape[-1] == 64
         lib = L.load()
@@ -297,13 +298,23 @@ class PairConvPlan(ConvPlan):
             assert res.shape[-1] == 64
             d.res, d.res_ld = res.data_ptr(), 128
         d.out, d.out_ld, d.out_coff = out.data_ptr(), 128, 0
-        self._keep = (src0, src1, wpair, out, film, res)
+        rc = 0
+        if rsrc0 is not None:        # fused 1x1 skip conv over (rsrc0 | rsrc1), 64 channels each: rweight = pack_linear([64, rc])
+            assert rsrc0.shape[-1] == 64 and rweight.w.shape[-2] == 64
+            d.rsrc0, d.rc0, d.rld0 = rsrc0.data_ptr(), 128, 128
+            rc = 64
+            if rsrc1 is not None:
+                assert rsrc1.shape[-1] == 64
+                d.rsrc1, d.rc1, d.rld1 = rsrc1.data_ptr(), 128, 128
+                rc = 128
+            d.rweight = rweight.w.data_ptr()
+        self._keep = (src0, src1, wpair, out, film, res, rsrc0, rsrc1, rweight)
         self.desc = d
         h = C.c_void_p()
         L.check(lib.dac_conv_create(C.byref(d), C.byref(h)))
         self.handle = h
         self._lib = lib
-        self.flops = 2.0 * B * H * W * 9 * (64 + (64 if src1 is not None else 0)) * 64
+        self.flops = 2.0 * B * H * W * 9 * (64 + (64 if src1 is not None else 0)) * 64 + 2.0 * B * H * W * rc * 64
 
 
 def ctx_slots(B, h, w, tensor_core_kv):

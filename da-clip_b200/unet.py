@@ -423,6 +423,11 @@ class UNetEngine:
             assert skip is None
             self.pair_conv(prefix + "block2", h1, rb["w2p"], out, h, w, act=L.ACT_SILU, res=x)
             return out
+        if pair and rb["wr"] is not None and stats is None:
+            # ... and with the 1x1 res_conv fused as a second accumulator (two N = 64 MMA groups per source slice)
+            self.pair_conv(prefix + "block2", h1, rb["w2p"], out, h, w, act=L.ACT_SILU, rsrc0=x, rsrc1=skip,
+                           rweight=rb["wr"])
+            return out
         if rb["wr"] is not None and cout <= 128:
             # res_conv fused into block2: a second TMEM accumulator fed by extra K steps over (x | skip); neither the
             # 1x1 conv launch nor its output tensor exists

@@ -123,6 +123,28 @@ def test_conv3x3_pixel_pair(ops, gen, B, H, W, concat, mode):
     assert_close_bf16(nchw(out), y, f"pixel-pair conv3x3 {B}x{H}x{W} {cin}->64 {mode} {plan.info()}")
 
 
+@pytest.mark.parametrize("B,H,W,two", [(2, 32, 32, True), (3, 24, 40, False), (1, 256, 256, True), (2, 19, 34, True)])
+def test_conv3x3_pixel_pair_fused_skip(ops, gen, B, H, W, two):
+    """Pixel-pair mode with the ResBlock's 1x1 res_conv fused as a second accumulator (even pixels -> first half of its
+    columns, odd pixels -> second half): silu(conv3x3(h)) + W_r [x | skip]."""
+    from daclip_b200 import lib as L
+    rc = 128 if two else 64
+    hh = nhwc(rnd(gen, B, 64, H, W))
+    xr = nhwc(rnd(gen, B, rc, H, W))
+    w = rnd(gen, 64, 64, 3, 3, scale=(9 * 64) ** -0.5)
+    wr = rnd(gen, 64, rc, scale=rc ** -0.5)
+    out = torch.full((B, H, W, 64), float("nan"), device="cuda", dtype=torch.bfloat16)
+    r0 = xr[..., :64].contiguous()
+    r1 = xr[..., 64:].contiguous() if two else None
+    plan = ops.PairConvPlan(hh, ops.pack_conv_pair(w), out, B=B, H=H, W=W, act=L.ACT_SILU, rsrc0=r0, rsrc1=r1,
+                            rweight=ops.pack_linear(wr))
+    for _ in range(2):
+        plan.run()
+    torch.cuda.synchronize()
+    ref = F.silu(F.conv2d(nchw(hh), bf(w).float(), padding=1)) + F.conv2d(nchw(xr), bf(wr).float()[:, :, None, None])
+    assert_close_bf16(nchw(out), ref, f"pixel-pair conv3x3 + fused skip {B}x{H}x{W} rc={rc} {plan.info()}")
+
+
 @pytest.mark.parametrize("B,H,W,c0,c1,cout", [(2, 40, 24, 64, 0, 64), (3, 37, 51, 64, 64, 64), (1, 16, 8, 128, 0, 64),
                                                (2, 9, 200, 64, 0, 128)])
 def test_conv3x3_halo_load(ops, gen, B, H, W, c0, c1, cout):

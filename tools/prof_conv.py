@@ -22,6 +22,8 @@ CASES = {
     "l0_pair": (16, 256, 256, 64, 64, "pair"),
     "l0_pair_cat": (16, 256, 256, 128, 64, "pair"),
     "l1_pair": (16, 128, 128, 64, 64, "pair"),
+    "l0_pair_skip": (16, 256, 256, 64, 64, "pair_skip"),
+    "l0_3x3_skip": (16, 256, 256, 64, 64, "3x3_skip"),
     "l1_3x3_64": (16, 128, 128, 64, 64, "3x3"),
     "l1_qout": (16, 128, 128, 128, 128, "qout"),
 }
@@ -57,6 +59,17 @@ def make(name):
         a = x[..., :64].contiguous()
         s1 = x[..., 64:].contiguous() if cin == 128 else None
         plan = ops.PairConvPlan(a, ops.pack_conv_pair(w), out, B=B, H=H, W=W, src1=s1, act=L.ACT_SILU, film=film)
+    elif kind in ("pair_skip", "3x3_skip"):
+        w = torch.randn(cout, cin, 3, 3, device="cuda", generator=g) * (9 * cin) ** -0.5
+        wr = torch.randn(64, 128, device="cuda", generator=g) * 128 ** -0.5
+        r0 = torch.randn(B, H, W, 64, device="cuda", generator=g).to(torch.bfloat16)
+        r1 = torch.randn(B, H, W, 64, device="cuda", generator=g).to(torch.bfloat16)
+        if kind == "pair_skip":
+            plan = ops.PairConvPlan(x, ops.pack_conv_pair(w), out, B=B, H=H, W=W, act=L.ACT_SILU, rsrc0=r0, rsrc1=r1,
+                                    rweight=ops.pack_linear(wr))
+        else:
+            plan = ops.ConvPlan(x, cin, ops.pack_conv(w), out, B=B, H=H, W=W, act=L.ACT_SILU, rsrc0=r0, rc0=64, rsrc1=r1,
+                                rc1=64, rweight=ops.pack_linear(wr))
     elif kind == "kvtc":
         w = torch.randn(cout, cin, device="cuda", generator=g) * cin ** -0.5
         shift = torch.full((128,), 12.0, device="cuda")
