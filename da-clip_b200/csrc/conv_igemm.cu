@@ -226,7 +226,10 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
     int without = (smem_budget - (int)k.b_res_bytes) / (int)stage_bytes;
     if (without > kMaxStages) without = kMaxStages;
     const int with = (smem_budget - (int)k.b_res_bytes - 2 * (int)want) / (int)stage_bytes;
-    if (with >= 4 || (with >= 3 && with >= without)) stg_bytes = want;
+    // (pixel-pair mode with a residual: one K chunk keeps the tensor pipe busy for 1344 cycles, three stages are enough,
+    // and direct residual loads - one 256-byte row per thread - cost far more than the pipeline depth buys: 124 -> 95 us;
+    // without a residual the deeper pipeline wins: FiLM 91 vs 94 us, fused skip 107 vs 130 us)
+    if (with >= 4 || (with >= 3 && (with >= without || (d->pair && d->res)))) stg_bytes = want;
   }
   if (d->epi == DAC_EPI_KVCTX) stg_bytes = kKvStageBytes;   // P / V head tiles of each epilogue group
   k.kv_shift = d->kv_shift; k.ctx_acc = d->ctx_acc;

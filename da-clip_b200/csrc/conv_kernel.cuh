@@ -885,6 +885,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           mbar_arrive_expect_tx(&res_bar[group], static_cast<uint32_t>(cols) * kTileM * 2);
           for (int s_ = 0; s_ * 64 < cols; ++s_)
             tma_load_4d(stg + s_ * (kTileM * 128), &mapRes, &res_bar[group], t.nt * cols + s_ * 64, t.x0, t.y0, t.n);
+          // ... and pull the residual of this group's NEXT tile into L2: its load can only be issued once the store of
+          // this tile has left the staging buffer, and a DRAM round trip at that point was the longest link of the
+          // per-group chain (store drained -> residual lands -> epilogue -> store) - 4.5 us per tile, whatever its size
+          if (tile + 2 < tile_end) {
+            const TileCoord tn = decode_tile(p, tile + 2);
+            for (int s_ = 0; s_ * 64 < cols; ++s_)
+              tma_prefetch_l2_4d(&mapRes, tn.nt * cols + s_ * 64, tn.x0, tn.y0, tn.n);
+          }
         }
       }
       mbar_wait(&tmem_full[group], acc_phase);

@@ -67,6 +67,12 @@ __device__ __forceinline__ void tma_load_4d(void* smem, const void* map, uint64_
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// Brings a 4-D box into L2 only (no shared memory, no barrier): a later tma_load_4d of the same box hits L2.
+__device__ __forceinline__ void tma_prefetch_l2_4d(const void* map, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(map), "r"(c0), "r"(c1),
+               "r"(c2), "r"(c3)
+               : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(void* smem, const void* map, uint64_t* bar, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], "

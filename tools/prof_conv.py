@@ -22,6 +22,8 @@ CASES = {
     "l0_pair": (16, 256, 256, 64, 64, "pair"),
     "l0_pair_cat": (16, 256, 256, 128, 64, "pair"),
     "l1_pair": (16, 128, 128, 64, 64, "pair"),
+    "l0_pair_plain": (16, 256, 256, 64, 64, "pair_plain"),
+    "l0_pair_res": (16, 256, 256, 64, 64, "pair_res"),
     "l0_pair_skip": (16, 256, 256, 64, 64, "pair_skip"),
     "l0_3x3_skip": (16, 256, 256, 64, 64, "3x3_skip"),
     "l1_3x3_64": (16, 128, 128, 64, 64, "3x3"),
@@ -53,6 +55,11 @@ def make(name):
         ctx = torch.zeros(B, 4, ops.ctx_slots(B, H, W, False), 32 * 34, device="cuda")
         plan = ops.ConvPlan(x, cin, ops.pack_linear(w), None, B=B, H=H, W=W, epi=L.EPI_KVCTX, block_n=256,
                             kv_shift=shift, ctx_acc=ctx)
+    elif kind in ("pair_plain", "pair_res"):
+        w = torch.randn(cout, cin, 3, 3, device="cuda", generator=g) * (9 * cin) ** -0.5
+        res = torch.randn(B, H, W, 64, device="cuda", generator=g).to(torch.bfloat16) if kind == "pair_res" else None
+        plan = ops.PairConvPlan(x, ops.pack_conv_pair(w), out, B=B, H=H, W=W, act=L.ACT_SILU if res is not None else L.ACT_NONE,
+                                res=res)
     elif kind == "pair":
         w = torch.randn(cout, cin, 3, 3, device="cuda", generator=g) * (9 * cin) ** -0.5
         film = torch.randn(B, 2 * cout, device="cuda", generator=g) * 0.1
