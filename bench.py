@@ -36,8 +36,8 @@ ALGO_GFLOP_PER_EVAL = {256: 266.2, 512: 1129.1}
 CONV_GFLOP_PER_EVAL = {256: 257.98 + 1.41, 512: 1031.9 + 5.64}
 # dram__bytes_read.sum + dram__bytes_write.sum of conv_igemm_kernel, averaged over its launches of one evaluation, from
 # the ncu launch list of this same command in steady state (profiles/r01_ncu_launches_bench_n1.csv: --launch-skip 16000
-# -c 250 = 2.05 evaluations, 161 conv launches): batch 16, 256^2 only.
-CONV_DRAM_BYTES_PER_LAUNCH = {(16, 256): 117.9e6}
+# -c 250 = 2.05 evaluations, 163 conv launches): batch 16, 256^2 only.
+CONV_DRAM_BYTES_PER_LAUNCH = {(16, 256): 95.8e6}
 
 
 def peaks():

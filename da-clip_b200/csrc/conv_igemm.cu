@@ -80,7 +80,7 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
     return set_error(-2, "dac_conv_create: fp32 stream only with the PLAIN epilogue");
   const bool nchw = d->out_nchw != nullptr;
   if (nchw) {
-    if (d->block_n != 16 || d->out_nchw_c > 16 || d->epi != DAC_EPI_PLAIN || d->act != DAC_ACT_NONE || d->film ||
+    if (d->block_n != (d->pair ? 32 : 16) || d->out_nchw_c > 16 || d->epi != DAC_EPI_PLAIN || d->act != DAC_ACT_NONE || d->film ||
         d->out || d->out_f32)
       return set_error(-2, "dac_conv_create: fp32 NCHW output needs block_n 16, <= 16 channels, plain epilogue");
   } else if (d->epi == DAC_EPI_LN) {
@@ -127,7 +127,9 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
       return set_error(-2, "dac_conv_create: fused skip conv needs PLAIN epilogue, one N tile <= 128, stride 1");
   }
   if (d->pair) {
-    if (!d->halo || d->block_n != 128 || d->cout != 128 || d->cout_pad != 128 || d->epi != DAC_EPI_PLAIN || nchw ||
+    const bool pair_ok = nchw ? (d->block_n == 32 && d->cout_pad == 32 && !d->rsrc0)
+                              : (d->block_n == 128 && d->cout == 128 && d->cout_pad == 128);
+    if (!d->halo || !pair_ok || d->epi != DAC_EPI_PLAIN ||
         d->stats_out || d->per_image_w || d->rc0 % 128 || d->rc1 % 128 || d->c0 % 128 || d->c1 % 128 || d->out_scale > 1 || d->out_f32 ||
         d->res_f32 || d->bias_img)
       return set_error(-2, "dac_conv_create: pixel-pair mode needs a haloed 3x3 conv, PLAIN epilogue, wide views with "
@@ -205,8 +207,8 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
   k.b_res_bytes = resident ? (uint32_t)res_bytes : 0u;
   k.pair = d->pair ? 1 : 0;
   if (d->pair) {   // one 192-row block per (64-channel source slice, ky), always resident
-    k.b_res_bytes = (uint32_t)(chunks / 2) * 3u * kPairBlock;
-    k.film_cols = 64;
+    k.b_res_bytes = (uint32_t)(chunks / 2) * 3u * (3u * (uint32_t)(d->block_n / 2) * 128u);
+    k.film_cols = d->block_n / 2;
     resident = true;
     if ((smem_budget - (long long)k.b_res_bytes) / (long long)k.a_slot < 2) {
       delete pl;
@@ -274,10 +276,10 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
     PFN_encodeTiled enc = get_encode_fn();
     const int ctot = d->pair ? (d->c0 + d->c1) / 2 : d->c0 + d->c1;
     const long long Z = d->pair ? 3 : (long long)d->ngroups * d->ntaps * (d->per_image_w ? d->B : 1);
-    const int wrows = d->pair ? 192 : d->cout_pad;
+    const int wrows = d->pair ? 3 * (d->block_n / 2) : d->cout_pad;
     cuuint64_t dims[3] = {(cuuint64_t)ctot, (cuuint64_t)wrows, (cuuint64_t)Z};
     cuuint64_t strides[2] = {(cuuint64_t)ctot * 2, (cuuint64_t)wrows * ctot * 2};
-    cuuint32_t box[3] = {(cuuint32_t)kChunkK, (cuuint32_t)(d->pair ? 192 : d->block_n), 1};
+    cuuint32_t box[3] = {(cuuint32_t)kChunkK, (cuuint32_t)(d->pair ? wrows : d->block_n), 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(&pl->mapW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(d->weight), dims, strides,
                      box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,

@@ -30,7 +30,6 @@ constexpr int kKvPitch = 40;                                   // bf16 per row o
 constexpr uint32_t kKvTileBytes = kTileM * kKvPitch * 2;         // 10 KB
 constexpr uint32_t kKvStageBytes = 4 * kKvTileBytes;             // P and V head tiles, double-buffered: per group
 constexpr int kCtxRecord = 32 * 32 + 64;                        // {C[32][32], m[32], S[32]} per (image, head)
-constexpr uint32_t kPairBlock = 192 * 128;                       // pixel-pair mode: three 64-row weight tiles of one (slice, ky)
 
 // Division by a launch-time constant without the ~60-cycle IDIV sequence (Granlund-Montgomery round-up method):
 // t = umulhi(mul, n); q = (t + ((n - t) >> s1)) >> s2.  Exact for 0 <= n < 2^31.
@@ -155,15 +154,19 @@ __device__ __forceinline__ void epilogue_tile(const ConvKParams& p, const TileCo
 
   if (EPI == KE_NCHW) {
     // final_conv: 16-column tile, fp32 planar output cropped to the un-padded image; one warp per quadrant works.
-    uint32_t r[16];
-    tmem_ld16(tmem_acc, r);
-    tmem_ld_wait();
-    if (valid && Y < p.nchw_h && X < p.nchw_w) {
+    // (pixel-pair mode: two 16-column halves, the even and the odd pixel of the pair)
+    for (int hp = 0; hp <= p.pair; ++hp) {
+      uint32_t r[16];
+      tmem_ld16(tmem_acc + 16 * hp, r);
+      tmem_ld_wait();
+      const int Xp = p.pair ? 2 * X + hp : X;
+      if (valid && Y < p.nchw_h && Xp < p.nchw_w) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        if (j < p.nchw_c) {
-          const float o = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + j) : 0.f);
-          p.out_nchw[((static_cast<long long>(n) * p.nchw_c + j) * p.nchw_h + Y) * p.nchw_w + X] = o;
+        for (int j = 0; j < 16; ++j) {
+          if (j < p.nchw_c) {
+            const float o = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + j) : 0.f);
+            p.out_nchw[((static_cast<long long>(n) * p.nchw_c + j) * p.nchw_h + Y) * p.nchw_w + Xp] = o;
+          }
         }
       }
     }
@@ -617,7 +620,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           // chunk of the slice read overlapping 128-row windows of it (see the issuer)
           for (int s_ = 0; s_ < (chunks >> 1); ++s_)
             for (int ky = 0; ky < 3; ++ky)
-              tma_load_3d(b_res + static_cast<size_t>(s_ * 3 + ky) * kPairBlock, &mapW, b_full, s_ * kChunkK, 0, ky);
+              tma_load_3d(b_res + static_cast<size_t>(s_ * 3 + ky) * (3u * (p.block_n >> 1) * 128u), &mapW, b_full,
+                          s_ * kChunkK, 0, ky);
         } else
         for (int nt = 0; nt < p.n_tiles; ++nt)
           for (int ck = 0; ck < chunks; ++ck)
@@ -708,7 +712,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           // = 224 instead of 288 fetch-bound cycles per 256 output pixels and K step.
           const uint32_t idesc_half = make_idesc_bf16(kTileM, p.block_n >> 1);
           const uint32_t half_cols = p.block_n >> 1;
-          const uint32_t blk_lo = kPairBlock >> 4, rows64_lo = (64u * 128u) >> 4;
+          // (half_cols rows per kx block: 64 for the ResBlock layers, 16 for final_conv; every window starts on a multiple
+          // of 8 rows = one 1024-byte swizzle atom)
+          const uint32_t blk_lo = (3u * half_cols * 128u) >> 4, rows64_lo = (half_cols * 128u) >> 4;
           for (int ck = 0; ck < chunks; ++ck) {
             mbar_wait(&full[stage], phase);
             tc_fence_after();

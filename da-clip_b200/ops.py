@@ -257,7 +257,7 @@ def pack_conv_pair(weight):
     (centre of the even output | left neighbour of the odd one) and rows [0,64) (right neighbour of the odd output, from
     the next pair); the odd-pixel chunk rows [0,128) and rows [128,192)."""
     cout, cin, kh, kw = weight.shape
-    assert (cout, kh, kw) == (64, 3, 3) and cin % 64 == 0
+    assert (kh, kw) == (3, 3) and cin % 64 == 0 and cout in (16, 64), "64 output channels, or final_conv padded to 16"
     w = torch.stack([torch.cat([weight[:, :, ky, 2], weight[:, :, ky, 1], weight[:, :, ky, 0]], 0) for ky in range(3)])
     return w.to(torch.bfloat16).contiguous()
 
@@ -273,9 +273,10 @@ class PairConvPlan(ConvPlan):
     MMA is capped at 66.6 % of the tensor peak by its shared-memory operand fetch, profiles/r01_mma_rate.txt)."""
 
     def __init__(self, src0, wpair, out, *, B, H, W, src1=None, act=L.ACT_NONE, film=None, film_off=0, res=None,
-                 rsrc0=None, rsrc1=None, rweight=None):
-        L.require_cuda(src0, wpair, out)
-        assert W % 2 == 0 and src0.shape[-1] == 64 and out.shape[-1] == 64
+                 rsrc0=None, rsrc1=None, rweight=None, out_nchw=None, bias=None):
+        L.require_cuda(src0, wpair, out if out is not None else out_nchw)
+        assert W % 2 == 0 and src0.shape[-1] == 64 and (out is None or out.shape[-1] == 64)
+        bn = 32 if out_nchw is not None else 128      # final_conv: 2 x 16 padded output channels, fp32 NCHW, cropped
         lib = L.load()
         d = L.ConvDesc()
         Wp = W // 2
@@ -289,15 +290,22 @@ class PairConvPlan(ConvPlan):
         for i in range(9):
             d.col_tap[0][i] = i
         d.out_scale = 1
-        d.weight, d.cout, d.cout_pad, d.per_image_w = wpair.data_ptr(), 128, 128, 0
-        d.block_n, d.tile_h, d.tile_w = 128, 16, 8
+        d.weight, d.cout, d.cout_pad, d.per_image_w = wpair.data_ptr(), bn, bn, 0
+        d.block_n, d.tile_h, d.tile_w = bn, 16, 8
+        assert wpair.shape[-2] == 3 * bn // 2
         d.epi, d.act, d.halo, d.pair = L.EPI_PLAIN, act, 1, 1
         if film is not None:
             d.film, d.film_ld, d.film_off = film.data_ptr(), film.shape[-1], film_off
         if res is not None:
             assert res.shape[-1] == 64
             d.res, d.res_ld = res.data_ptr(), 128
-        d.out, d.out_ld, d.out_coff = out.data_ptr(), 128, 0
+        if out is not None:
+            d.out, d.out_ld, d.out_coff = out.data_ptr(), 128, 0
+        if out_nchw is not None:
+            d.out_nchw = out_nchw.data_ptr()
+            d.out_nchw_c, d.out_nchw_h, d.out_nchw_w = out_nchw.shape[1], out_nchw.shape[2], out_nchw.shape[3]
+        if bias is not None:
+            d.bias = bias.data_ptr()
         rc = 0
         if rsrc0 is not None:        # fused 1x1 skip conv over (rsrc0 | rsrc1), 64 channels each: rweight = pack_linear([64, rc])
             assert rsrc0.shape[-1] == 64 and rweight.w.shape[-2] == 64
@@ -308,13 +316,14 @@ class PairConvPlan(ConvPlan):
                 d.rsrc1, d.rc1, d.rld1 = rsrc1.data_ptr(), 128, 128
                 rc = 128
             d.rweight = rweight.w.data_ptr()
-        self._keep = (src0, src1, wpair, out, film, res, rsrc0, rsrc1, rweight)
+        self._keep = (src0, src1, wpair, out, film, res, rsrc0, rsrc1, rweight, out_nchw, bias)
         self.desc = d
         h = C.c_void_p()
         L.check(lib.dac_conv_create(C.byref(d), C.byref(h)))
         self.handle = h
         self._lib = lib
-        self.flops = 2.0 * B * H * W * 9 * (64 + (64 if src1 is not None else 0)) * 64 + 2.0 * B * H * W * rc * 64
+        cout = out_nchw.shape[1] if out_nchw is not None else 64
+        self.flops = 2.0 * B * H * W * 9 * (64 + (64 if src1 is not None else 0)) * cout + 2.0 * B * H * W * rc * 64
 
 
 def ctx_slots(B, h, w, tensor_core_kv):

@@ -301,6 +301,9 @@ class PackedUNet:
             self.pre_down = (ops.pack_conv(f32("downsample.weight"), stride=2, pad=1), f32("downsample.bias"))
             self.post_up = (ops.pack_upsample_conv(f32("upsample.1.weight")), f32("upsample.1.bias"))
         self.final_w = ops.pack_conv(f32("final_conv.weight"))
+        fw = f32("final_conv.weight")
+        self.final_pair = ops.pack_conv_pair(torch.nn.functional.pad(fw, (0, 0, 0, 0, 0, 0, 0, 16 - fw.shape[0]))) \
+            if fw.shape[0] <= 16 and fw.shape[1] == 64 else None
         self.final_b = f32("final_conv.bias")
 
     def _pack_attn(self, sd, p, dim, transformer):
@@ -653,7 +656,10 @@ class UNetEngine:
             self.taps["upsample"] = x
         x = self.resblock("final_res_block.", x, cfg.nf, h, w, skip=x0, sc=cfg.nf)
         self.taps["final_res_block"] = x
-        self.conv("final_conv", x, cfg.nf, pk.final_w, None, h, w, bias=pk.final_b, out_nchw=self.out_noise)
+        if self.PAIR and pk.final_pair is not None and ops.pair_eligible(None, 64, cfg.nf, 0, w):
+            self.pair_conv("final_conv", x, pk.final_pair, None, h, w, bias=pk.final_b, out_nchw=self.out_noise)
+        else:
+            self.conv("final_conv", x, cfg.nf, pk.final_w, None, h, w, bias=pk.final_b, out_nchw=self.out_noise)
 
     # -------------------------------------------------------------- execution
     def set_inputs(self, xt, cond, text_context=None, image_context=None):

@@ -123,6 +123,23 @@ def test_conv3x3_pixel_pair(ops, gen, B, H, W, concat, mode):
     assert_close_bf16(nchw(out), y, f"pixel-pair conv3x3 {B}x{H}x{W} {cin}->64 {mode} {plan.info()}")
 
 
+@pytest.mark.parametrize("B,H,W,Hc,Wc", [(2, 32, 32, 32, 32), (1, 48, 64, 40, 57), (3, 16, 16, 16, 15), (1, 256, 256, 256, 256)])
+def test_final_conv_pixel_pair_nchw(ops, gen, B, H, W, Hc, Wc):
+    """final_conv (64 -> 3, fp32 NCHW output cropped to the un-padded image) in pixel-pair mode: N = 32 centre MMAs over
+    16-row weight blocks, two 16-column halves in the epilogue."""
+    x = nhwc(rnd(gen, B, 64, H, W))
+    w = rnd(gen, 3, 64, 3, 3, scale=(9 * 64) ** -0.5)
+    b = rnd(gen, 3)
+    out = torch.full((B, 3, Hc, Wc), float("nan"), device="cuda")
+    wp = ops.pack_conv_pair(torch.nn.functional.pad(w, (0, 0, 0, 0, 0, 0, 0, 13)))
+    plan = ops.PairConvPlan(x, wp, None, B=B, H=H, W=W, bias=b, out_nchw=out)
+    for _ in range(2):
+        plan.run()
+    torch.cuda.synchronize()
+    ref = F.conv2d(nchw(x), bf(w).float(), b, padding=1)[:, :, :Hc, :Wc]
+    assert (out - ref).abs().max().item() <= 2e-3 * max(1.0, ref.abs().max().item()), (out - ref).abs().max().item()
+
+
 @pytest.mark.parametrize("B,H,W,two", [(2, 32, 32, True), (3, 24, 40, False), (1, 256, 256, True), (2, 19, 34, True)])
 def test_conv3x3_pixel_pair_fused_skip(ops, gen, B, H, W, two):
     """Pixel-pair mode with the ResBlock's 1x1 res_conv fused as a second accumulator (even pixels -> first half of its

@@ -23,6 +23,8 @@ CASES = {
     "l0_pair_cat": (16, 256, 256, 128, 64, "pair"),
     "l1_pair": (16, 128, 128, 64, 64, "pair"),
     "l0_pair_plain": (16, 256, 256, 64, 64, "pair_plain"),
+    "l0_final_pair": (16, 256, 256, 64, 3, "final_pair"),
+    "l0_final": (16, 256, 256, 64, 3, "final"),
     "l0_pair_res": (16, 256, 256, 64, 64, "pair_res"),
     "l0_pair_skip": (16, 256, 256, 64, 64, "pair_skip"),
     "l0_3x3_skip": (16, 256, 256, 64, 64, "3x3_skip"),
@@ -60,6 +62,15 @@ def make(name):
         res = torch.randn(B, H, W, 64, device="cuda", generator=g).to(torch.bfloat16) if kind == "pair_res" else None
         plan = ops.PairConvPlan(x, ops.pack_conv_pair(w), out, B=B, H=H, W=W, act=L.ACT_SILU if res is not None else L.ACT_NONE,
                                 res=res)
+    elif kind in ("final", "final_pair"):
+        w = torch.randn(3, cin, 3, 3, device="cuda", generator=g) * (9 * cin) ** -0.5
+        b = torch.randn(3, device="cuda", generator=g)
+        o32 = torch.zeros(B, 3, H, W, device="cuda")
+        if kind == "final":
+            plan = ops.ConvPlan(x, cin, ops.pack_conv(w), None, B=B, H=H, W=W, bias=b, out_nchw=o32)
+        else:
+            plan = ops.PairConvPlan(x, ops.pack_conv_pair(torch.nn.functional.pad(w, (0, 0, 0, 0, 0, 0, 0, 13))), None,
+                                    B=B, H=H, W=W, bias=b, out_nchw=o32)
     elif kind == "pair":
         w = torch.randn(cout, cin, 3, 3, device="cuda", generator=g) * (9 * cin) ** -0.5
         film = torch.randn(B, 2 * cout, device="cuda", generator=g) * 0.1
