@@ -136,3 +136,37 @@ def test_irsde_host_tables_match_oracle():
         for a, b in zip(sde._posterior_coef(t), S.posterior_coeffs(s, t)):
             assert float(a) == float(b)
     assert sde.sample_scale == 1.0 and abs(sde.max_sigma - 50 / 255) < 1e-12
+
+
+def test_pixel_pair_packing_semantics():
+    """The pixel-pair schedule of the conv kernel (dac_conv_desc.pair), emulated on the CPU from the packed weight block:
+    on the [B, H, W/2, 2C] view, per (64-channel slice, ky) the even chunk multiplies rows [64,192) of the block at pair i
+    and rows [0,64) at pair i+1 (into the odd half), the odd chunk rows [0,128) at pair i and rows [128,192) at pair i-1
+    (into the even half) - together exactly the 3x3 convolution, for one source and for a two-source concat."""
+    from daclip_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    bfr = lambda t: t.to(torch.bfloat16).float()
+    B, H, W = 2, 6, 10
+    for cin in (64, 128):
+        x = bfr(torch.randn(B, cin, H, W, generator=g))
+        w = bfr(torch.randn(64, cin, 3, 3, generator=g) * 0.05)
+        wp = ops.pack_conv_pair(w).float()                      # [3][192][cin]
+        assert wp.shape == (3, 192, cin)
+        xp = F.pad(x.permute(0, 2, 3, 1), (0, 0, 2, 2, 1, 1))  # NHWC, two pixels = one pair of zero padding left and right
+        out = torch.zeros(B, H, W // 2, 128)
+        for s in range(cin // 64):
+            sl = slice(64 * s, 64 * s + 64)
+            for ky in range(3):
+                blk = wp[ky][:, sl]                             # [192][64]
+                rows = xp[:, ky:ky + H]                         # input row y + ky - 1
+                even = lambda d: rows[:, :, 2 + 2 * d:2 + 2 * d + W:2, sl]    # x[2(i + d)]
+                odd = lambda d: rows[:, :, 3 + 2 * d:3 + 2 * d + W:2, sl]     # x[2(i + d) + 1]
+                out += even(0) @ blk[64:192].T                  # N = 128: centre of 2i | left neighbour of 2i+1
+                out += odd(0) @ blk[0:128].T                    # N = 128: right neighbour of 2i | centre of 2i+1
+                out[..., :64] += odd(-1) @ blk[128:192].T       # N = 64: left neighbour of pixel 2i
+                out[..., 64:] += even(1) @ blk[0:64].T          # N = 64: right neighbour of pixel 2i+1
+        got = out.reshape(B, H, W, 64).permute(0, 3, 1, 2)      # the wide output IS the NHWC output
+        assert torch.allclose(got, F.conv2d(x, w, padding=1), atol=1e-4)
+    w3 = torch.randn(3, 64, 3, 3, generator=g)
+    wp = ops.pack_conv_pair(F.pad(w3, (0, 0, 0, 0, 0, 0, 0, 13)))
+    assert wp.shape == (3, 48, 64) and torch.equal(wp[1, 16:19].float(), bfr(w3[:, :, 1, 1]))
