@@ -170,3 +170,22 @@ def test_pixel_pair_packing_semantics():
     w3 = torch.randn(3, 64, 3, 3, generator=g)
     wp = ops.pack_conv_pair(F.pad(w3, (0, 0, 0, 0, 0, 0, 0, 13)))
     assert wp.shape == (3, 48, 64) and torch.equal(wp[1, 16:19].float(), bfr(w3[:, :, 1, 1]))
+
+
+def test_context_partial_slots_cover_every_image():
+    """dac_linattn_ctx_slots (no GPU needed: 148 SMs assumed without a device) against a brute-force walk of the kernels'
+    tile ranges: CTA b owns tiles [T b / G, T (b+1) / G); the slot count must cover the widest span of CTAs over any
+    image, for one record per CTA (k|v kernel) and two (KVCTX epilogue groups)."""
+    from daclip_b200 import lib as L
+    lib = L.load()
+    for B, tpi in [(16, 512), (16, 32), (1, 512), (1, 3), (5, 37), (40, 1), (16, 18), (3, 2048), (128, 8)]:
+        T = B * tpi
+        G = min(T, 148)
+        owner = []
+        for b in range(G):
+            owner += [b] * (T * (b + 1) // G - T * b // G)
+        assert len(owner) == T
+        span = max(owner[(i + 1) * tpi - 1] - owner[i * tpi] + 1 for i in range(B))
+        assert lib.dac_linattn_ctx_slots(B, tpi, 1) == span, (B, tpi)
+        assert lib.dac_linattn_ctx_slots(B, tpi, 2) == 2 * span
+    assert lib.dac_linattn_ctx_slots(0, 4, 1) == 0
