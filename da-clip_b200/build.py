@@ -18,11 +18,47 @@ NVCC_FLAGS = [
 ]
 
 
+STAMP = LIB + ".srchash"      # content hash of the sources the library was built from (git-ignored, travels with the .so)
+OBJDIR = os.path.join(HERE, "build")
+
+
+def _hash(files, extra=""):
+    import hashlib
+    h = hashlib.sha256((" ".join(NVCC_FLAGS) + extra).encode())
+    for f in files:
+        with open(os.path.join(CSRC, f), "rb") as fh:
+            h.update(f.encode() + b"\0" + fh.read())
+    return h.hexdigest()
+
+
+def source_hash():
+    """sha256 over every source, header and the compiler flags: staleness is decided by CONTENT, not by mtimes (a repo
+    snapshot copied to the GPU box carries arbitrary mtimes)."""
+    return _hash(SOURCES + HEADERS)
+
+
 def _stale():
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(STAMP):
         return True
-    t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
+    with open(STAMP) as fh:
+        return fh.read().strip() != source_hash()
+
+
+def _compile_one(nvcc, src, verbose):
+    """One translation unit -> build/<src>.o, skipped when its own content hash (source + all headers) is unchanged."""
+    obj = os.path.join(OBJDIR, src + ".o")
+    want = _hash([src] + HEADERS)
+    stamp = obj + ".srchash"
+    if os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read().strip() == want:
+        return obj, ""
+    flags = [f for f in NVCC_FLAGS if f != "--shared"]
+    cmd = [nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}{r.stderr}")
+    with open(stamp, "w") as fh:
+        fh.write(want + "\n")
+    return obj, r.stderr
 
 
 def build(force=False, verbose=False, debug=False):
@@ -30,15 +66,25 @@ def build(force=False, verbose=False, debug=False):
         return _build_debug()
     if not force and not _stale():
         return LIB
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-        [os.path.join(CSRC, f) for f in SOURCES] + ["-o", LIB]
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    os.makedirs(OBJDIR, exist_ok=True)
+    if force:
+        for f in os.listdir(OBJDIR):
+            os.remove(os.path.join(OBJDIR, f))
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as ex:
+        results = list(ex.map(lambda s: _compile_one(nvcc, s, verbose), SOURCES))
+    if verbose:
+        sys.stderr.write("".join(log for _, log in results))
+    tmp = LIB + f".tmp{os.getpid()}"
+    r = subprocess.run([nvcc, "--shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a"]
+                       + [o for o, _ in results] + ["-o", tmp], capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
-        raise RuntimeError("nvcc failed building libdac_b200.so")
-    if verbose:
-        sys.stderr.write(r.stderr)
+        raise RuntimeError("nvcc failed linking libdac_b200.so")
+    os.replace(tmp, LIB)          # atomic: concurrent ranks never dlopen a half-written library
+    with open(STAMP, "w") as fh:
+        fh.write(source_hash() + "\n")
     return LIB
 
 

@@ -176,25 +176,31 @@ class DaCLIP(nn.Module):
 
     # ------------------------------------------------------------------ public API (daclip_model.py:46-55)
     def encode_image(self, image, control=False, normalize=False):
-        if not control:
-            raise NotImplementedError("the restoration path always calls encode_image(control=True)")
-        L.require_cuda(image)
-        B = image.shape[0]
+        """control=True: (image_features, degra_features) (daclip_model.py:47-52); control=False: the frozen CLIP tower
+        alone, `self.clip.encode_image(image, normalize)` -> image_features (daclip_model.py:53-54, model.py:232-235)."""
         dev = self.visual.proj.device
-        if dev.type != "cuda":
-            raise L.DacError("DaCLIP (daclip_b200) runs on CUDA only")
-        if self._packed is None:
-            self._packed = _PackedDaCLIP(self)
-        if B not in self._engines:
-            self._engines[B] = _EncodeEngine(self._packed, self.visual, B, dev)
-        eng = self._engines[B]
-        eng.image.copy_(image.to(torch.float32))
-        eng.replay()
-        img_f, deg_f = eng.image_features.clone(), eng.degra_features.clone()
-        if normalize:
-            img_f = torch.nn.functional.normalize(img_f, dim=-1)      # plumbing on [B,512] outputs
-            deg_f = torch.nn.functional.normalize(deg_f, dim=-1)
-        return img_f, deg_f
+        if dev.type != "cuda" or not image.is_cuda:
+            raise L.DacError("DaCLIP (daclip_b200) runs on CUDA only (no CPU fallback)")
+        B = image.shape[0]
+        with L.on_device(dev):
+            L.require_cuda(image)
+            if self._packed is None:
+                self._packed = _PackedDaCLIP(self)
+            key = (B, bool(control))
+            if key not in self._engines:
+                self._engines[key] = _EncodeEngine(self._packed, self.visual, B, dev, control=bool(control))
+            eng = self._engines[key]
+            eng.image.copy_(image.to(torch.float32))
+            eng.replay()
+            img_f = eng.image_features.clone()
+            if normalize:
+                img_f = torch.nn.functional.normalize(img_f, dim=-1)      # plumbing on [B,512] outputs
+            if not control:
+                return img_f
+            deg_f = eng.degra_features.clone()
+            if normalize:
+                deg_f = torch.nn.functional.normalize(deg_f, dim=-1)
+            return img_f, deg_f
 
     def encode_text(self, text, normalize=False):
         """CLIP.encode_text (model.py:237-249) through DaCLIP.encode_text (daclip_model.py:55-56): text = int64 token ids
@@ -209,24 +215,27 @@ class DaCLIP(nn.Module):
         if text.numel() and (int(text.min()) < 0 or int(text.max()) >= self.vocab_size):
             raise IndexError("index out of range in self")        # what nn.Embedding raises in the reference
         N = text.shape[0]
-        if self._packed_text is None:
-            self._packed_text = _PackedText(self.clip)
-        if N not in self._text_engines:
-            self._text_engines[N] = _TextEngine(self._packed_text, self.clip, N, dev)
-        eng = self._text_engines[N]
-        eng.tokens.copy_(text.to(device=dev, dtype=torch.int64))
-        eng.replay()
-        f = eng.features.clone()
+        with L.on_device(dev):
+            if self._packed_text is None:
+                self._packed_text = _PackedText(self.clip)
+            if N not in self._text_engines:
+                self._text_engines[N] = _TextEngine(self._packed_text, self.clip, N, dev)
+            eng = self._text_engines[N]
+            eng.tokens.copy_(text.to(device=dev, dtype=torch.int64))
+            eng.replay()
+            f = eng.features.clone()
         return torch.nn.functional.normalize(f, dim=-1) if normalize else f
 
     def degradation_argmax(self, degra_features, text_features, return_logits=False):
         """argmax_j softmax(100 * cos(degra, text_j)) (da-clip/src/evaluate_daclip.py:46-47,79-81)."""
-        L.require_cuda(degra_features, text_features)
-        d = degra_features.to(torch.float32).contiguous()
-        t = text_features.to(device=d.device, dtype=torch.float32).contiguous()
-        logits = torch.empty(d.shape[0], t.shape[0], device=d.device)
-        am = torch.empty(d.shape[0], dtype=torch.int64, device=d.device)
-        ops.degradation_argmax(d, t, logits, am)
+        if not degra_features.is_cuda:
+            raise L.DacError("degradation_argmax takes CUDA tensors only (no CPU fallback)")
+        with L.on_device(degra_features):
+            d = degra_features.to(torch.float32).contiguous()
+            t = text_features.to(device=d.device, dtype=torch.float32).contiguous()
+            logits = torch.empty(d.shape[0], t.shape[0], device=d.device)
+            am = torch.empty(d.shape[0], dtype=torch.int64, device=d.device)
+            ops.degradation_argmax(d, t, logits, am)
         return (am, logits) if return_logits else am
 
 
@@ -284,9 +293,10 @@ class _PackedDaCLIP:
 
 
 class _EncodeEngine:
-    """Launch plan of encode_image(control=True) for a fixed batch, captured in one CUDA graph."""
+    """Launch plan of encode_image for a fixed batch, captured in one CUDA graph: control=True = the control tower
+    followed by the CLIP tower that consumes its hidden states; control=False = the CLIP tower alone."""
 
-    def __init__(self, pk: _PackedDaCLIP, vit, B, dev):
+    def __init__(self, pk: _PackedDaCLIP, vit, B, dev, control=True):
         self.B, self.dev = B, dev
         S, p, w, heads = vit.image_size, vit.patch, vit.width, vit.heads
         g = S // p
@@ -302,7 +312,7 @@ class _EncodeEngine:
         self.add(lambda: ops.vit_patchify(self.image, patches, B, S, p))
         hiddens = []
 
-        def tower(tp, out_features, control_in=None):
+        def tower(tp, out_features, control_in=None, plain=False):
             pe = torch.zeros(1, 1, B * g * g, w, **bf)
             self.conv(patches, kpad, tp.conv1, pe, B * g * g)
             x = torch.zeros(1, 1, M, w, **f32)
@@ -318,7 +328,9 @@ class _EncodeEngine:
                 self.conv(att, w, blk["out"], None, M, bias=blk["out_b"], res_f32=x, out_f32=x)
                 self.add(lambda blk=blk: ops.layernorm_rows_f32(x, n, M, w, blk["ln2"][0], blk["ln2"][1], 1e-5))
                 self.conv(n, w, blk["fc"], hid, M, bias=blk["fc_b"], act=L.ACT_GELU)
-                if control_in is None:
+                if plain:
+                    self.conv(hid, 4 * w, blk["proj"], None, M, bias=blk["proj_b"], res_f32=x, out_f32=x)
+                elif control_in is None:
                     # control tower: x <- x + mlp; also keep a bf16 copy as the zero-linear's GEMM operand
                     xb = torch.zeros(1, 1, M, w, **bf)
                     self.conv(hid, 4 * w, blk["proj"], xb, M, bias=blk["proj_b"], res_f32=x, out_f32=x)
@@ -331,9 +343,12 @@ class _EncodeEngine:
                               res2=control_in[len(tp.blocks) - 1 - i])
             self.add(lambda: ops.vit_pool(x, B, Ltok, w, tp.ln_post[0], tp.ln_post[1], tp.proj, out_features))
 
-        tower(pk.control, self.degra_features)
-        tower(pk.clip, self.image_features, control_in=hiddens)
-        self.flops += 2 * 4.0 * B * heads * Ltok * Ltok * (w // heads) * len(pk.clip.blocks)
+        if control:
+            tower(pk.control, self.degra_features)
+            tower(pk.clip, self.image_features, control_in=hiddens)
+        else:
+            tower(pk.clip, self.image_features, plain=True)
+        self.flops += (2 if control else 1) * 4.0 * B * heads * Ltok * Ltok * (w // heads) * len(pk.clip.blocks)
         self.graph = None
 
     def add(self, fn):

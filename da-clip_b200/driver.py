@@ -41,8 +41,12 @@ class BatchedRestorer:
         for (h, w), idx in groups.items():
             for s in range(0, len(idx), self.max_batch):
                 chunk = idx[s:s + self.max_batch]
-                self._restore_group([lq_images[i] for i in chunk], chunk, results,
-                                    None if noise is None else noise.get((h, w)))
+                nz = None if noise is None else noise.get((h, w))
+                if nz is not None:
+                    if nz.shape[1] != len(idx):
+                        raise ValueError(f"noise for size {(h, w)} has {nz.shape[1]} images, the group has {len(idx)}")
+                    nz = nz[:, s:s + len(chunk)].contiguous()      # this chunk's rows of the group's [T, B, 3, H, W]
+                self._restore_group([lq_images[i] for i in chunk], chunk, results, nz)
         return results
 
     @torch.no_grad()

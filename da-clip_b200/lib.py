@@ -119,8 +119,8 @@ def load(build_if_missing=True):
     path = _build.LIB
     if os.environ.get("DAC_DEBUG") == "1":
         path = _build.build(debug=True)
-    if build_if_missing and not os.path.exists(path):
-        _build.build()
+    if build_if_missing:
+        _build.build()       # no-op when the library matches the content hash of csrc/ (never runs a stale binary)
     if not os.path.exists(path):
         raise DacError(f"{path} is missing: run `python __graft_entry__.py build` (nvcc, sm_100a)")
     lib = C.CDLL(path)
@@ -143,11 +143,27 @@ def check(rc):
 
 
 def require_cuda(*tensors):
+    """Every tensor handed to a kernel must live on the CURRENT CUDA device: launches, TMA descriptor encodes and the
+    stream from stream_ptr() all target it.  Entry points switch to their tensors' device first (on_device)."""
     if not torch.cuda.is_available():
         raise DacError("daclip_b200 needs a CUDA device: there is no CPU fallback for this path")
+    cur = torch.cuda.current_device()
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise DacError("daclip_b200 kernels take CUDA tensors only (no CPU fallback)")
+        if t.device.index != cur:
+            raise DacError(f"tensor on cuda:{t.device.index} but the current device is cuda:{cur}: "
+                           f"wrap the call in `with torch.cuda.device({t.device.index})`")
+
+
+def on_device(dev):
+    """Context manager making `dev` (a torch.device / tensor / index) the current CUDA device, as PyTorch ops do
+    implicitly for their arguments; a no-op for the device that is already current."""
+    if torch.is_tensor(dev):
+        dev = dev.device
+    return torch.cuda.device(dev)
 
 
 def stream_ptr():

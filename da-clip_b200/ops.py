@@ -403,14 +403,29 @@ def _coef(vals):
     return arr
 
 
+def _same_fp32(what, ref, *tensors):
+    """Raw-pointer kernels: every operand must be fp32, contiguous, on one device and exactly as large as the state."""
+    for name, t in tensors:
+        if t is None:
+            continue
+        if t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != ref.numel() or t.device != ref.device:
+            raise L.DacError(f"{what}: `{name}` must be a contiguous fp32 tensor of {ref.numel()} elements on {ref.device} "
+                             f"(got {t.dtype}, {tuple(t.shape)}, {t.device}, contiguous={t.is_contiguous()})")
+
+
 def sde_step(mode, x, mu, net, eps, out, coef):
-    L.require_cuda(x, mu, net, out)
+    """out = one reverse step from x (out may alias x: each element is read before it is written)."""
+    L.require_cuda(x, mu, net, eps, out)
+    _same_fp32("sde_step", x, ("x", x), ("mu", mu), ("net", net), ("eps", eps), ("out", out))
+    if mode != 2 and eps is None:
+        raise L.DacError("sde_step: the sde / posterior updates need a noise tensor")
     L.check(L.load().dac_sde_step(mode, L.ptr(x), L.ptr(mu), L.ptr(net), L.ptr(eps), L.ptr(out), x.numel(),
                                   _coef(coef), L.stream_ptr()))
 
 
 def noise_state(x, eps, out, max_sigma):
     L.require_cuda(x, eps, out)
+    _same_fp32("noise_state", x, ("x", x), ("eps", eps), ("out", out))
     L.check(L.load().dac_noise_state(L.ptr(x), L.ptr(eps), L.ptr(out), x.numel(), float(max_sigma), L.stream_ptr()))
 
 

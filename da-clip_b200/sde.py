@@ -126,12 +126,21 @@ class IRSDE:
 
     def _step_from_noise(self, mode, x, net, t, eps=None, out=None):
         """x' from the network's noise prediction; one kernel launch."""
-        x = x.contiguous()
+        if not x.is_cuda:
+            raise ops.L.DacError("IRSDE (daclip_b200) updates CUDA tensors only (no CPU fallback)")
+        with ops.L.on_device(x):
+            return self._step_from_noise_on_device(mode, x, net, t, eps, out)
+
+    def _step_from_noise_on_device(self, mode, x, net, t, eps, out):
+        x = x.contiguous().float()
+        net = net.float()
         out = torch.empty_like(x) if out is None else out
         if mode == "posterior":
-            ops.sde_step(1, x, self._mu_like(x), net.contiguous(), self._draw(x, eps), out, self._posterior_coef(t))
+            ops.sde_step(1, x, self._mu_like(x), net.contiguous(), self._draw(x, eps).contiguous(), out,
+                         self._posterior_coef(t))
         elif mode == "sde":
-            ops.sde_step(0, x, self._mu_like(x), net.contiguous(), self._draw(x, eps), out, self._sde_coef(t))
+            ops.sde_step(0, x, self._mu_like(x), net.contiguous(), self._draw(x, eps).contiguous(), out,
+                         self._sde_coef(t))
         else:
             ops.sde_step(2, x, self._mu_like(x), net.contiguous(), None, out, self._sde_coef(t, half=True))
         return out
@@ -140,17 +149,23 @@ class IRSDE:
         # score = -noise / sigma_bar  <=>  "noise" = score with sigma_bar = -1 (negation and /(-1) are exact)
         coef = self._sde_coef(t)
         coef[2] = -1.0
-        x = x.contiguous()
-        out = torch.empty_like(x)
-        ops.sde_step(0, x, self._mu_like(x), score.contiguous(), self._draw(x, eps), out, coef)
+        if not x.is_cuda:
+            raise ops.L.DacError("IRSDE (daclip_b200) updates CUDA tensors only (no CPU fallback)")
+        with ops.L.on_device(x):
+            x = x.contiguous().float()
+            out = torch.empty_like(x)
+            ops.sde_step(0, x, self._mu_like(x), score.contiguous().float(), self._draw(x, eps).contiguous(), out, coef)
         return out
 
     def reverse_ode_step(self, x, score, t):
         coef = self._sde_coef(t, half=True)
         coef[2] = -1.0
-        x = x.contiguous()
-        out = torch.empty_like(x)
-        ops.sde_step(2, x, self._mu_like(x), score.contiguous(), None, out, coef)
+        if not x.is_cuda:
+            raise ops.L.DacError("IRSDE (daclip_b200) updates CUDA tensors only (no CPU fallback)")
+        with ops.L.on_device(x):
+            x = x.contiguous().float()
+            out = torch.empty_like(x)
+            ops.sde_step(2, x, self._mu_like(x), score.contiguous().float(), None, out, coef)
         return out
 
     def reverse_posterior_step(self, xt, noise, t, eps=None):
@@ -159,11 +174,16 @@ class IRSDE:
     def noise_state(self, tensor):
         """x_T = LQ + N(0,1) * max_sigma (sde_utils.py:374-375).  The draw uses the input's device RNG like the
         reference; the arithmetic runs on the GPU and the result returns on the input's device."""
-        eps = torch.randn_like(tensor)
-        dev = self.device if self.device is not None else "cuda"
-        x = tensor.to(dev, torch.float32).contiguous()
-        out = torch.empty_like(x)
-        ops.noise_state(x, eps.to(dev, torch.float32).contiguous(), out, self.max_sigma)
+        return self._noise_state(tensor, torch.randn_like(tensor))
+
+    def _noise_state(self, tensor, eps):
+        dev = torch.device(self.device if self.device is not None else "cuda")
+        if dev.type != "cuda":
+            raise ops.L.DacError("IRSDE (daclip_b200) needs a CUDA device (no CPU fallback)")
+        with ops.L.on_device(dev):
+            x = tensor.to(dev, torch.float32).contiguous()
+            out = torch.empty_like(x)
+            ops.noise_state(x, eps.to(dev, torch.float32).contiguous(), out, self.max_sigma)
         return out.to(tensor.device)
 
     # ------------------------------------------------------------------ loops (sde_utils.py:261-313)
@@ -193,6 +213,10 @@ class IRSDE:
     def _reverse_fused(self, net, mode, xt, T, save_states, save_dir, noise, kwargs):
         """Hot loop: the state lives in the engine's static buffer; per step = one CUDA-graph replay of the
         denoiser plus one in-place fused update kernel.  No per-step allocation, copy or host sync."""
+        with ops.L.on_device(xt):
+            return self._reverse_fused_on_device(net, mode, xt, T, save_states, save_dir, noise, kwargs)
+
+    def _reverse_fused_on_device(self, net, mode, xt, T, save_states, save_dir, noise, kwargs):
         B, _, H, W = xt.shape
         eng = net.engine(B, H, W)
         eng.set_inputs(xt, self.mu, kwargs.get("text_context"), kwargs.get("image_context"))

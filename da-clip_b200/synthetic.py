@@ -61,7 +61,20 @@ def unet_state_dict(seed=0, stabilize=True, **ctor):
     sd = randomize_state_dict({k: v.shape for k, v in m.state_dict().items()}, seed)
     if stabilize:
         _add_denoiser_path(sd, kw["nf"])
+    if "prompt" in sd:
+        _amplify_prompt_path(sd)
     return sd, kw
+
+
+def _amplify_prompt_path(sd, prompt_gain=64.0, logit_gain=4.0):
+    """Make the degradation-prompt path numerically visible.  With default-style random weights
+    `softmax(text_mlp(text_context)) * prompt` (arch.py:134-137) is ~1/256 per entry, so swapping text_context moved a
+    64x64 prediction by 6e-4 (image_context: 0.19) and a wiring bug on that path would pass every end-to-end check.
+    A peakier softmax (x4 logits) and a larger learned prompt (x64) give the path the weight a trained prompt has:
+    swapping text_context now moves the prediction by ~0.4 (measured with the oracle; tests assert >= 5e-2)."""
+    sd["prompt"] *= prompt_gain
+    sd["text_mlp.2.weight"] *= logit_gain
+    sd["text_mlp.2.bias"] *= logit_gain
 
 
 def _add_denoiser_path(sd, nf, gain=5.1, random_scale=0.05):

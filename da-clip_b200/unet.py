@@ -10,6 +10,7 @@ and replays it.  No CPU fallback.
 """
 import math
 import os
+from collections import OrderedDict
 
 import torch
 import torch.nn as nn
@@ -111,8 +112,10 @@ class _Residual(_Holder):  # module_util.py:27-33
 
 
 class UNetConfig:
-    def __init__(self, in_nc, out_nc, nf, ch_mult, context_dim, use_degra_context, use_image_context, scale=1):
+    def __init__(self, in_nc, out_nc, nf, ch_mult, context_dim, use_degra_context, use_image_context, scale=1,
+                 wild=False):
         self.scale = scale
+        self.wild = wild
         self.in_nc, self.out_nc, self.nf = in_nc, out_nc, nf
         self.ch_mult = list(ch_mult)
         self.depth = len(self.ch_mult)
@@ -125,7 +128,9 @@ class UNetConfig:
         self.transformer = use_image_context and self.context_dim > 0
 
     def level_is_transformer(self, i):
-        return self.transformer and i >= 3        # arch.py:77-82
+        # daclip-sde: `i < 3` keeps LinearAttention (arch.py:78-80); the wild-ir class tests `i < depth - 1`
+        # (config/wild-ir/.../DenoisingUNet_arch.py:83-84) - the two differ for depth != 4
+        return self.transformer and i >= (self.depth - 1 if self.wild else 3)
 
     def resblocks(self):
         """(state-dict prefix, cin, cout) of every ResBlock, in FiLM-table order."""
@@ -146,11 +151,13 @@ class ConditionalUNet(nn.Module):
     resolution between an extra Downsample(nf, nf) and Upsample(nf, nf))."""
 
     def __init__(self, in_nc, out_nc, nf, ch_mult=[1, 2, 4, 4], context_dim=512, use_degra_context=True,
-                 use_image_context=False, upscale=1, scale=1):
+                 use_image_context=False, upscale=1, scale=None):
         super().__init__()
+        wild = scale is not None          # only the wild-ir class has a `scale` argument (daclip-sde: `upscale`, unused)
+        scale = 1 if scale is None else scale
         if scale not in (1, 0.5):
             raise NotImplementedError("scale must be 1 or 0.5 (the reference only builds the resamplers for 0.5)")
-        cfg = UNetConfig(in_nc, out_nc, nf, ch_mult, context_dim, use_degra_context, use_image_context, scale)
+        cfg = UNetConfig(in_nc, out_nc, nf, ch_mult, context_dim, use_degra_context, use_image_context, scale, wild)
         if in_nc != 3 or out_nc != 3 or nf != 64:
             raise NotImplementedError("the sm_100a engine is built for in_nc=out_nc=3, nf=64 (options/test.yml)")
         self.cfg = cfg
@@ -191,14 +198,20 @@ class ConditionalUNet(nn.Module):
         self.final_res_block = _ResBlock(nf * 2, nf, td)
         self.final_conv = nn.Conv2d(nf, out_nc, 3, 1, 1)
         self._packed = None
-        self._engines = {}
+        self._engines = OrderedDict()
         self.register_load_state_dict_post_hook(lambda m, keys: m.invalidate())
 
     # ------------------------------------------------------------------ engine management
+    # Launch plans kept alive, least recently used first out.  One engine owns every activation buffer, the TMA plans
+    # and a CUDA graph for its (batch, H, W): ~0.2 GB at batch 1 256^2, ~3 GB at batch 16 256^2; a new size costs a plan
+    # build + warm-up + capture (~0.3 s).  A dataset of many distinct native sizes (the reference's test loop feeds
+    # them one by one) therefore recycles MAX_ENGINES slots instead of growing until the GPU is full.
+    MAX_ENGINES = int(os.environ.get("DAC_MAX_ENGINES", "4"))
+
     def invalidate(self):
         """Drop repacked weights and launch plans (call after changing parameters in place)."""
         self._packed = None
-        self._engines = {}
+        self._engines = OrderedDict()
 
     def _apply(self, fn, *a, **k):
         self.invalidate()
@@ -211,18 +224,27 @@ class ConditionalUNet(nn.Module):
         if self._packed is None:
             self._packed = PackedUNet({k: v.detach() for k, v in self.state_dict().items()}, self.cfg, dev)
         key = (B, H, W)
-        if key not in self._engines:
-            self._engines[key] = UNetEngine(self._packed, self.cfg, B, H, W, dev)
+        with L.on_device(dev):
+            if key in self._engines:
+                self._engines.move_to_end(key)
+            else:
+                while len(self._engines) >= max(1, self.MAX_ENGINES):
+                    _, old = self._engines.popitem(last=False)
+                    old.release()
+                self._engines[key] = UNetEngine(self._packed, self.cfg, B, H, W, dev)
         return self._engines[key]
 
     def forward(self, xt, cond, time, text_context=None, image_context=None):
-        L.require_cuda(xt, cond)
+        if not (torch.is_tensor(xt) and xt.is_cuda):
+            raise L.DacError("ConditionalUNet (daclip_b200) takes CUDA tensors only (no CPU fallback)")
         B, _, H, W = xt.shape
-        eng = self.engine(B, H, W)
-        eng.set_inputs(xt, cond, text_context, image_context)
-        eng.set_time(time)
-        eng.replay()
-        return eng.out_noise.clone()
+        with L.on_device(xt):
+            L.require_cuda(xt, cond if torch.is_tensor(cond) else None)
+            eng = self.engine(B, H, W)
+            eng.set_inputs(xt, cond, text_context, image_context)
+            eng.set_time(time)
+            eng.replay()
+            return eng.out_noise.clone()
 
 
 # ------------------------------------------------------------------------------------------------ packed weights
@@ -684,10 +706,22 @@ class UNetEngine:
             fn()
 
     def set_time(self, time):
+        """One time for the whole batch (what the samplers pass: a python float, sde_utils.py:197)."""
         if torch.is_tensor(time):
-            self.t_dev.copy_(time.reshape(-1)[:1])
+            flat = time.reshape(-1)
+            if flat.numel() > 1 and not bool((flat == flat[0]).all()):
+                raise NotImplementedError("per-image time steps: the FiLM table is built for one time per batch "
+                                          "(the reference's samplers always pass a scalar)")
+            self.t_dev.copy_(flat[:1])
         else:
             self.t_dev.fill_(float(time))
+
+    def release(self):
+        """Drop the graph, the plans (their destructors free the C-side handles) and every buffer (LRU eviction)."""
+        self.graph = None
+        self.steps, self.pre_steps, self.taps = [], [], {}
+        for k in ("xt", "cond", "out_noise", "film", "temb", "prompt_emb", "text_ctx", "image_ctx"):
+            setattr(self, k, None)
 
     def run_eager(self):
         for _, fn in self.steps:

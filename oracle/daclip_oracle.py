@@ -77,6 +77,16 @@ def encode_image_control(sd, image, cfg: ViTConfig = None, taps=None):
     return _pool(sd, pv, cfg, x), degra
 
 
+def encode_image_plain(sd, image, cfg: ViTConfig = None):
+    """encode_image(control=False) = CLIP.encode_image: the frozen tower alone (daclip_model.py:53-54, model.py:232-235)."""
+    cfg = cfg or ViTConfig()
+    pv = "visual."
+    x = _stem(sd, pv, cfg, image)
+    for i in range(cfg.layers):
+        x = _res_attn_block(sd, f"{pv}transformer.resblocks.{i}.", cfg, x)
+    return _pool(sd, pv, cfg, x)
+
+
 def encode_text(sd, text, heads=8, prefix="clip."):
     """CLIP.encode_text (open_clip/model.py:237-249): token + positional embedding, the ResidualAttentionBlock chain
     under the causal mask of build_attention_mask (tr.py:629-635), ln_final, the row of each prompt's end-of-text token

@@ -102,6 +102,33 @@ def gen_reduced_step():
     print("sampler_reduced.pt written", out["sde"].abs().max().item(), out["posterior"].abs().max().item())
 
 
+def gen_trajectory_128():
+    """Full T=100 reverse_sde / reverse_posterior of the reference at 128x128 (B = 1): every level is large enough
+    for the production kernels (LinearAttention at 128^2 / 64^2 / 32^2 pixels, 256-token self-attention), unlike the
+    32x32 trajectory of unet_sampler.pt."""
+    from models.modules.DenoisingUNet_arch import ConditionalUNet
+    from utils.sde_utils import IRSDE
+    sd, kw = synthetic.unet_state_dict(0)
+    net = ConditionalUNet(**kw)
+    net.load_state_dict(sd, strict=True)
+    net.eval()
+    T = 100
+    inp = synthetic.restoration_inputs(1, 128, 128, T=T, seed=13)
+    sde = IRSDE(max_sigma=50, T=T, schedule="cosine", eps=0.005, device="cpu")
+    sde.set_model(net)
+    sde.set_mu(inp["lq"])
+    x_T = inp["lq"] + inp["eps0"] * sde.max_sigma
+    out = dict(seed=13, shape=(1, 128, 128), T=T, weights_seed=0)
+    with torch.no_grad():
+        for mode in ("sde", "posterior"):
+            it = iter(inp["noise"])
+            with um.patch("torch.randn_like", lambda t: next(it)):
+                fn = sde.reverse_sde if mode == "sde" else sde.reverse_posterior
+                out[mode] = fn(x_T, text_context=inp["text_context"], image_context=inp["image_context"])
+    torch.save(out, os.path.join(GOLD, "trajectory_128.pt"))
+    print("trajectory_128.pt written", out["sde"].abs().max().item(), out["posterior"].abs().max().item())
+
+
 def gen_daclip():
     sys.modules.setdefault("ftfy", types.SimpleNamespace(fix_text=lambda s: s))
     import open_clip
@@ -124,12 +151,13 @@ def gen_daclip():
     with torch.no_grad():
         text_features = model.encode_text(tok(DISTORTIONS))
         image_features, degra_features = model.encode_image(image, control=True)
+        plain_features = model.encode_image(image, control=False)       # daclip_model.py:53-54: the CLIP tower alone
         d = degra_features / degra_features.norm(dim=-1, keepdim=True)
         t = text_features / text_features.norm(dim=-1, keepdim=True)
         probs = (100.0 * d @ t.T).softmax(dim=-1)       # evaluate_daclip.py:79-80
         pred = torch.argmax(probs, dim=-1)
     torch.save(dict(weights_seed=10, image_seed=4, text_features=text_features, image_features=image_features,
-                    degra_features=degra_features, logits=100.0 * d @ t.T, argmax=pred),
+                    degra_features=degra_features, plain_features=plain_features, logits=100.0 * d @ t.T, argmax=pred),
                os.path.join(GOLD, "daclip.pt"))
     print("daclip.pt written; argmax", pred.tolist(), "top-2 gap",
           (probs.topk(2).values[:, 0] - probs.topk(2).values[:, 1]).tolist())
@@ -203,6 +231,8 @@ if __name__ == "__main__":
         gen_daclip()
     if "reduced" in which:
         gen_reduced_step()
+    if "traj128" in which:
+        gen_trajectory_128()
     if "daclip_l14" in which:
         gen_daclip_l14()
     if "daclip_text" in which:

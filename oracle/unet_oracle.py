@@ -20,10 +20,11 @@ class UNetConfig:
     """Constructor arguments of ConditionalUNet (arch.py:22-23) + derived dims."""
 
     def __init__(self, in_nc=3, out_nc=3, nf=64, ch_mult=(1, 2, 4, 8), context_dim=512,
-                 use_degra_context=True, use_image_context=True, upscale=1, scale=1):
+                 use_degra_context=True, use_image_context=True, upscale=1, scale=None):
         # `scale` is the wild-ir variant's argument (config/wild-ir/models/modules/DenoisingUNet_arch.py:22-40): 0.5 adds
         # a Downsample(nf, nf) after init_conv and an Upsample(nf, nf) before the final concat
-        self.scale = scale
+        self.wild = scale is not None                      # only the wild-ir class takes `scale`
+        self.scale = 1 if scale is None else scale
         self.in_nc, self.out_nc, self.nf = in_nc, out_nc, nf
         self.ch_mult = list(ch_mult)
         self.depth = len(self.ch_mult)
@@ -40,8 +41,9 @@ class UNetConfig:
         return self.use_image_context and self.context_dim > 0
 
     def level_is_transformer(self, i):
-        # arch.py:77-82: SpatialTransformer only at i >= 3, LinearAttention elsewhere
-        return self.spatial_transformer and i >= 3
+        # arch.py:77-82: SpatialTransformer only at i >= 3, LinearAttention elsewhere; the wild-ir class tests
+        # i >= depth - 1 instead (config/wild-ir/models/modules/DenoisingUNet_arch.py:83-84)
+        return self.spatial_transformer and i >= (self.depth - 1 if self.wild else 3)
 
 
 def silu(x):

@@ -68,7 +68,9 @@ def test_batched_driver_matches_per_image_loop(cuda, stack):
         got = res[i]
         assert got["Output"].shape == (sizes[i][0], sizes[i][1], 3) and got["Output"].dtype == np.uint8
         err = (got["Output_tensor"] - o).abs().max().item()
-        assert err < 4e-3, f"image {i}: batched vs single max err {err}"       # GroupNorm fp32 atomics order
+        # batch 1 and batch 3 pick different tile -> CTA assignments, i.e. different fp32 summation orders of the
+        # LinearAttention context partials and GroupNorm slabs (each deterministic): not bit-equal, but close
+        assert err < 4e-3, f"image {i}: batched vs single max err {err}"
         assert np.abs(got["Output"].astype(int) - u8.astype(int)).max() <= 1
         assert got["degradation"] == cls
 

@@ -36,8 +36,22 @@ def psnr(a, b):
     return 99.0 if mse == 0 else 10 * math.log10(1.0 / mse)
 
 
+_ACHIEVED = {}
+
+
 def rel_err(got, ref):
-    return (got - ref).abs().max().item() / max(ref.abs().max().item(), 1e-6)
+    """max |got - ref| / max |ref|; every value is also logged per calling test (gpurun_out/unet_errors.json), which is
+    where the bounds below come from: 2x the worst value measured on a B200."""
+    import inspect
+    import json
+    e = (got - ref).abs().max().item() / max(ref.abs().max().item(), 1e-6)
+    who = inspect.stack()[1].function
+    _ACHIEVED[who] = max(_ACHIEVED.get(who, 0.0), e)
+    out = os.path.join(os.path.dirname(GOLD), "..", "gpurun_out")
+    if os.path.isdir(out):
+        with open(os.path.join(out, "unet_errors.json"), "w") as f:
+            json.dump(_ACHIEVED, f, indent=1, sort_keys=True)
+    return e
 
 
 def test_forward_vs_reference_golden_padded(model, gold):
@@ -130,8 +144,8 @@ def test_full_trajectory_vs_reference_golden(model, gold, cuda, mode):
     # the generic (non-fused) loop - any callable as the model - must agree with the fused one
     sde.set_model(lambda x_, mu, t, **kw: m(x_, mu, t, **kw))
     x2 = fn(x_T, noise=inp["noise"], text_context=inp["text_context"], image_context=inp["image_context"]).cpu()
-    # (not bit-identical: GroupNorm statistics are reduced with fp32 atomics, whose order varies run to run)
-    assert (x2 - x).abs().max().item() < 2e-3
+    # (same kernels, same order: the eager per-step path and the fused loop agree bit for bit - no atomics anywhere)
+    assert torch.equal(x2, x), (x2 - x).abs().max().item()
 
 
 def test_trajectory_256_batch_vs_oracle(model, cuda):
