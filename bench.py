@@ -318,10 +318,10 @@ def run_product(args):
             "clocks": clocks.summary(),
         }
         result["roofline"]["unet_convs"] = conv_subroofline(layers, B, S, peak_tf)
-        if world == 1 and args.library_baseline:
+        if world == 1 and not args.no_library_baseline:
             result["library_baseline"] = library_baseline(dev, B, S, args.mode)
         if world == 1 and not args.no_cpu_baseline:
-            result["cpu_baseline"] = cpu_baseline(S, args.mode, batch=1, evals=args.cpu_evals)
+            result["cpu_baseline"] = cpu_baseline(S, args.mode, evals=args.cpu_evals)
         print(json.dumps(result), flush=True)
     if world > 1:
         dist.barrier()
@@ -330,64 +330,83 @@ def run_product(args):
 
 
 # ------------------------------------------------------------------------------------------------ CPU side
-def cpu_sample(S, mode, batch, evals, threads=None):
-    """Times `evals` denoiser+update steps of the oracle port (fp32, all host threads) after one warm-up."""
+def cpu_sample(S, mode, evals, threads=None):
+    """ONE protocol for both CPU legs (`cpu_baseline` of the product line and `--impl reference`): batch 1 (the reference's
+    test loader is hard-wired to batch 1, data/__init__.py:30-33), `evals` denoiser + update steps through the sampler's
+    own loop after a one-step warm-up, all host threads, fp32.  Runs THE REFERENCE's modules (IRSDE.reverse_* driving
+    ConditionalUNet, vendored unmodified into the git-ignored baseline/_ref/ by oracle/vendor_reference.py) when they
+    are present, else the oracle port.  Returns (seconds per denoiser step, threads, kind)."""
     from daclip_b200 import synthetic
-    from oracle import sde_oracle as So
-    from oracle import unet_oracle as O
     threads = threads or os.cpu_count()
     torch.set_num_threads(threads)
     sd, kw = synthetic.unet_state_dict(0)
-    cfg = O.UNetConfig(**kw)
-    inp = synthetic.restoration_inputs(batch, S, S, T=evals + 1, seed=100)
-    sch = So.Schedule(50, T_STEPS, "cosine", 0.005)
-    den = O.make_denoiser(sd, cfg)
-    x = inp["lq"] + inp["eps0"] * sch.max_sigma
-    step = So.posterior_step if mode == "posterior" else So.sde_step
-    secs = []
+    inp = synthetic.restoration_inputs(1, S, S, T=1, seed=100)
+    from oracle import vendor_reference as V
+    if V.available():
+        IRSDE, UNet = V.load_reference()
+        net = UNet(**kw)
+        net.load_state_dict(sd, strict=True)
+        net.eval()
+        sde = IRSDE(max_sigma=50, T=T_STEPS, schedule="cosine", eps=0.005, device="cpu")     # options/test.yml:7-12
+        sde.set_model(net)
+        sde.set_mu(inp["lq"])
+        x = sde.noise_state(inp["lq"])
+        loop = sde.reverse_posterior if mode == "posterior" else sde.reverse_sde
+        run = lambda k: loop(x, T=k, text_context=inp["text_context"], image_context=inp["image_context"])
+        kind = "reference"
+    else:
+        from oracle import sde_oracle as So
+        from oracle import unet_oracle as O
+        sch = So.Schedule(50, T_STEPS, "cosine", 0.005)
+        den = O.make_denoiser(sd, O.UNetConfig(**kw))
+        x = inp["lq"] + inp["eps0"] * sch.max_sigma
+        run = lambda k: So.reverse(sch, den, x, inp["lq"], mode=mode, T=k, text_context=inp["text_context"],
+                                   image_context=inp["image_context"])
+        kind = "port"
     with torch.no_grad():
-        for i, t in enumerate(range(T_STEPS, T_STEPS - evals - 1, -1)):
-            t0 = time.perf_counter()
-            n = den(x, inp["lq"], float(t), text_context=inp["text_context"], image_context=inp["image_context"])
-            x = step(sch, x, inp["lq"], n, inp["noise"][i], t)
-            secs.append(time.perf_counter() - t0)
-    per_eval = sum(secs[1:]) / max(1, len(secs) - 1)
-    return per_eval, threads
+        run(1)
+        t0 = time.perf_counter()
+        run(evals)
+        per_eval = (time.perf_counter() - t0) / evals
+    return per_eval, threads, kind
 
 
-def cpu_baseline(S, mode, batch, evals):
-    per_eval, threads = cpu_sample(S, mode, batch, evals)
-    return {"value": round(batch / (per_eval * T_STEPS), 5), "unit": "images/s", "cores": threads, "kind": "port",
+def cpu_baseline(S, mode, evals):
+    per_eval, threads, kind = cpu_sample(S, mode, evals)
+    what = ("the reference's IRSDE + ConditionalUNet (baseline/_ref, unmodified)" if kind == "reference"
+            else "oracle port (fp32 PyTorch restatement of the reference)")
+    return {"value": round(1.0 / (per_eval * T_STEPS), 5), "unit": "images/s", "cores": threads, "kind": kind,
             "s_per_denoiser_step": round(per_eval, 3),
-            "sample": f"oracle port (fp32 PyTorch restatement of the reference), batch {batch} at {S}x{S}: "
-                      f"{evals} of T={T_STEPS} denoiser+{mode} steps timed after 1 warm-up, extrapolated x{T_STEPS}/{evals}"}
+            "sample": f"{what}, batch 1 at {S}x{S}: {evals} of T={T_STEPS} denoiser+{mode} steps through the sampler loop "
+                      f"after a 1-step warm-up, extrapolated x{T_STEPS}/{evals}"}
 
 
 def run_reference(args):
-    """Reference arm: the reference's algorithm on the host CPU.  The reference is pure Python on PyTorch with no
-    compiled code of its own, and /root/reference does not exist on the GPU box, so this times the oracle port
-    (validated against the reference's own outputs in tests/test_oracle_golden.py).  Each step is a bounded
-    sample: one denoiser+update step of a quarter batch, extrapolated to images/s at T=100."""
+    """Reference arm: the reference's own implementation of the path on the host CPU (baseline/_ref, vendored unmodified
+    from /root/reference by oracle/vendor_reference.py; the oracle port if that directory is missing).  Same protocol
+    as `cpu_baseline`; each bench step is a bounded sample (--cpu-evals denoiser steps of one image), extrapolated to
+    images/s at T=100."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     B, S, K, W = args.batch, args.size, args.steps, args.warmup
-    b = max(1, min(B, 4))
-    threads = os.cpu_count()
-    vals = []
+    evals = max(1, min(args.cpu_evals, 3))
+    vals, kind, threads = [], "port", os.cpu_count()
     for _ in range(W + K):
-        per_eval, _ = cpu_sample(S, args.mode, b, 1, threads)
+        per_eval, threads, kind = cpu_sample(S, args.mode, evals)
         vals.append(per_eval)
     per_eval = sum(vals[W:]) / K
-    value = b / (per_eval * T_STEPS)
+    value = 1.0 / (per_eval * T_STEPS)
+    sample = (f"batch 1, {evals} denoiser+{args.mode} steps per bench step through the "
+              f"{'reference' if kind == 'reference' else 'oracle'} sampler loop (+1 warm-up step each), x{T_STEPS}/{evals}")
     out = {"impl": "reference", "metric": "restored images/sec @256^2 T=100", "value": round(value, 5),
            "unit": "images/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": K, "warmup": W,
-           "ms_per_step": round(per_eval * T_STEPS * 1e3 * B / b, 1), "higher_is_better": True, "scaling": "weak",
+           "ms_per_step": round(per_eval * T_STEPS * 1e3 * B, 1), "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": f"{S}x{S} batch {B}, T={T_STEPS} {args.mode} sampling (CPU sample: batch {b}, "
-                                  f"1 denoiser step per bench step, extrapolated)", "image": S, "T": T_STEPS},
-           "cpu_baseline": {"value": round(value, 5), "unit": "images/s", "cores": threads, "kind": "port",
-                            "sample": f"batch {b}, 1 denoiser+{args.mode} step per bench step (+1 warm-up each), x{T_STEPS}"},
+           "config": {"workload": f"{S}x{S} batch {B}, T={T_STEPS} {args.mode} sampling (CPU sample: {sample})",
+                      "image": S, "T": T_STEPS},
+           "cpu_baseline": {"value": round(value, 5), "unit": "images/s", "cores": threads, "kind": kind,
+                            "sample": sample},
            "e2e": {"value": round(value, 5), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out), flush=True)
@@ -404,8 +423,9 @@ def main():
     ap.add_argument("--mode", default="posterior", choices=["posterior", "sde"])
     ap.add_argument("--cpu-evals", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--library-baseline", action="store_true",
-                    help="also time the oracle restatement as eager PyTorch (cuDNN/cuBLAS) on the GPU")
+    ap.add_argument("--no-library-baseline", action="store_true",
+                    help="skip timing the oracle restatement as eager PyTorch (cuDNN/cuBLAS) on the GPU")
+    ap.add_argument("--library-baseline", action="store_true", help="(default now; kept for old command lines)")
     ap.add_argument("--dump-layers", default=None, help="write the per-launch CUDA-event times of one evaluation here")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -15,6 +15,7 @@
 // Roles: warp 0 = TMA producer, warps 1 and 10 = MMA issuers of head A / B, warps 2-5 = softmax of head A, 6-9 = head B.
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include "../../include/dac_b200.h"
 #include "common.h"
@@ -32,6 +33,7 @@ struct AttnParams {
   int items, q_tiles, pairs, n, heads;
   float scale_log2;                          // d^-0.5 * log2(e)
   __nv_bfloat16* out;
+  int dbg;                                   // profiling only (DAC_ATTN_DEBUG): 1 no exponentials, 2 no max pass, 4 no P store
 };
 
 constexpr int kAtThreads = 352;   // warp 0 TMA, warps 1 / 10 MMA issuers (one per head), warps 2-9 softmax
@@ -220,6 +222,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constant
         tc_fence_after();
         // pass A: row max of this key block (two TMEM loads in flight, four independent max chains)
         float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        if (p.dbg & 2) m4[0] = 0.f;
+        else
 #pragma unroll
         for (int cc = 0; cc < 128; cc += 64) {
           uint32_t r0[32], r1[32];
@@ -244,10 +248,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constant
           chunk_from_tmem(s_addr + cc, v);
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            v[i] = ex2_approx(fmaf(v[i], c, -mc));
+            v[i] = (p.dbg & 1) ? fmaf(v[i], c, -mc) : ex2_approx(fmaf(v[i], c, -mc));
             l4[i & 3] += v[i];
           }
-          chunk_stage_bf16(pt, row, cc, v);
+          if (!(p.dbg & 4)) chunk_stage_bf16(pt, row, cc, v);
         }
         const float l_blk = (l4[0] + l4[1]) + (l4[2] + l4[3]);
         tc_fence_before();
@@ -320,6 +324,7 @@ int dac_attention_tc(const void* qkv, void* out, int B, int n, int heads, cudaSt
   k.heads = heads;
   k.scale_log2 = 0.17677669529663687f * 1.4426950408889634f;
   k.out = static_cast<__nv_bfloat16*>(out);
+  k.dbg = getenv("DAC_ATTN_DEBUG") ? atoi(getenv("DAC_ATTN_DEBUG")) : 0;
   const int smem = (1 + kAtStages + 8) * (int)kAtSlab + 1024 + 512;
   static bool attr_set = false;
   if (!attr_set) {

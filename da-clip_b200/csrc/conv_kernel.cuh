@@ -111,6 +111,7 @@ struct ConvKParams {
   float kv_shift_max[4];   // KVCTX: the largest bound of each head - one scalar shift per head is all the softmax needs
   float* ctx_acc;          // KVCTX: [B][4][ctx_slots][kCtxRecord] fp32 partial records
   int ctx_slots, ctx_tpi;  // slots per (image, head); tiles per image
+  int dbg;                 // profiling only (DAC_EPI_DEBUG, tools/prof_conv.py): 1 skip stores, 2 skip activation, 4 skip FiLM
 };
 
 struct TileCoord {
@@ -344,7 +345,8 @@ __device__ __forceinline__ void epilogue_tile(const ConvKParams& p, const TileCo
     }
     if (p.bias) chunk_add_f32(p.bias + ch, v);
     if (p.bias_img) chunk_add_f32(p.bias_img + static_cast<long long>(n) * p.cout + ch, v);
-    if (FILM && p.film_tmem) {
+    if (FILM && (p.dbg & 4)) {
+    } else if (FILM && p.film_tmem) {
       // (scale + 1, shift) of this image replicated in every TMEM lane: two 32-column loads, no shared-memory traffic
       // (a broadcast LDS.128 is four wavefronts on the pipe that bounds these layers)
       float f[32];
@@ -368,7 +370,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvKParams& p, const TileCo
         v[4 * q + 3] = fmaf(v[4 * q + 3], a.w, b.w);
       }
     }
-    if (ACT != DAC_ACT_NONE) {
+    if (ACT != DAC_ACT_NONE && !(p.dbg & 2)) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = apply_act<ACT>(v[j]);
     }
@@ -384,9 +386,9 @@ __device__ __forceinline__ void epilogue_tile(const ConvKParams& p, const TileCo
       if (p.res && !p.res_tma) chunk_add_bf16(p.res + opix * p.res_ld + ch, v);
       if (p.res2) chunk_add_bf16(p.res2 + opix * p.res2_ld + ch, v);
       if (p.out_f32) chunk_store_f32(p.out_f32 + opix * p.out_f32_ld + ch, v);
-      if (p.out && !stg) chunk_store_bf16(p.out + opix * p.out_ld + p.out_coff + ch, v);
+      if (p.out && !stg && !(p.dbg & 1)) chunk_store_bf16(p.out + opix * p.out_ld + p.out_coff + ch, v);
     }
-    if (stg) chunk_stage_bf16(stg, row, c, v);
+    if (stg && !(p.dbg & 1)) chunk_stage_bf16(stg, row, c, v);
     if (EPI == KE_PLAIN && p.stats_out) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) {

@@ -4,7 +4,8 @@
 Checkers: (1) committed outputs of the REFERENCE modules (tests/golden/unet_sampler.pt, fp32, CPU);
 (2) the fp32 oracle evaluated on the same seeded inputs at sizes the goldens do not cover.
 Tolerances (north_star): final restored image max-abs <= 2e-2 and PSNR >= 45 dB (images in [0,1]) for the
-bf16 tensor-core path; single denoiser evaluations within 2 % of the output range.
+bf16 tensor-core path; single denoiser evaluations within 1 % of the output range (measured on a B200: 3.8e-3 ... 4.4e-3
+for every case below, 1.5e-2 for the worst single layer - the bounds are ~2x those; gpurun_out/unet_errors.json).
 """
 import math
 import os
@@ -65,7 +66,7 @@ def test_forward_vs_reference_golden_padded(model, gold):
             image_context=inp["image_context"].cuda())
     assert out.shape == g["out"].shape and out.dtype == torch.float32
     e = rel_err(out.cpu(), g["out"])
-    assert e < 2e-2, f"relative max error {e:.4f}"
+    assert e < 1e-2, f"relative max error {e:.4f}"
 
 
 def test_forward_vs_reference_golden_64(model, gold):
@@ -78,7 +79,7 @@ def test_forward_vs_reference_golden_64(model, gold):
         out = m(xt, inp["lq"].cuda(), t, text_context=inp["text_context"].cuda(),
                 image_context=inp["image_context"].cuda())
         e = rel_err(out.cpu(), g[key])
-        assert e < 2e-2, f"{key}: relative max error {e:.4f}"
+        assert e < 1e-2, f"{key}: relative max error {e:.4f}"
 
 
 def test_forward_per_layer_vs_oracle(model):
@@ -100,8 +101,8 @@ def test_forward_per_layer_vs_oracle(model):
         got = buf.float().permute(0, 3, 1, 2)
         e = rel_err(got, taps[name])
         worst.append((e, name))
-        assert e < 4e-2, f"{name}: relative max error {e:.4f}"
-    assert rel_err(out, ref) < 2e-2, sorted(worst)[-3:]
+        assert e < 3e-2, f"{name}: relative max error {e:.4f}"      # worst layer measured: 1.5e-2
+    assert rel_err(out, ref) < 1e-2, sorted(worst)[-3:]
 
 
 def test_forward_256_vs_oracle(model):
@@ -115,12 +116,12 @@ def test_forward_256_vs_oracle(model):
     with torch.no_grad():
         ref = O.unet_forward(sdc, cfg, xt, inp["lq"], 80.0, inp["text_context"], inp["image_context"])
     out = m(xt, inp["lq"], 80.0, text_context=inp["text_context"], image_context=inp["image_context"])
-    assert rel_err(out, ref) < 2e-2, rel_err(out, ref)
+    assert rel_err(out, ref) < 1e-2, rel_err(out, ref)
     # a second call with different inputs must not reuse stale state (CUDA graph replays static buffers)
     out2 = m(xt * 0.5, inp["lq"], 3.0, text_context=inp["text_context"], image_context=inp["image_context"])
     with torch.no_grad():
         ref2 = O.unet_forward(sdc, cfg, xt * 0.5, inp["lq"], 3.0, inp["text_context"], inp["image_context"])
-    assert rel_err(out2, ref2) < 2e-2
+    assert rel_err(out2, ref2) < 1e-2
 
 
 @pytest.mark.parametrize("mode", ["sde", "posterior"])
@@ -188,7 +189,7 @@ def test_forward_512_vs_oracle(model):
     with torch.no_grad():
         ref = O.unet_forward(sdc, cfg, xt, inp["lq"], 42.0, inp["text_context"], inp["image_context"])
     out = m(xt, inp["lq"], 42.0, text_context=inp["text_context"], image_context=inp["image_context"])
-    assert rel_err(out, ref) < 2e-2, rel_err(out, ref)
+    assert rel_err(out, ref) < 1e-2, rel_err(out, ref)
 
 
 def test_odd_sizes_and_batch(model):
@@ -205,7 +206,7 @@ def test_odd_sizes_and_batch(model):
             ref = O.unet_forward(sdc, cfg, xt, inp["lq"], 7.0, inp["text_context"], inp["image_context"])
         out = m(xt, inp["lq"], 7.0, text_context=inp["text_context"], image_context=inp["image_context"])
         assert out.shape == (B, 3, H, W)
-        assert rel_err(out, ref) < 2e-2, (B, H, W, rel_err(out, ref))
+        assert rel_err(out, ref) < 1e-2, (B, H, W, rel_err(out, ref))
 
 
 def test_wrapper_test_api(model, cuda):
@@ -251,7 +252,7 @@ def test_wild_ir_variant_vs_reference_golden(cuda):
         out = m(xt, inp["lq"], case["time"], text_context=inp["text_context"], image_context=inp["image_context"])
         ref = case["out"].cuda()
         assert out.shape == ref.shape
-        assert rel_err(out, ref) < 2e-2, (case["shape"], rel_err(out, ref))
+        assert rel_err(out, ref) < 1e-2, (case["shape"], rel_err(out, ref))
 
 
 @pytest.mark.parametrize("mode", ["sde", "posterior"])
