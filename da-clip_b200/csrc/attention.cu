@@ -186,6 +186,7 @@ __global__ void __launch_bounds__(kWarps * 32) flash_attn_kernel(const __nv_bflo
 using namespace dac;
 
 int dac_attention_tc(const void* qkv, void* out, int B, int n, int heads, cudaStream_t stream);   // attention_tc.cu
+int dac_attention_tc2(const void* qkv, void* out, int B, int n, int heads, cudaStream_t stream);  // attention_tc2.cu
 
 extern "C" int dac_attention(const void* qkv, void* out, int32_t B, int32_t n, int32_t heads, int32_t d,
                              dac_stream_t stream) {
@@ -193,7 +194,11 @@ extern "C" int dac_attention(const void* qkv, void* out, int32_t B, int32_t n, i
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   // d = 32 with whole 128-token tiles and head pairs: the tcgen05 kernel; everything else: the mma.sync kernel below
   static const bool no_tc = getenv("DAC_NO_TC_ATTN") != nullptr;
-  if (d == 32 && n % 128 == 0 && heads % 2 == 0 && B > 0 && !no_tc) return dac_attention_tc(qkv, out, B, n, heads, s);
+  if (d == 32 && n % 128 == 0 && heads % 2 == 0 && B > 0 && !no_tc) {
+    // DAC_ATTN_V1=1: round 1's kernel (one softmax warp per head and lane quadrant), kept for A/B timing
+    if (getenv("DAC_ATTN_V1")) return dac_attention_tc(qkv, out, B, n, heads, s);
+    return dac_attention_tc2(qkv, out, B, n, heads, s);
+  }
   const float l2e = 1.4426950408889634f;
   if (d == 32) {   // UNet self-attention: 1024 / 4096 tokens, 128 query rows per CTA
     flash_attn_kernel<32, 8><<<dim3((n + 127) / 128, heads, B), 256, 0, s>>>(

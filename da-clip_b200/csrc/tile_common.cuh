@@ -101,6 +101,19 @@ __device__ __forceinline__ void chunk_stage_bf16(uint8_t* stg, int row, int col,
     *reinterpret_cast<uint4*>(slab + (((c16 + q) ^ (row & 7)) << 4)) = u;
   }
 }
+// Same, addressed in the shared state space (32-bit address, STS.128): the generic-pointer form above costs a 64-bit add
+// per store, which matters in the issue-bound softmax loops.
+__device__ __forceinline__ void chunk_stage_bf16_s(uint32_t stg_s, int row, int col, const float (&v)[32]) {
+  const uint32_t slab = stg_s + (col >> 6) * (kTileM * 128) + row * 128;
+  const int c16 = (col & 63) >> 3;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(slab + (((c16 + q) ^ (row & 7)) << 4)),
+                 "r"(pack_bf16(v[q * 8 + 0], v[q * 8 + 1])), "r"(pack_bf16(v[q * 8 + 2], v[q * 8 + 3])),
+                 "r"(pack_bf16(v[q * 8 + 4], v[q * 8 + 5])), "r"(pack_bf16(v[q * 8 + 6], v[q * 8 + 7]))
+                 : "memory");
+  }
+}
 // ... and the read side: add the 32 staged bf16 values of this row (a TMA-loaded residual tile) to v
 __device__ __forceinline__ void chunk_add_staged(const uint8_t* stg, int row, int col, float (&v)[32]) {
   const uint8_t* slab = stg + (col >> 6) * (kTileM * 128) + row * 128;

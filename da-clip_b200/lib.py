@@ -119,6 +119,8 @@ def load(build_if_missing=True):
     path = _build.LIB
     if os.environ.get("DAC_DEBUG") == "1":
         path = _build.build(debug=True)
+    elif os.environ.get("DAC_LIB"):            # a hand-built variant of the library (kernel debugging)
+        path, build_if_missing = os.environ["DAC_LIB"], False
     if build_if_missing:
         _build.build()       # no-op when the library matches the content hash of csrc/ (never runs a stale binary)
     if not os.path.exists(path):

@@ -599,6 +599,27 @@ def test_flash_attention_d32(ops, gen, B, n, heads):
     assert_close_bf16(out, ref, f"flash d32 n={n}", rel=2 ** -6, abs_=4e-3)
 
 
+@pytest.mark.parametrize("B,n,heads", [(1, 1024, 2), (2, 2048, 4)])
+def test_flash_attention_d32_growing_scores(ops, gen, B, n, heads):
+    """The tcgen05 attention kernel keeps O in tensor memory and rescales a row only when its running max grows by more
+    than 2^8 (attention_tc2.cu).  Random scores never trigger that path: here the key norms step up x4 every 256 keys, so
+    the row max jumps by far more than the threshold from block to block (and some rows shrink instead, which must NOT
+    rescale), against the fp32 softmax(QK^T / sqrt(d)) V of attention.py:178-192."""
+    d = 32
+    qkv = rnd(gen, B, n, 3 * heads * d)
+    step = 4.0 ** torch.div(torch.arange(n, device="cuda"), 256, rounding_mode="floor").float()
+    kcols = slice(heads * d, 2 * heads * d)
+    qkv[:, :, kcols] = qkv[:, :, kcols] * step[None, :, None] * 0.5
+    qkv = bf(qkv)
+    out = torch.zeros(B, n, heads * d, device="cuda", dtype=torch.bfloat16)
+    ops.attention(qkv, out, B, n, heads, d)
+    torch.cuda.synchronize()
+    q, k, v = [t.reshape(B, n, heads, d).transpose(1, 2) for t in qkv.float().chunk(3, dim=-1)]
+    ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, n, heads * d)
+    assert torch.isfinite(out.float()).all()
+    assert_close_bf16(out, ref, f"flash d32 growing scores n={n}", rel=2 ** -6, abs_=6e-3)
+
+
 def test_small_attention_d64(ops, gen):
     B, n, heads, d = 3, 50, 12, 64
     qkv = bf(rnd(gen, B, n, 3 * heads * d))
