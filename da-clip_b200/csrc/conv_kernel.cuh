@@ -281,7 +281,10 @@ __device__ __forceinline__ void epilogue_tile(const ConvKParams& p, const TileCo
       chunk_add_f32(p.bias + col, v);
       chunk_add_f32(p.bias + col + hn, g);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] *= gelu_f(g[j]);
+      for (int j = 0; j < 32; j += 2) {
+        gelu2_f(g[j], g[j + 1]);
+        unpack_f32x2(mul_f32x2(pack_f32x2(v[j], v[j + 1]), pack_f32x2(g[j], g[j + 1])), v[j], v[j + 1]);
+      }
       if (stg) chunk_stage_bf16(stg, row, c, v);
       else if (valid) chunk_store_bf16(p.out + opix * p.out_ld + p.out_coff + t.nt * hn + c, v);
     }
@@ -347,17 +350,21 @@ __device__ __forceinline__ void epilogue_tile(const ConvKParams& p, const TileCo
     if (p.bias_img) chunk_add_f32(p.bias_img + static_cast<long long>(n) * p.cout + ch, v);
     if (FILM && (p.dbg & 4)) {
     } else if (FILM && p.film_tmem) {
-      // (scale + 1, shift) of this image replicated in every TMEM lane: two 32-column loads, no shared-memory traffic
-      // (a broadcast LDS.128 is four wavefronts on the pipe that bounds these layers)
-      float f[32];
+      // (scale + 1, shift) of this image replicated in every TMEM lane: two 32-column loads issued back to back (one
+      // wait), no shared-memory traffic (a broadcast LDS.128 is four wavefronts on the pipe that bounds these layers);
+      // applied as packed fp32 pairs (FFMA2)
       const int fcols = p.film_cols ? p.film_cols : p.block_n;   // pair mode: both pixels of the pair share the vectors
       const int fc = p.film_cols ? (c & (p.film_cols - 1)) : c;
-      chunk_from_tmem(tmem_acc + p.block_n + fc, f);
+      uint32_t fa[32], fb[32];
+      tmem_ld32(tmem_acc + p.block_n + fc, fa);
+      tmem_ld32(tmem_acc + p.block_n + fcols + fc, fb);
+      tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] *= f[j];
-      chunk_from_tmem(tmem_acc + p.block_n + fcols + fc, f);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] += f[j];
+      for (int j = 0; j < 32; j += 2)
+        unpack_f32x2(fma_f32x2(pack_f32x2(v[j], v[j + 1]),
+                               pack_f32x2(__uint_as_float(fa[j]), __uint_as_float(fa[j + 1])),
+                               pack_f32x2(__uint_as_float(fb[j]), __uint_as_float(fb[j + 1]))),
+                     v[j], v[j + 1]);
     } else if (FILM) {
       // (scale + 1, shift) of this image, staged in shared memory by the epilogue warps when the image changes
 #pragma unroll
@@ -370,9 +377,19 @@ __device__ __forceinline__ void epilogue_tile(const ConvKParams& p, const TileCo
         v[4 * q + 3] = fmaf(v[4 * q + 3], a.w, b.w);
       }
     }
-    if (ACT != DAC_ACT_NONE && !(p.dbg & 2)) {
+    if (ACT == DAC_ACT_SILU && !(p.dbg & 2)) {
+      // x * sigmoid(x) = h + h * tanh(h), h = x / 2: FMUL2, two MUFU.TANH, FFMA2 per pair of values
+      const uint64_t half2 = pack_f32x2(0.5f, 0.5f);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = apply_act<ACT>(v[j]);
+      for (int j = 0; j < 32; j += 2) {
+        const uint64_t h2 = mul_f32x2(pack_f32x2(v[j], v[j + 1]), half2);
+        float h0, h1;
+        unpack_f32x2(h2, h0, h1);
+        unpack_f32x2(fma_f32x2(h2, pack_f32x2(tanh_approx(h0), tanh_approx(h1)), h2), v[j], v[j + 1]);
+      }
+    } else if (ACT == DAC_ACT_GELU && !(p.dbg & 2)) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) gelu2_f(v[j], v[j + 1]);
     }
     if (p.r_chunks0) {   // fused res_conv: its product sits in the next block_n TMEM columns
       float r2[32];

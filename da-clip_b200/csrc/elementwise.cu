@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(256) time_embed_kernel(dac_embed_weights w, co
   __syncthreads();
   block_linear(w.time_w1, w.time_b1, a, h, td, w.nf);
   __syncthreads();
-  for (int i = threadIdx.x; i < td; i += blockDim.x) h[i] = gelu_f(h[i]);
+  for (int i = threadIdx.x; i < td; i += blockDim.x) h[i] = gelu_precise_f(h[i]);
   __syncthreads();
   block_linear(w.time_w2, w.time_b2, h, t, td, td);
   __syncthreads();

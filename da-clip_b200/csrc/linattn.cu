@@ -11,6 +11,7 @@
 
 #include "../../include/dac_b200.h"
 #include "common.h"
+#include "linattn_kv_common.h"
 #include "ptx.cuh"
 
 namespace dac {
@@ -210,6 +211,54 @@ __global__ void __launch_bounds__(256) linattn_fold_kernel(const float* __restri
   }
 }
 
+// The fold for dac_linattn_kv's in-kernel-PreNorm mode (linattn_kv2.cu), whose partial records hold G = P^T xn
+// ([32 d][64 c]) and S instead of the context: context = G W_v^T / (S hw) and W_eff = W_out context^T collapse into
+//   weff[b][c'][h*32+d] = sum_c G[b,h,d,c] M_h[c'][c] / (S[b,h,d] hw),   M_h = W_out[:, h] W_v[h]   (constant, fp32)
+// One CTA per (head, image, group of kFoldRows d rows); slots are added in a FIXED order (two interleaved chains + one
+// add, shuffle trees for S): bit-reproducible.  No running-max weights: the k|v kernels use a data-independent shift.
+__global__ void __launch_bounds__(256) linattn_fold_g_kernel(const float* __restrict__ partial, int hw, int nslots,
+                                                             const float* __restrict__ m_fold, int C, int c_pad,
+                                                             __nv_bfloat16* __restrict__ weff) {
+  extern __shared__ float fold_sm[];
+  float* msm = fold_sm;                          // [C][65]: M_h[c'][c]
+  float* g = msm + C * 65;                       // [kFoldRows][64]
+  __shared__ float inv_s[kFoldRows];
+  const int h = blockIdx.x, b = blockIdx.y, d0 = blockIdx.z * kFoldRows, t = threadIdx.x;
+  const int warp = t >> 5, lane = t & 31;
+  const float* pbase = partial + (static_cast<int64_t>(b) * 4 + h) * nslots * kKvGRec;
+  griddep_launch();
+  for (int i = t; i < C * 64; i += 256)         // a constant: staged while the producing kernel drains
+    msm[(i >> 6) * 65 + (i & 63)] = __ldg(m_fold + static_cast<int64_t>(h) * C * 64 + i);
+  griddep_wait();
+  if (warp < kFoldRows) {
+    float S = 0.f;
+    for (int c = lane; c < nslots; c += 32) S += pbase[static_cast<int64_t>(c) * kKvGRec + 2048 + d0 + warp];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) S += __shfl_xor_sync(0xffffffffu, S, o);
+    if (lane == 0) inv_s[warp] = 1.0f / (S * static_cast<float>(hw));   // softmax denominator and v / (h*w) (module_util.py:177)
+  }
+  float a0 = 0.f, a1 = 0.f;
+  {
+    const float* src = pbase + d0 * 64 + t;      // 4 rows x 64 channels = 256 consecutive floats of a record
+    int c = 0;
+    for (; c + 1 < nslots; c += 2) {
+      a0 += src[static_cast<int64_t>(c) * kKvGRec];
+      a1 += src[static_cast<int64_t>(c + 1) * kKvGRec];
+    }
+    if (c < nslots) a0 += src[static_cast<int64_t>(c) * kKvGRec];
+  }
+  __syncthreads();
+  g[t] = (a0 + a1) * inv_s[t >> 6];
+  __syncthreads();
+  const int dl = t & (kFoldRows - 1);
+  for (int c = t >> 2; c < C; c += 64) {
+    float a = 0.f;
+#pragma unroll 16
+    for (int e = 0; e < 64; ++e) a = fmaf(msm[c * 65 + e], g[dl * 64 + e], a);
+    weff[(static_cast<int64_t>(b) * c_pad + c) * 128 + h * 32 + d0 + dl] = __float2bfloat16(a);
+  }
+}
+
 }  // namespace dac
 
 using namespace dac;
@@ -239,4 +288,15 @@ extern "C" int dac_linattn_fold(const float* partial, int32_t B, int32_t hw, int
   launch_k(linattn_fold_kernel, dim3(4, B, 32 / kFoldRows), dim3(256), smem, static_cast<cudaStream_t>(stream), partial, hw, nchunks, w_out,
            C, c_pad, static_cast<__nv_bfloat16*>(weff));
   return check_launch("linattn_fold_kernel");
+}
+
+extern "C" int dac_linattn_fold_g(const float* partial, int32_t B, int32_t hw, int32_t nslots, const float* m_fold,
+                                  int32_t C, int32_t c_pad, void* weff, dac_stream_t stream) {
+  if (!partial || !m_fold || !weff) return set_error(-1, "dac_linattn_fold_g: null argument");
+  if (nslots < 1 || nslots > 2048) return set_error(-2, "dac_linattn_fold_g: nslots must be in [1,2048]");
+  if (C <= 0 || C > 128 || c_pad < C) return set_error(-2, "dac_linattn_fold_g: C must be in [1,128], c_pad >= C");
+  const size_t smem = sizeof(float) * (static_cast<size_t>(C) * 65 + kFoldRows * 64);
+  launch_k(linattn_fold_g_kernel, dim3(4, B, 32 / kFoldRows), dim3(256), smem, static_cast<cudaStream_t>(stream), partial, hw,
+           nslots, m_fold, C, c_pad, static_cast<__nv_bfloat16*>(weff));
+  return check_launch("linattn_fold_g_kernel");
 }

@@ -20,6 +20,7 @@
 
 #include "../../include/dac_b200.h"
 #include "common.h"
+#include "linattn_kv_common.h"
 #include "tensormap.h"
 #include "tile_common.cuh"
 
@@ -319,7 +320,9 @@ using namespace dac;
 struct dac_kv_plan {
   CUtensorMap mapX, mapW;
   KvParams kp;
+  Kv2Params kp2;
   int C, B, grid, smem;
+  int prenorm;             // the input is the RAW tensor: linattn_kv2_kernel normalises its rows in shared memory
 };
 
 static int kv_encode_2d(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t rows, uint32_t box_rows,
@@ -339,10 +342,12 @@ static int kv_encode_2d(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_
 
 extern "C" int dac_linattn_kv_create(const void* xn, const void* wkv, const float* kv_shift, float* ctx_acc,
                                      int32_t ctx_slots, const float* ln_stats, const float* ln_colsum, int32_t B,
-                                     int32_t hw, int32_t C, dac_kv_t* plan) {
+                                     int32_t hw, int32_t C, int32_t prenorm, float prenorm_eps, dac_kv_t* plan) {
   if (!xn || !wkv || !kv_shift || !ctx_acc || !plan) return set_error(-1, "dac_linattn_kv_create: null argument");
   *plan = nullptr;
   if (C != 64 && C != 128) return set_error(-2, "dac_linattn_kv_create: C must be 64 or 128 (got %d)", C);
+  if (prenorm && (C != 64 || ln_stats))
+    return set_error(-2, "dac_linattn_kv_create: in-kernel PreNorm needs C = 64 and no ln_stats");
   if (B <= 0 || hw <= 0 || hw % kTileM) return set_error(-2, "dac_linattn_kv_create: hw must be a multiple of 128");
   if ((reinterpret_cast<uintptr_t>(xn) | reinterpret_cast<uintptr_t>(wkv) | reinterpret_cast<uintptr_t>(kv_shift) |
        reinterpret_cast<uintptr_t>(ctx_acc)) & 15)
@@ -351,7 +356,7 @@ extern "C" int dac_linattn_kv_create(const void* xn, const void* wkv, const floa
   if (!pl) return set_error(-3, "out of host memory");
   const uint64_t rows = static_cast<uint64_t>(B) * hw;
   int rc = kv_encode_2d(&pl->mapX, xn, C, rows, kTileM, "xn");
-  if (!rc) rc = kv_encode_2d(&pl->mapW, wkv, C, 256, 128, "wkv");
+  if (!rc) rc = kv_encode_2d(&pl->mapW, wkv, C, prenorm ? 128 : 256, 128, "wkv");
   if (rc) { delete pl; return rc; }
   KvParams& k = pl->kp;
   k.tiles = static_cast<int>(rows / kTileM);
@@ -391,6 +396,16 @@ extern "C" int dac_linattn_kv_create(const void* xn, const void* wkv, const floa
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   pl->grid = k.tiles < sms ? k.tiles : sms;
   k.slots = ctx_slots;
+  pl->prenorm = prenorm ? 1 : 0;
+  if (prenorm) {
+    Kv2Params& k2 = pl->kp2;
+    k2.tiles = k.tiles;
+    k2.tiles_per_image = k.tiles_per_image;
+    for (int h = 0; h < 4; ++h) k2.shift_max[h] = k.shift_max[h];
+    k2.ctx_acc = ctx_acc;
+    k2.slots = ctx_slots;
+    k2.ln_eps = prenorm_eps;
+  }
   if (ctx_slots < max_image_span(B, k.tiles_per_image, pl->grid)) {
     const int need = max_image_span(B, k.tiles_per_image, pl->grid);
     delete pl;
@@ -410,8 +425,9 @@ extern "C" int dac_linattn_kv_create(const void* xn, const void* wkv, const floa
 extern "C" int dac_linattn_kv_launch(dac_kv_t pl, dac_stream_t stream) {
   if (!pl) return set_error(-1, "dac_linattn_kv_launch: null plan");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  cudaError_t e = cudaMemsetAsync(pl->kp.ctx_acc, 0, sizeof(float) * pl->B * 4 * pl->kp.slots * kCtxRec, st);
+  cudaError_t e = cudaMemsetAsync(pl->kp.ctx_acc, 0, sizeof(float) * pl->B * 4 * pl->kp.slots * (pl->prenorm ? kKvGRec : kCtxRec), st);
   if (e != cudaSuccess) return set_error(-20, "dac_linattn_kv_launch: memset failed: %s", cudaGetErrorString(e));
+  if (pl->prenorm) return dac_kv2_launch(pl->mapX, pl->mapW, pl->kp2, pl->grid, st);
   if (pl->C == 64) linattn_kv_kernel<64><<<pl->grid, kThreads, pl->smem, st>>>(pl->mapX, pl->mapW, pl->kp);
   else linattn_kv_kernel<128><<<pl->grid, kThreads, pl->smem, st>>>(pl->mapX, pl->mapW, pl->kp);
   return check_launch("linattn_kv_kernel");

@@ -19,6 +19,7 @@
 
 #include "../../include/dac_b200.h"
 #include "common.h"
+#include "linattn_qout_common.h"
 #include "tile_common.cuh"
 #include "tensormap.h"
 
@@ -388,7 +389,9 @@ using namespace dac;
 struct dac_qout_plan {
   CUtensorMap mapX, mapWq, mapWeff, mapOut, mapRes;
   QoutParams kp;
+  Qout2Params kp2;
   int C, grid, smem;
+  int prenorm;             // the input is the RAW tensor: linattn_qout2_kernel normalises its rows in shared memory
 };
 
 static int encode_2d(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t rows, uint64_t pitch_bytes,
@@ -409,11 +412,13 @@ static int encode_2d(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t r
 extern "C" int dac_linattn_qout_create(const void* xn, const void* wq, const void* weff, int32_t c_pad,
                                        const void* res, void* out, const float* bias, const float* ln_g,
                                        float ln_eps, const float* ln_stats, const float* ln_colsum, int32_t B,
-                                       int32_t hw, int32_t C, dac_qout_t* plan) {
+                                       int32_t hw, int32_t C, int32_t prenorm, float prenorm_eps, dac_qout_t* plan) {
   if (!xn || !wq || !weff || !res || !out || !ln_g || !plan) return set_error(-1, "dac_linattn_qout_create: null argument");
   *plan = nullptr;
   if (C != 64 && C != 128) return set_error(-2, "dac_linattn_qout_create: C must be 64 or 128 (got %d)", C);
   if (B <= 0 || hw <= 0 || hw % kTileM) return set_error(-2, "dac_linattn_qout_create: hw must be a multiple of 128");
+  if (prenorm && (C != 64 || ln_stats || res != xn))
+    return set_error(-2, "dac_linattn_qout_create: in-kernel PreNorm needs C = 64, no ln_stats and res == xn (the raw tensor)");
   if (c_pad < C || (c_pad & 7)) return set_error(-2, "dac_linattn_qout_create: bad c_pad");
   if ((reinterpret_cast<uintptr_t>(xn) | reinterpret_cast<uintptr_t>(wq) | reinterpret_cast<uintptr_t>(weff) |
        reinterpret_cast<uintptr_t>(res) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(bias) |
@@ -456,6 +461,17 @@ extern "C" int dac_linattn_qout_create(const void* xn, const void* wq, const voi
     delete pl;
     return set_error(-12, "dac_linattn_qout_create: cudaFuncSetAttribute(%d B smem): %s", pl->smem, cudaGetErrorString(e));
   }
+  pl->prenorm = prenorm ? 1 : 0;
+  if (prenorm) {
+    Qout2Params& k2 = pl->kp2;
+    k2.tiles = k.tiles;
+    k2.tiles_per_image = k.tiles_per_image;
+    k2.c_pad = c_pad;
+    k2.bias = bias;
+    k2.ln_g = ln_g;
+    k2.ln_eps = ln_eps;
+    k2.prenorm_eps = prenorm_eps;
+  }
   *plan = pl;
   return 0;
 }
@@ -463,6 +479,7 @@ extern "C" int dac_linattn_qout_create(const void* xn, const void* wq, const voi
 extern "C" int dac_linattn_qout_launch(dac_qout_t pl, dac_stream_t stream) {
   if (!pl) return set_error(-1, "dac_linattn_qout_launch: null plan");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (pl->prenorm) return dac_qout2_launch(pl->mapX, pl->mapWq, pl->mapWeff, pl->mapOut, pl->kp2, pl->grid, st);
   if (pl->C == 64)
     launch_k(linattn_qout_kernel<64>, dim3(pl->grid), dim3(kThreads), pl->smem, st, pl->mapX, pl->mapWq, pl->mapWeff,
              pl->mapOut, pl->mapRes, pl->kp);

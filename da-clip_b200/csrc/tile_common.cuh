@@ -89,16 +89,15 @@ __device__ __forceinline__ void chunk_store_bf16(__nv_bfloat16* __restrict__ dst
 // 32 columns of one row into the staging tile: 64-channel slabs of 128 rows x 128 B, 16 B pieces XOR-swizzled by the
 // row (the SWIZZLE_128B pattern of the output tensor map; also conflict-free for one-row-per-lane writes).
 __device__ __forceinline__ void chunk_stage_bf16(uint8_t* stg, int row, int col, const float (&v)[32]) {
-  uint8_t* slab = stg + (col >> 6) * (kTileM * 128) + row * 128;
+  // shared-state-space stores (STS.128 with a 32-bit address): a generic ST.E.128 costs a 64-bit address add per store
+  const uint32_t slab = smem_u32(stg) + (col >> 6) * (kTileM * 128) + row * 128;
   const int c16 = (col & 63) >> 3;
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    uint4 u;
-    u.x = pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
-    u.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
-    u.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
-    u.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
-    *reinterpret_cast<uint4*>(slab + (((c16 + q) ^ (row & 7)) << 4)) = u;
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(slab + (((c16 + q) ^ (row & 7)) << 4)),
+                 "r"(pack_bf16(v[q * 8 + 0], v[q * 8 + 1])), "r"(pack_bf16(v[q * 8 + 2], v[q * 8 + 3])),
+                 "r"(pack_bf16(v[q * 8 + 4], v[q * 8 + 5])), "r"(pack_bf16(v[q * 8 + 6], v[q * 8 + 7]))
+                 : "memory");
   }
 }
 // Same, addressed in the shared state space (32-bit address, STS.128): the generic-pointer form above costs a 64-bit add
@@ -116,14 +115,19 @@ __device__ __forceinline__ void chunk_stage_bf16_s(uint32_t stg_s, int row, int 
 }
 // ... and the read side: add the 32 staged bf16 values of this row (a TMA-loaded residual tile) to v
 __device__ __forceinline__ void chunk_add_staged(const uint8_t* stg, int row, int col, float (&v)[32]) {
-  const uint8_t* slab = stg + (col >> 6) * (kTileM * 128) + row * 128;
+  const uint32_t slab = smem_u32(stg) + (col >> 6) * (kTileM * 128) + row * 128;
   const int c16 = (col & 63) >> 3;
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    const uint4 u = *reinterpret_cast<const uint4*>(slab + (((c16 + q) ^ (row & 7)) << 4));
-    const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
-    v[q * 8 + 0] += a.x; v[q * 8 + 1] += a.y; v[q * 8 + 2] += b.x; v[q * 8 + 3] += b.y;
-    v[q * 8 + 4] += c.x; v[q * 8 + 5] += c.y; v[q * 8 + 6] += d.x; v[q * 8 + 7] += d.y;
+    uint32_t ux, uy, uz, uw;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(ux), "=r"(uy), "=r"(uz), "=r"(uw)
+                 : "r"(slab + (((c16 + q) ^ (row & 7)) << 4)));
+    const float2 a = unpack_bf16(ux), b = unpack_bf16(uy), c = unpack_bf16(uz), d = unpack_bf16(uw);
+    unpack_f32x2(add_f32x2(pack_f32x2(v[q * 8 + 0], v[q * 8 + 1]), pack_f32x2(a.x, a.y)), v[q * 8 + 0], v[q * 8 + 1]);
+    unpack_f32x2(add_f32x2(pack_f32x2(v[q * 8 + 2], v[q * 8 + 3]), pack_f32x2(b.x, b.y)), v[q * 8 + 2], v[q * 8 + 3]);
+    unpack_f32x2(add_f32x2(pack_f32x2(v[q * 8 + 4], v[q * 8 + 5]), pack_f32x2(c.x, c.y)), v[q * 8 + 4], v[q * 8 + 5]);
+    unpack_f32x2(add_f32x2(pack_f32x2(v[q * 8 + 6], v[q * 8 + 7]), pack_f32x2(d.x, d.y)), v[q * 8 + 6], v[q * 8 + 7]);
   }
 }
 __device__ __forceinline__ void chunk_store_f32(float* __restrict__ dst, const float (&v)[32]) {

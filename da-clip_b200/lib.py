@@ -84,6 +84,7 @@ SYMBOLS = {
     "dac_two_linear": (C.c_int, [_p, _i32, _i32, _p, _i32, _p, _p, _i32, _p, _p]),
     "dac_linattn_context": (C.c_int, [_p, _i32, _i32, _i32, _p, _p]),
     "dac_linattn_fold": (C.c_int, [_p, _i32, _i32, _i32, _p, _i32, _i32, _p, _p]),
+    "dac_linattn_fold_g": (C.c_int, [_p, _i32, _i32, _i32, _p, _i32, _i32, _p, _p]),
     "dac_attention": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _p]),
     "dac_vit_patchify": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _p]),
     "dac_vit_embed": (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _f, _p]),
@@ -94,10 +95,10 @@ SYMBOLS = {
     "dac_text_pool": (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p, _f, _p, _i32, _p, _p]),
     "dac_degradation_argmax": (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p, _p]),
     "dac_linattn_ctx_slots": (C.c_int32, [_i32, _i32, _i32]),
-    "dac_linattn_kv_create": (C.c_int, [_p, _p, _p, _p, _i32, _p, _p, _i32, _i32, _i32, C.POINTER(_p)]),
+    "dac_linattn_kv_create": (C.c_int, [_p, _p, _p, _p, _i32, _p, _p, _i32, _i32, _i32, _i32, _f, C.POINTER(_p)]),
     "dac_linattn_kv_launch": (C.c_int, [_p, _p]),
     "dac_linattn_kv_destroy": (None, [_p]),
-    "dac_linattn_qout_create": (C.c_int, [_p, _p, _p, _i32, _p, _p, _p, _p, _f, _p, _p, _i32, _i32, _i32, C.POINTER(_p)]),
+    "dac_linattn_qout_create": (C.c_int, [_p, _p, _p, _i32, _p, _p, _p, _p, _f, _p, _p, _i32, _i32, _i32, _i32, _f, C.POINTER(_p)]),
     "dac_linattn_qout_launch": (C.c_int, [_p, _p]),
     "dac_linattn_qout_destroy": (None, [_p]),
     "dac_clip_resample_h": (C.c_int, [_p, _i32, _i32, _p, _i32, _p, _p, _i32, _i32, _i32, _p]),

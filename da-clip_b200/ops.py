@@ -347,16 +347,19 @@ def pack_kv_grouped(wkv):
 class KvPlan:
     """LinearAttention key/value side on tcgen05: k|v GEMM, exp, context GEMM accumulated in tensor memory."""
 
-    def __init__(self, xn, wkv_grouped, kv_shift, ctx_acc, B, hw, Cn, ln_stats=None, ln_colsum=None):
+    def __init__(self, xn, wkv_grouped, kv_shift, ctx_acc, B, hw, Cn, ln_stats=None, ln_colsum=None, prenorm_eps=None):
+        """prenorm_eps: `xn` is the RAW tensor and the kernel applies the gain-free channel LayerNorm itself (C = 64); then
+        `wkv_grouped` holds only the key rows ([128, 64] bf16, head order) and `ctx_acc` is [B, 4, slots, KV_G_REC] for
+        linattn_fold_g."""
         L.require_cuda(xn, wkv_grouped, kv_shift, ctx_acc, ln_stats, ln_colsum)
         lib = L.load()
         h = C.c_void_p()
         L.check(lib.dac_linattn_kv_create(xn.data_ptr(), wkv_grouped.data_ptr(), kv_shift.data_ptr(),
                                           ctx_acc.data_ptr(), ctx_acc.shape[-2], L.ptr(ln_stats), L.ptr(ln_colsum),
-                                          B, hw, Cn, C.byref(h)))
+                                          B, hw, Cn, int(prenorm_eps is not None), float(prenorm_eps or 0.0), C.byref(h)))
         self.handle, self._lib = h, lib
         self._keep = (xn, wkv_grouped, kv_shift, ctx_acc, ln_stats, ln_colsum)
-        self.flops = 2.0 * B * hw * Cn * 256
+        self.flops = 2.0 * B * hw * Cn * 256      # algorithmic (k and v rows), whichever way the kernel gets there
 
     def run(self):
         L.check(self._lib.dac_linattn_kv_launch(self.handle, L.stream_ptr()))
@@ -372,14 +375,16 @@ class KvPlan:
 class QoutPlan:
     """LinearAttention query side (to_q softmax -> W_eff q -> LayerNorm -> + x) as one chained-GEMM launch."""
 
-    def __init__(self, xn, wq, weff, res, out, bias, ln_g, ln_eps, B, hw, Cn, ln_stats=None, ln_colsum=None):
+    def __init__(self, xn, wq, weff, res, out, bias, ln_g, ln_eps, B, hw, Cn, ln_stats=None, ln_colsum=None,
+                 prenorm_eps=None):
+        """prenorm_eps: `xn` (== `res`) is the RAW tensor and the kernel applies the gain-free channel LayerNorm itself (C = 64)."""
         L.require_cuda(xn, wq, weff, res, out, ln_g, ln_stats, ln_colsum)
         lib = L.load()
         h = C.c_void_p()
         L.check(lib.dac_linattn_qout_create(xn.data_ptr(), wq.data_ptr(), weff.data_ptr(), weff.shape[-2],
                                             res.data_ptr(), out.data_ptr(), bias.data_ptr() if bias is not None else None,
                                             ln_g.data_ptr(), ln_eps, L.ptr(ln_stats), L.ptr(ln_colsum), B, hw, Cn,
-                                            C.byref(h)))
+                                            int(prenorm_eps is not None), float(prenorm_eps or 0.0), C.byref(h)))
         self.handle, self._lib = h, lib
         self._keep = (xn, wq, weff, res, out, bias, ln_g, ln_stats, ln_colsum)
         self.flops = 2.0 * B * hw * 128 * Cn * 2
@@ -471,6 +476,23 @@ def linattn_context(kv, B, hw, nchunks, partial):
 def linattn_fold(partial, B, hw, nchunks, w_out, C_, c_pad, weff):
     L.check(L.load().dac_linattn_fold(L.ptr(partial), B, hw, nchunks, L.ptr(w_out), C_, c_pad, L.ptr(weff),
                                       L.stream_ptr()))
+
+
+def linattn_fold_g(partial, B, hw, nslots, m_fold, C_, c_pad, weff):
+    """Fold for KvPlan(prenorm_eps=...): records {G[32][64], S[32]} -> weff (dac_linattn_fold_g)."""
+    L.check(L.load().dac_linattn_fold_g(L.ptr(partial), B, hw, nslots, L.ptr(m_fold), C_, c_pad, L.ptr(weff),
+                                        L.stream_ptr()))
+
+
+def kv_fold_matrix(w_out, w_v):
+    """M_h[c'][c] = sum_e W_out[c'][h*32+e] W_v[h*32+e][c] (fp32 [4, C, Cin]) from to_out's [C, 128] weight and the
+    gain-folded value rows [128, Cin] of to_qkv, rounded to bf16 first as the GEMM operand would have been."""
+    wv = w_v.to(torch.bfloat16).float().reshape(4, 32, -1)
+    wo = w_out.float().reshape(w_out.shape[0], 4, 32).permute(1, 0, 2)
+    return torch.bmm(wo, wv).contiguous()
+
+
+KV_G_REC = 32 * 64 + 32      # floats per {G, S} record of the in-kernel-PreNorm k kernel
 
 
 def attention(qkv, out, B, n, heads, d):

@@ -350,6 +350,9 @@ class PackedUNet:
                      qkv_colsum=colsum.contiguous(),
                      out=ops.pack_linear(f32(q + "to_out.0.weight")),
                      w_out=f32(q + "to_out.0.weight").reshape(dim, 128).contiguous(),
+                     # in-kernel-PreNorm k kernel (64 channels): key rows only + the constant W_out,h W_v,h of its fold
+                     k_rows=wq[128:256].to(torch.bfloat16).contiguous(),
+                     m_fold=ops.kv_fold_matrix(f32(q + "to_out.0.weight").reshape(dim, 128), wq[256:384]),
                      b_out=f32(q + "to_out.0.bias"), g_out=f32(q + "to_out.1.g").reshape(-1).contiguous())
             return a
         b = q + "transformer_blocks.0."
@@ -482,14 +485,24 @@ class UNetEngine:
     FUSE_KV_TC = True      # LinearAttention: the k|v context reduction as a second tcgen05 GEMM (TMEM-resident context)
     FUSE_QOUT = True       # LinearAttention: to_q + softmax + to_out + LayerNorm + residual as one chained-GEMM kernel
     FUSE_KVCTX = True      # LinearAttention: reduce k | v into the context inside the to_kv GEMM epilogue
+    PRENORM_IN_KERNEL = True   # 64-channel LinearAttention: PreNorm on the tile in shared memory inside the k|v / q-out kernels
 
     # A/B switches from the environment, e.g. DAC_SWITCHES="FOLD_PRENORM=1,PDL=0" (tools/ab_engine.py, bench.py runs)
     for _kv in filter(None, os.environ.get("DAC_SWITCHES", "").split(",")):
         _k, _v = _kv.split("=")
         locals()[_k] = bool(int(_v))
 
-    def needs_stats(self, prefix, hw):
+    def prenorm_in_kernel(self, prefix, C, hw):
+        """True if the LinearAttention layer `prefix` normalises its input tiles inside the k|v and q-out kernels (64 channels:
+        linattn_kv2 / linattn_qout2 take the raw tensor; no LayerNorm pass, no statistics from the producer)."""
+        a = self.pk.attn[prefix]
+        return (self.PRENORM_IN_KERNEL and not a["transformer"] and C == 64 and hw % 128 == 0 and self.FUSE_KVCTX
+                and a["kv_safe"] and self.FUSE_KV_TC and self.FUSE_QOUT)
+
+    def needs_stats(self, prefix, hw, C=None):
         """True if the attention layer `prefix` consumes per-pixel LayerNorm statistics from its producer."""
+        if C is not None and self.prenorm_in_kernel(prefix, C, hw):
+            return False
         return (self.FOLD_PRENORM or hw <= self.FOLD_PRENORM_MAX_HW) and not self.pk.attn[prefix]["transformer"]
 
     def attn_layer(self, prefix, x, C, h, w, stats=None):
@@ -503,7 +516,11 @@ class UNetEngine:
             c_pad = a["out"].w.shape[-2]
             if self.FUSE_KVCTX and a["kv_safe"]:
                 # k | v never reach memory: the KVCTX epilogue reduces them into {C, S} per (image, head)
-                if stats is None:
+                pn_eps = 1e-5 if self.prenorm_in_kernel(prefix, C, hw) else None
+                if pn_eps is not None:
+                    assert stats is None
+                    xn = x                              # raw tensor: the kernels normalise each tile in shared memory
+                elif stats is None:
                     xn = self.buf(B, h, w, C)
                     self.add(prefix + "prenorm", lambda: ops.layernorm_rows(x, xn, B * hw, C, None, None, 1e-5))
                 else:
@@ -515,13 +532,13 @@ class UNetEngine:
                 # partial {C, S} records, one per CTA (and epilogue group) that touches the image, merged in slot order by
                 # the fold kernel: no atomics, so an evaluation is bit-reproducible
                 nslots = ops.ctx_slots(B, h, w, kv_tc)
-                ctx = self.buf(B, 4, nslots, 32 * 34, dtype=torch.float32)
+                ctx = self.buf(B, 4, nslots, ops.KV_G_REC if pn_eps is not None else 32 * 34, dtype=torch.float32)
                 if kv_tc:
                     # ... and reduced on tcgen05 too: P^T V with MN-major operands, context accumulated in TMEM
                     # (measured: 128 -> 111 us at level 0; the C = 128 instances have room for one P|V buffer only
                     # and run 25 % slower than the KVCTX epilogue, so they keep it)
-                    plan = ops.KvPlan(xn, a["kv_grouped"], a["kv_shift"], ctx, B, hw, C, ln_stats=stats,
-                                      ln_colsum=a["kv_grouped_colsum"] if fold else None)
+                    plan = ops.KvPlan(xn, a["k_rows"] if pn_eps is not None else a["kv_grouped"], a["kv_shift"], ctx, B, hw, C,
+                                      ln_stats=stats, ln_colsum=a["kv_grouped_colsum"] if fold else None, prenorm_eps=pn_eps)
                     self.flops += plan.flops
                     self.conv_names.add(prefix + "to_kv")
                     self.add(prefix + "to_kv", plan.run)
@@ -533,9 +550,12 @@ class UNetEngine:
                 self.flops += 2.0 * B * 4 * 32 * 32 * hw
                 if self.FUSE_QOUT and C in (64, 128) and hw % 128 == 0:
                     # q never reaches memory either: to_q -> softmax -> W_eff q -> LayerNorm -> + x in one kernel
-                    self.add(prefix + "fold", lambda: ops.linattn_fold(ctx, B, hw, nslots, a["w_out"], C, c_pad, weff))
+                    if pn_eps is not None:
+                        self.add(prefix + "fold", lambda: ops.linattn_fold_g(ctx, B, hw, nslots, a["m_fold"], C, c_pad, weff))
+                    else:
+                        self.add(prefix + "fold", lambda: ops.linattn_fold(ctx, B, hw, nslots, a["w_out"], C, c_pad, weff))
                     plan = ops.QoutPlan(xn, a["q"].w, weff, x, out, a["b_out"], a["g_out"], 1e-5, B, hw, C, ln_stats=stats,
-                                        ln_colsum=a["q_colsum"] if fold else None)
+                                        ln_colsum=a["q_colsum"] if fold else None, prenorm_eps=pn_eps)
                     self.flops += plan.flops
                     self.conv_names.add(prefix + "to_q_out")
                     self.add(prefix + "to_q_out", plan.run)
@@ -621,7 +641,7 @@ class UNetEngine:
             x = self.resblock(p + "0.", x, din, h, w)
             self.taps[p + "0"] = x
             skips.append((x, din))
-            st = self.buf(B * h * w, 2, dtype=torch.float32) if self.needs_stats(p + "2.", h * w) else None
+            st = self.buf(B * h * w, 2, dtype=torch.float32) if self.needs_stats(p + "2.", h * w, din) else None
             x = self.resblock(p + "1.", x, din, h, w, stats=st)
             self.taps[p + "1"] = x
             x = self.attn_layer(p + "2.", x, din, h, w, stats=st)
@@ -638,7 +658,7 @@ class UNetEngine:
             x = y
             self.taps[p + "3"] = x
         md = cfg.mid_dim
-        st = self.buf(B * h * w, 2, dtype=torch.float32) if self.needs_stats("mid_attn.", h * w) else None
+        st = self.buf(B * h * w, 2, dtype=torch.float32) if self.needs_stats("mid_attn.", h * w, md) else None
         x = self.resblock("mid_block1.", x, md, h, w, stats=st)
         self.taps["mid_block1"] = x
         x = self.attn_layer("mid_attn.", x, md, h, w, stats=st)
@@ -653,7 +673,7 @@ class UNetEngine:
             x = self.resblock(p + "0.", x, dout, h, w, skip=sk, sc=sc)
             self.taps[p + "0"] = x
             sk, sc = skips.pop()
-            st = self.buf(B * h * w, 2, dtype=torch.float32) if self.needs_stats(p + "2.", h * w) else None
+            st = self.buf(B * h * w, 2, dtype=torch.float32) if self.needs_stats(p + "2.", h * w, dout) else None
             x = self.resblock(p + "1.", x, dout, h, w, skip=sk, sc=sc, stats=st)
             self.taps[p + "1"] = x
             x = self.attn_layer(p + "2.", x, dout, h, w, stats=st)

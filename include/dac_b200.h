@@ -200,6 +200,12 @@ int dac_linattn_context(const void* kv, int32_t B, int32_t hw, int32_t nchunks, 
 int dac_linattn_fold(const float* partial, int32_t B, int32_t hw, int32_t nchunks, const float* w_out /*[C,128] fp32*/,
                      int32_t C, int32_t c_pad, void* weff /*[B][c_pad][128] bf16*/, dac_stream_t stream);
 
+/* The fold for dac_linattn_kv's in-kernel-PreNorm mode: partial = [B][4][nslots][2080] records {G[32][64], S[32]};
+ * m_fold = fp32 [4][C][64], M_h[c'][c] = sum_e W_out[c'][h*32+e] W_v[h*32+e][c] (W_v = the bf16 gain-folded value rows of
+ * to_qkv); weff[b][c'][h*32+d] = sum_c G[b,h,d,c] M_h[c'][c] / (S[b,h,d] hw) (MU:170-184 with the context never formed). */
+int dac_linattn_fold_g(const float* partial, int32_t B, int32_t hw, int32_t nslots, const float* m_fold /*[4,C,64] fp32*/,
+                       int32_t C, int32_t c_pad, void* weff /*[B][c_pad][128] bf16*/, dac_stream_t stream);
+
 /* Partial records per (image, head) that the context-reducing kernels need: an image's tiles are contiguous in the tile
  * order and CTA b owns tiles [tiles*b/grid, tiles*(b+1)/grid), grid = min(tiles, SM count); every CTA that touches an
  * image stores `groups` partials for it (2 for DAC_EPI_KVCTX - one per epilogue group - 1 for dac_linattn_kv).  Returns
@@ -214,11 +220,17 @@ int32_t dac_linattn_ctx_slots(int32_t B, int32_t tiles_per_image, int32_t groups
  * wkv: bf16 [256][C], rows packed per head pair g as k_2g k_2g+1 v_2g v_2g+1.  Replaces DAC_EPI_KVCTX where it fits.
  * Folded PreNorm (MU:89-97): with ln_stats ([B*hw][2] fp32 {mean, rstd} per pixel, written by the producing layer's
  * stats_out) and ln_colsum ([256] fp32 row sums of the bf16 wkv rows, same packed order) `xn` is the RAW input and the
- * epilogue finishes the normalisation: W' LN(x) = rstd (W' x - mean colsum(W')); both NULL: xn is already normalised. */
+ * epilogue finishes the normalisation: W' LN(x) = rstd (W' x - mean colsum(W')); both NULL: xn is already normalised.
+ * In-kernel PreNorm (prenorm != 0; C = 64, ln_stats NULL): `xn` is the RAW input and every 128 x 64 tile is normalised in
+ * shared memory between the TMA load and the MMA (gain-free channel LayerNorm with eps prenorm_eps, MU:77-86; bf16
+ * result, i.e. what a separate LayerNorm pass would have written) - no LayerNorm launch, no normalised tensor.  In this
+ * mode the values are never formed: wkv holds ONLY the key rows, bf16 [128][64] in head order, and the kernel accumulates
+ * G[(h,d)][c] = sum_px P[px][(h,d)] xn[px][c] and S (context = G W_v^T / S); ctx_acc is [B][4][ctx_slots][2080] fp32
+ * records {G[32][64], S[32]}, to be merged by dac_linattn_fold_g (NOT dac_linattn_fold). */
 typedef struct dac_kv_plan* dac_kv_t;
 int dac_linattn_kv_create(const void* xn, const void* wkv, const float* kv_shift, float* ctx_acc, int32_t ctx_slots,
                           const float* ln_stats, const float* ln_colsum, int32_t B, int32_t hw, int32_t C,
-                          dac_kv_t* plan);
+                          int32_t prenorm, float prenorm_eps, dac_kv_t* plan);
 int dac_linattn_kv_launch(dac_kv_t plan, dac_stream_t stream);
 void dac_linattn_kv_destroy(dac_kv_t plan);
 
@@ -228,11 +240,15 @@ void dac_linattn_kv_destroy(dac_kv_t plan);
  * xn, res, out: bf16 [B*hw, C] (C = 64 or 128, hw % 128 == 0); wq: bf16 [128][C] (gain-folded rows of to_qkv);
  * weff: bf16 [B][c_pad][128] from dac_linattn_fold.  Replaces the to_q (DAC_EPI_QKV) + to_out (DAC_EPI_LN) pair.
  * ln_stats / ln_colsum ([B*hw][2], [128]; or both NULL): folded PreNorm as for dac_linattn_kv_create - xn is then the
- * raw input (normally the same tensor as res). */
+ * raw input (normally the same tensor as res).
+ * In-kernel PreNorm (prenorm != 0; C = 64, ln_stats NULL, res == xn): `xn` is the RAW input; every 128 x 64 tile is read
+ * ONCE, normalised in shared memory into the A operand of the first GEMM (gain-free channel LayerNorm, eps prenorm_eps,
+ * MU:77-86) and reused as the residual - no LayerNorm launch, no normalised tensor, half the input traffic. */
 typedef struct dac_qout_plan* dac_qout_t;
 int dac_linattn_qout_create(const void* xn, const void* wq, const void* weff, int32_t c_pad, const void* res,
                             void* out, const float* bias, const float* ln_g, float ln_eps, const float* ln_stats,
-                            const float* ln_colsum, int32_t B, int32_t hw, int32_t C, dac_qout_t* plan);
+                            const float* ln_colsum, int32_t B, int32_t hw, int32_t C, int32_t prenorm,
+                            float prenorm_eps, dac_qout_t* plan);
 int dac_linattn_qout_launch(dac_qout_t plan, dac_stream_t stream);
 void dac_linattn_qout_destroy(dac_qout_t plan);
 

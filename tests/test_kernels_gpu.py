@@ -468,6 +468,43 @@ def test_linear_attention_kv_tensor_core_context(ops, gen, B, H, W, C):
     assert (got - ctx_ref).abs().max().item() <= 6e-3 * scale, (got - ctx_ref).abs().max().item() / scale
 
 
+@pytest.mark.parametrize("B,H,W", [(3, 32, 32), (5, 64, 48), (40, 16, 8), (1, 128, 128), (16, 8, 16)])
+def test_linear_attention_kv_in_kernel_prenorm(ops, gen, B, H, W):
+    """dac_linattn_kv with prenorm: the RAW 64-channel tensor goes in, every tile is normalised in shared memory (gain-free
+    channel LayerNorm, module_util.py:77-97) before the k GEMM, and the kernel accumulates G = P^T xn and S = P^T 1 per
+    image (the values are never formed); checked as G W_v^T / (S hw) against LayerNorm -> bf16 -> to_kv ->
+    softmax_pixels(k) v^T / hw in fp32 (module_util.py:170-177), and bit-reproducible."""
+    C, hw = 64, H * W
+    x = rnd(gen, B, C, H, W) * 1.7 + 0.3
+    xr = nhwc(x)                                               # what the producing layer stored (bf16)
+    xf = nchw(xr)
+    xn = bf((xf - xf.mean(1, keepdim=True)) * torch.rsqrt(xf.var(1, unbiased=False, keepdim=True) + 1e-5)).float()
+    wkv = rnd(gen, 256, C, scale=C ** -0.5)
+    wkv[:128] *= 1.5
+    shift = 1.02 * bf(wkv[:128]).float().norm(dim=1) * math.sqrt(C)
+    ctx = torch.full((B, 4, ops.ctx_slots(B, H, W, True), ops.KV_G_REC), float("nan"), device="cuda")
+    plan = ops.KvPlan(xr, wkv[:128].to(torch.bfloat16).contiguous(), (shift * 1.4426950408889634).contiguous(), ctx, B, hw,
+                      C, prenorm_eps=1e-5)
+    for _ in range(2):
+        plan.run()
+    torch.cuda.synchronize()
+    first = ctx.clone()
+    plan.run()
+    torch.cuda.synchronize()
+    assert torch.equal(ctx, first)
+    assert torch.equal(nhwc(x), xr)                            # the input tensor is not modified (normalised in smem only)
+    rec = ctx.sum(2)                                           # [B, 4, 2080]
+    G, S = rec[..., :2048].reshape(B, 4, 32, 64), rec[..., 2048:2080]
+    wv = bf(wkv[128:]).float().reshape(4, 32, C)
+    got = torch.einsum("bhdc,hec->bhde", G, wv) / (S[..., None] * hw)
+    kvr = F.conv2d(xn, bf(wkv).float()[:, :, None, None]).reshape(B, 2, 4, 32, hw)
+    k, v = kvr[:, 0].softmax(-1), kvr[:, 1] / hw
+    ctx_ref = torch.einsum("bhdn,bhen->bhde", k, v)
+    scale = ctx_ref.abs().max().item()
+    assert torch.isfinite(got).all()
+    assert (got - ctx_ref).abs().max().item() <= 6e-3 * scale, (got - ctx_ref).abs().max().item() / scale
+
+
 @pytest.mark.parametrize("B,H,W,C", [(3, 32, 32, 64), (2, 16, 40, 128), (5, 64, 48, 64), (1, 8, 16, 128)])
 def test_linear_attention_chained_q_out(ops, gen, B, H, W, C):
     """Whole LinearAttention block on the fused path: KVCTX context -> fold -> chained kernel (to_q, head softmax,
@@ -552,6 +589,49 @@ def test_linear_attention_folded_prenorm(ops, gen, B, H, W, C, kv_tc):
         pq.run()
     torch.cuda.synchronize()
     assert_close_bf16(nchw(out), ref, f"folded PreNorm linear attention {H}x{W} C={C}", rel=2 ** -5, abs_=2e-2)
+
+
+@pytest.mark.parametrize("B,H,W", [(3, 32, 32), (5, 64, 48), (1, 8, 16), (40, 16, 8), (2, 128, 128)])
+def test_linear_attention_in_kernel_prenorm(ops, gen, B, H, W):
+    """PreNorm inside the fused 64-channel LinearAttention kernels (dac_linattn_kv / dac_linattn_qout with prenorm): both
+    take the RAW tensor, normalise each tile in shared memory, and the q-out kernel reuses the raw tile as the residual;
+    checked against PreNorm(LinearAttention) + x of the oracle (module_util.py:89-97,157-185) and for bit-reproducibility."""
+    from oracle import unet_oracle as O
+    C, hw = 64, H * W
+    x = rnd(gen, B, C, H, W) * 1.7 + 0.4
+    xh = nhwc(x)                                                 # bf16 NHWC: what the producing ResBlock stored
+    xf = nchw(xh)
+    g = 1 + 0.2 * rnd(gen, C)
+    sd = {"to_qkv.weight": rnd(gen, 384, C, 1, 1, scale=C ** -0.5),
+          "to_out.0.weight": rnd(gen, C, 128, 1, 1, scale=128 ** -0.5 * 8),
+          "to_out.0.bias": rnd(gen, C, scale=0.1), "to_out.1.g": (1 + 0.1 * rnd(gen, 1, C, 1, 1))}
+    wf = sd["to_qkv.weight"].reshape(384, C) * g[None, :]        # W' = W diag(g)
+    sdr = dict(sd)
+    sdr["to_qkv.weight"] = bf(wf).float().reshape(384, C, 1, 1)
+    xn = (xf - xf.mean(1, keepdim=True)) * torch.rsqrt(xf.var(1, unbiased=False, keepdim=True) + 1e-5)
+    ref = O.linear_attention(sdr, "", xn) + xf
+    shift = 1.02 * bf(wf[128:256]).float().norm(dim=1) * math.sqrt(C)
+    ns = ops.ctx_slots(B, H, W, True)
+    ctx = torch.zeros(B, 4, ns, ops.KV_G_REC, device="cuda")
+    c_pad = ops.choose_block_n(C)[1]
+    weff = torch.zeros(B, c_pad, 128, device="cuda", dtype=torch.bfloat16)
+    out = torch.full((B, H, W, C), float("nan"), device="cuda", dtype=torch.bfloat16)
+    pkv = ops.KvPlan(xh, wf[128:256].to(torch.bfloat16).contiguous(), (shift * 1.4426950408889634).contiguous(), ctx, B, hw,
+                     C, prenorm_eps=1e-5)
+    m_fold = ops.kv_fold_matrix(sd["to_out.0.weight"].reshape(C, 128), wf[256:])
+    pq = ops.QoutPlan(xh, ops.pack_linear(wf[:128].contiguous()).w, weff, xh, out, sd["to_out.0.bias"],
+                      sd["to_out.1.g"].reshape(-1).contiguous(), 1e-5, B, hw, C, prenorm_eps=1e-5)
+    outs = []
+    for _ in range(3):
+        out.fill_(float("nan"))
+        pkv.run()
+        ops.linattn_fold_g(ctx, B, hw, ns, m_fold, C, c_pad, weff)
+        pq.run()
+        torch.cuda.synchronize()
+        outs.append(out.clone())
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])
+    assert torch.equal(nhwc(x), xh)                              # the input is not modified
+    assert_close_bf16(nchw(out), ref, f"in-kernel PreNorm linear attention {H}x{W}", rel=2 ** -5, abs_=2e-2)
 
 
 @pytest.mark.parametrize("B,H,W,C", [(2, 32, 32, 64), (1, 16, 48, 128), (1, 16, 16, 256)])

@@ -19,6 +19,12 @@ CASES = {
     "l0_toout": (16, 256, 256, 128, 64, "toout"),
     "l0_qout": (16, 256, 256, 64, 64, "qout"),
     "l0_kvtc": (16, 256, 256, 64, 256, "kvtc"),
+    "l0_qout_pn": (16, 256, 256, 64, 64, "qout_pn"),
+    "l1_qout": (16, 128, 128, 64, 64, "qout"),
+    "l1_qout_pn": (16, 128, 128, 64, 64, "qout_pn"),
+    "l0_kvtc_pn": (16, 256, 256, 64, 256, "kvtc_pn"),
+    "l1_kvtc_pn": (16, 128, 128, 64, 256, "kvtc_pn"),
+    "l1_kvtc": (16, 128, 128, 64, 256, "kvtc"),
     "l0_pair": (16, 256, 256, 64, 64, "pair"),
     "l0_pair_cat": (16, 256, 256, 128, 64, "pair"),
     "l1_pair": (16, 128, 128, 64, 64, "pair"),
@@ -88,11 +94,13 @@ def make(name):
         else:
             plan = ops.ConvPlan(x, cin, ops.pack_conv(w), out, B=B, H=H, W=W, act=L.ACT_SILU, rsrc0=r0, rc0=64, rsrc1=r1,
                                 rc1=64, rweight=ops.pack_linear(wr))
-    elif kind == "kvtc":
+    elif kind in ("kvtc", "kvtc_pn"):
         w = torch.randn(cout, cin, device="cuda", generator=g) * cin ** -0.5
         shift = torch.full((128,), 12.0, device="cuda")
-        ctx = torch.zeros(B, 4, ops.ctx_slots(B, H, W, True), 32 * 34, device="cuda")
-        plan = ops.KvPlan(x.reshape(B * H * W, cin), ops.pack_kv_grouped(w), shift, ctx, B, H * W, cin)
+        pn = kind == "kvtc_pn"
+        ctx = torch.zeros(B, 4, ops.ctx_slots(B, H, W, True), ops.KV_G_REC if pn else 32 * 34, device="cuda")
+        plan = ops.KvPlan(x.reshape(B * H * W, cin), w[:128].to(torch.bfloat16).contiguous() if pn else ops.pack_kv_grouped(w),
+                          shift, ctx, B, H * W, cin, prenorm_eps=1e-5 if pn else None)
         plan.info = lambda: {}
     elif kind == "toout":
         w = torch.randn(cout, cin, device="cuda", generator=g) * cin ** -0.5
@@ -101,6 +109,12 @@ def make(name):
         plan = ops.ConvPlan(x, cin, ops.pack_linear(w), out, B=B, H=H, W=W, epi=L.EPI_LN,
                             bias=torch.zeros(cout, device="cuda"), ln_g=torch.ones(cout, device="cuda"), res=res,
                             per_image_w=True, weight_override=weff)
+    elif kind == "qout_pn":
+        wq = (torch.randn(1, 128, cin, device="cuda", generator=g) * cin ** -0.5).to(torch.bfloat16)
+        weff = (torch.randn(B, cout, 128, device="cuda", generator=g) * 128 ** -0.5).to(torch.bfloat16)
+        plan = ops.QoutPlan(x, wq, weff, x, out, torch.zeros(cout, device="cuda"), torch.ones(cout, device="cuda"),
+                            1e-5, B, H * W, cout, prenorm_eps=1e-5)
+        plan.info = lambda: {}
     elif kind == "qout":
         wq = (torch.randn(1, 128, cin, device="cuda", generator=g) * cin ** -0.5).to(torch.bfloat16)
         weff = (torch.randn(B, cout, 128, device="cuda", generator=g) * 128 ** -0.5).to(torch.bfloat16)
