@@ -13,6 +13,7 @@
 #include "common.h"
 #include "linattn_kv_common.h"
 #include "ptx.cuh"
+#include "tile_common.cuh"
 
 namespace dac {
 
@@ -216,16 +217,20 @@ __global__ void __launch_bounds__(256) linattn_fold_kernel(const float* __restri
 //   weff[b][c'][h*32+d] = sum_c G[b,h,d,c] M_h[c'][c] / (S[b,h,d] hw),   M_h = W_out[:, h] W_v[h]   (constant, fp32)
 // One CTA per (head, image, group of kFoldRows d rows); slots are added in a FIXED order (two interleaved chains + one
 // add, shuffle trees for S): bit-reproducible.  No running-max weights: the k|v kernels use a data-independent shift.
-__global__ void __launch_bounds__(256) linattn_fold_g_kernel(const float* __restrict__ partial, int hw, int nslots,
-                                                             const float* __restrict__ m_fold, int C, int c_pad,
-                                                             __nv_bfloat16* __restrict__ weff) {
+__global__ void __launch_bounds__(256) linattn_fold_g_kernel(const float* __restrict__ partial, int hw, int slots,
+                                                             int tiles, int grid, const float* __restrict__ m_fold, int C,
+                                                             int c_pad, __nv_bfloat16* __restrict__ weff) {
   extern __shared__ float fold_sm[];
   float* msm = fold_sm;                          // [C][65]: M_h[c'][c]
   float* g = msm + C * 65;                       // [kFoldRows][64]
   __shared__ float inv_s[kFoldRows];
   const int h = blockIdx.x, b = blockIdx.y, d0 = blockIdx.z * kFoldRows, t = threadIdx.x;
   const int warp = t >> 5, lane = t & 31;
-  const float* pbase = partial + (static_cast<int64_t>(b) * 4 + h) * nslots * kKvGRec;
+  const float* pbase = partial + (static_cast<int64_t>(b) * 4 + h) * slots * kKvGRec;
+  // the records that exist: one per CTA of the producing kernel whose tile range touches image b (the rest of the
+  // `slots` records is never written - and never read, so ctx_acc needs no clearing between launches)
+  const int tpi = hw / 128;
+  const int nslots = tile_owner((b + 1) * tpi - 1, tiles, grid) - tile_owner(b * tpi, tiles, grid) + 1;
   griddep_launch();
   for (int i = t; i < C * 64; i += 256)         // a constant: staged while the producing kernel drains
     msm[(i >> 6) * 65 + (i & 63)] = __ldg(m_fold + static_cast<int64_t>(h) * C * 64 + i);
@@ -295,8 +300,15 @@ extern "C" int dac_linattn_fold_g(const float* partial, int32_t B, int32_t hw, i
   if (!partial || !m_fold || !weff) return set_error(-1, "dac_linattn_fold_g: null argument");
   if (nslots < 1 || nslots > 2048) return set_error(-2, "dac_linattn_fold_g: nslots must be in [1,2048]");
   if (C <= 0 || C > 128 || c_pad < C) return set_error(-2, "dac_linattn_fold_g: C must be in [1,128], c_pad >= C");
+  if (hw <= 0 || hw % 128) return set_error(-2, "dac_linattn_fold_g: hw must be a multiple of 128");
   const size_t smem = sizeof(float) * (static_cast<size_t>(C) * 65 + kFoldRows * 64);
+  // the producer's geometry (dac_linattn_kv_create): B * hw / 128 tiles in contiguous ranges over min(tiles, SMs) CTAs
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int tiles = B * (hw / 128), grid = tiles < sms ? tiles : sms;
+  if (nslots < max_image_span(B, hw / 128, grid)) return set_error(-2, "dac_linattn_fold_g: nslots below dac_linattn_ctx_slots");
   launch_k(linattn_fold_g_kernel, dim3(4, B, 32 / kFoldRows), dim3(256), smem, static_cast<cudaStream_t>(stream), partial, hw,
-           nslots, m_fold, C, c_pad, static_cast<__nv_bfloat16*>(weff));
+           nslots, tiles, grid, m_fold, C, c_pad, static_cast<__nv_bfloat16*>(weff));
   return check_launch("linattn_fold_g_kernel");
 }

@@ -16,6 +16,7 @@
 // TMEM: [0,128) / [128,256) GEMM-1 accumulators of group 0 / 1, [256,384) C, [384,400) S.
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <cstdlib>
 #include <new>
 
 #include "../../include/dac_b200.h"
@@ -405,6 +406,9 @@ extern "C" int dac_linattn_kv_create(const void* xn, const void* wkv, const floa
     k2.ctx_acc = ctx_acc;
     k2.slots = ctx_slots;
     k2.ln_eps = prenorm_eps;
+    const char* dbg = getenv("DAC_KV2_DBG");
+    k2.dbg = dbg ? atoi(dbg) : 0;
+    k2.prof = nullptr;
   }
   if (ctx_slots < max_image_span(B, k.tiles_per_image, pl->grid)) {
     const int need = max_image_span(B, k.tiles_per_image, pl->grid);
@@ -425,9 +429,10 @@ extern "C" int dac_linattn_kv_create(const void* xn, const void* wkv, const floa
 extern "C" int dac_linattn_kv_launch(dac_kv_t pl, dac_stream_t stream) {
   if (!pl) return set_error(-1, "dac_linattn_kv_launch: null plan");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  cudaError_t e = cudaMemsetAsync(pl->kp.ctx_acc, 0, sizeof(float) * pl->B * 4 * pl->kp.slots * (pl->prenorm ? kKvGRec : kCtxRec), st);
-  if (e != cudaSuccess) return set_error(-20, "dac_linattn_kv_launch: memset failed: %s", cudaGetErrorString(e));
+  // in-kernel-PreNorm mode: every record dac_linattn_fold_g reads is written by this launch - nothing to clear
   if (pl->prenorm) return dac_kv2_launch(pl->mapX, pl->mapW, pl->kp2, pl->grid, st);
+  cudaError_t e = cudaMemsetAsync(pl->kp.ctx_acc, 0, sizeof(float) * pl->B * 4 * pl->kp.slots * kCtxRec, st);
+  if (e != cudaSuccess) return set_error(-20, "dac_linattn_kv_launch: memset failed: %s", cudaGetErrorString(e));
   if (pl->C == 64) linattn_kv_kernel<64><<<pl->grid, kThreads, pl->smem, st>>>(pl->mapX, pl->mapW, pl->kp);
   else linattn_kv_kernel<128><<<pl->grid, kThreads, pl->smem, st>>>(pl->mapX, pl->mapW, pl->kp);
   return check_launch("linattn_kv_kernel");

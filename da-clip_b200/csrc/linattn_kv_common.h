@@ -11,6 +11,8 @@ struct Kv2Params {
   float* ctx_acc;          // [B][4][slots][kKvGRec]: one partial record per (CTA, image)
   int slots;
   float ln_eps;            // eps of the channel LayerNorm applied to the raw input rows
+  long long* prof;         // DAC_KV2_PROF builds: [22 warps][8] cycle totals of CTA 0
+  int dbg;                 // timing experiments only (DAC_KV2_DBG): 1 no exp2, 2 no GEMM 2, 4 no P staging, 8 no row moments
 };
 }  // namespace dac
 

@@ -412,13 +412,15 @@ static int encode_2d(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t r
 extern "C" int dac_linattn_qout_create(const void* xn, const void* wq, const void* weff, int32_t c_pad,
                                        const void* res, void* out, const float* bias, const float* ln_g,
                                        float ln_eps, const float* ln_stats, const float* ln_colsum, int32_t B,
-                                       int32_t hw, int32_t C, int32_t prenorm, float prenorm_eps, dac_qout_t* plan) {
+                                       int32_t hw, int32_t C, int32_t prenorm, float prenorm_eps, const float* q_shift,
+                                       dac_qout_t* plan) {
   if (!xn || !wq || !weff || !res || !out || !ln_g || !plan) return set_error(-1, "dac_linattn_qout_create: null argument");
   *plan = nullptr;
   if (C != 64 && C != 128) return set_error(-2, "dac_linattn_qout_create: C must be 64 or 128 (got %d)", C);
   if (B <= 0 || hw <= 0 || hw % kTileM) return set_error(-2, "dac_linattn_qout_create: hw must be a multiple of 128");
   if (prenorm && (C != 64 || ln_stats || res != xn))
     return set_error(-2, "dac_linattn_qout_create: in-kernel PreNorm needs C = 64, no ln_stats and res == xn (the raw tensor)");
+  if (q_shift && !prenorm) return set_error(-2, "dac_linattn_qout_create: q_shift belongs to the in-kernel PreNorm mode");
   if (c_pad < C || (c_pad & 7)) return set_error(-2, "dac_linattn_qout_create: bad c_pad");
   if ((reinterpret_cast<uintptr_t>(xn) | reinterpret_cast<uintptr_t>(wq) | reinterpret_cast<uintptr_t>(weff) |
        reinterpret_cast<uintptr_t>(res) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(bias) |
@@ -467,10 +469,27 @@ extern "C" int dac_linattn_qout_create(const void* xn, const void* wq, const voi
     k2.tiles = k.tiles;
     k2.tiles_per_image = k.tiles_per_image;
     k2.c_pad = c_pad;
-    k2.bias = bias;
-    k2.ln_g = ln_g;
     k2.ln_eps = ln_eps;
     k2.prenorm_eps = prenorm_eps;
+    // bias, gain and the softmax bounds are constants of the layer: they travel in the kernel parameters
+    cudaError_t ce = cudaMemcpy(k2.ln_g, ln_g, sizeof(k2.ln_g), cudaMemcpyDeviceToHost);
+    if (ce == cudaSuccess && bias) ce = cudaMemcpy(k2.bias, bias, sizeof(k2.bias), cudaMemcpyDeviceToHost);
+    if (!bias) for (float& b : k2.bias) b = 0.f;
+    k2.use_max = q_shift ? 0 : 1;
+    for (float& q : k2.q_shift) q = 0.f;
+    if (ce == cudaSuccess && q_shift) {
+      float sh[128];
+      ce = cudaMemcpy(sh, q_shift, sizeof(sh), cudaMemcpyDeviceToHost);
+      for (int h = 0; h < 4 && ce == cudaSuccess; ++h) {
+        float m = sh[h * 32];
+        for (int d = 1; d < 32; ++d) m = sh[h * 32 + d] > m ? sh[h * 32 + d] : m;
+        k2.q_shift[h] = m;
+      }
+    }
+    if (ce != cudaSuccess) {
+      delete pl;
+      return set_error(-20, "dac_linattn_qout_create: reading the layer constants: %s", cudaGetErrorString(ce));
+    }
   }
   *plan = pl;
   return 0;

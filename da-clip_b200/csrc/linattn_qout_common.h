@@ -6,10 +6,12 @@
 namespace dac {
 struct Qout2Params {
   int tiles, tiles_per_image, c_pad;
-  const float* bias;       // [64] to_out bias (may be NULL)
-  const float* ln_g;       // [64] gain of the output LayerNorm
+  int use_max;             // 1: softmax shift = the row maximum; 0: the data-independent per-head bound q_shift
   float ln_eps;            // eps of the output LayerNorm
-  float prenorm_eps;       // eps of the channel LayerNorm applied to the raw input rows
+  float prenorm_eps;       // eps of the channel LayerNorm folded into GEMM 1
+  float q_shift[4];        // per head: max_d c_d * log2(e)
+  float bias[64];          // to_out bias (zeros if absent): in the parameter constant bank, i.e. instruction operands
+  float ln_g[64];          // gain of the output LayerNorm
 };
 }  // namespace dac
 

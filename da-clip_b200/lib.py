@@ -98,7 +98,7 @@ SYMBOLS = {
     "dac_linattn_kv_create": (C.c_int, [_p, _p, _p, _p, _i32, _p, _p, _i32, _i32, _i32, _i32, _f, C.POINTER(_p)]),
     "dac_linattn_kv_launch": (C.c_int, [_p, _p]),
     "dac_linattn_kv_destroy": (None, [_p]),
-    "dac_linattn_qout_create": (C.c_int, [_p, _p, _p, _i32, _p, _p, _p, _p, _f, _p, _p, _i32, _i32, _i32, _i32, _f, C.POINTER(_p)]),
+    "dac_linattn_qout_create": (C.c_int, [_p, _p, _p, _i32, _p, _p, _p, _p, _f, _p, _p, _i32, _i32, _i32, _i32, _f, _p, C.POINTER(_p)]),
     "dac_linattn_qout_launch": (C.c_int, [_p, _p]),
     "dac_linattn_qout_destroy": (None, [_p]),
     "dac_clip_resample_h": (C.c_int, [_p, _i32, _i32, _p, _i32, _p, _p, _i32, _i32, _i32, _p]),

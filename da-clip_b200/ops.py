@@ -349,7 +349,7 @@ class KvPlan:
 
     def __init__(self, xn, wkv_grouped, kv_shift, ctx_acc, B, hw, Cn, ln_stats=None, ln_colsum=None, prenorm_eps=None):
         """prenorm_eps: `xn` is the RAW tensor and the kernel applies the gain-free channel LayerNorm itself (C = 64); then
-        `wkv_grouped` holds only the key rows ([128, 64] bf16, head order) and `ctx_acc` is [B, 4, slots, KV_G_REC] for
+        `wkv_grouped` holds only the ROW-CENTRED key rows ([128, 64] bf16, head order; centre_rows) and `ctx_acc` is [B, 4, slots, KV_G_REC] for
         linattn_fold_g."""
         L.require_cuda(xn, wkv_grouped, kv_shift, ctx_acc, ln_stats, ln_colsum)
         lib = L.load()
@@ -376,17 +376,20 @@ class QoutPlan:
     """LinearAttention query side (to_q softmax -> W_eff q -> LayerNorm -> + x) as one chained-GEMM launch."""
 
     def __init__(self, xn, wq, weff, res, out, bias, ln_g, ln_eps, B, hw, Cn, ln_stats=None, ln_colsum=None,
-                 prenorm_eps=None):
-        """prenorm_eps: `xn` (== `res`) is the RAW tensor and the kernel applies the gain-free channel LayerNorm itself (C = 64)."""
-        L.require_cuda(xn, wq, weff, res, out, ln_g, ln_stats, ln_colsum)
+                 prenorm_eps=None, q_shift=None):
+        """prenorm_eps: `xn` (== `res`) is the RAW tensor, `wq` the ROW-CENTRED weight (centre_rows) and the kernel folds the
+        gain-free channel LayerNorm into its first GEMM (C = 64); q_shift: [128] fp32 bounds c_d log2(e) for a softmax shift
+        without the row maximum."""
+        L.require_cuda(xn, wq, weff, res, out, ln_g, ln_stats, ln_colsum, q_shift)
         lib = L.load()
         h = C.c_void_p()
         L.check(lib.dac_linattn_qout_create(xn.data_ptr(), wq.data_ptr(), weff.data_ptr(), weff.shape[-2],
                                             res.data_ptr(), out.data_ptr(), bias.data_ptr() if bias is not None else None,
                                             ln_g.data_ptr(), ln_eps, L.ptr(ln_stats), L.ptr(ln_colsum), B, hw, Cn,
-                                            int(prenorm_eps is not None), float(prenorm_eps or 0.0), C.byref(h)))
+                                            int(prenorm_eps is not None), float(prenorm_eps or 0.0), L.ptr(q_shift),
+                                            C.byref(h)))
         self.handle, self._lib = h, lib
-        self._keep = (xn, wq, weff, res, out, bias, ln_g, ln_stats, ln_colsum)
+        self._keep = (xn, wq, weff, res, out, bias, ln_g, ln_stats, ln_colsum, q_shift)
         self.flops = 2.0 * B * hw * 128 * Cn * 2
 
     def run(self):
@@ -484,12 +487,19 @@ def linattn_fold_g(partial, B, hw, nslots, m_fold, C_, c_pad, weff):
                                         L.stream_ptr()))
 
 
+def centre_rows(w):
+    """W - rowmean(W): W_c x = W (x - mean(x)), so a GEMM on the RAW tensor followed by the pixel's rstd equals W LN(x)."""
+    return w - w.mean(dim=1, keepdim=True)
+
+
 def kv_fold_matrix(w_out, w_v):
-    """M_h[c'][c] = sum_e W_out[c'][h*32+e] W_v[h*32+e][c] (fp32 [4, C, Cin]) from to_out's [C, 128] weight and the
-    gain-folded value rows [128, Cin] of to_qkv, rounded to bf16 first as the GEMM operand would have been."""
-    wv = w_v.to(torch.bfloat16).float().reshape(4, 32, -1)
+    """M_h[c'][c] = sum_e W_out[c'][h*32+e] W_vc[h*32+e][c] (fp32 [4, C, Cin]) from to_out's [C, 128] weight and the
+    gain-folded value rows [128, Cin] of to_qkv - row-centred and rounded to bf16 as the GEMM operand would have been; the
+    rows of M_h are centred again in fp32 so that the per-pixel mean drops out of G' M_h^T exactly."""
+    wv = centre_rows(w_v.float()).to(torch.bfloat16).float().reshape(4, 32, -1)
     wo = w_out.float().reshape(w_out.shape[0], 4, 32).permute(1, 0, 2)
-    return torch.bmm(wo, wv).contiguous()
+    m = torch.bmm(wo, wv)
+    return (m - m.mean(dim=2, keepdim=True)).contiguous()
 
 
 KV_G_REC = 32 * 64 + 32      # floats per {G, S} record of the in-kernel-PreNorm k kernel

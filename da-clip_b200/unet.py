@@ -343,6 +343,8 @@ class PackedUNet:
             a.update(q=ops.pack_linear(wq[:128].contiguous()), kv=ops.pack_linear(wq[128:].contiguous()),
                      kv_grouped=ops.pack_kv_grouped(wq[128:]),
                      kv_shift=(kbound * 1.4426950408889634).contiguous(), kv_safe=bool(kbound.max().item() <= 40.0))
+            qbound = 1.02 * ops.centre_rows(wq[:128]).to(torch.bfloat16).float().norm(dim=1) * math.sqrt(dim)
+            a.update(q_shift=(qbound * 1.4426950408889634).contiguous() if qbound.max().item() <= 40.0 else None)
             colsum = wq.to(torch.bfloat16).float().sum(dim=1)                               # of the bf16 operand
             a.update(q_colsum=colsum[:128].contiguous(), kv_colsum=colsum[128:].contiguous(),
                      kv_grouped_colsum=ops.pack_kv_grouped(wq[128:]).float().sum(dim=1).contiguous())
@@ -351,8 +353,10 @@ class PackedUNet:
                      out=ops.pack_linear(f32(q + "to_out.0.weight")),
                      w_out=f32(q + "to_out.0.weight").reshape(dim, 128).contiguous(),
                      # in-kernel-PreNorm k kernel (64 channels): key rows only + the constant W_out,h W_v,h of its fold
-                     k_rows=wq[128:256].to(torch.bfloat16).contiguous(),
+                     # (row-centred weights: W_c x rstd = W LN(x), so those kernels take the raw tensor)
+                     k_rows=ops.centre_rows(wq[128:256]).to(torch.bfloat16).contiguous(),
                      m_fold=ops.kv_fold_matrix(f32(q + "to_out.0.weight").reshape(dim, 128), wq[256:384]),
+                     q_c=ops.pack_linear(ops.centre_rows(wq[:128]).contiguous()),
                      b_out=f32(q + "to_out.0.bias"), g_out=f32(q + "to_out.1.g").reshape(-1).contiguous())
             return a
         b = q + "transformer_blocks.0."
@@ -554,8 +558,9 @@ class UNetEngine:
                         self.add(prefix + "fold", lambda: ops.linattn_fold_g(ctx, B, hw, nslots, a["m_fold"], C, c_pad, weff))
                     else:
                         self.add(prefix + "fold", lambda: ops.linattn_fold(ctx, B, hw, nslots, a["w_out"], C, c_pad, weff))
-                    plan = ops.QoutPlan(xn, a["q"].w, weff, x, out, a["b_out"], a["g_out"], 1e-5, B, hw, C, ln_stats=stats,
-                                        ln_colsum=a["q_colsum"] if fold else None, prenorm_eps=pn_eps)
+                    plan = ops.QoutPlan(xn, (a["q_c"] if pn_eps is not None else a["q"]).w, weff, x, out, a["b_out"], a["g_out"],
+                                        1e-5, B, hw, C, ln_stats=stats, ln_colsum=a["q_colsum"] if fold else None,
+                                        prenorm_eps=pn_eps, q_shift=a["q_shift"] if pn_eps is not None else None)
                     self.flops += plan.flops
                     self.conv_names.add(prefix + "to_q_out")
                     self.add(prefix + "to_q_out", plan.run)

@@ -201,8 +201,8 @@ int dac_linattn_fold(const float* partial, int32_t B, int32_t hw, int32_t nchunk
                      int32_t C, int32_t c_pad, void* weff /*[B][c_pad][128] bf16*/, dac_stream_t stream);
 
 /* The fold for dac_linattn_kv's in-kernel-PreNorm mode: partial = [B][4][nslots][2080] records {G[32][64], S[32]};
- * m_fold = fp32 [4][C][64], M_h[c'][c] = sum_e W_out[c'][h*32+e] W_v[h*32+e][c] (W_v = the bf16 gain-folded value rows of
- * to_qkv); weff[b][c'][h*32+d] = sum_c G[b,h,d,c] M_h[c'][c] / (S[b,h,d] hw) (MU:170-184 with the context never formed). */
+ * m_fold = fp32 [4][C][64], M_h[c'][c] = sum_e W_out[c'][h*32+e] W_vc[h*32+e][c] (W_vc = the bf16 gain-folded, row-centred
+ * value rows of to_qkv; rows of M_h centred again in fp32); weff[b][c'][h*32+d] = sum_c G[b,h,d,c] M_h[c'][c] / (S[b,h,d] hw) (MU:170-184 with the context never formed). */
 int dac_linattn_fold_g(const float* partial, int32_t B, int32_t hw, int32_t nslots, const float* m_fold /*[4,C,64] fp32*/,
                        int32_t C, int32_t c_pad, void* weff /*[B][c_pad][128] bf16*/, dac_stream_t stream);
 
@@ -221,12 +221,13 @@ int32_t dac_linattn_ctx_slots(int32_t B, int32_t tiles_per_image, int32_t groups
  * Folded PreNorm (MU:89-97): with ln_stats ([B*hw][2] fp32 {mean, rstd} per pixel, written by the producing layer's
  * stats_out) and ln_colsum ([256] fp32 row sums of the bf16 wkv rows, same packed order) `xn` is the RAW input and the
  * epilogue finishes the normalisation: W' LN(x) = rstd (W' x - mean colsum(W')); both NULL: xn is already normalised.
- * In-kernel PreNorm (prenorm != 0; C = 64, ln_stats NULL): `xn` is the RAW input and every 128 x 64 tile is normalised in
- * shared memory between the TMA load and the MMA (gain-free channel LayerNorm with eps prenorm_eps, MU:77-86; bf16
- * result, i.e. what a separate LayerNorm pass would have written) - no LayerNorm launch, no normalised tensor.  In this
- * mode the values are never formed: wkv holds ONLY the key rows, bf16 [128][64] in head order, and the kernel accumulates
- * G[(h,d)][c] = sum_px P[px][(h,d)] xn[px][c] and S (context = G W_v^T / S); ctx_acc is [B][4][ctx_slots][2080] fp32
- * records {G[32][64], S[32]}, to be merged by dac_linattn_fold_g (NOT dac_linattn_fold). */
+ * In-kernel PreNorm (prenorm != 0; C = 64, ln_stats NULL): `xn` is the RAW input and the gain-free channel LayerNorm
+ * (eps prenorm_eps, MU:77-86) is folded into the GEMMs: wkv holds ONLY the key rows, ROW-CENTRED (W_k - rowmean(W_k), so
+ * that W_k LN(x) = rstd (wkv . x)), bf16 [128][64] in head order; four warps compute each pixel's rstd from the landed
+ * tile - no LayerNorm launch, no normalised tensor.  The values are never formed: the kernel accumulates
+ * G'[(h,d)][c] = sum_px P[px][(h,d)] rstd[px] x[px][c] and S = sum_px P (context = G' W_vc^T / S with the row-centred
+ * W_vc); ctx_acc is [B][4][ctx_slots][2080] fp32 records {G'[32][64], S[32]}, to be merged by dac_linattn_fold_g (NOT
+ * dac_linattn_fold). */
 typedef struct dac_kv_plan* dac_kv_t;
 int dac_linattn_kv_create(const void* xn, const void* wkv, const float* kv_shift, float* ctx_acc, int32_t ctx_slots,
                           const float* ln_stats, const float* ln_colsum, int32_t B, int32_t hw, int32_t C,
@@ -241,14 +242,17 @@ void dac_linattn_kv_destroy(dac_kv_t plan);
  * weff: bf16 [B][c_pad][128] from dac_linattn_fold.  Replaces the to_q (DAC_EPI_QKV) + to_out (DAC_EPI_LN) pair.
  * ln_stats / ln_colsum ([B*hw][2], [128]; or both NULL): folded PreNorm as for dac_linattn_kv_create - xn is then the
  * raw input (normally the same tensor as res).
- * In-kernel PreNorm (prenorm != 0; C = 64, ln_stats NULL, res == xn): `xn` is the RAW input; every 128 x 64 tile is read
- * ONCE, normalised in shared memory into the A operand of the first GEMM (gain-free channel LayerNorm, eps prenorm_eps,
- * MU:77-86) and reused as the residual - no LayerNorm launch, no normalised tensor, half the input traffic. */
+ * In-kernel PreNorm (prenorm != 0; C = 64, ln_stats NULL, res == xn): `xn` is the RAW input and wq holds the ROW-CENTRED
+ * rows W_q - rowmean(W_q), so that W_q LN(x) = rstd (wq . x): every 128 x 64 tile is read ONCE, is the A operand of the
+ * first GEMM as it is, gets its per-pixel rstd (eps prenorm_eps, MU:77-86) from four statistics warps, and is reused as
+ * the residual - no LayerNorm launch, no normalised tensor, half the input traffic.  q_shift (fp32 [128] on the device,
+ * or NULL): data-independent bounds c_d * log2(e) >= |q_d| log2(e) (c_d = ||wq[d]|| sqrt(C)); the softmax over a head's
+ * channels then uses max_d c_d as its shift instead of the row maximum (needs c_d <= 40). */
 typedef struct dac_qout_plan* dac_qout_t;
 int dac_linattn_qout_create(const void* xn, const void* wq, const void* weff, int32_t c_pad, const void* res,
                             void* out, const float* bias, const float* ln_g, float ln_eps, const float* ln_stats,
                             const float* ln_colsum, int32_t B, int32_t hw, int32_t C, int32_t prenorm,
-                            float prenorm_eps, dac_qout_t* plan);
+                            float prenorm_eps, const float* q_shift, dac_qout_t* plan);
 int dac_linattn_qout_launch(dac_qout_t plan, dac_stream_t stream);
 void dac_linattn_qout_destroy(dac_qout_t plan);
 

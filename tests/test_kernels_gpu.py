@@ -483,8 +483,8 @@ def test_linear_attention_kv_in_kernel_prenorm(ops, gen, B, H, W):
     wkv[:128] *= 1.5
     shift = 1.02 * bf(wkv[:128]).float().norm(dim=1) * math.sqrt(C)
     ctx = torch.full((B, 4, ops.ctx_slots(B, H, W, True), ops.KV_G_REC), float("nan"), device="cuda")
-    plan = ops.KvPlan(xr, wkv[:128].to(torch.bfloat16).contiguous(), (shift * 1.4426950408889634).contiguous(), ctx, B, hw,
-                      C, prenorm_eps=1e-5)
+    plan = ops.KvPlan(xr, ops.centre_rows(wkv[:128]).to(torch.bfloat16).contiguous(),
+                      (shift * 1.4426950408889634).contiguous(), ctx, B, hw, C, prenorm_eps=1e-5)
     for _ in range(2):
         plan.run()
     torch.cuda.synchronize()
@@ -493,9 +493,12 @@ def test_linear_attention_kv_in_kernel_prenorm(ops, gen, B, H, W):
     torch.cuda.synchronize()
     assert torch.equal(ctx, first)
     assert torch.equal(nhwc(x), xr)                            # the input tensor is not modified (normalised in smem only)
-    rec = ctx.sum(2)                                           # [B, 4, 2080]
+    written = ~torch.isnan(ctx).any(-1)                        # records no CTA owns stay untouched (and are never read)
+    assert written[:, :, 0].all() and (written == written[:, :1]).all()
+    rec = torch.where(written[..., None], ctx, torch.zeros_like(ctx)).sum(2)     # [B, 4, 2080]
     G, S = rec[..., :2048].reshape(B, 4, 32, 64), rec[..., 2048:2080]
-    wv = bf(wkv[128:]).float().reshape(4, 32, C)
+    wv = bf(ops.centre_rows(wkv[128:])).float().reshape(4, 32, C)     # centred: the per-pixel mean drops out of G W_v^T
+    wv = wv - wv.mean(2, keepdim=True)
     got = torch.einsum("bhdc,hec->bhde", G, wv) / (S[..., None] * hw)
     kvr = F.conv2d(xn, bf(wkv).float()[:, :, None, None]).reshape(B, 2, 4, 32, hw)
     k, v = kvr[:, 0].softmax(-1), kvr[:, 1] / hw
@@ -591,8 +594,9 @@ def test_linear_attention_folded_prenorm(ops, gen, B, H, W, C, kv_tc):
     assert_close_bf16(nchw(out), ref, f"folded PreNorm linear attention {H}x{W} C={C}", rel=2 ** -5, abs_=2e-2)
 
 
+@pytest.mark.parametrize("bound", [True, False])
 @pytest.mark.parametrize("B,H,W", [(3, 32, 32), (5, 64, 48), (1, 8, 16), (40, 16, 8), (2, 128, 128)])
-def test_linear_attention_in_kernel_prenorm(ops, gen, B, H, W):
+def test_linear_attention_in_kernel_prenorm(ops, gen, B, H, W, bound):
     """PreNorm inside the fused 64-channel LinearAttention kernels (dac_linattn_kv / dac_linattn_qout with prenorm): both
     take the RAW tensor, normalise each tile in shared memory, and the q-out kernel reuses the raw tile as the residual;
     checked against PreNorm(LinearAttention) + x of the oracle (module_util.py:89-97,157-185) and for bit-reproducibility."""
@@ -616,11 +620,13 @@ def test_linear_attention_in_kernel_prenorm(ops, gen, B, H, W):
     c_pad = ops.choose_block_n(C)[1]
     weff = torch.zeros(B, c_pad, 128, device="cuda", dtype=torch.bfloat16)
     out = torch.full((B, H, W, C), float("nan"), device="cuda", dtype=torch.bfloat16)
-    pkv = ops.KvPlan(xh, wf[128:256].to(torch.bfloat16).contiguous(), (shift * 1.4426950408889634).contiguous(), ctx, B, hw,
-                     C, prenorm_eps=1e-5)
+    pkv = ops.KvPlan(xh, ops.centre_rows(wf[128:256]).to(torch.bfloat16).contiguous(),
+                     (shift * 1.4426950408889634).contiguous(), ctx, B, hw, C, prenorm_eps=1e-5)
     m_fold = ops.kv_fold_matrix(sd["to_out.0.weight"].reshape(C, 128), wf[256:])
-    pq = ops.QoutPlan(xh, ops.pack_linear(wf[:128].contiguous()).w, weff, xh, out, sd["to_out.0.bias"],
-                      sd["to_out.1.g"].reshape(-1).contiguous(), 1e-5, B, hw, C, prenorm_eps=1e-5)
+    wqc = ops.centre_rows(wf[:128]).contiguous()
+    qsh = (1.02 * bf(wqc).float().norm(dim=1) * math.sqrt(C) * 1.4426950408889634).contiguous() if bound else None
+    pq = ops.QoutPlan(xh, ops.pack_linear(wqc).w, weff, xh, out, sd["to_out.0.bias"],
+                      sd["to_out.1.g"].reshape(-1).contiguous(), 1e-5, B, hw, C, prenorm_eps=1e-5, q_shift=qsh)
     outs = []
     for _ in range(3):
         out.fill_(float("nan"))

@@ -18,6 +18,20 @@ __global__ void k(float* out, int iters, long long* cycles) {
       if (MODE == 3) asm volatile("tanh.approx.f32 %0, %0;" : "+f"(a[i]));
       if (MODE == 4) asm volatile("tanh.approx.bf16x2 %0, %0;" : "+r"(u[i]));
       if (MODE == 5) asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(a[i]));
+      if (MODE == 6) asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(u[i]) : "f"(a[i]), "f"(a[(i + 1) & 7]));        // F2FP
+      if (MODE == 7) {                                   // ex2 and F2FP interleaved: do they share a pipe?
+        asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a[i]));
+        asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(u[i]) : "f"(a[i]), "f"(a[(i + 1) & 7]));
+      }
+      if (MODE == 8) {                                   // integer round-to-nearest pack: 2 x IADD + PRMT
+        uint32_t lo = __float_as_uint(a[i]) + 0x8000u, hi = __float_as_uint(a[(i + 1) & 7]) + 0x8000u;
+        asm volatile("prmt.b32 %0, %1, %2, 0x7632;" : "=r"(u[i]) : "r"(lo), "r"(hi));
+      }
+      if (MODE == 9) {                                   // ex2 + integer pack
+        asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a[i]));
+        uint32_t lo = __float_as_uint(a[i]) + 0x8000u, hi = __float_as_uint(a[(i + 1) & 7]) + 0x8000u;
+        asm volatile("prmt.b32 %0, %1, %2, 0x7632;" : "=r"(u[i]) : "r"(lo), "r"(hi));
+      }
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) { a[i] = a[i] * 0.5f - 1.0f; u[i] ^= 0x00010001u; }
@@ -46,5 +60,9 @@ int main() {
   run<3>("tanh.approx.f32", out, cyc);
   run<4>("tanh.approx.bf16x2", out, cyc);
   run<5>("rcp.approx.ftz.f32", out, cyc);
+  run<6>("cvt.rn.bf16x2.f32", out, cyc);
+  run<7>("ex2 + cvt.bf16x2 pairs", out, cyc);
+  run<8>("int pack (2 IADD+PRMT)", out, cyc);
+  run<9>("ex2 + int pack pairs", out, cyc);
   return 0;
 }

@@ -99,7 +99,7 @@ def make(name):
         shift = torch.full((128,), 12.0, device="cuda")
         pn = kind == "kvtc_pn"
         ctx = torch.zeros(B, 4, ops.ctx_slots(B, H, W, True), ops.KV_G_REC if pn else 32 * 34, device="cuda")
-        plan = ops.KvPlan(x.reshape(B * H * W, cin), w[:128].to(torch.bfloat16).contiguous() if pn else ops.pack_kv_grouped(w),
+        plan = ops.KvPlan(x.reshape(B * H * W, cin), ops.centre_rows(w[:128]).to(torch.bfloat16).contiguous() if pn else ops.pack_kv_grouped(w),
                           shift, ctx, B, H * W, cin, prenorm_eps=1e-5 if pn else None)
         plan.info = lambda: {}
     elif kind == "toout":
@@ -113,7 +113,7 @@ def make(name):
         wq = (torch.randn(1, 128, cin, device="cuda", generator=g) * cin ** -0.5).to(torch.bfloat16)
         weff = (torch.randn(B, cout, 128, device="cuda", generator=g) * 128 ** -0.5).to(torch.bfloat16)
         plan = ops.QoutPlan(x, wq, weff, x, out, torch.zeros(cout, device="cuda"), torch.ones(cout, device="cuda"),
-                            1e-5, B, H * W, cout, prenorm_eps=1e-5)
+                            1e-5, B, H * W, cout, prenorm_eps=1e-5, q_shift=torch.full((128,), 12.0, device="cuda"))
         plan.info = lambda: {}
     elif kind == "qout":
         wq = (torch.randn(1, 128, cin, device="cuda", generator=g) * cin ** -0.5).to(torch.bfloat16)
