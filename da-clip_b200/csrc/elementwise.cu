@@ -72,13 +72,20 @@ static int elementwise_grid(int64_t work_items) {
 }
 
 // ------------------------------------------------------------------------------------------------ stem input
+// PAIR = false: one packed 64-channel row per pixel (kx = 0..6, 8 channels each; kx = 7 zero) -> out [B][Hp][Wp][64].
+// PAIR = true: one packed row per PAIR of horizontally adjacent pixels, the 8-wide window kx' = 0..7 around them (source
+// x = 2 j + kx' - 3): pixel 2j uses kx' 0..6, pixel 2j+1 uses kx' 1..7 -> out [B][Hp][Wp/2][64].  With the weights
+// packed as 128 rows (ops.pack_stem_pair: the second pixel's copies shifted by one kx) init_conv becomes a 7-tap vertical
+// conv with N = 128 over HALF as many GEMM rows: half the packed tensor, half the K steps per pixel, and MMAs that are
+// not capped by the N = 64 operand fetch.
+template <bool PAIR>
 __global__ void __launch_bounds__(256) stem_input_kernel(const float* __restrict__ xt, const float* __restrict__ cond,
                                                          __nv_bfloat16* __restrict__ out, int B, int H, int W, int Hp,
                                                          int Wp) {
   // One CTA per (row, image).  Phase 1: the row's six channels (xt - cond | cond), reflect-padded to Wp and with the
   // three zero columns of the 7-tap window on either side, go to shared memory with coalesced loads.  Phase 2: one
-  // thread per (pixel, kx) packs its 8 channels (6 + 2 zeros; kx = 7 is all zero) into one 16 B store - the row's
-  // Wp * 128 B are written fully coalesced and every input value is read from global memory once, not seven times.
+  // thread per (pixel or pair, kx) packs its 8 channels (6 + 2 zeros) into one 16 B store - the row is written fully
+  // coalesced and every input value is read from global memory once, not seven times.
   extern __shared__ float srow[];                      // [6][Wp + 6]; column j holds source x = j - 3
   const int y = blockIdx.x, b = blockIdx.y;
   const int pitch = Wp + 6;
@@ -102,12 +109,13 @@ __global__ void __launch_bounds__(256) stem_input_kernel(const float* __restrict
     for (int c = 0; c < 6; ++c) srow[c * pitch + j] = v[c];
   }
   __syncthreads();
-  uint4* orow = reinterpret_cast<uint4*>(out) + (static_cast<int64_t>(b) * Hp + y) * Wp * 8;
-  for (int i = threadIdx.x; i < Wp * 8; i += blockDim.x) {
+  const int units = PAIR ? Wp / 2 : Wp;                // packed rows of this image row
+  uint4* orow = reinterpret_cast<uint4*>(out) + (static_cast<int64_t>(b) * Hp + y) * units * 8;
+  for (int i = threadIdx.x; i < units * 8; i += blockDim.x) {
     const int kx = i & 7;
-    const float* s = srow + (i >> 3) + kx;             // source x = pixel + kx - 3  ->  column pixel + kx
+    const float* s = srow + (PAIR ? 2 : 1) * (i >> 3) + kx;   // source x = first pixel + kx - 3  ->  column first pixel + kx
     uint4 u = make_uint4(0u, 0u, 0u, 0u);
-    if (kx < 7) {
+    if (PAIR || kx < 7) {
       u.x = pack_bf16(s[0], s[pitch]);
       u.y = pack_bf16(s[2 * pitch], s[3 * pitch]);
       u.z = pack_bf16(s[4 * pitch], s[5 * pitch]);
@@ -501,13 +509,18 @@ extern "C" int dac_noise_state(const float* x, const float* eps, float* out, int
 }
 
 extern "C" int dac_unet_stem_input(const float* xt, const float* cond, void* out, int B, int H, int W, int Hp, int Wp,
-                                   dac_stream_t stream) {
+                                   int pair, dac_stream_t stream) {
   if (!xt || !cond || !out) return set_error(-1, "dac_unet_stem_input: null argument");
   if (Hp < H || Wp < W || Hp - H >= H || Wp - W >= W) return set_error(-2, "dac_unet_stem_input: bad padding");
   if (Hp > 65535 || B > 65535) return set_error(-2, "dac_unet_stem_input: Hp and B must be < 65536");
   if (Wp > 2000) return set_error(-2, "dac_unet_stem_input: padded width must be <= 2000 (one row in 48 KB of shared memory)");
-  stem_input_kernel<<<dim3(Hp, B), 256, sizeof(float) * 6 * (Wp + 6), static_cast<cudaStream_t>(stream)>>>(
-      xt, cond, static_cast<__nv_bfloat16*>(out), B, H, W, Hp, Wp);
+  if (pair && (Wp & 1)) return set_error(-2, "dac_unet_stem_input: the pixel-pair packing needs an even padded width");
+  if (pair)
+    stem_input_kernel<true><<<dim3(Hp, B), 256, sizeof(float) * 6 * (Wp + 6), static_cast<cudaStream_t>(stream)>>>(
+        xt, cond, static_cast<__nv_bfloat16*>(out), B, H, W, Hp, Wp);
+  else
+    stem_input_kernel<false><<<dim3(Hp, B), 256, sizeof(float) * 6 * (Wp + 6), static_cast<cudaStream_t>(stream)>>>(
+        xt, cond, static_cast<__nv_bfloat16*>(out), B, H, W, Hp, Wp);
   return check_launch("stem_input_kernel");
 }
 

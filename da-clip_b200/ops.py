@@ -104,6 +104,20 @@ def pack_stem(weight):
     return PackedWeight(_pad_rows(w, choose_block_n(cout)[1]), taps, cout, cols=[[(0, -3, list(range(kh)))]])
 
 
+def pack_stem_pair(weight):
+    """init_conv in pixel-pair form (dac_unet_stem_input with pair=1): A row = the 8-wide window (kx' = 0..7, 8 channels
+    each) around a pair of horizontally adjacent pixels; 2 * cout weight rows - pixel 2j's copy at kx = kx', pixel 2j+1's
+    at kx = kx' - 1 - so the accumulator row holds both outputs ([B, Hp, Wp/2, 2 cout] == [B, Hp, Wp, cout])."""
+    cout, cin, kh, kw = weight.shape
+    assert (cin, kh, kw) == (6, 7, 7) and 2 * cout <= 256
+    w = torch.zeros(kh, 2 * cout, 64, dtype=weight.dtype, device=weight.device)
+    for kx in range(kw):
+        w[:, :cout, kx * 8:kx * 8 + cin] = weight[:, :, :, kx].permute(2, 0, 1)
+        w[:, cout:, (kx + 1) * 8:(kx + 1) * 8 + cin] = weight[:, :, :, kx].permute(2, 0, 1)
+    taps = [[(ky - 3, 0) for ky in range(kh)]]
+    return PackedWeight(_pad_rows(w, choose_block_n(2 * cout)[1]), taps, 2 * cout, cols=[[(0, -3, list(range(kh)))]])
+
+
 def pack_upsample_conv(weight):
     """nearest-2x upsample followed by a 3x3 conv (module_util.py:100-104) == four 2x2 convs on the
     low-resolution input, one per output parity (py, px), whose taps are sums of the original taps that hit the
@@ -437,9 +451,10 @@ def noise_state(x, eps, out, max_sigma):
     L.check(L.load().dac_noise_state(L.ptr(x), L.ptr(eps), L.ptr(out), x.numel(), float(max_sigma), L.stream_ptr()))
 
 
-def stem_input(xt, cond, out, H, W):
-    B, Hp, Wp = out.shape[0], out.shape[1], out.shape[2]
-    L.check(L.load().dac_unet_stem_input(L.ptr(xt), L.ptr(cond), L.ptr(out), B, H, W, Hp, Wp, L.stream_ptr()))
+def stem_input(xt, cond, out, H, W, pair=False):
+    """out: [B, Hp, Wp, 64], or [B, Hp, Wp/2, 64] with pair=True (one packed row per pair of adjacent pixels)."""
+    B, Hp, Wp = out.shape[0], out.shape[1], out.shape[2] * (2 if pair else 1)
+    L.check(L.load().dac_unet_stem_input(L.ptr(xt), L.ptr(cond), L.ptr(out), B, H, W, Hp, Wp, int(pair), L.stream_ptr()))
 
 
 def layernorm_rows(x, out, rows, c, w=None, b=None, eps=1e-5):

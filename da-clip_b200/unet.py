@@ -259,6 +259,7 @@ class PackedUNet:
 
         self.f32 = f32
         self.stem = ops.pack_stem(f32("init_conv.weight"))
+        self.stem_pair = ops.pack_stem_pair(f32("init_conv.weight")) if 2 * f32("init_conv.weight").shape[0] <= 256 else None
         # FiLM table: all ResBlock mlp.1 linears stacked
         ws, bs, self.film_off, off = [], [], {}, 0
         self.rb = {}
@@ -624,15 +625,20 @@ class UNetEngine:
         cfg, pk, B, Hp, Wp = self.cfg, self.pk, self.B, self.Hp, self.Wp
         if cfg.transformer and not cfg.use_image_context:
             raise L.DacError("inconsistent config")
-        stem = self.buf(B, Hp, Wp, 64)
-        self.add("stem_input", lambda: ops.stem_input(self.xt, self.cond, stem, self.H, self.W))
+        # 7x7 stem in pixel-pair form: one packed row per pair of adjacent pixels, 2 nf weight rows (N = 128 for nf = 64)
+        stem_pair = self.PAIR and pk.stem_pair is not None and Wp % 2 == 0
+        stem = self.buf(B, Hp, Wp // 2, 64) if stem_pair else self.buf(B, Hp, Wp, 64)
+        self.add("stem_input", lambda: ops.stem_input(self.xt, self.cond, stem, self.H, self.W, pair=stem_pair))
         if pk.has_prompt:
             self.pre_steps.append(lambda: ops.prompt_embed(pk.ew, self.text_ctx, B, self.prompt_emb)
                                   if self.use_text else None)
         self.add("time_film", lambda: ops.time_film(pk.ew, self.t_dev, self.prompt_emb if self.use_text else None, B,
                                                     self.temb, self.film))
-        x0 = self.buf(B, Hp, Wp, 64)
-        self.conv("init_conv", stem, 64, pk.stem, x0, Hp, Wp)
+        x0 = self.buf(B, Hp, Wp, cfg.nf)
+        if stem_pair:
+            self.conv("init_conv", stem, 64, pk.stem_pair, x0.view(B, Hp, Wp // 2, 2 * cfg.nf), Hp, Wp // 2)
+        else:
+            self.conv("init_conv", stem, 64, pk.stem, x0, Hp, Wp)
         self.taps["init_conv"] = x0
         x, h, w = x0, Hp, Wp
         if cfg.scale == 0.5:         # wild-ir: everything between here and final_res_block runs at half resolution

@@ -58,9 +58,13 @@ int dac_noise_state(const float* x, const float* eps, float* out, int64_t n, flo
  * xt, cond: [B,3,H,W] fp32 NCHW.  out: [B,Hp,Wp,64] bf16 NHWC where Hp,Wp = H,W reflect-padded up to a
  * multiple of 16 and channel (kx*8 + c), kx in 0..6, c in 0..5, holds cat[xt-cond, cond][c] at column x+kx-3
  * (zero outside the padded image; channels 6,7 of each group and 56..63 are zero).  This turns the 7x7
- * init_conv (ARCH:36,129) into a 7-tap vertical conv over 64 channels for the tensor-core kernel. */
+ * init_conv (ARCH:36,129) into a 7-tap vertical conv over 64 channels for the tensor-core kernel.
+ * pair != 0 (Wp even): one packed row per PAIR of horizontally adjacent pixels instead - out [B,Hp,Wp/2,64], group kx'
+ * (0..7) holds source column 2 j + kx' - 3; with weights packed as 128 rows (pixel 2j: kx = kx', pixel 2j+1: kx = kx' - 1)
+ * init_conv is a 7-tap vertical conv with N = 128 on half as many GEMM rows, its [B,Hp,Wp/2,128] output being the
+ * [B,Hp,Wp,64] tensor. */
 int dac_unet_stem_input(const float* xt, const float* cond, void* out, int B, int H, int W, int Hp, int Wp,
-                        dac_stream_t stream);
+                        int pair, dac_stream_t stream);
 
 /* ------------------------------------------------------------------ implicit-GEMM conv / linear (tcgen05)
  * One descriptor covers: 3x3 / 1x1 / 7x1 stride-1 convs, the 4x4 stride-2 Downsample (MU:107-108), the

@@ -103,6 +103,14 @@ def test_weight_packing_semantics():
     for kx in range(7):
         packed[:, kx * 8:kx * 8 + 6] = xp[:, :, :, kx:kx + W]
     assert torch.allclose(_emulate(ops.pack_stem(ws), packed, B, H, W), F.conv2d(x6, ws, padding=3), atol=1e-4)
+    # ... and in pixel-pair form: window kx' = 0..7 around a pair, 128 weight rows, output [.., W/2, 128] == [.., W, 64]
+    packed2 = torch.zeros(B, 64, H, W // 2)
+    xp2 = F.pad(x6, (3, 4, 0, 0))
+    for kx in range(8):
+        packed2[:, kx * 8:kx * 8 + 6] = xp2[:, :, :, kx:kx + W:2]
+    got2 = _emulate(ops.pack_stem_pair(ws), packed2, B, H, W // 2)               # [B, 128, H, W/2]
+    got2 = got2.reshape(B, 2, 64, H, W // 2).permute(0, 2, 3, 4, 1).reshape(B, 64, H, W)
+    assert torch.allclose(got2, F.conv2d(x6, ws, padding=3), atol=1e-4)
     # GEGLU interleave
     wg, bg = torch.randn(1024, 64, generator=g) * 0.125, torch.randn(1024, generator=g)
     pw, bperm = ops.pack_geglu(wg, bg, block_n=256)

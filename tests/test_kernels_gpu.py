@@ -293,6 +293,14 @@ def test_stem_and_init_conv(ops, gen, B, H, W):
     x = F.pad(x, (0, Wp - W, 0, Hp - H), mode="reflect") if (Hp > H or Wp > W) else x
     ref = F.conv2d(bf(x).float(), bf(w).float(), padding=3)
     assert_close_bf16(nchw(out), ref, f"init_conv {H}x{W}")
+    # pixel-pair form: one packed row per pair of adjacent pixels, 128 weight rows; the [B,Hp,Wp/2,128] output IS [B,Hp,Wp,64]
+    stem2 = torch.full((B, Hp, Wp // 2, 64), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.stem_input(xt, cond, stem2, H, W, pair=True)
+    out2 = torch.full((B, Hp, Wp, 64), float("nan"), device="cuda", dtype=torch.bfloat16)
+    plan2 = ops.ConvPlan(stem2, 64, ops.pack_stem_pair(w), out2.view(B, Hp, Wp // 2, 128), B=B, H=Hp, W=Wp // 2)
+    plan2.run()
+    torch.cuda.synchronize()
+    assert_close_bf16(nchw(out2), ref, f"init_conv (pixel pairs) {H}x{W}")
 
 
 def test_final_conv_nchw_crop(ops, gen):

@@ -14,6 +14,8 @@ CASES = {
     "l3_3x3": (16, 32, 32, 512, 512, "3x3"),
     "l3_geglu": (16, 32, 32, 512, 4096, "geglu"),
     "l0_1x1": (16, 256, 256, 128, 64, "1x1"),
+    "stem": (16, 256, 256, 64, 64, "stem"),
+    "stem_pair": (16, 256, 128, 64, 128, "stem"),
     "l0_q": (16, 256, 256, 64, 128, "q"),
     "l0_kv": (16, 256, 256, 64, 256, "kv"),
     "l0_toout": (16, 256, 256, 128, 64, "toout"),
@@ -122,6 +124,9 @@ def make(name):
         plan = ops.QoutPlan(x, wq, weff, res, out, torch.zeros(cout, device="cuda"), torch.ones(cout, device="cuda"),
                             1e-5, B, H * W, cout)
         plan.info = lambda: {}
+    elif kind == "stem":
+        w6 = torch.randn(64, 6, 7, 7, device="cuda", generator=g) * 0.05
+        plan = ops.ConvPlan(x, 64, ops.pack_stem_pair(w6) if cout == 128 else ops.pack_stem(w6), out, B=B, H=H, W=W)
     elif kind == "geglu":
         w = torch.randn(cout, cin, device="cuda", generator=g) * cin ** -0.5
         b = torch.randn(cout, device="cuda", generator=g)
