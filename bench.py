@@ -282,7 +282,9 @@ def run_product(args):
         if args.dump_layers:
             with open(args.dump_layers, "w") as f:
                 for n, ms_ in layers:
-                    f.write(f"{ms_ * 1e3:9.1f} us  {'conv' if eng.is_conv(n) else 'aux '}  {n}\n")
+                    fl = getattr(eng, "layer_flops", {}).get(n)
+                    tf = f"{fl / 1e9:8.1f} GFLOP {fl / ms_ / 1e9:7.1f} TFLOP/s" if fl else ""
+                    f.write(f"{ms_ * 1e3:9.1f} us  {'conv' if eng.is_conv(n) else 'aux '}  {n:28s} {tf}\n")
         peak_tf, peak_bw, which = peaks()
         gflop = CONV_GFLOP_PER_EVAL.get(S, CONV_GFLOP_PER_EVAL[256] * (S / 256) ** 2) * B
         achieved = gflop / n_conv / (conv_ms / n_conv) if conv_ms > 0 else 0.0       # GFLOP/ms == TFLOP/s

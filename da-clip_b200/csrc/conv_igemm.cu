@@ -60,11 +60,14 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
   if (d->ndy < 1 || d->ncols < 1 || d->ndy * d->ncols != d->ntaps || (d->ndy > 1 && d->stride != 1))
     return set_error(-2, "dac_conv_create: column groups (%d x %d) must cover the %d taps; ndy > 1 needs stride 1",
                      d->ncols, d->ndy, d->ntaps);
-  if (d->halo && (d->stride != 1 || d->ntaps != 9 || d->ndy != 9 || d->ncols != 1 || d->tile_w != 8 ||
-                  d->ngroups != 1 || d->halo > 2))
-    return set_error(-2, "dac_conv_create: halo loads need a 3x3 stride-1 conv, tile_w 8, ncols 1, ndy 9");
-  const int a_rows = d->halo ? d->tile_h + 2 : (d->stride == 1 ? d->tile_h + d->ndy - 1 : d->tile_h);
-  const int box_w = d->halo ? d->tile_w + 2 : d->tile_w;                    // rows x box_w pixels land in smem
+  // halo loads: a k x k window of taps (3 x 3, or the 2 x 2 of one parity group of the folded upsample conv) served by
+  // ONE (tile_h + k - 1) x (tile_w + k - 1) pixel box per K chunk; tap i = (i / k, i % k) pixels into the box
+  const int halo_k = !d->halo ? 0 : (d->ntaps == 9 ? 3 : (d->ntaps == 4 ? 2 : -1));
+  if (d->halo && (d->stride != 1 || halo_k < 0 || d->ndy != d->ntaps || d->ncols != 1 || d->tile_w != 8 ||
+                  (d->ngroups != 1 && halo_k != 2) || d->halo > 2))
+    return set_error(-2, "dac_conv_create: halo loads need a 3x3 (or per-group 2x2) stride-1 conv, tile_w 8, ncols 1, ndy = ntaps");
+  const int a_rows = d->halo ? d->tile_h + halo_k - 1 : (d->stride == 1 ? d->tile_h + d->ndy - 1 : d->tile_h);
+  const int box_w = d->halo ? d->tile_w + halo_k - 1 : d->tile_w;           // rows x box_w pixels land in smem
   if (d->tile_w * d->stride > 256 || a_rows * d->stride > 256)
     return set_error(-2, "dac_conv_create: TMA box exceeds 256");
   if ((reinterpret_cast<uintptr_t>(d->src0) | reinterpret_cast<uintptr_t>(d->src1) |
@@ -174,8 +177,8 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
   k.a_sbo = d->halo ? (uint32_t)box_w * 128u : 1024u;          // halo, tile_w 8: one (padded) pixel row per 8-row group
   k.halo = d->halo;
   for (int i = 0; i < d->ndy; ++i) {
-    // tap i of a load: halo = (ky, kx) = (i / 3, i % 3) pixels into the haloed box; else i tile rows down
-    const uint32_t off = d->halo ? (uint32_t)((i / 3) * box_w + (i % 3)) * 128u : (uint32_t)i * d->tile_w * 128u;
+    // tap i of a load: halo = (ky, kx) = (i / k, i % k) pixels into the haloed box; else i tile rows down
+    const uint32_t off = d->halo ? (uint32_t)((i / halo_k) * box_w + (i % halo_k)) * 128u : (uint32_t)i * d->tile_w * 128u;
     k.tap_off[i] = (uint16_t)(off >> 4);
   }
   k.cout = d->cout;
@@ -202,7 +205,8 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
   const int chunks = k.chunks0 + k.chunks1;
   const long long res_bytes = (long long)k.n_tiles * d->ntaps * chunks * k.b_bytes;
   const long long kv_extra = d->epi == DAC_EPI_KVCTX ? 2ll * kKvStageBytes : 0;   // P / V head tiles, both groups
-  bool resident = d->ngroups == 1 && !d->per_image_w && res_bytes <= 160 * 1024 &&
+  // (per parity group: tiles are numbered group-major and the kernel swaps the resident set when the group changes)
+  bool resident = !d->per_image_w && res_bytes <= 160 * 1024 &&
                   (smem_budget - res_bytes - kv_extra) / (long long)k.a_slot >= 3;
   k.b_res_bytes = resident ? (uint32_t)res_bytes : 0u;
   k.pair = d->pair ? 1 : 0;

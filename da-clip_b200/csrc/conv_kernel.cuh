@@ -574,6 +574,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   uint64_t* b_full = tmem_empty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
   uint64_t* res_bar = b_full + 2;   // one per epilogue group: residual tile landed in the staging tile
+  uint64_t* b_empty = b_full + 4;   // parity-group layers: every MMA on the resident weights of the previous group is done
   float* film_sh = reinterpret_cast<float*>(bars + 32);   // [2][block_n]: scale + 1 | shift of the current image
   const int chunks = p.chunks0 + p.chunks1;
 
@@ -603,6 +604,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       mbar_init(&tmem_empty[s], kEpiWarps / 2);
     }
     mbar_init(b_full, 1);
+    mbar_init(b_empty, 1);
     mbar_init(&res_bar[0], 1);
     mbar_init(&res_bar[1], 1);
     fence_barrier_init();
@@ -629,30 +631,44 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   if (warp == 0) {
     // ===================== TMA producer (one elected thread) =====================
     if (elect_one()) {
-      if (b_resident) {
-        // whole weight tensor (ntaps x chunks tiles) loaded once per CTA, laid out in the ORDER THE MMA LOOP CONSUMES
-        // IT (N tile, chunk, column group, tap within the group), so the issuer walks it with one add per tap;
-        // ngroups == 1 here
+      // Resident weights: the whole weight tensor of ONE parity group (ntaps x chunks tiles) sits in shared memory, laid
+      // out in the ORDER THE MMA LOOP CONSUMES IT (N tile, chunk, column group, tap within the group), so the issuer
+      // walks it with one add per tap.  Tiles are numbered group-major, so a CTA's contiguous range changes group at
+      // most ngroups - 1 times: the weights are reloaded then (after the issuer's last MMA on the old ones).
+      int w_group = -1;
+      uint32_t w_loads = 0;
+      auto load_group_weights = [&](int g) {
+        if (w_loads) mbar_wait(b_empty, (w_loads - 1) & 1);
         mbar_arrive_expect_tx(b_full, p.b_res_bytes);
+        for (int nt = 0; nt < p.n_tiles; ++nt)
+          for (int ck = 0; ck < chunks; ++ck)
+            for (int jt = 0; jt < p.ntaps; ++jt)
+              tma_load_3d(b_res + static_cast<size_t>((nt * chunks + ck) * p.ntaps + jt) * p.b_bytes, &mapW, b_full,
+                          ck * kChunkK, nt * p.block_n, g * p.ntaps + p.col_tap[g][jt]);
+        w_group = g;
+        ++w_loads;
+      };
+      if (b_resident) {
         if (p.pair) {
+          mbar_arrive_expect_tx(b_full, p.b_res_bytes);
           // per (64-channel source slice, ky): ONE 192-row block [W(kx=2); W(kx=1); W(kx=0)] - the even and the odd
           // chunk of the slice read overlapping 128-row windows of it (see the issuer)
           for (int s_ = 0; s_ < (chunks >> 1); ++s_)
             for (int ky = 0; ky < 3; ++ky)
               tma_load_3d(b_res + static_cast<size_t>(s_ * 3 + ky) * (3u * (p.block_n >> 1) * 128u), &mapW, b_full,
                           s_ * kChunkK, 0, ky);
-        } else
-        for (int nt = 0; nt < p.n_tiles; ++nt)
-          for (int ck = 0; ck < chunks; ++ck)
-            for (int jt = 0; jt < p.ntaps; ++jt)
-              tma_load_3d(b_res + static_cast<size_t>((nt * chunks + ck) * p.ntaps + jt) * p.b_bytes, &mapW, b_full,
-                          ck * kChunkK, nt * p.block_n, p.col_tap[0][jt]);
+          w_group = 0;
+          ++w_loads;
+        } else if (tile_begin < tile_end) {
+          load_group_weights(decode_tile(p, tile_begin).g);
+        }
       }
       int stage = 0;
       uint32_t phase = 0;
       griddep_wait();
       for (int tile = tile_begin; tile < tile_end; ++tile) {
         const TileCoord t = decode_tile(p, tile);
+        if (b_resident && t.g != w_group) load_group_weights(t.g);
         const int xin = t.x0 * p.stride, yin = t.y0 * p.stride;
         const int zbase = (p.per_image_w ? t.n * p.ngroups * p.ntaps : 0) + t.g * p.ntaps;
         const int ncoord = t.nt * p.block_n;
@@ -709,8 +725,21 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      if (b_resident) mbar_wait(b_full, 0);
+      int w_group = -1;
+      uint32_t w_loads = 0;
       for (int tile = tile_begin; tile < tile_end; ++tile) {
+        if (b_resident) {
+          const int g = p.ngroups == 1 ? 0 : fast_div(fast_div(tile, p.fd_ntiles), p.fd_mtiles);
+          if (g != w_group) {               // (next) parity group: its weights replace the resident ones
+            if (w_group >= 0) {
+              if (elect_one()) umma_commit(b_empty);
+              __syncwarp();
+            }
+            mbar_wait(b_full, w_loads & 1);
+            ++w_loads;
+            w_group = g;
+          }
+        }
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kAccStride;

@@ -177,6 +177,7 @@ class ConvPlan:
         # vertically adjacent taps share one activation load when the weight tiles are small enough to ride along
         share = pw.cols is not None and s == 1 and block_n <= 128 and share_taps
         cols = pw.cols if share else [[(dx, dy, [i]) for i, (dy, dx) in enumerate(gt)] for gt in pw.taps]
+        halo_req = halo
         if halo is None:
             # 3x3 stride-1 convs whose whole weight tensor stays resident in shared memory (the 64-/128-channel
             # layers, which are shared-memory-bandwidth bound): ONE haloed activation load per K chunk instead of
@@ -184,7 +185,19 @@ class ConvPlan:
             halo = int(share and len(pw.taps[0]) == 9 and pw.ngroups == 1 and not per_image_w and tile is None
                        and cout_pad == block_n and 9 * ((c0 + c1) // 64) * block_n * 128 <= 150 * 1024
                        and not os.environ.get("DAC_NO_HALO"))
-        if halo:                     # nine shifted operand views of one (16+2) x (8+2) pixel box
+        halo4 = False
+        if halo_req is None or halo_req:
+            # ... and the folded upsample conv (four parity groups of 2 x 2 taps): one (16+1) x (8+1) box per K chunk and
+            # group instead of two column loads - the N = 64 instance at 128^2 -> 256^2 is bound by L2 -> SM ingest
+            halo4 = (pw.ngroups == 4 and len(pw.taps[0]) == 4 and s == 1 and share and tile is None and not per_image_w
+                     and cout_pad == block_n and 4 * ((c0 + c1) // 64) * block_n * 128 <= 150 * 1024
+                     and not os.environ.get("DAC_NO_HALO"))
+        if halo4:
+            halo = 1
+            # taps of a group are stored as (a, b) = (row, column) offset index, a * 2 + b: origin = the smallest offsets
+            cols = [[(min(dx for _, dx in gt), min(dy for dy, _ in gt), [0, 1, 2, 3])] for gt in pw.taps]
+            tile = (16, 8)
+        elif halo:                   # nine shifted operand views of one (16+2) x (8+2) pixel box
             assert len(pw.taps[0]) == 9 and s == 1 and pw.ngroups == 1
             cols, tile = [[(-1, -1, list(range(9)))]], (16, 8)
         ndy = len(cols[0][0][2])

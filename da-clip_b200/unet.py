@@ -406,6 +406,7 @@ class UNetEngine:
         self.steps = []          # (name, callable)
         self.taps = {}           # block name -> output buffer (NHWC bf16), for per-layer parity checks
         self.conv_names = set()  # steps that are tcgen05 implicit-GEMM launches
+        self.layer_flops = {}    # algorithmic FLOPs of each of them (layer dumps)
         self.flops = 0.0
         self._bytes = 0
         self._build()
@@ -423,6 +424,7 @@ class UNetEngine:
     def conv(self, name, src, c0, pw, out, h, w, **kw):
         plan = ops.ConvPlan(src, c0, pw, out, B=self.B, H=h, W=w, **kw)
         self.flops += plan.flops
+        self.layer_flops[name] = plan.flops
         self.conv_names.add(name)
         self.add(name, plan.run)
         return plan
@@ -433,6 +435,7 @@ class UNetEngine:
     def pair_conv(self, name, src0, wpair, out, h, w, **kw):
         plan = ops.PairConvPlan(src0, wpair, out, B=self.B, H=h, W=w, **kw)
         self.flops += plan.flops
+        self.layer_flops[name] = plan.flops
         self.conv_names.add(name)
         self.add(name, plan.run)
         return plan
@@ -545,6 +548,7 @@ class UNetEngine:
                     plan = ops.KvPlan(xn, a["k_rows"] if pn_eps is not None else a["kv_grouped"], a["kv_shift"], ctx, B, hw, C,
                                       ln_stats=stats, ln_colsum=a["kv_grouped_colsum"] if fold else None, prenorm_eps=pn_eps)
                     self.flops += plan.flops
+                    self.layer_flops[prefix + "to_kv"] = plan.flops
                     self.conv_names.add(prefix + "to_kv")
                     self.add(prefix + "to_kv", plan.run)
                 else:
@@ -563,6 +567,7 @@ class UNetEngine:
                                         1e-5, B, hw, C, ln_stats=stats, ln_colsum=a["q_colsum"] if fold else None,
                                         prenorm_eps=pn_eps, q_shift=a["q_shift"] if pn_eps is not None else None)
                     self.flops += plan.flops
+                    self.layer_flops[prefix + "to_q_out"] = plan.flops
                     self.conv_names.add(prefix + "to_q_out")
                     self.add(prefix + "to_q_out", plan.run)
                     return out
@@ -604,6 +609,7 @@ class UNetEngine:
         att = self.buf(B, h, w, C)
         self.add(prefix + "attn1", lambda: ops.attention(qkv, att, B, hw, heads, 32))
         self.flops += 4.0 * B * heads * hw * hw * 32
+        self.layer_flops[prefix + "attn1"] = 4.0 * B * heads * hw * hw * 32
         cvec = self.buf(B, C, dtype=torch.float32)
         # constant over tokens AND over the T steps: computed once per restoration (set_inputs), not per step
         self.pre_steps.append(lambda: ops.two_linear(self.image_ctx, a["cross_v"], a["cross_o"], a["cross_ob"], cvec))

@@ -139,7 +139,10 @@ typedef struct dac_conv_desc {
   const float* kv_shift; float* ctx_acc;          /* KVCTX: [128] shift * log2(e); [B][4][ctx_slots][1088] fp32 (zeroed by launch) */
   int32_t halo;                                   /* 3x3 stride-1, tile_w 8: ONE (tile_h+2) x (tile_w+2) load per K chunk
                                                      serves all nine taps (descriptors with a (tile_w+2)*128 B group
-                                                     stride); ncols = 1, ndy = 9, col_dx = col_dy0 = -1 */
+                                                     stride); ncols = 1, ndy = 9, col_dx = col_dy0 = -1.  Also the 2x2
+                                                     taps of each parity group of the folded upsample conv (ntaps = ndy
+                                                     = 4, tap i = (i / 2, i % 2) into a (tile_h+1) x (tile_w+1) box whose
+                                                     origin is the group's col_dx / col_dy0) */
   int32_t ctx_slots;                              /* KVCTX: partial records per (image, head) in ctx_acc,
                                                      >= dac_linattn_ctx_slots(B, tiles per image, 2) */
   int32_t pair;                                   /* pixel-pair mode of a 3x3 stride-1 conv with 64 output channels (the

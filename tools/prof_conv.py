@@ -14,6 +14,12 @@ CASES = {
     "l3_3x3": (16, 32, 32, 512, 512, "3x3"),
     "l3_geglu": (16, 32, 32, 512, 4096, "geglu"),
     "l0_1x1": (16, 256, 256, 128, 64, "1x1"),
+    "l1_up": (16, 128, 128, 128, 64, "up"),
+    "l0_down": (16, 256, 256, 64, 64, "down"),
+    "l1_pair64": (16, 128, 128, 64, 64, "pair"),
+    "l2_3x3_128": (16, 64, 64, 128, 128, "3x3"),
+    "l3_3x3_256": (16, 32, 32, 256, 256, "3x3"),
+    "l3_1x1_512": (16, 32, 32, 512, 512, "1x1"),
     "stem": (16, 256, 256, 64, 64, "stem"),
     "stem_pair": (16, 256, 128, 64, 128, "stem"),
     "l0_q": (16, 256, 256, 64, 128, "q"),
@@ -124,6 +130,14 @@ def make(name):
         plan = ops.QoutPlan(x, wq, weff, res, out, torch.zeros(cout, device="cuda"), torch.ones(cout, device="cuda"),
                             1e-5, B, H * W, cout)
         plan.info = lambda: {}
+    elif kind == "up":
+        w = torch.randn(cout, cin, 3, 3, device="cuda", generator=g) * (9 * cin) ** -0.5
+        out = torch.zeros(B, 2 * H, 2 * W, cout, device="cuda", dtype=torch.bfloat16)
+        plan = ops.ConvPlan(x, cin, ops.pack_upsample_conv(w), out, B=B, H=H, W=W, bias=torch.zeros(cout, device="cuda"))
+    elif kind == "down":
+        w = torch.randn(cout, cin, 4, 4, device="cuda", generator=g) * (16 * cin) ** -0.5
+        out = torch.zeros(B, H // 2, W // 2, cout, device="cuda", dtype=torch.bfloat16)
+        plan = ops.ConvPlan(x, cin, ops.pack_conv(w, stride=2, pad=1), out, B=B, H=H, W=W, bias=torch.zeros(cout, device="cuda"))
     elif kind == "stem":
         w6 = torch.randn(64, 6, 7, 7, device="cuda", generator=g) * 0.05
         plan = ops.ConvPlan(x, 64, ops.pack_stem_pair(w6) if cout == 128 else ops.pack_stem(w6), out, B=B, H=H, W=W)
