@@ -288,7 +288,7 @@ def run_product(args):
         peak_tf, peak_bw, which = peaks()
         gflop = CONV_GFLOP_PER_EVAL.get(S, CONV_GFLOP_PER_EVAL[256] * (S / 256) ** 2) * B
         achieved = gflop / n_conv / (conv_ms / n_conv) if conv_ms > 0 else 0.0       # GFLOP/ms == TFLOP/s
-        launches_per_eval = eng.launches + 1                                          # + fused SDE update
+        launches_per_eval = eng.launches + 2                                          # + loop tick + fused SDE update
         algo = ALGO_GFLOP_PER_EVAL.get(S, ALGO_GFLOP_PER_EVAL[256] * (S / 256) ** 2)
         result = {
             "metric": "restored images/sec @256^2 T=100", "value": round(value, 3), "unit": "images/s",

@@ -2,6 +2,7 @@
 // GroupNorm, and the tiny fp32 conditioning MLPs (time / prompt embedding -> FiLM table).
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <curand_kernel.h>
 
 #include "../../include/dac_b200.h"
 #include "common.h"
@@ -56,6 +57,64 @@ __global__ void __launch_bounds__(256) sde_step_kernel(const float* __restrict__
   // tail (n not a multiple of 4)
   for (int64_t i = (n4 << 2) + static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
     out[i] = sde_update<MODE>(x[i], mu[i], net[i], MODE != 2 ? eps[i] : 0.f, k);
+}
+
+// ---- the sampling loop driven from the device: no per-step host work, no per-step ATen launch ----
+// loop_tick_kernel (first node of a step, one thread): step s = state[0]; publishes the network time of this step in
+// t_dev (what time_embed reads), its 8 update coefficients in coef_dev, s itself in state[1], and advances state[0].
+__global__ void loop_tick_kernel(long long* __restrict__ state, const float* __restrict__ t_table,
+                                 const float* __restrict__ coef_table, float* __restrict__ t_dev,
+                                 float* __restrict__ coef_dev) {
+  if (threadIdx.x == 0) {
+    const long long s = state[0];
+    t_dev[0] = t_table[s];
+    state[1] = s;
+    state[0] = s + 1;
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) coef_dev[threadIdx.x] = coef_table[state[1] * 8 + threadIdx.x];
+}
+
+// sde_step_kernel with the coefficients and the step index read from device memory (written by loop_tick_kernel of the
+// same step) and the Gaussian noise either read from a pre-generated [T][n] tensor (eps_base + step * n: the parity
+// tests inject the reference's draws) or generated here: Philox4x32-10 keyed by (seed, element quad, step), four normals
+// per call - the sampler then launches nothing but its own kernels (sde_utils.py:227-231 draws torch.randn_like per step).
+template <int MODE>
+__global__ void __launch_bounds__(256) sde_step_dev_kernel(const float* __restrict__ x, const float* __restrict__ mu,
+                                                           const float* __restrict__ net, float* __restrict__ out,
+                                                           int64_t n, const float* __restrict__ coef_dev,
+                                                           const long long* __restrict__ state) {
+  griddep_wait();      // launched with programmatic serialisation behind final_conv: its output must be complete
+  SdeCoef k;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) k.c[i] = coef_dev[i];
+  const long long step = state[1];
+  const float* eps_base = reinterpret_cast<const float*>(state[2]);   // the host sets it before the first step
+  const unsigned long long seed = static_cast<unsigned long long>(state[3]);
+  const float* eps = eps_base ? eps_base + step * n : nullptr;
+  const int64_t n4 = n >> 2;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 a = reinterpret_cast<const float4*>(x)[i];
+    const float4 m = reinterpret_cast<const float4*>(mu)[i];
+    const float4 nn = reinterpret_cast<const float4*>(net)[i];
+    float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (MODE != 2) {
+      if (eps) {
+        e = reinterpret_cast<const float4*>(eps)[i];
+      } else {
+        curandStatePhilox4_32_10_t st;
+        curand_init(seed, static_cast<unsigned long long>(i), static_cast<unsigned long long>(step), &st);
+        e = curand_normal4(&st);
+      }
+    }
+    float4 r;
+    r.x = sde_update<MODE>(a.x, m.x, nn.x, e.x, k);
+    r.y = sde_update<MODE>(a.y, m.y, nn.y, e.y, k);
+    r.z = sde_update<MODE>(a.z, m.z, nn.z, e.z, k);
+    r.w = sde_update<MODE>(a.w, m.w, nn.w, e.w, k);
+    reinterpret_cast<float4*>(out)[i] = r;
+  }
 }
 
 __global__ void __launch_bounds__(256) noise_state_kernel(const float* __restrict__ x, const float* __restrict__ eps,
@@ -498,6 +557,31 @@ extern "C" int dac_sde_step(int mode, const float* x, const float* mu, const flo
   else if (mode == 2) sde_step_kernel<2><<<grid, 256, 0, s>>>(x, mu, net, eps, out, n, k);
   else return set_error(-2, "dac_sde_step: unknown mode %d", mode);
   return check_launch("sde_step_kernel");
+}
+
+extern "C" int dac_loop_tick(int64_t* state, const float* t_table, const float* coef_table, float* t_dev,
+                             float* coef_dev, dac_stream_t stream) {
+  if (!state || !t_table || !coef_table || !t_dev || !coef_dev) return set_error(-1, "dac_loop_tick: null argument");
+  loop_tick_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<long long*>(state), t_table, coef_table,
+                                                                    t_dev, coef_dev);
+  return check_launch("loop_tick_kernel");
+}
+
+extern "C" int dac_sde_step_dev(int mode, const float* x, const float* mu, const float* net, float* out, int64_t n,
+                                const float* coef_dev, const int64_t* state, dac_stream_t stream) {
+  if (!x || !mu || !net || !out || !coef_dev || !state) return set_error(-1, "dac_sde_step_dev: null argument");
+  if (n <= 0 || (n & 3)) return set_error(-2, "dac_sde_step_dev: n must be a positive multiple of 4");
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(mu) | reinterpret_cast<uintptr_t>(net) |
+       reinterpret_cast<uintptr_t>(out)) & 15)
+    return set_error(-2, "dac_sde_step_dev: pointers must be 16-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int grid = elementwise_grid(n / 4 + 1);
+  const long long* st = reinterpret_cast<const long long*>(state);
+  if (mode == 0) launch_k(sde_step_dev_kernel<0>, dim3(grid), dim3(256), 0, s, x, mu, net, out, n, coef_dev, st);
+  else if (mode == 1) launch_k(sde_step_dev_kernel<1>, dim3(grid), dim3(256), 0, s, x, mu, net, out, n, coef_dev, st);
+  else if (mode == 2) launch_k(sde_step_dev_kernel<2>, dim3(grid), dim3(256), 0, s, x, mu, net, out, n, coef_dev, st);
+  else return set_error(-2, "dac_sde_step_dev: unknown mode %d", mode);
+  return check_launch("sde_step_dev_kernel");
 }
 
 extern "C" int dac_noise_state(const float* x, const float* eps, float* out, int64_t n, float max_sigma,

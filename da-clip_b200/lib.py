@@ -70,6 +70,8 @@ SYMBOLS = {
     "dac_reset_launch_count": (None, []),
     "dac_abi_sizes": (C.c_int, [C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "dac_sde_step": (C.c_int, [C.c_int, _p, _p, _p, _p, _p, _i64, C.POINTER(C.c_float), _p]),
+    "dac_loop_tick": (C.c_int, [_p, _p, _p, _p, _p, _p]),
+    "dac_sde_step_dev": (C.c_int, [C.c_int, _p, _p, _p, _p, C.c_int64, _p, _p, _p]),
     "dac_noise_state": (C.c_int, [_p, _p, _p, _i64, _f, _p]),
     "dac_unet_stem_input": (C.c_int, [_p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _i32, _p]),
     "dac_conv_create": (C.c_int, [C.POINTER(ConvDesc), C.POINTER(_p)]),

@@ -464,6 +464,19 @@ def noise_state(x, eps, out, max_sigma):
     L.check(L.load().dac_noise_state(L.ptr(x), L.ptr(eps), L.ptr(out), x.numel(), float(max_sigma), L.stream_ptr()))
 
 
+def loop_tick(state, t_table, coef_table, t_dev, coef_dev):
+    """First launch of a device-driven sampling step (dac_loop_tick): publishes the step's time and coefficients."""
+    L.check(L.load().dac_loop_tick(L.ptr(state), L.ptr(t_table), L.ptr(coef_table), L.ptr(t_dev), L.ptr(coef_dev),
+                                   L.stream_ptr()))
+
+
+def sde_step_dev(mode, x, mu, net, out, coef_dev, state):
+    """Last launch of a device-driven sampling step (dac_sde_step_dev)."""
+    _same_fp32("sde_step_dev", x, ("x", x), ("mu", mu), ("net", net), ("out", out))
+    L.check(L.load().dac_sde_step_dev(mode, L.ptr(x), L.ptr(mu), L.ptr(net), L.ptr(out), x.numel(), L.ptr(coef_dev),
+                                      L.ptr(state), L.stream_ptr()))
+
+
 def stem_input(xt, cond, out, H, W, pair=False):
     """out: [B, Hp, Wp, 64], or [B, Hp, Wp/2, 64] with pair=True (one packed row per pair of adjacent pixels)."""
     B, Hp, Wp = out.shape[0], out.shape[1], out.shape[2] * (2 if pair else 1)

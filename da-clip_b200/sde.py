@@ -210,6 +210,8 @@ class IRSDE:
             and set(kwargs) <= {"text_context", "image_context"}
         return m if ok else None
 
+    DEVICE_LOOP = os.environ.get("DAC_DEVICE_LOOP", "1") != "0"   # one CUDA graph per sampling step, nothing else launched
+
     def _reverse_fused(self, net, mode, xt, T, save_states, save_dir, noise, kwargs):
         """Hot loop: the state lives in the engine's static buffer; per step = one CUDA-graph replay of the
         denoiser plus one in-place fused update kernel.  No per-step allocation, copy or host sync."""
@@ -221,7 +223,28 @@ class IRSDE:
         eng = net.engine(B, H, W)
         eng.set_inputs(xt, self.mu, kwargs.get("text_context"), kwargs.get("image_context"))
         code = {"sde": 0, "posterior": 1, "ode": 2}[mode]
-        for i, t in enumerate(reversed(range(1, T + 1))):
+        ts = list(reversed(range(1, T + 1)))
+        eps_all, device_loop = None, self.DEVICE_LOOP and not save_states and eng.xt.numel() % 4 == 0 and len(ts) > 0
+        if device_loop and noise is not None and mode != "ode":
+            if isinstance(noise, (list, tuple)) and len(noise) >= len(ts) and all(torch.is_tensor(n) for n in noise[:len(ts)]):
+                noise = torch.stack([n.to(eng.xt.device, torch.float32) for n in noise[:len(ts)]])
+            if torch.is_tensor(noise) and noise.dim() == eng.xt.dim() + 1 and noise.shape[0] >= len(ts) \
+                    and noise.shape[1:] == eng.xt.shape:
+                eps_all = noise[:len(ts)].to(eng.xt.device, torch.float32).contiguous()
+            else:
+                device_loop = False                      # a callable / oddly shaped noise source: the per-step host loop
+        if device_loop:
+            # The whole step - tick (time and coefficients of step s from device tables), evaluation, fused in-place
+            # update with in-kernel Philox noise - is ONE CUDA graph; the host only replays it T times
+            # (sde_utils.py:297-313 is a python loop with a randn_like and a dozen pointwise launches per step).
+            pad = lambda c: list(c) + [0.0] * (8 - len(c))
+            coefs = [pad(self._posterior_coef(t) if mode == "posterior" else self._sde_coef(t, half=(mode == "ode"))) for t in ts]
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())     # follows torch.manual_seed (CPU generator)
+            eng.loop_begin([t * self.sample_scale for t in ts], coefs, eps_all, seed)
+            for _ in ts:
+                eng.loop_step(code)
+            return eng.xt.clone()
+        for i, t in enumerate(ts):
             eng.set_time(t * self.sample_scale)
             eng.replay()
             eps = None

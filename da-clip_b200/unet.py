@@ -397,6 +397,12 @@ class UNetEngine:
         self.text_ctx = torch.zeros(B, max(cfg.context_dim, 1), **f32)
         self.image_ctx = torch.zeros(B, max(cfg.context_dim, 1), **f32)
         self.t_dev = torch.zeros(1, **f32)
+        # device-driven sampling loop (IRSDE._reverse_fused): {next step, current step, noise tensor address or 0, Philox
+        # seed}, the step's 8 update coefficients, and the per-step tables the tick kernel reads them from
+        self.loop_state = torch.zeros(4, device=device, dtype=torch.int64)
+        self.loop_coef = torch.zeros(8, **f32)
+        self.loop_tables = None              # (t_table [Tmax], coef_table [Tmax, 8]) on the device, fixed addresses
+        self.loop_graphs = {}                # sampling mode code -> CUDA graph of one step incl. tick and update
         self.out_noise = torch.zeros(B, 3, H, W, **f32)
         self.temb = torch.zeros(B, cfg.time_dim, **f32)
         self.prompt_emb = torch.zeros(B, cfg.time_dim, **f32)
@@ -731,7 +737,7 @@ class UNetEngine:
             self.cond.fill_(float(cond))
         use_text = self.pk.has_prompt and text_context is not None
         if use_text != self.use_text:
-            self.use_text, self.graph = use_text, None
+            self.use_text, self.graph, self.loop_graphs = use_text, None, {}
         if use_text:
             self.text_ctx.copy_(text_context.reshape(self.B, -1))
         if self.cfg.transformer:
@@ -753,9 +759,57 @@ class UNetEngine:
         else:
             self.t_dev.fill_(float(time))
 
+    # -------------------------------------------------------------- device-driven sampling loop
+    LOOP_TMAX = 1024
+
+    def loop_begin(self, t_values, coefs, noise=None, seed=0):
+        """Uploads the per-step network times and update coefficients (two small H2D copies, once per restoration) and
+        resets the step counter.  noise: None (Philox inside the update kernel, keyed by `seed`) or a contiguous fp32
+        [T, B, 3, H, W] CUDA tensor with the draws of every step."""
+        T = len(t_values)
+        if T > self.LOOP_TMAX:
+            raise L.DacError(f"device-driven loop: at most {self.LOOP_TMAX} steps (got {T})")
+        if self.loop_tables is None:
+            dev = self.xt.device
+            self.loop_tables = (torch.zeros(self.LOOP_TMAX, device=dev), torch.zeros(self.LOOP_TMAX, 8, device=dev))
+        tt, ct = self.loop_tables
+        tt[:T].copy_(torch.tensor(t_values, dtype=torch.float32), non_blocking=False)
+        ct[:T].copy_(torch.tensor(coefs, dtype=torch.float32).reshape(T, 8), non_blocking=False)
+        addr = 0
+        if noise is not None:
+            if (noise.dtype != torch.float32 or not noise.is_contiguous() or noise.device != self.xt.device
+                    or noise.numel() != T * self.xt.numel()):
+                raise L.DacError("device-driven loop: noise must be a contiguous fp32 CUDA tensor [T, *x.shape]")
+            addr = noise.data_ptr()
+        self.loop_state.copy_(torch.tensor([0, 0, addr, int(seed) & 0x7FFFFFFFFFFFFFFF], dtype=torch.int64))
+        self._loop_keep = noise
+
+    def loop_step(self, code):
+        """One step of the sampling loop = one graph replay: tick, the whole evaluation, the fused in-place update."""
+        g = self.loop_graphs.get(code)
+        if g is None:
+            # first use: an eager warm-up step (validates every launch outside capture) and the capture; the warm-up
+            # advances the counter and updates the state in place, so both are put back afterwards
+            st, x0 = self.loop_state.clone(), self.xt.clone()
+            self._loop_eager(code)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._run_forked(loop_code=code)
+            self.loop_graphs[code] = g
+            self.loop_state.copy_(st)
+            self.xt.copy_(x0)
+        g.replay()
+
+    def _loop_eager(self, code):
+        ops.loop_tick(self.loop_state, self.loop_tables[0], self.loop_tables[1], self.t_dev, self.loop_coef)
+        self.run_eager()
+        ops.sde_step_dev(code, self.xt, self.cond, self.out_noise, self.xt, self.loop_coef, self.loop_state)
+
     def release(self):
         """Drop the graph, the plans (their destructors free the C-side handles) and every buffer (LRU eviction)."""
         self.graph = None
+        self.loop_graphs = {}
         self.steps, self.pre_steps, self.taps = [], [], {}
         for k in ("xt", "cond", "out_noise", "film", "temb", "prompt_emb", "text_ctx", "image_ctx"):
             setattr(self, k, None)
@@ -764,9 +818,11 @@ class UNetEngine:
         for _, fn in self.steps:
             fn()
 
-    def _run_forked(self):
+    def _run_forked(self, loop_code=None):
         """Capture order: the FiLM table (time MLP -> every ResBlock's scale/shift; a latency-bound chain of tiny
-        launches) runs on a side branch of the graph, beside stem_input + init_conv which do not need it."""
+        launches) runs on a side branch of the graph, beside stem_input + init_conv which do not need it.
+        loop_code: capture a whole sampling step - the tick kernel in front of the time MLP on the side branch and the
+        fused in-place update behind final_conv."""
         main = torch.cuda.current_stream()
         side = torch.cuda.Stream()
         fork, join = torch.cuda.Event(), torch.cuda.Event()
@@ -774,6 +830,8 @@ class UNetEngine:
         fork.record(main)
         side.wait_event(fork)
         with torch.cuda.stream(side):
+            if loop_code is not None:
+                ops.loop_tick(self.loop_state, self.loop_tables[0], self.loop_tables[1], self.t_dev, self.loop_coef)
             for name, fn in self.steps:
                 if name == "time_film":
                     fn()
@@ -791,6 +849,12 @@ class UNetEngine:
                 L.set_pdl(self.PDL and prev_kernel and not just_joined)
                 fn()
                 prev_kernel = True   # every step ends with a kernel launch (memsets come first where there are any)
+            if loop_code is not None:
+                if not joined:
+                    main.wait_event(join)
+                    joined = True
+                L.set_pdl(self.PDL)
+                ops.sde_step_dev(loop_code, self.xt, self.cond, self.out_noise, self.xt, self.loop_coef, self.loop_state)
         finally:
             L.set_pdl(False)
         if not joined:

@@ -51,6 +51,20 @@ int dac_abi_sizes(int32_t* conv_desc_bytes, int32_t* embed_weights_bytes);
  * update is bit-identical to the PyTorch fp32 expression. */
 int dac_sde_step(int mode, const float* x, const float* mu, const float* net, const float* eps, float* out,
                  int64_t n, const float* host_coef, dac_stream_t stream);
+/* The same updates inside a device-driven sampling loop (SDE:297-313: the host loop over t): every step of the loop is
+ * the same sequence of launches, so it can be one CUDA graph replayed T times with no host work in between.
+ * state: int64 [4] on the device = {next step, current step, address of a pre-generated [T][n] fp32 noise tensor or 0,
+ * Philox seed}; the host writes {0, 0, address, seed} before the first step and nothing afterwards.
+ * dac_loop_tick (first launch of a step): s = state[0]; t_dev[0] = t_table[s] (the network time of the step, read by
+ * dac_time_film); coef_dev[0..8) = coef_table[s][0..8) (coefficients as for dac_sde_step); state[1] = s; state[0] = s+1.
+ * dac_sde_step_dev (last launch of a step): dac_sde_step with the coefficients from coef_dev and the noise from row
+ * state[1] of the tensor at state[2] (the reference's draws in the parity tests) or, when state[2] == 0, from
+ * Philox4x32-10 keyed by (state[3], element / 4, state[1]) inside the kernel (four standard normals per call;
+ * statistically, not bitwise, what torch.randn_like draws at SDE:227-231).  n % 4 == 0; out may alias x. */
+int dac_loop_tick(int64_t* state, const float* t_table /*[T]*/, const float* coef_table /*[T][8]*/, float* t_dev,
+                  float* coef_dev /*[8]*/, dac_stream_t stream);
+int dac_sde_step_dev(int mode, const float* x, const float* mu, const float* net, float* out, int64_t n,
+                     const float* coef_dev, const int64_t* state, dac_stream_t stream);
 /* SDE:374-375  out = x + eps * max_sigma */
 int dac_noise_state(const float* x, const float* eps, float* out, int64_t n, float max_sigma, dac_stream_t stream);
 

@@ -795,6 +795,55 @@ def test_sde_step_bit_exact(cuda, mode):
         assert diff <= 2e-7 * max(1.0, ref.abs().max().item()), f"{mode} t={t}: max diff {diff}"
 
 
+def test_device_driven_step_tick_philox_and_injected_noise(ops, cuda):
+    """dac_loop_tick + dac_sde_step_dev: the step counter, time and coefficients come from device tables; the noise is
+    either row `step` of a pre-generated tensor (bit-identical to dac_sde_step with the same operands) or Philox normals
+    generated in the kernel (mean 0, variance 1, different per step, reproducible per seed)."""
+    from daclip_b200.sde import IRSDE
+    sde = IRSDE(50, T=100, schedule="cosine", eps=0.005, device=cuda)
+    g = torch.Generator(device="cuda").manual_seed(11)
+    shape, T = (2, 3, 64, 64), 5
+    x, mu, n = [torch.randn(shape, device="cuda", generator=g) for _ in range(3)]
+    eps = torch.randn((T,) + shape, device="cuda", generator=g)
+    ts = [100, 57, 33, 2, 1]
+    coefs = [list(sde._posterior_coef(t)) + [0.0] * 3 for t in ts]
+    t_tab = torch.tensor([float(t) for t in ts], device="cuda")
+    c_tab = torch.tensor(coefs, device="cuda", dtype=torch.float32)
+    t_dev, c_dev = torch.zeros(1, device="cuda"), torch.zeros(8, device="cuda")
+    state = torch.tensor([0, 0, eps.data_ptr(), 0], device="cuda", dtype=torch.int64)
+    for i, t in enumerate(ts):
+        ops.loop_tick(state, t_tab, c_tab, t_dev, c_dev)
+        out = torch.empty_like(x)
+        ops.sde_step_dev(1, x, mu, n, out, c_dev, state)
+        ref = torch.empty_like(x)
+        ops.sde_step(1, x, mu, n, eps[i].contiguous(), ref, sde._posterior_coef(t))
+        torch.cuda.synchronize()
+        assert state[:2].tolist() == [i + 1, i] and t_dev.item() == float(t)
+        assert torch.equal(out, ref), f"step {i}"
+    # Philox: x = mu = net = 0 and {term1, term2, std, exp, sigma_bar} = {0, 0, 1, 1, 0}: out is the noise itself
+    z = torch.zeros(4, 3, 256, 256, device="cuda")
+    c_tab = torch.tensor([[0, 0, 1, 1, 0, 0, 0, 0]] * 3, device="cuda", dtype=torch.float32)
+    draws = {}
+    for seed in (1234, 1234, 99):
+        state = torch.tensor([0, 0, 0, seed], device="cuda", dtype=torch.int64)
+        outs = []
+        for i in range(3):
+            ops.loop_tick(state, t_tab, c_tab, t_dev, c_dev)
+            o = torch.empty_like(z)
+            ops.sde_step_dev(1, z, z, z, o, c_dev, state)
+            outs.append(o)
+        torch.cuda.synchronize()
+        if seed in draws:
+            assert all(torch.equal(a, b) for a, b in zip(draws[seed], outs))      # reproducible per seed
+        draws[seed] = outs
+    a = draws[1234]
+    for o in a:
+        assert abs(o.mean().item()) < 5e-3 and abs(o.var().item() - 1.0) < 1e-2
+        assert abs((o ** 4).mean().item() - 3.0) < 0.1                            # Gaussian kurtosis
+    assert not torch.equal(a[0], a[1]) and not torch.equal(a[0], draws[99][0])
+    assert abs((a[0] * a[1]).mean().item()) < 5e-3                                # steps are uncorrelated
+
+
 # ---------------------------------------------------------------------------------------------- conditioning
 def test_time_film_and_cross_vec(ops, gen):
     from daclip_b200 import lib as L
