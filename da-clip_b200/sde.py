@@ -211,6 +211,12 @@ class IRSDE:
         return m if ok else None
 
     DEVICE_LOOP = os.environ.get("DAC_DEVICE_LOOP", "1") != "0"   # one CUDA graph per sampling step, nothing else launched
+    # Where the per-step Gaussian noise of the fused loop comes from when none is passed in:
+    #   "philox" - generated inside the update kernel (Philox4x32-10, seeded from torch's CPU generator once per call):
+    #              no noise tensor, no launch besides the step graph;
+    #   "torch"  - T x torch.randn_like drawn up front in loop order, i.e. the reference's own RNG stream
+    #              (sde_utils.py:227-231) - what the parity tests patch to inject the reference's draws.
+    noise_source = os.environ.get("DAC_NOISE_SOURCE", "philox")
 
     def _reverse_fused(self, net, mode, xt, T, save_states, save_dir, noise, kwargs):
         """Hot loop: the state lives in the engine's static buffer; per step = one CUDA-graph replay of the
@@ -233,6 +239,9 @@ class IRSDE:
                 eps_all = noise[:len(ts)].to(eng.xt.device, torch.float32).contiguous()
             else:
                 device_loop = False                      # a callable / oddly shaped noise source: the per-step host loop
+        elif device_loop and noise is None and mode != "ode" and self.noise_source == "torch":
+            # the reference's RNG stream: T draws of torch.randn_like in loop order (sde_utils.py:227-231), made up front
+            eps_all = torch.stack([torch.randn_like(eng.xt) for _ in ts])
         if device_loop:
             # The whole step - tick (time and coefficients of step s from device tables), evaluation, fused in-place
             # update with in-kernel Philox noise - is ONE CUDA graph; the host only replays it T times

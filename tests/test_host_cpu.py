@@ -197,3 +197,29 @@ def test_context_partial_slots_cover_every_image():
         assert lib.dac_linattn_ctx_slots(B, tpi, 1) == span, (B, tpi)
         assert lib.dac_linattn_ctx_slots(B, tpi, 2) == 2 * span
     assert lib.dac_linattn_ctx_slots(0, 4, 1) == 0
+
+
+def test_option_yaml_contract(tmp_path):
+    """options.parse + dict_to_nonedict on the reference's inference option file (tests/golden/options_test.yml, copied
+    byte for byte by oracle/gen_golden_options.py) against what the REFERENCE's own options.parse / dict_to_nonedict
+    produce (tests/golden/options_test.json; config/daclip-sde/options.py:18-120)."""
+    import json
+    from daclip_b200 import options
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    want = json.load(open(os.path.join(gold, "options_test.json")))
+    before = os.environ.get("CUDA_VISIBLE_DEVICES")
+    opt = options.dict_to_nonedict(options.parse(os.path.join(gold, "options_test.yml"), is_train=False, root=str(tmp_path)))
+    assert os.environ.get("CUDA_VISIBLE_DEVICES") == before            # the launcher owns it unless asked
+    got = json.loads(json.dumps(opt))
+    root = got["path"].pop("root")
+    assert root == str(tmp_path)
+    assert got["path"].pop("results_root") == os.path.join(root, "results", "daclip-sde", "universal-ir")
+    assert got["path"].pop("log") == os.path.join(root, "results", "daclip-sde", "universal-ir")
+    assert got == want["opt"]
+    assert isinstance(opt, options.NoneDict) and isinstance(opt["network_G"]["setting"], options.NoneDict)
+    assert opt["suffix"] is None and opt["crop_border"] is None and opt["no_such_key"] is None
+    assert opt["path"]["strict_load"] is None and opt["datasets"]["test1"]["no_such_key"] is None
+    assert want["missing_keys_read_as"] == {"suffix": None, "crop_border": None, "no_such_key": None, "path.strict_load": None}
+    # what the restoration script reads from it (test.py:68-85)
+    assert opt["sde"] == {"max_sigma": 50, "T": 100, "schedule": "cosine", "eps": 0.005, "sampling_mode": "posterior"}
+    assert opt["network_G"]["which_model_G"] == "ConditionalUNet" and opt["degradation"]["scale"] == 4

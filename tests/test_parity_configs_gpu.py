@@ -56,6 +56,7 @@ def stack(cuda):
     model = create_model(opt)
     model.load_state_dict_into_model(sd)
     sde = IRSDE(max_sigma=50, T=100, schedule="cosine", eps=0.005, device=cuda)
+    sde.noise_source = "torch"          # the reference's RNG stream (T x torch.randn_like): what the tests below patch
     sde.set_model(model.model)
     sdc = {k: v.to(cuda) for k, v in sd.items()}
     den = O.make_denoiser(sdc, O.UNetConfig(**kw))

@@ -290,3 +290,58 @@ def test_evaluation_is_bit_reproducible(model, B, H, W):
                       image_context=inp["image_context"]).clone())
     assert torch.isfinite(outs[0]).all()
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+
+
+def test_model_from_option_yaml_vs_reference_golden(model, gold, cuda, tmp_path):
+    """The reference's entry sequence (config/daclip-sde/test.py:26-28,68-85,112-127): options.parse(test.yml) ->
+    dict_to_nonedict -> create_model(opt) (checkpoint from path.pretrain_model_G, keys with the DataParallel `module.`
+    prefix) -> IRSDE(**opt['sde']) -> feed_data -> test(sde, opt['sde']['sampling_mode']) - against the reference's own
+    T = 100 loop (tests/golden/unet_sampler.pt)."""
+    import unittest.mock as um
+    from daclip_b200 import options, synthetic
+    from daclip_b200.model import create_model
+    from daclip_b200.sde import IRSDE
+    _, sd, kw = model
+    ckpt = tmp_path / "universal-ir.pth"
+    torch.save({"module." + k: v for k, v in sd.items()}, ckpt)
+    opt = options.parse(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "options_test.yml"),
+                        is_train=False, root=str(tmp_path))
+    opt["path"]["pretrain_model_G"] = str(ckpt)                 # the only edit a user makes: where the weights are
+    opt = options.dict_to_nonedict(opt)
+    assert dict(opt["network_G"]["setting"]) == {k: kw[k] for k in opt["network_G"]["setting"]}
+    m = create_model(opt)
+    assert m.device.type == "cuda"
+    so = opt["sde"]
+    sde = IRSDE(max_sigma=so["max_sigma"], T=so["T"], schedule=so["schedule"], eps=so["eps"], device=m.device)
+    sde.set_model(m.model)
+    sde.noise_source = "torch"                                  # the reference's RNG stream, patched below
+    g = gold["trajectory"]
+    inp = {k: v.cuda() for k, v in synthetic.restoration_inputs(1, 32, 32, T=g["T"], seed=g["seed"]).items()}
+    x_T = inp["lq"] + inp["eps0"] * sde.max_sigma
+    m.feed_data(x_T, inp["lq"], None, text_context=inp["text_context"], image_context=inp["image_context"])
+    it = iter(inp["noise"])
+    with um.patch("torch.randn_like", lambda t: next(it)):
+        m.test(sde, mode=so["sampling_mode"])
+    x = m.get_current_visuals(need_GT=False)["Output"]
+    ref = g[so["sampling_mode"]][0]
+    err = (x - ref).abs().max().item()
+    assert err <= 2e-2 and psnr(x, ref) >= 45.0, (err, psnr(x, ref))
+
+
+def test_default_noise_source_follows_torch_seed(model, cuda):
+    """Without injected noise the fused loop draws its Gaussians inside the update kernel (Philox, seeded once per call
+    from torch's generator): torch.manual_seed makes a restoration reproducible, another seed gives another sample."""
+    from daclip_b200 import synthetic
+    from daclip_b200.sde import IRSDE
+    m, _, _ = model
+    inp = {k: v.cuda() for k, v in synthetic.restoration_inputs(2, 32, 32, T=1, seed=9).items()}
+    sde = IRSDE(max_sigma=50, T=100, sample_T=10, schedule="cosine", eps=0.005, device=cuda)
+    sde.set_model(m)
+    sde.set_mu(inp["lq"])
+    x_T = inp["lq"] + inp["eps0"] * sde.max_sigma
+    outs = []
+    for seed in (5, 5, 6):
+        torch.manual_seed(seed)
+        outs.append(sde.reverse_sde(x_T, text_context=inp["text_context"], image_context=inp["image_context"]))
+    assert torch.isfinite(outs[0]).all()
+    assert torch.equal(outs[0], outs[1]) and not torch.equal(outs[0], outs[2])
