@@ -34,10 +34,25 @@ ALGO_GFLOP_PER_EVAL = {256: 266.2, 512: 1129.1}
 # plus the LinearAttention "apply" einsum that is folded into to_out = 1.41): everything except the k-softmax
 # context einsum (1.41) and the self-attention QK^T/PV (5.37).  At 512^2: 1031.9 + 5.64.
 CONV_GFLOP_PER_EVAL = {256: 257.98 + 1.41, 512: 1031.9 + 5.64}
-# dram__bytes_read.sum + dram__bytes_write.sum of conv_igemm_kernel, averaged over its launches of one evaluation, from
-# the ncu launch list of this same command in steady state (profiles/r01_ncu_launches_bench_n1.csv: --launch-skip 16000
-# -c 250 = 2.05 evaluations, 163 conv launches): batch 16, 256^2 only.
-CONV_DRAM_BYTES_PER_LAUNCH = {(16, 256): 95.8e6}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the tcgen05 GEMM kernels come from the committed summary of
+# the ncu launch list of this same command in steady state (tools/ncu_launches.py -> profiles/*_ncu_launch_summary.json:
+# `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --launch-skip N -c M python bench.py`);
+# the ALGORITHMIC bytes beside them are computed here from the plans (every operand tensor once).
+
+
+def measured_traffic(B, S):
+    """(mean DRAM bytes per launch of the tcgen05 GEMM kernels, source) from the newest committed ncu launch summary
+    whose configuration matches, else (None, why)."""
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_launch_summary.json")), reverse=True):
+        try:
+            d = json.load(open(path))
+        except Exception:
+            continue
+        if d.get("batch") == B and d.get("image") == S and d.get("gemm_kernels"):
+            g = d["gemm_kernels"]
+            return g["dram_bytes_per_launch"], f"{os.path.relpath(path, ROOT)} ({g['launches']} launches)"
+    return None, "no committed ncu launch summary for this configuration"
 
 
 def peaks():
@@ -289,6 +304,10 @@ def run_product(args):
         gflop = CONV_GFLOP_PER_EVAL.get(S, CONV_GFLOP_PER_EVAL[256] * (S / 256) ** 2) * B
         achieved = gflop / n_conv / (conv_ms / n_conv) if conv_ms > 0 else 0.0       # GFLOP/ms == TFLOP/s
         launches_per_eval = eng.launches + 2                                          # + loop tick + fused SDE update
+        n_lin = len(getattr(eng, "linattn_names", ()))
+        lb = getattr(eng, "layer_bytes", {})
+        algo_bytes = sum(lb.values()) / max(1, len(lb))                               # mean per tcgen05 GEMM launch
+        traffic, traffic_src = measured_traffic(B, S)
         algo = ALGO_GFLOP_PER_EVAL.get(S, ALGO_GFLOP_PER_EVAL[256] * (S / 256) ** 2)
         result = {
             "metric": "restored images/sec @256^2 T=100", "value": round(value, 3), "unit": "images/s",
@@ -303,10 +322,14 @@ def run_product(args):
                        "parallelism": f"batch-sharded x{world}, one all_gather per restoration",
                        "l2": "working set per denoiser step (>2 GB of activations) exceeds the 126 MB L2"},
             "whole_step_tensor_frac": round(world and (algo * B * T_STEPS / ms_per_step) / peak_tf, 4),
-            "roofline": {"bound": "tensor", "kernel": "conv_igemm_kernel (tcgen05 implicit GEMM)",
+            "roofline": {"bound": "tensor",
+                         "kernel": "the tcgen05 GEMM launches of one evaluation: conv_igemm_kernel (every Conv2d / Linear) "
+                                   "and the chained LinearAttention kernels linattn_kv(2)_kernel / linattn_qout(2)_kernel",
+                         "kernels_summed": {"conv_igemm_kernel": n_conv - n_lin, "linattn_kv/qout kernels": n_lin},
                          "achieved": round(achieved, 2), "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": round(achieved / peak_tf, 4),
-                         "traffic": CONV_DRAM_BYTES_PER_LAUNCH.get((B, S)),
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "algorithmic_bytes": round(algo_bytes, 1),
                          "peak_source": f"{which} bf16_tflops_sustained",
                          "launches_per_eval": n_conv, "conv_ms_per_eval": round(conv_ms, 3),
                          "all_kernels_ms_per_eval": round(all_ms, 3),

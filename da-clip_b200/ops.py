@@ -261,6 +261,17 @@ class ConvPlan:
         self._keep += (rsrc0, rsrc1, rweight, stats_out, ln_stats, ln_colsum, kv_shift, ctx_acc)
         self.flops = 2.0 * B * OH * OW * pw.ngroups * len(pw.taps[0]) * (c0 + c1) * pw.cout \
             + 2.0 * B * OH * OW * (rc0 + rc1) * pw.cout * (rsrc0 is not None)
+        # algorithmic DRAM bytes of one launch: every operand tensor once (bf16 unless noted)
+        opix = B * OH * OW * pw.out_scale ** 2
+        out_c = pw.cout // 2 if epi == L.EPI_GEGLU else pw.cout
+        self.bytes = (2.0 * B * H * W * (c0 + c1) + 2.0 * wt.numel()
+                      + (2.0 * opix * out_c if out is not None else 0.0)
+                      + (4.0 * out_nchw.numel() if out_nchw is not None else 0.0)
+                      + (4.0 * out_f32.numel() if out_f32 is not None else 0.0)
+                      + (4.0 * res_f32.numel() if res_f32 is not None else 0.0)
+                      + (2.0 * out_planar.numel() if out_planar is not None else 0.0)
+                      + 2.0 * opix * out_c * ((res is not None) + (res2 is not None))
+                      + 2.0 * B * H * W * (rc0 + rc1) * (rsrc0 is not None))
 
     def run(self):
         L.check(self._lib.dac_conv_launch(self.handle, L.stream_ptr()))
@@ -351,6 +362,9 @@ class PairConvPlan(ConvPlan):
         self._lib = lib
         cout = out_nchw.shape[1] if out_nchw is not None else 64
         self.flops = 2.0 * B * H * W * 9 * (64 + (64 if src1 is not None else 0)) * cout + 2.0 * B * H * W * rc * 64
+        self.bytes = (2.0 * B * H * W * 64 * (1 + (src1 is not None)) + 2.0 * wpair.numel()
+                      + (4.0 * out_nchw.numel() if out_nchw is not None else 2.0 * B * H * W * 64)
+                      + 2.0 * B * H * W * 64 * (res is not None) + 2.0 * B * H * W * rc)
 
 
 def ctx_slots(B, h, w, tensor_core_kv):
@@ -387,6 +401,7 @@ class KvPlan:
         self.handle, self._lib = h, lib
         self._keep = (xn, wkv_grouped, kv_shift, ctx_acc, ln_stats, ln_colsum)
         self.flops = 2.0 * B * hw * Cn * 256      # algorithmic (k and v rows), whichever way the kernel gets there
+        self.bytes = 2.0 * B * hw * Cn + 4.0 * ctx_acc.numel()
 
     def run(self):
         L.check(self._lib.dac_linattn_kv_launch(self.handle, L.stream_ptr()))
@@ -418,6 +433,7 @@ class QoutPlan:
         self.handle, self._lib = h, lib
         self._keep = (xn, wq, weff, res, out, bias, ln_g, ln_stats, ln_colsum, q_shift)
         self.flops = 2.0 * B * hw * 128 * Cn * 2
+        self.bytes = 2.0 * B * hw * Cn * (2 if xn.data_ptr() == res.data_ptr() else 3) + 2.0 * weff.numel()
 
     def run(self):
         L.check(self._lib.dac_linattn_qout_launch(self.handle, L.stream_ptr()))

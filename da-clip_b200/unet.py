@@ -413,6 +413,8 @@ class UNetEngine:
         self.taps = {}           # block name -> output buffer (NHWC bf16), for per-layer parity checks
         self.conv_names = set()  # steps that are tcgen05 implicit-GEMM launches
         self.layer_flops = {}    # algorithmic FLOPs of each of them (layer dumps)
+        self.layer_bytes = {}    # ... and algorithmic DRAM bytes (every operand tensor once)
+        self.linattn_names = set()   # the members of conv_names that run in the linattn_kv / linattn_qout kernels
         self.flops = 0.0
         self._bytes = 0
         self._build()
@@ -431,6 +433,7 @@ class UNetEngine:
         plan = ops.ConvPlan(src, c0, pw, out, B=self.B, H=h, W=w, **kw)
         self.flops += plan.flops
         self.layer_flops[name] = plan.flops
+        self.layer_bytes[name] = plan.bytes
         self.conv_names.add(name)
         self.add(name, plan.run)
         return plan
@@ -442,6 +445,7 @@ class UNetEngine:
         plan = ops.PairConvPlan(src0, wpair, out, B=self.B, H=h, W=w, **kw)
         self.flops += plan.flops
         self.layer_flops[name] = plan.flops
+        self.layer_bytes[name] = plan.bytes
         self.conv_names.add(name)
         self.add(name, plan.run)
         return plan
@@ -555,6 +559,8 @@ class UNetEngine:
                                       ln_stats=stats, ln_colsum=a["kv_grouped_colsum"] if fold else None, prenorm_eps=pn_eps)
                     self.flops += plan.flops
                     self.layer_flops[prefix + "to_kv"] = plan.flops
+                    self.layer_bytes[prefix + "to_kv"] = plan.bytes
+                    self.linattn_names.add(prefix + "to_kv")
                     self.conv_names.add(prefix + "to_kv")
                     self.add(prefix + "to_kv", plan.run)
                 else:
@@ -574,6 +580,8 @@ class UNetEngine:
                                         prenorm_eps=pn_eps, q_shift=a["q_shift"] if pn_eps is not None else None)
                     self.flops += plan.flops
                     self.layer_flops[prefix + "to_q_out"] = plan.flops
+                    self.layer_bytes[prefix + "to_q_out"] = plan.bytes
+                    self.linattn_names.add(prefix + "to_q_out")
                     self.conv_names.add(prefix + "to_q_out")
                     self.add(prefix + "to_q_out", plan.run)
                     return out
