@@ -138,7 +138,9 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
       return set_error(-2, "dac_conv_create: pixel-pair mode needs a haloed 3x3 conv, PLAIN epilogue, wide views with "
                            "block_n = cout = 128 and channel counts that are multiples of 128");
   }
-  ConvKernelFn kernel = pick_conv_kernel(d->epi, d->act, d->film != nullptr, nchw);
+  // the fp32 residual stream of the ViT blocks has its own flavour (residual chunks prefetched two ahead)
+  const bool f32_stream = d->res_f32 && !d->res && !d->res2 && !d->bias_img && !d->stats_out && !d->rsrc0;
+  ConvKernelFn kernel = pick_conv_kernel(d->epi, d->act, d->film != nullptr, nchw, f32_stream);
   if (!kernel) return set_error(-2, "dac_conv_create: unsupported activation / FiLM combination (%d, %d)", d->act,
                                 d->film != nullptr);
   if (d->out && ((d->out_ld | d->out_coff) & 7)) return set_error(-2, "dac_conv_create: out_ld/out_coff %% 8");

@@ -25,7 +25,7 @@
 
 namespace dac {
 
-enum { KE_PLAIN = 0, KE_GEGLU = 1, KE_LN = 2, KE_QKV = 3, KE_NCHW = 4, KE_KVCTX = 5 };
+enum { KE_PLAIN = 0, KE_GEGLU = 1, KE_LN = 2, KE_QKV = 3, KE_NCHW = 4, KE_KVCTX = 5, KE_F32 = 6 };
 constexpr int kKvPitch = 40;                                   // bf16 per row of a [128 px][32 ch] head tile
 constexpr uint32_t kKvTileBytes = kTileM * kKvPitch * 2;         // 10 KB
 constexpr uint32_t kKvStageBytes = 4 * kKvTileBytes;             // P and V head tiles, double-buffered: per group
@@ -267,6 +267,36 @@ __device__ __forceinline__ void epilogue_tile(const ConvKParams& p, const TileCo
       else if (valid && p.res) chunk_add_bf16(p.res + opix * p.res_ld + c, v);
       if (stg) chunk_stage_bf16(stg, row, c, v);
       else if (valid) chunk_store_bf16(p.out + opix * p.out_ld + p.out_coff + c, v);
+    }
+    return;
+  }
+
+  if (EPI == KE_F32) {
+    // out_f32 = acc + bias + res_f32 (the ViT blocks' fp32 residual stream, updated in place), optionally a bf16 copy.
+    // A thread's row is 3 KB away from its neighbour's: with 16-byte accesses every warp instruction touched 32 sectors
+    // and used half of each (out_proj 54 us against 26 us for the same GEMM without the stream); 256-bit accesses move
+    // whole 32-byte sectors.  (Prefetching the residual chunks two ahead in registers changed nothing: 56 us.)
+    for (int c = 0; c < p.block_n; c += 32) {
+      const int ch = t.nt * p.block_n + c;
+      if (ch >= p.cout) break;  // warp-uniform (cout_pad > cout)
+      chunk_from_tmem(tmem_acc + c, v);
+      if (p.bias) chunk_add_f32(p.bias + ch, v);
+      if (valid) {
+        const float* rs = p.res_f32 + opix * p.res_f32_ld + ch;
+        float* os = p.out_f32 ? p.out_f32 + opix * p.out_f32_ld + ch : nullptr;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          U32x8 r = ldg256(rs + 8 * q);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            v[8 * q + j] += __uint_as_float(r.v[j]);
+            r.v[j] = __float_as_uint(v[8 * q + j]);
+          }
+          if (os) stg256(os + 8 * q, r);
+        }
+        if (p.out && !stg && !(p.dbg & 1)) chunk_store_bf16(p.out + opix * p.out_ld + p.out_coff + ch, v);
+      }
+      if (stg && !(p.dbg & 1)) chunk_stage_bf16(stg, row, c, v);
     }
     return;
   }
@@ -993,8 +1023,9 @@ typedef void (*ConvKernelFn)(const CUtensorMap, const CUtensorMap, const CUtenso
 
 // The epilogue flavours that exist as separate kernels; everything else in the epilogue is a warp-uniform
 // runtime branch on a pointer.
-inline ConvKernelFn pick_conv_kernel(int epi, int act, bool film, bool nchw) {
+inline ConvKernelFn pick_conv_kernel(int epi, int act, bool film, bool nchw, bool f32_stream = false) {
   if (nchw) return conv_igemm_kernel<KE_NCHW, DAC_ACT_NONE, false>;
+  if (f32_stream && epi == DAC_EPI_PLAIN && act == DAC_ACT_NONE && !film) return conv_igemm_kernel<KE_F32, DAC_ACT_NONE, false>;
   if (epi == DAC_EPI_GEGLU) return conv_igemm_kernel<KE_GEGLU, DAC_ACT_NONE, false>;
   if (epi == DAC_EPI_LN) return conv_igemm_kernel<KE_LN, DAC_ACT_NONE, false>;
   if (epi == DAC_EPI_QKV) return conv_igemm_kernel<KE_QKV, DAC_ACT_NONE, false>;

@@ -36,9 +36,11 @@ __device__ __forceinline__ float sde_update(float x, float mu, float n, float e,
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(256) sde_step_kernel(const float* __restrict__ x, const float* __restrict__ mu,
+// (x and out carry no __restrict__: the samplers update the state in place, out == x; every element is read before it is
+// written by the same thread)
+__global__ void __launch_bounds__(256) sde_step_kernel(const float* x, const float* __restrict__ mu,
                                                        const float* __restrict__ net, const float* __restrict__ eps,
-                                                       float* __restrict__ out, int64_t n, SdeCoef k) {
+                                                       float* out, int64_t n, SdeCoef k) {
   const int64_t n4 = n >> 2;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -80,8 +82,8 @@ __global__ void loop_tick_kernel(long long* __restrict__ state, const float* __r
 // tests inject the reference's draws) or generated here: Philox4x32-10 keyed by (seed, element quad, step), four normals
 // per call - the sampler then launches nothing but its own kernels (sde_utils.py:227-231 draws torch.randn_like per step).
 template <int MODE>
-__global__ void __launch_bounds__(256) sde_step_dev_kernel(const float* __restrict__ x, const float* __restrict__ mu,
-                                                           const float* __restrict__ net, float* __restrict__ out,
+__global__ void __launch_bounds__(256) sde_step_dev_kernel(const float* x, const float* __restrict__ mu,
+                                                           const float* __restrict__ net, float* out,
                                                            int64_t n, const float* __restrict__ coef_dev,
                                                            const long long* __restrict__ state) {
   griddep_wait();      // launched with programmatic serialisation behind final_conv: its output must be complete

@@ -10,7 +10,7 @@ clip = DaCLIP().load_reference_state_dict(synthetic.daclip_visual_state_dict(10)
 img = torch.randn(B, 3, 224, 224, device=dev)
 for _ in range(2):
     clip.encode_image(img, control=True)
-eng = clip._engines[B]
+eng = next(iter(clip._engines.values()))
 torch.cuda.synchronize()
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(eng.steps) + 1)]
 for rep in range(2):
