@@ -263,7 +263,9 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const __nv_bfloat16
   }
 }
 
-// fp32 rows in (ViT residual stream), bf16 rows out.
+// fp32 rows in (ViT residual stream), bf16 rows out.  One warp per row; the row (up to 1024 channels = 8 float4 per lane)
+// is read ONCE into registers - the first version walked it three times (sum, centred squares, output), each pass a
+// dependent trip to L2.
 __global__ void __launch_bounds__(256) layernorm_rows_f32_kernel(const float* __restrict__ in, int ld_in,
                                                                  __nv_bfloat16* __restrict__ out, int ld_out,
                                                                  int64_t rows, int c, const float* __restrict__ w,
@@ -274,35 +276,43 @@ __global__ void __launch_bounds__(256) layernorm_rows_f32_kernel(const float* __
   const int nvec = c >> 2;
   for (int64_t row = warp_global; row < rows; row += nwarps) {
     const float4* src = reinterpret_cast<const float4*>(in + row * ld_in);
+    float4 u[8];
     float sum = 0.f;
-    for (int i = lane; i < nvec; i += 32) {
-      const float4 u = src[i];
-      sum += (u.x + u.y) + (u.z + u.w);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int i = lane + 32 * k;
+      u[k] = i < nvec ? src[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+      sum += (u[k].x + u[k].y) + (u[k].z + u[k].w);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     const float mean = sum / c;
     float ss = 0.f;
-    for (int i = lane; i < nvec; i += 32) {
-      const float4 u = src[i];
-      const float e0 = u.x - mean, e1 = u.y - mean, e2 = u.z - mean, e3 = u.w - mean;
-      ss += e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (lane + 32 * k < nvec) {
+        const float e0 = u[k].x - mean, e1 = u[k].y - mean, e2 = u[k].z - mean, e3 = u[k].w - mean;
+        ss += e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3;
+      }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
     const float rstd = rsqrtf(ss / c + eps);
     uint2* dst = reinterpret_cast<uint2*>(out + row * ld_out);
-    for (int i = lane; i < nvec; i += 32) {
-      const float4 u = src[i];
-      float v[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float y = (v[j] - mean) * rstd;
-        if (w) y *= __ldg(w + i * 4 + j);
-        if (b) y += __ldg(b + i * 4 + j);
-        v[j] = y;
+    for (int k = 0; k < 8; ++k) {
+      const int i = lane + 32 * k;
+      if (i < nvec) {
+        float v[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+        float4 wv = make_float4(1.f, 1.f, 1.f, 1.f), bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (w) wv = __ldg(reinterpret_cast<const float4*>(w) + i);
+        if (b) bv = __ldg(reinterpret_cast<const float4*>(b) + i);
+        v[0] = (v[0] - mean) * rstd * wv.x + bv.x;
+        v[1] = (v[1] - mean) * rstd * wv.y + bv.y;
+        v[2] = (v[2] - mean) * rstd * wv.z + bv.z;
+        v[3] = (v[3] - mean) * rstd * wv.w + bv.w;
+        dst[i] = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
       }
-      dst[i] = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
     }
   }
 }
@@ -642,8 +652,11 @@ extern "C" int dac_layernorm_rows_f32(const float* in, int32_t ld_in, void* out,
   if (!in || !out) return set_error(-1, "dac_layernorm_rows_f32: null argument");
   if ((c & 3) || (ld_in & 3) || (ld_out & 3)) return set_error(-2, "dac_layernorm_rows_f32: c and pitches must be multiples of 4");
   if (rows <= 0) return 0;
+  if (c > 1024) return set_error(-2, "dac_layernorm_rows_f32: c must be <= 1024");
+  if ((reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(in)) & 15)
+    return set_error(-2, "dac_layernorm_rows_f32: in, w and b must be 16-byte aligned");
   const int64_t blocks = ceil_div(rows, 8);
-  const int grid = static_cast<int>(blocks > 148 * 8 ? 148 * 8 : blocks);
+  const int grid = static_cast<int>(blocks > 148 * 16 ? 148 * 16 : blocks);
   layernorm_rows_f32_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       in, ld_in, static_cast<__nv_bfloat16*>(out), ld_out, rows, c, w, b, eps);
   return check_launch("layernorm_rows_f32_kernel");

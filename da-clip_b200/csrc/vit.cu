@@ -30,6 +30,29 @@ __global__ void __launch_bounds__(256) vit_patchify_kernel(const float* __restri
   }
 }
 
+// p % 8 == 0 (ViT-B/32): eight pixels per thread - two 16-byte loads, one 16-byte store, one set of divisions per eight
+// pixels (the two-pixel version above spends its time in integer divisions: 171 us for 154 MB at batch 256)
+__global__ void __launch_bounds__(256) vit_patchify8_kernel(const float* __restrict__ img,
+                                                            __nv_bfloat16* __restrict__ out, int B, int S, int p,
+                                                            int ld_out) {
+  const int g = S / p;
+  const int pv = p >> 3;                               // 8-pixel vectors per patch row
+  const int kv = 3 * p * pv;                           // ... per patch
+  const int64_t total = static_cast<int64_t>(B) * g * g * kv;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int v = static_cast<int>(i % kv);
+    const int64_t row = i / kv;
+    const int gx = static_cast<int>(row % g), gy = static_cast<int>((row / g) % g), b = static_cast<int>(row / (g * g));
+    const int x8 = v % pv, py = (v / pv) % p, c = v / (pv * p);
+    const float4* src = reinterpret_cast<const float4*>(
+        img + ((static_cast<int64_t>(b) * 3 + c) * S + gy * p + py) * S + gx * p + x8 * 8);
+    const float4 a = __ldg(src), d = __ldg(src + 1);
+    *reinterpret_cast<uint4*>(out + row * ld_out + (c * p + py) * p + x8 * 8) =
+        make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(d.x, d.y), pack_bf16(d.z, d.w));
+  }
+}
+
 __device__ __forceinline__ float block_sum(float v, float* red) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -207,6 +230,13 @@ extern "C" int dac_vit_patchify(const float* image, void* out, int32_t B, int32_
   if (S % p || (p & 1)) return set_error(-2, "dac_vit_patchify: patch must be even and divide the image");
   if (ld_out < 3 * p * p || (ld_out & 1)) return set_error(-2, "dac_vit_patchify: ld_out must be even and >= 3*p*p");
   const int g = S / p;
+  if (p % 8 == 0 && S % 8 == 0 && ld_out % 8 == 0 && !((reinterpret_cast<uintptr_t>(image) | reinterpret_cast<uintptr_t>(out)) & 15)) {
+    int64_t blocks8 = ceil_div(static_cast<int64_t>(B) * g * g * 3 * p * (p / 8), 256);
+    if (blocks8 > 148 * 32) blocks8 = 148 * 32;
+    vit_patchify8_kernel<<<static_cast<int>(blocks8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        image, static_cast<__nv_bfloat16*>(out), B, S, p, ld_out);
+    return check_launch("vit_patchify8_kernel");
+  }
   const int64_t total = static_cast<int64_t>(B) * g * g * 3 * p * p / 2;
   int64_t blocks = ceil_div(total, 256);
   if (blocks > 148 * 16) blocks = 148 * 16;

@@ -1,4 +1,4 @@
 #!/bin/bash
-timeout 600 python -m pytest tests/test_daclip_gpu.py tests/test_kernels_gpu.py -q -x 2>&1 | tail -3
-timeout 300 python tools/prof_encoder_layers.py 256
-timeout 300 python tools/abtime.py
+timeout 600 python -m pytest tests/test_daclip_gpu.py -q -x 2>&1 | tail -3
+timeout 300 python tools/prof_encoder_layers.py 256 | tail -3
+timeout 300 python tools/bench_configs.py 2>&1 | tail -2
