@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdac_b200.so")
-SOURCES = ["api.cu", "conv_igemm.cu", "elementwise.cu", "linattn.cu", "attention.cu", "vit.cu", "imageio.cu", "linattn_qout.cu", "attention_tc.cu", "attention_tc2.cu", "linattn_kv.cu", "linattn_kv2.cu", "linattn_qout2.cu"]
+SOURCES = ["api.cu", "conv_igemm.cu", "elementwise.cu", "linattn.cu", "attention.cu", "vit.cu", "imageio.cu", "linattn_qout.cu", "attention_tc.cu", "attention_tc2.cu", "attention_vit.cu", "linattn_kv.cu", "linattn_kv2.cu", "linattn_qout2.cu"]
 HEADERS = ["common.h", "ptx.cuh", "tile_common.cuh", "tensormap.h", "conv_kernel.cuh", "linattn_kv_common.h", "linattn_qout_common.h", os.path.join("..", "..", "include", "dac_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -187,6 +187,7 @@ using namespace dac;
 
 int dac_attention_tc(const void* qkv, void* out, int B, int n, int heads, cudaStream_t stream);   // attention_tc.cu
 int dac_attention_tc2(const void* qkv, void* out, int B, int n, int heads, cudaStream_t stream);  // attention_tc2.cu
+int dac_attention_vit(const void* qkv, void* out, int B, int n, int heads, int causal, cudaStream_t stream);  // attention_vit.cu
 
 extern "C" int dac_attention(const void* qkv, void* out, int32_t B, int32_t n, int32_t heads, int32_t d,
                              dac_stream_t stream) {
@@ -205,6 +206,8 @@ extern "C" int dac_attention(const void* qkv, void* out, int32_t B, int32_t n, i
         static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), n, heads, 0.17677669529663687f * l2e);
     return check_launch("flash_attn_kernel<32>");
   }
+  // d = 64, up to 512 tokens (the ViT blocks: 50 / 257 tokens): tcgen05 kernel of attention_vit.cu
+  if (d == 64 && n > 0 && n <= 512 && B > 0 && heads > 0 && !no_tc) return dac_attention_vit(qkv, out, B, n, heads, 0, s);
   if (d == 64) {   // ViT-B/32 blocks: 50 tokens, one 64-row CTA per (image, head)
     flash_attn_kernel<64, 4><<<dim3((n + 63) / 64, heads, B), 128, 0, s>>>(
         static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), n, heads, 0.125f * l2e);
@@ -218,6 +221,9 @@ extern "C" int dac_attention_causal(const void* qkv, void* out, int32_t B, int32
   if (!qkv || !out) return set_error(-1, "dac_attention_causal: null argument");
   if (d != 64 || B <= 0 || n <= 0 || heads <= 0)
     return set_error(-2, "dac_attention_causal: head dim 64 only (got %d), positive sizes", d);
+  // one key block (the text tower: 77 tokens): tcgen05 kernel of attention_vit.cu with the causal mask
+  if (n <= 128 && !getenv("DAC_NO_TC_ATTN"))
+    return dac_attention_vit(qkv, out, B, n, heads, 1, static_cast<cudaStream_t>(stream));
   flash_attn_kernel<64, 4, true><<<dim3((n + 63) / 64, heads, B), 128, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), n, heads, 0.125f * 1.4426950408889634f);
   return check_launch("flash_attn_kernel<64, causal>");

@@ -725,6 +725,30 @@ def test_small_attention_d64(ops, gen):
     assert_close_bf16(out, ref, "small attn d64")
 
 
+@pytest.mark.parametrize("B,n,heads,causal", [(3, 50, 12, False), (300, 50, 12, False), (2, 257, 16, False), (5, 128, 2, False),
+                                              (1, 1, 3, False), (2, 400, 4, False), (10, 77, 8, True), (3, 128, 12, True),
+                                              (2, 5, 1, True)])
+def test_attention_d64_tcgen05(ops, gen, B, n, heads, causal):
+    """attn_vit_kernel (tcgen05): the ViT blocks' attention (50 / 257 tokens, transformer.py:219-230) and, causal, the text
+    tower's (77 tokens, model.py:237-249) - unused tile rows, several key blocks, many items per CTA, growing scores."""
+    d = 64
+    qkv = rnd(gen, B, n, 3 * heads * d)
+    qkv[:, :, heads * d:2 * heads * d] *= (1.0 + 3.0 * torch.arange(n, device="cuda").float() / max(n, 2))[None, :, None]
+    qkv = bf(qkv)
+    out = torch.full((B, n, heads * d), float("nan"), device="cuda", dtype=torch.bfloat16)
+    guard = out.clone()
+    (ops.attention_causal if causal else ops.attention)(qkv, out, B, n, heads, d)
+    torch.cuda.synchronize()
+    q, k, v = [t.reshape(B, n, heads, d).transpose(1, 2) for t in qkv.float().chunk(3, dim=-1)]
+    ref = F.scaled_dot_product_attention(q, k, v, is_causal=causal).transpose(1, 2).reshape(B, n, heads * d)
+    assert torch.isfinite(out.float()).all()
+    assert_close_bf16(out, ref, f"attention d64 n={n} causal={causal}", rel=2 ** -6, abs_=6e-3)
+    out2 = guard.clone()
+    (ops.attention_causal if causal else ops.attention)(qkv, out2, B, n, heads, d)
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2)                                # bit-reproducible
+
+
 # ---------------------------------------------------------------------------------------------- norms
 @pytest.mark.parametrize("rows,c,affine", [(1000, 64, "g"), (4096, 512, "wb"), (350, 768, "wb")])
 def test_layernorm_rows(ops, gen, rows, c, affine):
