@@ -15,6 +15,12 @@
 // two items are in their softmax at any time (slot = item & 1: own TMEM columns, own P buffer, own four softmax warps), and
 // the single MMA issuer polls both slots and issues whichever MMA group has its operands ready.
 // Roles (10 warps): warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 softmax of slot 0, warps 6-9 of slot 1.
+//
+// Packed mode (sequences of at most 64 tokens: the 50-token ViT-B/32 blocks).  A 50-row sequence fills 39 % of a 128-row
+// tile, and the kernel is bound by the per-item chain (loads -> S -> softmax -> P V -> store), not by the tensor pipe: so a
+// work item carries TWO (image, head) units, unit u in tile rows / key columns [64 u, 64 u + n) (two 64-row TMA boxes per
+// stage).  S is the full 128 x (64 + Nv) product; the softmax of a row only looks at its own unit's columns and writes zeros
+// into the other unit's part of P, so the one P V MMA group yields both outputs.  Half the items, half the bytes staged.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdlib.h>
@@ -33,6 +39,7 @@ constexpr uint32_t kAvSlotCols = 192;        // TMEM per slot: S [0,128), O_blk 
 
 struct AttnVitParams {
   int items, q_tiles, kb, n, heads, causal;
+  int packed, units;                         // packed mode: two (image, head) units per item; units = B * heads
   float scale_log2;                          // d^-0.5 * log2(e)
   __nv_bfloat16* out;
 };
@@ -95,20 +102,30 @@ attn_vit_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constan
     if (elect_one()) {
       griddep_wait();
       int idx = 0;                                     // running stage index
-      auto load = [&](int col, int rowc) {
+      // one ring stage = one 128-row tile; packed mode fills it with two 64-row boxes (rows [0, 64) and [64, 128))
+      auto load = [&](int col0, int row0, int col1, int row1) {
         const int stage = idx % kAvStages;
         mbar_wait(&empty[stage], ((idx / kAvStages) & 1) ^ 1);
         mbar_arrive_expect_tx(&full[stage], kAvSlab);
-        tma_load_2d(ring + static_cast<size_t>(stage) * kAvSlab, &mapQKV, &full[stage], col, rowc);
+        uint8_t* dst = ring + static_cast<size_t>(stage) * kAvSlab;
+        tma_load_2d(dst, &mapQKV, &full[stage], col0, row0);
+        if (p.packed) tma_load_2d(dst + kAvSlab / 2, &mapQKV, &full[stage], col1, row1);
         ++idx;
       };
       for (int li = 0; li < n_items; ++li) {
+        if (p.packed) {
+          const int u0 = 2 * (begin + li), u1 = min(u0 + 1, p.units - 1);   // odd unit count: the last item repeats its unit
+          const int b0 = u0 / p.heads, h0 = u0 - b0 * p.heads, b1 = u1 / p.heads, h1 = u1 - b1 * p.heads;
+          for (int part = 0; part < 3; ++part)          // Q, K, V
+            load((part * p.heads + h0) * 64, b0 * p.n, (part * p.heads + h1) * 64, b1 * p.n);
+          continue;
+        }
         int b, h, qt;
         decode(begin + li, b, h, qt);
-        load(h * 64, b * p.n + qt * kTileM);
+        load(h * 64, b * p.n + qt * kTileM, 0, 0);
         for (int j = 0; j < p.kb; ++j) {
-          load((p.heads + h) * 64, b * p.n + j * kTileM);
-          load((2 * p.heads + h) * 64, b * p.n + j * kTileM);
+          load((p.heads + h) * 64, b * p.n + j * kTileM, 0, 0);
+          load((2 * p.heads + h) * 64, b * p.n + j * kTileM, 0, 0);
         }
       }
     }
@@ -127,7 +144,7 @@ attn_vit_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constan
         if (li[s] >= n_items) continue;
         const int base = li[s] * per_item;             // ring index of the item's Q tile
         const int iq = base, ik = base + 1 + 2 * blk[s], iv = ik + 1;
-        const int keys = min(kTileM, p.n - blk[s] * kTileM);
+        const int keys = p.packed ? 64 + p.n : min(kTileM, p.n - blk[s] * kTileM);
         const int nv = (keys + 15) & ~15;              // MMA N of S = K extent of P V
         if (!pv_stage[s]) {
           const bool ready = mbar_try_wait(&full[iq % kAvStages], (iq / kAvStages) & 1) &&
@@ -187,46 +204,69 @@ attn_vit_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constan
     const float c = p.scale_log2;
     uint32_t cnt = 0;
     for (int li = s; li < n_items; li += 2) {
-      int b, h, qt;
-      decode(begin + li, b, h, qt);
-      const int q = qt * kTileM + row;                 // token index of this row within its image
+      int b, h, qt, q;                                 // this row's image, head, query tile and token index
+      bool unit_ok = true;
+      if (p.packed) {
+        const int u = 2 * (begin + li) + (row >> 6);   // rows [0, 64): first unit of the item, [64, 128): second
+        unit_ok = u < p.units;
+        const int uc = min(u, p.units - 1);
+        b = uc / p.heads;
+        h = uc - b * p.heads;
+        qt = 0;
+        q = row & 63;
+      } else {
+        decode(begin + li, b, h, qt);
+        q = qt * kTileM + row;
+      }
       float m_run = -INFINITY, l_run = 0.f;
       float o[64];
 #pragma unroll
       for (int i = 0; i < 64; ++i) o[i] = 0.f;
       for (int j = 0; j < p.kb; ++j, ++cnt) {
-        const int keys = min(kTileM, p.n - j * kTileM);
-        // valid keys of this row: below the sequence end and, causal, not above the diagonal
-        int lim = keys;
-        if (p.causal) lim = min(lim, q - j * kTileM + 1);
+        // valid key columns [lo, hi) of this row within the block: its own sequence (packed: its own unit's 64-column half)
+        // and, causal, nothing above the diagonal
+        int lo = 0, hi = min(kTileM, p.n - j * kTileM), keys = hi;
+        if (p.packed) {
+          lo = (row >> 6) << 6;
+          hi = lo + p.n;
+          keys = 64 + p.n;
+        }
+        if (p.causal) hi = min(hi, lo + q - j * kTileM + 1);
         const int chunks = (((keys + 15) & ~15) + 31) >> 5;          // 32-column chunks the P V MMA will read
+        // (warp-uniform) chunks that can hold valid columns for this warp's rows
+        const int ck_lo = lo >> 5, ck_hi = p.packed ? (lo + p.n + 31) >> 5 : chunks;
         mbar_wait(&s_full[s], cnt & 1);
         tc_fence_after();
         // pass 1: row maximum over the valid keys
         float mx = -INFINITY;
-        for (int ck = 0; ck < chunks; ++ck) {
+        for (int ck = ck_lo; ck < ck_hi; ++ck) {
           uint32_t r[32];
           tmem_ld32(lane_base + 32 * ck, r);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (32 * ck + i < lim) mx = fmaxf(mx, __uint_as_float(r[i]));
+            if (32 * ck + i < hi) mx = fmaxf(mx, __uint_as_float(r[i]));
         }
         const float m_new = fmaxf(m_run, mx * c);
         const float m_use = m_new == -INFINITY ? 0.f : m_new;        // a row without any valid key (unused tile rows)
         const float alpha = exp2f(m_run - m_use);                    // first block: exp2(-inf) = 0
-        // pass 2: exponentials, row sum, bf16 P tile
+        // pass 2: exponentials, row sum, bf16 P tile (zeros in the columns of the other unit)
         float l_blk = 0.f;
         for (int ck = 0; ck < chunks; ++ck) {
-          uint32_t r[32];
-          tmem_ld32(lane_base + 32 * ck, r);
-          tmem_ld_wait();
           float v[32];
+          if (ck >= ck_lo && ck < ck_hi) {
+            uint32_t r[32];
+            tmem_ld32(lane_base + 32 * ck, r);
+            tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float e = ex2_approx(fmaf(__uint_as_float(r[i]), c, -m_use));
-            v[i] = (32 * ck + i < lim) ? e : 0.f;
-            l_blk += v[i];
+            for (int i = 0; i < 32; ++i) {
+              const float e = ex2_approx(fmaf(__uint_as_float(r[i]), c, -m_use));
+              v[i] = (32 * ck + i < hi) ? e : 0.f;
+              l_blk += v[i];
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0.f;
           }
           chunk_stage_bf16_s(ps_s, row, 32 * ck, v);
         }
@@ -249,7 +289,7 @@ attn_vit_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constan
         tc_fence_before();
         mbar_arrive(&o_free[s]);
       }
-      if (q < p.n) {
+      if (q < p.n && unit_ok) {
         const float inv = 1.0f / l_run;
         __nv_bfloat16* dst = p.out + (static_cast<long long>(b) * p.n + q) * (p.heads * 64) + h * 64;
 #pragma unroll
@@ -285,7 +325,9 @@ int dac_attention_vit(const void* qkv, void* out, int B, int n, int heads, int c
   const uint64_t cols = 3ull * heads * 64;
   cuuint64_t dims[2] = {cols, static_cast<cuuint64_t>(B) * n};
   cuuint64_t strides[1] = {cols * 2};
-  cuuint32_t box[2] = {64, static_cast<cuuint32_t>(kTileM)};
+  // packed mode: two (image, head) units per 128-row tile, each loaded as its own 64-row box
+  const int packed = (n <= 64 && !getenv("DAC_ATTN_NO_PACK")) ? 1 : 0;
+  cuuint32_t box[2] = {64, static_cast<cuuint32_t>(packed ? kTileM / 2 : kTileM)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(qkv), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -294,7 +336,9 @@ int dac_attention_vit(const void* qkv, void* out, int B, int n, int heads, int c
   AttnVitParams k;
   k.q_tiles = (n + kTileM - 1) / kTileM;
   k.kb = k.q_tiles;
-  k.items = B * heads * k.q_tiles;
+  k.items = packed ? (B * heads + 1) / 2 : B * heads * k.q_tiles;
+  k.packed = packed;
+  k.units = B * heads;
   k.n = n;
   k.heads = heads;
   k.causal = causal;
