@@ -63,6 +63,35 @@ struct Attn2Params {
   long long* prof;                           // DAC_ATTN2_PROF: [20 warps][8] cycles (CTA 0)
 };
 
+// exp2 of a pair of arguments on the FMA / ALU pipes (no MUFU): round to nearest integer with the 1.5 * 2^23 trick, degree-3
+// minimax polynomial of 2^f on [-0.5, 0.5] (relative error 7.5e-5, far below the bf16 rounding of P), exponent added to the
+// bit pattern.  Arguments below -126 are clamped (the result would wrap; 2^-126 rounds to zero weight anyway).
+__device__ __forceinline__ void ex2_poly2(uint64_t x2, float& e0, float& e1) {
+  float a0, a1;
+  unpack_f32x2(x2, a0, a1);
+  x2 = pack_f32x2(fmaxf(a0, -126.f), fmaxf(a1, -126.f));
+  const uint64_t r2 = add_f32x2(x2, pack_f32x2(12582912.f, 12582912.f));
+  const uint64_t j2 = add_f32x2(r2, pack_f32x2(-12582912.f, -12582912.f));
+  const uint64_t f2 = fma_f32x2(j2, pack_f32x2(-1.f, -1.f), x2);
+  uint64_t p2 = fma_f32x2(pack_f32x2(0.0551716648f, 0.0551716648f), f2, pack_f32x2(0.2426111251f, 0.2426111251f));
+  p2 = fma_f32x2(p2, f2, pack_f32x2(0.6932609677f, 0.6932609677f));
+  p2 = fma_f32x2(p2, f2, pack_f32x2(0.9999280572f, 0.9999280572f));
+  float p0, p1, r0, r1;
+  unpack_f32x2(p2, p0, p1);
+  unpack_f32x2(r2, r0, r1);
+  e0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(r0) << 23));
+  e1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(r1) << 23));
+}
+
+// which pairs of a 32-element chunk take the polynomial: 1 = every 8th, 2 = every 4th, 3 = two adjacent of 8, 4 = every 2nd
+template <int POLY>
+__device__ __forceinline__ constexpr bool poly_pair(int pr) {
+  return POLY == 1 ? (pr & 7) == 0 : POLY == 2 ? (pr & 3) == 0 : POLY == 3 ? (pr & 7) < 2 : POLY == 4 ? (pr & 1) == 0 : false;
+}
+
+// POLY: of every 8 pairs of exponentials, this many are computed by ex2_poly2 instead of MUFU.EX2 (the kernel is bound by the
+// MUFU pipe, 16 results / clk / SM, while half the issue slots idle)
+template <int POLY>
 __global__ void __launch_bounds__(kA2Threads, 1)
 attn_tc2_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constant__ Attn2Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -325,19 +354,29 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constan
         uint64_t lsum[4] = {0ull, 0ull, 0ull, 0ull};
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          float a0, a1;
-          unpack_f32x2(fma_f32x2(pack_f32x2(s0[i], s0[i + 1]), c2, mc2), a0, a1);
-          s0[i] = ex2_approx(a0);
-          s0[i + 1] = ex2_approx(a1);
+          const uint64_t x2 = fma_f32x2(pack_f32x2(s0[i], s0[i + 1]), c2, mc2);
+          if (poly_pair<POLY>(i >> 1)) {
+            ex2_poly2(x2, s0[i], s0[i + 1]);
+          } else {
+            float a0, a1;
+            unpack_f32x2(x2, a0, a1);
+            s0[i] = ex2_approx(a0);
+            s0[i + 1] = ex2_approx(a1);
+          }
           lsum[(i >> 1) & 3] = add_f32x2(lsum[(i >> 1) & 3], pack_f32x2(s0[i], s0[i + 1]));
         }
         chunk_stage_bf16_s(pt, row, 0, s0);
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          float a0, a1;
-          unpack_f32x2(fma_f32x2(pack_f32x2(s1[i], s1[i + 1]), c2, mc2), a0, a1);
-          s1[i] = ex2_approx(a0);
-          s1[i + 1] = ex2_approx(a1);
+          const uint64_t x2 = fma_f32x2(pack_f32x2(s1[i], s1[i + 1]), c2, mc2);
+          if (poly_pair<POLY>(i >> 1)) {
+            ex2_poly2(x2, s1[i], s1[i + 1]);
+          } else {
+            float a0, a1;
+            unpack_f32x2(x2, a0, a1);
+            s1[i] = ex2_approx(a0);
+            s1[i + 1] = ex2_approx(a1);
+          }
           lsum[(i >> 1) & 3] = add_f32x2(lsum[(i >> 1) & 3], pack_f32x2(s1[i], s1[i + 1]));
         }
         chunk_stage_bf16_s(pt, row, 32, s1);
@@ -456,7 +495,8 @@ int dac_attention_tc2(const void* qkv, void* out, int B, int n, int heads, cudaS
   const int smem = (1 + kA2Stages + 8) * (int)kA2Slab + 1024 + 512;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(attn_tc2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return set_error(-12, "dac_attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
@@ -465,6 +505,10 @@ int dac_attention_tc2(const void* qkv, void* out, int B, int n, int heads, cudaS
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int grid = k.items < sms ? k.items : sms;
   if (getenv("DAC_ATTN_GRID")) grid = atoi(getenv("DAC_ATTN_GRID")) < grid ? atoi(getenv("DAC_ATTN_GRID")) : grid;   // tests: many items per CTA
-  launch_k(attn_tc2_kernel, dim3(grid), dim3(kA2Threads), smem, stream, map, k);
+  // a quarter of the exponentials on the FMA / ALU pipes: 116 -> 110 us at 16 x 16 heads x 1024 tokens, 732 -> 687 us at 4096
+  // (12.5 % gives the same, 50 % is slower: the kernel then runs out of issue slots); DAC_ATTN_POLY=0 selects the all-MUFU form
+  const bool poly = !getenv("DAC_ATTN_POLY") || atoi(getenv("DAC_ATTN_POLY")) != 0;
+  if (poly) launch_k(attn_tc2_kernel<3>, dim3(grid), dim3(kA2Threads), smem, stream, map, k);
+  else launch_k(attn_tc2_kernel<0>, dim3(grid), dim3(kA2Threads), smem, stream, map, k);
   return check_launch("attn_tc2_kernel");
 }

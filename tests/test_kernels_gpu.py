@@ -714,6 +714,30 @@ def test_flash_attention_d32_growing_scores(ops, gen, B, n, heads):
     assert_close_bf16(out, ref, f"flash d32 growing scores n={n}", rel=2 ** -6, abs_=6e-3)
 
 
+def test_flash_attention_d32_polynomial_exp(ops, gen, monkeypatch):
+    """A quarter of the exponentials of attn_tc2_kernel run as a polynomial on the FMA pipe (ex2_poly2, attention_tc2.cu).
+    Scores far below the row max (here down to -600 in log2 units: the argument clamp) must give weight zero, not a wrapped
+    exponent; the all-MUFU build (DAC_ATTN_POLY=0) is the second witness next to the fp32 softmax of attention.py:178-192."""
+    B, n, heads, d = 2, 1024, 4, 32
+    qkv = rnd(gen, B, n, 3 * heads * d)
+    kcols = slice(heads * d, 2 * heads * d)
+    qkv[:, ::7, kcols] *= 24.0                      # a few dominant keys: every other score sits far below the max
+    qkv = bf(qkv)
+    outs = []
+    for poly in ("1", "0"):
+        monkeypatch.setenv("DAC_ATTN_POLY", poly)
+        out = torch.zeros(B, n, heads * d, device="cuda", dtype=torch.bfloat16)
+        ops.attention(qkv, out, B, n, heads, d)
+        torch.cuda.synchronize()
+        outs.append(out)
+    q, k, v = [t.reshape(B, n, heads, d).transpose(1, 2) for t in qkv.float().chunk(3, dim=-1)]
+    ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, n, heads * d)
+    for out, tag in zip(outs, ("polynomial", "MUFU")):
+        assert torch.isfinite(out.float()).all()
+        assert_close_bf16(out, ref, f"flash d32 {tag}", rel=2 ** -6, abs_=6e-3)
+    assert (outs[0].float() - outs[1].float()).abs().max().item() <= 2 ** -6 * ref.abs().max().item()
+
+
 def test_small_attention_d64(ops, gen):
     B, n, heads, d = 3, 50, 12, 64
     qkv = bf(rnd(gen, B, n, 3 * heads * d))
