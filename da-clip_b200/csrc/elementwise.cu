@@ -413,6 +413,105 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const __nv_bfloat1
   }
 }
 
+// PreNorm (channel LayerNorm, gain only: module_util.py:77-97) fused with GroupNorm pass 1 for the SpatialTransformer
+// levels (attention.py:251 normalises the PreNorm output): CTA (slab, image), one warp per pixel row.  The row is
+// normalised, rounded to bf16 and stored (it is also the residual of proj_out), and the SAME rounded values feed the
+// per-slab group sums - one launch and one read of the normalised tensor less than layernorm_rows + groupnorm_stats.
+// Lane l holds the 8-channel vectors l, l + 32, ...; partial sums meet in shared memory, one thread per group adds them
+// in a fixed order (bit-reproducible).
+template <int VPL>
+__global__ void __launch_bounds__(256) prenorm_gnstats_kernel(const __nv_bfloat16* __restrict__ in,
+                                                              __nv_bfloat16* __restrict__ out, int hw, int c, int groups,
+                                                              int slab, const float* __restrict__ g, float ln_eps,
+                                                              float* __restrict__ stats) {
+  __shared__ float2 part[8][32 * VPL];
+  griddep_wait();
+  griddep_launch();
+  const int b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nvec = c >> 3;
+  const int p0 = blockIdx.x * slab, p1 = min(hw, p0 + slab);
+  const float inv_c = 1.0f / c;
+  float gs[VPL], gss[VPL];
+  float gain[VPL][8];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    gs[i] = 0.f;
+    gss[i] = 0.f;
+    const int vi = lane + 32 * i;
+    const float4 w0 = vi < nvec ? __ldg(reinterpret_cast<const float4*>(g) + vi * 2) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 w1 = vi < nvec ? __ldg(reinterpret_cast<const float4*>(g) + vi * 2 + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+    gain[i][0] = w0.x; gain[i][1] = w0.y; gain[i][2] = w0.z; gain[i][3] = w0.w;
+    gain[i][4] = w1.x; gain[i][5] = w1.y; gain[i][6] = w1.z; gain[i][7] = w1.w;
+  }
+  for (int p = p0 + warp; p < p1; p += 8) {
+    const int64_t row = static_cast<int64_t>(b) * hw + p;
+    float v[VPL][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int vi = lane + 32 * i;
+      uint4 u = make_uint4(0, 0, 0, 0);
+      if (vi < nvec) u = __ldg(reinterpret_cast<const uint4*>(in + row * c) + vi);
+      float2 t;
+      t = unpack_bf16(u.x); v[i][0] = t.x; v[i][1] = t.y;
+      t = unpack_bf16(u.y); v[i][2] = t.x; v[i][3] = t.y;
+      t = unpack_bf16(u.z); v[i][4] = t.x; v[i][5] = t.y;
+      t = unpack_bf16(u.w); v[i][6] = t.x; v[i][7] = t.y;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += v[i][j];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum * inv_c;
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      if (lane + 32 * i < nvec) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float d = v[i][j] - mean;
+          ss = fmaf(d, d, ss);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float rstd = rsqrtf(ss * inv_c + ln_eps);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int vi = lane + 32 * i;
+      if (vi < nvec) {
+        float y[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y[j] = (v[i][j] - mean) * rstd * gain[i][j];
+        uint4 o;
+        o.x = pack_bf16(y[0], y[1]); o.y = pack_bf16(y[2], y[3]);
+        o.z = pack_bf16(y[4], y[5]); o.w = pack_bf16(y[6], y[7]);
+        reinterpret_cast<uint4*>(out + row * c)[vi] = o;
+        // statistics of what GroupNorm will read: the bf16-rounded values
+        const float2 a = unpack_bf16(o.x), bb = unpack_bf16(o.y), cc = unpack_bf16(o.z), d = unpack_bf16(o.w);
+        gs[i] += (a.x + a.y) + (bb.x + bb.y) + (cc.x + cc.y) + (d.x + d.y);
+        gss[i] += a.x * a.x + a.y * a.y + bb.x * bb.x + bb.y * bb.y + cc.x * cc.x + cc.y * cc.y + d.x * d.x + d.y * d.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) part[warp][lane + 32 * i] = make_float2(gs[i], gss[i]);
+  __syncthreads();
+  if (threadIdx.x < groups) {
+    const int gi = threadIdx.x, vpg = (c / groups) >> 3;
+    float s = 0.f, ss = 0.f;
+    for (int w = 0; w < 8; ++w)
+      for (int k = 0; k < vpg; ++k) {
+        const float2 t = part[w][gi * vpg + k];
+        s += t.x;
+        ss += t.y;
+      }
+    reinterpret_cast<float2*>(stats)[(static_cast<int64_t>(b) * gridDim.x + blockIdx.x) * groups + gi] = make_float2(s, ss);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ conditioning MLPs
 // y[r] = W[r,:] . x + b[r] for r in [0, rows): ONE THREAD per output row (rows <= 2 * blockDim), 16-byte weight
 // loads with four independent accumulators; x is broadcast from shared memory.  (A warp-per-row version with a
@@ -681,6 +780,36 @@ extern "C" int dac_groupnorm_nhwc(const void* in, void* out, int32_t B, int32_t 
   if (chunks > cap) chunks = cap;
   launch_k(groupnorm_apply_kernel, dim3(static_cast<unsigned>(chunks < 1 ? 1 : chunks), B), dim3(256), 0, s,
            static_cast<const __nv_bfloat16*>(in), static_cast<__nv_bfloat16*>(out), hw, c, groups, kGnSlabs, w, b, eps,
+           static_cast<const float*>(stats));
+  return check_launch("groupnorm_apply_kernel");
+}
+
+extern "C" int dac_prenorm_groupnorm_nhwc(const void* in, void* normed, void* out, int32_t B, int32_t hw, int32_t c,
+                                          int32_t groups, const float* pre_g, float pre_eps, const float* w, const float* b,
+                                          float eps, float* stats, dac_stream_t stream) {
+  if (!in || !normed || !out || !pre_g || !w || !b || !stats) return set_error(-1, "dac_prenorm_groupnorm_nhwc: null argument");
+  if (c % groups || (c / groups) % 8 || c > 1024 || (c & 7))
+    return set_error(-2, "dac_prenorm_groupnorm_nhwc: need 8 | c/groups, c <= 1024");
+  if ((reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(pre_g)) & 15)
+    return set_error(-2, "dac_prenorm_groupnorm_nhwc: pre_g, w and b must be 16-byte aligned");
+  if (groups > 256 || B > 65535) return set_error(-2, "dac_prenorm_groupnorm_nhwc: groups <= 256, B <= 65535");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int slab = static_cast<int>(ceil_div(hw, kGnSlabs));
+  const __nv_bfloat16* ip = static_cast<const __nv_bfloat16*>(in);
+  __nv_bfloat16* np = static_cast<__nv_bfloat16*>(normed);
+  const int vpl = (c / 8 + 31) / 32;
+  const dim3 g1(kGnSlabs, B), t(256);
+  if (vpl == 1) launch_k(prenorm_gnstats_kernel<1>, g1, t, 0, s, ip, np, hw, c, groups, slab, pre_g, pre_eps, stats);
+  else if (vpl == 2) launch_k(prenorm_gnstats_kernel<2>, g1, t, 0, s, ip, np, hw, c, groups, slab, pre_g, pre_eps, stats);
+  else launch_k(prenorm_gnstats_kernel<4>, g1, t, 0, s, ip, np, hw, c, groups, slab, pre_g, pre_eps, stats);
+  int rc = check_launch("prenorm_gnstats_kernel");
+  if (rc) return rc;
+  const int64_t per_image = static_cast<int64_t>(hw) * (c / 8);
+  int64_t chunks = ceil_div(per_image, 256 * 4);
+  const int64_t cap = ceil_div(148 * 16, B);
+  if (chunks > cap) chunks = cap;
+  launch_k(groupnorm_apply_kernel, dim3(static_cast<unsigned>(chunks < 1 ? 1 : chunks), B), dim3(256), 0, s,
+           static_cast<const __nv_bfloat16*>(np), static_cast<__nv_bfloat16*>(out), hw, c, groups, kGnSlabs, w, b, eps,
            static_cast<const float*>(stats));
   return check_launch("groupnorm_apply_kernel");
 }

@@ -14,6 +14,7 @@ Execution: every GEMM (patch embedding, in_proj, out_proj, c_fc, c_proj, zero-li
 tokens as pixels (M = 50*B); the residual stream stays fp32 (fp32 residual in the GEMM epilogue) so that the
 degradation-type argmax is stable; LayerNorm / 50-token attention / pooling are small fused CUDA kernels.
 """
+import os
 from collections import OrderedDict
 
 import torch
@@ -290,11 +291,25 @@ class _PackedDaCLIP:
         self.clip = _PackedTower(m.visual, m.visual.transformer.resblocks)
         ct = m.visual_control.transformer
         self.control = _PackedTower(m.visual_control, ct.transformer.resblocks, ct.zero_modules)
+        # CLIP layer i adds the hidden of control layer j = L-1-i through that layer's zero-linear (transformer.py:355-369:
+        # control.pop()).  x + W_proj hid + Z_j xc_j is ONE GEMM over the virtual concat [hid | xc_j] against [W_proj | Z_j]:
+        # no zero-linear launch, no hidden tensor written and read back, and the sum stays in fp32 (TMEM) until the stream
+        Lb = len(self.clip.blocks)
+        dev = m.visual.proj.device
+        for i, blk in enumerate(self.clip.blocks):
+            r, z = m.visual.transformer.resblocks[i], ct.zero_modules[Lb - 1 - i]
+            wcat = torch.cat([r.mlp.c_proj.weight.detach().to(dev, torch.float32),
+                              z.weight.detach().to(dev, torch.float32)], dim=1).contiguous()
+            blk["proj_ctl"] = ops.pack_linear(wcat)
+            blk["proj_ctl_b"] = (r.mlp.c_proj.bias.detach().to(dev, torch.float32)
+                                 + z.bias.detach().to(dev, torch.float32)).contiguous()
 
 
 class _EncodeEngine:
     """Launch plan of encode_image for a fixed batch, captured in one CUDA graph: control=True = the control tower
     followed by the CLIP tower that consumes its hidden states; control=False = the CLIP tower alone."""
+
+    FUSE_ZERO = os.environ.get("DAC_FUSE_ZERO", "1") != "0"   # zero-linears inside the CLIP tower's c_proj GEMMs
 
     def __init__(self, pk: _PackedDaCLIP, vit, B, dev, control=True):
         self.B, self.dev = B, dev
@@ -334,9 +349,16 @@ class _EncodeEngine:
                     # control tower: x <- x + mlp; also keep a bf16 copy as the zero-linear's GEMM operand
                     xb = torch.zeros(1, 1, M, w, **bf)
                     self.conv(hid, 4 * w, blk["proj"], xb, M, bias=blk["proj_b"], res_f32=x, out_f32=x)
-                    h = torch.zeros(1, 1, M, w, **bf)
-                    self.conv(xb, w, blk["zero"], h, M, bias=blk["zero_b"])
-                    hiddens.append(h)
+                    if self.FUSE_ZERO:
+                        hiddens.append(xb)              # the CLIP tower applies the zero-linear inside its c_proj GEMM
+                    else:
+                        h = torch.zeros(1, 1, M, w, **bf)
+                        self.conv(xb, w, blk["zero"], h, M, bias=blk["zero_b"])
+                        hiddens.append(h)
+                elif self.FUSE_ZERO:
+                    # CLIP tower: x <- x + [W_proj | Z_j] [hid | xc_j] + (b_proj + b_zero_j), j = L-1-i (control.pop())
+                    self.conv(hid, 4 * w, blk["proj_ctl"], None, M, src1=control_in[len(tp.blocks) - 1 - i], c1=w,
+                              bias=blk["proj_ctl_b"], res_f32=x, out_f32=x)
                 else:
                     # CLIP tower: x <- x + mlp + control.pop()  (hidden of control layer L-1-i)
                     self.conv(hid, 4 * w, blk["proj"], None, M, bias=blk["proj_b"], res_f32=x, out_f32=x,

@@ -81,6 +81,7 @@ SYMBOLS = {
     "dac_layernorm_rows": (C.c_int, [_p, _i32, _p, _i32, _i64, _i32, _p, _p, _f, _p]),
     "dac_layernorm_rows_f32": (C.c_int, [_p, _i32, _p, _i32, _i64, _i32, _p, _p, _f, _p]),
     "dac_groupnorm_nhwc": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _p, _p, _f, _p, _p]),
+    "dac_prenorm_groupnorm_nhwc": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _i32, _p, _f, _p, _p, _f, _p, _p]),
     "dac_prompt_embed": (C.c_int, [C.POINTER(EmbedWeights), _p, _i32, _p, _p]),
     "dac_time_film": (C.c_int, [C.POINTER(EmbedWeights), _p, _p, _i32, _p, _p, _p]),
     "dac_two_linear": (C.c_int, [_p, _i32, _i32, _p, _i32, _p, _p, _i32, _p, _p]),

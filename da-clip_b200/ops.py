@@ -514,6 +514,12 @@ def groupnorm_nhwc(x, out, B, hw, c, w, b, stats, groups=32, eps=1e-6):
                                         L.ptr(stats), L.stream_ptr()))
 
 
+def prenorm_groupnorm_nhwc(x, normed, out, B, hw, c, pre_g, w, b, stats, groups=32, pre_eps=1e-5, eps=1e-6):
+    """normed = LayerNorm_c(x) * pre_g, out = GroupNorm(normed): the PreNorm + Normalize pair in front of a SpatialTransformer."""
+    L.check(L.load().dac_prenorm_groupnorm_nhwc(L.ptr(x), L.ptr(normed), L.ptr(out), B, hw, c, groups, L.ptr(pre_g),
+                                                float(pre_eps), L.ptr(w), L.ptr(b), float(eps), L.ptr(stats), L.stream_ptr()))
+
+
 def prompt_embed(ew, text_ctx, B, prompt_emb):
     L.check(L.load().dac_prompt_embed(C.byref(ew), L.ptr(text_ctx), B, L.ptr(prompt_emb), L.stream_ptr()))
 

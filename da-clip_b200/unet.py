@@ -503,6 +503,7 @@ class UNetEngine:
     FUSE_KV_TC = True      # LinearAttention: the k|v context reduction as a second tcgen05 GEMM (TMEM-resident context)
     FUSE_QOUT = True       # LinearAttention: to_q + softmax + to_out + LayerNorm + residual as one chained-GEMM kernel
     FUSE_KVCTX = True      # LinearAttention: reduce k | v into the context inside the to_kv GEMM epilogue
+    FUSE_PRENORM_GN = True     # SpatialTransformer levels: PreNorm + GroupNorm statistics in one kernel
     PRENORM_IN_KERNEL = True   # 64-channel LinearAttention: PreNorm on the tile in shared memory inside the k|v / q-out kernels
 
     # A/B switches from the environment, e.g. DAC_SWITCHES="FOLD_PRENORM=1,PDL=0" (tools/ab_engine.py, bench.py runs)
@@ -609,11 +610,16 @@ class UNetEngine:
                       ln_g=a["g_out"], res=x, per_image_w=True, weight_override=weff)
             return out
         xn = self.buf(B, h, w, C)
-        self.add(prefix + "prenorm", lambda: ops.layernorm_rows(x, xn, B * hw, C, a["pre_g"], None, 1e-5))
         heads = a["heads"]
         gn = self.buf(B, h, w, C)
         stats = self.buf(B * 16 * 64, dtype=torch.float32)       # [B][16 slabs][32 groups][2]
-        self.add(prefix + "groupnorm", lambda: ops.groupnorm_nhwc(xn, gn, B, hw, C, a["gn_w"], a["gn_b"], stats))
+        if self.FUSE_PRENORM_GN:
+            # PreNorm and the GroupNorm statistics in one pass over x (the normalised rows are kept: proj_out's residual)
+            self.add(prefix + "prenorm_gn", lambda: ops.prenorm_groupnorm_nhwc(x, xn, gn, B, hw, C, a["pre_g"], a["gn_w"],
+                                                                                a["gn_b"], stats))
+        else:
+            self.add(prefix + "prenorm", lambda: ops.layernorm_rows(x, xn, B * hw, C, a["pre_g"], None, 1e-5))
+            self.add(prefix + "groupnorm", lambda: ops.groupnorm_nhwc(xn, gn, B, hw, C, a["gn_w"], a["gn_b"], stats))
         y0 = self.buf(B, h, w, C)
         self.conv(prefix + "proj_in", gn, C, a["proj_in"], y0, h, w, bias=a["proj_in_b"])
         n1 = self.buf(B, h, w, C)

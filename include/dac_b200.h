@@ -187,6 +187,12 @@ int dac_layernorm_rows_f32(const float* in, int32_t ld_in, void* out, int32_t ld
                            const float* w, const float* b, float eps, dac_stream_t stream);
 int dac_groupnorm_nhwc(const void* in, void* out, int32_t B, int32_t hw, int32_t c, int32_t groups,
                        const float* w, const float* b, float eps, float* stats, dac_stream_t stream);
+/* PreNorm + GroupNorm of a SpatialTransformer level in two launches: normed = LayerNorm_c(in) * pre_g (MU:77-97; kept: it is
+ * the residual of proj_out, ATT:261) and out = GroupNorm(normed) (ATT:76-77,251).  The first kernel normalises the rows AND
+ * accumulates the per-slab group sums of the bf16 values it stores; stats as for dac_groupnorm_nhwc. */
+int dac_prenorm_groupnorm_nhwc(const void* in, void* normed, void* out, int32_t B, int32_t hw, int32_t c, int32_t groups,
+                               const float* pre_g, float pre_eps, const float* w, const float* b, float eps, float* stats,
+                               dac_stream_t stream);
 
 /* ------------------------------------------------------------------ conditioning vectors
  * time_mlp + text_mlp/prompt/prompt_mlp (ARCH:51-62,132-137) -> silu(t_emb) [B,256] fp32, then every ResBlock

@@ -818,6 +818,31 @@ def test_groupnorm(ops, gen, B, hw, c):
     assert_close_bf16(out, ref, "groupnorm")
 
 
+@pytest.mark.parametrize("B,hw,c", [(2, 1024, 256), (3, 1024, 512), (1, 100, 512), (2, 64, 768)])
+def test_prenorm_groupnorm_fused(ops, gen, B, hw, c):
+    """dac_prenorm_groupnorm_nhwc: channel LayerNorm with gain (module_util.py:77-97) and GroupNorm(32, eps 1e-6) of its
+    output (attention.py:76-77,251) - the normalised rows and the GroupNorm output against fp32 torch, and the fused
+    statistics against the two-kernel path."""
+    x = bf(rnd(gen, B, hw, c) * (1 + torch.arange(c, device="cuda") % 5)[None, None, :] + 0.7)
+    g = 1 + 0.2 * rnd(gen, c)
+    w, b = 1 + 0.1 * rnd(gen, c), rnd(gen, c)
+    xn, out = torch.zeros_like(x), torch.zeros_like(x)
+    stats = torch.full((B * 16 * 64,), float("nan"), device="cuda")
+    ops.prenorm_groupnorm_nhwc(x, xn, out, B, hw, c, g, w, b, stats)
+    torch.cuda.synchronize()
+    xf = x.float()
+    ln = (xf - xf.mean(-1, keepdim=True)) * torch.rsqrt(xf.var(-1, unbiased=False, keepdim=True) + 1e-5) * g
+    assert_close_bf16(xn, ln, "fused prenorm")
+    ref = F.group_norm(xn.float().transpose(1, 2), 32, w, b, 1e-6).transpose(1, 2)
+    assert_close_bf16(out, ref, "fused prenorm -> groupnorm")
+    xn2, out2 = torch.zeros_like(x), torch.zeros_like(x)
+    ops.layernorm_rows(x, xn2, B * hw, c, g, None, 1e-5)
+    ops.groupnorm_nhwc(xn2, out2, B, hw, c, w, b, stats)
+    torch.cuda.synchronize()
+    assert torch.equal(xn, xn2)
+    assert (out.float() - out2.float()).abs().max().item() <= 2 ** -7 * ref.abs().max().item()
+
+
 # ---------------------------------------------------------------------------------------------- SDE updates
 @pytest.mark.parametrize("mode", ["sde", "posterior", "ode"])
 def test_sde_step_bit_exact(cuda, mode):

@@ -22,17 +22,18 @@ for rep in range(2):
 ts = [ev[i].elapsed_time(ev[i + 1]) * 1e3 for i in range(len(eng.steps))]
 # the steps of one block repeat: patchify | per tower: conv1, embed, 12 x (ln, qkv, attn, out, ln, fc, proj[, zero]), pool
 print("steps", len(ts), "total us", sum(ts))
-per = 8  # control tower block = 8 steps
-names = ["ln1", "qkv", "attn", "out", "ln2", "fc", "proj", "zero"]
+fused = os.environ.get("DAC_FUSE_ZERO", "1") != "0"   # zero-linears inside the CLIP tower's c_proj GEMMs: no "zero" step
+per = 7 if fused else 8
+names = ["ln1", "qkv", "attn", "out", "ln2", "fc", "proj", "zero"][:per]
 agg = collections.defaultdict(float)
 base = 3
 for l in range(12):
     for j, n in enumerate(names):
-        agg["ctl." + n] += ts[base + l * 8 + j]
-base2 = base + 12 * 8 + 1 + 2
+        agg["ctl." + n] += ts[base + l * per + j]
+base2 = base + 12 * per + 1 + 2
 for l in range(12):
     for j, n in enumerate(names[:7]):
         agg["clip." + n] += ts[base2 + l * 7 + j]
 for k, v in agg.items():
     print(f"{k:10s} {v:9.1f} us  ({v/12:7.1f} per layer)")
-print("first steps", [round(t, 1) for t in ts[:4]], "pool", round(ts[base + 96], 1))
+print("first steps", [round(t, 1) for t in ts[:4]], "pool", round(ts[base + 12 * per], 1))
