@@ -192,7 +192,8 @@ template <int LPR, int VPL>
 __global__ void __launch_bounds__(256) layernorm_rows_kernel(const __nv_bfloat16* __restrict__ in, int ld_in,
                                                              __nv_bfloat16* __restrict__ out, int ld_out, int64_t rows,
                                                              int c, const float* __restrict__ w,
-                                                             const float* __restrict__ b, float eps) {
+                                                             const float* __restrict__ b, float eps,
+                                                             const __nv_bfloat16* __restrict__ res, int ld_res) {
   griddep_wait();       // programmatic dependent launch (common.h): nothing to do before the producer is done
   griddep_launch();
   const int lane = threadIdx.x & 31;
@@ -253,6 +254,14 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const __nv_bfloat16
           const float4 b0 = __ldg(reinterpret_cast<const float4*>(b) + vi * 2), b1 = __ldg(reinterpret_cast<const float4*>(b) + vi * 2 + 1);
           y[0] += b0.x; y[1] += b0.y; y[2] += b0.z; y[3] += b0.w;
           y[4] += b1.x; y[5] += b1.y; y[6] += b1.z; y[7] += b1.w;
+        }
+        if (res) {    // + residual row (the Residual wrapper around a wide LinearAttention, module_util.py:27-33)
+          const uint4 r = __ldg(reinterpret_cast<const uint4*>(res + row * ld_res) + vi);
+          float2 t;
+          t = unpack_bf16(r.x); y[0] += t.x; y[1] += t.y;
+          t = unpack_bf16(r.y); y[2] += t.x; y[3] += t.y;
+          t = unpack_bf16(r.z); y[4] += t.x; y[5] += t.y;
+          t = unpack_bf16(r.w); y[6] += t.x; y[7] += t.y;
         }
         uint4 o;
         o.x = pack_bf16(y[0], y[1]); o.y = pack_bf16(y[2], y[3]);
@@ -721,8 +730,16 @@ extern "C" int dac_unet_stem_input(const float* xt, const float* cond, void* out
 
 extern "C" int dac_layernorm_rows(const void* in, int32_t ld_in, void* out, int32_t ld_out, int64_t rows, int32_t c,
                                   const float* w, const float* b, float eps, dac_stream_t stream) {
+  return dac_layernorm_rows_res(in, ld_in, nullptr, 0, out, ld_out, rows, c, w, b, eps, stream);
+}
+
+extern "C" int dac_layernorm_rows_res(const void* in, int32_t ld_in, const void* res, int32_t ld_res, void* out,
+                                      int32_t ld_out, int64_t rows, int32_t c, const float* w, const float* b, float eps,
+                                      dac_stream_t stream) {
   if (!in || !out) return set_error(-1, "dac_layernorm_rows: null argument");
-  if ((c & 7) || (ld_in & 7) || (ld_out & 7)) return set_error(-2, "dac_layernorm_rows: c and pitches must be multiples of 8");
+  if ((c & 7) || (ld_in & 7) || (ld_out & 7) || (ld_res & 7))
+    return set_error(-2, "dac_layernorm_rows: c and pitches must be multiples of 8");
+  const __nv_bfloat16* rp = static_cast<const __nv_bfloat16*>(res);
   if (rows <= 0) return 0;
   if (c > 1024) return set_error(-2, "dac_layernorm_rows: c must be <= 1024");
   if ((reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(b)) & 15)
@@ -738,11 +755,11 @@ extern "C" int dac_layernorm_rows(const void* in, int32_t ld_in, void* out, int3
   const int grid = static_cast<int>(blocks);
   const dim3 g(grid), t(256);
   const long long rows_ll = rows;
-  if (lpr == 8) launch_k(layernorm_rows_kernel<8, 1>, g, t, 0, st, ip, ld_in, op, ld_out, rows_ll, c, w, b, eps);
-  else if (lpr == 16) launch_k(layernorm_rows_kernel<16, 1>, g, t, 0, st, ip, ld_in, op, ld_out, rows_ll, c, w, b, eps);
-  else if (nvec <= 32) launch_k(layernorm_rows_kernel<32, 1>, g, t, 0, st, ip, ld_in, op, ld_out, rows_ll, c, w, b, eps);
-  else if (nvec <= 64) launch_k(layernorm_rows_kernel<32, 2>, g, t, 0, st, ip, ld_in, op, ld_out, rows_ll, c, w, b, eps);
-  else launch_k(layernorm_rows_kernel<32, 4>, g, t, 0, st, ip, ld_in, op, ld_out, rows_ll, c, w, b, eps);
+  if (lpr == 8) launch_k(layernorm_rows_kernel<8, 1>, g, t, 0, st, ip, ld_in, op, ld_out, rows_ll, c, w, b, eps, rp, ld_res);
+  else if (lpr == 16) launch_k(layernorm_rows_kernel<16, 1>, g, t, 0, st, ip, ld_in, op, ld_out, rows_ll, c, w, b, eps, rp, ld_res);
+  else if (nvec <= 32) launch_k(layernorm_rows_kernel<32, 1>, g, t, 0, st, ip, ld_in, op, ld_out, rows_ll, c, w, b, eps, rp, ld_res);
+  else if (nvec <= 64) launch_k(layernorm_rows_kernel<32, 2>, g, t, 0, st, ip, ld_in, op, ld_out, rows_ll, c, w, b, eps, rp, ld_res);
+  else launch_k(layernorm_rows_kernel<32, 4>, g, t, 0, st, ip, ld_in, op, ld_out, rows_ll, c, w, b, eps, rp, ld_res);
   return check_launch("layernorm_rows_kernel");
 }
 

@@ -283,7 +283,7 @@ extern "C" int dac_linattn_fold(const float* partial, int32_t B, int32_t hw, int
                                 int32_t C, int32_t c_pad, void* weff, dac_stream_t stream) {
   if (!partial || !w_out || !weff) return set_error(-1, "dac_linattn_fold: null argument");
   if (nchunks < 1 || nchunks > 2048) return set_error(-2, "dac_linattn_fold: nchunks must be in [1,2048]");
-  if (C <= 0 || C > 256) return set_error(-2, "dac_linattn_fold: C must be in [1,256]");
+  if (C <= 0 || C > 1024) return set_error(-2, "dac_linattn_fold: C must be in [1,1024]");
   const size_t smem = sizeof(float) * (static_cast<size_t>(C) * 33 + static_cast<size_t>(nchunks) * kFoldRows +
                                        2 * kFoldRows * 32 + kFoldRows * 33);
   if (smem > 48 * 1024) {

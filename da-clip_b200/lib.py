@@ -79,6 +79,7 @@ SYMBOLS = {
     "dac_conv_destroy": (None, [_p]),
     "dac_conv_info": (C.c_int, [_p] + [C.POINTER(_i32)] * 4),
     "dac_layernorm_rows": (C.c_int, [_p, _i32, _p, _i32, _i64, _i32, _p, _p, _f, _p]),
+    "dac_layernorm_rows_res": (C.c_int, [_p, _i32, _p, _i32, _p, _i32, _i64, _i32, _p, _p, _f, _p]),
     "dac_layernorm_rows_f32": (C.c_int, [_p, _i32, _p, _i32, _i64, _i32, _p, _p, _f, _p]),
     "dac_groupnorm_nhwc": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _p, _p, _f, _p, _p]),
     "dac_prenorm_groupnorm_nhwc": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _i32, _p, _f, _p, _p, _f, _p, _p]),

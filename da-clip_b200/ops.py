@@ -504,6 +504,12 @@ def layernorm_rows(x, out, rows, c, w=None, b=None, eps=1e-5):
                                         float(eps), L.stream_ptr()))
 
 
+def layernorm_rows_res(x, res, out, rows, c, w=None, b=None, eps=1e-5):
+    """out = LayerNorm(x) * w + b + res  (bf16 rows; res: bf16 rows of the same width)."""
+    L.check(L.load().dac_layernorm_rows_res(L.ptr(x), x.shape[-1], L.ptr(res), res.shape[-1], L.ptr(out), out.shape[-1], rows,
+                                            c, L.ptr(w), L.ptr(b), float(eps), L.stream_ptr()))
+
+
 def layernorm_rows_f32(x, out, rows, c, w=None, b=None, eps=1e-5):
     L.check(L.load().dac_layernorm_rows_f32(L.ptr(x), x.shape[-1], L.ptr(out), out.shape[-1], rows, c, L.ptr(w),
                                             L.ptr(b), float(eps), L.stream_ptr()))

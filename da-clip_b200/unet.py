@@ -334,8 +334,8 @@ class PackedUNet:
         a = dict(transformer=transformer, dim=dim, pre_g=f32(p + "fn.norm.g").reshape(-1).contiguous())
         q = p + "fn.fn."
         if not transformer:
-            if dim > 256:
-                raise NotImplementedError("LinearAttention with more than 256 channels (fused LN epilogue limit)")
+            if dim > 1024:
+                raise NotImplementedError("LinearAttention with more than 1024 channels")
             wq = f32(q + "to_qkv.weight").reshape(384, dim) * a["pre_g"][None, :]      # W' = W diag(g)
             # fused k|v -> context path: exp(k - c_d) with the data-independent bound c_d = ||W'_k[d]|| sqrt(C) >= |k_d|
             # (the gain-free LayerNorm output has norm <= sqrt(C)); safe in fp32 while c_d <= 40 (range [-80, 0])
@@ -522,7 +522,23 @@ class UNetEngine:
         """True if the attention layer `prefix` consumes per-pixel LayerNorm statistics from its producer."""
         if C is not None and self.prenorm_in_kernel(prefix, C, hw):
             return False
+        if self.pk.attn[prefix]["dim"] > 256:      # the producer's statistics epilogue needs the whole row in one N tile
+            return False
         return (self.FOLD_PRENORM or hw <= self.FOLD_PRENORM_MAX_HW) and not self.pk.attn[prefix]["transformer"]
+
+    def to_out_ln(self, prefix, a, q, weff, x, out, h, w):
+        """LinearAttention tail: to_out 1x1 (with the per-image folded weight) + bias -> channel LayerNorm -> + x
+        (module_util.py:168,185 and the Residual wrapper :27-33).  Up to 256 channels the LayerNorm and the residual live in
+        the GEMM epilogue (the row sits in one accumulator tile); wider rows (the 512-channel instances of a model built
+        with use_image_context=False) take a plain epilogue and one LayerNorm + residual pass."""
+        C = a["dim"]
+        if C <= 256:
+            self.conv(prefix + "to_out", q, 128, a["out"], out, h, w, epi=L.EPI_LN, bias=a["b_out"],
+                      ln_g=a["g_out"], res=x, per_image_w=True, weight_override=weff)
+            return
+        y = self.buf(self.B, h, w, C)
+        self.conv(prefix + "to_out", q, 128, a["out"], y, h, w, bias=a["b_out"], per_image_w=True, weight_override=weff)
+        self.add(prefix + "out_norm", lambda: ops.layernorm_rows_res(y, x, out, self.B * h * w, C, a["g_out"], None, 1e-5))
 
     def attn_layer(self, prefix, x, C, h, w, stats=None):
         a = self.pk.attn[prefix]
@@ -589,8 +605,7 @@ class UNetEngine:
                 self.conv(prefix + "to_q", xn, C, a["q"], q, h, w, epi=L.EPI_QKV, block_n=128, ln_stats=stats,
                           ln_colsum=a["q_colsum"] if fold else None)
                 self.add(prefix + "fold", lambda: ops.linattn_fold(ctx, B, hw, nslots, a["w_out"], C, c_pad, weff))
-                self.conv(prefix + "to_out", q, 128, a["out"], out, h, w, epi=L.EPI_LN, bias=a["b_out"],
-                          ln_g=a["g_out"], res=x, per_image_w=True, weight_override=weff)
+                self.to_out_ln(prefix, a, q, weff, x, out, h, w)
                 return out
             kv = self.buf(B, 256, h, w)                 # k | v, planar: pixel-contiguous rows for the context pass
             if stats is not None:
@@ -606,8 +621,7 @@ class UNetEngine:
             self.add(prefix + "context", lambda: ops.linattn_context(kv, B, hw, nchunks, partial))
             self.add(prefix + "fold", lambda: ops.linattn_fold(partial, B, hw, nchunks, a["w_out"], C, c_pad, weff))
             self.flops += 2.0 * B * 4 * 32 * 32 * hw      # context einsum (the apply einsum is folded into to_out)
-            self.conv(prefix + "to_out", q, 128, a["out"], out, h, w, epi=L.EPI_LN, bias=a["b_out"],
-                      ln_g=a["g_out"], res=x, per_image_w=True, weight_override=weff)
+            self.to_out_ln(prefix, a, q, weff, x, out, h, w)
             return out
         xn = self.buf(B, h, w, C)
         heads = a["heads"]

@@ -180,6 +180,10 @@ int dac_conv_info(dac_conv_t plan, int32_t* tiles, int32_t* ctas, int32_t* smem_
  * rows = pixels) and nn.LayerNorm of the transformer blocks (ATT:203-205) and ViT (TR:22-28). */
 int dac_layernorm_rows(const void* in, int32_t ld_in, void* out, int32_t ld_out, int64_t rows, int32_t c,
                        const float* w, const float* b, float eps, dac_stream_t stream);
+/* Same plus a bf16 residual row: out = LayerNorm(in) * w + b + res (res may be NULL).  The `to_out` LayerNorm and the Residual
+ * wrapper of a LinearAttention wider than 256 channels (MU:27-33,168,185), whose rows exceed the fused LN epilogue. */
+int dac_layernorm_rows_res(const void* in, int32_t ld_in, const void* res, int32_t ld_res, void* out, int32_t ld_out,
+                           int64_t rows, int32_t c, const float* w, const float* b, float eps, dac_stream_t stream);
 /* GroupNorm(32 groups, eps) over NHWC bf16 [B, hw, c] (ATT:76-77,251).  stats: workspace [B][16][groups][2] fp32 (per-slab
  * partial sums, added in a fixed order: no atomics, bit-reproducible). */
 /* Same, fp32 input rows (the ViT residual stream), bf16 output. */

@@ -222,6 +222,36 @@ def gen_daclip_text():
     torch.save(out, os.path.join(GOLD, "daclip_text.pt"))
 
 
+def gen_unet_noctx():
+    """The class-default construction ConditionalUNet(use_image_context=False) (DenoisingUNet_arch.py:22-23): every level is
+    a LinearAttention, incl. the 512-channel ones of level 3 / mid (:84-85,105).  Also reverse_ode, which forwards no
+    contexts (sde_utils.py:282-294) and therefore only runs with this construction."""
+    from models.modules.DenoisingUNet_arch import ConditionalUNet
+    from utils.sde_utils import IRSDE
+    ctor = dict(use_image_context=False)
+    sd, kw = synthetic.unet_state_dict(5, **ctor)
+    net = ConditionalUNet(**kw)
+    net.load_state_dict(sd, strict=True)
+    net.eval()
+    cases = []
+    with torch.no_grad():
+        for seed, (B, H, W), time in ((21, (1, 64, 64), 100.0), (22, (2, 40, 24), 13.0)):
+            inp = synthetic.restoration_inputs(B, H, W, T=1, seed=seed)
+            xt = inp["lq"] + inp["eps0"] * (50 / 255)
+            cases.append(dict(seed=seed, shape=(B, H, W), time=time,
+                              out=net(xt, inp["lq"], time, text_context=inp["text_context"], image_context=None)))
+        T = 100
+        inp = synthetic.restoration_inputs(1, 32, 32, T=T, seed=23)
+        sde = IRSDE(max_sigma=50, T=T, schedule="cosine", eps=0.005, device="cpu")
+        sde.set_model(net)
+        sde.set_mu(inp["lq"])
+        x_T = inp["lq"] + inp["eps0"] * sde.max_sigma
+        ode = dict(seed=23, shape=(1, 32, 32), T=T, out=sde.reverse_ode(x_T))
+    torch.save(dict(ctor=ctor, weights_seed=5, cases=cases, ode=ode), os.path.join(GOLD, "unet_noctx.pt"))
+    print("unet_noctx.pt written; absmax", [c["out"].abs().max().item() for c in cases], "ode absmax",
+          ode["out"].abs().max().item())
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     which = sys.argv[1:] or ["unet", "daclip"]
@@ -237,3 +267,5 @@ if __name__ == "__main__":
         gen_daclip_l14()
     if "daclip_text" in which:
         gen_daclip_text()
+    if "unet_noctx" in which:
+        gen_unet_noctx()

@@ -818,6 +818,20 @@ def test_groupnorm(ops, gen, B, hw, c):
     assert_close_bf16(out, ref, "groupnorm")
 
 
+@pytest.mark.parametrize("rows,c", [(1000, 512), (333, 64), (77, 1024)])
+def test_layernorm_rows_with_residual(ops, gen, rows, c):
+    """dac_layernorm_rows_res: LayerNorm(in) * g + res - the to_out LayerNorm and the Residual wrapper of a LinearAttention
+    wider than 256 channels (module_util.py:27-33,168,185)."""
+    x, res = bf(rnd(gen, rows, c) * 3 + 0.5), bf(rnd(gen, rows, c))
+    g = 1 + 0.2 * rnd(gen, c)
+    out = torch.zeros_like(x)
+    ops.layernorm_rows_res(x, res, out, rows, c, g, None, 1e-5)
+    torch.cuda.synchronize()
+    xf = x.float()
+    ref = (xf - xf.mean(-1, keepdim=True)) * torch.rsqrt(xf.var(-1, unbiased=False, keepdim=True) + 1e-5) * g + res.float()
+    assert_close_bf16(out, ref, "layernorm + residual")
+
+
 @pytest.mark.parametrize("B,hw,c", [(2, 1024, 256), (3, 1024, 512), (1, 100, 512), (2, 64, 768)])
 def test_prenorm_groupnorm_fused(ops, gen, B, hw, c):
     """dac_prenorm_groupnorm_nhwc: channel LayerNorm with gain (module_util.py:77-97) and GroupNorm(32, eps 1e-6) of its

@@ -136,6 +136,23 @@ def test_unet_wild_ir_variant_vs_reference_golden():
         assert (out - case["out"]).abs().max().item() < 2e-4
 
 
+def test_unet_without_image_context_vs_reference_golden():
+    """The class-default construction (use_image_context=False, DenoisingUNet_arch.py:22-23): LinearAttention at every
+    level incl. 512 channels; the oracle against the reference's own outputs (tests/golden/unet_noctx.pt)."""
+    g = torch.load(os.path.join(GOLD, "unet_noctx.pt"), weights_only=False)
+    sd, kw = synthetic.unet_state_dict(g["weights_seed"], **g["ctor"])
+    assert "mid_attn.fn.fn.to_qkv.weight" in sd and not any("transformer_blocks" in k for k in sd)
+    cfg = O.UNetConfig(**kw)
+    for case in g["cases"]:
+        B, H, W = case["shape"]
+        inp = synthetic.restoration_inputs(B, H, W, T=1, seed=case["seed"])
+        xt = inp["lq"] + inp["eps0"] * (50 / 255)
+        with torch.no_grad():
+            out = O.unet_forward(sd, cfg, xt, inp["lq"], case["time"], inp["text_context"], None)
+        assert out.shape == case["out"].shape
+        assert (out - case["out"]).abs().max().item() < 2e-4
+
+
 def test_daclip_vit_l14_encode_vs_reference_golden():
     """wild-ir encoder (daclip_ViT-L-14: patch 14, 257 tokens, width 1024, 24 layers, 16 heads, embed 768): oracle vs
     the reference model's own features (tests/golden/daclip_l14.pt)."""

@@ -255,6 +255,43 @@ def test_wild_ir_variant_vs_reference_golden(cuda):
         assert rel_err(out, ref) < 1e-2, (case["shape"], rel_err(out, ref))
 
 
+def test_no_image_context_variant_vs_reference_golden(cuda):
+    """ConditionalUNet(use_image_context=False) - the reference class default (DenoisingUNet_arch.py:22-23,84-85,105): every
+    level is a LinearAttention, the 512-channel ones (mid, ups.0) through the plain to_out epilogue + LayerNorm/residual
+    pass - against the reference's outputs, and IRSDE.reverse_ode (sde_utils.py:282-294: forwards no contexts, so it only
+    runs with this construction) over the full T = 100 against the reference's own ODE loop."""
+    from daclip_b200 import synthetic
+    from daclip_b200.sde import IRSDE
+    from daclip_b200.unet import ConditionalUNet
+    g = torch.load(os.path.join(GOLD, "unet_noctx.pt"), weights_only=False)
+    sd, kw = synthetic.unet_state_dict(g["weights_seed"], **g["ctor"])
+    m = ConditionalUNet(**kw)
+    m.load_state_dict(sd, strict=True)
+    m = m.to(cuda).eval()
+    for case in g["cases"]:
+        B, H, W = case["shape"]
+        inp = {k: v.cuda() for k, v in synthetic.restoration_inputs(B, H, W, T=1, seed=case["seed"]).items()}
+        xt = inp["lq"] + inp["eps0"] * (50 / 255)
+        out = m(xt, inp["lq"], case["time"], text_context=inp["text_context"], image_context=None)
+        ref = case["out"].cuda()
+        assert out.shape == ref.shape
+        err = rel_err(out, ref)
+        print(f"[parity] noctx_{H}x{W}: rel_err_of_range={err:.4g}")
+        assert err < 1e-2, (case["shape"], err)
+    ode = g["ode"]
+    B, H, W = ode["shape"]
+    inp = {k: v.cuda() for k, v in synthetic.restoration_inputs(B, H, W, T=ode["T"], seed=ode["seed"]).items()}
+    sde = IRSDE(max_sigma=50, T=ode["T"], schedule="cosine", eps=0.005, device=cuda)
+    sde.set_model(m)
+    sde.set_mu(inp["lq"])
+    x_T = inp["lq"] + inp["eps0"] * sde.max_sigma
+    got = sde.reverse_ode(x_T)
+    ref = ode["out"].cuda()
+    d = (got.clamp(0, 1) - ref.clamp(0, 1)).abs().max().item()
+    print(f"[parity] noctx_reverse_ode_T100: max_abs_clamped={d:.4g}, ref_absmax={ref.abs().max().item():.4g}")
+    assert d <= 2e-2
+
+
 @pytest.mark.parametrize("mode", ["sde", "posterior"])
 def test_reduced_step_sampling_vs_reference_golden(model, cuda, mode):
     """IRSDE(T=100, sample_T=20) through the drop-in sampler (fused loop) against the reference's loop."""
