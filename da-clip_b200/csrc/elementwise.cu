@@ -203,6 +203,26 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const __nv_bfloat16
   const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
   const int nvec = c >> 3;
   const float inv_c = 1.0f / c;
+  // gain / bias of this lane's vectors: loaded once per warp (16-byte parameter loads; per-row reloads were four loads per
+  // data load), kept in registers across the warp's rows
+  float wreg[VPL][8], breg[VPL][8];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int vi = sub + i * LPR;
+    float4 w0 = make_float4(1.f, 1.f, 1.f, 1.f), w1 = w0, b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+    if (w && vi < nvec) {
+      w0 = __ldg(reinterpret_cast<const float4*>(w) + vi * 2);
+      w1 = __ldg(reinterpret_cast<const float4*>(w) + vi * 2 + 1);
+    }
+    if (b && vi < nvec) {
+      b0 = __ldg(reinterpret_cast<const float4*>(b) + vi * 2);
+      b1 = __ldg(reinterpret_cast<const float4*>(b) + vi * 2 + 1);
+    }
+    wreg[i][0] = w0.x; wreg[i][1] = w0.y; wreg[i][2] = w0.z; wreg[i][3] = w0.w;
+    wreg[i][4] = w1.x; wreg[i][5] = w1.y; wreg[i][6] = w1.z; wreg[i][7] = w1.w;
+    breg[i][0] = b0.x; breg[i][1] = b0.y; breg[i][2] = b0.z; breg[i][3] = b0.w;
+    breg[i][4] = b1.x; breg[i][5] = b1.y; breg[i][6] = b1.z; breg[i][7] = b1.w;
+  }
   for (int64_t row0 = warp_global * rows_per_warp; row0 < rows; row0 += nwarps * rows_per_warp) {
     const int64_t row = row0 + lane / LPR;
     const bool live = row < rows;
@@ -244,17 +264,7 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const __nv_bfloat16
       if (live && vi < nvec) {
         float y[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) y[j] = (v[i][j] - mean) * rstd;
-        if (w) {      // 16-byte parameter loads (one scalar load per element made this kernel issue-bound)
-          const float4 w0 = __ldg(reinterpret_cast<const float4*>(w) + vi * 2), w1 = __ldg(reinterpret_cast<const float4*>(w) + vi * 2 + 1);
-          y[0] *= w0.x; y[1] *= w0.y; y[2] *= w0.z; y[3] *= w0.w;
-          y[4] *= w1.x; y[5] *= w1.y; y[6] *= w1.z; y[7] *= w1.w;
-        }
-        if (b) {
-          const float4 b0 = __ldg(reinterpret_cast<const float4*>(b) + vi * 2), b1 = __ldg(reinterpret_cast<const float4*>(b) + vi * 2 + 1);
-          y[0] += b0.x; y[1] += b0.y; y[2] += b0.z; y[3] += b0.w;
-          y[4] += b1.x; y[5] += b1.y; y[6] += b1.z; y[7] += b1.w;
-        }
+        for (int j = 0; j < 8; ++j) y[j] = fmaf((v[i][j] - mean) * rstd, wreg[i][j], breg[i][j]);
         if (res) {    // + residual row (the Residual wrapper around a wide LinearAttention, module_util.py:27-33)
           const uint4 r = __ldg(reinterpret_cast<const uint4*>(res + row * ld_res) + vi);
           float2 t;
@@ -757,7 +767,10 @@ extern "C" int dac_layernorm_rows_res(const void* in, int32_t ld_in, const void*
   const int lpr = nvec <= 8 ? 8 : (nvec <= 16 ? 16 : 32);
   const int64_t warps = ceil_div(rows, 32 / lpr);
   int64_t blocks = ceil_div(warps, 8);
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  // persistent warps (the parameters are loaded once per warp): as many CTAs as are resident at once - 48 / 76 / 128
+  // registers per thread for 1 / 2 / 4 vectors per lane
+  const int resident = 148 * (nvec <= 32 ? 4 : (nvec <= 64 ? 3 : 2));
+  if (blocks > resident) blocks = resident;
   const int grid = static_cast<int>(blocks);
   const dim3 g(grid), t(256);
   const long long rows_ll = rows;

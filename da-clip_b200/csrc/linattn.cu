@@ -246,7 +246,8 @@ __global__ void __launch_bounds__(256) linattn_fold_g_kernel(const float* __rest
   {
     const float* src = pbase + d0 * 64 + t;      // 4 rows x 64 channels = 256 consecutive floats of a record
     int c = 0;
-    for (; c + 1 < nslots; c += 2) {
+#pragma unroll 4
+    for (; c + 1 < nslots; c += 2) {      // (eight independent loads in flight: the merge is one L2 round trip per 8 slots)
       a0 += src[static_cast<int64_t>(c) * kKvGRec];
       a1 += src[static_cast<int64_t>(c + 1) * kKvGRec];
     }
