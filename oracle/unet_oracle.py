@@ -46,6 +46,9 @@ class UNetConfig:
         return self.spatial_transformer and i >= (self.depth - 1 if self.wild else 3)
 
 
+USE_SDPA = False     # see attention(): set by bench.py's library baseline for one of its legs
+
+
 def silu(x):
     return x * torch.sigmoid(x)
 
@@ -115,8 +118,11 @@ def attention(sd, p, x, context, heads):
         return t.reshape(b, t.shape[1], heads, d).transpose(1, 2)   # [b, heads, len, d]
 
     q, k, v = split(q), split(k), split(v)
-    sim = torch.matmul(q, k.transpose(2, 3)) * d ** -0.5
-    out = torch.matmul(torch.softmax(sim, dim=-1), v)
+    if USE_SDPA:     # bench.py's strongest library leg only (fused attention of the installed PyTorch); never in parity tests
+        out = F.scaled_dot_product_attention(q, k, v)
+    else:
+        sim = torch.matmul(q, k.transpose(2, 3)) * d ** -0.5
+        out = torch.matmul(torch.softmax(sim, dim=-1), v)
     out = out.transpose(1, 2).reshape(b, n, heads * d)
     return F.linear(out, sd[p + "to_out.0.weight"], sd[p + "to_out.0.bias"])
 
