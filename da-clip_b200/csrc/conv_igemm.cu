@@ -46,6 +46,9 @@ static int encode_act_map(CUtensorMap* m, const void* ptr, int c, int ld, int W,
   return 0;
 }
 
+// CTA-pair mode on by default?  (DAC_CTA2 overrides either way.)
+static const bool kCta2Default = false;
+
 extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
   if (!d || !out) return set_error(-1, "dac_conv_create: null argument");
   *out = nullptr;
@@ -212,6 +215,24 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
                   (smem_budget - res_bytes - kv_extra) / (long long)k.a_slot >= 3;
   k.b_res_bytes = resident ? (uint32_t)res_bytes : 0u;
   k.pair = d->pair ? 1 : 0;
+  k.bias_sh = (d->bias && !d->film && !nchw && !d->pair && d->block_n <= 512 && !getenv("DAC_NO_BIAS_SH") &&
+               (d->epi == DAC_EPI_PLAIN || d->epi == DAC_EPI_GEGLU)) ? 1 : 0;
+  // CTA-pair mode (conv_kernel.cuh): streamed-weight layers on 2-CTA clusters, each CTA loading half of every weight tile.
+  // DAC_CTA2=0 switches it off (A/B runs); layers whose weights are resident, the pixel-pair / fused-skip / per-image-weight
+  // / KVCTX / QKV / NCHW flavours and odd M-tile counts keep the 1-CTA kernel.
+  const char* cta2_env = getenv("DAC_CTA2");
+  const bool cta2 = (cta2_env ? atoi(cta2_env) != 0 : kCta2Default) && !resident && !d->pair && !fused_res && !d->per_image_w &&
+                    d->ngroups == 1 && !nchw && d->epi != DAC_EPI_KVCTX && d->epi != DAC_EPI_QKV && !d->halo &&
+                    (k.m_tiles % 2) == 0 && (d->block_n % 32) == 0 && d->block_n >= 64 && !d->stats_out;
+  if (cta2) {
+    ConvKernelFn kernel2 = pick_conv_kernel(d->epi, d->act, d->film != nullptr, nchw, f32_stream, true);
+    if (kernel2) {
+      kernel = kernel2;
+      pl->kernel = kernel2;
+      k.cta2 = 1;
+      k.b_bytes >>= 1;               // per CTA: half of the block_n weight rows of a K step
+    }
+  }
   if (d->pair) {   // one 192-row block per (64-channel source slice, ky), always resident
     k.b_res_bytes = (uint32_t)(chunks / 2) * 3u * (3u * (uint32_t)(d->block_n / 2) * 128u);
     k.film_cols = d->block_n / 2;
@@ -286,7 +307,7 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
     const int wrows = d->pair ? 3 * (d->block_n / 2) : d->cout_pad;
     cuuint64_t dims[3] = {(cuuint64_t)ctot, (cuuint64_t)wrows, (cuuint64_t)Z};
     cuuint64_t strides[2] = {(cuuint64_t)ctot * 2, (cuuint64_t)wrows * ctot * 2};
-    cuuint32_t box[3] = {(cuuint32_t)kChunkK, (cuuint32_t)(d->pair ? wrows : d->block_n), 1};
+    cuuint32_t box[3] = {(cuuint32_t)kChunkK, (cuuint32_t)(d->pair ? wrows : (k.cta2 ? d->block_n / 2 : d->block_n)), 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(&pl->mapW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(d->weight), dims, strides,
                      box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -362,6 +383,33 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (sms <= 0) sms = 148;
   pl->grid = pl->tiles < sms ? pl->tiles : sms;
+  if (k.cta2) {
+    // one cluster = two CTAs on the two SMs of a TPC; as many clusters as are resident at once (a TPC with one usable SM
+    // hosts none), each with a contiguous range of pair tiles
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(sms & ~1);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = pl->smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int ncl = 0;
+    cudaFuncSetAttribute(reinterpret_cast<const void*>(kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (cudaOccupancyMaxActiveClusters(&ncl, reinterpret_cast<const void*>(kernel), &cfg) != cudaSuccess || ncl <= 0) {
+      cudaGetLastError();
+      delete pl;
+      return set_error(-12, "dac_conv_create: no 2-CTA cluster of this kernel fits the device (DAC_CTA2=0 disables the mode)");
+    }
+    const int pairs = pl->tiles / 2;
+    pl->grid = 2 * (pairs < ncl ? pairs : ncl);
+    if (getenv("DAC_CTA2_DEBUG"))
+      fprintf(stderr, "[cta2] tiles %d pairs %d max active clusters %d grid %d smem %d stages %d block_n %d\n", pl->tiles, pairs,
+              ncl, pl->grid, pl->smem, k.stages, k.block_n);
+  }
   if (k.ctx_acc) {
     const int need = 2 * max_image_span(d->B, k.ctx_tpi, pl->grid);
     if (k.n_tiles != 1 || k.ngroups != 1 || d->ctx_slots < need) {
@@ -405,8 +453,8 @@ extern "C" int dac_conv_launch(dac_conv_t pl, dac_stream_t stream) {
                                                                                     pl->mapOut, pl->mapOut2, pl->mapR0,
                                                                                     pl->mapR1, pl->mapWR, pl->mapRes, pl->kp);
   else
-    launch_k(pl->kernel, dim3(pl->grid), dim3(kThreads), pl->smem, static_cast<cudaStream_t>(stream), pl->mapA0, pl->mapA1,
-             pl->mapW, pl->mapOut, pl->mapOut2, pl->mapR0, pl->mapR1, pl->mapWR, pl->mapRes, pl->kp);
+    launch_k_cluster(pl->kernel, dim3(pl->grid), dim3(kThreads), pl->smem, static_cast<cudaStream_t>(stream), pl->kp.cta2 ? 2 : 1,
+             pl->mapA0, pl->mapA1, pl->mapW, pl->mapOut, pl->mapOut2, pl->mapR0, pl->mapR1, pl->mapWR, pl->mapRes, pl->kp);
   return check_launch("conv_igemm_kernel");
 }
 

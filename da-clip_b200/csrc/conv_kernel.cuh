@@ -111,6 +111,8 @@ struct ConvKParams {
   float kv_shift_max[4];   // KVCTX: the largest bound of each head - one scalar shift per head is all the softmax needs
   float* ctx_acc;          // KVCTX: [B][4][ctx_slots][kCtxRecord] fp32 partial records
   int ctx_slots, ctx_tpi;  // slots per (image, head); tiles per image
+  int bias_sh;             // the tile's bias columns are staged in shared memory before the accumulator is awaited (PLAIN / F32 / GEGLU)
+  int cta2;                // CTA-pair mode (cta_group::2): see the kernel; block_n, b_bytes describe the WHOLE / HALF weight tile
   int dbg;                 // profiling only (DAC_EPI_DEBUG, tools/prof_conv.py): 1 skip stores, 2 skip activation, 4 skip FiLM
 };
 
@@ -131,6 +133,15 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvKParams& p, int tile)
   t.y0 = ty * p.tile_h;
   t.x0 = tx * p.tile_w;
   return t;
+}
+
+// v += 32 floats of this tile's staged bias (broadcast reads: every thread of the warp reads the same 16 bytes)
+__device__ __forceinline__ void chunk_add_sh(const float* sh, float (&v)[32]) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 a = *reinterpret_cast<const float4*>(sh + 4 * q);
+    v[4 * q] += a.x; v[4 * q + 1] += a.y; v[4 * q + 2] += a.z; v[4 * q + 3] += a.w;
+  }
 }
 
 template <int ACT>
@@ -280,7 +291,8 @@ __device__ __forceinline__ void epilogue_tile(const ConvKParams& p, const TileCo
       const int ch = t.nt * p.block_n + c;
       if (ch >= p.cout) break;  // warp-uniform (cout_pad > cout)
       chunk_from_tmem(tmem_acc + c, v);
-      if (p.bias) chunk_add_f32(p.bias + ch, v);
+      if (p.bias_sh) chunk_add_sh(film_sh + c, v);
+      else if (p.bias) chunk_add_f32(p.bias + ch, v);
       if (valid) {
         const float* rs = p.res_f32 + opix * p.res_f32_ld + ch;
         float* os = p.out_f32 ? p.out_f32 + opix * p.out_f32_ld + ch : nullptr;
@@ -308,8 +320,13 @@ __device__ __forceinline__ void epilogue_tile(const ConvKParams& p, const TileCo
       chunk_from_tmem(tmem_acc + c, v);
       chunk_from_tmem(tmem_acc + hn + c, g);
       const int col = t.nt * p.block_n + c;  // column in the (permuted) weight / bias row order
-      chunk_add_f32(p.bias + col, v);
-      chunk_add_f32(p.bias + col + hn, g);
+      if (p.bias_sh) {
+        chunk_add_sh(film_sh + c, v);
+        chunk_add_sh(film_sh + hn + c, g);
+      } else {
+        chunk_add_f32(p.bias + col, v);
+        chunk_add_f32(p.bias + col + hn, g);
+      }
 #pragma unroll
       for (int j = 0; j < 32; j += 2) {
         gelu2_f(g[j], g[j + 1]);
@@ -376,7 +393,8 @@ __device__ __forceinline__ void epilogue_tile(const ConvKParams& p, const TileCo
       }
       continue;
     }
-    if (p.bias) chunk_add_f32(p.bias + ch, v);
+    if (!FILM && p.bias_sh) chunk_add_sh(film_sh + c, v);
+    else if (p.bias) chunk_add_f32(p.bias + ch, v);
     if (p.bias_img) chunk_add_f32(p.bias_img + static_cast<long long>(n) * p.cout + ch, v);
     if (FILM && (p.dbg & 4)) {
     } else if (FILM && p.film_tmem) {
@@ -575,7 +593,9 @@ __device__ __forceinline__ void kvctx_tile(const ConvKParams& p, const TileCoord
   }
 }
 
-template <int EPI, int ACT, bool FILM>
+// CTA2: the CTA-pair build of a flavour (a cubin that holds cta_group::2 instructions can only be launched in clusters of
+// even size - "cluster misconfiguration" otherwise - so the 1-CTA kernels must not contain them)
+template <int EPI, int ACT, bool FILM, bool CTA2 = false>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                   const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapOut,
@@ -611,8 +631,28 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.ngroups * p.m_tiles * p.n_tiles;
+  // ---- CTA-pair mode (p.cta2; streamed-weight layers, which are bound by L2 -> SM ingest: every CTA of the 1-CTA kernel
+  // pulls the whole weight tile of every K step).  The two CTAs of a 2-CTA cluster work on two M tiles of the same N tile
+  // as ONE M = 256 tcgen05.mma.cta_group::2: each loads its own activation tile and HALF of the weight tile (rows
+  // [block_n / 2 * rank, +block_n / 2)), i.e. a third less operand traffic per CTA at N = 256; the leader (rank 0) issues
+  // every MMA and its commits arrive in both CTAs; each CTA drains its own 128 accumulator rows with the usual epilogue.
+  // The loops below walk pair indices v = (pair of M tiles, N tile); tile_of(v) is this CTA's tile.
+  constexpr bool cta2 = CTA2;      // (p.cta2 says the same; the template keeps the pair instructions out of the 1-CTA builds)
+  const uint32_t crank = cta2 ? cluster_ctarank() : 0u;
   int tile_begin, tile_end;
-  tile_range(total_tiles, tile_begin, tile_end);
+  if (cta2) {
+    const long long total_pairs = static_cast<long long>(p.m_tiles >> 1) * p.n_tiles;
+    const int cl = blockIdx.x >> 1, ncl = gridDim.x >> 1;
+    tile_begin = static_cast<int>(total_pairs * cl / ncl);
+    tile_end = static_cast<int>(total_pairs * (cl + 1) / ncl);
+  } else {
+    tile_range(total_tiles, tile_begin, tile_end);
+  }
+  auto tile_of = [&](int v) -> int {
+    if (!cta2) return v;
+    const int mp = fast_div(v, p.fd_ntiles);
+    return (2 * mp + static_cast<int>(crank)) * p.n_tiles + (v - mp * p.n_tiles);
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA0);
@@ -626,12 +666,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       tma_prefetch_desc(&mapWR);
     }
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(&full[s], 1);
+      mbar_init(&full[s], 1);                      // pair mode: only the leader's barrier is used (see the producer)
       mbar_init(&empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], kEpiWarps / 2);
+      mbar_init(&tmem_empty[s], (kEpiWarps / 2) * (cta2 ? 2 : 1));   // ... and both CTAs' epilogue warps
     }
     mbar_init(b_full, 1);
     mbar_init(b_empty, 1);
@@ -640,11 +680,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, kTmemCols);
-    tmem_relinquish();
+    if constexpr (cta2) {
+      tmem_alloc_pair(tmem_slot, kTmemCols);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (cta2) cluster_sync_all();     // both CTAs' barriers are initialised before either signals the other
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // Programmatic dependent launch: the next kernel of the stream may be scheduled from now on (its CTAs land on an SM
@@ -696,18 +742,68 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       griddep_wait();
+      const uint32_t full_lead = cta2 ? mapa_u32(smem_u32(full), 0) : 0u;   // the leader's full[0] (shared::cluster address)
+      const int half_n = p.block_n >> 1;
+      const bool gemm_steps = !b_resident && p.ncols == 1 && p.ndy == 1 && r_chunks == 0 && !p.pair;
       for (int tile = tile_begin; tile < tile_end; ++tile) {
-        const TileCoord t = decode_tile(p, tile);
+        const TileCoord t = decode_tile(p, tile_of(tile));
         if (b_resident && t.g != w_group) load_group_weights(t.g);
         const int xin = t.x0 * p.stride, yin = t.y0 * p.stride;
         const int zbase = (p.per_image_w ? t.n * p.ngroups * p.ntaps : 0) + t.g * p.ntaps;
         const int ncoord = t.nt * p.block_n;
+        if (gemm_steps) {
+          // GEMM-shaped K loop (1x1 layers, every Linear of the transformers and the ViTs): one activation and one weight
+          // tile per step and nothing else to decide.  The general loop below costs ~250 instructions per step (tap tables,
+          // unrolled tap counts) - ~850 cycles of this single thread against the 384-512 cycles the four MMAs of a step
+          // take: the PRODUCER bounded these layers (tensor pipe 39 % busy, ncu source page of the ViT in_proj GEMM).
+          const int xa = xin + p.col_dx[t.g][0], ya = yin + p.col_dy0[t.g][0], zt = zbase + p.col_tap[t.g][0];
+          const int wrow = ncoord + (cta2 ? static_cast<int>(crank) * half_n : 0);
+          for (int ck = 0; ck < chunks; ++ck) {
+            const bool first = ck < p.chunks0;
+            const CUtensorMap* mapA = first ? &mapA0 : &mapA1;
+            const int ccoord = (first ? ck : ck - p.chunks0) * kChunkK;
+            mbar_wait(&empty[stage], phase ^ 1);
+            uint8_t* sa = ring + static_cast<size_t>(stage) * stage_bytes;
+            if constexpr (cta2) {
+              const uint32_t fb = full_lead + 8u * stage;
+              if (crank == 0) mbar_arrive_expect_tx(&full[stage], 2u * main_tx);
+              tma_load_4d_pair(sa, mapA, fb, ccoord, xa, ya, t.n);
+              tma_load_3d_pair(sa + p.a_slot, &mapW, fb, ck * kChunkK, wrow, zt);
+            } else {
+              mbar_arrive_expect_tx(&full[stage], main_tx);
+              tma_load_4d(sa, mapA, &full[stage], ccoord, xa, ya, t.n);
+              tma_load_3d(sa + p.a_slot, &mapW, &full[stage], ck * kChunkK, wrow, zt);
+            }
+            if (++stage == p.stages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          continue;
+        }
         for (int ck = 0; ck < chunks; ++ck) {
           const CUtensorMap* mapA = ck < p.chunks0 ? &mapA0 : &mapA1;
           const int ccoord = (ck < p.chunks0 ? ck : ck - p.chunks0) * kChunkK;
           for (int j = 0; j < p.ncols; ++j) {
             mbar_wait(&empty[stage], phase ^ 1);
             uint8_t* sa = ring + static_cast<size_t>(stage) * stage_bytes;
+            if constexpr (cta2) {
+              // this CTA's activation tile and its half of the weight rows, both signalling the leader's barrier
+              // (the leader announces the bytes of BOTH CTAs - they load equal amounts; the peer only issues its loads: its
+              // bytes may land before the leader's arrival, which merely takes the transaction count through zero while the
+              // arrival is still pending)
+              const uint32_t fb = full_lead + 8u * stage;
+              if (crank == 0) mbar_arrive_expect_tx(&full[stage], 2u * main_tx);
+              tma_load_4d_pair(sa, mapA, fb, ccoord, xin + p.col_dx[t.g][j], yin + p.col_dy0[t.g][j], t.n);
+              for (int i = 0; i < p.ndy; ++i)
+                tma_load_3d_pair(sa + p.a_slot + static_cast<size_t>(i) * p.b_bytes, &mapW, fb, ck * kChunkK,
+                                 ncoord + static_cast<int>(crank) * half_n, zbase + p.col_tap[t.g][j * p.ndy + i]);
+              if (++stage == p.stages) {
+                stage = 0;
+                phase ^= 1;
+              }
+              continue;
+            }
             mbar_arrive_expect_tx(&full[stage], main_tx);
             tma_load_4d(sa, mapA, &full[stage], ccoord, xin + p.col_dx[t.g][j], yin + p.col_dy0[t.g][j], t.n);
             if (!b_resident) {
@@ -743,8 +839,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     // that every operand is provably warp-uniform and lives in uniform registers; only the tcgen05 instructions sit
     // under elect.sync (a whole-loop `if (elected)` made the compiler compute descriptors in vector registers and
     // pay two R2UR per operand, ~3x the MMA time). ==========
-    {
-      const uint32_t idesc = make_idesc_bf16(kTileM, p.block_n);
+    if (!cta2 || crank == 0) {
+      const uint32_t idesc = make_idesc_bf16(cta2 ? 2 * kTileM : kTileM, p.block_n);
       const uint64_t desc_fixed = make_sw128_desc(0);                 // every field except the start address
       const uint64_t desc_fixed_a = make_sw128_desc(0, p.a_sbo);
       const uint32_t ring_lo = (smem_u32(ring) & 0x3FFFF) >> 4;
@@ -830,6 +926,36 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
               phase ^= 1;
             }
           }
+        } else if (!b_resident && p.ncols == 1 && p.ndy == 1) {
+          // GEMM-shaped K loop: one (activation, weight) tile pair per step - see the producer
+          const uint32_t t_off = p.tap_off[0];
+          for (int ck = 0; ck < chunks; ++ck) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            const uint32_t a0 = ring_lo + stage * stage_lo;
+            const uint64_t adesc = desc_fixed_a | (a0 + t_off);
+            const uint64_t bdesc = desc_fixed | (a0 + a_lo);
+            if (elect_one()) {
+              if constexpr (cta2) {
+                umma_bf16_pair(d_tmem, adesc, bdesc, idesc, accumulate);
+                umma_bf16_pair(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
+                umma_bf16_pair(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
+                umma_bf16_pair(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
+                umma_commit_pair(&empty[stage]);
+              } else {
+                umma_bf16(d_tmem, adesc, bdesc, idesc, accumulate);
+                umma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
+                umma_bf16(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
+                umma_bf16(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
+                umma_commit(&empty[stage]);
+              }
+            }
+            accumulate = 1u;
+            if (++stage == p.stages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
         } else
         for (int ck = 0; ck < chunks; ++ck) {
           for (int j = 0; j < p.ncols; ++j) {
@@ -847,14 +973,24 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
               bs_run += b_lo;
               b_run += b_lo;
               if (elect_one()) {
-                umma_bf16(d_tmem, adesc, bdesc, idesc, accumulate);
-                umma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
-                umma_bf16(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
-                umma_bf16(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
+                if constexpr (cta2) {
+                  umma_bf16_pair(d_tmem, adesc, bdesc, idesc, accumulate);
+                  umma_bf16_pair(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
+                  umma_bf16_pair(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
+                  umma_bf16_pair(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
+                } else {
+                  umma_bf16(d_tmem, adesc, bdesc, idesc, accumulate);
+                  umma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
+                  umma_bf16(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
+                  umma_bf16(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
+                }
               }
               accumulate = 1u;
             }
-            if (elect_one()) umma_commit(&empty[stage]);
+            if (elect_one()) {
+              if constexpr (cta2) umma_commit_pair(&empty[stage]);    // the stage is free again in BOTH CTAs
+              else umma_commit(&empty[stage]);
+            }
             if (++stage == p.stages) {
               stage = 0;
               phase ^= 1;
@@ -883,7 +1019,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
             phase ^= 1;
           }
         }
-        if (elect_one()) umma_commit(&tmem_full[acc]);
+        if (elect_one()) {
+          if constexpr (cta2) umma_commit_pair(&tmem_full[acc]);      // both CTAs' epilogue groups
+          else umma_commit(&tmem_full[acc]);
+        }
         __syncwarp();
         if (++acc == 2) {
           acc = 0;
@@ -905,6 +1044,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     uint32_t acc_phase = 0;
     int film_key = -1;
     griddep_wait();
+    const uint32_t tmem_empty_lead = cta2 ? mapa_u32(smem_u32(&tmem_empty[group]), 0) : 0u;
     if (EPI == KE_KVCTX) {
       KvCtxAcc cacc;
       kvctx_zero(cacc);
@@ -924,7 +1064,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       kvctx_flush(p, cur_img, quad, lane, group, cacc);
     } else
     for (int tile = tile_begin + group; tile < tile_end; tile += 2) {
-      const TileCoord t = decode_tile(p, tile);
+      const TileCoord t = decode_tile(p, tile_of(tile));
       if (FILM) {
         // FiLM parameters depend on (image, N tile) only: restage when that pair changes (rare with contiguous
         // tile ranges).  Named barrier 1 + group = the 128 threads of this group.
@@ -961,6 +1101,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");
         }
       }
+      if (!FILM && p.bias_sh && t.nt != film_key) {
+        // the bias columns of this N tile, staged once per (group, N tile) BEFORE the accumulator is awaited: the per-chunk
+        // bias loads sat on the epilogue's critical chain (accumulator ready -> TMEM load -> L2 round trip per 32 columns ->
+        // first add: 11 % of all stall samples of the ViT GEMMs)
+        film_key = t.nt;
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");
+        const int c0 = t.nt * p.block_n;
+        for (int i = gthread; i < p.block_n; i += 128) film_g[i] = (c0 + i < p.cout) ? __ldg(p.bias + c0 + i) : 0.f;
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");
+      }
       if (stg && gthread == 0) {
         // this group's previous TMA store must have finished reading the staging tile before it is rewritten
         tma_store_wait_read();
@@ -973,7 +1123,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           // this tile has left the staging buffer, and a DRAM round trip at that point was the longest link of the
           // per-group chain (store drained -> residual lands -> epilogue -> store) - 4.5 us per tile, whatever its size
           if (tile + 2 < tile_end) {
-            const TileCoord tn = decode_tile(p, tile + 2);
+            const TileCoord tn = decode_tile(p, tile_of(tile + 2));
             for (int s_ = 0; s_ * 64 < cols; ++s_)
               tma_prefetch_l2_4d(&mapRes, tn.nt * cols + s_ * 64, tn.x0, tn.y0, tn.n);
           }
@@ -1003,17 +1153,22 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[group]);
+      if (lane == 0) {
+        if constexpr (cta2) mbar_arrive_cluster(tmem_empty_lead);   // the leader issues for both CTAs: its barrier collects both
+        else mbar_arrive(&tmem_empty[group]);
+      }
       acc_phase ^= 1;
     }
     if (EPI != KE_KVCTX && stg && gthread == 0) tma_store_wait_read();   // smem must outlive the last bulk store's reads
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (cta2) cluster_sync_all();     // the peer's shared memory and barriers stay alive until both CTAs are done
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if constexpr (cta2) tmem_dealloc_pair(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -1023,7 +1178,18 @@ typedef void (*ConvKernelFn)(const CUtensorMap, const CUtensorMap, const CUtenso
 
 // The epilogue flavours that exist as separate kernels; everything else in the epilogue is a warp-uniform
 // runtime branch on a pointer.
-inline ConvKernelFn pick_conv_kernel(int epi, int act, bool film, bool nchw, bool f32_stream = false) {
+inline ConvKernelFn pick_conv_kernel(int epi, int act, bool film, bool nchw, bool f32_stream = false, bool cta2 = false) {
+  if (cta2) {   // CTA-pair builds of the flavours the streamed-weight layers use
+    if (nchw || epi == DAC_EPI_QKV || epi == DAC_EPI_KVCTX) return nullptr;
+    if (f32_stream && epi == DAC_EPI_PLAIN && act == DAC_ACT_NONE && !film) return conv_igemm_kernel<KE_F32, DAC_ACT_NONE, false, true>;
+    if (epi == DAC_EPI_GEGLU) return conv_igemm_kernel<KE_GEGLU, DAC_ACT_NONE, false, true>;
+    if (epi == DAC_EPI_LN) return conv_igemm_kernel<KE_LN, DAC_ACT_NONE, false, true>;
+    if (act == DAC_ACT_SILU)
+      return film ? conv_igemm_kernel<KE_PLAIN, DAC_ACT_SILU, true, true> : conv_igemm_kernel<KE_PLAIN, DAC_ACT_SILU, false, true>;
+    if (act == DAC_ACT_GELU && !film) return conv_igemm_kernel<KE_PLAIN, DAC_ACT_GELU, false, true>;
+    if (act == DAC_ACT_NONE && !film) return conv_igemm_kernel<KE_PLAIN, DAC_ACT_NONE, false, true>;
+    return nullptr;
+  }
   if (nchw) return conv_igemm_kernel<KE_NCHW, DAC_ACT_NONE, false>;
   if (f32_stream && epi == DAC_EPI_PLAIN && act == DAC_ACT_NONE && !film) return conv_igemm_kernel<KE_F32, DAC_ACT_NONE, false>;
   if (epi == DAC_EPI_GEGLU) return conv_igemm_kernel<KE_GEGLU, DAC_ACT_NONE, false>;

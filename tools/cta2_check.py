@@ -1,0 +1,84 @@
+"""CTA-pair mode (DAC_CTA2=1) against the 1-CTA kernel on the same inputs: outputs must agree bit for bit (same MMA
+order per accumulator element), plus timings.  usage: cta2_check.py [case ...]"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from daclip_b200 import lib as L, ops
+
+g = torch.Generator(device="cuda").manual_seed(0)
+
+
+def rnd(*shape, scale=1.0):
+    return torch.randn(*shape, device="cuda", generator=g) * scale
+
+
+def make(case, cta2):
+    os.environ["DAC_CTA2"] = "1" if cta2 else "0"
+    kind, B, H, W, cin, cout = case
+    x = CACHE.setdefault(("x", case), rnd(B, H, W, cin).to(torch.bfloat16))
+    if kind == "1x1":
+        w = CACHE.setdefault(("w", case), rnd(cout, cin, scale=cin ** -0.5))
+        b = CACHE.setdefault(("b", case), rnd(cout))
+        out = torch.zeros(B, H, W, cout, device="cuda", dtype=torch.bfloat16)
+        plan = ops.ConvPlan(x, cin, ops.pack_linear(w), out, B=B, H=H, W=W, bias=b, act=L.ACT_GELU)
+    elif kind == "3x3":
+        w = CACHE.setdefault(("w", case), rnd(cout, cin, 3, 3, scale=(9 * cin) ** -0.5))
+        film = CACHE.setdefault(("f", case), rnd(B, 2 * cout, scale=0.1))
+        out = torch.zeros(B, H, W, cout, device="cuda", dtype=torch.bfloat16)
+        plan = ops.ConvPlan(x, cin, ops.pack_conv(w), out, B=B, H=H, W=W, act=L.ACT_SILU, film=film)
+    elif kind == "3x3res":
+        w = CACHE.setdefault(("w", case), rnd(cout, cin, 3, 3, scale=(9 * cin) ** -0.5))
+        res = CACHE.setdefault(("r", case), rnd(B, H, W, cout).to(torch.bfloat16))
+        out = torch.zeros(B, H, W, cout, device="cuda", dtype=torch.bfloat16)
+        plan = ops.ConvPlan(x, cin, ops.pack_conv(w), out, B=B, H=H, W=W, act=L.ACT_SILU, res=res)
+    elif kind == "geglu":
+        w = CACHE.setdefault(("w", case), rnd(cout, cin, scale=cin ** -0.5))
+        b = CACHE.setdefault(("b", case), rnd(cout))
+        pw, bp = ops.pack_geglu(w, b)
+        out = torch.zeros(B, H, W, cout // 2, device="cuda", dtype=torch.bfloat16)
+        plan = ops.ConvPlan(x, cin, pw, out, B=B, H=H, W=W, epi=L.EPI_GEGLU, bias=bp, block_n=256)
+    elif kind == "f32":
+        w = CACHE.setdefault(("w", case), rnd(cout, cin, scale=cin ** -0.5))
+        b = CACHE.setdefault(("b", case), rnd(cout))
+        stream = CACHE.setdefault(("s", case), rnd(B, H, W, cout)).clone()
+        out = stream
+        plan = ops.ConvPlan(x, cin, ops.pack_linear(w), None, B=B, H=H, W=W, bias=b, res_f32=stream, out_f32=stream)
+    plan._out = out
+    return plan
+
+
+CACHE = {}
+CASES = {
+    "lin512": ("1x1", 16, 32, 32, 512, 512),
+    "vit_qkv": ("1x1", 1, 1, 12800, 768, 2304),
+    "vit_fc": ("1x1", 1, 1, 12800, 768, 3072),
+    "vit_out": ("f32", 1, 1, 12800, 768, 768),
+    "vit_proj": ("f32", 1, 1, 12800, 3072, 768),
+    "l3_256": ("3x3", 16, 32, 32, 256, 256),
+    "l2_128": ("3x3", 16, 64, 64, 128, 128),
+    "l3_512": ("3x3res", 16, 32, 32, 512, 512),
+    "l2_256": ("3x3", 16, 64, 64, 256, 256),
+    "geglu": ("geglu", 16, 32, 32, 512, 4096),
+    "odd": ("3x3", 2, 40, 24, 128, 128),
+}
+for name in (sys.argv[1:] or list(CASES)):
+    case = CASES[name]
+    res = {}
+    for cta2 in (0, 1):
+        plan = make(case, cta2)
+        plan.run()
+        torch.cuda.synchronize()
+        first = plan._out.clone()
+        for _ in range(3):
+            plan.run()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(10):
+            plan.run()
+        b.record()
+        torch.cuda.synchronize()
+        res[cta2] = (first, a.elapsed_time(b) / 10 * 1e3, plan.info())
+    d = (res[0][0].float() - res[1][0].float()).abs().max().item()
+    print(f"{name:10s} 1-CTA {res[0][1]:7.1f} us  pair {res[1][1]:7.1f} us  max|diff| {d:.3g}  finite {bool(torch.isfinite(res[1][0].float()).all())}  "
+          f"{res[0][2]} -> {res[1][2]}", flush=True)
