@@ -47,7 +47,7 @@ static int encode_act_map(CUtensorMap* m, const void* ptr, int c, int ld, int W,
 }
 
 // CTA-pair mode on by default?  (DAC_CTA2 overrides either way.)
-static const bool kCta2Default = false;
+static const bool kCta2Default = true;
 
 extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
   if (!d || !out) return set_error(-1, "dac_conv_create: null argument");
