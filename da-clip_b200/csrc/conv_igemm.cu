@@ -221,16 +221,19 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
   // DAC_CTA2=0 switches it off (A/B runs); layers whose weights are resident, the pixel-pair / fused-skip / per-image-weight
   // / KVCTX / QKV / NCHW flavours and odd M-tile counts keep the 1-CTA kernel.
   const char* cta2_env = getenv("DAC_CTA2");
-  const bool cta2 = (cta2_env ? atoi(cta2_env) != 0 : kCta2Default) && !resident && !d->pair && !fused_res && !d->per_image_w &&
-                    d->ngroups == 1 && !nchw && d->epi != DAC_EPI_KVCTX && d->epi != DAC_EPI_QKV && !d->halo &&
-                    (k.m_tiles % 2) == 0 && (d->block_n % 32) == 0 && d->block_n >= 64 && !d->stats_out;
+  const bool cta2_on = cta2_env ? atoi(cta2_env) != 0 : kCta2Default;
+  // (pixel-pair layers: only when the weight tensor carries the per-rank layouts, dac_conv_desc.pair == 2)
+  const bool cta2 = cta2_on && !fused_res && !d->per_image_w && d->ngroups == 1 && !nchw && d->epi != DAC_EPI_KVCTX &&
+                    d->epi != DAC_EPI_QKV && (k.m_tiles % 2) == 0 && (d->block_n % 32) == 0 && d->block_n >= 64 &&
+                    !d->stats_out &&
+                    (d->pair ? (d->pair == 2 && !getenv("DAC_NO_CTA2_PAIR")) : (!resident && !d->halo));
   if (cta2) {
     ConvKernelFn kernel2 = pick_conv_kernel(d->epi, d->act, d->film != nullptr, nchw, f32_stream, true);
     if (kernel2) {
       kernel = kernel2;
       pl->kernel = kernel2;
       k.cta2 = 1;
-      k.b_bytes >>= 1;               // per CTA: half of the block_n weight rows of a K step
+      if (!d->pair) k.b_bytes >>= 1;   // per CTA: half of the block_n weight rows of a K step
     }
   }
   if (d->pair) {   // one 192-row block per (64-channel source slice, ky), always resident
@@ -258,7 +261,9 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
     // (pixel-pair mode with a residual: one K chunk keeps the tensor pipe busy for 1344 cycles, three stages are enough,
     // and direct residual loads - one 256-byte row per thread - cost far more than the pipeline depth buys: 124 -> 95 us;
     // without a residual the deeper pipeline wins: FiLM 91 vs 94 us, fused skip 107 vs 130 us)
-    if (with >= 4 || (with >= 3 && (with >= without || (d->pair && d->res)))) stg_bytes = want;
+    // (CTA-pair mode: the leader waits for two TMA streams per stage, a deeper pipeline is worth more than coalesced stores
+    // below five stages - ViT c_fc 64.6 us with four stages + staging, 60.5 us with seven stages and direct stores)
+    if ((k.cta2 && !d->pair) ? with >= 5 : (with >= 4 || (with >= 3 && (with >= without || (d->pair && d->res))))) stg_bytes = want;
   }
   if (d->epi == DAC_EPI_KVCTX) stg_bytes = kKvStageBytes;   // P / V head tiles of each epilogue group
   k.kv_shift = d->kv_shift; k.ctx_acc = d->ctx_acc;
@@ -303,7 +308,7 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
   if (rc == 0) {
     PFN_encodeTiled enc = get_encode_fn();
     const int ctot = d->pair ? (d->c0 + d->c1) / 2 : d->c0 + d->c1;
-    const long long Z = d->pair ? 3 : (long long)d->ngroups * d->ntaps * (d->per_image_w ? d->B : 1);
+    const long long Z = d->pair ? (d->pair == 2 ? 9 : 3) : (long long)d->ngroups * d->ntaps * (d->per_image_w ? d->B : 1);
     const int wrows = d->pair ? 3 * (d->block_n / 2) : d->cout_pad;
     cuuint64_t dims[3] = {(cuuint64_t)ctot, (cuuint64_t)wrows, (cuuint64_t)Z};
     cuuint64_t strides[2] = {(cuuint64_t)ctot * 2, (cuuint64_t)wrows * ctot * 2};

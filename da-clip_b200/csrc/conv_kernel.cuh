@@ -726,13 +726,24 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       };
       if (b_resident) {
         if (p.pair) {
-          mbar_arrive_expect_tx(b_full, p.b_res_bytes);
           // per (64-channel source slice, ky): ONE 192-row block [W(kx=2); W(kx=1); W(kx=0)] - the even and the odd
           // chunk of the slice read overlapping 128-row windows of it (see the issuer)
+          if constexpr (cta2) {
+            // CTA-pair mode: this CTA's own 192-row block of the rank-specific layout (blocks 3 + 3 rank + ky of the weight
+            // tensor, see the issuer); both CTAs' bytes complete on the LEADER's barrier
+            const uint32_t bfl = mapa_u32(smem_u32(b_full), 0);
+            if (crank == 0) mbar_arrive_expect_tx(b_full, 2u * p.b_res_bytes);
+            for (int s_ = 0; s_ < (chunks >> 1); ++s_)
+              for (int ky = 0; ky < 3; ++ky)
+                tma_load_3d_pair(b_res + static_cast<size_t>(s_ * 3 + ky) * (3u * (p.block_n >> 1) * 128u), &mapW, bfl,
+                                 s_ * kChunkK, 0, 3 + 3 * static_cast<int>(crank) + ky);
+          } else {
+          mbar_arrive_expect_tx(b_full, p.b_res_bytes);
           for (int s_ = 0; s_ < (chunks >> 1); ++s_)
             for (int ky = 0; ky < 3; ++ky)
               tma_load_3d(b_res + static_cast<size_t>(s_ * 3 + ky) * (3u * (p.block_n >> 1) * 128u), &mapW, b_full,
                           s_ * kChunkK, 0, ky);
+          }
           w_group = 0;
           ++w_loads;
         } else if (tile_begin < tile_end) {
@@ -744,39 +755,59 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       griddep_wait();
       const uint32_t full_lead = cta2 ? mapa_u32(smem_u32(full), 0) : 0u;   // the leader's full[0] (shared::cluster address)
       const int half_n = p.block_n >> 1;
-      const bool gemm_steps = !b_resident && p.ncols == 1 && p.ndy == 1 && r_chunks == 0 && !p.pair;
+      const bool lean_steps = !b_resident && p.ncols <= 3 && p.ndy <= 3 && r_chunks == 0 && !p.pair;
       for (int tile = tile_begin; tile < tile_end; ++tile) {
         const TileCoord t = decode_tile(p, tile_of(tile));
         if (b_resident && t.g != w_group) load_group_weights(t.g);
         const int xin = t.x0 * p.stride, yin = t.y0 * p.stride;
         const int zbase = (p.per_image_w ? t.n * p.ngroups * p.ntaps : 0) + t.g * p.ntaps;
         const int ncoord = t.nt * p.block_n;
-        if (gemm_steps) {
-          // GEMM-shaped K loop (1x1 layers, every Linear of the transformers and the ViTs): one activation and one weight
-          // tile per step and nothing else to decide.  The general loop below costs ~250 instructions per step (tap tables,
-          // unrolled tap counts) - ~850 cycles of this single thread against the 384-512 cycles the four MMAs of a step
-          // take: the PRODUCER bounded these layers (tensor pipe 39 % busy, ncu source page of the ViT in_proj GEMM).
-          const int xa = xin + p.col_dx[t.g][0], ya = yin + p.col_dy0[t.g][0], zt = zbase + p.col_tap[t.g][0];
+        if (lean_steps) {
+          // Streamed-weight K loops with at most three loads per chunk and three taps per load (1x1 layers and every Linear of
+          // the transformers and the ViTs: one load, one tap; 3x3 layers: three column loads of three taps): the tap tables
+          // are read ONCE per tile and the loops are fully unrolled.  The general loop below costs ~250 instructions per
+          // load - ~850 cycles of this single thread against the 384-512 cycles the four MMAs of a GEMM step take: the
+          // PRODUCER bounded those layers (tensor pipe 39 % busy, ncu source page of the ViT in_proj GEMM).
+          int xa[3], ya[3], zt[3][3];
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            xa[j] = xin + p.col_dx[t.g][j];
+            ya[j] = yin + p.col_dy0[t.g][j];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) zt[j][i] = zbase + p.col_tap[t.g][j * p.ndy + i];
+          }
           const int wrow = ncoord + (cta2 ? static_cast<int>(crank) * half_n : 0);
           for (int ck = 0; ck < chunks; ++ck) {
             const bool first = ck < p.chunks0;
             const CUtensorMap* mapA = first ? &mapA0 : &mapA1;
             const int ccoord = (first ? ck : ck - p.chunks0) * kChunkK;
-            mbar_wait(&empty[stage], phase ^ 1);
-            uint8_t* sa = ring + static_cast<size_t>(stage) * stage_bytes;
-            if constexpr (cta2) {
-              const uint32_t fb = full_lead + 8u * stage;
-              if (crank == 0) mbar_arrive_expect_tx(&full[stage], 2u * main_tx);
-              tma_load_4d_pair(sa, mapA, fb, ccoord, xa, ya, t.n);
-              tma_load_3d_pair(sa + p.a_slot, &mapW, fb, ck * kChunkK, wrow, zt);
-            } else {
-              mbar_arrive_expect_tx(&full[stage], main_tx);
-              tma_load_4d(sa, mapA, &full[stage], ccoord, xa, ya, t.n);
-              tma_load_3d(sa + p.a_slot, &mapW, &full[stage], ck * kChunkK, wrow, zt);
-            }
-            if (++stage == p.stages) {
-              stage = 0;
-              phase ^= 1;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+              if (j < p.ncols) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                uint8_t* sa = ring + static_cast<size_t>(stage) * stage_bytes;
+                if constexpr (cta2) {
+                  const uint32_t fb = full_lead + 8u * stage;
+                  if (crank == 0) mbar_arrive_expect_tx(&full[stage], 2u * main_tx);
+                  tma_load_4d_pair(sa, mapA, fb, ccoord, xa[j], ya[j], t.n);
+#pragma unroll
+                  for (int i = 0; i < 3; ++i)
+                    if (i < p.ndy)
+                      tma_load_3d_pair(sa + p.a_slot + static_cast<size_t>(i) * p.b_bytes, &mapW, fb, ck * kChunkK, wrow, zt[j][i]);
+                } else {
+                  mbar_arrive_expect_tx(&full[stage], main_tx);
+                  tma_load_4d(sa, mapA, &full[stage], ccoord, xa[j], ya[j], t.n);
+#pragma unroll
+                  for (int i = 0; i < 3; ++i)
+                    if (i < p.ndy)
+                      tma_load_3d(sa + p.a_slot + static_cast<size_t>(i) * p.b_bytes, &mapW, &full[stage], ck * kChunkK, wrow,
+                                  zt[j][i]);
+                }
+                if (++stage == p.stages) {
+                  stage = 0;
+                  phase ^= 1;
+                }
+              }
             }
           }
           continue;
@@ -795,9 +826,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
               const uint32_t fb = full_lead + 8u * stage;
               if (crank == 0) mbar_arrive_expect_tx(&full[stage], 2u * main_tx);
               tma_load_4d_pair(sa, mapA, fb, ccoord, xin + p.col_dx[t.g][j], yin + p.col_dy0[t.g][j], t.n);
-              for (int i = 0; i < p.ndy; ++i)
-                tma_load_3d_pair(sa + p.a_slot + static_cast<size_t>(i) * p.b_bytes, &mapW, fb, ck * kChunkK,
-                                 ncoord + static_cast<int>(crank) * half_n, zbase + p.col_tap[t.g][j * p.ndy + i]);
+              if (!b_resident)
+                for (int i = 0; i < p.ndy; ++i)
+                  tma_load_3d_pair(sa + p.a_slot + static_cast<size_t>(i) * p.b_bytes, &mapW, fb, ck * kChunkK,
+                                   ncoord + static_cast<int>(crank) * half_n, zbase + p.col_tap[t.g][j * p.ndy + i]);
               if (++stage == p.stages) {
                 stage = 0;
                 phase ^= 1;
@@ -884,7 +916,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           //   odd  chunk, pair i - 1 : rows [128, 192) = W(0), N = 64 into columns [0, cout)      (left of pixel 2i)
           //   even chunk, pair i + 1 : rows [0, 64)    = W(2), N = 64 into columns [cout, 2 cout)  (right of pixel 2i+1)
           // = 224 instead of 288 fetch-bound cycles per 256 output pixels and K step.
-          const uint32_t idesc_half = make_idesc_bf16(kTileM, p.block_n >> 1);
+          // CTA-pair build (cta_group::2, M = 256): CTA r supplies the B rows of output columns [N/2 r, +N/2), so each CTA
+          // holds its own 192-row block per (slice, ky), [E; O; S0; S2] =
+          //   rank 0: [W(1); W(2); W(0)[0:32]; W(2)[0:32]]     rank 1: [W(0); W(1); W(0)[32:64]; W(2)[32:64]]
+          // E / O = this CTA's half of the even / odd centre window, S0 / S2 = its half of the W(0) / W(2) side windows
+          // (ops.pack_conv_pair).  Per CTA and MMA the operand fetch drops from 4 + 4 KB to 4 + 2 KB (N = 128) and from
+          // 4 + 2 to 4 + 1 KB (N = 64): the centre MMAs become math-bound, and the shared-memory pipe has room for the TMA
+          // writes and the epilogue's staging traffic.
+          const uint32_t idesc_half = make_idesc_bf16(cta2 ? 2 * kTileM : kTileM, p.block_n >> 1);
           const uint32_t half_cols = p.block_n >> 1;
           // (half_cols rows per kx block: 64 for the ResBlock layers, 16 for final_conv; every window starts on a multiple
           // of 8 rows = one 1024-byte swizzle atom)
@@ -905,22 +944,37 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
                 adesc_c |= static_cast<uint64_t>((a_c >> 3) & 7) << 49;
                 adesc_s |= static_cast<uint64_t>((a_s >> 3) & 7) << 49;
               }
-              const uint64_t bdesc_c = desc_fixed | (odd ? wb : wb + rows64_lo);
-              const uint64_t bdesc_s = desc_fixed | (odd ? wb + 2 * rows64_lo : wb);
+              const uint64_t bdesc_c = desc_fixed | (cta2 ? (odd ? wb + rows64_lo : wb) : (odd ? wb : wb + rows64_lo));
+              const uint64_t bdesc_s = desc_fixed | (cta2 ? (odd ? wb + 2 * rows64_lo : wb + 2 * rows64_lo + (rows64_lo >> 1))
+                                                          : (odd ? wb + 2 * rows64_lo : wb));
               const uint32_t d_s = d_tmem + (odd ? 0u : half_cols);
               if (elect_one()) {
-                umma_bf16(d_tmem, adesc_c, bdesc_c, idesc, accumulate);
-                umma_bf16(d_tmem, adesc_c + 2, bdesc_c + 2, idesc, 1u);
-                umma_bf16(d_tmem, adesc_c + 4, bdesc_c + 4, idesc, 1u);
-                umma_bf16(d_tmem, adesc_c + 6, bdesc_c + 6, idesc, 1u);
-                umma_bf16(d_s, adesc_s, bdesc_s, idesc_half, 1u);
-                umma_bf16(d_s, adesc_s + 2, bdesc_s + 2, idesc_half, 1u);
-                umma_bf16(d_s, adesc_s + 4, bdesc_s + 4, idesc_half, 1u);
-                umma_bf16(d_s, adesc_s + 6, bdesc_s + 6, idesc_half, 1u);
+                if constexpr (cta2) {
+                  umma_bf16_pair(d_tmem, adesc_c, bdesc_c, idesc, accumulate);
+                  umma_bf16_pair(d_tmem, adesc_c + 2, bdesc_c + 2, idesc, 1u);
+                  umma_bf16_pair(d_tmem, adesc_c + 4, bdesc_c + 4, idesc, 1u);
+                  umma_bf16_pair(d_tmem, adesc_c + 6, bdesc_c + 6, idesc, 1u);
+                  umma_bf16_pair(d_s, adesc_s, bdesc_s, idesc_half, 1u);
+                  umma_bf16_pair(d_s, adesc_s + 2, bdesc_s + 2, idesc_half, 1u);
+                  umma_bf16_pair(d_s, adesc_s + 4, bdesc_s + 4, idesc_half, 1u);
+                  umma_bf16_pair(d_s, adesc_s + 6, bdesc_s + 6, idesc_half, 1u);
+                } else {
+                  umma_bf16(d_tmem, adesc_c, bdesc_c, idesc, accumulate);
+                  umma_bf16(d_tmem, adesc_c + 2, bdesc_c + 2, idesc, 1u);
+                  umma_bf16(d_tmem, adesc_c + 4, bdesc_c + 4, idesc, 1u);
+                  umma_bf16(d_tmem, adesc_c + 6, bdesc_c + 6, idesc, 1u);
+                  umma_bf16(d_s, adesc_s, bdesc_s, idesc_half, 1u);
+                  umma_bf16(d_s, adesc_s + 2, bdesc_s + 2, idesc_half, 1u);
+                  umma_bf16(d_s, adesc_s + 4, bdesc_s + 4, idesc_half, 1u);
+                  umma_bf16(d_s, adesc_s + 6, bdesc_s + 6, idesc_half, 1u);
+                }
               }
               accumulate = 1u;
             }
-            if (elect_one()) umma_commit(&empty[stage]);
+            if (elect_one()) {
+              if constexpr (cta2) umma_commit_pair(&empty[stage]);
+              else umma_commit(&empty[stage]);
+            }
             if (++stage == p.stages) {
               stage = 0;
               phase ^= 1;

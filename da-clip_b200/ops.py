@@ -297,7 +297,17 @@ def pack_conv_pair(weight):
     cout, cin, kh, kw = weight.shape
     assert (kh, kw) == (3, 3) and cin % 64 == 0 and cout in (16, 64), "64 output channels, or final_conv padded to 16"
     w = torch.stack([torch.cat([weight[:, :, ky, 2], weight[:, :, ky, 1], weight[:, :, ky, 0]], 0) for ky in range(3)])
-    return w.to(torch.bfloat16).contiguous()
+    if cout != 64:
+        return w.to(torch.bfloat16).contiguous()
+    # ... followed by the two per-rank layouts of the CTA-pair build (conv_kernel.cuh, cta_group::2: CTA r supplies the weight
+    # rows of output columns [64 r, 64 r + 64) of the centre windows and rows [32 r, 32 r + 32) of the side windows):
+    #   rank 0: [W(1); W(2); W(0)[0:32]; W(2)[0:32]]      rank 1: [W(0); W(1); W(0)[32:64]; W(2)[32:64]]
+    blocks = [w]
+    for r in (0, 1):
+        blocks.append(torch.stack([torch.cat([weight[:, :, ky, 1 - r], weight[:, :, ky, 2 - r],
+                                              weight[32 * r:32 * r + 32, :, ky, 0], weight[32 * r:32 * r + 32, :, ky, 2]], 0)
+                                   for ky in range(3)]))
+    return torch.cat(blocks, 0).to(torch.bfloat16).contiguous()
 
 
 def pair_eligible(pw, cout, c0, c1, W):
@@ -331,7 +341,7 @@ class PairConvPlan(ConvPlan):
         d.weight, d.cout, d.cout_pad, d.per_image_w = wpair.data_ptr(), bn, bn, 0
         d.block_n, d.tile_h, d.tile_w = bn, 16, 8
         assert wpair.shape[-2] == 3 * bn // 2
-        d.epi, d.act, d.halo, d.pair = L.EPI_PLAIN, act, 1, 1
+        d.epi, d.act, d.halo, d.pair = L.EPI_PLAIN, act, 1, (2 if wpair.shape[0] == 9 else 1)
         if film is not None:
             d.film, d.film_ld, d.film_off = film.data_ptr(), film.shape[-1], film_off
         if res is not None:

@@ -31,6 +31,17 @@ def make(case, cta2):
         res = CACHE.setdefault(("r", case), rnd(B, H, W, cout).to(torch.bfloat16))
         out = torch.zeros(B, H, W, cout, device="cuda", dtype=torch.bfloat16)
         plan = ops.ConvPlan(x, cin, ops.pack_conv(w), out, B=B, H=H, W=W, act=L.ACT_SILU, res=res)
+    elif kind in ("pair", "pair_res", "pair_cat"):
+        w = CACHE.setdefault(("w", case), rnd(cout, cin, 3, 3, scale=(9 * cin) ** -0.5))
+        film = CACHE.setdefault(("f", case), rnd(B, 2 * cout, scale=0.1))
+        res = CACHE.setdefault(("r", case), rnd(B, H, W, cout).to(torch.bfloat16))
+        out = torch.zeros(B, H, W, cout, device="cuda", dtype=torch.bfloat16)
+        a = x[..., :64].contiguous()
+        s1 = x[..., 64:].contiguous() if cin == 128 else None
+        if kind == "pair_res":
+            plan = ops.PairConvPlan(a, ops.pack_conv_pair(w), out, B=B, H=H, W=W, act=L.ACT_SILU, res=res)
+        else:
+            plan = ops.PairConvPlan(a, ops.pack_conv_pair(w), out, B=B, H=H, W=W, src1=s1, act=L.ACT_SILU, film=film)
     elif kind == "geglu":
         w = CACHE.setdefault(("w", case), rnd(cout, cin, scale=cin ** -0.5))
         b = CACHE.setdefault(("b", case), rnd(cout))
@@ -60,6 +71,11 @@ CASES = {
     "l2_256": ("3x3", 16, 64, 64, 256, 256),
     "geglu": ("geglu", 16, 32, 32, 512, 4096),
     "odd": ("3x3", 2, 40, 24, 128, 128),
+    "p64": ("pair", 16, 256, 256, 64, 64),
+    "p64res": ("pair_res", 16, 256, 256, 64, 64),
+    "p128": ("pair_cat", 16, 256, 256, 128, 64),
+    "p64l1": ("pair", 16, 128, 128, 64, 64),
+    "p64small": ("pair", 2, 40, 24, 64, 64),
 }
 for name in (sys.argv[1:] or list(CASES)):
     case = CASES[name]
