@@ -223,7 +223,7 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
   const char* cta2_env = getenv("DAC_CTA2");
   const bool cta2_on = cta2_env ? atoi(cta2_env) != 0 : kCta2Default;
   // (pixel-pair layers: only when the weight tensor carries the per-rank layouts, dac_conv_desc.pair == 2)
-  const bool cta2 = cta2_on && !fused_res && !d->per_image_w && d->ngroups == 1 && !nchw && d->epi != DAC_EPI_KVCTX &&
+  const bool cta2 = cta2_on && !(fused_res && getenv("DAC_NO_CTA2_SKIP")) && !d->per_image_w && d->ngroups == 1 && !nchw && d->epi != DAC_EPI_KVCTX &&
                     d->epi != DAC_EPI_QKV && (k.m_tiles % 2) == 0 && (d->block_n % 32) == 0 && d->block_n >= 64 &&
                     !d->stats_out &&
                     (d->pair ? (d->pair == 2 && !getenv("DAC_NO_CTA2_PAIR")) : (!resident && !d->halo));
@@ -234,6 +234,7 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
       pl->kernel = kernel2;
       k.cta2 = 1;
       if (!d->pair) k.b_bytes >>= 1;   // per CTA: half of the block_n weight rows of a K step
+      k.r_b_bytes >>= 1;               // ... and half of the fused skip conv's weight rows
     }
   }
   if (d->pair) {   // one 192-row block per (64-channel source slice, ky), always resident
@@ -373,7 +374,7 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
       const int rrows = d->pair ? 64 : d->cout_pad;
       cuuint64_t dims[3] = {(cuuint64_t)rct, (cuuint64_t)rrows, 1};
       cuuint64_t strides[2] = {(cuuint64_t)rct * 2, (cuuint64_t)rrows * rct * 2};
-      cuuint32_t box[3] = {(cuuint32_t)kChunkK, (cuuint32_t)(d->pair ? 64 : d->block_n), 1};
+      cuuint32_t box[3] = {(cuuint32_t)kChunkK, (cuuint32_t)((d->pair ? 64 : d->block_n) / (k.cta2 ? 2 : 1)), 1};
       cuuint32_t estr[3] = {1, 1, 1};
       CUresult r = enc(&pl->mapWR, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(d->rweight), dims, strides,
                        box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,

@@ -853,6 +853,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         for (int rk = 0; rk < r_chunks; ++rk) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = ring + static_cast<size_t>(stage) * stage_bytes;
+          if constexpr (cta2) {
+            // CTA-pair build: this CTA's source tile and its half of the skip weight rows (r_b_bytes describes the half)
+            const uint32_t fb = full_lead + 8u * stage;
+            const int wr_rows = static_cast<int>(p.r_b_bytes >> 7);      // rows of 128 B
+            if (crank == 0) mbar_arrive_expect_tx(&full[stage], 2u * (p.r_a_bytes + p.r_b_bytes));
+            if (rk < p.r_chunks0) tma_load_4d_pair(sa, &mapR0, fb, rk * kChunkK, xin, yin, t.n);
+            else tma_load_4d_pair(sa, &mapR1, fb, (rk - p.r_chunks0) * kChunkK, xin, yin, t.n);
+            tma_load_3d_pair(sa + p.r_a_bytes, &mapWR, fb, (p.pair ? (rk >> 1) : rk) * kChunkK, static_cast<int>(crank) * wr_rows, 0);
+            if (++stage == p.stages) {
+              stage = 0;
+              phase ^= 1;
+            }
+            continue;
+          }
           mbar_arrive_expect_tx(&full[stage], p.r_a_bytes + p.r_b_bytes);
           if (rk < p.r_chunks0) tma_load_4d(sa, &mapR0, &full[stage], rk * kChunkK, xin, yin, t.n);
           else tma_load_4d(sa, &mapR1, &full[stage], (rk - p.r_chunks0) * kChunkK, xin, yin, t.n);
@@ -1059,14 +1073,22 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           const uint64_t bdesc = desc_fixed | (a0 + (p.r_a_bytes >> 4));
           // pair mode: the 1x1 conv of the even pixels lands in the first half of the second accumulator, odd: second half
           const uint32_t d_r = d_tmem + p.block_n + ((p.pair && (rk & 1)) ? (p.block_n >> 1) : 0);
-          const uint32_t idesc_r = p.pair ? make_idesc_bf16(kTileM, p.block_n >> 1) : idesc;
+          const uint32_t idesc_r = p.pair ? make_idesc_bf16(cta2 ? 2 * kTileM : kTileM, p.block_n >> 1) : idesc;
           const uint32_t acc_r = p.pair ? (rk >= 2 ? 1u : 0u) : (rk ? 1u : 0u);
           if (elect_one()) {
-            umma_bf16(d_r, adesc, bdesc, idesc_r, acc_r);
-            umma_bf16(d_r, adesc + 2, bdesc + 2, idesc_r, 1u);
-            umma_bf16(d_r, adesc + 4, bdesc + 4, idesc_r, 1u);
-            umma_bf16(d_r, adesc + 6, bdesc + 6, idesc_r, 1u);
-            umma_commit(&empty[stage]);
+            if constexpr (cta2) {
+              umma_bf16_pair(d_r, adesc, bdesc, idesc_r, acc_r);
+              umma_bf16_pair(d_r, adesc + 2, bdesc + 2, idesc_r, 1u);
+              umma_bf16_pair(d_r, adesc + 4, bdesc + 4, idesc_r, 1u);
+              umma_bf16_pair(d_r, adesc + 6, bdesc + 6, idesc_r, 1u);
+              umma_commit_pair(&empty[stage]);
+            } else {
+              umma_bf16(d_r, adesc, bdesc, idesc_r, acc_r);
+              umma_bf16(d_r, adesc + 2, bdesc + 2, idesc_r, 1u);
+              umma_bf16(d_r, adesc + 4, bdesc + 4, idesc_r, 1u);
+              umma_bf16(d_r, adesc + 6, bdesc + 6, idesc_r, 1u);
+              umma_commit(&empty[stage]);
+            }
           }
           if (++stage == p.stages) {
             stage = 0;

@@ -42,6 +42,19 @@ def make(case, cta2):
             plan = ops.PairConvPlan(a, ops.pack_conv_pair(w), out, B=B, H=H, W=W, act=L.ACT_SILU, res=res)
         else:
             plan = ops.PairConvPlan(a, ops.pack_conv_pair(w), out, B=B, H=H, W=W, src1=s1, act=L.ACT_SILU, film=film)
+    elif kind in ("pair_skip", "skip"):
+        w = CACHE.setdefault(("w", case), rnd(cout, cin, 3, 3, scale=(9 * cin) ** -0.5))
+        rc = 128 if kind == "pair_skip" else cout + cout // 2
+        wr = CACHE.setdefault(("wr", case), rnd(cout, rc, scale=rc ** -0.5))
+        r0 = CACHE.setdefault(("r0", case), rnd(B, H, W, cout).to(torch.bfloat16))
+        r1 = CACHE.setdefault(("r1", case), rnd(B, H, W, rc - cout).to(torch.bfloat16))
+        out = torch.zeros(B, H, W, cout, device="cuda", dtype=torch.bfloat16)
+        if kind == "pair_skip":
+            plan = ops.PairConvPlan(x, ops.pack_conv_pair(w), out, B=B, H=H, W=W, act=L.ACT_SILU, rsrc0=r0, rsrc1=r1,
+                                    rweight=ops.pack_linear(wr))
+        else:
+            plan = ops.ConvPlan(x, cin, ops.pack_conv(w), out, B=B, H=H, W=W, act=L.ACT_SILU, rsrc0=r0, rc0=cout, rsrc1=r1,
+                                rc1=rc - cout, rweight=ops.pack_linear(wr))
     elif kind == "geglu":
         w = CACHE.setdefault(("w", case), rnd(cout, cin, scale=cin ** -0.5))
         b = CACHE.setdefault(("b", case), rnd(cout))
@@ -76,6 +89,8 @@ CASES = {
     "p128": ("pair_cat", 16, 256, 256, 128, 64),
     "p64l1": ("pair", 16, 128, 128, 64, 64),
     "p64small": ("pair", 2, 40, 24, 64, 64),
+    "p64skip": ("pair_skip", 16, 256, 256, 64, 64),
+    "skip128": ("skip", 16, 128, 128, 128, 128),
 }
 for name in (sys.argv[1:] or list(CASES)):
     case = CASES[name]
