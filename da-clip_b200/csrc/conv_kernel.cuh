@@ -756,12 +756,61 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       const uint32_t full_lead = cta2 ? mapa_u32(smem_u32(full), 0) : 0u;   // the leader's full[0] (shared::cluster address)
       const int half_n = p.block_n >> 1;
       const bool lean_steps = !b_resident && p.ncols <= 3 && p.ndy <= 3 && r_chunks == 0 && !p.pair;
+      const bool tap_steps = p.ndy == 1 && p.ncols > 3 && p.ncols <= 16 && r_chunks == 0 && !p.pair && !p.halo;
       for (int tile = tile_begin; tile < tile_end; ++tile) {
         const TileCoord t = decode_tile(p, tile_of(tile));
         if (b_resident && t.g != w_group) load_group_weights(t.g);
         const int xin = t.x0 * p.stride, yin = t.y0 * p.stride;
         const int zbase = (p.per_image_w ? t.n * p.ngroups * p.ntaps : 0) + t.g * p.ntaps;
         const int ncoord = t.nt * p.block_n;
+        if (tap_steps) {
+          // One tap per load and up to 16 loads per chunk (the 4x4 stride-2 Downsample convs: 16 strided loads of four
+          // N <= 128 MMAs each, i.e. 192-256 tensor cycles per load - the ~850-cycle general loop bounded them): the three
+          // tap tables of the tile's group travel in registers as packed bytes.
+          uint32_t dxw[4], dyw[4], tpw[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            dxw[q] = dyw[q] = tpw[q] = 0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              dxw[q] |= static_cast<uint32_t>(static_cast<uint8_t>(p.col_dx[t.g][4 * q + e])) << (8 * e);
+              dyw[q] |= static_cast<uint32_t>(static_cast<uint8_t>(p.col_dy0[t.g][4 * q + e])) << (8 * e);
+              tpw[q] |= static_cast<uint32_t>(static_cast<uint8_t>(p.col_tap[t.g][4 * q + e])) << (8 * e);
+            }
+          }
+          const int wrow = ncoord + (cta2 ? static_cast<int>(crank) * half_n : 0);
+          for (int ck = 0; ck < chunks; ++ck) {
+            const bool first = ck < p.chunks0;
+            const CUtensorMap* mapA = first ? &mapA0 : &mapA1;
+            const int ccoord = (first ? ck : ck - p.chunks0) * kChunkK;
+#pragma unroll 4
+            for (int j = 0; j < p.ncols; ++j) {
+              const int sh = 8 * (j & 3);
+              const uint32_t wx = j < 8 ? (j < 4 ? dxw[0] : dxw[1]) : (j < 12 ? dxw[2] : dxw[3]);
+              const uint32_t wy = j < 8 ? (j < 4 ? dyw[0] : dyw[1]) : (j < 12 ? dyw[2] : dyw[3]);
+              const uint32_t wt = j < 8 ? (j < 4 ? tpw[0] : tpw[1]) : (j < 12 ? tpw[2] : tpw[3]);
+              const int xa = xin + static_cast<int8_t>(wx >> sh), ya = yin + static_cast<int8_t>(wy >> sh);
+              const int zt = zbase + static_cast<int8_t>(wt >> sh);
+              mbar_wait(&empty[stage], phase ^ 1);
+              uint8_t* sa = ring + static_cast<size_t>(stage) * stage_bytes;
+              if constexpr (cta2) {
+                const uint32_t fb = full_lead + 8u * stage;
+                if (crank == 0) mbar_arrive_expect_tx(&full[stage], 2u * main_tx);
+                tma_load_4d_pair(sa, mapA, fb, ccoord, xa, ya, t.n);
+                if (!b_resident) tma_load_3d_pair(sa + p.a_slot, &mapW, fb, ck * kChunkK, wrow, zt);
+              } else {
+                mbar_arrive_expect_tx(&full[stage], main_tx);
+                tma_load_4d(sa, mapA, &full[stage], ccoord, xa, ya, t.n);
+                if (!b_resident) tma_load_3d(sa + p.a_slot, &mapW, &full[stage], ck * kChunkK, wrow, zt);
+              }
+              if (++stage == p.stages) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+          }
+          continue;
+        }
         if (lean_steps) {
           // Streamed-weight K loops with at most three loads per chunk and three taps per load (1x1 layers and every Linear of
           // the transformers and the ViTs: one load, one tap; 3x3 layers: three column loads of three taps): the tap tables
@@ -994,15 +1043,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
               phase ^= 1;
             }
           }
-        } else if (!b_resident && p.ncols == 1 && p.ndy == 1) {
-          // GEMM-shaped K loop: one (activation, weight) tile pair per step - see the producer
+        } else if (p.ndy == 1 && !p.halo) {
+          // One (activation, weight) tile pair per step - GEMM-shaped K loops and the one-tap-per-load convs; see the producer
           const uint32_t t_off = p.tap_off[0];
-          for (int ck = 0; ck < chunks; ++ck) {
+          const int steps = chunks * p.ncols;
+          for (int ck = 0; ck < steps; ++ck) {
             mbar_wait(&full[stage], phase);
             tc_fence_after();
             const uint32_t a0 = ring_lo + stage * stage_lo;
             const uint64_t adesc = desc_fixed_a | (a0 + t_off);
-            const uint64_t bdesc = desc_fixed | (a0 + a_lo);
+            const uint64_t bdesc = desc_fixed | (b_resident ? b_run : a0 + a_lo);
+            b_run += b_lo;
             if (elect_one()) {
               if constexpr (cta2) {
                 umma_bf16_pair(d_tmem, adesc, bdesc, idesc, accumulate);
