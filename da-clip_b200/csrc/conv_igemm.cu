@@ -288,7 +288,7 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
   // are the shared-memory-bound ones); alignment of the float4 parameter loads needs cout % 4 == 0 (validated above)
   k.film_tmem = (d->film && !fused_res && d->block_n % 32 == 0 &&
                  d->block_n + 2 * (k.film_cols ? k.film_cols : d->block_n) <= (int)kAccStride &&
-                 (k.pair || !getenv("DAC_NO_FILM_TMEM"))) ? 1 : 0;
+                 !getenv("DAC_NO_FILM_TMEM")) ? 1 : 0;
   k.stg_bytes = stg_bytes;
   k.dbg = getenv("DAC_EPI_DEBUG") ? atoi(getenv("DAC_EPI_DEBUG")) : 0;   // profiling only: wrong results by design
   k.stg_count = stg_bytes ? 2 : 1;   // one staging tile per epilogue group

@@ -763,6 +763,31 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         const int xin = t.x0 * p.stride, yin = t.y0 * p.stride;
         const int zbase = (p.per_image_w ? t.n * p.ngroups * p.ntaps : 0) + t.g * p.ntaps;
         const int ncoord = t.nt * p.block_n;
+        if (b_resident && p.ncols == 1) {
+          // Resident weights and one (haloed) activation load per chunk - the pixel-pair and halo layers of levels 0-1: the
+          // main K loop issues nothing but that load (the fused skip conv's loads follow below)
+          const int xa = xin + p.col_dx[t.g][0], ya = yin + p.col_dy0[t.g][0];
+          for (int ck = 0; ck < chunks; ++ck) {
+            const bool first = ck < p.chunks0;
+            const CUtensorMap* mapA = first ? &mapA0 : &mapA1;
+            const int ccoord = (first ? ck : ck - p.chunks0) * kChunkK;
+            mbar_wait(&empty[stage], phase ^ 1);
+            uint8_t* sa = ring + static_cast<size_t>(stage) * stage_bytes;
+            if (p.dbg & 8) {          // profiling only (DAC_EPI_DEBUG & 8): no activation loads - the MMA / barrier skeleton alone
+              if (crank == 0) mbar_arrive(&full[stage]);
+            } else if constexpr (cta2) {
+              if (crank == 0) mbar_arrive_expect_tx(&full[stage], 2u * main_tx);
+              tma_load_4d_pair(sa, mapA, full_lead + 8u * stage, ccoord, xa, ya, t.n);
+            } else {
+              mbar_arrive_expect_tx(&full[stage], main_tx);
+              tma_load_4d(sa, mapA, &full[stage], ccoord, xa, ya, t.n);
+            }
+            if (++stage == p.stages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        } else
         if (tap_steps) {
           // One tap per load and up to 16 loads per chunk (the 4x4 stride-2 Downsample convs: 16 strided loads of four
           // N <= 128 MMAs each, i.e. 192-256 tensor cycles per load - the ~850-cycle general loop bounded them): the three
@@ -861,6 +886,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           }
           continue;
         }
+        if (!(b_resident && p.ncols == 1))
         for (int ck = 0; ck < chunks; ++ck) {
           const CUtensorMap* mapA = ck < p.chunks0 ? &mapA0 : &mapA1;
           const int ccoord = (ck < p.chunks0 ? ck : ck - p.chunks0) * kChunkK;
@@ -1221,9 +1247,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           film_key = key;
           asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");
           const float* src = p.film + static_cast<long long>(t.n) * p.film_ld + p.film_off + t.nt * p.block_n;
+          // (pair mode: the 64-entry vectors serve both pixels of the pair - replicated across the two column halves)
+          const int fcout = p.film_cols ? p.film_cols : p.cout;
           for (int i = gthread; i < 2 * p.block_n; i += 128) {
             const int c = i < p.block_n ? i : i - p.block_n;
-            film_g[i] = i < p.block_n ? __ldg(src + c) + 1.0f : __ldg(src + p.cout + c);
+            const int cc = p.film_cols ? (c & (p.film_cols - 1)) : c;
+            film_g[i] = i < p.block_n ? __ldg(src + cc) + 1.0f : __ldg(src + fcout + cc);
           }
           asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");
         }
