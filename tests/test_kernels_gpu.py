@@ -680,6 +680,83 @@ def test_prenorm_folded_into_qkv(ops, gen, B, H, W, C):
                       abs_=4e-3)
 
 
+# ---------------------------------------------------------------------------------------------- CTA-pair mode
+@pytest.mark.parametrize("kind,B,H,W,cin,cout", [
+    ("1x1", 2, 32, 32, 512, 512), ("1x1", 1, 1, 1280, 768, 2304), ("f32", 1, 1, 1280, 768, 768),
+    ("3x3", 2, 32, 32, 256, 256), ("3x3", 4, 64, 64, 128, 128), ("geglu", 2, 32, 32, 512, 4096),
+    ("pair", 2, 64, 64, 64, 64), ("pair", 2, 64, 64, 128, 64), ("pair_res", 2, 64, 64, 64, 64),
+    ("pair_skip", 2, 64, 64, 64, 64), ("skip", 2, 64, 64, 128, 128), ("down", 2, 64, 64, 64, 128)])
+def test_cta_pair_mode_is_bit_identical(ops, gen, monkeypatch, kind, B, H, W, cin, cout):
+    """conv_igemm_kernel<..., CTA2 = true> (tcgen05.mma.cta_group::2 on 2-CTA clusters: every CTA loads its own activation tile
+    and half of the weight rows, the leader issues M = 256 MMAs for both) against the 1-CTA build of the same layer on the same
+    inputs: the accumulation order of every output element is the same, so the outputs must agree bit for bit - streamed
+    weights (1x1 / Linear / 3x3 / GEGLU / fp32 residual stream), the pixel-pair layers with their per-rank weight layouts,
+    fused skip convs; and the 1-CTA result against the fp32 reference of the op (F.conv2d / F.linear)."""
+    x = bf(rnd(gen, B, H, W, cin))
+    outs = []
+    for cta2 in ("0", "1"):
+        monkeypatch.setenv("DAC_CTA2", cta2)
+        ref = None
+        if kind in ("1x1", "f32"):
+            w, b = rnd(gen.manual_seed(11), cout, cin) * cin ** -0.5, rnd(gen, cout)
+            if kind == "1x1":
+                out = torch.zeros(B, H, W, cout, device="cuda", dtype=torch.bfloat16)
+                plan = ops.ConvPlan(x, cin, ops.pack_linear(w), out, B=B, H=H, W=W, bias=b, act=ops.L.ACT_GELU)
+                ref = F.gelu(F.linear(x.float(), bf(w).float(), b))
+            else:
+                out = rnd(gen, B, H, W, cout)
+                ref = out + F.linear(x.float(), bf(w).float(), b)
+                plan = ops.ConvPlan(x, cin, ops.pack_linear(w), None, B=B, H=H, W=W, bias=b, res_f32=out, out_f32=out)
+        elif kind == "geglu":
+            w, b = rnd(gen.manual_seed(11), cout, cin) * cin ** -0.5, rnd(gen, cout)
+            pw, bp = ops.pack_geglu(w, b)
+            out = torch.zeros(B, H, W, cout // 2, device="cuda", dtype=torch.bfloat16)
+            plan = ops.ConvPlan(x, cin, pw, out, B=B, H=H, W=W, epi=ops.L.EPI_GEGLU, bias=bp, block_n=256)
+            y = F.linear(x.float(), bf(w).float(), b)
+            ref = y[..., :cout // 2] * F.gelu(y[..., cout // 2:])
+        elif kind == "down":
+            w, b = rnd(gen.manual_seed(11), cout, cin, 4, 4) * (16 * cin) ** -0.5, rnd(gen, cout)
+            out = torch.zeros(B, H // 2, W // 2, cout, device="cuda", dtype=torch.bfloat16)
+            plan = ops.ConvPlan(x, cin, ops.pack_conv(w, stride=2, pad=1), out, B=B, H=H, W=W, bias=b)
+            ref = F.conv2d(x.float().permute(0, 3, 1, 2), bf(w).float(), b, stride=2, padding=1).permute(0, 2, 3, 1)
+        else:
+            w = rnd(gen.manual_seed(11), cout, cin, 3, 3) * (9 * cin) ** -0.5
+            film = rnd(gen, B, 2 * cout) * 0.1
+            res = bf(rnd(gen, B, H, W, cout))
+            out = torch.zeros(B, H, W, cout, device="cuda", dtype=torch.bfloat16)
+            conv = F.conv2d(x.float().permute(0, 3, 1, 2), bf(w).float(), padding=1).permute(0, 2, 3, 1)
+            if kind == "3x3":
+                plan = ops.ConvPlan(x, cin, ops.pack_conv(w), out, B=B, H=H, W=W, act=ops.L.ACT_SILU, film=film)
+                ref = F.silu(conv * (film[:, None, None, :cout] + 1) + film[:, None, None, cout:])
+            elif kind == "pair":
+                a, s1 = x[..., :64].contiguous(), (x[..., 64:].contiguous() if cin == 128 else None)
+                plan = ops.PairConvPlan(a, ops.pack_conv_pair(w), out, B=B, H=H, W=W, src1=s1, act=ops.L.ACT_SILU, film=film)
+                ref = F.silu(conv * (film[:, None, None, :cout] + 1) + film[:, None, None, cout:])
+            elif kind == "pair_res":
+                plan = ops.PairConvPlan(x, ops.pack_conv_pair(w), out, B=B, H=H, W=W, act=ops.L.ACT_SILU, res=res)
+                ref = F.silu(conv) + res.float()
+            else:
+                rc = 128 if kind == "pair_skip" else cout + cout // 2
+                wr = rnd(gen, cout, rc) * rc ** -0.5
+                r0, r1 = bf(rnd(gen, B, H, W, cout)), bf(rnd(gen, B, H, W, rc - cout))
+                skip = F.linear(torch.cat([r0, r1], -1).float(), bf(wr).float())
+                ref = F.silu(conv) + skip
+                if kind == "pair_skip":
+                    plan = ops.PairConvPlan(x, ops.pack_conv_pair(w), out, B=B, H=H, W=W, act=ops.L.ACT_SILU, rsrc0=r0,
+                                            rsrc1=r1, rweight=ops.pack_linear(wr))
+                else:
+                    plan = ops.ConvPlan(x, cin, ops.pack_conv(w), out, B=B, H=H, W=W, act=ops.L.ACT_SILU, rsrc0=r0, rc0=cout,
+                                        rsrc1=r1, rc1=rc - cout, rweight=ops.pack_linear(wr))
+        plan.run()
+        torch.cuda.synchronize()
+        outs.append((out.clone(), ref))
+    assert torch.equal(outs[0][0], outs[1][0]), (outs[0][0].float() - outs[1][0].float()).abs().max().item()
+    if outs[0][0].dtype == torch.bfloat16:
+        assert_close_bf16(outs[0][0], outs[0][1], f"cta-pair case {kind}", rel=2 ** -6, abs_=6e-3)
+    else:
+        assert (outs[0][0] - outs[0][1]).abs().max().item() <= 2e-2 * outs[0][1].abs().max().item()
+
+
 # ---------------------------------------------------------------------------------------------- attention
 @pytest.mark.parametrize("B,n,heads", [(2, 1024, 8), (1, 4096, 16), (1, 200, 4), (1, 128, 2), (3, 384, 6), (5, 1024, 16)])
 def test_flash_attention_d32(ops, gen, B, n, heads):
