@@ -48,6 +48,12 @@ static int encode_act_map(CUtensorMap* m, const void* ptr, int c, int ld, int W,
 
 // CTA-pair mode on by default?  (DAC_CTA2 overrides either way.)
 static const bool kCta2Default = true;
+// ... and for layers with resident non-pair weights (DAC_CTA2_RES=0 / 1 overrides)
+static const bool kCta2ResDefault = false;
+static bool cta2_res_on() {
+  const char* e = getenv("DAC_CTA2_RES");
+  return e ? atoi(e) != 0 : kCta2ResDefault;
+}
 
 extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
   if (!d || !out) return set_error(-1, "dac_conv_create: null argument");
@@ -165,6 +171,7 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
   k.n_tiles = d->cout_pad / d->block_n;
   k.ngroups = d->ngroups; k.ntaps = d->ntaps;
   k.fd_ntiles = make_fast_div(k.n_tiles); k.fd_mtiles = make_fast_div(k.m_tiles);
+  k.fd_mpairs = make_fast_div(k.m_tiles > 1 ? k.m_tiles / 2 : 1);
   k.fd_tx = make_fast_div(k.tiles_x); k.fd_ty = make_fast_div(k.tiles_y);
   k.chunks0 = d->c0 / kChunkK; k.chunks1 = d->c1 / kChunkK; k.c0 = d->c0;
   k.per_image_w = d->per_image_w;
@@ -223,17 +230,23 @@ extern "C" int dac_conv_create(const dac_conv_desc* d, dac_conv_t* out) {
   const char* cta2_env = getenv("DAC_CTA2");
   const bool cta2_on = cta2_env ? atoi(cta2_env) != 0 : kCta2Default;
   // (pixel-pair layers: only when the weight tensor carries the per-rank layouts, dac_conv_desc.pair == 2)
-  const bool cta2 = cta2_on && !(fused_res && getenv("DAC_NO_CTA2_SKIP")) && !d->per_image_w && d->ngroups == 1 && !nchw && d->epi != DAC_EPI_KVCTX &&
-                    d->epi != DAC_EPI_QKV && (k.m_tiles % 2) == 0 && (d->block_n % 32) == 0 && d->block_n >= 64 &&
-                    !d->stats_out &&
-                    (d->pair ? (d->pair == 2 && !getenv("DAC_NO_CTA2_PAIR")) : (!resident && !d->halo));
+  // (resident non-pair weights - haloed 3x3, parity-group upsample, stride-2 and 7-tap stem layers: each CTA keeps half of the
+  // rows of every weight tile; DAC_CTA2_RES=0 / 1 selects it)
+  const bool cta2 = cta2_on && !(fused_res && (getenv("DAC_NO_CTA2_SKIP") || resident)) && !d->per_image_w && !nchw &&
+                    d->epi != DAC_EPI_KVCTX && d->epi != DAC_EPI_QKV && (k.m_tiles % 2) == 0 && (d->block_n % 32) == 0 &&
+                    d->block_n >= 64 && !d->stats_out &&
+                    (d->pair ? (d->pair == 2 && !getenv("DAC_NO_CTA2_PAIR"))
+                             : (d->ngroups == 1 && !resident && !d->halo) || ((resident || d->halo) && cta2_res_on()));
   if (cta2) {
     ConvKernelFn kernel2 = pick_conv_kernel(d->epi, d->act, d->film != nullptr, nchw, f32_stream, true);
     if (kernel2) {
       kernel = kernel2;
       pl->kernel = kernel2;
       k.cta2 = 1;
-      if (!d->pair) k.b_bytes >>= 1;   // per CTA: half of the block_n weight rows of a K step
+      if (!d->pair) {
+        k.b_bytes >>= 1;               // per CTA: half of the block_n weight rows of a K step
+        k.b_res_bytes >>= 1;           // ... and of the resident weight tensor
+      }
       k.r_b_bytes >>= 1;               // ... and half of the fused skip conv's weight rows
     }
   }

@@ -56,6 +56,7 @@ struct ConvKParams {
   int tile_h, tile_w, tiles_x, tiles_y, m_tiles;
   int tile_w_shift;
   FastDiv fd_ntiles, fd_mtiles, fd_tx, fd_ty;
+  FastDiv fd_mpairs;       // CTA-pair mode: m_tiles / 2 (pairs of M tiles per parity group)
   int n_tiles, block_n, ngroups, ntaps;
   int chunks0, chunks1, c0;
   int per_image_w;
@@ -641,7 +642,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   const uint32_t crank = cta2 ? cluster_ctarank() : 0u;
   int tile_begin, tile_end;
   if (cta2) {
-    const long long total_pairs = static_cast<long long>(p.m_tiles >> 1) * p.n_tiles;
+    const long long total_pairs = static_cast<long long>(p.ngroups) * (p.m_tiles >> 1) * p.n_tiles;
     const int cl = blockIdx.x >> 1, ncl = gridDim.x >> 1;
     tile_begin = static_cast<int>(total_pairs * cl / ncl);
     tile_end = static_cast<int>(total_pairs * (cl + 1) / ncl);
@@ -650,8 +651,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   }
   auto tile_of = [&](int v) -> int {
     if (!cta2) return v;
-    const int mp = fast_div(v, p.fd_ntiles);
-    return (2 * mp + static_cast<int>(crank)) * p.n_tiles + (v - mp * p.n_tiles);
+    const int rest = fast_div(v, p.fd_ntiles);                    // (group, pair of M tiles), group-major like the tiles
+    const int g = p.ngroups == 1 ? 0 : fast_div(rest, p.fd_mpairs);
+    const int mp = rest - g * (p.m_tiles >> 1);
+    return (g * p.m_tiles + 2 * mp + static_cast<int>(crank)) * p.n_tiles + (v - rest * p.n_tiles);
   };
 
   if (warp == 0 && lane == 0) {
@@ -715,12 +718,25 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       uint32_t w_loads = 0;
       auto load_group_weights = [&](int g) {
         if (w_loads) mbar_wait(b_empty, (w_loads - 1) & 1);
+        if constexpr (cta2) {
+          // CTA-pair build: this CTA keeps its HALF of the rows of every weight tile; both CTAs' bytes complete on the leader's
+          // barrier (the leader's issuer is the only reader of b_full)
+          const uint32_t bfl = mapa_u32(smem_u32(b_full), 0);
+          if (crank == 0) mbar_arrive_expect_tx(b_full, 2u * p.b_res_bytes);
+          for (int nt = 0; nt < p.n_tiles; ++nt)
+            for (int ck = 0; ck < chunks; ++ck)
+              for (int jt = 0; jt < p.ntaps; ++jt)
+                tma_load_3d_pair(b_res + static_cast<size_t>((nt * chunks + ck) * p.ntaps + jt) * p.b_bytes, &mapW, bfl,
+                                 ck * kChunkK, nt * p.block_n + static_cast<int>(crank) * (p.block_n >> 1),
+                                 g * p.ntaps + p.col_tap[g][jt]);
+        } else {
         mbar_arrive_expect_tx(b_full, p.b_res_bytes);
         for (int nt = 0; nt < p.n_tiles; ++nt)
           for (int ck = 0; ck < chunks; ++ck)
             for (int jt = 0; jt < p.ntaps; ++jt)
               tma_load_3d(b_res + static_cast<size_t>((nt * chunks + ck) * p.ntaps + jt) * p.b_bytes, &mapW, b_full,
                           ck * kChunkK, nt * p.block_n, g * p.ntaps + p.col_tap[g][jt]);
+        }
         w_group = g;
         ++w_loads;
       };
@@ -747,7 +763,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           w_group = 0;
           ++w_loads;
         } else if (tile_begin < tile_end) {
-          load_group_weights(decode_tile(p, tile_begin).g);
+          load_group_weights(decode_tile(p, tile_of(tile_begin)).g);
         }
       }
       int stage = 0;
@@ -976,10 +992,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       uint32_t w_loads = 0;
       for (int tile = tile_begin; tile < tile_end; ++tile) {
         if (b_resident) {
-          const int g = p.ngroups == 1 ? 0 : fast_div(fast_div(tile, p.fd_ntiles), p.fd_mtiles);
+          const int g = p.ngroups == 1 ? 0 : fast_div(fast_div(tile, p.fd_ntiles), cta2 ? p.fd_mpairs : p.fd_mtiles);
           if (g != w_group) {               // (next) parity group: its weights replace the resident ones
             if (w_group >= 0) {
-              if (elect_one()) umma_commit(b_empty);
+              if (elect_one()) {
+                if constexpr (cta2) umma_commit_pair(b_empty);   // both CTAs' producers reload their halves
+                else umma_commit(b_empty);
+              }
               __syncwarp();
             }
             mbar_wait(b_full, w_loads & 1);

@@ -14,6 +14,7 @@ def rnd(*shape, scale=1.0):
 
 def make(case, cta2):
     os.environ["DAC_CTA2"] = "1" if cta2 else "0"
+    os.environ["DAC_CTA2_RES"] = "1" if cta2 else "0"
     kind, B, H, W, cin, cout = case
     x = CACHE.setdefault(("x", case), rnd(B, H, W, cin).to(torch.bfloat16))
     if kind == "1x1":
@@ -55,6 +56,22 @@ def make(case, cta2):
         else:
             plan = ops.ConvPlan(x, cin, ops.pack_conv(w), out, B=B, H=H, W=W, act=L.ACT_SILU, rsrc0=r0, rc0=cout, rsrc1=r1,
                                 rc1=rc - cout, rweight=ops.pack_linear(wr))
+    elif kind == "up":
+        w = CACHE.setdefault(("w", case), rnd(cout, cin, 3, 3, scale=(9 * cin) ** -0.5))
+        b = CACHE.setdefault(("b", case), rnd(cout))
+        out = torch.zeros(B, 2 * H, 2 * W, cout, device="cuda", dtype=torch.bfloat16)
+        plan = ops.ConvPlan(x, cin, ops.pack_upsample_conv(w), out, B=B, H=H, W=W, bias=b)
+    elif kind == "down":
+        w = CACHE.setdefault(("w", case), rnd(cout, cin, 4, 4, scale=(16 * cin) ** -0.5))
+        b = CACHE.setdefault(("b", case), rnd(cout))
+        out = torch.zeros(B, H // 2, W // 2, cout, device="cuda", dtype=torch.bfloat16)
+        plan = ops.ConvPlan(x, cin, ops.pack_conv(w, stride=2, pad=1), out, B=B, H=H, W=W, bias=b)
+    elif kind == "halo":
+        w = CACHE.setdefault(("w", case), rnd(cout, cin, 3, 3, scale=(9 * cin) ** -0.5))
+        film = CACHE.setdefault(("f", case), rnd(B, 2 * cout, scale=0.1))
+        out = torch.zeros(B, H, W, cout, device="cuda", dtype=torch.bfloat16)
+        os.environ["DAC_NO_PAIR"] = "1"
+        plan = ops.ConvPlan(x, cin, ops.pack_conv(w), out, B=B, H=H, W=W, act=L.ACT_SILU, film=film)
     elif kind == "geglu":
         w = CACHE.setdefault(("w", case), rnd(cout, cin, scale=cin ** -0.5))
         b = CACHE.setdefault(("b", case), rnd(cout))
@@ -90,6 +107,12 @@ CASES = {
     "p64l1": ("pair", 16, 128, 128, 64, 64),
     "p64small": ("pair", 2, 40, 24, 64, 64),
     "p64skip": ("pair_skip", 16, 256, 256, 64, 64),
+    "up128": ("up", 16, 128, 128, 128, 64),
+    "up512": ("up", 16, 32, 32, 512, 256),
+    "down64": ("down", 16, 256, 256, 64, 64),
+    "down128": ("down", 16, 64, 64, 128, 256),
+    "halo64": ("halo", 16, 128, 128, 64, 64),
+    "upsmall": ("up", 2, 20, 12, 128, 64),
     "skip128": ("skip", 16, 128, 128, 128, 128),
 }
 for name in (sys.argv[1:] or list(CASES)):
