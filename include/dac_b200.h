@@ -164,9 +164,18 @@ typedef struct dac_conv_desc {
                                                      is passed as its [B, H, W/2, 2C] view (W even; c0 / c1 / cout / block_n
                                                      = twice the real counts, 128), halo loads, weight = bf16
                                                      [3 ky][192 = kx 2,1,0 x 64 cout][cin], FiLM vectors of 64 entries;
-                                                     the centre taps run as N = 128 MMAs.  PLAIN epilogue only */
+                                                     the centre taps run as N = 128 MMAs.  PLAIN epilogue only.
+                                                     pair = 2: the weight tensor holds 9 blocks - the layout above followed
+                                                     by the two per-rank layouts of the CTA-pair build,
+                                                     [3 + 3 rank + ky][192 = E | O | S0 | S2][cin] with, for rank 0 / 1,
+                                                     E = W(kx=1) / W(0), O = W(2) / W(1), S0 = W(0)[32 rank, +32),
+                                                     S2 = W(2)[32 rank, +32) */
 } dac_conv_desc;
 
+/* CTA-pair mode (chosen by dac_conv_create, nothing to request): layers whose weights are streamed, pixel-pair layers
+ * (pair = 2) and layers with a fused skip conv run as 2-CTA clusters issuing tcgen05.mma.cta_group::2 (M = 256; every CTA
+ * loads its own activation tile and half of the weight rows) when the M-tile count is even; results are bit-identical to the
+ * 1-CTA build.  Environment: DAC_CTA2=0 disables it, DAC_CTA2_RES=1 extends it to resident non-pair weights. */
 typedef struct dac_conv_plan* dac_conv_t;
 int dac_conv_create(const dac_conv_desc* desc, dac_conv_t* plan);
 int dac_conv_launch(dac_conv_t plan, dac_stream_t stream);
