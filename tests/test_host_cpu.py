@@ -158,8 +158,9 @@ def test_pixel_pair_packing_semantics():
     for cin in (64, 128):
         x = bfr(torch.randn(B, cin, H, W, generator=g))
         w = bfr(torch.randn(64, cin, 3, 3, generator=g) * 0.05)
-        wp = ops.pack_conv_pair(w).float()                      # [3][192][cin]
-        assert wp.shape == (3, 192, cin)
+        wall = ops.pack_conv_pair(w).float()                    # [9][192][cin]: 1-CTA layout + the two per-rank layouts
+        assert wall.shape == (9, 192, cin)
+        wp = wall[:3]                                           # [3][192][cin]
         xp = F.pad(x.permute(0, 2, 3, 1), (0, 0, 2, 2, 1, 1))  # NHWC, two pixels = one pair of zero padding left and right
         out = torch.zeros(B, H, W // 2, 128)
         for s in range(cin // 64):
@@ -175,6 +176,22 @@ def test_pixel_pair_packing_semantics():
                 out[..., 64:] += even(1) @ blk[0:64].T          # N = 64: right neighbour of pixel 2i+1
         got = out.reshape(B, H, W, 64).permute(0, 3, 1, 2)      # the wide output IS the NHWC output
         assert torch.allclose(got, F.conv2d(x, w, padding=1), atol=1e-4)
+        # CTA-pair build (tcgen05.mma.cta_group::2): CTA r supplies the B rows of output columns [N/2 r, +N/2) from ITS block
+        # [E; O; S0; S2] (blocks 3 + 3 r + ky): N = 128 windows = [E_0; E_1] / [O_0; O_1], N = 64 windows = [S0_0; S0_1] /
+        # [S2_0; S2_1] - the same four products as above
+        out2 = torch.zeros(B, H, W // 2, 128)
+        for sidx in range(cin // 64):
+            sl = slice(64 * sidx, 64 * sidx + 64)
+            for ky in range(3):
+                r0, r1 = wall[3 + ky][:, sl], wall[6 + ky][:, sl]
+                rows = xp[:, ky:ky + H]
+                even = lambda d: rows[:, :, 2 + 2 * d:2 + 2 * d + W:2, sl]
+                odd = lambda d: rows[:, :, 3 + 2 * d:3 + 2 * d + W:2, sl]
+                out2 += even(0) @ torch.cat([r0[0:64], r1[0:64]]).T          # E: centre window of the even chunk
+                out2 += odd(0) @ torch.cat([r0[64:128], r1[64:128]]).T       # O: centre window of the odd chunk
+                out2[..., :64] += odd(-1) @ torch.cat([r0[128:160], r1[128:160]]).T   # S0 = W(kx=0): left neighbour of pixel 2i
+                out2[..., 64:] += even(1) @ torch.cat([r0[160:192], r1[160:192]]).T   # S2 = W(kx=2): right neighbour of 2i+1
+        assert torch.equal(out2, out)
     w3 = torch.randn(3, 64, 3, 3, generator=g)
     wp = ops.pack_conv_pair(F.pad(w3, (0, 0, 0, 0, 0, 0, 0, 13)))
     assert wp.shape == (3, 48, 64) and torch.equal(wp[1, 16:19].float(), bfr(w3[:, :, 1, 1]))
