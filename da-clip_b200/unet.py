@@ -906,8 +906,8 @@ class UNetEngine:
 
     @property
     def launches(self):
-        """Kernel launches of one evaluation (groupnorm is two kernels)."""
+        """Kernel launches of one evaluation (groupnorm, the fused PreNorm + GroupNorm and time_film are two kernels each)."""
         n = 0
         for name, _ in self.steps:
-            n += 2 if name.endswith(("groupnorm", "time_film")) else 1
+            n += 2 if name.endswith(("groupnorm", "prenorm_gn", "time_film")) else 1
         return n
