@@ -40,6 +40,7 @@ constexpr uint32_t kAvSlotCols = 192;        // TMEM per slot: S [0,128), O_blk 
 struct AttnVitParams {
   int items, q_tiles, kb, n, heads, causal;
   int packed, units;                         // packed mode: two (image, head) units per item; units = B * heads
+  uint32_t heads_mul, heads_s1, heads_s2;    // division by `heads` without the ~60-cycle IDIV sequence (round-up method)
   float scale_log2;                          // d^-0.5 * log2(e)
   __nv_bfloat16* out;
 };
@@ -89,12 +90,16 @@ attn_vit_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
   griddep_launch();
 
+  auto div_heads = [&](int v) -> int {
+    const uint32_t t = __umulhi(p.heads_mul, static_cast<uint32_t>(v));
+    return static_cast<int>((t + ((static_cast<uint32_t>(v) - t) >> p.heads_s1)) >> p.heads_s2);
+  };
   // item -> (image b, head h, query tile qt); tokens of image b are rows [b n, b n + n) of the qkv matrix
   auto decode = [&](int it, int& b, int& h, int& qt) {
     qt = it % p.q_tiles;
     const int r = it / p.q_tiles;
-    h = r % p.heads;
-    b = r / p.heads;
+    b = div_heads(r);
+    h = r - b * p.heads;
   };
 
   if (warp == 0) {
@@ -115,7 +120,7 @@ attn_vit_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constan
       for (int li = 0; li < n_items; ++li) {
         if (p.packed) {
           const int u0 = 2 * (begin + li), u1 = min(u0 + 1, p.units - 1);   // odd unit count: the last item repeats its unit
-          const int b0 = u0 / p.heads, h0 = u0 - b0 * p.heads, b1 = u1 / p.heads, h1 = u1 - b1 * p.heads;
+          const int b0 = div_heads(u0), h0 = u0 - b0 * p.heads, b1 = div_heads(u1), h1 = u1 - b1 * p.heads;
           for (int part = 0; part < 3; ++part)          // Q, K, V
             load((part * p.heads + h0) * 64, b0 * p.n, (part * p.heads + h1) * 64, b1 * p.n);
           continue;
@@ -210,7 +215,7 @@ attn_vit_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constan
         const int u = 2 * (begin + li) + (row >> 6);   // rows [0, 64): first unit of the item, [64, 128): second
         unit_ok = u < p.units;
         const int uc = min(u, p.units - 1);
-        b = uc / p.heads;
+        b = div_heads(uc);
         h = uc - b * p.heads;
         qt = 0;
         q = row & 63;
@@ -239,17 +244,23 @@ attn_vit_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constan
         tc_fence_after();
         // pass 1: row maximum over the valid keys
         float mx = -INFINITY;
+        const int hi_w = __reduce_min_sync(0xffffffffu, hi);          // columns below it are valid for every row of the warp
         for (int ck = ck_lo; ck < ck_hi; ++ck) {
           uint32_t r[32];
           tmem_ld32(lane_base + 32 * ck, r);
           tmem_ld_wait();
+          if (32 * ck + 32 <= hi_w) {                                  // whole chunk valid: no per-element masks
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (32 * ck + i < hi) mx = fmaxf(mx, __uint_as_float(r[i]));
+            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (32 * ck + i < hi) mx = fmaxf(mx, __uint_as_float(r[i]));
+          }
         }
         const float m_new = fmaxf(m_run, mx * c);
         const float m_use = m_new == -INFINITY ? 0.f : m_new;        // a row without any valid key (unused tile rows)
-        const float alpha = exp2f(m_run - m_use);                    // first block: exp2(-inf) = 0
+        const float alpha = j == 0 ? 0.f : ex2_approx(m_run - m_use);   // first block: nothing accumulated yet
         // pass 2: exponentials, row sum, bf16 P tile (zeros in the columns of the other unit)
         float l_blk = 0.f;
         for (int ck = 0; ck < chunks; ++ck) {
@@ -258,11 +269,19 @@ attn_vit_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constan
             uint32_t r[32];
             tmem_ld32(lane_base + 32 * ck, r);
             tmem_ld_wait();
+            if (32 * ck + 32 <= hi_w) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float e = ex2_approx(fmaf(__uint_as_float(r[i]), c, -m_use));
-              v[i] = (32 * ck + i < hi) ? e : 0.f;
-              l_blk += v[i];
+              for (int i = 0; i < 32; ++i) {
+                v[i] = ex2_approx(fmaf(__uint_as_float(r[i]), c, -m_use));
+                l_blk += v[i];
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const float e = ex2_approx(fmaf(__uint_as_float(r[i]), c, -m_use));
+                v[i] = (32 * ck + i < hi) ? e : 0.f;
+                l_blk += v[i];
+              }
             }
           } else {
 #pragma unroll
@@ -284,7 +303,8 @@ attn_vit_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constan
           tmem_ld32(lane_base + 128 + 32 * hc, r);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[32 * hc + i] = fmaf(o[32 * hc + i], alpha, __uint_as_float(r[i]));
+          for (int i = 0; i < 32; ++i)
+            o[32 * hc + i] = p.kb == 1 ? __uint_as_float(r[i]) : fmaf(o[32 * hc + i], alpha, __uint_as_float(r[i]));
         }
         tc_fence_before();
         mbar_arrive(&o_free[s]);
@@ -339,6 +359,13 @@ int dac_attention_vit(const void* qkv, void* out, int B, int n, int heads, int c
   k.items = packed ? (B * heads + 1) / 2 : B * heads * k.q_tiles;
   k.packed = packed;
   k.units = B * heads;
+  {
+    uint32_t l = 0;
+    while ((1ull << l) < static_cast<uint32_t>(heads)) ++l;
+    k.heads_mul = static_cast<uint32_t>(((1ull << 32) * ((1ull << l) - heads)) / heads + 1);
+    k.heads_s1 = l < 1 ? l : 1;
+    k.heads_s2 = l > 0 ? l - 1 : 0;
+  }
   k.n = n;
   k.heads = heads;
   k.causal = causal;
