@@ -49,7 +49,7 @@ static int encode_act_map(CUtensorMap* m, const void* ptr, int c, int ld, int W,
 // CTA-pair mode on by default?  (DAC_CTA2 overrides either way.)
 static const bool kCta2Default = true;
 // ... and for layers with resident non-pair weights (DAC_CTA2_RES=0 / 1 overrides)
-static const bool kCta2ResDefault = false;
+static const bool kCta2ResDefault = true;
 static bool cta2_res_on() {
   const char* e = getenv("DAC_CTA2_RES");
   return e ? atoi(e) != 0 : kCta2ResDefault;

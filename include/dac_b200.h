@@ -175,7 +175,7 @@ typedef struct dac_conv_desc {
 /* CTA-pair mode (chosen by dac_conv_create, nothing to request): layers whose weights are streamed, pixel-pair layers
  * (pair = 2) and layers with a fused skip conv run as 2-CTA clusters issuing tcgen05.mma.cta_group::2 (M = 256; every CTA
  * loads its own activation tile and half of the weight rows) when the M-tile count is even; results are bit-identical to the
- * 1-CTA build.  Environment: DAC_CTA2=0 disables it, DAC_CTA2_RES=1 extends it to resident non-pair weights. */
+ * 1-CTA build.  Environment: DAC_CTA2=0 disables it, DAC_CTA2_RES=0 keeps layers with resident non-pair weights on the 1-CTA build. */
 typedef struct dac_conv_plan* dac_conv_t;
 int dac_conv_create(const dac_conv_desc* desc, dac_conv_t* plan);
 int dac_conv_launch(dac_conv_t plan, dac_stream_t stream);
